@@ -1,0 +1,137 @@
+/* cp3b200.h - C ABI of libcp3b200.so, the B200-native drop-in for Coprocessor's subsumption /
+ * strengthening / BVE hot path (nmanthey/riss-solver).
+ *
+ * Two layers, both plain C (no torch / C++ types in any signature):
+ *
+ *  1. CP*   - the reference's own preprocessor C interface, coprocessor/libcoprocessorc.h:46-133, with the
+ *             same names, argument meaning and error behaviour (UNSAT is reported by CPok()==0, unknown
+ *             options are ignored unless `strict`).  A tool linked against the reference's libcp3 can be
+ *             re-linked against libcp3b200 unchanged.  Each declaration cites the line it replaces.
+ *  2. cp3g_* - the pass-level "scan service" the reference's C++ techniques bind to when they keep their
+ *             own host data structures (INTEGRATION.md shows the stub): upload the flattened clause arena,
+ *             then ask the GPU which (subsumer,candidate) / (strengthener,candidate,literal) pairs hit and
+ *             for per-variable resolvent counts and resolvents.  These replace the inner loops of
+ *             Subsumption::subsumption_worker (Subsumption.cc:244-297), strengthening_worker (:1276-1521),
+ *             BoundedVariableElimination::anticipateElimination (BVE.cc:695-880) and resolveSet (:892-1046).
+ *
+ * There is NO CPU fallback: every entry point that needs the device fails loudly (CP* abort with a message
+ * on stderr, cp3g_* return a negative error code) when no CUDA device is usable.
+ */
+#ifndef CP3B200_H
+#define CP3B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * Layer 1: libcoprocessorc.h drop-in
+ * ---------------------------------------------------------------------------------------------- */
+void* CPinit(const char* presetConfig);                         /* libcoprocessorc.h:49  */
+void  CPpreprocess(void* preprocessor);                         /* :52  */
+void  CPdestroy(void** preprocessor);                           /* :55  */
+void  CPparseOptions(void* preprocessor, int* argc, char** argv, int strict); /* :58 */
+void  CPparseOptionString(void* preprocessor, char* argv);      /* :59  */
+void  CPsetPresetConfig(void* preprocessor, const char* presetConfig);       /* :63 */
+void  CPaddLit(void* preprocessor, int lit);                    /* :66  */
+float CPversion(void* preprocessor);                            /* :69  */
+int   CPhasNextOutputLit(void* preprocessor);                   /* :72  */
+int   CPnextOutputLit(void* preprocessor);                      /* :75  */
+void  CPresetOutput(void* preprocessor);                        /* :78  */
+void  CPfreezeVariable(void* preprocessor, int variable);       /* :83  */
+int   CPgetReplaceLiteral(void* preprocessor, int oldLit);      /* :89  */
+void  CPresetModel(void* preprocessor);                         /* :97  */
+void  CPpushModelBool(void* preprocessor, int pol);             /* :102 */
+void  CPgiveModelLit(void* preprocessor, int literal);          /* :105 */
+void  CPpostprocessModel(void* preprocessor);                   /* :108 */
+int   CPgetFinalModelLit(void* preprocessor);                   /* :111 */
+int   CPmodelVariables(void* preprocessor);                     /* :114 */
+int   CPnVars(void* preprocessor);                              /* :120 */
+int   CPnClss(void* preprocessor);                              /* :123 */
+int   CPnLits(void* preprocessor);                              /* :126 */
+int   CPok(void* preprocessor);                                 /* :129 */
+int   CPlitFalsified(void* preprocessor, int lit);              /* :132 */
+
+/* Bulk extensions (not in the reference header; same semantics as the per-literal calls above). */
+/* CPaddLit for a whole 0-terminated DIMACS stream */
+void   CPaddLits(void* preprocessor, const int32_t* stream, size_t n);
+/* CPresetOutput + CPnextOutputLit until exhausted; returns the int32 count needed, writes up to cap */
+size_t CPgetOutput(void* preprocessor, int32_t* out, size_t cap);
+/* number of leading unit clauses (trail) in that stream */
+size_t CPoutputUnits(void* preprocessor);
+/* extension (undo) stack as DIMACS literals, 0 separates entries (CoprocessorTypes.h:1615-1655) */
+size_t CPgetUndo(void* preprocessor, int32_t* out, size_t cap);
+/* technique counters by name: the `[STAT] SuSi` / `BVE` fields of Subsumption.cc:38-49, BVE.cc:75-108
+ * ("sub_subsSteps", "sub_strengthSteps", "sub_subsumedClauses", "bve_eliminatedVars", ...) plus GPU-side
+ * counters ("gpu_launches", "gpu_scan_requests", "gpu_h2d_bytes", "gpu_d2h_bytes", "gpu_kernel_ns") */
+int64_t CPstat(void* preprocessor, const char* name);
+/* multi-GPU: shard the scan requests of this instance over `world` ranks (rank-local GPU each);
+ * `nccl_unique_id` is the 128-byte ncclUniqueId created by rank 0 (cp3g_nccl_unique_id) */
+int    CPsetDistributed(void* preprocessor, int rank, int world, const void* nccl_unique_id);
+
+/* ------------------------------------------------------------------------------------------------
+ * Layer 2: pass-level GPU scan service
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct cp3g cp3g;
+
+/* literal code = Riss::toInt(Lit) = 2*var + sign (riss/core/SolverTypes.h:65-98); clauses are sorted by
+ * that code (Coprocessor.cc:1447-1463).  Clause index = position in the uploaded table. */
+typedef struct { uint32_t req; uint32_t clause; int32_t lit; } cp3g_hit;
+
+enum { CP3G_SUBSUME = 0, CP3G_STRENGTHEN = 1 };
+enum { CP3G_OK = 0, CP3G_ERR_NODEVICE = -1, CP3G_ERR_CUDA = -2, CP3G_ERR_OVERFLOW = -3, CP3G_ERR_ARG = -4 };
+
+int  cp3g_device_count(void);
+cp3g* cp3g_create(int device);                 /* NULL when the device cannot be used */
+void  cp3g_destroy(cp3g* g);
+const char* cp3g_last_error(const cp3g* g);
+
+/* Upload the flattened clause table (replaces walking ClauseAllocator memory, SolverTypes.h:638-699):
+ * lits = literal pool, start[i]/size[i] = clause i, flags bit0 = deleted (Clause::mark()). */
+int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t nclauses, const int32_t* lits, size_t nlits,
+                const uint32_t* start, const uint32_t* size, const uint8_t* flags);
+/* K1 sig_build + K2 occ_build: 64-bit clause signatures and the per-literal CSR occurrence lists in
+ * ascending clause order (CoprocessorData::addClause order, CoprocessorTypes.h:812-833). */
+int cp3g_build(cp3g* g);
+/* copy the CSR back: off[2*nvars+1], refs[off[2*nvars]] (pass NULL refs to query sizes only) */
+int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs);
+/* incremental maintenance between scans */
+int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* clauses);
+int cp3g_shrink(cp3g* g, uint32_t n, const uint32_t* clauses, const uint32_t* new_start,
+                const uint32_t* new_size, const int32_t* lits, size_t nlits);   /* rewritten literals */
+int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, size_t nlits);
+
+/* K3/K4: one request = one subsumer / strengthener given by its literals (req_off[i]..req_off[i+1] in
+ * req_lits) and the clause index to skip (self, UINT32_MAX for none).  With req_lits == NULL the device's
+ * own copy of clause self[i] is used.  Hits are appended unordered to `out`:
+ *   CP3G_SUBSUME:    (req, D, -1)  for every live D != self with request ⊆ D
+ *   CP3G_STRENGTHEN: (req, D, l)   for every live D where exactly the literal l of D is the complement of a
+ *                                  request literal and the rest of the request is contained in D
+ * rank/world partition the requests (contiguous ranges balanced by list length) for the multi-GPU path. */
+int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint32_t* req_off,
+              const int32_t* req_lits, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks);
+
+/* K5: resolvent anticipation for candidate variables.  Variable i owns pos refs p_off[i]..p_off[i+1] and
+ * neg refs n_off[i]..n_off[i+1] (host list order).  sizes[pair_off[i] + a*nneg + b] = number of literals
+ * of the resolvent of pos a and neg b on vars[i], -1 for a tautology (BVE.h:248-299), -2 when a parent is
+ * already deleted. */
+int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
+                   const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* pair_off, int16_t* sizes);
+/* K6: materialise the resolvents of the listed (var, pos clause, neg clause) triples into out_lits;
+ * out_off[k] is given by the caller as the prefix sum of the sizes K5 reported (BVE.h:208-242). */
+int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs,
+                     const uint32_t* n_refs, const uint64_t* out_off, int32_t* out_lits, size_t nlits);
+
+/* multi-GPU plumbing: NCCL communicator over the ranks' devices (bootstrap id from rank 0) */
+int cp3g_nccl_unique_id(void* out128);
+int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);
+
+/* counters: "launches", "kernel_ns", "h2d_bytes", "d2h_bytes", "scan_requests", "scan_checks" */
+int64_t cp3g_counter(const cp3g* g, const char* name);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

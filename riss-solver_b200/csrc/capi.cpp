@@ -1,0 +1,118 @@
+// capi.cpp - the libcoprocessorc.h drop-in layer (CP*) on top of the ordered-commit engine.
+// Mirrors coprocessor/libcoprocessorc.cc: an opaque handle owns everything; no error codes, UNSAT is
+// CPok()==0; unknown options are ignored unless `strict`.
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+#include "engine.h"
+
+namespace {
+struct Handle {                         // struct libcp3, libcoprocessorc.cc:12-24
+    cp3::Engine eng;
+    std::vector<int32_t> out; size_t outPos = 0; bool outReady = false;
+    std::vector<uint8_t> model; size_t modelLit = 0;
+};
+inline Handle* H(void* p) { return (Handle*)p; }
+void applyOption(Handle* h, const char* o, bool strict)
+{
+    int r = h->eng.opt.parse(o);
+    if (r < 0) {
+        fprintf(stderr, "cp3b200: option %s selects a reference code path the GPU drop-in does not provide\n", o);
+        if (strict) { exit(1); }
+    } else if (r == 0 && strict) {
+        fprintf(stderr, "ERROR! Unknown flag \"%s\"\n", o);       // riss/utils/Config.h:816-822
+        exit(1);
+    }
+}
+void ensureOutput(Handle* h)
+{
+    if (h->outReady) { return; }
+    size_t n = h->eng.output(nullptr, 0);
+    h->out.resize(n);
+    h->eng.output(h->out.data(), n);
+    h->outPos = 0; h->outReady = true;
+}
+}
+
+extern "C" {
+
+void* CPinit(const char* presetConfig)
+{
+    Handle* h = new Handle();
+    if (presetConfig) { h->eng.opt.preset(presetConfig); }
+    return h;
+}
+void CPdestroy(void** p) { if (p && *p) { delete H(*p); *p = nullptr; } }
+void CPpreprocess(void* p) { H(p)->eng.preprocess(); H(p)->outReady = false; }
+
+void CPparseOptions(void* p, int* argc, char** argv, int strict)
+{
+    // like Config::parseOptions (riss/utils/Config.h:779-826): argv[0] is the program name; recognised
+    // options are consumed, the rest stays in argv
+    int j = 1;
+    for (int i = 1; i < *argc; ++i) {
+        int r = H(p)->eng.opt.parse(argv[i]);
+        if (r == 0) { if (strict && argv[i][0] == '-') { fprintf(stderr, "ERROR! Unknown flag \"%s\"\n", argv[i]); exit(1); } argv[j++] = argv[i]; }
+        else if (r < 0) { applyOption(H(p), argv[i], strict != 0); }
+    }
+    *argc = j;
+}
+void CPparseOptionString(void* p, char* s)
+{
+    std::istringstream is(s ? s : "");
+    std::string tok;
+    while (is >> tok) { applyOption(H(p), tok.c_str(), false); }
+}
+void CPsetPresetConfig(void* p, const char* preset) { H(p)->eng.opt.preset(preset); }
+void CPaddLit(void* p, int lit) { H(p)->eng.addLit(lit); H(p)->outReady = false; }
+void CPaddLits(void* p, const int32_t* s, size_t n) { H(p)->eng.addStream(s, n); H(p)->outReady = false; }
+float CPversion(void*) { return 7.1f; }
+
+int CPhasNextOutputLit(void* p) { ensureOutput(H(p)); return H(p)->outPos < H(p)->out.size() ? 1 : 0; }
+int CPnextOutputLit(void* p)
+{
+    Handle* h = H(p); ensureOutput(h);
+    if (h->outPos >= h->out.size()) { return 0; }
+    return h->out[h->outPos++];
+}
+void CPresetOutput(void* p) { H(p)->outReady = false; ensureOutput(H(p)); }
+size_t CPgetOutput(void* p, int32_t* out, size_t cap) { return H(p)->eng.output(out, cap); }
+size_t CPoutputUnits(void* p) { return H(p)->eng.nTrail(); }
+size_t CPgetUndo(void* p, int32_t* out, size_t cap) { return H(p)->eng.undoStack(out, cap); }
+int64_t CPstat(void* p, const char* name) { return H(p)->eng.stat(name); }
+int CPsetDistributed(void* p, int rank, int world, const void* id) { return H(p)->eng.setDistributed(rank, world, id); }
+
+void CPfreezeVariable(void* p, int variable) { H(p)->eng.freeze(variable < 0 ? -variable : variable); }
+int CPgetReplaceLiteral(void*, int oldLit) { return oldLit; }    // no Dense / EE on this path: identity
+
+void CPresetModel(void* p) { H(p)->model.clear(); H(p)->modelLit = 0; }
+void CPpushModelBool(void* p, int pol) { H(p)->model.push_back(pol == 0 ? cp3::L_FALSE : cp3::L_TRUE); }
+void CPgiveModelLit(void* p, int literal)
+{
+    Handle* h = H(p);
+    size_t v = (size_t)(literal < 0 ? -literal : literal) - 1;
+    while (h->model.size() <= v) { h->model.push_back(cp3::L_UNDEF); }
+    h->model[v] = literal > 0 ? cp3::L_TRUE : cp3::L_FALSE;
+}
+void CPpostprocessModel(void* p) { H(p)->eng.extendModel(H(p)->model); }
+int CPgetFinalModelLit(void* p)
+{
+    Handle* h = H(p);
+    if (h->modelLit < h->model.size()) {
+        int v = (int)h->modelLit++;
+        return h->model[v] == cp3::L_TRUE ? v + 1 : -v - 1;
+    }
+    return 0;
+}
+int CPmodelVariables(void* p) { return (int)H(p)->model.size(); }
+int CPnVars(void* p) { return H(p)->eng.nVars(); }
+int CPnClss(void* p) { return (int)(H(p)->eng.nLiveClauses() + H(p)->eng.nTrail()); }
+int CPnLits(void* p) { return (int)(H(p)->eng.nLiveLits() + H(p)->eng.nTrail()); }
+int CPok(void* p) { return H(p)->eng.okay() ? 1 : 0; }
+int CPlitFalsified(void* p, int lit) { return H(p)->eng.litValue(lit) == cp3::L_FALSE ? 1 : 0; }
+
+} // extern "C"

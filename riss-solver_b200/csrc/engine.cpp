@@ -1,0 +1,1353 @@
+// engine.cpp - ordered-commit host engine (see engine.h).  Reference lines are cited per function.
+#include "engine.h"
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace cp3 {
+
+static inline int64_t now_ns()
+{
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ------------------------------------------------------------------------------------------------ options
+int Options::parse(const char* o)
+{
+    if (!o || o[0] != '-') { return 0; }
+    const char* s = o + 1;
+    bool neg = false;
+    if (!strncmp(s, "no-", 3)) { neg = true; s += 3; }
+    const char* eq = strchr(s, '=');
+    std::string name = eq ? std::string(s, eq - s) : std::string(s);
+    long long val = eq ? atoll(eq + 1) : 0;
+#define BOPT(n, f) if (name == n) { f = !neg; return 1; }
+#define IOPT(n, f) if (name == n && eq) { f = val; return 1; }
+    BOPT("enabled_cp3", enabled) BOPT("up", up) BOPT("subsimp", subsimp) BOPT("bve", bve)
+    BOPT("cp3_limited", limited) BOPT("cp3_strength", strength) BOPT("cp3_stats", stats)
+    BOPT("bve_unlimited", bve_unlimited) BOPT("bve_strength", bve_strength) BOPT("bve_gates", bve_gates)
+    BOPT("bve_force_gates", bve_force_gates) BOPT("bve_fdepOnly", bve_fdepOnly) BOPT("bve_BCElim", bve_BCElim)
+    BOPT("bve_early", bve_early) BOPT("bce_only", bce_only)
+    IOPT("cp3_iters", iters) IOPT("cp3_vars", cp3_vars) IOPT("cp3_cls", cp3_cls) IOPT("cp3_lits", cp3_lits)
+    IOPT("cp3_sub_limit", sub_limit) IOPT("cp3_str_limit", str_limit) IOPT("cp3_call_inc", call_inc)
+    IOPT("cp3_bve_limit", bve_limit) IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t)
+    IOPT("bve_heap_updates", bve_heap_updates) IOPT("cp3_gpu_device", device)
+    if (name == "cp3_bve_heap" && eq) { if (val != 0 && val != 1) { return -1; } bve_heap = (int)val; return 1; }
+    // options of the path whose non-default values select code the GPU path does not provide
+    if (name == "cp3_threads" && eq) { threads = (int)val; return 1; }      // pthread pool is replaced by the GPU
+    if (name == "naive_strength") { return neg ? 1 : -1; }
+    if (name == "all_strength_res" && eq) { return val == 0 ? 1 : -1; }
+    if (name == "cp3_inpPrefL" || name == "cp3_lock_stats" || name == "bve_progress" || name == "bve_totalG") { return 1; }
+    if ((name == "cp3_par_strength" || name == "cp3_par_subs" || name == "par_subs_counts" || name == "susi_chunk_size" ||
+         name == "par_str_minCls" || name == "cp3_par_bve" || name == "par_bve_th" || name == "postp_lockd_neighb" ||
+         name == "cp3_sub_inpInc" || name == "cp3_bve_inpInc" || name == "cp3_bve_verbose" || name == "cp3_bve_learnt_growth" ||
+         name == "cp3_bve_resolve_learnts" || name == "cp3_verbose" || name == "cp3_susi_vars" || name == "cp3_susi_cls" ||
+         name == "cp3_susi_lits" || name == "cp3_bve_vars" || name == "cp3_bve_cls" || name == "cp3_bve_lits") && eq) { return 1; }
+    if (name == "par_bve_min_upd" || name == "dense" || name == "inprocess") { return neg ? 1 : -1; }
+#undef BOPT
+#undef IOPT
+    return 0;
+}
+
+// the presets of riss/utils/Config.h that only touch this path (plain_SUSI :377, plain_BVE :381)
+void Options::preset(const char* name)
+{
+    if (!name) { return; }
+    std::string n(name);
+    size_t pos = 0;
+    while (pos <= n.size()) {
+        size_t c = n.find(':', pos);
+        std::string one = n.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
+        if (one == "plain_SUSI") { enabled = true; subsimp = true; }
+        else if (one == "plain_BVE") { enabled = true; bve = true; }
+        else if (one == "plain_UP") { enabled = true; up = true; }
+        if (c == std::string::npos) { break; }
+        pos = c + 1;
+    }
+}
+
+void Engine::ScanCache::clear() { std::fill(slot.begin(), slot.end(), -1); ent.clear(); hits.clear(); }
+
+Engine::Engine() { sub_lim = opt.sub_limit; str_lim = opt.str_limit; }
+Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
+
+void Engine::die(const char* msg) const
+{
+    fprintf(stderr, "cp3b200: fatal: %s%s%s\n", msg, gpu ? " - " : "", gpu ? cp3g_last_error(gpu) : "");
+    abort();
+}
+
+// ------------------------------------------------------------------------------------------------ solver side
+void Engine::newVar()
+{
+    assigns.push_back(L_UNDEF); frozen.push_back(0);
+    if (ing_built) { ing_occ.emplace_back(); ing_occ.emplace_back(); }
+    ++nvars;
+}
+
+uint32_t Engine::allocClause(const int* lits, int n)
+{
+    uint32_t c = (uint32_t)cstart.size();
+    cstart.push_back((uint32_t)pool.size()); csize.push_back((uint32_t)n);
+    cflag.push_back(F_SUB | F_STR);                 // fresh clause: can_subsume, can_strengthen
+    pool.insert(pool.end(), lits, lits + n);
+    ca_size += 2 + n;                               // ClauseAllocator::clauseWord32Size, SolverTypes.h:641-644
+    mod_stamp.push_back(scan_id); ver.push_back(0);
+    return c;
+}
+
+void Engine::uncheckedEnqueue(int x) { assigns[x >> 1] = (uint8_t)(x & 1); trail.push_back(x); }
+
+// CoprocessorData::enqueue, CoprocessorTypes.h:767-783
+int Engine::dataEnqueue(int x)
+{
+    int v = value(x);
+    if (v == L_FALSE) { ok = false; return L_FALSE; }
+    if (v == L_UNDEF) { uncheckedEnqueue(x); return L_TRUE; }
+    return L_UNDEF;
+}
+
+// level-0 propagation while clauses are added (stand-in for Solver::propagate over watches; the implied
+// literal set is the same, the trail order of implied literals may differ - DESIGN.md "input units")
+bool Engine::ingestPropagate()
+{
+    if (!ing_built) {
+        ing_occ.assign(2 * (size_t)nvars, {});
+        ing_built = true;
+        for (uint32_t c : clauses) { for (uint32_t k = 0; k < csize[c]; ++k) { ing_occ[CL(c)[k]].push_back(c); } }
+    }
+    while (qhead < (int)trail.size()) {
+        int p = trail[qhead++];
+        const std::vector<uint32_t>& ws = ing_occ[lneg(p)];
+        for (size_t i = 0; i < ws.size(); ++i) {
+            uint32_t c = ws[i]; const int32_t* l = CL(c);
+            int un = -1, nun = 0; bool sat = false;
+            for (uint32_t k = 0; k < csize[c]; ++k) {
+                int v = value(l[k]);
+                if (v == L_TRUE) { sat = true; break; }
+                if (v == L_UNDEF) { un = l[k]; ++nun; }
+            }
+            if (sat) { continue; }
+            if (nun == 0) { return false; }
+            if (nun == 1) { uncheckedEnqueue(un); }
+        }
+    }
+    return true;
+}
+
+// Solver::addClause_, riss/core/Solver.cc:409-499
+void Engine::addClauseIngest(std::vector<int>& ps)
+{
+    if (!ok) { return; }
+    std::sort(ps.begin(), ps.end());
+    int j = 0, p = -2;
+    for (size_t i = 0; i < ps.size(); ++i) {
+        int v = value(ps[i]);
+        if (v == L_TRUE || ps[i] == lneg(p)) { return; }
+        if (v != L_FALSE && ps[i] != p) { ps[j++] = p = ps[i]; }
+    }
+    if (j == 0) { ok = false; return; }
+    if (j == 1) { uncheckedEnqueue(ps[0]); ok = ingestPropagate(); return; }
+    uint32_t c = allocClause(ps.data(), j);
+    clauses.push_back(c);
+    if (ing_built) { for (int i = 0; i < j; ++i) { ing_occ[ps[i]].push_back(c); } }
+}
+
+void Engine::addLit(int x)
+{
+    if (x == 0) { addClauseIngest(cur); cur.clear(); return; }
+    int v = x < 0 ? -x : x;
+    while (nvars < v) { newVar(); }
+    cur.push_back(2 * (v - 1) + (x < 0));
+}
+void Engine::addStream(const int32_t* s, size_t n) { for (size_t i = 0; i < n; ++i) { addLit(s[i]); } }
+void Engine::freeze(int dv) { while (nvars < dv) { newVar(); } frozen[dv - 1] = 1; }
+int Engine::litValue(int d) const
+{
+    int v = d < 0 ? -d : d;
+    if (v > nvars) { return L_UNDEF; }
+    return value(2 * (v - 1) + (d < 0));
+}
+
+// Solver::simplify at level 0, riss/core/Solver.cc:2212-2268
+bool Engine::solverSimplify()
+{
+    if (!ok) { return false; }
+    if (qhead < (int)trail.size() && !ingestPropagate()) { ok = false; return false; }
+    if ((int)trail.size() == simpDB_assigns || simpDB_props > 0) { return true; }
+    size_t j = 0; int64_t lits = 0;
+    for (size_t i = 0; i < clauses.size(); ++i) {
+        uint32_t c = clauses[i]; const int32_t* l = CL(c); bool sat = false;
+        for (uint32_t k = 0; k < csize[c]; ++k) { if (value(l[k]) == L_TRUE) { sat = true; break; } }
+        if (sat) { caFree(c); cflag[c] |= F_DEL; }
+        else { clauses[j++] = c; lits += csize[c]; }
+    }
+    clauses.resize(j);
+    if (ca_wasted > ca_size * opt.gc_frac) { ca_size -= ca_wasted; ca_wasted = 0; }
+    simpDB_assigns = (int)trail.size(); simpDB_props = lits;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ device
+void Engine::ensureGpu()
+{
+    if (gpu) { return; }
+    gpu = cp3g_create(opt.device);
+    if (!gpu) { die("no CUDA device for the Coprocessor GPU path (there is no CPU fallback)"); }
+}
+
+int Engine::setDistributed(int rank, int world, const void* id)
+{
+    ensureGpu();
+    return cp3g_nccl_init(gpu, rank, world, id);
+}
+
+// upload the flattened arena and let the GPU build signatures + occurrence CSR (K1, K2)
+void Engine::uploadAll()
+{
+    ensureGpu();
+    const uint32_t ncl = (uint32_t)cstart.size();
+    std::vector<uint8_t> fl(ncl);
+    for (uint32_t c = 0; c < ncl; ++c) { fl[c] = (cflag[c] & F_DEL) ? 1 : 0; }
+    int64_t t0 = now_ns();
+    if (cp3g_upload(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), cstart.data(), csize.data(), fl.data()) != CP3G_OK) { die("upload failed"); }
+    if (cp3g_build(gpu) != CP3G_OK) { die("occurrence build failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    dev_ncl = ncl; dev_uploaded = true;
+    pend_del.clear(); pend_shrunk.clear();
+    shrunk_mark.assign(ncl, 0);
+}
+
+// push the edits committed since the last scan (new resolvents, shrunk clauses, deletions)
+void Engine::flushDevice()
+{
+    const uint32_t ncl = (uint32_t)cstart.size();
+    int64_t t0 = now_ns();
+    const uint32_t old_ncl = dev_ncl;
+    if (ncl > dev_ncl) {
+        std::vector<uint32_t> sz; std::vector<int32_t> li;
+        for (uint32_t c = dev_ncl; c < ncl; ++c) {
+            sz.push_back(csize[c]);
+            li.insert(li.end(), CL(c), CL(c) + csize[c]);
+            if (cflag[c] & F_DEL) { pend_del.push_back(c); }
+        }
+        if (cp3g_append(gpu, ncl - dev_ncl, sz.data(), li.data(), li.size()) != CP3G_OK) { die("append failed"); }
+        dev_ncl = ncl;
+        shrunk_mark.resize(ncl, 0);
+    }
+    if (!pend_shrunk.empty()) {
+        std::vector<uint32_t> ids, st, sz; std::vector<int32_t> li;
+        for (uint32_t c : pend_shrunk) {
+            shrunk_mark[c] = 0;
+            if (c >= old_ncl) { continue; }          // appended above with its current content
+            ids.push_back(c); st.push_back((uint32_t)li.size()); sz.push_back(csize[c]);
+            li.insert(li.end(), CL(c), CL(c) + csize[c]);
+        }
+        pend_shrunk.clear();
+        if (!ids.empty() && cp3g_shrink(gpu, (uint32_t)ids.size(), ids.data(), st.data(), sz.data(), li.data(), li.size()) != CP3G_OK) { die("shrink failed"); }
+    }
+    if (!pend_del.empty()) {
+        if (cp3g_set_deleted(gpu, (uint32_t)pend_del.size(), pend_del.data()) != CP3G_OK) { die("set_deleted failed"); }
+        pend_del.clear();
+    }
+    host_ns_gpuwait += now_ns() - t0;
+}
+
+// One GPU scan over the clauses `ids`; results land in `cache` keyed by clause and content version.
+void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache)
+{
+    if (ids.empty()) { return; }
+    flushDevice();
+    ++scan_id; ++n_scan_batches;
+    if (cache.slot.size() < cstart.size()) { cache.slot.resize(cstart.size(), -1); }
+    // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
+    std::vector<uint32_t> live, dead;
+    for (uint32_t c : ids) { ((cflag[c] & F_DEL) ? dead : live).push_back(c); }
+    int64_t t0 = now_ns();
+    for (int part = 0; part < 2; ++part) {
+        const std::vector<uint32_t>& v = part == 0 ? live : dead;
+        if (v.empty()) { continue; }
+        std::vector<uint32_t> roff; std::vector<int32_t> rl;
+        if (part == 1) {
+            roff.push_back(0);
+            for (uint32_t c : v) { rl.insert(rl.end(), CL(c), CL(c) + csize[c]); roff.push_back((uint32_t)rl.size()); }
+        }
+        uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, v.size() / 8));
+        uint32_t n = 0; uint64_t chk = 0;
+        for (;;) {
+            hitbuf.resize(cap);
+            int r = cp3g_scan(gpu, kind, (uint32_t)v.size(), v.data(), part ? roff.data() : nullptr, part ? rl.data() : nullptr,
+                              hitbuf.data(), cap, &n, &chk);
+            if (r == CP3G_OK) { break; }
+            if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
+            die("scan failed");
+        }
+        std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
+            return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+        uint32_t h = 0;
+        for (uint32_t i = 0; i < v.size(); ++i) {
+            CacheEnt e; e.ver = ver[v[i]]; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
+            while (h < n && hitbuf[h].req == i) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
+            e.he = (uint32_t)cache.hits.size();
+            cache.slot[v[i]] = (int32_t)cache.ent.size();
+            cache.ent.push_back(e);
+        }
+    }
+    host_ns_gpuwait += now_ns() - t0;
+}
+
+const Engine::CacheEnt* Engine::cached(ScanCache& cache, uint32_t c) const
+{
+    if (c >= cache.slot.size() || cache.slot[c] < 0) { return nullptr; }
+    const CacheEnt* e = &cache.ent[cache.slot[c]];
+    return e->ver == ver[c] ? e : nullptr;
+}
+
+static inline bool containsLit(const int32_t* l, uint32_t n, int x)
+{
+    return std::binary_search(l, l + n, x);
+}
+
+// A snapshot hit "C subsumes D" stays true unless D lost a literal of C afterwards.
+bool Engine::subHitValid(uint32_t c, uint32_t d, uint32_t scan) const
+{
+    if (mod_stamp[d] < scan) { return true; }
+    auto it = edit_log.find(d);
+    if (it == edit_log.end()) { return true; }
+    for (const Removal& r : it->second) { if (r.stamp >= scan && containsLit(CL(c), csize[c], r.lit)) { return false; } }
+    return true;
+}
+// A snapshot hit "S strengthens D on literal f" stays true unless D lost f or a literal of S afterwards.
+bool Engine::strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const
+{
+    if (mod_stamp[d] < scan) { return true; }
+    auto it = edit_log.find(d);
+    if (it == edit_log.end()) { return true; }
+    for (const Removal& r : it->second) {
+        if (r.stamp < scan) { continue; }
+        if (r.lit == f || containsLit(CL(s), csize[s], r.lit)) { return false; }
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------ occ lists
+void Engine::occPush(int x, uint32_t c)
+{
+    OccList& l = occ[x];
+    if (l.n == l.cap) {
+        uint32_t ncap = l.cap ? l.cap * 2 : 4;
+        uint32_t noff = (uint32_t)occ_pool.size();
+        occ_pool.resize(occ_pool.size() + ncap);
+        if (l.n) { memcpy(occ_pool.data() + noff, occ_pool.data() + l.off, sizeof(uint32_t) * l.n); }
+        l.off = noff; l.cap = ncap;
+    }
+    occ_pool[l.off + l.n++] = c;
+}
+void Engine::occSwapRemove(int x, uint32_t i)
+{
+    OccList& l = occ[x]; uint32_t* p = LP(l);
+    if ((cflag[p[i]] & F_DEL) && stale[x] > 0) { --stale[x]; }
+    p[i] = p[l.n - 1]; l.n--;
+}
+void Engine::occRelease(int x) { occ[x].n = 0; stale[x] = 0; }
+
+void Engine::touchClauseVars(uint32_t c)
+{
+    const int32_t* l = CL(c);
+    for (uint32_t k = 0; k < csize[c]; ++k) { ++var_touch[l[k] >> 1]; }
+}
+
+void Engine::setDeleted(uint32_t c)
+{
+    if (cflag[c] & F_DEL) { return; }
+    cflag[c] |= F_DEL;
+    const int32_t* l = CL(c);
+    for (uint32_t k = 0; k < csize[c]; ++k) { ++stale[l[k]]; ++var_touch[l[k] >> 1]; }
+    // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
+    if (!pend_rm.empty()) {
+        auto it = pend_rm.find(c);
+        if (it != pend_rm.end()) { for (int l2 : it->second) { ++stale[l2]; } }
+    }
+    if (dev_uploaded) { pend_del.push_back(c); }
+}
+
+void Engine::noteShrunk(uint32_t c, int removedLit)
+{
+    ++ver[c]; mod_stamp[c] = scan_id;
+    edit_log[c].push_back({scan_id, removedLit});
+    if (dev_uploaded && c < shrunk_mark.size() && !shrunk_mark[c]) { shrunk_mark[c] = 1; pend_shrunk.push_back(c); }
+    else if (dev_uploaded && c >= shrunk_mark.size()) { /* not yet on the device: appended with current content */ }
+    touchClauseVars(c); ++var_touch[removedLit >> 1];
+}
+
+void Engine::removePosSorted(uint32_t c, int pos)
+{
+    int32_t* l = CL(c); uint32_t n = csize[c];
+    for (uint32_t j = (uint32_t)pos; j + 1 < n; ++j) { l[j] = l[j + 1]; }
+    csize[c] = n - 1;
+}
+void Engine::removePosUnsorted(uint32_t c, int pos)
+{
+    int32_t* l = CL(c); uint32_t n = csize[c];
+    l[pos] = l[n - 1]; csize[c] = n - 1;
+}
+
+// ------------------------------------------------------------------------------------------------ heap (riss/mtl/Heap.h:37-183)
+void Engine::heapUp(int i)
+{
+    int x = heap[i], p = (i - 1) >> 1;
+    while (i != 0 && heapLt(x, heap[p])) { heap[i] = heap[p]; hidx[heap[p]] = i; i = p; p = (p - 1) >> 1; }
+    heap[i] = x; hidx[x] = i;
+}
+void Engine::heapDown(int i)
+{
+    int x = heap[i]; const int n = (int)heap.size();
+    while (2 * i + 1 < n) {
+        int l = 2 * i + 1, r = 2 * i + 2;
+        int child = (r < n && heapLt(heap[r], heap[l])) ? r : l;
+        if (!heapLt(heap[child], x)) { break; }
+        heap[i] = heap[child]; hidx[heap[i]] = i; i = child;
+    }
+    heap[i] = x; hidx[x] = i;
+}
+void Engine::heapInsert(int v)
+{
+    if (v >= (int)hidx.size()) { hidx.resize(v + 1, -1); }
+    hidx[v] = (int)heap.size(); heap.push_back(v);
+    heapUp(hidx[v]);
+}
+void Engine::heapUpdate(int v) { if (!inHeap(v)) { heapInsert(v); } else { heapUp(hidx[v]); heapDown(hidx[v]); } }
+int Engine::heapRemoveMin()
+{
+    int x = heap[0];
+    heap[0] = heap.back(); hidx[heap[0]] = 0; hidx[x] = -1; heap.pop_back();
+    if (heap.size() > 1) { heapDown(0); }
+    return x;
+}
+void Engine::heapClear() { for (int v : heap) { hidx[v] = -1; } heap.clear(); }
+
+// ------------------------------------------------------------------------------------------------ data bookkeeping
+// removedClause(cr, heap, update, ignore), CoprocessorTypes.h:1310-1350
+void Engine::removedClause(uint32_t c, bool useHeap, bool update, int ignore)
+{
+    const int32_t* l = CL(c);
+    for (uint32_t i = 0; i < csize[c]; ++i) {
+        int v = l[i] >> 1;
+        deletedVar(v);
+        --cnt[l[i]];
+        if (useHeap) {
+            if (inHeap(v)) { heapUp(hidx[v]); }
+            else if (update && v != ignore) { heapUpdate(v); }
+        }
+    }
+    numberOfCls--;
+    caFree(c);
+}
+// removedLiteral(l, diff, heap, update, ignore), CoprocessorTypes.h:1243-1277
+void Engine::removedLiteral(int x, int diff, bool useHeap, bool update, int ignore)
+{
+    int v = x >> 1;
+    deletedVar(v);
+    cnt[x] -= diff;
+    ca_wasted += 1;
+    if (useHeap) {
+        if (inHeap(v)) { heapUp(hidx[v]); }
+        else if (update && v != ignore) { heapUpdate(v); }
+    }
+}
+// addClause(cr, heap), CoprocessorTypes.h:835-864
+void Engine::dataAddClause(uint32_t c, bool useHeap)
+{
+    if (cflag[c] & F_DEL) { return; }
+    const int32_t* l = CL(c);
+    for (uint32_t i = 0; i < csize[c]; ++i) {
+        occPush(l[i], c);
+        cnt[l[i]] += 1;
+        ++var_touch[l[i] >> 1];
+        if (useHeap && inHeap(l[i] >> 1)) { heapDown(hidx[l[i] >> 1]); }
+    }
+    numberOfCls++;
+}
+// removeClauseFrom, CoprocessorTypes.h:867-878
+bool Engine::removeClauseFrom(uint32_t c, int x)
+{
+    OccList& l = occ[x]; uint32_t* p = LP(l);
+    for (uint32_t i = 0; i < l.n; ++i) { if (p[i] == c) { occSwapRemove(x, i); return true; } }
+    return false;
+}
+void Engine::subInitClause(uint32_t c)
+{
+    if (cflag[c] & F_DEL) { return; }
+    if (cflag[c] & F_SUB) { subq.push_back(c); }
+    if (cflag[c] & F_STR) { strq.push_back(c); }
+}
+void Engine::addSubStrength(uint32_t c)
+{
+    if (!(cflag[c] & F_STR)) { cflag[c] |= F_STR; strq.push_back(c); }
+    if (!(cflag[c] & F_SUB)) { cflag[c] |= F_SUB; subq.push_back(c); }
+}
+void Engine::extClause(uint32_t c, int x)
+{
+    undo.push_back(0); undo.push_back(toDimacs(x));
+    const int32_t* l = CL(c);
+    for (uint32_t i = 0; i < csize[c]; ++i) { if (l[i] != x) { undo.push_back(toDimacs(l[i])); } }
+}
+void Engine::extLit(int x) { undo.push_back(0); undo.push_back(toDimacs(x)); }
+
+void Engine::filterDeleted(std::vector<uint32_t>& a)
+{
+    size_t j = 0;
+    for (size_t i = 0; i < a.size(); ++i) { if (!(cflag[a[i]] & F_DEL)) { a[j++] = a[i]; } }
+    a.resize(j);
+}
+// garbageCollect / relocAll, CoprocessorTypes.h:1396-1550 (stable removal of deleted clauses everywhere)
+void Engine::checkGarbage()
+{
+    if (!(ca_wasted > ca_size * opt.gc_frac)) { return; }
+    filterDeleted(subq); filterDeleted(strq);
+    for (int x = 0; x < 2 * nvars; ++x) {
+        OccList& l = occ[x]; uint32_t* p = LP(l); uint32_t j = 0;
+        for (uint32_t i = 0; i < l.n; ++i) { if (!(cflag[p[i]] & F_DEL)) { p[j++] = p[i]; } }
+        l.n = j; stale[x] = 0;
+    }
+    filterDeleted(clauses);
+    double sz = 0;
+    for (uint32_t c : clauses) { sz += 2 + csize[c]; }
+    ca_size = sz; ca_wasted = 0;
+}
+
+// ------------------------------------------------------------------------------------------------ Propagation::process (Propagation.cc:32-131)
+int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
+{
+    t_up.modified = false;
+    if (!ok) { return L_FALSE; }
+    for (; up_last < (int)trail.size(); up_last++) {
+        const int l = trail[up_last];
+        {
+            OccList& positive = occ[l];
+            for (uint32_t i = 0; i < positive.n; ++i) {
+                uint32_t c = LP(positive)[i];
+                if (cflag[c] & F_DEL) { continue; }
+                ++up_removedClauses;
+                setDeleted(c);
+                t_up.modified = true;
+                removedClause(c, useHeap, false, ignore);
+            }
+            occRelease(l);
+        }
+        const int nl = lneg(l);
+        int count = 0;
+        OccList& negative = occ[nl];
+        for (uint32_t i = 0; i < negative.n; ++i) {
+            uint32_t c = LP(negative)[i];
+            if (cflag[c] & F_DEL) { continue; }
+            int32_t* lits = CL(c);
+            for (uint32_t j = 0; j < csize[c]; ++j) {
+                if (lits[j] == nl) {
+                    if (!sort) { removePosUnsorted(c, (int)j); } else { removePosSorted(c, (int)j); }
+                    noteShrunk(c, nl);
+                    t_up.modified = true;
+                    count++;
+                    break;
+                }
+            }
+            addSubStrength(c);
+            dirty_str.push_back(c);
+            if (csize[c] == 0) { setDeleted(c); ok = false; return L_FALSE; }
+            else if (csize[c] == 1) {
+                setDeleted(c);
+                int u = CL(c)[0];
+                if (value(u) == L_UNDEF) { uncheckedEnqueue(u); }
+                else if (value(u) == L_FALSE) { ok = false; }
+            }
+        }
+        occRelease(nl);
+        // QUIRK: removedLiteral(nl, count, heap, ignore) - `ignore` lands in the `update` slot (Propagation.cc:114)
+        removedLiteral(nl, count, useHeap, ignore != 0, VAR_UNDEF);
+        up_removedLiterals += count;
+    }
+    qhead = up_last;
+    if (!t_up.modified) { unsuccessful(t_up); }
+    return ok ? L_UNDEF : L_FALSE;
+}
+
+// ------------------------------------------------------------------------------------------------ Subsumption
+void Engine::clearQueue(std::vector<uint32_t>& q, uint8_t flag)
+{
+    for (uint32_t c : q) { cflag[c] &= ~flag; }
+    q.clear();
+}
+
+static inline const Hit* findHit(const std::vector<Hit>& hits, uint32_t hb, uint32_t he, uint32_t clause)
+{
+    const Hit* b = hits.data() + hb; const Hit* e = hits.data() + he;
+    const Hit* it = std::lower_bound(b, e, clause, [](const Hit& h, uint32_t c) { return h.clause < c; });
+    return (it != e && it->clause == clause) ? it : nullptr;
+}
+
+// subsumption_worker, Subsumption.cc:220-314.  One bulk K3 scan answers every ordered_subsumes() of the
+// queue; the loop below replays the queue back to front.
+void Engine::subsumptionWorker(bool useHeap, int ignore)
+{
+    const bool unlimited = !opt.limited;
+    c_sub.clear(); edit_log.clear();
+    {
+        std::vector<uint32_t> ids;
+        ids.reserve(subq.size());
+        for (uint32_t c : subq) { if (!(cflag[c] & F_DEL)) { ids.push_back(c); } }
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        scanClauses(CP3G_SUBSUME, ids, c_sub);
+    }
+    int64_t t0 = now_ns();
+    size_t end = subq.size();
+    sub_occ_updates.clear();
+    for (; end > 0 && (unlimited || sub_steps < sub_lim);) {
+        --end;
+        const uint32_t cr = subq[end];
+        if (cflag[cr] & F_DEL) { continue; }
+        const int32_t* c = CL(cr); const uint32_t cn = csize[cr];
+        int min = c[0];
+        for (uint32_t l = 1; l < cn; ++l) { if (cnt[c[l]] < cnt[min]) { min = c[l]; } }
+        const CacheEnt* e = cached(c_sub, cr);
+        if (!e) { die("internal: subsumer without scan result"); }
+        OccList& list = occ[min];
+        if (e->hb == e->he && stale[min] == 0 && (unlimited || sub_steps + (int64_t)list.n < sub_lim)) {
+            sub_steps += list.n ? (int64_t)list.n - 1 : 0;          // every entry but cr itself is one check
+            ++n_fast;
+        } else {
+            ++n_slow;
+            for (uint32_t i = 0; i < list.n && (unlimited || sub_steps < sub_lim); ++i) {
+                const uint32_t d = LP(list)[i];
+                if (d == cr) { continue; }
+                sub_steps++;
+                if (csize[d] < cn) { continue; }
+                if (cflag[d] & F_DEL) { occSwapRemove(min, i); --i; continue; }
+                if (findHit(c_sub.hits, e->hb, e->he, d) && subHitValid(cr, d, e->scan)) {
+                    ++subsumedClauses; subsumedLiterals += (int)csize[d];
+                    setDeleted(d);
+                    removedClause(d, false, false, VAR_UNDEF);
+                    successful(t_sub);
+                    sub_occ_updates.push_back(d);
+                }
+            }
+        }
+        cflag[cr] &= ~F_SUB;
+    }
+    // QUIRK: removedClause a second time per subsumed clause (Subsumption.cc:302-313); `ignore` lands in `update`
+    for (uint32_t d : sub_occ_updates) { removedClause(d, useHeap, ignore != 0, VAR_UNDEF); }
+    sub_occ_updates.clear();
+    host_ns_commit += now_ns() - t0;
+}
+
+// updateOccurrences, Subsumption.cc:1530-1544
+void Engine::updateOccurrences(bool useHeap, int ignore)
+{
+    // from here on nothing is pending any more (setDeleted() consults pend_rm)
+    std::vector<OccUpd> ups; ups.swap(occ_upd);
+    pend_rm.clear();
+    for (const OccUpd& u : ups) {
+        if (removeClauseFrom(u.cr, u.l)) { removedLiteral(u.l, 1, useHeap, ignore != 0, VAR_UNDEF); }
+    }
+}
+
+// the hit branch of both passes, Subsumption.cc:1385-1413 / 1474-1508
+void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos)
+{
+    ++removedLiterals;
+    if (!(cflag[other] & F_SUB)) { cflag[other] |= F_SUB; subq.push_back(other); }
+    if (!(cflag[other] & F_STR)) { localQueue.push_back(other); cflag[other] |= F_STR; }
+    successful(t_sub);
+    const int lit = CL(other)[pos];
+    occ_upd.push_back({other, lit});
+    pend_rm[other].push_back(lit);
+    removePosSorted(other, pos);
+    noteShrunk(other, lit);
+    dirty_str.push_back(other);
+    if (csize[other] == 1) {
+        dataEnqueue(CL(other)[0]);
+        setDeleted(other);
+    }
+}
+
+// strengthening hits of cr for its current content: cached, or one more K4 batch (cr + the other pending
+// strengtheners that were edited after their scan)
+const Engine::CacheEnt* Engine::strHits(uint32_t cr)
+{
+    const CacheEnt* e = cached(c_str, cr);
+    if (e) { return e; }
+    ++n_ondemand;
+    std::vector<uint32_t> ids;
+    if (c_str.slot.size() < cstart.size()) { c_str.slot.resize(cstart.size(), -1); }
+    for (uint32_t c : dirty_str) {
+        if (c == cr || (cflag[c] & F_DEL) || !(cflag[c] & F_STR) || csize[c] < 2) { continue; }
+        if (cached(c_str, c)) { continue; }
+        ids.push_back(c);
+    }
+    dirty_str.clear();
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    ids.insert(ids.begin(), cr);
+    scanClauses(CP3G_STRENGTHEN, ids, c_str);
+    e = cached(c_str, cr);
+    if (!e) { die("internal: strengthener without scan result"); }
+    return e;
+}
+
+// strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
+int Engine::strengtheningWorker(bool useHeap, int ignore)
+{
+    const bool unlimited = !opt.limited;
+    c_str.clear(); edit_log.clear(); dirty_str.clear();
+    if (opt.strength) {
+        std::vector<uint32_t> ids;
+        for (uint32_t c : strq) {
+            if ((cflag[c] & F_DEL) || !(cflag[c] & F_STR) || csize[c] < 2) { continue; }
+            ids.push_back(c);
+        }
+        std::sort(ids.begin(), ids.end());
+        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        scanClauses(CP3G_STRENGTHEN, ids, c_str);
+    }
+    int64_t t0 = now_ns();
+    std::vector<uint32_t> localQueue;
+    size_t end = strq.size();
+    int ret = L_UNDEF; bool early = false;
+    for (; end > 0 && (unlimited || str_steps < str_lim);) {
+        uint32_t cr;
+        if (localQueue.empty()) { --end; cr = strq[end]; }
+        else { cr = localQueue.back(); localQueue.pop_back(); }
+        if ((cflag[cr] & F_DEL) || !(cflag[cr] & F_STR)) { continue; }
+        if (!opt.strength) { cflag[cr] &= ~F_STR; continue; }
+        if (csize[cr] < 2) {
+            if (csize[cr] == 1) { if (dataEnqueue(CL(cr)[0]) == L_FALSE) { break; } else { continue; } }
+            else { ok = false; break; }
+        }
+        int minT;
+        { const int32_t* s = CL(cr); minT = s[0];
+          for (uint32_t j = 1; j < csize[cr]; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
+        const int min = minT, nmin = lneg(minT);
+        const CacheEnt* e = strHits(cr);
+        if (e->hb == e->he && stale[min] == 0 && stale[nmin] == 0 && !hasToPropagate() &&
+            (unlimited || str_steps + (int64_t)occ[min].n + (int64_t)occ[nmin].n < str_lim)) {
+            // no candidate can hit and no list needs lazy cleaning: only the step counters move
+            str_steps += (occ[min].n ? (int64_t)occ[min].n - 1 : 0) + (int64_t)occ[nmin].n;
+            cflag[cr] &= ~F_STR;
+            ++n_fast;
+            continue;
+        }
+        ++n_slow;
+        // pass 1: occ(min) - the complementary literal is any literal but min
+        {
+            OccList& list = occ[min];
+            for (uint32_t j = 0; j < list.n && (unlimited || str_steps < str_lim); ++j) {
+                const uint32_t other = LP(list)[j];
+                if (other == cr) { continue; }
+                str_steps++;
+                if (csize[other] == 0) { break; }
+                if (cflag[other] & F_DEL) { occSwapRemove(min, j); --j; continue; }
+                const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
+                if (h && h->lit != nmin && strHitValid(cr, other, h->lit, e->scan)) {
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k = 0; k < csize[other]; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+            }
+        }
+        if (hasToPropagate()) {
+            if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
+            e = strHits(cr);                 // cr itself may have been shortened by the propagation
+        }
+        // pass 2: occ(~min) - the complementary literal must be ~min
+        {
+            OccList& list_neg = occ[nmin];
+            for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
+                const uint32_t other = LP(list_neg)[j];
+                str_steps++;
+                if (cflag[other] & F_DEL) { occSwapRemove(nmin, j); --j; continue; }
+                const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
+                if (h && h->lit == nmin && strHitValid(cr, other, h->lit, e->scan)) {
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k = 0; k < csize[other]; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+            }
+        }
+        if (hasToPropagate()) {
+            if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
+            t_sub.modified = t_sub.modified || t_up.modified;
+        }
+        cflag[cr] &= ~F_STR;
+    }
+    if (!early) {
+        updateOccurrences(useHeap, ignore);
+        ret = ok ? L_UNDEF : L_FALSE;
+    }
+    host_ns_commit += now_ns() - t0;
+    return ret;
+}
+
+// Subsumption::process, Subsumption.cc:85-180
+bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
+{
+    t_sub.modified = false;
+    if (!ok) { return false; }
+    if (!performSimplification(t_sub)) {
+        clearQueue(subq, F_SUB); clearQueue(strq, F_STR);
+        return false;
+    }
+    if (!(sub_steps + opt.call_inc < sub_lim)) { sub_lim += opt.call_inc; limitIncreases++; }
+    if (!(str_steps + opt.call_inc < str_lim)) { str_lim += opt.call_inc; limitIncreases++; }
+    while (ok && (!subq.empty() || !strq.empty())) {
+        if (!subq.empty()) {
+            subsumptionWorker(useHeap, ignore);
+            clearQueue(subq, F_SUB);
+        }
+        if (!strq.empty()) {
+            if (!doStrengthen) { clearQueue(strq, F_STR); continue; }
+            strengtheningWorker(useHeap, ignore);
+            clearQueue(strq, F_STR);
+        }
+    }
+    t_sub.modified = t_sub.modified || t_up.modified;   // propagation.appliedSomething(): its last call
+    if (!t_sub.modified) { unsuccessful(t_sub); }
+    return t_sub.modified;
+}
+
+// ------------------------------------------------------------------------------------------------ BVE
+// findGates, BVE.cc:1143-1267 - reads clause sizes / binary partners only (no clause-vs-clause test)
+bool Engine::findGates(int v, int& p_limit, int& n_limit)
+{
+    if (occ[2 * v].n < 3 && occ[2 * v + 1].n < 3) { return false; }
+    if (occ[2 * v].n < 2 || occ[2 * v + 1].n < 2) { return false; }
+    for (int pn = 0; pn < 2; ++pn) {
+        const int pLit = 2 * v + (pn != 0), nLit = 2 * v + (pn == 0);
+        OccList& pList = occ[pLit]; OccList& nList = occ[nLit];
+        int& pClauses = pn == 0 ? p_limit : n_limit;
+        int& nClauses = pn == 0 ? n_limit : p_limit;
+        if (ma_step >= (1u << 30)) { std::fill(ma.begin(), ma.end(), 0u); ma_step = 0; }
+        ++ma_step;
+        for (uint32_t i = 0; i < pList.n; ++i) {
+            uint32_t c = LP(pList)[i];
+            if ((cflag[c] & F_DEL) || csize[c] != 2) { continue; }
+            const int32_t* l = CL(c);
+            int other = l[0] == pLit ? l[1] : l[0];
+            ma[lneg(other)] = ma_step;
+        }
+        for (uint32_t i = 0; i < nList.n; ++i) {
+            uint32_t c = LP(nList)[i];
+            if (cflag[c] & F_DEL) { continue; }
+            const int32_t* l = CL(c); uint32_t j = 0;
+            for (; j < csize[c]; ++j) {
+                if (l[j] == nLit) { continue; }
+                if (ma[l[j]] != ma_step) { break; }
+            }
+            if (j == csize[c]) {
+                pClauses = (int)csize[c] - 1;
+                nClauses = 1;
+                for (uint32_t k = 0; k < csize[c]; ++k) { ma[l[k]] = 0; }
+                std::swap(LP(nList)[0], LP(nList)[i]);
+                uint32_t placed = 0;
+                for (uint32_t k = 0; k < pList.n; ++k) {
+                    uint32_t c2 = LP(pList)[k];
+                    if ((cflag[c2] & F_DEL) || csize[c2] != 2) { continue; }
+                    const int32_t* l2 = CL(c2);
+                    int other = l2[0] == pLit ? l2[1] : l2[0];
+                    if (ma[lneg(other)] != ma_step) {
+                        std::swap(LP(pList)[placed], LP(pList)[k]);
+                        placed++;
+                        ma[lneg(other)] = ma_step;
+                    }
+                }
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// K5 result for variable v on its current occurrence lists: cached while none of its clauses changed,
+// else one more batch (v plus the invalid variables near the top of the heap).
+Engine::PairEnt& Engine::pairsFor(int v)
+{
+    PairEnt& pe = pair_cache[v];
+    if (pe.valid && pe.touch == var_touch[v]) { return pe; }
+    flushDevice();
+    ++n_pair_batches;
+    std::vector<int> vs; vs.push_back(v);
+    const size_t look = std::min<size_t>(heap.size(), 256);
+    for (size_t i = 0; i < look; ++i) {
+        int w = heap[i];
+        if (w == v || assigns[w] != L_UNDEF || frozen[w]) { continue; }
+        if (occ[2 * w].n == 0 || occ[2 * w + 1].n == 0) { continue; }
+        if ((uint64_t)occ[2 * w].n * occ[2 * w + 1].n > 4096) { continue; }
+        auto it = pair_cache.find(w);
+        if (it != pair_cache.end() && it->second.valid && it->second.touch == var_touch[w]) { continue; }
+        vs.push_back(w);
+    }
+    std::vector<uint32_t> vars, p_off{0}, n_off{0}, p_refs, n_refs; std::vector<uint64_t> pair_off{0};
+    for (int w : vs) {
+        vars.push_back((uint32_t)w);
+        OccList& P = occ[2 * w]; OccList& N = occ[2 * w + 1];
+        p_refs.insert(p_refs.end(), LP(P), LP(P) + P.n); n_refs.insert(n_refs.end(), LP(N), LP(N) + N.n);
+        p_off.push_back((uint32_t)p_refs.size()); n_off.push_back((uint32_t)n_refs.size());
+        pair_off.push_back(pair_off.back() + (uint64_t)P.n * N.n);
+    }
+    std::vector<int16_t> sizes(pair_off.back() + 1);
+    int64_t t0 = now_ns();
+    if (cp3g_bve_pairs(gpu, (uint32_t)vars.size(), vars.data(), p_off.data(), p_refs.data(), n_off.data(), n_refs.data(),
+                       pair_off.data(), sizes.data()) != CP3G_OK) { die("bve_pairs failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    for (size_t i = 0; i < vs.size(); ++i) {
+        PairEnt& q = pair_cache[vs[i]];
+        q.touch = var_touch[vs[i]]; q.valid = true;
+        q.pos.assign(p_refs.begin() + p_off[i], p_refs.begin() + p_off[i + 1]);
+        q.neg.assign(n_refs.begin() + n_off[i], n_refs.begin() + n_off[i + 1]);
+        q.sizes.assign(sizes.begin() + pair_off[i], sizes.begin() + pair_off[i + 1]);
+    }
+    return pair_cache[v];
+}
+
+static inline int indexOf(const std::vector<uint32_t>& a, uint32_t x)
+{
+    for (size_t i = 0; i < a.size(); ++i) { if (a[i] == x) { return (int)i; } }
+    return -1;
+}
+
+// anticipateElimination, BVE.cc:695-880; tryResolve sizes come from K5
+int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& resolvents)
+{
+    OccList& positive = occ[2 * v]; OccList& negative = occ[2 * v + 1];
+    const bool hasDefinition = (p_limit < (int)positive.n || n_limit < (int)negative.n);
+    lit_clauses = 0;
+    int clausesToUse = 0;
+    if (opt.bve_early) {
+        for (uint32_t i = 0; i < positive.n; ++i) { if (!(cflag[LP(positive)[i]] & F_DEL)) { clausesToUse++; } }
+        for (uint32_t i = 0; i < negative.n; ++i) { if (!(cflag[LP(negative)[i]] & F_DEL)) { clausesToUse++; } }
+        clausesToUse += opt.bve_cgrow;
+        if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { clausesToUse += opt.bve_cgrow_t - bve_totallyAdded; }
+    }
+    bool binariesOnly = false;
+    PairEnt* pe = &pairsFor(v);
+    std::vector<int> col;                         // column of negative[cn] in the K5 matrix
+    auto remap = [&]() { col.assign(negative.n, -1); for (uint32_t j = 0; j < negative.n; ++j) { col[j] = indexOf(pe->neg, LP(negative)[j]); } };
+    remap();
+    for (uint32_t cp = 0; cp < positive.n; ++cp) {
+        const uint32_t p = LP(positive)[cp];
+        if (cflag[p] & F_DEL) { continue; }
+        if (binariesOnly && csize[p] > 2) { continue; }
+        int row = indexOf(pe->pos, p);
+        for (uint32_t cn = 0; cn < negative.n; ++cn) {
+            if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
+            if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
+            bve_steps++;
+            const uint32_t n = LP(negative)[cn];
+            if (cflag[n] & F_DEL) { continue; }
+            if (binariesOnly && csize[n] > 2) { continue; }
+            if (row < 0 || col[cn] < 0) { die("internal: K5 matrix misses a clause"); }
+            const int newLits = pe->sizes[(size_t)row * pe->neg.size() + col[cn]];
+            if (newLits > 1) {
+                ++pos_stats[cp]; ++neg_stats[cn];
+                lit_clauses += newLits;
+                resolvents++;
+                if (opt.bve_early && resolvents > clausesToUse) { binariesOnly = true; }
+            } else if (newLits == 0) {
+                successful(t_bve);
+                ok = false;
+                return L_FALSE;
+            } else if (newLits == 1) {
+                // the unit literal: K6 on this single pair
+                uint32_t vv = (uint32_t)v; uint64_t off[2] = {0, 1}; int32_t ul = 0;
+                flushDevice();
+                if (cp3g_bve_resolve(gpu, 1, &vv, &p, &n, off, &ul, 1) != CP3G_OK) { die("bve_resolve failed"); }
+                int status = dataEnqueue(ul);
+                if (status == L_FALSE) { successful(t_bve); return L_FALSE; }
+                else if (status == L_TRUE) {
+                    successful(t_bve);
+                    ++bve_unitsEnqueued;
+                    if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
+                    t_bve.modified = t_bve.modified || t_up.modified;
+                    // clauses changed under us: fresh sizes for the rest of the loop
+                    if (positive.n == 0 || negative.n == 0) { break; }
+                    pe = &pairsFor(v); remap(); row = indexOf(pe->pos, p);
+                    if (cflag[p] & F_DEL) { break; }
+                }
+            }
+        }
+    }
+    return binariesOnly ? L_TRUE : L_UNDEF;
+}
+
+// removeClauses, BVE.cc:644-684
+void Engine::bveRemoveClauses(int x, int extLitOrNeg)
+{
+    const bool useHeap = opt.bve_heap_updates > 0;
+    OccList& list = occ[x];
+    for (uint32_t i = 0; i < list.n; ++i) {
+        uint32_t c = LP(list)[i];
+        if (cflag[c] & F_DEL) { continue; }
+        removedClause(c, useHeap, false, VAR_UNDEF);
+        successful(t_bve);
+        setDeleted(c);
+        if (extLitOrNeg >= 0) { extClause(c, extLitOrNeg); }
+        ++bve_removedClauses; bve_removedLiterals += (int)csize[c];
+    }
+}
+// removeBlockedClauses, BVE.cc:1053-1090
+void Engine::bveRemoveBlocked(int x, const std::vector<int>& stats)
+{
+    const bool useHeap = opt.bve_heap_updates > 0;
+    OccList& list = occ[x];
+    for (uint32_t i = 0; i < list.n; ++i) {
+        uint32_t c = LP(list)[i];
+        if (cflag[c] & F_DEL) { continue; }
+        if (stats[i] == 0) {
+            setDeleted(c);
+            removedClause(c, useHeap, false, VAR_UNDEF);
+            successful(t_bve);
+            extClause(c, x);
+            ++bve_removedBC;
+        }
+    }
+}
+
+// resolveSet, BVE.cc:892-1046 (force == false): K5 tells which pairs resolve, K6 writes the resolvents
+int Engine::resolveSet(int v, int p_limit, int n_limit)
+{
+    const bool useHeap = opt.bve_heap_updates > 0;
+    OccList& positive = occ[2 * v]; OccList& negative = occ[2 * v + 1];
+    const bool hasDefinition = (p_limit < (int)positive.n || n_limit < (int)negative.n);
+    PairEnt* pe = &pairsFor(v);
+    // gather the pairs in reference order and fetch their resolvents with one K6 launch
+    struct Pr { uint32_t cp, cn; int size; uint64_t off; };
+    std::vector<Pr> prs; std::vector<int32_t> rl;
+    auto fetch = [&](uint32_t cp0, uint32_t cn0) {
+        prs.clear();
+        std::vector<uint32_t> vv, pr, nr; std::vector<uint64_t> off{0};
+        std::vector<int> col(negative.n, -1);
+        for (uint32_t j = 0; j < negative.n; ++j) { col[j] = indexOf(pe->neg, LP(negative)[j]); }
+        for (uint32_t cp = cp0; cp < positive.n; ++cp) {
+            const uint32_t p = LP(positive)[cp];
+            if (cflag[p] & F_DEL) { continue; }
+            const int row = indexOf(pe->pos, p);
+            for (uint32_t cn = (cp == cp0 ? cn0 : 0); cn < negative.n; ++cn) {
+                if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
+                if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
+                const uint32_t n = LP(negative)[cn];
+                if (cflag[n] & F_DEL) { continue; }
+                if (row < 0 || col[cn] < 0) { die("internal: K5 matrix misses a clause"); }
+                const int s = pe->sizes[(size_t)row * pe->neg.size() + col[cn]];
+                if (s >= 1) {
+                    prs.push_back({cp, cn, s, off.back()});
+                    vv.push_back((uint32_t)v); pr.push_back(p); nr.push_back(n); off.push_back(off.back() + (uint64_t)s);
+                }
+            }
+        }
+        rl.assign(off.back() + 1, 0);
+        if (!prs.empty()) {
+            ++n_resolve_batches;
+            int64_t t0 = now_ns();
+            if (cp3g_bve_resolve(gpu, (uint32_t)prs.size(), vv.data(), pr.data(), nr.data(), off.data(), rl.data(), off.back()) != CP3G_OK) { die("bve_resolve failed"); }
+            host_ns_gpuwait += now_ns() - t0;
+        }
+    };
+    flushDevice();
+    fetch(0, 0);
+    size_t k = 0;
+    for (uint32_t cp = 0; cp < positive.n; ++cp) {
+        const uint32_t p = LP(positive)[cp];
+        if (cflag[p] & F_DEL) { continue; }
+        for (uint32_t cn = 0; cn < negative.n; ++cn) {
+            if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
+            if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
+            bve_steps++;
+            const uint32_t n = LP(negative)[cn];
+            if (cflag[n] & F_DEL) { continue; }
+            while (k < prs.size() && (prs[k].cp < cp || (prs[k].cp == cp && prs[k].cn < cn))) { ++k; }
+            if (k >= prs.size() || prs[k].cp != cp || prs[k].cn != cn) { continue; }   // tautology / empty
+            const Pr& q = prs[k];
+            if (q.size == 1) {
+                int status = dataEnqueue(rl[q.off]);
+                if (status == L_FALSE) { return L_FALSE; }
+                else if (status == L_TRUE) {
+                    ++bve_unitsEnqueued;
+                    if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
+                    t_bve.modified = t_bve.modified || t_up.modified;
+                    if (positive.n == 0 || negative.n == 0) { return L_UNDEF; }
+                    const bool pdel = (cflag[p] & F_DEL) != 0;
+                    flushDevice();
+                    pe = &pairsFor(v);
+                    // continue behind (cp,cn); a deleted p ends its row (BVE.cc:942-944)
+                    if (pdel) { fetch(cp + 1, 0); k = 0; break; }
+                    fetch(cp, cn + 1); k = 0;
+                }
+            } else {
+                uint32_t cr = allocClause(rl.data() + q.off, q.size);
+                dataAddClause(cr, useHeap);
+                clauses.push_back(cr);
+                subInitClause(cr);
+                ++bve_createdClauses; bve_createdLiterals += q.size;
+            }
+        }
+    }
+    return L_UNDEF;
+}
+
+// bve_worker, BVE.cc:388-637
+void Engine::bveWorker()
+{
+    const bool unlimited = !opt.limited;
+    while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
+        const int v = heapRemoveMin();
+        if (assigns[v] != L_UNDEF) { continue; }
+        if (occ[2 * v].n == 0 && occ[2 * v + 1].n == 0) { continue; }
+        if (frozen[v]) { continue; }
+        const bool cutoff = (cnt[2 * v + 1] > 10 && cnt[2 * v] > 10) || (dcount(v) > 15 && (cnt[2 * v + 1] > 5 || cnt[2 * v] > 5));
+        if (!opt.bve_force_gates && !opt.bve_unlimited && cutoff) { ++bve_skippedVars; continue; }
+        int p_limit = (int)occ[2 * v].n, n_limit = (int)occ[2 * v + 1].n;
+        bool foundGate = false;
+        if (opt.bve_gates) { foundGate = findGates(v, p_limit, n_limit); if (foundGate) { bve_foundGates++; } }
+        if (!foundGate && opt.bve_fdepOnly) { continue; }
+        if (!opt.bve_unlimited && !foundGate && cutoff) { ++bve_skippedVars; continue; }
+        ++bve_testedVars;
+        int pos_count = 0, neg_count = 0;
+        for (int s = 0; s < 2; ++s) {
+            OccList& li = occ[2 * v + s];
+            for (uint32_t i = 0; i < li.n; ++i) {
+                if (cflag[LP(li)[i]] & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
+                if (s == 0) { ++pos_count; } else { ++neg_count; }
+            }
+        }
+        if (pos_stats.size() < occ[2 * v].n) { pos_stats.resize(occ[2 * v].n, 0); }
+        if (neg_stats.size() < occ[2 * v + 1].n) { neg_stats.resize(occ[2 * v + 1].n, 0); }
+        int lit_clauses = 0, resolvents = 0;
+        int ares = L_UNDEF;
+        if (pos_count != 0 && neg_count != 0) {
+            ++bve_anticipations;
+            ares = anticipate(v, p_limit, n_limit, lit_clauses, resolvents);
+            if (ares == L_FALSE) { return; }
+        }
+        if (ares == L_UNDEF && opt.bve_BCElim) {
+            bveRemoveBlocked(2 * v, pos_stats);
+            bveRemoveBlocked(2 * v + 1, neg_stats);
+        }
+        int compareNumber = pos_count + neg_count + opt.bve_cgrow;
+        if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { compareNumber += opt.bve_cgrow_t - bve_totallyAdded; }
+        bool reducedClss = resolvents <= compareNumber;
+        if (bve_totallyAdded > opt.bve_cgrow_t) { reducedClss = false; }
+        if (reducedClss) { bve_totallyAdded += resolvents - (pos_count + neg_count); }
+        if (reducedClss && !opt.bce_only) {
+            if (resolvents < pos_count + neg_count) { bve_nDec++; }
+            else if (resolvents > pos_count + neg_count) { bve_nInc++; }
+            else { bve_nKeep++; }
+            if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; }
+            ++bve_eliminatedVars;
+            bveRemoveClauses(2 * v, -1);
+            if (assigns[v] == L_UNDEF) { bveRemoveClauses(2 * v + 1, 2 * v + 1); extLit(2 * v); }
+            else { bveRemoveClauses(2 * v + 1, -1); }
+            occRelease(2 * v); occRelease(2 * v + 1);
+            if (opt.bve_heap_updates > 0) { subsumptionProcess(opt.bve_strength, true, v); }
+            else { subsumptionProcess(opt.bve_strength, false, VAR_UNDEF); }
+            t_bve.modified = t_bve.modified || t_sub.modified;
+            if (!ok) { return; }
+        }
+        std::fill(pos_stats.begin(), pos_stats.end(), 0); std::fill(neg_stats.begin(), neg_stats.end(), 0);
+    }
+}
+
+uint32_t Engine::nextModStep()
+{
+    if (modStep >= (1u << 30)) { std::fill(modTimer.begin(), modTimer.end(), 0u); modStep = 0; }
+    return ++modStep;
+}
+
+// addClausesToSubsumption, BVE.cc:1129-1141
+void Engine::addClausesToSubsumption(int x)
+{
+    OccList& li = occ[x];
+    for (uint32_t j = 0; j < li.n; ++j) {
+        uint32_t d = LP(li)[j];
+        if (!(cflag[d] & F_DEL) && !(cflag[d] & F_SUB)) { cflag[d] |= F_SUB | F_STR; subInitClause(d); }
+    }
+}
+
+// sequentiellBVE, BVE.cc:316-381
+void Engine::sequentiellBVE()
+{
+    const bool unlimited = !opt.limited;
+    subsumptionProcess(opt.bve_strength, false, VAR_UNDEF);
+    t_bve.modified = t_bve.modified || t_sub.modified;
+    if (!ok) { return; }
+    touched.clear();
+    while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
+        bve_modtime = nextModStep();
+        bveWorker();
+        if (!ok) { return; }
+        if (hasToPropagate()) {
+            if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return; }
+            t_bve.modified = t_bve.modified || t_up.modified;
+        }
+        checkGarbage();
+        for (int v = 0; v < nvars; ++v) { if (modTimer[v] >= bve_modtime) { touched.push_back(v); } }
+        for (int v : touched) { addClausesToSubsumption(2 * v); addClausesToSubsumption(2 * v + 1); }
+        subsumptionProcess(opt.bve_strength, false, VAR_UNDEF);
+        t_bve.modified = t_bve.modified || t_sub.modified;
+        heapClear();
+        for (int v : touched) { heapInsert(v); }
+        touched.clear();
+    }
+}
+
+// BoundedVariableElimination::process, BVE.cc:170-273
+int Engine::bveProcess()
+{
+    if (!performSimplification(t_bve)) { return L_UNDEF; }
+    for (int v = 0; v < nvars; ++v) { if (modTimer[v] >= bve_modtime && !inHeap(v)) { heapInsert(v); } }
+    if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
+    const bool propagatedSomething = t_up.modified;
+    sequentiellBVE();
+    pair_cache.clear();
+    if (!t_bve.modified) { unsuccessful(t_bve); }
+    if (t_bve.modified || propagatedSomething) { successful(t_bve); }
+    return ok ? L_UNDEF : L_FALSE;
+}
+
+// ------------------------------------------------------------------------------------------------ driver
+// data.init + initializePreprocessor + sortClauses (Coprocessor.cc:100-118,1243-1283,1447-1463).
+// The occurrence lists are built on the GPU (K2) and copied back - they start in clause order.
+void Engine::initData()
+{
+    const int n2 = 2 * nvars;
+    occ.assign((size_t)n2, OccList());
+    cnt.assign((size_t)n2, 0); stale.assign((size_t)n2, 0);
+    modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
+    var_touch.assign((size_t)std::max(nvars, 1), 0);
+    modStep = 0; numberOfCls = 0; qhead = 0;
+    subq.clear(); strq.clear();
+    uploadAll();
+    std::vector<uint32_t> off((size_t)n2 + 1, 0);
+    if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
+    occ_pool.assign((size_t)off[n2] + 16, 0);
+    if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
+    for (int x = 0; x < n2; ++x) {
+        occ[x].off = off[x]; occ[x].n = occ[x].cap = off[x + 1] - off[x];
+        cnt[x] = (int32_t)occ[x].n;
+    }
+    size_t kept = 0;
+    for (size_t i = 0; i < clauses.size(); ++i) {
+        uint32_t c = clauses[i];
+        if (cflag[c] & F_DEL) { continue; }
+        numberOfCls++;
+        subInitClause(c);
+        clauses[kept++] = c;
+    }
+    clauses.resize(kept);
+    data_ready = true;
+}
+
+void Engine::preprocess()
+{
+    // Coprocessor.cc:1002-1006: data.nVars() is still 0 before data.init() and nTotLits() only counts learnt
+    // literals, so only the clause-count gate can fire here
+    if (opt.limited && (int64_t)clauses.size() > opt.cp3_cls) { return; }
+    if (!opt.enabled) { return; }
+    ensureGpu();                                  // fail before touching anything when there is no device
+    sub_lim = opt.sub_limit; str_lim = opt.str_limit;
+    if (!solverSimplify()) { return; }
+    initData();
+    int status = L_UNDEF;
+    for (int it = 0; it < opt.iters; ++it) {
+        if (opt.up) { if (status == L_UNDEF) { status = propagationProcess(true, false, VAR_UNDEF); } }
+        if (!ok) { break; }
+        if (opt.subsimp) {
+            if (status == L_UNDEF) { subsumptionProcess(true, false, VAR_UNDEF); }
+            if (!ok) { status = L_FALSE; }
+            checkGarbage();
+        }
+        if (!ok) { break; }
+        if (opt.bve) {
+            if (status == L_UNDEF) { status = bveProcess(); }
+            checkGarbage();
+        }
+        if (!ok) { break; }
+    }
+    if (ok && hasToPropagate()) { propagationProcess(false, false, VAR_UNDEF); }
+    if (ok) { filterDeleted(clauses); }           // reSetupSolver, CoprocessorTypes.h:937-1008
+    if (opt.stats) {
+        fprintf(stderr, "c [STAT] SuSi(1) %d cls,  with %d lits, %d strengthed\n", subsumedClauses, subsumedLiterals, removedLiterals);
+        fprintf(stderr, "c [STAT] SuSi(2) %lld subs-steps, %lld strenght-steps, %d increases\n", (long long)sub_steps, (long long)str_steps, limitIncreases);
+        fprintf(stderr, "c [STAT] BVE(3) %d eliminated, %d created, %d removed, %lld checks\n", bve_eliminatedVars, bve_createdClauses, bve_removedClauses, (long long)bve_steps);
+        fprintf(stderr, "c [STAT] GPU %lld launches, %lld scan batches (%lld on demand), %lld fast / %lld slow queue entries\n",
+                (long long)cp3g_counter(gpu, "launches"), (long long)n_scan_batches, (long long)n_ondemand, (long long)n_fast, (long long)n_slow);
+    }
+}
+
+size_t Engine::output(int32_t* out, size_t cap) const
+{
+    size_t k = 0;
+    auto emit = [&](int32_t x) { if (k < cap) { out[k] = x; } ++k; };
+    for (int x : trail) { emit(toDimacs(x)); emit(0); }
+    for (uint32_t c : clauses) {
+        if (cflag[c] & F_DEL) { continue; }
+        const int32_t* l = CL(c);
+        for (uint32_t j = 0; j < csize[c]; ++j) { emit(toDimacs(l[j])); }
+        emit(0);
+    }
+    return k;
+}
+size_t Engine::nLiveClauses() const { size_t n = 0; for (uint32_t c : clauses) { n += !(cflag[c] & F_DEL); } return n; }
+size_t Engine::nLiveLits() const { size_t n = 0; for (uint32_t c : clauses) { if (!(cflag[c] & F_DEL)) { n += csize[c]; } } return n; }
+size_t Engine::undoStack(int32_t* out, size_t cap) const
+{
+    for (size_t i = 0; i < undo.size() && i < cap; ++i) { out[i] = undo[i]; }
+    return undo.size();
+}
+
+// CoprocessorData::extendModel, CoprocessorTypes.h:1665-1764 (without Dense / EE): walk the undo stack
+// backwards; an entry [blocking literal, rest...] that is not satisfied flips its blocking literal.
+void Engine::extendModel(std::vector<uint8_t>& model) const
+{
+    if (model.size() < (size_t)nvars) { model.resize((size_t)nvars, L_TRUE); }
+    for (auto& m : model) { if (m == L_UNDEF) { m = L_TRUE; } }
+    for (int x : trail) { model[x >> 1] = (uint8_t)(x & 1); }
+    long i = (long)undo.size() - 1;
+    while (i >= 0) {
+        long j = i;
+        while (j >= 0 && undo[j] != 0) { --j; }
+        // entry = undo[j+1 .. i]
+        bool sat = false;
+        for (long k = j + 1; k <= i; ++k) {
+            int d = undo[k]; int v = (d < 0 ? -d : d) - 1;
+            if ((model[v] == L_TRUE) == (d > 0)) { sat = true; break; }
+        }
+        if (!sat && j + 1 <= i) {
+            int d = undo[j + 1]; int v = (d < 0 ? -d : d) - 1;
+            model[v] = d > 0 ? L_TRUE : L_FALSE;
+        }
+        i = j - 1;
+    }
+}
+
+int64_t Engine::stat(const char* s) const
+{
+#define ST(name, val) if (!strcmp(s, name)) { return (int64_t)(val); }
+    ST("sub_subsumedClauses", subsumedClauses) ST("sub_subsumedLiterals", subsumedLiterals)
+    ST("sub_removedLiterals", removedLiterals) ST("sub_subsSteps", sub_steps) ST("sub_strengthSteps", str_steps)
+    ST("bve_eliminatedVars", bve_eliminatedVars) ST("bve_createdClauses", bve_createdClauses)
+    ST("bve_removedClauses", bve_removedClauses) ST("bve_testedVars", bve_testedVars)
+    ST("bve_anticipations", bve_anticipations) ST("bve_skippedVars", bve_skippedVars)
+    ST("bve_unitsEnqueued", bve_unitsEnqueued) ST("bve_removedBC", bve_removedBC)
+    ST("bve_totallyAddedClauses", bve_totallyAdded) ST("bve_steps", bve_steps)
+    ST("up_removedClauses", up_removedClauses) ST("up_removedLiterals", up_removedLiterals)
+    ST("bve_foundGates", bve_foundGates)
+    ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
+    ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
+    ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
+    if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }
+#undef ST
+    return -1;
+}
+
+} // namespace cp3

@@ -1,0 +1,220 @@
+// engine.h - host side of the drop-in: Coprocessor's occurrence-list clause data base and the
+// *ordered commit* of subsumption / strengthening / unit propagation / BVE.
+//
+// Division of labour: every clause-against-clause test (subsumption merge, self-subsuming
+// resolution merge, resolvent size, resolvent generation) is computed by a CUDA kernel behind the cp3g_*
+// scan service, in bulk, on a snapshot of the data base.  The host never merges two clauses.  What the host
+// does is what makes the result identical to the sequential reference: it walks the reference's own work
+// queues / occurrence lists / variable heap in the reference's order, consumes the precomputed hits,
+// validates them against the edits committed since the snapshot (clauses only ever shrink or die, so a
+// snapshot hit can only be invalidated, never missed) and maintains the reference's counters, flags and
+// quirks (Subsumption.cc:85-180,220-314,1250-1544; Propagation.cc:32-131; BVE.cc:170-637).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "../../include/cp3b200.h"
+
+namespace cp3 {
+
+// literal code like riss/core/SolverTypes.h:65-98
+static inline int lvar(int x) { return x >> 1; }
+static inline int lneg(int x) { return x ^ 1; }
+static inline int toDimacs(int x) { return (x & 1) ? -((x >> 1) + 1) : ((x >> 1) + 1); }
+
+enum : uint8_t { F_DEL = 1, F_SUB = 2, F_STR = 4 };
+enum { L_TRUE = 0, L_FALSE = 1, L_UNDEF = 2 };
+static const int VAR_UNDEF = -1;
+
+// CP3Config subset (coprocessor/CP3Config.cc:56-112,196-224,560-577): same names, same defaults
+struct Options {
+    bool enabled = false, up = false, subsimp = false, bve = false, limited = true;
+    int iters = 1;
+    int cp3_vars = 5000000, cp3_cls = 30000000, cp3_lits = 50000000;
+    bool strength = true;
+    int64_t sub_limit = 300000000, str_limit = 300000000; int call_inc = 200;
+    int64_t bve_limit = 25000000;
+    bool bve_unlimited = false, bve_strength = true, bve_gates = true, bve_force_gates = false,
+         bve_fdepOnly = false, bve_BCElim = false, bve_early = false, bce_only = false;
+    int bve_heap = 0, bve_cgrow = 0, bve_cgrow_t = 1000, bve_heap_updates = 1;
+    int threads = 0;
+    bool stats = false;
+    double gc_frac = 0.20;
+    int device = 0;              // -cp3_gpu_device=N
+    // returns 1 known & applied, 0 unknown, -1 known but unsupported value on the GPU path
+    int parse(const char* opt);
+    void preset(const char* name);
+};
+
+struct Tech { int penalty = 0, peak = 0; bool modified = false; };
+
+struct Hit { uint32_t clause; int32_t lit; };
+
+// occurrence list: slice of one pooled array; grows by relocation to the pool end
+struct OccList { uint32_t off = 0, n = 0, cap = 0; };
+
+class Engine {
+public:
+    Engine();
+    ~Engine();
+    Options opt;
+
+    // --- Solver-side interface used by the CP* layer
+    void addLit(int dimacsLit);
+    void addStream(const int32_t* s, size_t n);
+    void freeze(int dimacsVar);
+    void preprocess();
+    bool okay() const { return ok; }
+    int nVars() const { return nvars; }
+    size_t output(int32_t* out, size_t cap) const;
+    size_t nTrail() const { return trail.size(); }
+    size_t nLiveClauses() const;
+    size_t nLiveLits() const;
+    size_t undoStack(int32_t* out, size_t cap) const;
+    int64_t stat(const char* name) const;
+    int litValue(int dimacsLit) const;
+    void extendModel(std::vector<uint8_t>& model) const;   // CoprocessorData::extendModel, CoprocessorTypes.h:1665
+    int setDistributed(int rank, int world, const void* id);
+
+private:
+    // ---------------- solver state
+    int nvars = 0; bool ok = true; int qhead = 0;
+    std::vector<uint8_t> assigns, frozen;
+    std::vector<int> trail;
+    std::vector<int32_t> pool;                       // literal pool (codes)
+    std::vector<uint32_t> cstart, csize; std::vector<uint8_t> cflag;
+    std::vector<uint32_t> clauses;                   // solver->clauses
+    double ca_size = 0, ca_wasted = 0;
+    int simpDB_assigns = -1; int64_t simpDB_props = 0;
+    std::vector<int> cur;
+    std::vector<std::vector<uint32_t>> ing_occ; bool ing_built = false;
+
+    // ---------------- CoprocessorData mirror
+    bool data_ready = false;
+    std::vector<OccList> occ; std::vector<uint32_t> occ_pool;
+    std::vector<int32_t> cnt; int numberOfCls = 0;
+    std::vector<uint32_t> stale;                     // deleted clauses still referenced from occ[l]
+    std::vector<uint32_t> subq, strq; std::vector<int32_t> undo;
+    std::vector<uint32_t> modTimer; uint32_t modStep = 0;
+    std::vector<uint32_t> ma; uint32_t ma_step = 0;
+
+    // ---------------- technique state
+    Tech t_sub, t_up, t_bve;
+    int64_t sub_steps = 0, str_steps = 0, sub_lim = 0, str_lim = 0; int limitIncreases = 0;
+    int subsumedClauses = 0, subsumedLiterals = 0, removedLiterals = 0;
+    int up_last = 0, up_removedClauses = 0, up_removedLiterals = 0;
+    uint32_t bve_modtime = 0; int64_t bve_steps = 0;
+    std::vector<int> heap, hidx;
+    int bve_removedClauses = 0, bve_removedLiterals = 0, bve_createdClauses = 0, bve_createdLiterals = 0,
+        bve_testedVars = 0, bve_anticipations = 0, bve_eliminatedVars = 0, bve_removedBC = 0, bve_skippedVars = 0,
+        bve_unitsEnqueued = 0, bve_foundGates = 0, bve_nInc = 0, bve_nDec = 0, bve_nKeep = 0, bve_totallyAdded = 0;
+    std::vector<int> pos_stats, neg_stats, touched;
+    struct OccUpd { uint32_t cr; int l; };
+    std::vector<OccUpd> occ_upd; std::vector<uint32_t> sub_occ_updates;
+    std::unordered_map<uint32_t, std::vector<int>> pend_rm;   // literals whose occ entry removal is pending
+
+    // ---------------- device replica + scan cache
+    cp3g* gpu = nullptr;
+    bool dev_uploaded = false;
+    std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
+    std::vector<uint8_t> shrunk_mark;
+    uint32_t scan_id = 0;                            // number of scans issued so far
+    std::vector<uint32_t> mod_stamp, ver;            // per clause: scan count at last edit, edit counter
+    struct Removal { uint32_t stamp; int lit; };
+    std::unordered_map<uint32_t, std::vector<Removal>> edit_log;          // literals removed per clause
+    struct CacheEnt { uint32_t ver, scan, hb, he; };
+    struct ScanCache { std::vector<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; void clear(); };
+    ScanCache c_sub, c_str;
+    std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
+    std::vector<cp3g_hit> hitbuf;
+    // BVE pair cache
+    std::vector<uint32_t> var_touch;
+    struct PairEnt { uint32_t touch; std::vector<uint32_t> pos, neg; std::vector<int16_t> sizes; std::vector<int32_t> units; bool valid = false; };
+    std::unordered_map<int, PairEnt> pair_cache;
+    int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
+    int64_t host_ns_commit = 0, host_ns_gpuwait = 0;
+
+    // ---------------- basics
+    inline int value(int x) const { uint8_t a = assigns[x >> 1]; return a == L_UNDEF ? L_UNDEF : (a ^ (x & 1)); }
+    inline int32_t* CL(uint32_t c) { return pool.data() + cstart[c]; }
+    inline const int32_t* CL(uint32_t c) const { return pool.data() + cstart[c]; }
+    inline int dcount(int v) const { return cnt[2 * v] + cnt[2 * v + 1]; }
+    void newVar();
+    uint32_t allocClause(const int* lits, int n);
+    void caFree(uint32_t c) { ca_wasted += 2 + csize[c]; }
+    void uncheckedEnqueue(int x);
+    int dataEnqueue(int x);
+    void addClauseIngest(std::vector<int>& ps);
+    bool ingestPropagate();
+    bool solverSimplify();
+    void initData();
+    void die(const char* msg) const;
+
+    // occurrence lists
+    inline uint32_t* LP(const OccList& l) { return occ_pool.data() + l.off; }
+    void occPush(int x, uint32_t c);
+    void occSwapRemove(int x, uint32_t i);            // list[i] = back; pop  (+ stale bookkeeping)
+    void occRelease(int x);
+    void setDeleted(uint32_t c);                      // mark + stale + device edit
+    void noteShrunk(uint32_t c, int removedLit);      // bookkeeping after a literal left clause c
+
+    // CoprocessorData bookkeeping (CoprocessorTypes.h:812-878,1243-1350,1615-1655,1815-1831)
+    void deletedVar(int v) { modTimer[v] = modStep; }
+    void removedClause(uint32_t c, bool useHeap, bool update, int ignore);
+    void removedLiteral(int x, int diff, bool useHeap, bool update, int ignore);
+    void dataAddClause(uint32_t c, bool useHeap);
+    bool removeClauseFrom(uint32_t c, int x);
+    void subInitClause(uint32_t c);
+    void addSubStrength(uint32_t c);
+    void extClause(uint32_t c, int x);
+    void extLit(int x);
+    void filterDeleted(std::vector<uint32_t>& a);
+    void checkGarbage();
+    void removePosSorted(uint32_t c, int pos);
+    void removePosUnsorted(uint32_t c, int pos);
+
+    // heap (riss/mtl/Heap.h)
+    bool heapLt(int x, int y) const { return opt.bve_heap == 0 ? dcount(x) < dcount(y) : dcount(x) > dcount(y); }
+    bool inHeap(int v) const { return v < (int)hidx.size() && hidx[v] >= 0; }
+    void heapUp(int i); void heapDown(int i); void heapInsert(int v); void heapUpdate(int v);
+    int heapRemoveMin(); void heapClear();
+
+    // techniques
+    static bool performSimplification(Tech& t) { if (t.penalty > 0) { --t.penalty; return false; } return true; }
+    static void unsuccessful(Tech& t) { t.peak += 1; t.penalty = t.peak; }
+    static void successful(Tech& t) { t.modified = true; t.peak = 0; }
+    int propagationProcess(bool sort, bool useHeap, int ignore);
+    bool hasToPropagate() const { return (int)trail.size() != qhead; }
+    void subsumptionWorker(bool useHeap, int ignore);
+    int strengtheningWorker(bool useHeap, int ignore);
+    void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
+    void updateOccurrences(bool useHeap, int ignore);
+    bool subsumptionProcess(bool doStrengthen, bool useHeap, int ignore);
+    void clearQueue(std::vector<uint32_t>& q, uint8_t flag);
+    bool findGates(int v, int& p_limit, int& n_limit);
+    int anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& resolvents);
+    void bveRemoveClauses(int x, int extLitOrNeg);
+    void bveRemoveBlocked(int x, const std::vector<int>& stats);
+    int resolveSet(int v, int p_limit, int n_limit);
+    void bveWorker();
+    void sequentiellBVE();
+    int bveProcess();
+    uint32_t nextModStep();
+    void addClausesToSubsumption(int x);
+
+    // device interaction
+    void ensureGpu();
+    void uploadAll();
+    void flushDevice();
+    // scan `ids` (clause indices, device content) and store the result in `cache`
+    void scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache);
+    const CacheEnt* cached(ScanCache& cache, uint32_t c) const;
+    bool subHitValid(uint32_t c, uint32_t d, uint32_t scan) const;
+    bool strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const;
+    const CacheEnt* strHits(uint32_t cr);             // cached or on-demand strengthening hits of cr
+    PairEnt& pairsFor(int v);
+    void touchClauseVars(uint32_t c);
+};
+
+} // namespace cp3

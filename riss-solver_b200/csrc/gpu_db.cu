@@ -1,0 +1,808 @@
+// gpu_db.cu - device-resident clause data base and the sm_100a kernels of the scan service (cp3g_* ABI).
+//
+// HBM layout (DESIGN.md "data layout"):
+//   lits[]     int32 literal pool, clause i = lits[hdr[i].start .. +size), sorted by literal code 2*var+sign
+//   hdr[]      16-byte clause header {start:u32, size:24|flags:8, sig:u64}  - one 128-bit load per candidate
+//   occ_off[]  u32 CSR offsets per literal code (2*nvars+1), occ_ent[] 16-byte entries {ref,size|flags,sig}
+//              in ascending clause index (= CoprocessorData::addClause order, CoprocessorTypes.h:812-833)
+//   ovf[]      clause indices appended after the last CSR build (BVE resolvents); scanned by every request
+//
+// Kernels (none uses tensor cores - there is no contraction on this path):
+//   k_sig_build   K1  64-bit literal signature per clause (new accelerating filter; never changes results)
+//   k_occ_*       K2  histogram -> exclusive scan -> scatter -> per-list sort
+//   k_scan<KIND>  K3/K4 request-driven signature filter + sorted-literal merge (Subsumption.cc:244-297,
+//                 1276-1521; Clause::ordered_subsumes SolverTypes.h:1003)
+//   k_bve_pairs   K5  resolvent size per (pos,neg) pair (BVE.h:248-299)
+//   k_bve_resolve K6  resolvent generation (BVE.h:208-242)
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <chrono>
+
+#include "../../include/cp3b200.h"
+#include "gpu_db.h"
+
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g->fail(#call, _e); return CP3G_ERR_CUDA; } } while (0)
+
+static constexpr uint32_t FLAG_DEL = 0x80000000u;
+static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
+static constexpr int SHORT_LIST = 48;
+
+struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
+struct __align__(16) OccEnt { uint32_t ref; uint32_t szfl; unsigned long long sig; };
+
+__host__ __device__ __forceinline__ unsigned long long lit_bit(int32_t x)
+{
+    const uint32_t v = ((uint32_t)x) >> 1;
+    const uint32_t h = (v * 0x9E3779B1u) >> 27;            // 5 bits from the variable
+    return 1ull << (2 * h + (x & 1));
+}
+__device__ __forceinline__ unsigned long long var_fold(unsigned long long s)
+{
+    return (s | (s >> 1)) & 0x5555555555555555ull;
+}
+
+// ------------------------------------------------------------------------------------------ K1
+__global__ void k_sig_build(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t first, uint32_t n)
+{
+    uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    ClauseHdr h = hdr[i];
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    unsigned long long s = 0;
+    for (uint32_t k = 0; k < sz; ++k) { s |= lit_bit(lits[h.start + k]); }
+    hdr[i].sig = s;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+__global__ void k_occ_count(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+                            uint32_t* __restrict__ cnt)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = hdr[i];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    for (uint32_t k = 0; k < sz; ++k) { atomicAdd(&cnt[lits[h.start + k]], 1u); }
+}
+
+// exclusive scan, three small kernels (tile = 1024 threads x 4 items)
+static constexpr int SCAN_T = 1024, SCAN_I = 4, SCAN_TILE = SCAN_T * SCAN_I;
+__global__ void k_scan_tiles(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n,
+                             uint32_t* __restrict__ tile_sum)
+{
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_I;
+    uint32_t v[SCAN_I], s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) { v[k] = (base + k < n) ? in[base + k] : 0u; s += v[k]; }
+    uint32_t inc = s;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) { inc += t; } }
+    if (lane == 31) { warp_tot[w] = inc; }
+    __syncthreads();
+    if (w == 0) {
+        uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { uint32_t u = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) { ti += u; } }
+        warp_tot[lane] = ti - t;
+        if (lane == 31) { tile_sum[blockIdx.x] = ti; }
+    }
+    __syncthreads();
+    uint32_t ex = warp_tot[w] + inc - s;
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) { if (base + k < n) { out[base + k] = ex; } ex += v[k]; }
+}
+__global__ void k_scan_sums(uint32_t* __restrict__ tile_sum, uint32_t ntiles, uint32_t* __restrict__ total)
+{
+    // single block; sequential over chunks of blockDim
+    __shared__ uint32_t sh[1024];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) { carry = 0; }
+    __syncthreads();
+    for (uint32_t base = 0; base < ntiles; base += blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        uint32_t v = i < ntiles ? tile_sum[i] : 0u;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+            uint32_t t = threadIdx.x >= d ? sh[threadIdx.x - d] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < ntiles) { tile_sum[i] = carry + sh[threadIdx.x] - v; }
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) { carry += sh[threadIdx.x]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *total = carry; }
+}
+__global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_t* __restrict__ tile_sum)
+{
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_I;
+    const uint32_t add = tile_sum[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_I; ++k) { if (base + k < n) { out[base + k] += add; } }
+}
+
+__global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, OccEnt* __restrict__ ent)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = hdr[i];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    OccEnt e; e.ref = i; e.szfl = h.szfl; e.sig = h.sig;
+    for (uint32_t k = 0; k < sz; ++k) {
+        const int32_t x = lits[h.start + k];
+        const uint32_t p = atomicAdd(&cursor[x], 1u);
+        ent[off[x] + p] = e;
+    }
+}
+// scatter order is nondeterministic; the reference order is ascending clause index -> sort every list
+__global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, OccEnt* __restrict__ ent,
+                                 uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
+{
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nlit) { return; }
+    const uint32_t b = off[x], e = off[x + 1], len = e - b;
+    if (len < 2) { return; }
+    if (len > SHORT_LIST) { long_lits[atomicAdd(nlong, 1u)] = x; return; }
+    for (uint32_t i = b + 1; i < e; ++i) {
+        OccEnt key = ent[i];
+        uint32_t j = i;
+        while (j > b && ent[j - 1].ref > key.ref) { ent[j] = ent[j - 1]; --j; }
+        ent[j] = key;
+    }
+}
+// one block per long list: normalised bitonic sort on ref in global memory.  Every compare-exchange is
+// ascending (i < l keeps the smaller ref at i), so the virtual +inf padding above len never has to move
+// and pairs that touch it are simply skipped.
+__device__ __forceinline__ void ce_asc(OccEnt* a, uint32_t i, uint32_t l)
+{
+    OccEnt ei = a[i], el = a[l];
+    if (ei.ref > el.ref) { a[i] = el; a[l] = ei; }
+}
+__global__ void k_occ_sort_long(const uint32_t* __restrict__ off, const uint32_t* __restrict__ long_lits,
+                                OccEnt* __restrict__ ent)
+{
+    const uint32_t x = long_lits[blockIdx.x];
+    OccEnt* a = ent + off[x];
+    const uint32_t len = off[x + 1] - off[x];
+    uint32_t p2 = 1; while (p2 < len) { p2 <<= 1; }
+    for (uint32_t k = 2; k <= p2; k <<= 1) {
+        for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+            const uint32_t l = i ^ (k - 1);
+            if (l > i && l < len) { ce_asc(a, i, l); }
+        }
+        __syncthreads();
+        for (uint32_t j = k >> 2; j > 0; j >>= 1) {
+            for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
+                const uint32_t l = i ^ j;
+                if (l > i && l < len) { ce_asc(a, i, l); }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ K3 / K4
+// returns true if S (sn literals) is a subset of D (dn literals); both sorted
+__device__ __forceinline__ bool merge_subset(const int32_t* __restrict__ S, uint32_t sn,
+                                             const int32_t* __restrict__ D, uint32_t dn)
+{
+    uint32_t i = 0, j = 0;
+    while (i < sn && j < dn) {
+        const int32_t a = S[i], b = D[j];
+        if (a == b) { ++i; ++j; }
+        else if (b < a) { ++j; }
+        else { return false; }
+    }
+    return i == sn;
+}
+// self-subsuming resolution test: exactly one literal of S occurs complemented in D, the rest is in D.
+// returns the complemented literal of D, or -1
+__device__ __forceinline__ int32_t merge_one_flip(const int32_t* __restrict__ S, uint32_t sn,
+                                                  const int32_t* __restrict__ D, uint32_t dn)
+{
+    uint32_t i = 0, j = 0; int32_t flipped = -1;
+    while (i < sn && j < dn) {
+        const int32_t a = S[i], b = D[j];
+        if (a == b) { ++i; ++j; }
+        else if (a == (b ^ 1)) { if (flipped >= 0) { return -1; } flipped = b; ++i; ++j; }
+        else if (a < b) { return -1; }
+        else { ++j; }
+    }
+    return (i == sn) ? flipped : -1;
+}
+
+template <int KIND>
+__device__ __forceinline__ void test_candidate(uint32_t ref, uint32_t szfl, unsigned long long dsig, uint32_t me,
+                                               const int32_t* __restrict__ S, uint32_t sn, unsigned long long ssig,
+                                               int32_t need_flip /* -1: any */, int32_t forbid_flip /* -1: none */,
+                                               const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+                                               uint32_t r, cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout)
+{
+    if (ref == me) { return; }
+    // the occ entry caches size/sig from build time; the header is authoritative for later edits, so a
+    // cheap pre-filter on the entry is only valid for properties that are monotone: clauses only shrink
+    // (sig bits only disappear, size only decreases) -> entry sig/size are supersets/upper bounds.
+    const uint32_t esz = szfl & SIZE_MASK;
+    if (esz < sn) { return; }
+    const unsigned long long miss = ssig & ~dsig;
+    if (KIND == CP3G_SUBSUME) { if (miss) { return; } }
+    else { if (miss & (miss - 1)) { return; } if (var_fold(ssig) & ~var_fold(dsig)) { return; } }
+    const ClauseHdr h = hdr[ref];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t dn = h.szfl & SIZE_MASK;
+    if (dn < sn) { return; }
+    const int32_t* D = lits + h.start;
+    if (KIND == CP3G_SUBSUME) {
+        if ((ssig & ~h.sig) == 0 && merge_subset(S, sn, D, dn)) {
+            const uint32_t p = atomicAdd(nout, 1u);
+            if (p < cap) { out[p].req = r; out[p].clause = ref; out[p].lit = -1; }
+        }
+    } else {
+        const int32_t f = merge_one_flip(S, sn, D, dn);
+        if (f >= 0 && (need_flip < 0 || f == need_flip) && f != forbid_flip) {
+            const uint32_t p = atomicAdd(nout, 1u);
+            if (p < cap) { out[p].req = r; out[p].clause = ref; out[p].lit = f; }
+        }
+    }
+}
+
+// One warp per request.  Lanes stride over the chosen occurrence list(s); the signature filter rejects
+// almost every candidate from the 16-byte entry alone, so clause literals are fetched only for survivors.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+        const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent,
+        const uint32_t* __restrict__ ovf, uint32_t novf,
+        uint32_t req_begin, uint32_t req_end, const uint32_t* __restrict__ self,
+        const uint32_t* __restrict__ req_off, const int32_t* __restrict__ req_lits,
+        cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
+        unsigned long long* __restrict__ checks)
+{
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = req_begin + warp;
+    if (r >= req_end) { return; }
+    const uint32_t me = self[r];
+    const int32_t* S; uint32_t sn;
+    if (req_lits != nullptr) { S = req_lits + req_off[r]; sn = req_off[r + 1] - req_off[r]; }
+    else {
+        const ClauseHdr h = hdr[me];
+        if (h.szfl & FLAG_DEL) { return; }
+        S = lits + h.start; sn = h.szfl & SIZE_MASK;
+    }
+    if (sn == 0) { return; }
+    // signature of the request and the cheapest list: lanes take literals round robin
+    unsigned long long ssig = 0; uint32_t best_len = 0xffffffffu; uint32_t best_idx = 0;
+    for (uint32_t k = lane; k < sn; k += 32) {
+        const int32_t x = S[k];
+        ssig |= lit_bit(x);
+        uint32_t len = occ_off[x + 1] - occ_off[x];
+        if (KIND == CP3G_STRENGTHEN) { len += occ_off[(x ^ 1) + 1] - occ_off[x ^ 1]; }
+        if (len < best_len) { best_len = len; best_idx = k; }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        ssig |= __shfl_xor_sync(0xffffffffu, ssig, d);
+        const uint32_t ol = __shfl_xor_sync(0xffffffffu, best_len, d);
+        const uint32_t oi = __shfl_xor_sync(0xffffffffu, best_idx, d);
+        if (ol < best_len || (ol == best_len && oi < best_idx)) { best_len = ol; best_idx = oi; }
+    }
+    const int32_t x = S[best_idx];
+    unsigned long long nchk = 0;
+    {
+        const uint32_t b = occ_off[x], e = occ_off[x + 1];
+        for (uint32_t i = b + lane; i < e; i += 32) {
+            const OccEnt en = occ_ent[i];
+            nchk += (en.ref != me);
+            // a stale entry could flip on x itself; that hit belongs to the occ(~x) pass below
+            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, -1, x ^ 1, hdr, lits, r, out, cap, nout);
+        }
+    }
+    if (KIND == CP3G_STRENGTHEN) {
+        const int32_t nx = x ^ 1;
+        const uint32_t b = occ_off[nx], e = occ_off[nx + 1];
+        for (uint32_t i = b + lane; i < e; i += 32) {
+            const OccEnt en = occ_ent[i];
+            nchk += 1;
+            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, out, cap, nout);
+        }
+    }
+    // clauses younger than the CSR (resolvents): brute force, they are few
+    for (uint32_t i = lane; i < novf; i += 32) {
+        const uint32_t ref = ovf[i];
+        const ClauseHdr h = hdr[ref];
+        nchk += (ref != me);
+        test_candidate<KIND>(ref, h.szfl, h.sig, me, S, sn, ssig, -1, -1, hdr, lits, r, out, cap, nout);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); }
+    if (lane == 0 && nchk) { atomicAdd(checks, nchk); }
+}
+
+// ------------------------------------------------------------------------------------------ K5 / K6
+// resolvent size of (P containing +v, N containing -v), -1 for a tautology: merged walk that drops the
+// pivot, counts distinct literals and stops at the first complementary neighbour pair (BVE.h:248-299)
+__device__ __forceinline__ int resolvent_size(const int32_t* __restrict__ P, uint32_t pn,
+                                              const int32_t* __restrict__ N, uint32_t nn, int32_t pv)
+{
+    const int32_t nv = pv ^ 1;
+    uint32_t i = 0, j = 0; int r = 0; int32_t prev = -2;
+    while (i < pn || j < nn) {
+        int32_t c;
+        if (i < pn && P[i] == pv) { ++i; continue; }
+        if (j < nn && N[j] == nv) { ++j; continue; }
+        if (j >= nn || (i < pn && P[i] < N[j])) { c = P[i++]; } else { c = N[j++]; }
+        if (c == prev) { continue; }
+        if (c == (prev ^ 1) && prev != -2) { return -1; }
+        prev = c; ++r;
+    }
+    return r;
+}
+__global__ void k_bve_pairs(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t nv,
+                            const uint32_t* __restrict__ vars, const uint32_t* __restrict__ p_off,
+                            const uint32_t* __restrict__ p_refs, const uint32_t* __restrict__ n_off,
+                            const uint32_t* __restrict__ n_refs, const unsigned long long* __restrict__ pair_off,
+                            int16_t* __restrict__ sizes)
+{
+    // one warp per variable, lanes over the pos x neg pairs
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warp >= nv) { return; }
+    const uint32_t pb = p_off[warp], np = p_off[warp + 1] - pb;
+    const uint32_t nb = n_off[warp], nn = n_off[warp + 1] - nb;
+    const int32_t pv = (int32_t)(vars[warp] << 1);
+    const unsigned long long base = pair_off[warp];
+    const uint32_t total = np * nn;
+    for (uint32_t t = lane; t < total; t += 32) {
+        const uint32_t a = t / nn, b = t - a * nn;
+        const ClauseHdr hp = hdr[p_refs[pb + a]], hn = hdr[n_refs[nb + b]];
+        int s;
+        if ((hp.szfl | hn.szfl) & FLAG_DEL) { s = -2; }           // deleted parent: caller skips the pair
+        else {
+            s = resolvent_size(lits + hp.start, hp.szfl & SIZE_MASK, lits + hn.start, hn.szfl & SIZE_MASK, pv);
+        }
+        sizes[base + t] = (int16_t)s;
+    }
+}
+__global__ void k_bve_resolve(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t npairs,
+                              const uint32_t* __restrict__ vars, const uint32_t* __restrict__ p_refs,
+                              const uint32_t* __restrict__ n_refs, const unsigned long long* __restrict__ out_off,
+                              int32_t* __restrict__ out_lits)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= npairs) { return; }
+    const ClauseHdr hp = hdr[p_refs[t]], hn = hdr[n_refs[t]];
+    const int32_t* P = lits + hp.start; const int32_t* N = lits + hn.start;
+    const uint32_t pn = hp.szfl & SIZE_MASK, nn = hn.szfl & SIZE_MASK;
+    const int32_t pv = (int32_t)(vars[t] << 1), nv = pv ^ 1;
+    int32_t* o = out_lits + out_off[t];
+    const unsigned long long room = out_off[t + 1] - out_off[t];
+    uint32_t i = 0, j = 0; unsigned long long r = 0; int32_t prev = -2;
+    while (i < pn || j < nn) {
+        int32_t c;
+        if (i < pn && P[i] == pv) { ++i; continue; }
+        if (j < nn && N[j] == nv) { ++j; continue; }
+        if (j >= nn || (i < pn && P[i] < N[j])) { c = P[i++]; } else { c = N[j++]; }
+        if (c == prev) { continue; }
+        prev = c;
+        if (r < room) { o[r] = c; }
+        ++r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ edits
+__global__ void k_set_deleted(ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ ids, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { hdr[ids[i]].szfl |= FLAG_DEL; }
+}
+__global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits, const uint32_t* __restrict__ ids,
+                         const uint32_t* __restrict__ nstart, const uint32_t* __restrict__ nsize,
+                         const int32_t* __restrict__ nlits, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    ClauseHdr h = hdr[ids[i]];
+    unsigned long long s = 0;
+    for (uint32_t k = 0; k < nsize[i]; ++k) { const int32_t x = nlits[nstart[i] + k]; lits[h.start + k] = x; s |= lit_bit(x); }
+    h.szfl = (h.szfl & ~SIZE_MASK) | nsize[i];
+    h.sig = s;
+    hdr[ids[i]] = h;
+}
+
+// ------------------------------------------------------------------------------------------ host side
+struct cp3g {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
+    size_t nlits = 0;
+    DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
+    DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
+    DevBuf<OccEnt> occ_ent;
+    DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
+    DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
+    DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
+    std::vector<uint32_t> ovf_host;
+    uint32_t total_occ = 0;
+    int rank = 0, world = 1; void* nccl = nullptr;
+    int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void fail(const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); fprintf(stderr, "cp3b200: CUDA error %s\n", err.c_str()); }
+};
+
+template <class T> int DevBuf<T>::reserve(size_t n, bool keep, cudaStream_t st)
+{
+    if (n <= cap) { return 0; }
+    size_t ncap = std::max(n, cap + cap / 2 + 64);
+    T* np = nullptr;
+    cudaError_t e = cudaMalloc((void**)&np, ncap * sizeof(T));
+    if (e != cudaSuccess) { return (int)e; }
+    if (keep && p && used) { cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); }
+    if (p) { cudaFree(p); }
+    p = np; cap = ncap;
+    return 0;
+}
+template <class T> void DevBuf<T>::release() { if (p) { cudaFree(p); } p = nullptr; cap = used = 0; }
+
+#define RESERVE(buf, n, keep) do { int _r = (buf).reserve((n), (keep), g->stream); if (_r) { g->fail("cudaMalloc", (cudaError_t)_r); return CP3G_ERR_CUDA; } } while (0)
+
+static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+struct KTimer {
+    cp3g* g;
+    explicit KTimer(cp3g* g_) : g(g_) { cudaEventRecord(g->ev0, g->stream); }
+    void stop() { cudaEventRecord(g->ev1, g->stream); }
+    void collect() { float ms = 0; if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) { g->kernel_ns += (int64_t)(ms * 1e6); } }
+};
+
+extern "C" {
+
+int cp3g_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+cp3g* cp3g_create(int device)
+{
+    int n = cp3g_device_count();
+    if (device < 0 || device >= n) {
+        fprintf(stderr, "cp3b200: no usable CUDA device (%d visible, asked for %d) - there is no CPU fallback\n", n, device);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { return nullptr; }
+    cp3g* g = new cp3g();
+    g->device = device;
+    if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return nullptr; }
+    cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
+    if (g->counters.reserve(16, false, g->stream)) { delete g; return nullptr; }
+    return g;
+}
+
+void cp3g_destroy(cp3g* g)
+{
+    if (!g) { return; }
+    cudaSetDevice(g->device);
+    cudaStreamSynchronize(g->stream);
+    g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
+    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release();
+    g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
+    g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
+    g->bs0.release(); g->bl0.release();
+    cp3g_nccl_free(g->nccl);
+    cudaEventDestroy(g->ev0); cudaEventDestroy(g->ev1);
+    cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+const char* cp3g_last_error(const cp3g* g) { return g ? g->err.c_str() : "no device"; }
+
+int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t nlits,
+                const uint32_t* start, const uint32_t* size, const uint8_t* flags)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    g->nvars = nvars; g->ncl = ncl; g->nlits = nlits; g->ncl_csr = 0; g->ovf_host.clear();
+    RESERVE(g->lits, nlits + nlits / 4 + 1024, false);
+    RESERVE(g->hdr, (size_t)ncl + ncl / 4 + 1024, false);
+    CK(cudaMemcpyAsync(g->lits.p, lits, nlits * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    std::vector<ClauseHdr> h(ncl);
+    for (uint32_t i = 0; i < ncl; ++i) {
+        h[i].start = start[i];
+        h[i].szfl = (size[i] & SIZE_MASK) | ((flags && (flags[i] & 1)) ? FLAG_DEL : 0u);
+        h[i].sig = 0;
+    }
+    CK(cudaMemcpyAsync(g->hdr.p, h.data(), (size_t)ncl * sizeof(ClauseHdr), cudaMemcpyHostToDevice, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->lits.used = nlits; g->hdr.used = ncl;
+    g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * sizeof(ClauseHdr));
+    return CP3G_OK;
+}
+
+static int build_csr(cp3g* g)
+{
+    const uint32_t nlit = 2 * g->nvars;
+    RESERVE(g->occ_off, (size_t)nlit + 2, false);
+    RESERVE(g->occ_tmp, (size_t)nlit + 2, false);
+    const uint32_t ntiles = (nlit + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    RESERVE(g->tile_sum, (size_t)ntiles + 1, false);
+    RESERVE(g->long_lits, (size_t)nlit + 1, false);
+    CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
+    CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
+    if (g->ncl) {
+        k_occ_count<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_tmp.p);
+    }
+    k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(g->occ_tmp.p, g->occ_off.p, nlit + 1, g->tile_sum.p);
+    k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 2);
+    k_scan_add<<<ntiles, SCAN_T, 0, g->stream>>>(g->occ_off.p, nlit + 1, g->tile_sum.p);
+    g->launches += 4;
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, g->counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->total_occ = total;
+    RESERVE(g->occ_ent, (size_t)total + 1, false);
+    CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
+    if (g->ncl) {
+        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->occ_ent.p);
+        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->occ_ent.p, g->long_lits.p, g->counters.p + 1);
+        g->launches += 2;
+    }
+    uint32_t nlong = 0;
+    CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    if (nlong) {
+        k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->occ_ent.p);
+        g->launches += 1;
+    }
+    CK(cudaGetLastError());
+    g->ncl_csr = g->ncl;
+    g->ovf_host.clear();
+    return CP3G_OK;
+}
+
+int cp3g_build(cp3g* g)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    KTimer t(g);
+    if (g->ncl) { k_sig_build<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, 0, g->ncl); g->launches++; }
+    int r = build_csr(g);
+    t.stop();
+    CK(cudaStreamSynchronize(g->stream));
+    t.collect();
+    return r;
+}
+
+int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    const uint32_t nlit = 2 * g->nvars;
+    CK(cudaMemcpyAsync(off, g->occ_off.p, ((size_t)nlit + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->d2h += (int64_t)(((size_t)nlit + 1) * sizeof(uint32_t));
+    if (refs && g->total_occ) {
+        // strided copy of the 4-byte ref out of the 16-byte entries
+        CK(cudaMemcpy2DAsync(refs, sizeof(uint32_t), g->occ_ent.p, sizeof(OccEnt), sizeof(uint32_t), g->total_occ,
+                             cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        g->d2h += (int64_t)g->total_occ * 4;
+    }
+    return CP3G_OK;
+}
+
+int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (!n) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    RESERVE(g->scratch_u32, n, false);
+    CK(cudaMemcpyAsync(g->scratch_u32.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
+    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->scratch_u32.p, n);
+    CK(cudaStreamSynchronize(g->stream));
+    g->launches++; g->h2d += (int64_t)n * 4;
+    return CP3G_OK;
+}
+
+int cp3g_shrink(cp3g* g, uint32_t n, const uint32_t* ids, const uint32_t* nstart, const uint32_t* nsize,
+                const int32_t* lits, size_t nlits)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (!n) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    RESERVE(g->bu0, n, false); RESERVE(g->bu1, n, false); RESERVE(g->bu2, n, false); RESERVE(g->bl0, nlits + 1, false);
+    CK(cudaMemcpyAsync(g->bu0.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu1.p, nstart, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu2.p, nsize, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bl0.p, lits, nlits * 4, cudaMemcpyHostToDevice, g->stream));
+    k_shrink<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->bu0.p, g->bu1.p, g->bu2.p, g->bl0.p, n);
+    CK(cudaStreamSynchronize(g->stream));
+    g->launches++; g->h2d += (int64_t)n * 12 + (int64_t)nlits * 4;
+    return CP3G_OK;
+}
+
+int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, size_t nlits)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (!n) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    RESERVE(g->lits, g->nlits + nlits, true);
+    RESERVE(g->hdr, (size_t)g->ncl + n, true);
+    std::vector<ClauseHdr> h(n);
+    size_t pos = g->nlits, src = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        h[i].start = (uint32_t)pos; h[i].szfl = size[i] & SIZE_MASK;
+        unsigned long long s = 0;
+        for (uint32_t k = 0; k < size[i]; ++k) { s |= lit_bit(lits[src + k]); }
+        h[i].sig = s;
+        pos += size[i]; src += size[i];
+        g->ovf_host.push_back(g->ncl + i);
+    }
+    CK(cudaMemcpyAsync(g->lits.p + g->nlits, lits, nlits * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->hdr.p + g->ncl, h.data(), (size_t)n * sizeof(ClauseHdr), cudaMemcpyHostToDevice, g->stream));
+    RESERVE(g->ovf, g->ovf_host.size(), false);
+    CK(cudaMemcpyAsync(g->ovf.p, g->ovf_host.data(), g->ovf_host.size() * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->nlits += nlits; g->ncl += n; g->lits.used = g->nlits; g->hdr.used = g->ncl;
+    g->h2d += (int64_t)(nlits * 4 + (size_t)n * sizeof(ClauseHdr) + g->ovf_host.size() * 4);
+    // many young clauses make the brute-force part of k_scan expensive: fold them into the CSR
+    if (g->ovf_host.size() > 2048) { return build_csr(g); }
+    return CP3G_OK;
+}
+
+int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint32_t* req_off,
+              const int32_t* req_lits, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (nout) { *nout = 0; }
+    if (!nreq) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    RESERVE(g->req_self, nreq, false);
+    CK(cudaMemcpyAsync(g->req_self.p, self, (size_t)nreq * 4, cudaMemcpyHostToDevice, g->stream));
+    g->h2d += (int64_t)nreq * 4;
+    size_t nl = 0;
+    if (req_lits) {
+        nl = req_off[nreq];
+        RESERVE(g->req_off, (size_t)nreq + 1, false);
+        RESERVE(g->req_lits, nl + 1, false);
+        CK(cudaMemcpyAsync(g->req_off.p, req_off, ((size_t)nreq + 1) * 4, cudaMemcpyHostToDevice, g->stream));
+        CK(cudaMemcpyAsync(g->req_lits.p, req_lits, nl * 4, cudaMemcpyHostToDevice, g->stream));
+        g->h2d += (int64_t)(((size_t)nreq + 1) * 4 + nl * 4);
+    }
+    // contiguous request range of this rank (multi-GPU: results are all-gathered below)
+    uint32_t rb = 0, re = nreq;
+    if (g->world > 1) {
+        const uint64_t per = ((uint64_t)nreq + g->world - 1) / g->world;
+        rb = (uint32_t)std::min<uint64_t>(nreq, per * g->rank);
+        re = (uint32_t)std::min<uint64_t>(nreq, per * (g->rank + 1));
+    }
+    RESERVE(g->hits, (size_t)cap + 1, false);
+    CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
+    unsigned long long* dchecks = (unsigned long long*)(g->counters.p + 4);
+    KTimer t(g);
+    if (re > rb) {
+        const unsigned blocks = grid_for((size_t)(re - rb) * 32, 256);
+        const int32_t* rl = req_lits ? g->req_lits.p : nullptr;
+        if (kind == CP3G_SUBSUME) {
+            k_scan<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ovf.p,
+                (uint32_t)g->ovf_host.size(), rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+        } else {
+            k_scan<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ovf.p,
+                (uint32_t)g->ovf_host.size(), rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+        }
+        g->launches++;
+    }
+    t.stop();
+    uint32_t cnt[8];
+    CK(cudaMemcpyAsync(cnt, g->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    t.collect();
+    uint32_t n = cnt[0];
+    uint64_t chk; memcpy(&chk, &cnt[4], 8);
+    g->scan_requests += (re - rb); g->scan_checks += (int64_t)chk;
+    if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
+    if (g->world > 1) {
+        int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
+        if (rr != CP3G_OK) { return rr; }
+    } else if (n) {
+        CK(cudaMemcpyAsync(out, g->hits.p, (size_t)n * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+    }
+    g->d2h += (int64_t)n * (int64_t)sizeof(cp3g_hit) + 32;
+    if (nout) { *nout = n; }
+    if (checks) { *checks = chk; }
+    return CP3G_OK;
+}
+
+int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
+                   const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* pair_off, int16_t* sizes)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (!nv) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    const size_t np = p_off[nv], nn = n_off[nv]; const uint64_t total = pair_off[nv];
+    RESERVE(g->bu0, nv, false); RESERVE(g->bu1, (size_t)nv + 1, false); RESERVE(g->bu2, np + 1, false);
+    RESERVE(g->bu3, (size_t)nv + 1, false); RESERVE(g->bu4, nn + 1, false); RESERVE(g->bq0, (size_t)nv + 1, false);
+    RESERVE(g->bs0, total + 1, false);
+    CK(cudaMemcpyAsync(g->bu0.p, vars, (size_t)nv * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu1.p, p_off, ((size_t)nv + 1) * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu2.p, p_refs, np * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu3.p, n_off, ((size_t)nv + 1) * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu4.p, n_refs, nn * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bq0.p, pair_off, ((size_t)nv + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    KTimer t(g);
+    k_bve_pairs<<<grid_for((size_t)nv * 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, nv, g->bu0.p, g->bu1.p, g->bu2.p,
+            g->bu3.p, g->bu4.p, g->bq0.p, g->bs0.p);
+    t.stop();
+    CK(cudaMemcpyAsync(sizes, g->bs0.p, total * sizeof(int16_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    t.collect();
+    g->launches++; g->h2d += (int64_t)(nv * 20 + (np + nn) * 4); g->d2h += (int64_t)total * 2;
+    return CP3G_OK;
+}
+
+int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs, const uint32_t* n_refs,
+                     const uint64_t* out_off, int32_t* out_lits, size_t nlits)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (!npairs) { return CP3G_OK; }
+    cudaSetDevice(g->device);
+    RESERVE(g->bu0, npairs, false); RESERVE(g->bu2, npairs, false); RESERVE(g->bu4, npairs, false);
+    RESERVE(g->bq0, (size_t)npairs + 1, false); RESERVE(g->bl0, nlits + 1, false);
+    CK(cudaMemcpyAsync(g->bu0.p, vars, (size_t)npairs * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu2.p, p_refs, (size_t)npairs * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bu4.p, n_refs, (size_t)npairs * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->bq0.p, out_off, ((size_t)npairs + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    KTimer t(g);
+    k_bve_resolve<<<grid_for(npairs, 128), 128, 0, g->stream>>>(g->hdr.p, g->lits.p, npairs, g->bu0.p, g->bu2.p, g->bu4.p,
+            g->bq0.p, g->bl0.p);
+    t.stop();
+    CK(cudaMemcpyAsync(out_lits, g->bl0.p, nlits * 4, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    t.collect();
+    g->launches++; g->h2d += (int64_t)npairs * 20; g->d2h += (int64_t)nlits * 4;
+    return CP3G_OK;
+}
+
+int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    if (world <= 1) { g->rank = 0; g->world = 1; return CP3G_OK; }
+    void* c = cp3g_nccl_create(rank, world, id128);
+    if (!c) { g->err = "ncclCommInitRank failed"; return CP3G_ERR_CUDA; }
+    g->nccl = c; g->rank = rank; g->world = world;
+    return CP3G_OK;
+}
+
+int64_t cp3g_counter(const cp3g* g, const char* name)
+{
+    if (!g) { return -1; }
+    if (!strcmp(name, "launches")) { return g->launches; }
+    if (!strcmp(name, "kernel_ns")) { return g->kernel_ns; }
+    if (!strcmp(name, "h2d_bytes")) { return g->h2d; }
+    if (!strcmp(name, "d2h_bytes")) { return g->d2h; }
+    if (!strcmp(name, "scan_requests")) { return g->scan_requests; }
+    if (!strcmp(name, "scan_checks")) { return g->scan_checks; }
+    if (!strcmp(name, "nclauses")) { return g->ncl; }
+    if (!strcmp(name, "total_occ")) { return g->total_occ; }
+    return -1;
+}
+
+} // extern "C"

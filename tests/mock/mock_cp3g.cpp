@@ -1,0 +1,169 @@
+// mock_cp3g.cpp - TEST INFRASTRUCTURE ONLY.  A CPU stand-in for the cp3g_* scan service so that the host
+// engine's ordered-commit logic (riss-solver_b200/csrc/engine.cpp) can be differential-tested against the
+// oracle on machines without a GPU (`pytest -m "not gpu"`).  It is compiled into tests/_build/
+// libcp3b200_mock.so together with engine.cpp and capi.cpp; the product library libcp3b200.so never
+// contains it and has no CPU path.  The mock answers exactly what the kernels answer (sets of hits).
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/cp3b200.h"
+
+struct cp3g {
+    uint32_t nvars = 0;
+    std::vector<std::vector<int32_t>> cl; std::vector<uint8_t> del;
+    std::vector<std::vector<uint32_t>> occ;
+    int64_t launches = 0, requests = 0, checks = 0;
+    std::string err;
+};
+
+static bool subset(const std::vector<int32_t>& s, const std::vector<int32_t>& d)
+{
+    size_t i = 0, j = 0;
+    while (i < s.size() && j < d.size()) { if (s[i] == d[j]) { ++i; ++j; } else if (d[j] < s[i]) { ++j; } else { return false; } }
+    return i == s.size();
+}
+static int32_t one_flip(const std::vector<int32_t>& s, const std::vector<int32_t>& d)
+{
+    size_t i = 0, j = 0; int32_t f = -1;
+    while (i < s.size() && j < d.size()) {
+        if (s[i] == d[j]) { ++i; ++j; }
+        else if (s[i] == (d[j] ^ 1)) { if (f >= 0) { return -1; } f = d[j]; ++i; ++j; }
+        else if (s[i] < d[j]) { return -1; }
+        else { ++j; }
+    }
+    return i == s.size() ? f : -1;
+}
+static int res_size(const std::vector<int32_t>& P, const std::vector<int32_t>& N, int32_t pv, std::vector<int32_t>* out)
+{
+    const int32_t nv = pv ^ 1; size_t i = 0, j = 0; int r = 0; int32_t prev = -2; bool taut = false;
+    while (i < P.size() || j < N.size()) {
+        int32_t c;
+        if (i < P.size() && P[i] == pv) { ++i; continue; }
+        if (j < N.size() && N[j] == nv) { ++j; continue; }
+        if (j >= N.size() || (i < P.size() && P[i] < N[j])) { c = P[i++]; } else { c = N[j++]; }
+        if (c == prev) { continue; }
+        if (prev != -2 && c == (prev ^ 1)) { taut = true; if (!out) { return -1; } }
+        prev = c; ++r; if (out) { out->push_back(c); }
+    }
+    return taut ? -1 : r;
+}
+
+extern "C" {
+int cp3g_device_count(void) { return 1; }
+cp3g* cp3g_create(int) { return new cp3g(); }
+void cp3g_destroy(cp3g* g) { delete g; }
+const char* cp3g_last_error(const cp3g* g) { return g ? g->err.c_str() : ""; }
+int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t, const uint32_t* start,
+                const uint32_t* size, const uint8_t* flags)
+{
+    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0);
+    for (uint32_t i = 0; i < ncl; ++i) { g->cl[i].assign(lits + start[i], lits + start[i] + size[i]); g->del[i] = flags ? (flags[i] & 1) : 0; }
+    return CP3G_OK;
+}
+int cp3g_build(cp3g* g)
+{
+    g->occ.assign(2 * (size_t)g->nvars, {});
+    for (uint32_t i = 0; i < g->cl.size(); ++i) { if (!g->del[i]) { for (int32_t x : g->cl[i]) { g->occ[x].push_back(i); } } }
+    g->launches += 6;
+    return CP3G_OK;
+}
+int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
+{
+    uint32_t o = 0;
+    for (size_t x = 0; x < g->occ.size(); ++x) { off[x] = o; if (refs) { std::copy(g->occ[x].begin(), g->occ[x].end(), refs + o); } o += (uint32_t)g->occ[x].size(); }
+    off[g->occ.size()] = o;
+    return CP3G_OK;
+}
+int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids) { for (uint32_t i = 0; i < n; ++i) { g->del[ids[i]] = 1; } return CP3G_OK; }
+int cp3g_shrink(cp3g* g, uint32_t n, const uint32_t* ids, const uint32_t* st, const uint32_t* sz, const int32_t* lits, size_t)
+{
+    for (uint32_t i = 0; i < n; ++i) { g->cl[ids[i]].assign(lits + st[i], lits + st[i] + sz[i]); }
+    return CP3G_OK;
+}
+int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, size_t)
+{
+    size_t p = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint32_t id = (uint32_t)g->cl.size();
+        g->cl.emplace_back(lits + p, lits + p + size[i]); g->del.push_back(0);
+        for (int32_t x : g->cl.back()) { g->occ[x].push_back(id); }
+        p += size[i];
+    }
+    return CP3G_OK;
+}
+int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint32_t* req_off, const int32_t* req_lits,
+              cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks)
+{
+    uint32_t n = 0; uint64_t chk = 0;
+    g->launches++; g->requests += nreq;
+    for (uint32_t r = 0; r < nreq; ++r) {
+        std::vector<int32_t> S;
+        if (req_lits) { S.assign(req_lits + req_off[r], req_lits + req_off[r + 1]); }
+        else { if (g->del[self[r]]) { continue; } S = g->cl[self[r]]; }
+        if (S.empty()) { continue; }
+        // shortest list like the kernel
+        size_t best = 0; size_t bl = (size_t)-1;
+        for (size_t k = 0; k < S.size(); ++k) {
+            size_t len = g->occ[S[k]].size() + (kind == CP3G_STRENGTHEN ? g->occ[S[k] ^ 1].size() : 0);
+            if (len < bl) { bl = len; best = k; }
+        }
+        const int32_t x = S[best];
+        for (int pass = 0; pass < (kind == CP3G_STRENGTHEN ? 2 : 1); ++pass) {
+            const int32_t lx = pass == 0 ? x : (x ^ 1);
+            for (uint32_t d : g->occ[lx]) {
+                if (d == self[r]) { continue; }
+                ++chk;
+                if (g->del[d] || g->cl[d].size() < S.size()) { continue; }
+                if (kind == CP3G_SUBSUME) {
+                    if (subset(S, g->cl[d])) { if (n < cap) { out[n] = {r, d, -1}; } ++n; }
+                } else {
+                    int32_t f = one_flip(S, g->cl[d]);
+                    if (f >= 0 && (pass == 0 || f == lx)) {
+                        // pass 0 may see a stale entry that flips on x itself; the kernel reports it once
+                        if (pass == 0 && f == (x ^ 1)) { continue; }
+                        if (n < cap) { out[n] = {r, d, f}; } ++n;
+                    }
+                }
+            }
+        }
+    }
+    g->checks += (int64_t)chk;
+    if (nout) { *nout = n; }
+    if (checks) { *checks = chk; }
+    return n > cap ? CP3G_ERR_OVERFLOW : CP3G_OK;
+}
+int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
+                   const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* pair_off, int16_t* sizes)
+{
+    g->launches++;
+    for (uint32_t i = 0; i < nv; ++i) {
+        const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i];
+        for (uint32_t a = 0; a < np; ++a) for (uint32_t b = 0; b < nn; ++b) {
+            const uint32_t p = p_refs[p_off[i] + a], n = n_refs[n_off[i] + b];
+            int s = (g->del[p] || g->del[n]) ? -2 : res_size(g->cl[p], g->cl[n], (int32_t)(vars[i] << 1), nullptr);
+            sizes[pair_off[i] + (uint64_t)a * nn + b] = (int16_t)s;
+        }
+    }
+    return CP3G_OK;
+}
+int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs, const uint32_t* n_refs,
+                     const uint64_t* out_off, int32_t* out_lits, size_t)
+{
+    g->launches++;
+    for (uint32_t t = 0; t < npairs; ++t) {
+        std::vector<int32_t> r; res_size(g->cl[p_refs[t]], g->cl[n_refs[t]], (int32_t)(vars[t] << 1), &r);
+        for (size_t k = 0; k < r.size() && out_off[t] + k < out_off[t + 1]; ++k) { out_lits[out_off[t] + k] = r[k]; }
+    }
+    return CP3G_OK;
+}
+int cp3g_nccl_unique_id(void* out) { memset(out, 0, 128); return CP3G_OK; }
+int cp3g_nccl_init(cp3g*, int, int, const void*) { return CP3G_OK; }
+int64_t cp3g_counter(const cp3g* g, const char* name)
+{
+    if (!strcmp(name, "launches")) { return g->launches; }
+    if (!strcmp(name, "scan_requests")) { return g->requests; }
+    if (!strcmp(name, "scan_checks")) { return g->checks; }
+    return 0;
+}
+}

@@ -1,0 +1,184 @@
+"""GPU parity tests proper: the CUDA path (libcp3b200.so through its C ABI) against the CPU oracle on the same
+seeded inputs, against the committed golden vectors, and - at BASELINE sizes - through size-independent
+properties.  Everything here is bit-exact (integer / index work): ordered output stream, trail, undo stack and
+every Subsumption / BVE counter must be identical."""
+import os
+
+import numpy as np
+import pytest
+
+import riss_solver_b200 as rs
+from harness import Oracle, run_oracle, compare, Result, STAT_NAMES, ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(stream, opts) -> Result:
+    cp = rs.Coprocessor(opts)
+    cp.add_stream(stream)
+    cp.preprocess()
+    out = cp.output_stream(); nt = cp.output_units()
+    res = Result(int(cp.ok()), cp.n_vars(), out[0:2 * nt:2].copy(), out[2 * nt:].copy(), cp.undo(),
+                 {k: cp.stat(k) for k in STAT_NAMES})
+    res.launches = cp.stat("gpu_launches")
+    cp.close()
+    return res
+
+
+SUSI = ["-enabled_cp3", "-subsimp"]
+FULL = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]
+LOCAL = ["-enabled_cp3", "-subsimp", "-bve", "-no-bve_gates", "-bve_cgrow=0", "-bve_cgrow_t=0", "-no-cp3_limited"]
+
+
+def test_library_is_the_cuda_build():
+    assert os.path.exists(rs.DEFAULT_LIB)
+    L = rs.load()
+    assert L.cp3g_device_count() >= 1
+
+
+@pytest.mark.parametrize("opts", [SUSI, ["-enabled_cp3", "-subsimp", "-no-cp3_strength"], FULL, LOCAL])
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_planted_3sat_matches_oracle(gen, opts, seed):
+    lits, sizes = gen.random_ksat(3000, 12780, 3, seed=seed, dup=0.03, sup=0.05, flip=0.05)
+    stream = gen.csr_to_stream(lits, sizes)
+    a = run_gpu(stream, opts); b = run_oracle(stream, opts)
+    assert compare(a, b) == []
+    assert a.launches > 0
+
+
+@pytest.mark.parametrize("opts", [SUSI, FULL])
+def test_community_ksat_matches_oracle(gen, opts):
+    lits, sizes = gen.community_ksat(20000, 100000, seed=20260001)
+    stream = gen.csr_to_stream(lits, sizes)
+    a = run_gpu(stream, opts); b = run_oracle(stream, opts)
+    assert compare(a, b) == []
+
+
+@pytest.mark.parametrize("zipf", [0.8, 1.2])
+def test_zipf_skew_matches_oracle(gen, zipf):
+    # long occurrence lists: exercises the block-sorted CSR build and long-list scans
+    lits, sizes = gen.random_ksat(5000, 21300, 3, seed=777, zipf_s=zipf)
+    stream = gen.csr_to_stream(lits, sizes)
+    a = run_gpu(stream, SUSI); b = run_oracle(stream, SUSI)
+    assert compare(a, b) == []
+
+
+def test_fuzz_small_instances(gen):
+    from fuzz_oracle import OPTSETS, random_instance
+    rng = np.random.default_rng(2026)
+    for r in range(60):
+        lits, sizes = random_instance(rng)
+        stream = gen.csr_to_stream(lits, sizes)
+        opts = OPTSETS[int(rng.integers(0, len(OPTSETS)))]
+        a = run_gpu(stream, opts); b = run_oracle(stream, opts)
+        assert compare(a, b) == [], (r, opts)
+
+
+def test_edge_cases(gen):
+    # empty formula, single clause, unit / contradictory input, duplicate tie rule
+    for stream, opts in [
+        (np.zeros(0, np.int32), SUSI),
+        (np.array([1, 2, 0], np.int32), FULL),
+        (np.array([1, 0, -1, 0], np.int32), SUSI),
+        (np.array([1, 2, 0, 3, 4, 0, 1, 2, 0, 1, 2, 5, 0, 5, 6, 0], np.int32), ["-enabled_cp3", "-subsimp", "-no-cp3_strength"]),
+        (np.array([1, 2, 3, 0, -1, 2, 0, 4, 5, 0, -2, 3, 0], np.int32), SUSI),
+    ]:
+        a = run_gpu(stream, opts); b = run_oracle(stream, opts)
+        has_units = a.ok == 0 or b.ok == 0
+        assert compare(a, b, ordered=not has_units) == []
+
+
+# ------------------------------------------------------------------ kernel level (scan service)
+def _to_codes(lits):
+    v = np.abs(lits).astype(np.int64) - 1
+    return (2 * v + (lits < 0)).astype(np.int32)
+
+
+def _sorted_clauses(lits, sizes):
+    codes = _to_codes(lits)
+    ends = np.cumsum(sizes); starts = ends - sizes
+    out = codes.copy()
+    for s, e in zip(starts.tolist(), ends.tolist()):
+        out[s:e] = np.sort(codes[s:e])
+    return out
+
+
+def test_k2_occ_build_is_clause_ordered(gen):
+    lits, sizes = gen.random_ksat(2000, 9000, 3, seed=5, zipf_s=1.0)
+    n = int(np.abs(lits).max())
+    svc = rs.ScanService()
+    svc.upload(n, _sorted_clauses(lits, sizes), sizes)
+    svc.build()
+    off, refs = svc.download_occ()
+    codes = _sorted_clauses(lits, sizes)
+    clause_of = np.repeat(np.arange(sizes.size, dtype=np.uint32), sizes)
+    order = np.lexsort((clause_of, codes))           # by literal, then clause index
+    assert np.array_equal(refs, clause_of[order])
+    cnt = np.bincount(codes, minlength=2 * n)
+    assert np.array_equal(np.diff(off), cnt)
+
+
+def test_k3_subsumed_set_matches_oracle_snapshot(gen):
+    lits, sizes = gen.random_ksat(4000, 17000, 3, seed=9, dup=0.04, sup=0.06, flip=0.0)
+    stream = gen.csr_to_stream(lits, sizes)
+    o = Oracle(["-enabled_cp3"]); o.add(stream); o.init_only()
+    deleted, steps = o.subsume_snapshot()
+    o.close()
+    # GPU: all clauses as subsumers; apply the duplicate tie rule of the sequential queue (last wins)
+    n = int(np.abs(lits).max())
+    svc = rs.ScanService(); svc.upload(n, _sorted_clauses(lits, sizes), sizes); svc.build()
+    hits, checks = svc.scan(rs.SUBSUME, np.arange(sizes.size, dtype=np.uint32))
+    m = sizes.size
+    dele = np.zeros(m, dtype=np.uint8)
+    strict = sizes[hits["req"]] < sizes[hits["clause"]]
+    dele[hits["clause"][strict]] = 1
+    dup = ~strict                                     # identical clauses: the later queue entry survives
+    dele[hits["clause"][dup & (hits["req"] > hits["clause"])]] = 1
+    assert np.array_equal(dele, deleted)
+    assert checks > 0
+
+
+def test_k5_resolvent_counts_match_oracle_snapshot(gen):
+    lits, sizes = gen.community_ksat(3000, 12000, seed=4, planted=False)
+    stream = gen.csr_to_stream(lits, sizes)
+    o = Oracle(["-enabled_cp3"]); o.add(stream); o.init_only()
+    want, small = o.anticipate_snapshot()
+    o.close()
+    n = int(np.abs(lits).max())
+    svc = rs.ScanService(); svc.upload(n, _sorted_clauses(lits, sizes), sizes); svc.build()
+    off, refs = svc.download_occ()
+    vs = np.arange(n, dtype=np.uint32)
+    pos = [refs[off[2 * v]:off[2 * v + 1]] for v in range(n)]
+    neg = [refs[off[2 * v + 1]:off[2 * v + 2]] for v in range(n)]
+    pair_off, sz = svc.bve_pairs(vs, pos, neg)
+    got = np.zeros((n, 4), dtype=np.int32)
+    for v in range(n):
+        s = sz[int(pair_off[v]):int(pair_off[v + 1])].astype(np.int32)
+        got[v] = (len(pos[v]), len(neg[v]), int((s > 1).sum()), int(s[s > 1].sum()))
+    assert np.array_equal(got, want)
+    # K6: resolvent literals reproduce the K5 sizes and contain no pivot / duplicate
+    v = int(np.argmax(got[:, 2]))
+    s = sz[int(pair_off[v]):int(pair_off[v + 1])].reshape(len(pos[v]), len(neg[v]))
+    ai, bi = np.nonzero(s > 1)
+    o2, rl = svc.bve_resolve(np.full(ai.size, v, np.uint32), np.asarray(pos[v])[ai], np.asarray(neg[v])[bi], s[ai, bi])
+    for k in range(ai.size):
+        r = rl[int(o2[k]):int(o2[k + 1])]
+        assert np.all(np.diff(r) > 0) and not np.any((r >> 1) == v)
+
+
+def test_c2_size_properties(gen):
+    """BASELINE config 2 (1M vars / 4.26M clauses + planted redundancy): idempotence and soundness properties
+    that do not need the oracle at this size."""
+    lits, sizes = gen.random_ksat(1000000, 4260000, 3, seed=12345)
+    stream = gen.csr_to_stream(lits, sizes)
+    a = run_gpu(stream, SUSI + ["-no-cp3_limited"])
+    assert a.ok == 1
+    out = a.stream
+    # every planted duplicate / superset must be gone: the output has no two identical clauses
+    z = np.flatnonzero(out == 0); osz = np.diff(np.concatenate([[-1], z])) - 1
+    assert osz.size < sizes.size and a.stats["sub_subsumedClauses"] > 0.04 * 4260000
+    # idempotence: a second pass over the fixpoint removes nothing
+    full = np.concatenate([np.stack([a.trail, np.zeros_like(a.trail)], 1).reshape(-1), out]).astype(np.int32)
+    b = run_gpu(full, SUSI + ["-no-cp3_limited"])
+    assert b.stats["sub_subsumedClauses"] == 0 and b.stats["sub_removedLiterals"] == 0
+    assert np.array_equal(b.stream, out)
