@@ -109,9 +109,15 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
  *   CP3G_SUBSUME:    (req, D, -1)  for every live D != self with request ⊆ D
  *   CP3G_STRENGTHEN: (req, D, l)   for every live D where exactly the literal l of D is the complement of a
  *                                  request literal and the rest of the request is contained in D
- * rank/world partition the requests (contiguous ranges balanced by list length) for the multi-GPU path. */
+ * With out == NULL the hits are only counted (they stay on the device).
+ * After cp3g_nccl_init the requests are partitioned over the ranks and the hit lists all-gathered. */
 int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint32_t* req_off,
               const int32_t* req_lits, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks);
+
+/* K3/K4 bulk form: every live clause is a request (the first pass over the full queue); hit.req is the clause
+ * index of the subsumer / strengthener.  One thread per occurrence entry: each list is streamed once for all
+ * of its subsumers.  Rebuilds signatures + CSR first when clauses were edited since the last cp3g_build. */
+int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks);
 
 /* K5: resolvent anticipation for candidate variables.  Variable i owns pos refs p_off[i]..p_off[i+1] and
  * neg refs n_off[i]..n_off[i+1] (host list order).  sizes[pair_off[i] + a*nneg + b] = number of literals
@@ -128,7 +134,8 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
 int cp3g_nccl_unique_id(void* out128);
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);
 
-/* counters: "launches", "kernel_ns", "h2d_bytes", "d2h_bytes", "scan_requests", "scan_checks" */
+/* counters: "launches", "kernel_ns" (all kernels, CUDA events), "scan_ns" (K3/K4 only), "h2d_bytes", "d2h_bytes",
+ * "scan_requests", "scan_checks", "scan_alg_bytes" (sum over checks of 4 + 8 + 4*#D) */
 int64_t cp3g_counter(const cp3g* g, const char* name);
 
 #ifdef __cplusplus

@@ -144,6 +144,12 @@ int main(int argc, char** argv)
     fprintf(fo, "stat sub_removedLiterals %d\n", pp->subsumption.removedLiterals);
     fprintf(fo, "stat sub_subsSteps %lld\n", (long long)pp->subsumption.subsumptionStepper.getCurrentSteps());
     fprintf(fo, "stat sub_strengthSteps %lld\n", (long long)pp->subsumption.strengtheningStepper.getCurrentSteps());
+    {   // pthread workers keep their own counters (Subsumption.h localStats, Subsumption.cc:50-63)
+        long long ts = 0, tt = 0;
+        for (size_t i = 0; i < pp->subsumption.localStats.size(); ++i) { ts += pp->subsumption.localStats[i].subsumeSteps; tt += pp->subsumption.localStats[i].strengthSteps; }
+        fprintf(fo, "stat par_subsSteps %lld\n", ts);
+        fprintf(fo, "stat par_strengthSteps %lld\n", tt);
+    }
     fprintf(fo, "stat sub_seconds %.6f\n", pp->subsumption.processTime);
     fprintf(fo, "stat str_seconds %.6f\n", pp->subsumption.strengthTime);
     fprintf(fo, "stat bve_eliminatedVars %d\n", pp->bve.eliminatedVars);

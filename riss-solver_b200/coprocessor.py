@@ -148,8 +148,12 @@ class ScanService:
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         self._ck(self.L.cp3g_set_deleted(self.g, ids.size, ids.ctypes.data), "set_deleted")
 
-    def scan(self, kind, self_ids, req_off=None, req_lits=None, cap=None):
+    def scan(self, kind, self_ids, req_off=None, req_lits=None, cap=None, count_only=False):
         ids = np.ascontiguousarray(self_ids, dtype=np.uint32)
+        if count_only:      # hits stay on the device; returns (number of hits, checks)
+            n = C.c_uint32(0); chk = C.c_uint64(0)
+            self._ck(self.L.cp3g_scan(self.g, kind, ids.size, ids.ctypes.data, None, None, None, 0, C.byref(n), C.byref(chk)), "scan")
+            return int(n.value), int(chk.value)
         ro = None if req_off is None else np.ascontiguousarray(req_off, dtype=np.uint32)
         rl = None if req_lits is None else np.ascontiguousarray(req_lits, dtype=np.int32)
         cap = int(cap or max(1024, ids.size))
@@ -162,6 +166,24 @@ class ScanService:
                 cap = int(n.value) + 1024
                 continue
             self._ck(r, "scan")
+            a = np.frombuffer(out, dtype=np.dtype([("req", "<u4"), ("clause", "<u4"), ("lit", "<i4")]), count=n.value).copy()
+            return a, int(chk.value)
+
+    def scan_all(self, kind, cap=None, count_only=False):
+        """full-queue bulk pass (K3/K4 bulk kernels): every live clause is a request; hit.req = clause index"""
+        if count_only:
+            n = C.c_uint32(0); chk = C.c_uint64(0)
+            self._ck(self.L.cp3g_scan_all(self.g, kind, None, 0, C.byref(n), C.byref(chk)), "scan_all")
+            return int(n.value), int(chk.value)
+        cap = int(cap or 1 << 16)
+        while True:
+            out = (_lib.cp3g_hit * cap)()
+            n = C.c_uint32(0); chk = C.c_uint64(0)
+            r = self.L.cp3g_scan_all(self.g, kind, C.cast(out, C.c_void_p), cap, C.byref(n), C.byref(chk))
+            if r == -3:
+                cap = int(n.value) + 1024
+                continue
+            self._ck(r, "scan_all")
             a = np.frombuffer(out, dtype=np.dtype([("req", "<u4"), ("clause", "<u4"), ("lit", "<i4")]), count=n.value).copy()
             return a, int(chk.value)
 

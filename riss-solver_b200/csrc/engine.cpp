@@ -8,10 +8,18 @@
 
 namespace cp3 {
 
+struct PhaseTimer {
+    int64_t& acc; int64_t t0;
+    explicit PhaseTimer(int64_t& a);
+    ~PhaseTimer();
+};
 static inline int64_t now_ns()
 {
     return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
+
+PhaseTimer::PhaseTimer(int64_t& a) : acc(a), t0(now_ns()) {}
+PhaseTimer::~PhaseTimer() { acc += now_ns() - t0; }
 
 // ------------------------------------------------------------------------------------------------ options
 int Options::parse(const char* o)
@@ -68,7 +76,7 @@ void Options::preset(const char* name)
     }
 }
 
-void Engine::ScanCache::clear() { std::fill(slot.begin(), slot.end(), -1); ent.clear(); hits.clear(); }
+void Engine::ScanCache::clear() { std::fill(slot.begin(), slot.end(), -1); ent.clear(); hits.clear(); lits.clear(); bulk_all = false; }
 
 Engine::Engine() { sub_lim = opt.sub_limit; str_lim = opt.str_limit; }
 Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
@@ -89,12 +97,14 @@ void Engine::newVar()
 
 uint32_t Engine::allocClause(const int* lits, int n)
 {
-    uint32_t c = (uint32_t)cstart.size();
-    cstart.push_back((uint32_t)pool.size()); csize.push_back((uint32_t)n);
-    cflag.push_back(F_SUB | F_STR);                 // fresh clause: can_subsume, can_strengthen
+    uint32_t c = (uint32_t)C.size();
+    ClauseInfo ci; ci.start = (uint32_t)pool.size(); ci.size = (uint32_t)n;
+    ci.flag = F_SUB | F_STR;                        // fresh clause: can_subsume, can_strengthen
+    ci.stamp = scan_id; ci.ver = 0;
+    C.push_back(ci);
+    ++n_live;
     pool.insert(pool.end(), lits, lits + n);
     ca_size += 2 + n;                               // ClauseAllocator::clauseWord32Size, SolverTypes.h:641-644
-    mod_stamp.push_back(scan_id); ver.push_back(0);
     return c;
 }
 
@@ -116,7 +126,7 @@ bool Engine::ingestPropagate()
     if (!ing_built) {
         ing_occ.assign(2 * (size_t)nvars, {});
         ing_built = true;
-        for (uint32_t c : clauses) { for (uint32_t k = 0; k < csize[c]; ++k) { ing_occ[CL(c)[k]].push_back(c); } }
+        for (uint32_t c : clauses) { for (uint32_t k = 0; k < C[c].size; ++k) { ing_occ[CL(c)[k]].push_back(c); } }
     }
     while (qhead < (int)trail.size()) {
         int p = trail[qhead++];
@@ -124,7 +134,7 @@ bool Engine::ingestPropagate()
         for (size_t i = 0; i < ws.size(); ++i) {
             uint32_t c = ws[i]; const int32_t* l = CL(c);
             int un = -1, nun = 0; bool sat = false;
-            for (uint32_t k = 0; k < csize[c]; ++k) {
+            for (uint32_t k = 0; k < C[c].size; ++k) {
                 int v = value(l[k]);
                 if (v == L_TRUE) { sat = true; break; }
                 if (v == L_UNDEF) { un = l[k]; ++nun; }
@@ -180,9 +190,9 @@ bool Engine::solverSimplify()
     size_t j = 0; int64_t lits = 0;
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i]; const int32_t* l = CL(c); bool sat = false;
-        for (uint32_t k = 0; k < csize[c]; ++k) { if (value(l[k]) == L_TRUE) { sat = true; break; } }
-        if (sat) { caFree(c); cflag[c] |= F_DEL; }
-        else { clauses[j++] = c; lits += csize[c]; }
+        for (uint32_t k = 0; k < C[c].size; ++k) { if (value(l[k]) == L_TRUE) { sat = true; break; } }
+        if (sat) { caFree(c); C[c].flag |= F_DEL; --n_live; }
+        else { clauses[j++] = c; lits += C[c].size; }
     }
     clauses.resize(j);
     if (ca_wasted > ca_size * opt.gc_frac) { ca_size -= ca_wasted; ca_wasted = 0; }
@@ -208,9 +218,9 @@ int Engine::setDistributed(int rank, int world, const void* id)
 void Engine::uploadAll()
 {
     ensureGpu();
-    const uint32_t ncl = (uint32_t)cstart.size();
-    std::vector<uint8_t> fl(ncl);
-    for (uint32_t c = 0; c < ncl; ++c) { fl[c] = (cflag[c] & F_DEL) ? 1 : 0; }
+    const uint32_t ncl = (uint32_t)C.size();
+    std::vector<uint8_t> fl(ncl); std::vector<uint32_t> cstart(ncl), csize(ncl);
+    for (uint32_t c = 0; c < ncl; ++c) { fl[c] = (C[c].flag & F_DEL) ? 1 : 0; cstart[c] = C[c].start; csize[c] = C[c].size; }
     int64_t t0 = now_ns();
     if (cp3g_upload(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), cstart.data(), csize.data(), fl.data()) != CP3G_OK) { die("upload failed"); }
     if (cp3g_build(gpu) != CP3G_OK) { die("occurrence build failed"); }
@@ -223,15 +233,15 @@ void Engine::uploadAll()
 // push the edits committed since the last scan (new resolvents, shrunk clauses, deletions)
 void Engine::flushDevice()
 {
-    const uint32_t ncl = (uint32_t)cstart.size();
+    const uint32_t ncl = (uint32_t)C.size();
     int64_t t0 = now_ns();
     const uint32_t old_ncl = dev_ncl;
     if (ncl > dev_ncl) {
         std::vector<uint32_t> sz; std::vector<int32_t> li;
         for (uint32_t c = dev_ncl; c < ncl; ++c) {
-            sz.push_back(csize[c]);
-            li.insert(li.end(), CL(c), CL(c) + csize[c]);
-            if (cflag[c] & F_DEL) { pend_del.push_back(c); }
+            sz.push_back(C[c].size);
+            li.insert(li.end(), CL(c), CL(c) + C[c].size);
+            if (C[c].flag & F_DEL) { pend_del.push_back(c); }
         }
         if (cp3g_append(gpu, ncl - dev_ncl, sz.data(), li.data(), li.size()) != CP3G_OK) { die("append failed"); }
         dev_ncl = ncl;
@@ -242,8 +252,8 @@ void Engine::flushDevice()
         for (uint32_t c : pend_shrunk) {
             shrunk_mark[c] = 0;
             if (c >= old_ncl) { continue; }          // appended above with its current content
-            ids.push_back(c); st.push_back((uint32_t)li.size()); sz.push_back(csize[c]);
-            li.insert(li.end(), CL(c), CL(c) + csize[c]);
+            ids.push_back(c); st.push_back((uint32_t)li.size()); sz.push_back(C[c].size);
+            li.insert(li.end(), CL(c), CL(c) + C[c].size);
         }
         pend_shrunk.clear();
         if (!ids.empty() && cp3g_shrink(gpu, (uint32_t)ids.size(), ids.data(), st.data(), sz.data(), li.data(), li.size()) != CP3G_OK) { die("shrink failed"); }
@@ -261,18 +271,47 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     if (ids.empty()) { return; }
     flushDevice();
     ++scan_id; ++n_scan_batches;
-    if (cache.slot.size() < cstart.size()) { cache.slot.resize(cstart.size(), -1); }
+    if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
     // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
     std::vector<uint32_t> live, dead;
-    for (uint32_t c : ids) { ((cflag[c] & F_DEL) ? dead : live).push_back(c); }
+    for (uint32_t c : ids) { ((C[c].flag & F_DEL) ? dead : live).push_back(c); }
     int64_t t0 = now_ns();
+    static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
+    if (dead.empty() && live.size() == n_live && n_live > bulk_min) {
+        // the queue holds every live clause: full-queue bulk kernel (one thread per occurrence entry)
+        uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, live.size() / 8));
+        uint32_t n = 0; uint64_t chk = 0;
+        for (;;) {
+            hitbuf.resize(cap);
+            int r = cp3g_scan_all(gpu, kind, hitbuf.data(), cap, &n, &chk);
+            if (r == CP3G_OK) { break; }
+            if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
+            die("bulk scan failed");
+        }
+        std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
+            return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+        cache.bulk_all = true; cache.bulk_scan = scan_id; cache.bulk_ncl = (uint32_t)C.size();
+        cache.empty.ver = 0; cache.empty.scan = scan_id; cache.empty.hb = cache.empty.he = 0; cache.empty.next = -1;
+        cache.empty.lit_off = cache.empty.lit_n = 0; cache.empty.time = 0;
+        for (uint32_t h = 0; h < n;) {
+            const uint32_t c = hitbuf[h].req;
+            CacheEnt e; e.ver = C[c].ver; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
+            while (h < n && hitbuf[h].req == c) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
+            e.he = (uint32_t)cache.hits.size();
+            e.next = cache.slot[c]; e.lit_off = e.lit_n = 0; e.time = 0;
+            cache.slot[c] = (int32_t)cache.ent.size();
+            cache.ent.push_back(e);
+        }
+        host_ns_gpuwait += now_ns() - t0;
+        return;
+    }
     for (int part = 0; part < 2; ++part) {
         const std::vector<uint32_t>& v = part == 0 ? live : dead;
         if (v.empty()) { continue; }
         std::vector<uint32_t> roff; std::vector<int32_t> rl;
         if (part == 1) {
             roff.push_back(0);
-            for (uint32_t c : v) { rl.insert(rl.end(), CL(c), CL(c) + csize[c]); roff.push_back((uint32_t)rl.size()); }
+            for (uint32_t c : v) { rl.insert(rl.end(), CL(c), CL(c) + C[c].size); roff.push_back((uint32_t)rl.size()); }
         }
         uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, v.size() / 8));
         uint32_t n = 0; uint64_t chk = 0;
@@ -288,9 +327,10 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
         uint32_t h = 0;
         for (uint32_t i = 0; i < v.size(); ++i) {
-            CacheEnt e; e.ver = ver[v[i]]; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
+            CacheEnt e; e.ver = C[v[i]].ver; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
             while (h < n && hitbuf[h].req == i) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
             e.he = (uint32_t)cache.hits.size();
+            e.next = cache.slot[v[i]]; e.lit_off = e.lit_n = 0; e.time = 0;
             cache.slot[v[i]] = (int32_t)cache.ent.size();
             cache.ent.push_back(e);
         }
@@ -298,11 +338,121 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     host_ns_gpuwait += now_ns() - t0;
 }
 
-const Engine::CacheEnt* Engine::cached(ScanCache& cache, uint32_t c) const
+const Engine::CacheEnt* Engine::cached(const ScanCache& cache, uint32_t c) const
 {
-    if (c >= cache.slot.size() || cache.slot[c] < 0) { return nullptr; }
-    const CacheEnt* e = &cache.ent[cache.slot[c]];
-    return e->ver == ver[c] ? e : nullptr;
+    if (c >= cache.slot.size()) { return nullptr; }
+    if (cache.slot[c] < 0) {
+        return (cache.bulk_all && c < cache.bulk_ncl && C[c].stamp < cache.bulk_scan) ? &cache.empty : nullptr;
+    }
+    for (int32_t i = cache.slot[c]; i >= 0; i = cache.ent[i].next) {
+        const CacheEnt* e = &cache.ent[i];
+        if (e->ver != UINT32_MAX) { if (e->ver == C[c].ver) { return e; } continue; }
+        if (e->lit_n == C[c].size && !memcmp(cache.lits.data() + e->lit_off, CL(c), sizeof(int32_t) * e->lit_n)) { return e; }
+    }
+    return nullptr;
+}
+
+// Scan explicit literal contents (predicted future versions of clauses) against the current device state.
+void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache)
+{
+    if (reqs.empty()) { return; }
+    ++scan_id; ++n_scan_batches; ++n_spec_rounds; n_spec_requests += (int64_t)reqs.size();
+    if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
+    std::vector<uint32_t> self(reqs.size()), roff(reqs.size() + 1); std::vector<int32_t> rl;
+    roff[0] = 0;
+    for (size_t i = 0; i < reqs.size(); ++i) {
+        self[i] = reqs[i].clause;
+        rl.insert(rl.end(), spec_lits.begin() + reqs[i].off, spec_lits.begin() + reqs[i].off + reqs[i].n);
+        roff[i + 1] = (uint32_t)rl.size();
+    }
+    int64_t t0 = now_ns();
+    uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, reqs.size() / 4));
+    uint32_t n = 0; uint64_t chk = 0;
+    for (;;) {
+        hitbuf.resize(cap);
+        int r = cp3g_scan(gpu, kind, (uint32_t)reqs.size(), self.data(), roff.data(), rl.data(), hitbuf.data(), cap, &n, &chk);
+        if (r == CP3G_OK) { break; }
+        if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
+        die("speculative scan failed");
+    }
+    host_ns_gpuwait += now_ns() - t0;
+    std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
+        return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+    uint32_t h = 0;
+    for (uint32_t i = 0; i < reqs.size(); ++i) {
+        CacheEnt e; e.ver = UINT32_MAX; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
+        while (h < n && hitbuf[h].req == i) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
+        e.he = (uint32_t)cache.hits.size();
+        e.lit_off = (uint32_t)cache.lits.size(); e.lit_n = reqs[i].n; e.time = reqs[i].time;
+        cache.lits.insert(cache.lits.end(), spec_lits.begin() + reqs[i].off, spec_lits.begin() + reqs[i].off + reqs[i].n);
+        e.next = cache.slot[reqs[i].clause];
+        cache.slot[reqs[i].clause] = (int32_t)cache.ent.size();
+        cache.ent.push_back(e);
+    }
+}
+
+// Speculative closure of a strengthening pass.  The bulk K4 scan of the queue tells which clauses will lose
+// which literal; a clause that loses a literal is processed again as a strengthener in its shortened form
+// (at its own queue turn, or right away through the LIFO localQueue, Subsumption.cc:1280-1287,1394-1397).
+// Instead of discovering those versions one by one during the ordered commit (one GPU round trip each),
+// predict them from the hit lists, scan them in bulk, and repeat on the hits they produce.  A wrong
+// prediction costs nothing but an unused cache entry; a missing one falls back to an on-demand scan.
+void Engine::prefetchStrengthenClosure()
+{
+    PhaseTimer pt(ph_prefetch);
+    struct Ev { double time; int lit; };
+    std::unordered_map<uint32_t, std::vector<Ev>> events;
+    std::unordered_map<uint32_t, std::vector<uint64_t>> requested;     // content hashes already scanned
+    size_t first_ent = 0;
+    for (int round = 0; round < 8; ++round) {
+        std::vector<uint32_t> changed;
+        for (size_t ei = first_ent; ei < c_str.ent.size(); ++ei) {
+            const CacheEnt& e = c_str.ent[ei];
+            for (uint32_t h = e.hb; h < e.he; ++h) {
+                const Hit& ht = c_str.hits[h];
+                std::vector<Ev>& ev = events[ht.clause];
+                bool dup = false;
+                for (const Ev& x : ev) { if (x.lit == ht.lit) { dup = true; break; } }
+                if (dup) { continue; }
+                ev.push_back({e.time, ht.lit});
+                changed.push_back(ht.clause);
+            }
+        }
+        first_ent = c_str.ent.size();
+        if (changed.empty()) { break; }
+        std::sort(changed.begin(), changed.end());
+        changed.erase(std::unique(changed.begin(), changed.end()), changed.end());
+        std::vector<SpecReq> reqs; spec_lits.clear();
+        for (uint32_t d : changed) {
+            if (C[d].flag & F_DEL) { continue; }
+            std::vector<Ev>& ev = events[d];
+            std::stable_sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.time < b.time; });
+            const bool pending = (C[d].flag & F_STR) && d < qtime.size() && qtime[d] >= 0;
+            const double own = pending ? (double)qtime[d] : -1.0;
+            size_t k0 = 0;
+            if (pending) { while (k0 < ev.size() && ev[k0].time < own) { ++k0; } }
+            std::vector<uint64_t>& done = requested[d];
+            for (size_t k = std::max<size_t>(k0, 1); k <= ev.size(); ++k) {
+                if (C[d].size < k + 2) { break; }          // would be a unit: handled by propagation, never scanned
+                // content = current literals minus the first k predicted removals
+                uint64_t hsh = 1469598103934665603ull;
+                const uint32_t off = (uint32_t)spec_lits.size();
+                const int32_t* l = CL(d);
+                for (uint32_t i = 0; i < C[d].size; ++i) {
+                    bool rm = false;
+                    for (size_t j = 0; j < k; ++j) { if (ev[j].lit == l[i]) { rm = true; break; } }
+                    if (!rm) { spec_lits.push_back(l[i]); hsh = (hsh ^ (uint32_t)l[i]) * 1099511628211ull; }
+                }
+                const uint32_t nl = (uint32_t)spec_lits.size() - off;
+                if (nl != C[d].size - k || std::find(done.begin(), done.end(), hsh) != done.end()) { spec_lits.resize(off); continue; }
+                done.push_back(hsh);
+                const double t = (pending && k == k0) ? own : std::max(own, ev[k - 1].time) + 1e-3 * (round + 1);
+                reqs.push_back({d, off, nl, t});
+            }
+        }
+        if (reqs.empty()) { break; }
+        scanSpeculative(CP3G_STRENGTHEN, reqs, c_str);
+    }
 }
 
 static inline bool containsLit(const int32_t* l, uint32_t n, int x)
@@ -313,21 +463,21 @@ static inline bool containsLit(const int32_t* l, uint32_t n, int x)
 // A snapshot hit "C subsumes D" stays true unless D lost a literal of C afterwards.
 bool Engine::subHitValid(uint32_t c, uint32_t d, uint32_t scan) const
 {
-    if (mod_stamp[d] < scan) { return true; }
+    if (C[d].stamp < scan) { return true; }
     auto it = edit_log.find(d);
     if (it == edit_log.end()) { return true; }
-    for (const Removal& r : it->second) { if (r.stamp >= scan && containsLit(CL(c), csize[c], r.lit)) { return false; } }
+    for (const Removal& r : it->second) { if (r.stamp >= scan && containsLit(CL(c), C[c].size, r.lit)) { return false; } }
     return true;
 }
 // A snapshot hit "S strengthens D on literal f" stays true unless D lost f or a literal of S afterwards.
 bool Engine::strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const
 {
-    if (mod_stamp[d] < scan) { return true; }
+    if (C[d].stamp < scan) { return true; }
     auto it = edit_log.find(d);
     if (it == edit_log.end()) { return true; }
     for (const Removal& r : it->second) {
         if (r.stamp < scan) { continue; }
-        if (r.lit == f || containsLit(CL(s), csize[s], r.lit)) { return false; }
+        if (r.lit == f || containsLit(CL(s), C[s].size, r.lit)) { return false; }
     }
     return true;
 }
@@ -348,34 +498,34 @@ void Engine::occPush(int x, uint32_t c)
 void Engine::occSwapRemove(int x, uint32_t i)
 {
     OccList& l = occ[x]; uint32_t* p = LP(l);
-    if ((cflag[p[i]] & F_DEL) && stale[x] > 0) { --stale[x]; }
+    if ((C[p[i]].flag & F_DEL) && occ[x].stale > 0) { --occ[x].stale; }
     p[i] = p[l.n - 1]; l.n--;
 }
-void Engine::occRelease(int x) { occ[x].n = 0; stale[x] = 0; }
+void Engine::occRelease(int x) { occ[x].n = 0; occ[x].stale = 0; }
 
 void Engine::touchClauseVars(uint32_t c)
 {
     const int32_t* l = CL(c);
-    for (uint32_t k = 0; k < csize[c]; ++k) { ++var_touch[l[k] >> 1]; }
+    for (uint32_t k = 0; k < C[c].size; ++k) { ++var_touch[l[k] >> 1]; }
 }
 
 void Engine::setDeleted(uint32_t c)
 {
-    if (cflag[c] & F_DEL) { return; }
-    cflag[c] |= F_DEL;
+    if (C[c].flag & F_DEL) { return; }
+    C[c].flag |= F_DEL; --n_live;
     const int32_t* l = CL(c);
-    for (uint32_t k = 0; k < csize[c]; ++k) { ++stale[l[k]]; ++var_touch[l[k] >> 1]; }
+    for (uint32_t k = 0; k < C[c].size; ++k) { ++occ[l[k]].stale; ++var_touch[l[k] >> 1]; }
     // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
     if (!pend_rm.empty()) {
         auto it = pend_rm.find(c);
-        if (it != pend_rm.end()) { for (int l2 : it->second) { ++stale[l2]; } }
+        if (it != pend_rm.end()) { for (int l2 : it->second) { ++occ[l2].stale; } }
     }
     if (dev_uploaded) { pend_del.push_back(c); }
 }
 
 void Engine::noteShrunk(uint32_t c, int removedLit)
 {
-    ++ver[c]; mod_stamp[c] = scan_id;
+    ++C[c].ver; C[c].stamp = scan_id;
     edit_log[c].push_back({scan_id, removedLit});
     if (dev_uploaded && c < shrunk_mark.size() && !shrunk_mark[c]) { shrunk_mark[c] = 1; pend_shrunk.push_back(c); }
     else if (dev_uploaded && c >= shrunk_mark.size()) { /* not yet on the device: appended with current content */ }
@@ -384,14 +534,14 @@ void Engine::noteShrunk(uint32_t c, int removedLit)
 
 void Engine::removePosSorted(uint32_t c, int pos)
 {
-    int32_t* l = CL(c); uint32_t n = csize[c];
+    int32_t* l = CL(c); uint32_t n = C[c].size;
     for (uint32_t j = (uint32_t)pos; j + 1 < n; ++j) { l[j] = l[j + 1]; }
-    csize[c] = n - 1;
+    C[c].size = n - 1;
 }
 void Engine::removePosUnsorted(uint32_t c, int pos)
 {
-    int32_t* l = CL(c); uint32_t n = csize[c];
-    l[pos] = l[n - 1]; csize[c] = n - 1;
+    int32_t* l = CL(c); uint32_t n = C[c].size;
+    l[pos] = l[n - 1]; C[c].size = n - 1;
 }
 
 // ------------------------------------------------------------------------------------------------ heap (riss/mtl/Heap.h:37-183)
@@ -433,10 +583,10 @@ void Engine::heapClear() { for (int v : heap) { hidx[v] = -1; } heap.clear(); }
 void Engine::removedClause(uint32_t c, bool useHeap, bool update, int ignore)
 {
     const int32_t* l = CL(c);
-    for (uint32_t i = 0; i < csize[c]; ++i) {
+    for (uint32_t i = 0; i < C[c].size; ++i) {
         int v = l[i] >> 1;
         deletedVar(v);
-        --cnt[l[i]];
+        --occ[l[i]].cnt;
         if (useHeap) {
             if (inHeap(v)) { heapUp(hidx[v]); }
             else if (update && v != ignore) { heapUpdate(v); }
@@ -450,7 +600,7 @@ void Engine::removedLiteral(int x, int diff, bool useHeap, bool update, int igno
 {
     int v = x >> 1;
     deletedVar(v);
-    cnt[x] -= diff;
+    occ[x].cnt -= diff;
     ca_wasted += 1;
     if (useHeap) {
         if (inHeap(v)) { heapUp(hidx[v]); }
@@ -460,11 +610,11 @@ void Engine::removedLiteral(int x, int diff, bool useHeap, bool update, int igno
 // addClause(cr, heap), CoprocessorTypes.h:835-864
 void Engine::dataAddClause(uint32_t c, bool useHeap)
 {
-    if (cflag[c] & F_DEL) { return; }
+    if (C[c].flag & F_DEL) { return; }
     const int32_t* l = CL(c);
-    for (uint32_t i = 0; i < csize[c]; ++i) {
+    for (uint32_t i = 0; i < C[c].size; ++i) {
         occPush(l[i], c);
-        cnt[l[i]] += 1;
+        occ[l[i]].cnt += 1;
         ++var_touch[l[i] >> 1];
         if (useHeap && inHeap(l[i] >> 1)) { heapDown(hidx[l[i] >> 1]); }
     }
@@ -479,27 +629,27 @@ bool Engine::removeClauseFrom(uint32_t c, int x)
 }
 void Engine::subInitClause(uint32_t c)
 {
-    if (cflag[c] & F_DEL) { return; }
-    if (cflag[c] & F_SUB) { subq.push_back(c); }
-    if (cflag[c] & F_STR) { strq.push_back(c); }
+    if (C[c].flag & F_DEL) { return; }
+    if (C[c].flag & F_SUB) { subq.push_back(c); }
+    if (C[c].flag & F_STR) { strq.push_back(c); }
 }
 void Engine::addSubStrength(uint32_t c)
 {
-    if (!(cflag[c] & F_STR)) { cflag[c] |= F_STR; strq.push_back(c); }
-    if (!(cflag[c] & F_SUB)) { cflag[c] |= F_SUB; subq.push_back(c); }
+    if (!(C[c].flag & F_STR)) { C[c].flag |= F_STR; strq.push_back(c); }
+    if (!(C[c].flag & F_SUB)) { C[c].flag |= F_SUB; subq.push_back(c); }
 }
 void Engine::extClause(uint32_t c, int x)
 {
     undo.push_back(0); undo.push_back(toDimacs(x));
     const int32_t* l = CL(c);
-    for (uint32_t i = 0; i < csize[c]; ++i) { if (l[i] != x) { undo.push_back(toDimacs(l[i])); } }
+    for (uint32_t i = 0; i < C[c].size; ++i) { if (l[i] != x) { undo.push_back(toDimacs(l[i])); } }
 }
 void Engine::extLit(int x) { undo.push_back(0); undo.push_back(toDimacs(x)); }
 
 void Engine::filterDeleted(std::vector<uint32_t>& a)
 {
     size_t j = 0;
-    for (size_t i = 0; i < a.size(); ++i) { if (!(cflag[a[i]] & F_DEL)) { a[j++] = a[i]; } }
+    for (size_t i = 0; i < a.size(); ++i) { if (!(C[a[i]].flag & F_DEL)) { a[j++] = a[i]; } }
     a.resize(j);
 }
 // garbageCollect / relocAll, CoprocessorTypes.h:1396-1550 (stable removal of deleted clauses everywhere)
@@ -509,12 +659,12 @@ void Engine::checkGarbage()
     filterDeleted(subq); filterDeleted(strq);
     for (int x = 0; x < 2 * nvars; ++x) {
         OccList& l = occ[x]; uint32_t* p = LP(l); uint32_t j = 0;
-        for (uint32_t i = 0; i < l.n; ++i) { if (!(cflag[p[i]] & F_DEL)) { p[j++] = p[i]; } }
-        l.n = j; stale[x] = 0;
+        for (uint32_t i = 0; i < l.n; ++i) { if (!(C[p[i]].flag & F_DEL)) { p[j++] = p[i]; } }
+        l.n = j; occ[x].stale = 0;
     }
     filterDeleted(clauses);
     double sz = 0;
-    for (uint32_t c : clauses) { sz += 2 + csize[c]; }
+    for (uint32_t c : clauses) { sz += 2 + C[c].size; }
     ca_size = sz; ca_wasted = 0;
 }
 
@@ -529,7 +679,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
             OccList& positive = occ[l];
             for (uint32_t i = 0; i < positive.n; ++i) {
                 uint32_t c = LP(positive)[i];
-                if (cflag[c] & F_DEL) { continue; }
+                if (C[c].flag & F_DEL) { continue; }
                 ++up_removedClauses;
                 setDeleted(c);
                 t_up.modified = true;
@@ -542,9 +692,9 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
         OccList& negative = occ[nl];
         for (uint32_t i = 0; i < negative.n; ++i) {
             uint32_t c = LP(negative)[i];
-            if (cflag[c] & F_DEL) { continue; }
+            if (C[c].flag & F_DEL) { continue; }
             int32_t* lits = CL(c);
-            for (uint32_t j = 0; j < csize[c]; ++j) {
+            for (uint32_t j = 0; j < C[c].size; ++j) {
                 if (lits[j] == nl) {
                     if (!sort) { removePosUnsorted(c, (int)j); } else { removePosSorted(c, (int)j); }
                     noteShrunk(c, nl);
@@ -555,8 +705,8 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
             }
             addSubStrength(c);
             dirty_str.push_back(c);
-            if (csize[c] == 0) { setDeleted(c); ok = false; return L_FALSE; }
-            else if (csize[c] == 1) {
+            if (C[c].size == 0) { setDeleted(c); ok = false; return L_FALSE; }
+            else if (C[c].size == 1) {
                 setDeleted(c);
                 int u = CL(c)[0];
                 if (value(u) == L_UNDEF) { uncheckedEnqueue(u); }
@@ -576,7 +726,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
 // ------------------------------------------------------------------------------------------------ Subsumption
 void Engine::clearQueue(std::vector<uint32_t>& q, uint8_t flag)
 {
-    for (uint32_t c : q) { cflag[c] &= ~flag; }
+    for (uint32_t c : q) { C[c].flag &= ~flag; }
     q.clear();
 }
 
@@ -591,12 +741,13 @@ static inline const Hit* findHit(const std::vector<Hit>& hits, uint32_t hb, uint
 // queue; the loop below replays the queue back to front.
 void Engine::subsumptionWorker(bool useHeap, int ignore)
 {
+    PhaseTimer pt(ph_sub);
     const bool unlimited = !opt.limited;
     c_sub.clear(); edit_log.clear();
     {
         std::vector<uint32_t> ids;
         ids.reserve(subq.size());
-        for (uint32_t c : subq) { if (!(cflag[c] & F_DEL)) { ids.push_back(c); } }
+        for (uint32_t c : subq) { if (!(C[c].flag & F_DEL)) { ids.push_back(c); } }
         std::sort(ids.begin(), ids.end());
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         scanClauses(CP3G_SUBSUME, ids, c_sub);
@@ -604,17 +755,23 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     int64_t t0 = now_ns();
     size_t end = subq.size();
     sub_occ_updates.clear();
+    const size_t PF = 16;                               // the walk is bound by cache misses on occ[lit]
     for (; end > 0 && (unlimited || sub_steps < sub_lim);) {
         --end;
+        if (end >= PF) {
+            const uint32_t c2 = subq[end - PF];
+            const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
+            for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&occ[l2[k]]); }
+        }
         const uint32_t cr = subq[end];
-        if (cflag[cr] & F_DEL) { continue; }
-        const int32_t* c = CL(cr); const uint32_t cn = csize[cr];
+        if (C[cr].flag & F_DEL) { continue; }
+        const int32_t* c = CL(cr); const uint32_t cn = C[cr].size;
         int min = c[0];
-        for (uint32_t l = 1; l < cn; ++l) { if (cnt[c[l]] < cnt[min]) { min = c[l]; } }
+        for (uint32_t l = 1; l < cn; ++l) { if (occ[c[l]].cnt < occ[min].cnt) { min = c[l]; } }
         const CacheEnt* e = cached(c_sub, cr);
         if (!e) { die("internal: subsumer without scan result"); }
         OccList& list = occ[min];
-        if (e->hb == e->he && stale[min] == 0 && (unlimited || sub_steps + (int64_t)list.n < sub_lim)) {
+        if (e->hb == e->he && occ[min].stale == 0 && (unlimited || sub_steps + (int64_t)list.n < sub_lim)) {
             sub_steps += list.n ? (int64_t)list.n - 1 : 0;          // every entry but cr itself is one check
             ++n_fast;
         } else {
@@ -623,10 +780,10 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
                 const uint32_t d = LP(list)[i];
                 if (d == cr) { continue; }
                 sub_steps++;
-                if (csize[d] < cn) { continue; }
-                if (cflag[d] & F_DEL) { occSwapRemove(min, i); --i; continue; }
+                if (C[d].size < cn) { continue; }
+                if (C[d].flag & F_DEL) { occSwapRemove(min, i); --i; continue; }
                 if (findHit(c_sub.hits, e->hb, e->he, d) && subHitValid(cr, d, e->scan)) {
-                    ++subsumedClauses; subsumedLiterals += (int)csize[d];
+                    ++subsumedClauses; subsumedLiterals += (int)C[d].size;
                     setDeleted(d);
                     removedClause(d, false, false, VAR_UNDEF);
                     successful(t_sub);
@@ -634,7 +791,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
                 }
             }
         }
-        cflag[cr] &= ~F_SUB;
+        C[cr].flag &= ~F_SUB;
     }
     // QUIRK: removedClause a second time per subsumed clause (Subsumption.cc:302-313); `ignore` lands in `update`
     for (uint32_t d : sub_occ_updates) { removedClause(d, useHeap, ignore != 0, VAR_UNDEF); }
@@ -657,8 +814,8 @@ void Engine::updateOccurrences(bool useHeap, int ignore)
 void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos)
 {
     ++removedLiterals;
-    if (!(cflag[other] & F_SUB)) { cflag[other] |= F_SUB; subq.push_back(other); }
-    if (!(cflag[other] & F_STR)) { localQueue.push_back(other); cflag[other] |= F_STR; }
+    if (!(C[other].flag & F_SUB)) { C[other].flag |= F_SUB; subq.push_back(other); }
+    if (!(C[other].flag & F_STR)) { localQueue.push_back(other); C[other].flag |= F_STR; }
     successful(t_sub);
     const int lit = CL(other)[pos];
     occ_upd.push_back({other, lit});
@@ -666,7 +823,7 @@ void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, in
     removePosSorted(other, pos);
     noteShrunk(other, lit);
     dirty_str.push_back(other);
-    if (csize[other] == 1) {
+    if (C[other].size == 1) {
         dataEnqueue(CL(other)[0]);
         setDeleted(other);
     }
@@ -677,12 +834,12 @@ void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, in
 const Engine::CacheEnt* Engine::strHits(uint32_t cr)
 {
     const CacheEnt* e = cached(c_str, cr);
-    if (e) { return e; }
+    if (e) { if (e->ver == UINT32_MAX) { ++n_spec_used; } return e; }
     ++n_ondemand;
     std::vector<uint32_t> ids;
-    if (c_str.slot.size() < cstart.size()) { c_str.slot.resize(cstart.size(), -1); }
+    if (c_str.slot.size() < C.size()) { c_str.slot.resize(C.size(), -1); }
     for (uint32_t c : dirty_str) {
-        if (c == cr || (cflag[c] & F_DEL) || !(cflag[c] & F_STR) || csize[c] < 2) { continue; }
+        if (c == cr || (C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
         if (cached(c_str, c)) { continue; }
         ids.push_back(c);
     }
@@ -699,17 +856,24 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
 // strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
 int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
+    PhaseTimer pt(ph_str);
     const bool unlimited = !opt.limited;
     c_str.clear(); edit_log.clear(); dirty_str.clear();
     if (opt.strength) {
         std::vector<uint32_t> ids;
         for (uint32_t c : strq) {
-            if ((cflag[c] & F_DEL) || !(cflag[c] & F_STR) || csize[c] < 2) { continue; }
+            if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
             ids.push_back(c);
         }
         std::sort(ids.begin(), ids.end());
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         scanClauses(CP3G_STRENGTHEN, ids, c_str);
+        // processing time of the queue entries: the queue is drained from the back
+        qtime.assign(C.size(), -1);
+        for (size_t i = 0; i < strq.size(); ++i) { qtime[strq[i]] = (int32_t)(strq.size() - 1 - i); }
+        for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
+        for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
+        prefetchStrengthenClosure();
     }
     int64_t t0 = now_ns();
     std::vector<uint32_t> localQueue;
@@ -717,24 +881,31 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     int ret = L_UNDEF; bool early = false;
     for (; end > 0 && (unlimited || str_steps < str_lim);) {
         uint32_t cr;
-        if (localQueue.empty()) { --end; cr = strq[end]; }
+        if (localQueue.empty()) {
+            --end; cr = strq[end];
+            if (end >= 16) {
+                const uint32_t c2 = strq[end - 16];
+                const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
+                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&occ[l2[k] & ~1]); }
+            }
+        }
         else { cr = localQueue.back(); localQueue.pop_back(); }
-        if ((cflag[cr] & F_DEL) || !(cflag[cr] & F_STR)) { continue; }
-        if (!opt.strength) { cflag[cr] &= ~F_STR; continue; }
-        if (csize[cr] < 2) {
-            if (csize[cr] == 1) { if (dataEnqueue(CL(cr)[0]) == L_FALSE) { break; } else { continue; } }
+        if ((C[cr].flag & F_DEL) || !(C[cr].flag & F_STR)) { continue; }
+        if (!opt.strength) { C[cr].flag &= ~F_STR; continue; }
+        if (C[cr].size < 2) {
+            if (C[cr].size == 1) { if (dataEnqueue(CL(cr)[0]) == L_FALSE) { break; } else { continue; } }
             else { ok = false; break; }
         }
         int minT;
         { const int32_t* s = CL(cr); minT = s[0];
-          for (uint32_t j = 1; j < csize[cr]; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
+          for (uint32_t j = 1; j < C[cr].size; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
         const int min = minT, nmin = lneg(minT);
         const CacheEnt* e = strHits(cr);
-        if (e->hb == e->he && stale[min] == 0 && stale[nmin] == 0 && !hasToPropagate() &&
+        if (e->hb == e->he && occ[min].stale == 0 && occ[nmin].stale == 0 && !hasToPropagate() &&
             (unlimited || str_steps + (int64_t)occ[min].n + (int64_t)occ[nmin].n < str_lim)) {
             // no candidate can hit and no list needs lazy cleaning: only the step counters move
             str_steps += (occ[min].n ? (int64_t)occ[min].n - 1 : 0) + (int64_t)occ[nmin].n;
-            cflag[cr] &= ~F_STR;
+            C[cr].flag &= ~F_STR;
             ++n_fast;
             continue;
         }
@@ -746,12 +917,12 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 const uint32_t other = LP(list)[j];
                 if (other == cr) { continue; }
                 str_steps++;
-                if (csize[other] == 0) { break; }
-                if (cflag[other] & F_DEL) { occSwapRemove(min, j); --j; continue; }
+                if (C[other].size == 0) { break; }
+                if (C[other].flag & F_DEL) { occSwapRemove(min, j); --j; continue; }
                 const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
                 if (h && h->lit != nmin && strHitValid(cr, other, h->lit, e->scan)) {
                     const int32_t* t = CL(other); int pos = -1;
-                    for (uint32_t k = 0; k < csize[other]; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    for (uint32_t k = 0; k < C[other].size; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
                     if (pos >= 0) { strengthenHit(localQueue, other, pos); }
                 }
             }
@@ -766,11 +937,11 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list_neg)[j];
                 str_steps++;
-                if (cflag[other] & F_DEL) { occSwapRemove(nmin, j); --j; continue; }
+                if (C[other].flag & F_DEL) { occSwapRemove(nmin, j); --j; continue; }
                 const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
                 if (h && h->lit == nmin && strHitValid(cr, other, h->lit, e->scan)) {
                     const int32_t* t = CL(other); int pos = -1;
-                    for (uint32_t k = 0; k < csize[other]; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    for (uint32_t k = 0; k < C[other].size; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
                     if (pos >= 0) { strengthenHit(localQueue, other, pos); }
                 }
             }
@@ -779,7 +950,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
             t_sub.modified = t_sub.modified || t_up.modified;
         }
-        cflag[cr] &= ~F_STR;
+        C[cr].flag &= ~F_STR;
     }
     if (!early) {
         updateOccurrences(useHeap, ignore);
@@ -831,28 +1002,28 @@ bool Engine::findGates(int v, int& p_limit, int& n_limit)
         ++ma_step;
         for (uint32_t i = 0; i < pList.n; ++i) {
             uint32_t c = LP(pList)[i];
-            if ((cflag[c] & F_DEL) || csize[c] != 2) { continue; }
+            if ((C[c].flag & F_DEL) || C[c].size != 2) { continue; }
             const int32_t* l = CL(c);
             int other = l[0] == pLit ? l[1] : l[0];
             ma[lneg(other)] = ma_step;
         }
         for (uint32_t i = 0; i < nList.n; ++i) {
             uint32_t c = LP(nList)[i];
-            if (cflag[c] & F_DEL) { continue; }
+            if (C[c].flag & F_DEL) { continue; }
             const int32_t* l = CL(c); uint32_t j = 0;
-            for (; j < csize[c]; ++j) {
+            for (; j < C[c].size; ++j) {
                 if (l[j] == nLit) { continue; }
                 if (ma[l[j]] != ma_step) { break; }
             }
-            if (j == csize[c]) {
-                pClauses = (int)csize[c] - 1;
+            if (j == C[c].size) {
+                pClauses = (int)C[c].size - 1;
                 nClauses = 1;
-                for (uint32_t k = 0; k < csize[c]; ++k) { ma[l[k]] = 0; }
+                for (uint32_t k = 0; k < C[c].size; ++k) { ma[l[k]] = 0; }
                 std::swap(LP(nList)[0], LP(nList)[i]);
                 uint32_t placed = 0;
                 for (uint32_t k = 0; k < pList.n; ++k) {
                     uint32_t c2 = LP(pList)[k];
-                    if ((cflag[c2] & F_DEL) || csize[c2] != 2) { continue; }
+                    if ((C[c2].flag & F_DEL) || C[c2].size != 2) { continue; }
                     const int32_t* l2 = CL(c2);
                     int other = l2[0] == pLit ? l2[1] : l2[0];
                     if (ma[lneg(other)] != ma_step) {
@@ -924,8 +1095,8 @@ int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& r
     lit_clauses = 0;
     int clausesToUse = 0;
     if (opt.bve_early) {
-        for (uint32_t i = 0; i < positive.n; ++i) { if (!(cflag[LP(positive)[i]] & F_DEL)) { clausesToUse++; } }
-        for (uint32_t i = 0; i < negative.n; ++i) { if (!(cflag[LP(negative)[i]] & F_DEL)) { clausesToUse++; } }
+        for (uint32_t i = 0; i < positive.n; ++i) { if (!(C[LP(positive)[i]].flag & F_DEL)) { clausesToUse++; } }
+        for (uint32_t i = 0; i < negative.n; ++i) { if (!(C[LP(negative)[i]].flag & F_DEL)) { clausesToUse++; } }
         clausesToUse += opt.bve_cgrow;
         if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { clausesToUse += opt.bve_cgrow_t - bve_totallyAdded; }
     }
@@ -936,16 +1107,16 @@ int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& r
     remap();
     for (uint32_t cp = 0; cp < positive.n; ++cp) {
         const uint32_t p = LP(positive)[cp];
-        if (cflag[p] & F_DEL) { continue; }
-        if (binariesOnly && csize[p] > 2) { continue; }
+        if (C[p].flag & F_DEL) { continue; }
+        if (binariesOnly && C[p].size > 2) { continue; }
         int row = indexOf(pe->pos, p);
         for (uint32_t cn = 0; cn < negative.n; ++cn) {
             if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
             if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
             bve_steps++;
             const uint32_t n = LP(negative)[cn];
-            if (cflag[n] & F_DEL) { continue; }
-            if (binariesOnly && csize[n] > 2) { continue; }
+            if (C[n].flag & F_DEL) { continue; }
+            if (binariesOnly && C[n].size > 2) { continue; }
             if (row < 0 || col[cn] < 0) { die("internal: K5 matrix misses a clause"); }
             const int newLits = pe->sizes[(size_t)row * pe->neg.size() + col[cn]];
             if (newLits > 1) {
@@ -972,7 +1143,7 @@ int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& r
                     // clauses changed under us: fresh sizes for the rest of the loop
                     if (positive.n == 0 || negative.n == 0) { break; }
                     pe = &pairsFor(v); remap(); row = indexOf(pe->pos, p);
-                    if (cflag[p] & F_DEL) { break; }
+                    if (C[p].flag & F_DEL) { break; }
                 }
             }
         }
@@ -987,12 +1158,12 @@ void Engine::bveRemoveClauses(int x, int extLitOrNeg)
     OccList& list = occ[x];
     for (uint32_t i = 0; i < list.n; ++i) {
         uint32_t c = LP(list)[i];
-        if (cflag[c] & F_DEL) { continue; }
+        if (C[c].flag & F_DEL) { continue; }
         removedClause(c, useHeap, false, VAR_UNDEF);
         successful(t_bve);
         setDeleted(c);
         if (extLitOrNeg >= 0) { extClause(c, extLitOrNeg); }
-        ++bve_removedClauses; bve_removedLiterals += (int)csize[c];
+        ++bve_removedClauses; bve_removedLiterals += (int)C[c].size;
     }
 }
 // removeBlockedClauses, BVE.cc:1053-1090
@@ -1002,7 +1173,7 @@ void Engine::bveRemoveBlocked(int x, const std::vector<int>& stats)
     OccList& list = occ[x];
     for (uint32_t i = 0; i < list.n; ++i) {
         uint32_t c = LP(list)[i];
-        if (cflag[c] & F_DEL) { continue; }
+        if (C[c].flag & F_DEL) { continue; }
         if (stats[i] == 0) {
             setDeleted(c);
             removedClause(c, useHeap, false, VAR_UNDEF);
@@ -1030,13 +1201,13 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
         for (uint32_t j = 0; j < negative.n; ++j) { col[j] = indexOf(pe->neg, LP(negative)[j]); }
         for (uint32_t cp = cp0; cp < positive.n; ++cp) {
             const uint32_t p = LP(positive)[cp];
-            if (cflag[p] & F_DEL) { continue; }
+            if (C[p].flag & F_DEL) { continue; }
             const int row = indexOf(pe->pos, p);
             for (uint32_t cn = (cp == cp0 ? cn0 : 0); cn < negative.n; ++cn) {
                 if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
                 if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
                 const uint32_t n = LP(negative)[cn];
-                if (cflag[n] & F_DEL) { continue; }
+                if (C[n].flag & F_DEL) { continue; }
                 if (row < 0 || col[cn] < 0) { die("internal: K5 matrix misses a clause"); }
                 const int s = pe->sizes[(size_t)row * pe->neg.size() + col[cn]];
                 if (s >= 1) {
@@ -1058,13 +1229,13 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
     size_t k = 0;
     for (uint32_t cp = 0; cp < positive.n; ++cp) {
         const uint32_t p = LP(positive)[cp];
-        if (cflag[p] & F_DEL) { continue; }
+        if (C[p].flag & F_DEL) { continue; }
         for (uint32_t cn = 0; cn < negative.n; ++cn) {
             if ((int)cp >= p_limit && (int)cn >= n_limit) { continue; }
             if (hasDefinition && (int)cp < p_limit && (int)cn < n_limit) { continue; }
             bve_steps++;
             const uint32_t n = LP(negative)[cn];
-            if (cflag[n] & F_DEL) { continue; }
+            if (C[n].flag & F_DEL) { continue; }
             while (k < prs.size() && (prs[k].cp < cp || (prs[k].cp == cp && prs[k].cn < cn))) { ++k; }
             if (k >= prs.size() || prs[k].cp != cp || prs[k].cn != cn) { continue; }   // tautology / empty
             const Pr& q = prs[k];
@@ -1076,7 +1247,7 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
                     if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
                     t_bve.modified = t_bve.modified || t_up.modified;
                     if (positive.n == 0 || negative.n == 0) { return L_UNDEF; }
-                    const bool pdel = (cflag[p] & F_DEL) != 0;
+                    const bool pdel = (C[p].flag & F_DEL) != 0;
                     flushDevice();
                     pe = &pairsFor(v);
                     // continue behind (cp,cn); a deleted p ends its row (BVE.cc:942-944)
@@ -1104,7 +1275,7 @@ void Engine::bveWorker()
         if (assigns[v] != L_UNDEF) { continue; }
         if (occ[2 * v].n == 0 && occ[2 * v + 1].n == 0) { continue; }
         if (frozen[v]) { continue; }
-        const bool cutoff = (cnt[2 * v + 1] > 10 && cnt[2 * v] > 10) || (dcount(v) > 15 && (cnt[2 * v + 1] > 5 || cnt[2 * v] > 5));
+        const bool cutoff = (occ[2 * v + 1].cnt > 10 && occ[2 * v].cnt > 10) || (dcount(v) > 15 && (occ[2 * v + 1].cnt > 5 || occ[2 * v].cnt > 5));
         if (!opt.bve_force_gates && !opt.bve_unlimited && cutoff) { ++bve_skippedVars; continue; }
         int p_limit = (int)occ[2 * v].n, n_limit = (int)occ[2 * v + 1].n;
         bool foundGate = false;
@@ -1116,7 +1287,7 @@ void Engine::bveWorker()
         for (int s = 0; s < 2; ++s) {
             OccList& li = occ[2 * v + s];
             for (uint32_t i = 0; i < li.n; ++i) {
-                if (cflag[LP(li)[i]] & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
+                if (C[LP(li)[i]].flag & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
                 if (s == 0) { ++pos_count; } else { ++neg_count; }
             }
         }
@@ -1169,7 +1340,7 @@ void Engine::addClausesToSubsumption(int x)
     OccList& li = occ[x];
     for (uint32_t j = 0; j < li.n; ++j) {
         uint32_t d = LP(li)[j];
-        if (!(cflag[d] & F_DEL) && !(cflag[d] & F_SUB)) { cflag[d] |= F_SUB | F_STR; subInitClause(d); }
+        if (!(C[d].flag & F_DEL) && !(C[d].flag & F_SUB)) { C[d].flag |= F_SUB | F_STR; subInitClause(d); }
     }
 }
 
@@ -1219,9 +1390,9 @@ int Engine::bveProcess()
 // The occurrence lists are built on the GPU (K2) and copied back - they start in clause order.
 void Engine::initData()
 {
+    PhaseTimer pt(ph_init);
     const int n2 = 2 * nvars;
     occ.assign((size_t)n2, OccList());
-    cnt.assign((size_t)n2, 0); stale.assign((size_t)n2, 0);
     modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
     var_touch.assign((size_t)std::max(nvars, 1), 0);
     modStep = 0; numberOfCls = 0; qhead = 0;
@@ -1233,12 +1404,12 @@ void Engine::initData()
     if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
     for (int x = 0; x < n2; ++x) {
         occ[x].off = off[x]; occ[x].n = occ[x].cap = off[x + 1] - off[x];
-        cnt[x] = (int32_t)occ[x].n;
+        occ[x].cnt = (int32_t)occ[x].n;
     }
     size_t kept = 0;
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i];
-        if (cflag[c] & F_DEL) { continue; }
+        if (C[c].flag & F_DEL) { continue; }
         numberOfCls++;
         subInitClause(c);
         clauses[kept++] = c;
@@ -1253,6 +1424,7 @@ void Engine::preprocess()
     // literals, so only the clause-count gate can fire here
     if (opt.limited && (int64_t)clauses.size() > opt.cp3_cls) { return; }
     if (!opt.enabled) { return; }
+    PhaseTimer ptot(ph_total);
     ensureGpu();                                  // fail before touching anything when there is no device
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
     if (!solverSimplify()) { return; }
@@ -1290,15 +1462,15 @@ size_t Engine::output(int32_t* out, size_t cap) const
     auto emit = [&](int32_t x) { if (k < cap) { out[k] = x; } ++k; };
     for (int x : trail) { emit(toDimacs(x)); emit(0); }
     for (uint32_t c : clauses) {
-        if (cflag[c] & F_DEL) { continue; }
+        if (C[c].flag & F_DEL) { continue; }
         const int32_t* l = CL(c);
-        for (uint32_t j = 0; j < csize[c]; ++j) { emit(toDimacs(l[j])); }
+        for (uint32_t j = 0; j < C[c].size; ++j) { emit(toDimacs(l[j])); }
         emit(0);
     }
     return k;
 }
-size_t Engine::nLiveClauses() const { size_t n = 0; for (uint32_t c : clauses) { n += !(cflag[c] & F_DEL); } return n; }
-size_t Engine::nLiveLits() const { size_t n = 0; for (uint32_t c : clauses) { if (!(cflag[c] & F_DEL)) { n += csize[c]; } } return n; }
+size_t Engine::nLiveClauses() const { size_t n = 0; for (uint32_t c : clauses) { n += !(C[c].flag & F_DEL); } return n; }
+size_t Engine::nLiveLits() const { size_t n = 0; for (uint32_t c : clauses) { if (!(C[c].flag & F_DEL)) { n += C[c].size; } } return n; }
 size_t Engine::undoStack(int32_t* out, size_t cap) const
 {
     for (size_t i = 0; i < undo.size() && i < cap; ++i) { out[i] = undo[i]; }
@@ -1344,6 +1516,8 @@ int64_t Engine::stat(const char* s) const
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
+    ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
+    ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }
 #undef ST

@@ -52,7 +52,9 @@ struct Tech { int penalty = 0, peak = 0; bool modified = false; };
 struct Hit { uint32_t clause; int32_t lit; };
 
 // occurrence list: slice of one pooled array; grows by relocation to the pool end
-struct OccList { uint32_t off = 0, n = 0, cap = 0; };
+// plus the per-literal counter (lit_occurrence_count) and the number of deleted clauses still listed, packed so
+// that both literals of a variable share one 64-byte line (the commit walks are cache-miss bound)
+struct alignas(32) OccList { uint32_t off = 0, n = 0, cap = 0; int32_t cnt = 0; uint32_t stale = 0; uint32_t pad[3] = {0, 0, 0}; };
 
 class Engine {
 public:
@@ -83,7 +85,9 @@ private:
     std::vector<uint8_t> assigns, frozen;
     std::vector<int> trail;
     std::vector<int32_t> pool;                       // literal pool (codes)
-    std::vector<uint32_t> cstart, csize; std::vector<uint8_t> cflag;
+    // per clause: pool offset, size + flags, edit counter, scan count at the last edit - one 16-byte record
+    struct ClauseInfo { uint32_t start; uint32_t size : 24; uint32_t flag : 8; uint32_t ver; uint32_t stamp; };
+    std::vector<ClauseInfo> C;
     std::vector<uint32_t> clauses;                   // solver->clauses
     double ca_size = 0, ca_wasted = 0;
     int simpDB_assigns = -1; int64_t simpDB_props = 0;
@@ -93,8 +97,7 @@ private:
     // ---------------- CoprocessorData mirror
     bool data_ready = false;
     std::vector<OccList> occ; std::vector<uint32_t> occ_pool;
-    std::vector<int32_t> cnt; int numberOfCls = 0;
-    std::vector<uint32_t> stale;                     // deleted clauses still referenced from occ[l]
+    int numberOfCls = 0;
     std::vector<uint32_t> subq, strq; std::vector<int32_t> undo;
     std::vector<uint32_t> modTimer; uint32_t modStep = 0;
     std::vector<uint32_t> ma; uint32_t ma_step = 0;
@@ -120,11 +123,25 @@ private:
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
     std::vector<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far
-    std::vector<uint32_t> mod_stamp, ver;            // per clause: scan count at last edit, edit counter
     struct Removal { uint32_t stamp; int lit; };
     std::unordered_map<uint32_t, std::vector<Removal>> edit_log;          // literals removed per clause
-    struct CacheEnt { uint32_t ver, scan, hb, he; };
-    struct ScanCache { std::vector<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; void clear(); };
+    // one scanned content version of a clause: keyed by the edit counter (ver) when the device copy was
+    // scanned by id, or by the literal content itself (ver == UINT32_MAX) for speculative versions
+    struct CacheEnt { uint32_t ver, scan, hb, he; int32_t next; uint32_t lit_off, lit_n; double time; };
+    struct ScanCache {
+        std::vector<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; std::vector<int32_t> lits;
+        // a full-queue bulk scan covers every clause that was live at that time: clauses without an entry had
+        // no hit (no per-request record is kept for them)
+        bool bulk_all = false; uint32_t bulk_scan = 0, bulk_ncl = 0; CacheEnt empty;
+        void clear();
+    };
+    uint32_t n_live = 0;                             // clauses without F_DEL
+    struct SpecReq { uint32_t clause; uint32_t off, n; double time; };   // literals in spec_lits[off..off+n)
+    std::vector<int32_t> spec_lits;
+    void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache);
+    void prefetchStrengthenClosure();
+    std::vector<int32_t> qtime;                      // strengthening queue: processing time of a pending clause
+    int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0;
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
@@ -134,15 +151,16 @@ private:
     std::unordered_map<int, PairEnt> pair_cache;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
     int64_t host_ns_commit = 0, host_ns_gpuwait = 0;
+    int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0;
 
     // ---------------- basics
     inline int value(int x) const { uint8_t a = assigns[x >> 1]; return a == L_UNDEF ? L_UNDEF : (a ^ (x & 1)); }
-    inline int32_t* CL(uint32_t c) { return pool.data() + cstart[c]; }
-    inline const int32_t* CL(uint32_t c) const { return pool.data() + cstart[c]; }
-    inline int dcount(int v) const { return cnt[2 * v] + cnt[2 * v + 1]; }
+    inline int32_t* CL(uint32_t c) { return pool.data() + C[c].start; }
+    inline const int32_t* CL(uint32_t c) const { return pool.data() + C[c].start; }
+    inline int dcount(int v) const { return occ[2 * v].cnt + occ[2 * v + 1].cnt; }
     void newVar();
     uint32_t allocClause(const int* lits, int n);
-    void caFree(uint32_t c) { ca_wasted += 2 + csize[c]; }
+    void caFree(uint32_t c) { ca_wasted += 2 + C[c].size; }
     void uncheckedEnqueue(int x);
     int dataEnqueue(int x);
     void addClauseIngest(std::vector<int>& ps);
@@ -209,7 +227,7 @@ private:
     void flushDevice();
     // scan `ids` (clause indices, device content) and store the result in `cache`
     void scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache);
-    const CacheEnt* cached(ScanCache& cache, uint32_t c) const;
+    const CacheEnt* cached(const ScanCache& cache, uint32_t c) const;
     bool subHitValid(uint32_t c, uint32_t d, uint32_t scan) const;
     bool strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const;
     const CacheEnt* strHits(uint32_t cr);             // cached or on-demand strengthening hits of cr

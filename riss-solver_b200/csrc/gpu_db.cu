@@ -29,6 +29,8 @@
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g->fail(#call, _e); return CP3G_ERR_CUDA; } } while (0)
 
 static constexpr uint32_t FLAG_DEL = 0x80000000u;
+static constexpr uint32_t ENT_MIN_SUB = 0x40000000u;   // this entry's list is the clause's shortest list (K3 bulk)
+static constexpr uint32_t ENT_MIN_STR = 0x20000000u;   // ... shortest list pair of a variable (K4 bulk)
 static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
 
@@ -132,19 +134,48 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
 }
 
 __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, OccEnt* __restrict__ ent)
+                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, OccEnt* __restrict__ ent,
+                           uint32_t* __restrict__ ent_lit)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
     const ClauseHdr h = hdr[i];
     if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
-    OccEnt e; e.ref = i; e.szfl = h.szfl; e.sig = h.sig;
+    OccEnt e; e.ref = i; e.szfl = h.szfl & SIZE_MASK; e.sig = h.sig;
     for (uint32_t k = 0; k < sz; ++k) {
         const int32_t x = lits[h.start + k];
         const uint32_t p = atomicAdd(&cursor[x], 1u);
         ent[off[x] + p] = e;
+        ent_lit[off[x] + p] = (uint32_t)x;
     }
+}
+// after the per-list sort: tag, for every clause, its entry in the list a bulk scan walks for it
+__device__ __forceinline__ void mark_entry(const uint32_t* __restrict__ off, OccEnt* __restrict__ ent, int32_t x, uint32_t c, uint32_t bit)
+{
+    uint32_t lo = off[x], hi = off[x + 1];
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ent[mid].ref < c) { lo = mid + 1; } else { hi = mid; } }
+    ent[lo].szfl |= bit;          // exists: the clause contains x
+}
+__global__ void k_mark_min(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+                           const uint32_t* __restrict__ off, OccEnt* __restrict__ ent)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) { return; }
+    const ClauseHdr h = hdr[c];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    if (sz == 0) { return; }
+    uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = 0, xt = 0;
+    for (uint32_t k = 0; k < sz; ++k) {
+        const int32_t x = lits[h.start + k];
+        const uint32_t len = off[x + 1] - off[x];
+        const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
+        if (len < bs) { bs = len; xs = x; }
+        if (both < bt) { bt = both; xt = x; }
+    }
+    mark_entry(off, ent, xs, c, ENT_MIN_SUB);
+    mark_entry(off, ent, xt, c, ENT_MIN_STR);
 }
 // scatter order is nondeterministic; the reference order is ascending clause index -> sort every list
 __global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, OccEnt* __restrict__ ent,
@@ -299,12 +330,12 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         if (ol < best_len || (ol == best_len && oi < best_idx)) { best_len = ol; best_idx = oi; }
     }
     const int32_t x = S[best_idx];
-    unsigned long long nchk = 0;
+    unsigned long long nchk = 0, nbytes = 0;   // checks and their algorithmic bytes: 4 (entry) + 8 (header) + 4*#D
     {
         const uint32_t b = occ_off[x], e = occ_off[x + 1];
         for (uint32_t i = b + lane; i < e; i += 32) {
             const OccEnt en = occ_ent[i];
-            nchk += (en.ref != me);
+            if (en.ref != me) { nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK); }
             // a stale entry could flip on x itself; that hit belongs to the occ(~x) pass below
             test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, -1, x ^ 1, hdr, lits, r, out, cap, nout);
         }
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         const uint32_t b = occ_off[nx], e = occ_off[nx + 1];
         for (uint32_t i = b + lane; i < e; i += 32) {
             const OccEnt en = occ_ent[i];
-            nchk += 1;
+            nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
             test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, out, cap, nout);
         }
     }
@@ -322,12 +353,70 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
     for (uint32_t i = lane; i < novf; i += 32) {
         const uint32_t ref = ovf[i];
         const ClauseHdr h = hdr[ref];
-        nchk += (ref != me);
+        if (ref != me) { nchk += 1; nbytes += 12 + 4 * (h.szfl & SIZE_MASK); }
         test_candidate<KIND>(ref, h.szfl, h.sig, me, S, sn, ssig, -1, -1, hdr, lits, r, out, cap, nout);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); }
-    if (lane == 0 && nchk) { atomicAdd(checks, nchk); }
+    for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
+    if (lane == 0 && nchk) { atomicAdd(checks, nchk); atomicAdd(checks + 1, nbytes); }
+    // (one same-address atomic pair per request: fine for the small incremental batches this kernel serves;
+    //  full-queue passes go through k_bulk, which reduces per block)
+}
+
+// ------------------------------------------------------------------------------------------ K3 / K4 bulk
+// Full-queue pass (every live clause is a subsumer / strengthener): one thread per occurrence entry.  The
+// thread whose entry carries the MIN tag plays that clause against the rest of the same list (and, for
+// strengthening, the list of the complementary literal).  Threads of a warp own 32 consecutive entries, so
+// the lists they walk are the cache lines the warp has just loaded: every list is streamed from HBM once
+// for all of its subsumers, instead of once per subsumer.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_bulk(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+        const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent, const uint32_t* __restrict__ ent_lit,
+        uint32_t first, uint32_t last, cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
+        unsigned long long* __restrict__ checks)
+{
+    __shared__ unsigned long long sh_chk[8], sh_byt[8];
+    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long nchk = 0, nbytes = 0;
+    if (i < last) {
+        const OccEnt me = occ_ent[i];
+        if (me.szfl & (KIND == CP3G_SUBSUME ? ENT_MIN_SUB : ENT_MIN_STR)) {
+            const ClauseHdr hs = hdr[me.ref];
+            if (!(hs.szfl & FLAG_DEL)) {
+                const int32_t* S = lits + hs.start; const uint32_t sn = hs.szfl & SIZE_MASK;
+                const unsigned long long ssig = hs.sig;
+                const int32_t x = (int32_t)ent_lit[i];
+                {
+                    const uint32_t b = occ_off[x], e = occ_off[x + 1];
+                    for (uint32_t j = b; j < e; ++j) {
+                        if (j == i) { continue; }
+                        const OccEnt en = occ_ent[j];
+                        nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
+                        test_candidate<KIND>(en.ref, en.szfl, en.sig, me.ref, S, sn, ssig, -1, x ^ 1, hdr, lits, me.ref, out, cap, nout);
+                    }
+                }
+                if (KIND == CP3G_STRENGTHEN) {
+                    const int32_t nx = x ^ 1;
+                    const uint32_t b = occ_off[nx], e = occ_off[nx + 1];
+                    for (uint32_t j = b; j < e; ++j) {
+                        const OccEnt en = occ_ent[j];
+                        nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
+                        test_candidate<KIND>(en.ref, en.szfl, en.sig, me.ref, S, sn, ssig, nx, -1, hdr, lits, me.ref, out, cap, nout);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh_chk[w] = nchk; sh_byt[w] = nbytes; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long a = 0, b2 = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a += sh_chk[k]; b2 += sh_byt[k]; }
+        if (a) { atomicAdd(checks, a); atomicAdd(checks + 1, b2); }
+    }
 }
 
 // ------------------------------------------------------------------------------------------ K5 / K6
@@ -430,14 +519,14 @@ struct cp3g {
     size_t nlits = 0;
     DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent;
+    DevBuf<OccEnt> occ_ent; DevBuf<uint32_t> ent_lit; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
     DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
     std::vector<uint32_t> ovf_host;
     uint32_t total_occ = 0;
     int rank = 0, world = 1; void* nccl = nullptr;
-    int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0;
+    int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0, scan_ns = 0, scan_alg_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void fail(const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); fprintf(stderr, "cp3b200: CUDA error %s\n", err.c_str()); }
 };
@@ -464,7 +553,7 @@ struct KTimer {
     cp3g* g;
     explicit KTimer(cp3g* g_) : g(g_) { cudaEventRecord(g->ev0, g->stream); }
     void stop() { cudaEventRecord(g->ev1, g->stream); }
-    void collect() { float ms = 0; if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) { g->kernel_ns += (int64_t)(ms * 1e6); } }
+    int64_t collect() { float ms = 0; if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) { g->kernel_ns += (int64_t)(ms * 1e6); return (int64_t)(ms * 1e6); } return 0; }
 };
 
 extern "C" {
@@ -498,7 +587,7 @@ void cp3g_destroy(cp3g* g)
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
-    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release();
+    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release();
     g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
@@ -554,9 +643,10 @@ static int build_csr(cp3g* g)
     CK(cudaStreamSynchronize(g->stream));
     g->total_occ = total;
     RESERVE(g->occ_ent, (size_t)total + 1, false);
+    RESERVE(g->ent_lit, (size_t)total + 1, false);
     CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     if (g->ncl) {
-        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->occ_ent.p);
+        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->occ_ent.p, g->ent_lit.p);
         k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->occ_ent.p, g->long_lits.p, g->counters.p + 1);
         g->launches += 2;
     }
@@ -567,9 +657,14 @@ static int build_csr(cp3g* g)
         k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->occ_ent.p);
         g->launches += 1;
     }
+    if (g->ncl) {
+        k_mark_min<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_ent.p);
+        g->launches += 1;
+    }
     CK(cudaGetLastError());
     g->ncl_csr = g->ncl;
     g->ovf_host.clear();
+    g->dirty_since_build = false;
     return CP3G_OK;
 }
 
@@ -628,6 +723,7 @@ int cp3g_shrink(cp3g* g, uint32_t n, const uint32_t* ids, const uint32_t* nstart
     CK(cudaMemcpyAsync(g->bu1.p, nstart, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bu2.p, nsize, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bl0.p, lits, nlits * 4, cudaMemcpyHostToDevice, g->stream));
+    g->dirty_since_build = true;
     k_shrink<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->bu0.p, g->bu1.p, g->bu2.p, g->bl0.p, n);
     CK(cudaStreamSynchronize(g->stream));
     g->launches++; g->h2d += (int64_t)n * 12 + (int64_t)nlits * 4;
@@ -710,10 +806,64 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
     CK(cudaMemcpyAsync(cnt, g->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
-    t.collect();
+    g->scan_ns += t.collect();
     uint32_t n = cnt[0];
-    uint64_t chk; memcpy(&chk, &cnt[4], 8);
-    g->scan_requests += (re - rb); g->scan_checks += (int64_t)chk;
+    uint64_t chk, ab; memcpy(&chk, &cnt[4], 8); memcpy(&ab, &cnt[6], 8);
+    g->scan_requests += (re - rb); g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
+    if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }   // count only
+    if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
+    if (g->world > 1) {
+        int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
+        if (rr != CP3G_OK) { return rr; }
+    } else if (n) {
+        CK(cudaMemcpyAsync(out, g->hits.p, (size_t)n * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+    }
+    g->d2h += (int64_t)n * (int64_t)sizeof(cp3g_hit) + 32;
+    if (nout) { *nout = n; }
+    if (checks) { *checks = chk; }
+    return CP3G_OK;
+}
+
+int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    if (nout) { *nout = 0; }
+    cudaSetDevice(g->device);
+    if (g->dirty_since_build || !g->ovf_host.empty()) { int r = cp3g_build(g); if (r != CP3G_OK) { return r; } }
+    if (!g->total_occ) { if (checks) { *checks = 0; } return CP3G_OK; }
+    RESERVE(g->hits, (size_t)cap + 1, false);
+    CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
+    unsigned long long* dchecks = (unsigned long long*)(g->counters.p + 4);
+    // multi-GPU: contiguous slice of the entry array per rank
+    uint32_t eb = 0, ee = g->total_occ;
+    if (g->world > 1) {
+        const uint64_t per = (((uint64_t)g->total_occ + g->world - 1) / g->world + 255) / 256 * 256;
+        eb = (uint32_t)std::min<uint64_t>(g->total_occ, per * g->rank);
+        ee = (uint32_t)std::min<uint64_t>(g->total_occ, per * (g->rank + 1));
+    }
+    KTimer t(g);
+    if (ee > eb) {
+        const unsigned blocks = grid_for(ee - eb, 256);
+        if (kind == CP3G_SUBSUME) {
+            k_bulk<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ent_lit.p,
+                eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+        } else {
+            k_bulk<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ent_lit.p,
+                eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+        }
+        g->launches++;
+    }
+    t.stop();
+    uint32_t cnt[8];
+    CK(cudaMemcpyAsync(cnt, g->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    g->scan_ns += t.collect();
+    uint32_t n = cnt[0];
+    uint64_t chk, ab; memcpy(&chk, &cnt[4], 8); memcpy(&ab, &cnt[6], 8);
+    g->scan_requests += g->ncl; g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
+    if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }
     if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
     if (g->world > 1) {
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
@@ -800,6 +950,8 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "d2h_bytes")) { return g->d2h; }
     if (!strcmp(name, "scan_requests")) { return g->scan_requests; }
     if (!strcmp(name, "scan_checks")) { return g->scan_checks; }
+    if (!strcmp(name, "scan_ns")) { return g->scan_ns; }
+    if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }
     if (!strcmp(name, "total_occ")) { return g->total_occ; }
     return -1;

@@ -133,6 +133,18 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
     if (checks) { *checks = chk; }
     return n > cap ? CP3G_ERR_OVERFLOW : CP3G_OK;
 }
+int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks)
+{
+    // same answer as cp3g_scan over all live clauses, hit.req = clause index
+    std::vector<uint32_t> ids;
+    for (uint32_t i = 0; i < g->cl.size(); ++i) { if (!g->del[i]) { ids.push_back(i); } }
+    uint32_t n = 0;
+    int r = cp3g_scan(g, kind, (uint32_t)ids.size(), ids.data(), nullptr, nullptr, out, cap, &n, checks);
+    if (nout) { *nout = n; }
+    if (r != CP3G_OK) { return r; }
+    for (uint32_t k = 0; k < n; ++k) { out[k].req = ids[out[k].req]; }
+    return CP3G_OK;
+}
 int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
                    const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* pair_off, int16_t* sizes)
 {
