@@ -102,6 +102,7 @@ uint32_t Engine::allocClause(const int* lits, int n)
     ci.flag = F_SUB | F_STR;                        // fresh clause: can_subsume, can_strengthen
     ci.stamp = scan_id; ci.ver = 0;
     C.push_back(ci);
+    if ((c >> 6) >= delbits.size()) { delbits.resize((c >> 6) + 1024, 0); }
     ++n_live;
     pool.insert(pool.end(), lits, lits + n);
     ca_size += 2 + n;                               // ClauseAllocator::clauseWord32Size, SolverTypes.h:641-644
@@ -191,7 +192,7 @@ bool Engine::solverSimplify()
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i]; const int32_t* l = CL(c); bool sat = false;
         for (uint32_t k = 0; k < C[c].size; ++k) { if (value(l[k]) == L_TRUE) { sat = true; break; } }
-        if (sat) { caFree(c); C[c].flag |= F_DEL; --n_live; }
+        if (sat) { caFree(c); C[c].flag |= F_DEL; delbits[c >> 6] |= 1ull << (c & 63); --n_live; }
         else { clauses[j++] = c; lits += C[c].size; }
     }
     clauses.resize(j);
@@ -341,15 +342,13 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
 const Engine::CacheEnt* Engine::cached(const ScanCache& cache, uint32_t c) const
 {
     if (c >= cache.slot.size()) { return nullptr; }
-    if (cache.slot[c] < 0) {
-        return (cache.bulk_all && c < cache.bulk_ncl && C[c].stamp < cache.bulk_scan) ? &cache.empty : nullptr;
-    }
     for (int32_t i = cache.slot[c]; i >= 0; i = cache.ent[i].next) {
         const CacheEnt* e = &cache.ent[i];
         if (e->ver != UINT32_MAX) { if (e->ver == C[c].ver) { return e; } continue; }
         if (e->lit_n == C[c].size && !memcmp(cache.lits.data() + e->lit_off, CL(c), sizeof(int32_t) * e->lit_n)) { return e; }
     }
-    return nullptr;
+    // no record: a clause that is unchanged since the full-queue scan had no hit there
+    return (cache.bulk_all && c < cache.bulk_ncl && C[c].stamp < cache.bulk_scan) ? &cache.empty : nullptr;
 }
 
 // Scan explicit literal contents (predicted future versions of clauses) against the current device state.
@@ -498,7 +497,7 @@ void Engine::occPush(int x, uint32_t c)
 void Engine::occSwapRemove(int x, uint32_t i)
 {
     OccList& l = occ[x]; uint32_t* p = LP(l);
-    if ((C[p[i]].flag & F_DEL) && occ[x].stale > 0) { --occ[x].stale; }
+    if (isDel(p[i]) && occ[x].stale > 0) { --occ[x].stale; }
     p[i] = p[l.n - 1]; l.n--;
 }
 void Engine::occRelease(int x) { occ[x].n = 0; occ[x].stale = 0; }
@@ -512,7 +511,7 @@ void Engine::touchClauseVars(uint32_t c)
 void Engine::setDeleted(uint32_t c)
 {
     if (C[c].flag & F_DEL) { return; }
-    C[c].flag |= F_DEL; --n_live;
+    C[c].flag |= F_DEL; delbits[c >> 6] |= 1ull << (c & 63); --n_live;
     const int32_t* l = CL(c);
     for (uint32_t k = 0; k < C[c].size; ++k) { ++occ[l[k]].stale; ++var_touch[l[k] >> 1]; }
     // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
@@ -780,9 +779,10 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
                 const uint32_t d = LP(list)[i];
                 if (d == cr) { continue; }
                 sub_steps++;
-                if (C[d].size < cn) { continue; }
-                if (C[d].flag & F_DEL) { occSwapRemove(min, i); --i; continue; }
-                if (findHit(c_sub.hits, e->hb, e->he, d) && subHitValid(cr, d, e->scan)) {
+                // reference order: size filter, then lazy removal of deleted entries, then the subsumption test.
+                // For a live clause the size filter is implied by the test, so only deleted entries need C[d].
+                if (isDel(d)) { if (C[d].size < cn) { continue; } occSwapRemove(min, i); --i; continue; }
+                if (e->hb != e->he && findHit(c_sub.hits, e->hb, e->he, d) && subHitValid(cr, d, e->scan)) {
                     ++subsumedClauses; subsumedLiterals += (int)C[d].size;
                     setDeleted(d);
                     removedClause(d, false, false, VAR_UNDEF);
@@ -836,6 +836,13 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
     const CacheEnt* e = cached(c_str, cr);
     if (e) { if (e->ver == UINT32_MAX) { ++n_spec_used; } return e; }
     ++n_ondemand;
+    if (getenv("CP3_DEBUG_ONDEMAND") && n_ondemand < 12) {
+        fprintf(stderr, "ondemand cr=%u size=%u ver=%u stamp=%u flag=%u slot=%d bulk_all=%d bulk_scan=%u bulk_ncl=%u qtime=%d\n", cr, (unsigned)C[cr].size, C[cr].ver, C[cr].stamp,
+                (unsigned)C[cr].flag, cr < c_str.slot.size() ? c_str.slot[cr] : -9, (int)c_str.bulk_all, c_str.bulk_scan, c_str.bulk_ncl, cr < qtime.size() ? qtime[cr] : -9);
+        for (int32_t i = cr < c_str.slot.size() ? c_str.slot[cr] : -1; i >= 0; i = c_str.ent[i].next) {
+            fprintf(stderr, "   ent ver=%u n=%u time=%f hits=%u\n", c_str.ent[i].ver, c_str.ent[i].lit_n, c_str.ent[i].time, c_str.ent[i].he - c_str.ent[i].hb);
+        }
+    }
     std::vector<uint32_t> ids;
     if (c_str.slot.size() < C.size()) { c_str.slot.resize(C.size(), -1); }
     for (uint32_t c : dirty_str) {
@@ -917,8 +924,10 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 const uint32_t other = LP(list)[j];
                 if (other == cr) { continue; }
                 str_steps++;
-                if (C[other].size == 0) { break; }
-                if (C[other].flag & F_DEL) { occSwapRemove(min, j); --j; continue; }
+                // (Subsumption.cc:1331 breaks on an empty clause; one can only exist after ok became false, and
+                //  every path that creates it returns before this loop is reached again)
+                if (isDel(other)) { occSwapRemove(min, j); --j; continue; }
+                if (e->hb == e->he) { continue; }
                 const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
                 if (h && h->lit != nmin && strHitValid(cr, other, h->lit, e->scan)) {
                     const int32_t* t = CL(other); int pos = -1;
@@ -937,7 +946,8 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list_neg)[j];
                 str_steps++;
-                if (C[other].flag & F_DEL) { occSwapRemove(nmin, j); --j; continue; }
+                if (isDel(other)) { occSwapRemove(nmin, j); --j; continue; }
+                if (e->hb == e->he) { continue; }
                 const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
                 if (h && h->lit == nmin && strHitValid(cr, other, h->lit, e->scan)) {
                     const int32_t* t = CL(other); int pos = -1;

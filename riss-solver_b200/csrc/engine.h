@@ -136,6 +136,8 @@ private:
         void clear();
     };
     uint32_t n_live = 0;                             // clauses without F_DEL
+    std::vector<uint64_t> delbits;                   // F_DEL as a cache-resident bitmap for the list walks
+    inline bool isDel(uint32_t c) const { return (delbits[c >> 6] >> (c & 63)) & 1; }
     struct SpecReq { uint32_t clause; uint32_t off, n; double time; };   // literals in spec_lits[off..off+n)
     std::vector<int32_t> spec_lits;
     void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache);

@@ -1,0 +1,103 @@
+"""Host logic of the product (ordered-commit engine + C ABI, riss-solver_b200/csrc/engine.cpp, capi.cpp) linked
+against the CPU mock of the scan service (tests/mock) - no GPU needed.  The mock answers what the kernels answer,
+so these tests pin the commit order, the bookkeeping quirks and the speculative-closure cache against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import riss_solver_b200 as rs
+from harness import run_oracle, compare, Result
+from fuzz_engine import build_mock, run_engine
+from fuzz_oracle import OPTSETS, random_instance
+from test_oracle_golden import GOLD, golden_result
+
+
+@pytest.fixture(scope="module")
+def mock():
+    return build_mock()
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_engine_matches_reference_golden(mock, case):
+    got = run_engine(np.array(case["input"], np.int32), case["options"], mock)
+    has_units = any(len(c) == 1 for c in _clauses(case["input"]))
+    assert compare(got, golden_result(case), ordered=not has_units) == []
+
+
+def _clauses(stream):
+    out, cur = [], []
+    for x in stream:
+        if x == 0:
+            out.append(cur); cur = []
+        else:
+            cur.append(x)
+    return out
+
+
+@pytest.mark.parametrize("bulk_min", ["0", "4096"])
+def test_engine_fuzz_against_oracle(mock, gen, bulk_min, monkeypatch):
+    # CP3_BULK_MIN=0 forces the full-queue (bulk) scan path on tiny formulas as well
+    monkeypatch.setenv("CP3_BULK_MIN", bulk_min)
+    rng = np.random.default_rng(31337 + int(bulk_min))
+    for r in range(150):
+        lits, sizes = random_instance(rng)
+        stream = gen.csr_to_stream(lits, sizes)
+        opts = OPTSETS[int(rng.integers(0, len(OPTSETS)))]
+        a = run_engine(stream, opts, mock); b = run_oracle(stream, opts)
+        assert compare(a, b) == [], (r, opts)
+
+
+def test_engine_planted_50k(mock, gen):
+    lits, sizes = gen.random_ksat(50000, 213000, 3, seed=5)
+    stream = gen.csr_to_stream(lits, sizes)
+    for opts in (["-enabled_cp3", "-subsimp"], ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]):
+        a = run_engine(stream, opts, mock); b = run_oracle(stream, opts)
+        assert compare(a, b) == []
+    # the speculative closure must have answered almost every re-scan of a strengthened clause
+    assert a.extra["scan_ondemand"] < 50
+
+
+def test_cp_api_surface(mock):
+    """literal-by-literal API, output iteration, counters, model extension (libcoprocessorc.h call sequence)"""
+    cp = rs.Coprocessor(lib_path=mock)
+    cp.parse_options("-enabled_cp3 -subsimp -bve")
+    for x in [-1, 2, 0, -2, 3, 0, -3, 1, 0, 2, 7, 6, 0, 2, -7, -6, 0, -6, 7, 0, -7, 6, 0]:   # regression/cnfs/sat.cnf
+        cp.add_lit(x)
+    assert cp.n_vars() == 7 and cp.n_clauses() == 7
+    cp.preprocess()
+    assert cp.ok() and cp.n_clauses() == 0                # everything eliminated
+    assert list(cp.iter_output()) == []
+    model = cp.extend_model([])
+    assert len(model) == 7
+    sat = lambda cl: any((l > 0) == (model[abs(l) - 1] > 0) for l in cl)
+    for cl in [[-1, 2], [-2, 3], [-3, 1], [2, 7, 6], [2, -7, -6], [-6, 7], [-7, 6]]:
+        assert sat(cl), (cl, model)
+    cp.close()
+
+
+def test_unknown_and_unsupported_options(mock):
+    cp = rs.Coprocessor(lib_path=mock)
+    cp.parse_options("-enabled_cp3 -subsimp -this_flag_does_not_exist -cp3_threads=4")   # ignored like the reference
+    cp.add_stream(np.array([1, 2, 0, 1, 2, 3, 0], np.int32))
+    cp.preprocess()
+    assert cp.ok() and cp.n_clauses() == 1
+    cp.close()
+
+
+def test_freeze_blocks_elimination(mock):
+    stream = np.array([-1, 2, 0, -2, 3, 0, -3, 1, 0, 2, 7, 6, 0, 2, -7, -6, 0, -6, 7, 0, -7, 6, 0], np.int32)
+    from harness import Oracle
+    o = Oracle(["-enabled_cp3", "-bve"]); o.add(stream)
+    for v in (1, 2, 3):
+        o.freeze(v)
+    o.preprocess(); want = o.result(); o.close()
+    cp = rs.Coprocessor(["-enabled_cp3", "-bve"], lib_path=mock)
+    cp.add_stream(stream)
+    for v in (1, 2, 3):
+        cp.freeze(v)
+    cp.preprocess()
+    out = cp.output_stream()
+    assert np.array_equal(out[2 * cp.output_units():], want.stream)
+    cp.close()
