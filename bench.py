@@ -206,11 +206,13 @@ def main():
     opts = SUSI + [f"-cp3_gpu_device={local}"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
 
-    uid = None
-    if world > 1 and args.mode == "sharded":
+    def fresh_uid():
+        # one ncclUniqueId per communicator: every Coprocessor instance of the sharded mode gets its own
+        if not (world > 1 and args.mode == "sharded"):
+            return None
         box = [rs.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        uid = box[0]
+        return box[0]
 
     # ---------------- leg 1: device-resident bulk pass (value, roofline)
     svc = rs.ScanService(local)
@@ -244,8 +246,9 @@ def main():
     def e2e_step():
         cp = rs.Coprocessor(opts)
         cp.add_stream(stream)                         # host-side ingest (CPaddLit stream), not timed
-        if uid is not None:
-            cp.set_distributed(rank, world, uid)
+        uid = fresh_uid()
+        if uid is not None and cp.set_distributed(rank, world, uid) != 0:
+            raise SystemExit("CPsetDistributed failed (NCCL communicator)")
         barrier()
         t0 = time.perf_counter()
         cp.preprocess()
