@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unordered_set>
 
 namespace cp3 {
 
@@ -399,42 +400,44 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
 void Engine::prefetchStrengthenClosure()
 {
     PhaseTimer pt(ph_prefetch);
-    struct Ev { double time; int lit; };
-    std::unordered_map<uint32_t, std::vector<Ev>> events;
-    std::unordered_map<uint32_t, std::vector<uint64_t>> requested;     // content hashes already scanned
+    struct Ev { uint32_t clause; int32_t lit; double time; };
+    std::vector<Ev> evs;                                 // all predicted removals so far, sorted by (clause, time)
+    std::unordered_set<uint64_t> requested;              // hash of (clause, content) already scanned
     size_t first_ent = 0;
     for (int round = 0; round < 8; ++round) {
         std::vector<uint32_t> changed;
+        const size_t old_n = evs.size();
         for (size_t ei = first_ent; ei < c_str.ent.size(); ++ei) {
             const CacheEnt& e = c_str.ent[ei];
-            for (uint32_t h = e.hb; h < e.he; ++h) {
-                const Hit& ht = c_str.hits[h];
-                std::vector<Ev>& ev = events[ht.clause];
-                bool dup = false;
-                for (const Ev& x : ev) { if (x.lit == ht.lit) { dup = true; break; } }
-                if (dup) { continue; }
-                ev.push_back({e.time, ht.lit});
-                changed.push_back(ht.clause);
-            }
+            for (uint32_t h = e.hb; h < e.he; ++h) { evs.push_back({c_str.hits[h].clause, c_str.hits[h].lit, e.time}); }
         }
         first_ent = c_str.ent.size();
-        if (changed.empty()) { break; }
+        if (evs.size() == old_n) { break; }
+        for (size_t i = old_n; i < evs.size(); ++i) { changed.push_back(evs[i].clause); }
+        // a literal can be removed once: keep the earliest prediction per (clause, literal)
+        std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) {
+            return a.clause != b.clause ? a.clause < b.clause : (a.lit != b.lit ? a.lit < b.lit : a.time < b.time); });
+        evs.erase(std::unique(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.clause == b.clause && a.lit == b.lit; }), evs.end());
+        std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.clause != b.clause ? a.clause < b.clause : a.time < b.time; });
         std::sort(changed.begin(), changed.end());
         changed.erase(std::unique(changed.begin(), changed.end()), changed.end());
         std::vector<SpecReq> reqs; spec_lits.clear();
+        size_t p = 0;
         for (uint32_t d : changed) {
-            if (C[d].flag & F_DEL) { continue; }
-            std::vector<Ev>& ev = events[d];
-            std::stable_sort(ev.begin(), ev.end(), [](const Ev& a, const Ev& b) { return a.time < b.time; });
+            while (p < evs.size() && evs[p].clause < d) { ++p; }
+            size_t q = p;
+            while (q < evs.size() && evs[q].clause == d) { ++q; }
+            const Ev* ev = evs.data() + p; const size_t m = q - p;
+            p = q;
+            if ((C[d].flag & F_DEL) || m == 0) { continue; }
             const bool pending = (C[d].flag & F_STR) && d < qtime.size() && qtime[d] >= 0;
             const double own = pending ? (double)qtime[d] : -1.0;
             size_t k0 = 0;
-            if (pending) { while (k0 < ev.size() && ev[k0].time < own) { ++k0; } }
-            std::vector<uint64_t>& done = requested[d];
-            for (size_t k = std::max<size_t>(k0, 1); k <= ev.size(); ++k) {
+            if (pending) { while (k0 < m && ev[k0].time < own) { ++k0; } }
+            for (size_t k = std::max<size_t>(k0, 1); k <= m && k <= 6; ++k) {
                 if (C[d].size < k + 2) { break; }          // would be a unit: handled by propagation, never scanned
                 // content = current literals minus the first k predicted removals
-                uint64_t hsh = 1469598103934665603ull;
+                uint64_t hsh = 1469598103934665603ull ^ d;
                 const uint32_t off = (uint32_t)spec_lits.size();
                 const int32_t* l = CL(d);
                 for (uint32_t i = 0; i < C[d].size; ++i) {
@@ -443,8 +446,7 @@ void Engine::prefetchStrengthenClosure()
                     if (!rm) { spec_lits.push_back(l[i]); hsh = (hsh ^ (uint32_t)l[i]) * 1099511628211ull; }
                 }
                 const uint32_t nl = (uint32_t)spec_lits.size() - off;
-                if (nl != C[d].size - k || std::find(done.begin(), done.end(), hsh) != done.end()) { spec_lits.resize(off); continue; }
-                done.push_back(hsh);
+                if (nl != C[d].size - k || !requested.insert(hsh).second) { spec_lits.resize(off); continue; }
                 const double t = (pending && k == k0) ? own : std::max(own, ev[k - 1].time) + 1e-3 * (round + 1);
                 reqs.push_back({d, off, nl, t});
             }
@@ -459,24 +461,35 @@ static inline bool containsLit(const int32_t* l, uint32_t n, int x)
     return std::binary_search(l, l + n, x);
 }
 
+void Engine::logClear()
+{
+    for (uint32_t c : log_touched) { log_head[c] = -1; }
+    log_touched.clear(); log_nodes.clear();
+}
+void Engine::logPush(uint32_t c, int lit, bool pendingOcc)
+{
+    if (c >= log_head.size()) { log_head.resize(C.size() + 1024, -1); }
+    if (log_head[c] < 0) { log_touched.push_back(c); }
+    log_nodes.push_back({scan_id, lit, log_head[c], pendingOcc ? pend_epoch : 0u});
+    log_head[c] = (int32_t)log_nodes.size() - 1;
+}
+
 // A snapshot hit "C subsumes D" stays true unless D lost a literal of C afterwards.
 bool Engine::subHitValid(uint32_t c, uint32_t d, uint32_t scan) const
 {
-    if (C[d].stamp < scan) { return true; }
-    auto it = edit_log.find(d);
-    if (it == edit_log.end()) { return true; }
-    for (const Removal& r : it->second) { if (r.stamp >= scan && containsLit(CL(c), C[c].size, r.lit)) { return false; } }
+    if (C[d].stamp < scan || d >= log_head.size()) { return true; }
+    for (int32_t i = log_head[d]; i >= 0; i = log_nodes[i].next) {
+        if (log_nodes[i].stamp >= scan && containsLit(CL(c), C[c].size, log_nodes[i].lit)) { return false; }
+    }
     return true;
 }
 // A snapshot hit "S strengthens D on literal f" stays true unless D lost f or a literal of S afterwards.
 bool Engine::strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const
 {
-    if (C[d].stamp < scan) { return true; }
-    auto it = edit_log.find(d);
-    if (it == edit_log.end()) { return true; }
-    for (const Removal& r : it->second) {
-        if (r.stamp < scan) { continue; }
-        if (r.lit == f || containsLit(CL(s), C[s].size, r.lit)) { return false; }
+    if (C[d].stamp < scan || d >= log_head.size()) { return true; }
+    for (int32_t i = log_head[d]; i >= 0; i = log_nodes[i].next) {
+        if (log_nodes[i].stamp < scan) { continue; }
+        if (log_nodes[i].lit == f || containsLit(CL(s), C[s].size, log_nodes[i].lit)) { return false; }
     }
     return true;
 }
@@ -515,17 +528,16 @@ void Engine::setDeleted(uint32_t c)
     const int32_t* l = CL(c);
     for (uint32_t k = 0; k < C[c].size; ++k) { ++occ[l[k]].stale; ++var_touch[l[k] >> 1]; }
     // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
-    if (!pend_rm.empty()) {
-        auto it = pend_rm.find(c);
-        if (it != pend_rm.end()) { for (int l2 : it->second) { ++occ[l2].stale; } }
+    if (c < log_head.size()) {
+        for (int32_t i = log_head[c]; i >= 0; i = log_nodes[i].next) { if (log_nodes[i].pending == pend_epoch) { ++occ[log_nodes[i].lit].stale; } }
     }
     if (dev_uploaded) { pend_del.push_back(c); }
 }
 
-void Engine::noteShrunk(uint32_t c, int removedLit)
+void Engine::noteShrunk(uint32_t c, int removedLit, bool pendingOcc)
 {
+    logPush(c, removedLit, pendingOcc);
     ++C[c].ver; C[c].stamp = scan_id;
-    edit_log[c].push_back({scan_id, removedLit});
     if (dev_uploaded && c < shrunk_mark.size() && !shrunk_mark[c]) { shrunk_mark[c] = 1; pend_shrunk.push_back(c); }
     else if (dev_uploaded && c >= shrunk_mark.size()) { /* not yet on the device: appended with current content */ }
     touchClauseVars(c); ++var_touch[removedLit >> 1];
@@ -696,7 +708,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
             for (uint32_t j = 0; j < C[c].size; ++j) {
                 if (lits[j] == nl) {
                     if (!sort) { removePosUnsorted(c, (int)j); } else { removePosSorted(c, (int)j); }
-                    noteShrunk(c, nl);
+                    noteShrunk(c, nl, false);
                     t_up.modified = true;
                     count++;
                     break;
@@ -742,7 +754,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_sub);
     const bool unlimited = !opt.limited;
-    c_sub.clear(); edit_log.clear();
+    c_sub.clear(); logClear();
     {
         std::vector<uint32_t> ids;
         ids.reserve(subq.size());
@@ -804,7 +816,7 @@ void Engine::updateOccurrences(bool useHeap, int ignore)
 {
     // from here on nothing is pending any more (setDeleted() consults pend_rm)
     std::vector<OccUpd> ups; ups.swap(occ_upd);
-    pend_rm.clear();
+    ++pend_epoch;
     for (const OccUpd& u : ups) {
         if (removeClauseFrom(u.cr, u.l)) { removedLiteral(u.l, 1, useHeap, ignore != 0, VAR_UNDEF); }
     }
@@ -819,9 +831,8 @@ void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, in
     successful(t_sub);
     const int lit = CL(other)[pos];
     occ_upd.push_back({other, lit});
-    pend_rm[other].push_back(lit);
     removePosSorted(other, pos);
-    noteShrunk(other, lit);
+    noteShrunk(other, lit, true);
     dirty_str.push_back(other);
     if (C[other].size == 1) {
         dataEnqueue(CL(other)[0]);
@@ -865,7 +876,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_str);
     const bool unlimited = !opt.limited;
-    c_str.clear(); edit_log.clear(); dirty_str.clear();
+    c_str.clear(); logClear(); dirty_str.clear();
     if (opt.strength) {
         std::vector<uint32_t> ids;
         for (uint32_t c : strq) {

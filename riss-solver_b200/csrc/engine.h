@@ -115,7 +115,6 @@ private:
     std::vector<int> pos_stats, neg_stats, touched;
     struct OccUpd { uint32_t cr; int l; };
     std::vector<OccUpd> occ_upd; std::vector<uint32_t> sub_occ_updates;
-    std::unordered_map<uint32_t, std::vector<int>> pend_rm;   // literals whose occ entry removal is pending
 
     // ---------------- device replica + scan cache
     cp3g* gpu = nullptr;
@@ -123,8 +122,12 @@ private:
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
     std::vector<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far
-    struct Removal { uint32_t stamp; int lit; };
-    std::unordered_map<uint32_t, std::vector<Removal>> edit_log;          // literals removed per clause
+    // literals removed per clause during the current pass: per-clause chains in one flat node array
+    struct LogNode { uint32_t stamp; int32_t lit; int32_t next; uint32_t pending; };
+    std::vector<LogNode> log_nodes; std::vector<int32_t> log_head; std::vector<uint32_t> log_touched;
+    uint32_t pend_epoch = 1;                         // LogNode.pending == pend_epoch: occ entry removal still pending
+    void logClear();
+    void logPush(uint32_t c, int lit, bool pendingOcc);
     // one scanned content version of a clause: keyed by the edit counter (ver) when the device copy was
     // scanned by id, or by the literal content itself (ver == UINT32_MAX) for speculative versions
     struct CacheEnt { uint32_t ver, scan, hb, he; int32_t next; uint32_t lit_off, lit_n; double time; };
@@ -177,7 +180,7 @@ private:
     void occSwapRemove(int x, uint32_t i);            // list[i] = back; pop  (+ stale bookkeeping)
     void occRelease(int x);
     void setDeleted(uint32_t c);                      // mark + stale + device edit
-    void noteShrunk(uint32_t c, int removedLit);      // bookkeeping after a literal left clause c
+    void noteShrunk(uint32_t c, int removedLit, bool pendingOcc);      // bookkeeping after a literal left clause c
 
     // CoprocessorData bookkeeping (CoprocessorTypes.h:812-878,1243-1350,1615-1655,1815-1831)
     void deletedVar(int v) { modTimer[v] = modStep; }

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -29,8 +30,6 @@
 #define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g->fail(#call, _e); return CP3G_ERR_CUDA; } } while (0)
 
 static constexpr uint32_t FLAG_DEL = 0x80000000u;
-static constexpr uint32_t ENT_MIN_SUB = 0x40000000u;   // this entry's list is the clause's shortest list (K3 bulk)
-static constexpr uint32_t ENT_MIN_STR = 0x20000000u;   // ... shortest list pair of a variable (K4 bulk)
 static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
 
@@ -150,15 +149,13 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
         ent_lit[off[x] + p] = (uint32_t)x;
     }
 }
-// after the per-list sort: tag, for every clause, its entry in the list a bulk scan walks for it
-__device__ __forceinline__ void mark_entry(const uint32_t* __restrict__ off, OccEnt* __restrict__ ent, int32_t x, uint32_t c, uint32_t bit)
-{
-    uint32_t lo = off[x], hi = off[x + 1];
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (ent[mid].ref < c) { lo = mid + 1; } else { hi = mid; } }
-    ent[lo].szfl |= bit;          // exists: the clause contains x
-}
-__global__ void k_mark_min(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                           const uint32_t* __restrict__ off, OccEnt* __restrict__ ent)
+// The "tagged" CSR of the candidate-major bulk kernels: clause c is filed under the literal whose list a bulk
+// scan walks for it (xs for subsumption, xt for strengthening).  phase 0 counts, phase 1 fills.
+__global__ void k_tag(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+                      const uint32_t* __restrict__ off, int phase,
+                      uint32_t* __restrict__ cnt_sub, uint32_t* __restrict__ cnt_str,
+                      const uint32_t* __restrict__ toff_sub, const uint32_t* __restrict__ toff_str,
+                      OccEnt* __restrict__ tag_sub, OccEnt* __restrict__ tag_str)
 {
     uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) { return; }
@@ -174,8 +171,12 @@ __global__ void k_mark_min(const ClauseHdr* __restrict__ hdr, const int32_t* __r
         if (len < bs) { bs = len; xs = x; }
         if (both < bt) { bt = both; xt = x; }
     }
-    mark_entry(off, ent, xs, c, ENT_MIN_SUB);
-    mark_entry(off, ent, xt, c, ENT_MIN_STR);
+    if (phase == 0) { atomicAdd(&cnt_sub[xs], 1u); atomicAdd(&cnt_str[xt], 1u); }
+    else {
+        OccEnt e; e.ref = c; e.szfl = sz; e.sig = h.sig;
+        tag_sub[toff_sub[xs] + atomicAdd(&cnt_sub[xs], 1u)] = e;
+        tag_str[toff_str[xt] + atomicAdd(&cnt_str[xt], 1u)] = e;
+    }
 }
 // scatter order is nondeterministic; the reference order is ascending clause index -> sort every list
 __global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, OccEnt* __restrict__ ent,
@@ -224,6 +225,41 @@ __global__ void k_occ_sort_long(const uint32_t* __restrict__ off, const uint32_t
     }
 }
 
+// Hits are appended to one global list.  A same-address atomicAdd per hit serialises in L2 (~1 ns each: at C2
+// the 3*10^5 hits of a full-queue pass cost more than the scan itself), so every block stages its hits in
+// shared memory and reserves their slots with ONE global atomic when it finishes.
+static constexpr int SINK_CAP = 96;
+struct HitSink {
+    cp3g_hit* s_hits; uint32_t* s_n;
+    cp3g_hit* out; uint32_t cap; uint32_t* nout;
+    __device__ __forceinline__ void emit(uint32_t req, uint32_t clause, int32_t lit) const
+    {
+        const uint32_t p = atomicAdd(s_n, 1u);
+        if (p < (uint32_t)SINK_CAP) { s_hits[p].req = req; s_hits[p].clause = clause; s_hits[p].lit = lit; }
+        else {      // staging area full (a block with very many hits): fall back to the global counter
+            const uint32_t q = atomicAdd(nout, 1u);
+            if (q < cap) { out[q].req = req; out[q].clause = clause; out[q].lit = lit; }
+        }
+    }
+    // all threads of the block must call this (contains __syncthreads)
+    __device__ __forceinline__ void flush(uint32_t* s_base) const
+    {
+        __syncthreads();
+        const uint32_t n = min(*s_n, (uint32_t)SINK_CAP);
+        if (n == 0) { return; }               // uniform: every thread read the same value after the barrier
+        if (threadIdx.x == 0) { *s_base = atomicAdd(nout, n); }
+        __syncthreads();
+        const uint32_t base = *s_base;
+        for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) { if (base + k < cap) { out[base + k] = s_hits[k]; } }
+        __syncthreads();
+        if (threadIdx.x == 0) { *s_n = 0; }
+        __syncthreads();
+    }
+};
+#define SINK_DECL __shared__ cp3g_hit sink_hits[SINK_CAP]; __shared__ uint32_t sink_n, sink_base; \
+    if (threadIdx.x == 0) { sink_n = 0; } __syncthreads(); \
+    const HitSink sink{sink_hits, &sink_n, out, cap, nout}
+
 // ------------------------------------------------------------------------------------------ K3 / K4
 // returns true if S (sn literals) is a subset of D (dn literals); both sorted
 __device__ __forceinline__ bool merge_subset(const int32_t* __restrict__ S, uint32_t sn,
@@ -259,7 +295,7 @@ __device__ __forceinline__ void test_candidate(uint32_t ref, uint32_t szfl, unsi
                                                const int32_t* __restrict__ S, uint32_t sn, unsigned long long ssig,
                                                int32_t need_flip /* -1: any */, int32_t forbid_flip /* -1: none */,
                                                const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
-                                               uint32_t r, cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout)
+                                               uint32_t r, const HitSink& sink)
 {
     if (ref == me) { return; }
     // the occ entry caches size/sig from build time; the header is authoritative for later edits, so a
@@ -276,16 +312,10 @@ __device__ __forceinline__ void test_candidate(uint32_t ref, uint32_t szfl, unsi
     if (dn < sn) { return; }
     const int32_t* D = lits + h.start;
     if (KIND == CP3G_SUBSUME) {
-        if ((ssig & ~h.sig) == 0 && merge_subset(S, sn, D, dn)) {
-            const uint32_t p = atomicAdd(nout, 1u);
-            if (p < cap) { out[p].req = r; out[p].clause = ref; out[p].lit = -1; }
-        }
+        if ((ssig & ~h.sig) == 0 && merge_subset(S, sn, D, dn)) { sink.emit(r, ref, -1); }
     } else {
         const int32_t f = merge_one_flip(S, sn, D, dn);
-        if (f >= 0 && (need_flip < 0 || f == need_flip) && f != forbid_flip) {
-            const uint32_t p = atomicAdd(nout, 1u);
-            if (p < cap) { out[p].req = r; out[p].clause = ref; out[p].lit = f; }
-        }
+        if (f >= 0 && (need_flip < 0 || f == need_flip) && f != forbid_flip) { sink.emit(r, ref, f); }
     }
 }
 
@@ -300,19 +330,23 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
         unsigned long long* __restrict__ checks)
 {
+    SINK_DECL;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t r = req_begin + warp;
-    if (r >= req_end) { return; }
-    const uint32_t me = self[r];
-    const int32_t* S; uint32_t sn;
-    if (req_lits != nullptr) { S = req_lits + req_off[r]; sn = req_off[r + 1] - req_off[r]; }
-    else {
-        const ClauseHdr h = hdr[me];
-        if (h.szfl & FLAG_DEL) { return; }
-        S = lits + h.start; sn = h.szfl & SIZE_MASK;
+    bool live = r < req_end;
+    uint32_t me = 0; const int32_t* S = nullptr; uint32_t sn = 0;
+    if (live) {
+        me = self[r];
+        if (req_lits != nullptr) { S = req_lits + req_off[r]; sn = req_off[r + 1] - req_off[r]; }
+        else {
+            const ClauseHdr h = hdr[me];
+            if (h.szfl & FLAG_DEL) { live = false; }
+            S = lits + h.start; sn = h.szfl & SIZE_MASK;
+        }
+        if (sn == 0) { live = false; }
     }
-    if (sn == 0) { return; }
+    if (live) {
     // signature of the request and the cheapest list: lanes take literals round robin
     unsigned long long ssig = 0; uint32_t best_len = 0xffffffffu; uint32_t best_idx = 0;
     for (uint32_t k = lane; k < sn; k += 32) {
@@ -337,7 +371,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
             const OccEnt en = occ_ent[i];
             if (en.ref != me) { nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK); }
             // a stale entry could flip on x itself; that hit belongs to the occ(~x) pass below
-            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, -1, x ^ 1, hdr, lits, r, out, cap, nout);
+            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, -1, x ^ 1, hdr, lits, r, sink);
         }
     }
     if (KIND == CP3G_STRENGTHEN) {
@@ -346,7 +380,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         for (uint32_t i = b + lane; i < e; i += 32) {
             const OccEnt en = occ_ent[i];
             nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
-            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, out, cap, nout);
+            test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, sink);
         }
     }
     // clauses younger than the CSR (resolvents): brute force, they are few
@@ -354,58 +388,81 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         const uint32_t ref = ovf[i];
         const ClauseHdr h = hdr[ref];
         if (ref != me) { nchk += 1; nbytes += 12 + 4 * (h.szfl & SIZE_MASK); }
-        test_candidate<KIND>(ref, h.szfl, h.sig, me, S, sn, ssig, -1, -1, hdr, lits, r, out, cap, nout);
+        test_candidate<KIND>(ref, h.szfl, h.sig, me, S, sn, ssig, -1, -1, hdr, lits, r, sink);
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
     if (lane == 0 && nchk) { atomicAdd(checks, nchk); atomicAdd(checks + 1, nbytes); }
     // (one same-address atomic pair per request: fine for the small incremental batches this kernel serves;
     //  full-queue passes go through k_bulk, which reduces per block)
+    }
+    sink.flush(&sink_base);
 }
 
 // ------------------------------------------------------------------------------------------ K3 / K4 bulk
-// Full-queue pass (every live clause is a subsumer / strengthener): one thread per occurrence entry.  The
-// thread whose entry carries the MIN tag plays that clause against the rest of the same list (and, for
-// strengthening, the list of the complementary literal).  Threads of a warp own 32 consecutive entries, so
-// the lists they walk are the cache lines the warp has just loaded: every list is streamed from HBM once
-// for all of its subsumers, instead of once per subsumer.
+// Full-queue pass (every live clause is a subsumer / strengthener).
+// rare path of k_bulk: the 16-byte entry of the candidate passed size + signature filters
 template <int KIND>
-__global__ void __launch_bounds__(256) k_bulk(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
-        const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent, const uint32_t* __restrict__ ent_lit,
+__device__ __forceinline__ void bulk_candidate_inl(uint32_t sref, uint32_t dref, int32_t need_flip, int32_t forbid_flip,
+                                            const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+                                            const HitSink& sink)
+{
+    const ClauseHdr hs = hdr[sref], hd = hdr[dref];
+    if ((hs.szfl | hd.szfl) & FLAG_DEL) { return; }
+    const uint32_t sn = hs.szfl & SIZE_MASK, dn = hd.szfl & SIZE_MASK;
+    if (dn < sn) { return; }
+    const int32_t* S = lits + hs.start; const int32_t* D = lits + hd.start;
+    if (KIND == CP3G_SUBSUME) {
+        if (merge_subset(S, sn, D, dn)) { sink.emit(sref, dref, -1); }
+    } else {
+        const int32_t f = merge_one_flip(S, sn, D, dn);
+        if (f >= 0 && (need_flip < 0 || f == need_flip) && f != forbid_flip) { sink.emit(sref, dref, f); }
+    }
+}
+
+// Candidate-major form of the full-queue pass: one thread per occurrence entry *as the candidate*.  The
+// thread streams its own 16-byte entry (perfectly coalesced) and tests it against the few clauses that are
+// filed under this literal in the tagged CSR, i.e. the subsumers / strengtheners whose bulk scan walks this
+// list.  All 32 lanes work, trip counts are tiny and uniform, neighbours read the same tagged entries.
+template <int KIND>
+__global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+        const OccEnt* __restrict__ occ_ent, const uint32_t* __restrict__ ent_lit, const uint32_t* __restrict__ delbits,
+        const uint32_t* __restrict__ toff, const OccEnt* __restrict__ tag,
         uint32_t first, uint32_t last, cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
         unsigned long long* __restrict__ checks)
 {
     __shared__ unsigned long long sh_chk[8], sh_byt[8];
-    const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+    SINK_DECL;
     unsigned long long nchk = 0, nbytes = 0;
-    if (i < last) {
-        const OccEnt me = occ_ent[i];
-        if (me.szfl & (KIND == CP3G_SUBSUME ? ENT_MIN_SUB : ENT_MIN_STR)) {
-            const ClauseHdr hs = hdr[me.ref];
-            if (!(hs.szfl & FLAG_DEL)) {
-                const int32_t* S = lits + hs.start; const uint32_t sn = hs.szfl & SIZE_MASK;
-                const unsigned long long ssig = hs.sig;
-                const int32_t x = (int32_t)ent_lit[i];
-                {
-                    const uint32_t b = occ_off[x], e = occ_off[x + 1];
-                    for (uint32_t j = b; j < e; ++j) {
-                        if (j == i) { continue; }
-                        const OccEnt en = occ_ent[j];
-                        nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
-                        test_candidate<KIND>(en.ref, en.szfl, en.sig, me.ref, S, sn, ssig, -1, x ^ 1, hdr, lits, me.ref, out, cap, nout);
-                    }
-                }
-                if (KIND == CP3G_STRENGTHEN) {
-                    const int32_t nx = x ^ 1;
-                    const uint32_t b = occ_off[nx], e = occ_off[nx + 1];
-                    for (uint32_t j = b; j < e; ++j) {
-                        const OccEnt en = occ_ent[j];
-                        nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
-                        test_candidate<KIND>(en.ref, en.szfl, en.sig, me.ref, S, sn, ssig, nx, -1, hdr, lits, me.ref, out, cap, nout);
-                    }
-                }
+    for (uint32_t tile = first + blockIdx.x * blockDim.x; tile < last; tile += gridDim.x * blockDim.x) {
+    const uint32_t j = tile + threadIdx.x;
+    if (j < last) {
+        const OccEnt en = occ_ent[j];
+        const int32_t l = (int32_t)ent_lit[j];
+        const uint32_t esz = en.szfl & SIZE_MASK;
+        const bool ddel = (delbits[en.ref >> 5] >> (en.ref & 31)) & 1u;
+        const unsigned long long dvar = var_fold(en.sig);
+        const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            const int32_t lx = pass == 0 ? l : (l ^ 1);         // the literal the strengthener is filed under
+            const uint32_t b = toff[lx], e = toff[lx + 1];
+            for (uint32_t k = b; k < e; ++k) {
+                const OccEnt s = tag[k];
+                if (s.ref == en.ref) { continue; }
+                nchk += 1; nbytes += 12 + 4 * esz;
+                const uint32_t sn = s.szfl & SIZE_MASK;
+                if (ddel || esz < sn) { continue; }
+                const unsigned long long miss = s.sig & ~en.sig;
+                if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
+                else { if ((miss & (miss - 1)) || (var_fold(s.sig) & ~dvar)) { continue; } }
+                if ((delbits[s.ref >> 5] >> (s.ref & 31)) & 1u) { continue; }
+                // pass 0: S holds l, any literal but ~l may be the flipped one; pass 1: S holds ~l, the flip is on l
+                bulk_candidate_inl<KIND>(s.ref, en.ref, pass == 0 ? -1 : l, pass == 0 ? (l ^ 1) : -1, hdr, lits, sink);
             }
         }
+    }
+    __syncthreads();
+    if (sink_n >= (uint32_t)(SINK_CAP / 2)) { sink.flush(&sink_base); }      // uniform: sink_n is read after the barrier
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
@@ -417,6 +474,7 @@ __global__ void __launch_bounds__(256) k_bulk(const ClauseHdr* __restrict__ hdr,
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a += sh_chk[k]; b2 += sh_byt[k]; }
         if (a) { atomicAdd(checks, a); atomicAdd(checks + 1, b2); }
     }
+    sink.flush(&sink_base);
 }
 
 // ------------------------------------------------------------------------------------------ K5 / K6
@@ -491,10 +549,24 @@ __global__ void k_bve_resolve(const ClauseHdr* __restrict__ hdr, const int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ edits
-__global__ void k_set_deleted(ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ ids, uint32_t n)
+__global__ void k_set_deleted(ClauseHdr* __restrict__ hdr, uint32_t* __restrict__ delbits, const uint32_t* __restrict__ ids, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { hdr[ids[i]].szfl |= FLAG_DEL; }
+    if (i < n) { const uint32_t c = ids[i]; hdr[c].szfl |= FLAG_DEL; atomicOr(&delbits[c >> 5], 1u << (c & 31)); }
+}
+// deleted flags as a bitmap (ncl/8 bytes: L2 resident) so the bulk kernels need no header gather for them
+__global__ void k_init_delbits(const ClauseHdr* __restrict__ hdr, uint32_t* __restrict__ delbits, uint32_t first_word, uint32_t ncl)
+{
+    const uint32_t w = first_word + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w * 32 >= ncl) { return; }
+    uint32_t bits = 0;
+    for (uint32_t k = 0; k < 32 && w * 32 + k < ncl; ++k) { if (hdr[w * 32 + k].szfl & FLAG_DEL) { bits |= 1u << k; } }
+    delbits[w] = bits;
+}
+__global__ void k_gather_refs(const OccEnt* __restrict__ ent, uint32_t* __restrict__ refs, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { refs[i] = ent[i].ref; }
 }
 __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits, const uint32_t* __restrict__ ids,
                          const uint32_t* __restrict__ nstart, const uint32_t* __restrict__ nsize,
@@ -512,14 +584,14 @@ __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits
 
 // ------------------------------------------------------------------------------------------ host side
 struct cp3g {
-    int device = 0;
+    int device = 0; int num_sms = 148;
     cudaStream_t stream = nullptr;
     std::string err;
     uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
     size_t nlits = 0;
     DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent; DevBuf<uint32_t> ent_lit; bool dirty_since_build = true;
+    DevBuf<OccEnt> occ_ent, tag_sub, tag_str; DevBuf<uint32_t> ent_lit, delbits, refs_tmp, toff_sub, toff_str, tcnt_sub, tcnt_str; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
     DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
@@ -577,6 +649,7 @@ cp3g* cp3g_create(int device)
     g->device = device;
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return nullptr; }
     cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
+    cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (g->counters.reserve(16, false, g->stream)) { delete g; return nullptr; }
     return g;
 }
@@ -587,7 +660,7 @@ void cp3g_destroy(cp3g* g)
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
-    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release();
+    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release(); g->delbits.release(); g->refs_tmp.release(); g->tag_sub.release(); g->tag_str.release(); g->toff_sub.release(); g->toff_str.release(); g->tcnt_sub.release(); g->tcnt_str.release();
     g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
@@ -615,8 +688,11 @@ int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size
         h[i].sig = 0;
     }
     CK(cudaMemcpyAsync(g->hdr.p, h.data(), (size_t)ncl * sizeof(ClauseHdr), cudaMemcpyHostToDevice, g->stream));
+    RESERVE(g->delbits, ((size_t)ncl + ncl / 4 + 1024) / 32 + 2, false);
+    CK(cudaMemsetAsync(g->delbits.p, 0, g->delbits.cap * sizeof(uint32_t), g->stream));
+    if (ncl) { k_init_delbits<<<grid_for((ncl + 31) / 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, 0, ncl); g->launches++; }
     CK(cudaStreamSynchronize(g->stream));
-    g->lits.used = nlits; g->hdr.used = ncl;
+    g->lits.used = nlits; g->hdr.used = ncl; g->delbits.used = g->delbits.cap;
     g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * sizeof(ClauseHdr));
     return CP3G_OK;
 }
@@ -658,8 +734,25 @@ static int build_csr(cp3g* g)
         g->launches += 1;
     }
     if (g->ncl) {
-        k_mark_min<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_ent.p);
-        g->launches += 1;
+        // tagged CSR for the candidate-major bulk kernels
+        RESERVE(g->toff_sub, (size_t)nlit + 2, false); RESERVE(g->toff_str, (size_t)nlit + 2, false);
+        RESERVE(g->tcnt_sub, (size_t)nlit + 2, false); RESERVE(g->tcnt_str, (size_t)nlit + 2, false);
+        RESERVE(g->tag_sub, (size_t)g->ncl + 1, false); RESERVE(g->tag_str, (size_t)g->ncl + 1, false);
+        CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
+        CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
+        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 0, g->tcnt_sub.p, g->tcnt_str.p,
+                                                          nullptr, nullptr, nullptr, nullptr);
+        for (int w = 0; w < 2; ++w) {
+            uint32_t* cntp = w == 0 ? g->tcnt_sub.p : g->tcnt_str.p; uint32_t* offp = w == 0 ? g->toff_sub.p : g->toff_str.p;
+            k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(cntp, offp, nlit + 1, g->tile_sum.p);
+            k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 3);
+            k_scan_add<<<ntiles, SCAN_T, 0, g->stream>>>(offp, nlit + 1, g->tile_sum.p);
+        }
+        CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
+        CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
+        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 1, g->tcnt_sub.p, g->tcnt_str.p,
+                                                          g->toff_sub.p, g->toff_str.p, g->tag_sub.p, g->tag_str.p);
+        g->launches += 8;
     }
     CK(cudaGetLastError());
     g->ncl_csr = g->ncl;
@@ -690,9 +783,10 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
     CK(cudaStreamSynchronize(g->stream));
     g->d2h += (int64_t)(((size_t)nlit + 1) * sizeof(uint32_t));
     if (refs && g->total_occ) {
-        // strided copy of the 4-byte ref out of the 16-byte entries
-        CK(cudaMemcpy2DAsync(refs, sizeof(uint32_t), g->occ_ent.p, sizeof(OccEnt), sizeof(uint32_t), g->total_occ,
-                             cudaMemcpyDeviceToHost, g->stream));
+        RESERVE(g->refs_tmp, g->total_occ, false);
+        k_gather_refs<<<grid_for(g->total_occ, 256), 256, 0, g->stream>>>(g->occ_ent.p, g->refs_tmp.p, g->total_occ);
+        g->launches++;
+        CK(cudaMemcpyAsync(refs, g->refs_tmp.p, (size_t)g->total_occ * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
         g->d2h += (int64_t)g->total_occ * 4;
     }
@@ -706,7 +800,7 @@ int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids)
     cudaSetDevice(g->device);
     RESERVE(g->scratch_u32, n, false);
     CK(cudaMemcpyAsync(g->scratch_u32.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
-    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->scratch_u32.p, n);
+    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, g->scratch_u32.p, n);
     CK(cudaStreamSynchronize(g->stream));
     g->launches++; g->h2d += (int64_t)n * 4;
     return CP3G_OK;
@@ -737,6 +831,12 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
     cudaSetDevice(g->device);
     RESERVE(g->lits, g->nlits + nlits, true);
     RESERVE(g->hdr, (size_t)g->ncl + n, true);
+    if (((size_t)g->ncl + n) / 32 + 2 > g->delbits.cap) {
+        const size_t oldcap = g->delbits.cap;
+        RESERVE(g->delbits, ((size_t)g->ncl + n) / 32 + 2, true);
+        CK(cudaMemsetAsync(g->delbits.p + oldcap, 0, (g->delbits.cap - oldcap) * sizeof(uint32_t), g->stream));
+        g->delbits.used = g->delbits.cap;
+    }
     std::vector<ClauseHdr> h(n);
     size_t pos = g->nlits, src = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -844,13 +944,14 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     }
     KTimer t(g);
     if (ee > eb) {
-        const unsigned blocks = grid_for(ee - eb, 256);
+        // persistent grid: 8 blocks of 256 threads per SM, each block strides over 256-entry tiles
+        const unsigned blocks = std::min<unsigned>(grid_for(ee - eb, 256), (unsigned)g->num_sms * 8u);
         if (kind == CP3G_SUBSUME) {
-            k_bulk<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ent_lit.p,
-                eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+            k_bulk_cm<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_ent.p, g->ent_lit.p, g->delbits.p,
+                g->toff_sub.p, g->tag_sub.p, eb, ee, g->hits.p, cap, g->counters.p, dchecks);
         } else {
-            k_bulk<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ent_lit.p,
-                eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+            k_bulk_cm<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_ent.p, g->ent_lit.p, g->delbits.p,
+                g->toff_str.p, g->tag_str.p, eb, ee, g->hits.p, cap, g->counters.p, dchecks);
         }
         g->launches++;
     }
