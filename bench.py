@@ -222,9 +222,15 @@ def main():
     def resident_pass():
         c0 = {k: svc.counter(k) for k in ("kernel_ns", "launches", "scan_ns", "scan_checks", "scan_alg_bytes")}
         svc.build()
+        b = svc.counter("kernel_ns") - c0["kernel_ns"]
+        s0 = svc.counter("scan_ns"); a0 = svc.counter("scan_alg_bytes"); k0 = svc.counter("scan_checks")
         svc.scan_all(rs.SUBSUME, count_only=True)
+        s1 = svc.counter("scan_ns"); a1 = svc.counter("scan_alg_bytes"); k1 = svc.counter("scan_checks")
         svc.scan_all(rs.STRENGTHEN, count_only=True)
-        return {k: svc.counter(k) - c0[k] for k in c0}
+        r = {k: svc.counter(k) - c0[k] for k in c0}
+        r.update(build_ns=b, k3_ns=s1 - s0, k3_bytes=a1 - a0, k3_checks=k1 - k0, k4_ns=svc.counter("scan_ns") - s1,
+                 k4_bytes=svc.counter("scan_alg_bytes") - a1, k4_checks=svc.counter("scan_checks") - k1)
+        return r
 
     for _ in range(args.warmup):
         flush.fill_(1); resident_pass()
@@ -280,6 +286,15 @@ def main():
             dist.all_reduce(w, op=dist.ReduceOp.SUM)
         checks, dev_checks = float(w[0]), float(w[1])
 
+    def mean(k):
+        return float(np.mean([r[k] for r in res]))
+
+    # DRAM bytes per launch of the dominant kernel from the last `ncu --set full` capture (profiles/), or None
+    TRAFFIC = None
+    try:
+        TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bulk_cm_bytes_per_launch")
+    except Exception:
+        pass
     if rank == 0:
         peaks = {}
         try:
@@ -298,10 +313,14 @@ def main():
                        "l2": "working set (occ entries + headers + literals, ~350 MB) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
                        "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank" if args.mode == "weak"
                                        else f"{world} ranks, one formula: scan requests partitioned, hits all-gathered over NCCL"))},
-            "roofline": {"bound": "hbm", "kernel": "k_bulk (K3+K4 full-queue form)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_bulk_cm (K3+K4 full-queue form, both launches)", "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                         "algorithmic_bytes_per_launch": alg_bytes / 2, "launch_ms": scan_ns * 1e-6 / 2},
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC,
+                         "algorithmic_bytes_per_launch": alg_bytes / 2, "launch_ms": scan_ns * 1e-6 / 2,
+                         "per_kernel": {
+                             "k_bulk_cm<subsume>": {"ms": mean("k3_ns") * 1e-6, "checks": mean("k3_checks"), "GB/s": mean("k3_bytes") / max(mean("k3_ns"), 1.0)},
+                             "k_bulk_cm<strengthen>": {"ms": mean("k4_ns") * 1e-6, "checks": mean("k4_checks"), "GB/s": mean("k4_bytes") / max(mean("k4_ns"), 1.0)},
+                             "K1+K2 build": {"ms": mean("build_ns") * 1e-6}}},
             "e2e": {"value": checks / T, "unit": UNIT, "ms_per_step": T * 1e3, "h2d_bytes_per_step": st["gpu_h2d_bytes"],
                     "d2h_bytes_per_step": st["gpu_d2h_bytes"], "checks_per_step": checks,
                     "subsumed_clauses": st["sub_subsumedClauses"], "strengthened_literals": st["sub_removedLiterals"],

@@ -497,7 +497,7 @@ bool Engine::strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const
 // ------------------------------------------------------------------------------------------------ occ lists
 void Engine::occPush(int x, uint32_t c)
 {
-    OccList& l = occ[x];
+    ListRef l = L(x);
     if (l.n == l.cap) {
         uint32_t ncap = l.cap ? l.cap * 2 : 4;
         uint32_t noff = (uint32_t)occ_pool.size();
@@ -509,11 +509,11 @@ void Engine::occPush(int x, uint32_t c)
 }
 void Engine::occSwapRemove(int x, uint32_t i)
 {
-    OccList& l = occ[x]; uint32_t* p = LP(l);
-    if (isDel(p[i]) && occ[x].stale > 0) { --occ[x].stale; }
+    ListRef l = L(x); uint32_t* p = LP(l);
+    if (isDel(p[i])) { staleDec(x); }
     p[i] = p[l.n - 1]; l.n--;
 }
-void Engine::occRelease(int x) { occ[x].n = 0; occ[x].stale = 0; }
+void Engine::occRelease(int x) { hot[x].n = 0; staleClear(x); }
 
 void Engine::touchClauseVars(uint32_t c)
 {
@@ -526,10 +526,10 @@ void Engine::setDeleted(uint32_t c)
     if (C[c].flag & F_DEL) { return; }
     C[c].flag |= F_DEL; delbits[c >> 6] |= 1ull << (c & 63); --n_live;
     const int32_t* l = CL(c);
-    for (uint32_t k = 0; k < C[c].size; ++k) { ++occ[l[k]].stale; ++var_touch[l[k] >> 1]; }
+    for (uint32_t k = 0; k < C[c].size; ++k) { staleInc(l[k]); ++var_touch[l[k] >> 1]; }
     // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
     if (c < log_head.size()) {
-        for (int32_t i = log_head[c]; i >= 0; i = log_nodes[i].next) { if (log_nodes[i].pending == pend_epoch) { ++occ[log_nodes[i].lit].stale; } }
+        for (int32_t i = log_head[c]; i >= 0; i = log_nodes[i].next) { if (log_nodes[i].pending == pend_epoch) { staleInc(log_nodes[i].lit); } }
     }
     if (dev_uploaded) { pend_del.push_back(c); }
 }
@@ -597,7 +597,7 @@ void Engine::removedClause(uint32_t c, bool useHeap, bool update, int ignore)
     for (uint32_t i = 0; i < C[c].size; ++i) {
         int v = l[i] >> 1;
         deletedVar(v);
-        --occ[l[i]].cnt;
+        --hot[l[i]].cnt;
         if (useHeap) {
             if (inHeap(v)) { heapUp(hidx[v]); }
             else if (update && v != ignore) { heapUpdate(v); }
@@ -611,7 +611,7 @@ void Engine::removedLiteral(int x, int diff, bool useHeap, bool update, int igno
 {
     int v = x >> 1;
     deletedVar(v);
-    occ[x].cnt -= diff;
+    hot[x].cnt -= diff;
     ca_wasted += 1;
     if (useHeap) {
         if (inHeap(v)) { heapUp(hidx[v]); }
@@ -625,7 +625,7 @@ void Engine::dataAddClause(uint32_t c, bool useHeap)
     const int32_t* l = CL(c);
     for (uint32_t i = 0; i < C[c].size; ++i) {
         occPush(l[i], c);
-        occ[l[i]].cnt += 1;
+        hot[l[i]].cnt += 1;
         ++var_touch[l[i] >> 1];
         if (useHeap && inHeap(l[i] >> 1)) { heapDown(hidx[l[i] >> 1]); }
     }
@@ -634,7 +634,7 @@ void Engine::dataAddClause(uint32_t c, bool useHeap)
 // removeClauseFrom, CoprocessorTypes.h:867-878
 bool Engine::removeClauseFrom(uint32_t c, int x)
 {
-    OccList& l = occ[x]; uint32_t* p = LP(l);
+    ListRef l = L(x); uint32_t* p = LP(l);
     for (uint32_t i = 0; i < l.n; ++i) { if (p[i] == c) { occSwapRemove(x, i); return true; } }
     return false;
 }
@@ -669,9 +669,9 @@ void Engine::checkGarbage()
     if (!(ca_wasted > ca_size * opt.gc_frac)) { return; }
     filterDeleted(subq); filterDeleted(strq);
     for (int x = 0; x < 2 * nvars; ++x) {
-        OccList& l = occ[x]; uint32_t* p = LP(l); uint32_t j = 0;
+        ListRef l = L(x); uint32_t* p = LP(l); uint32_t j = 0;
         for (uint32_t i = 0; i < l.n; ++i) { if (!(C[p[i]].flag & F_DEL)) { p[j++] = p[i]; } }
-        l.n = j; occ[x].stale = 0;
+        l.n = j; staleClear(x);
     }
     filterDeleted(clauses);
     double sz = 0;
@@ -687,7 +687,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
     for (; up_last < (int)trail.size(); up_last++) {
         const int l = trail[up_last];
         {
-            OccList& positive = occ[l];
+            ListRef positive = L(l);
             for (uint32_t i = 0; i < positive.n; ++i) {
                 uint32_t c = LP(positive)[i];
                 if (C[c].flag & F_DEL) { continue; }
@@ -700,7 +700,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
         }
         const int nl = lneg(l);
         int count = 0;
-        OccList& negative = occ[nl];
+        ListRef negative = L(nl);
         for (uint32_t i = 0; i < negative.n; ++i) {
             uint32_t c = LP(negative)[i];
             if (C[c].flag & F_DEL) { continue; }
@@ -772,17 +772,17 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
         if (end >= PF) {
             const uint32_t c2 = subq[end - PF];
             const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
-            for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&occ[l2[k]]); }
+            for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k]]); }
         }
         const uint32_t cr = subq[end];
         if (C[cr].flag & F_DEL) { continue; }
         const int32_t* c = CL(cr); const uint32_t cn = C[cr].size;
         int min = c[0];
-        for (uint32_t l = 1; l < cn; ++l) { if (occ[c[l]].cnt < occ[min].cnt) { min = c[l]; } }
+        for (uint32_t l = 1; l < cn; ++l) { if (hot[c[l]].cnt < hot[min].cnt) { min = c[l]; } }
         const CacheEnt* e = cached(c_sub, cr);
         if (!e) { die("internal: subsumer without scan result"); }
-        OccList& list = occ[min];
-        if (e->hb == e->he && occ[min].stale == 0 && (unlimited || sub_steps + (int64_t)list.n < sub_lim)) {
+        ListRef list = L(min);
+        if (e->hb == e->he && !hasStale(min) && (unlimited || sub_steps + (int64_t)list.n < sub_lim)) {
             sub_steps += list.n ? (int64_t)list.n - 1 : 0;          // every entry but cr itself is one check
             ++n_fast;
         } else {
@@ -904,7 +904,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             if (end >= 16) {
                 const uint32_t c2 = strq[end - 16];
                 const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
-                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&occ[l2[k] & ~1]); }
+                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
             }
         }
         else { cr = localQueue.back(); localQueue.pop_back(); }
@@ -919,10 +919,10 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
           for (uint32_t j = 1; j < C[cr].size; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
         const int min = minT, nmin = lneg(minT);
         const CacheEnt* e = strHits(cr);
-        if (e->hb == e->he && occ[min].stale == 0 && occ[nmin].stale == 0 && !hasToPropagate() &&
-            (unlimited || str_steps + (int64_t)occ[min].n + (int64_t)occ[nmin].n < str_lim)) {
+        if (e->hb == e->he && !hasStale(min) && !hasStale(nmin) && !hasToPropagate() &&
+            (unlimited || str_steps + (int64_t)hot[min].n + (int64_t)hot[nmin].n < str_lim)) {
             // no candidate can hit and no list needs lazy cleaning: only the step counters move
-            str_steps += (occ[min].n ? (int64_t)occ[min].n - 1 : 0) + (int64_t)occ[nmin].n;
+            str_steps += (hot[min].n ? (int64_t)hot[min].n - 1 : 0) + (int64_t)hot[nmin].n;
             C[cr].flag &= ~F_STR;
             ++n_fast;
             continue;
@@ -930,7 +930,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         ++n_slow;
         // pass 1: occ(min) - the complementary literal is any literal but min
         {
-            OccList& list = occ[min];
+            ListRef list = L(min);
             for (uint32_t j = 0; j < list.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list)[j];
                 if (other == cr) { continue; }
@@ -953,7 +953,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         // pass 2: occ(~min) - the complementary literal must be ~min
         {
-            OccList& list_neg = occ[nmin];
+            ListRef list_neg = L(nmin);
             for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list_neg)[j];
                 str_steps++;
@@ -1012,11 +1012,11 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
 // findGates, BVE.cc:1143-1267 - reads clause sizes / binary partners only (no clause-vs-clause test)
 bool Engine::findGates(int v, int& p_limit, int& n_limit)
 {
-    if (occ[2 * v].n < 3 && occ[2 * v + 1].n < 3) { return false; }
-    if (occ[2 * v].n < 2 || occ[2 * v + 1].n < 2) { return false; }
+    if (hot[2 * v].n < 3 && hot[2 * v + 1].n < 3) { return false; }
+    if (hot[2 * v].n < 2 || hot[2 * v + 1].n < 2) { return false; }
     for (int pn = 0; pn < 2; ++pn) {
         const int pLit = 2 * v + (pn != 0), nLit = 2 * v + (pn == 0);
-        OccList& pList = occ[pLit]; OccList& nList = occ[nLit];
+        ListRef pList = L(pLit); ListRef nList = L(nLit);
         int& pClauses = pn == 0 ? p_limit : n_limit;
         int& nClauses = pn == 0 ? n_limit : p_limit;
         if (ma_step >= (1u << 30)) { std::fill(ma.begin(), ma.end(), 0u); ma_step = 0; }
@@ -1073,8 +1073,8 @@ Engine::PairEnt& Engine::pairsFor(int v)
     for (size_t i = 0; i < look; ++i) {
         int w = heap[i];
         if (w == v || assigns[w] != L_UNDEF || frozen[w]) { continue; }
-        if (occ[2 * w].n == 0 || occ[2 * w + 1].n == 0) { continue; }
-        if ((uint64_t)occ[2 * w].n * occ[2 * w + 1].n > 4096) { continue; }
+        if (hot[2 * w].n == 0 || hot[2 * w + 1].n == 0) { continue; }
+        if ((uint64_t)hot[2 * w].n * hot[2 * w + 1].n > 4096) { continue; }
         auto it = pair_cache.find(w);
         if (it != pair_cache.end() && it->second.valid && it->second.touch == var_touch[w]) { continue; }
         vs.push_back(w);
@@ -1082,7 +1082,7 @@ Engine::PairEnt& Engine::pairsFor(int v)
     std::vector<uint32_t> vars, p_off{0}, n_off{0}, p_refs, n_refs; std::vector<uint64_t> pair_off{0};
     for (int w : vs) {
         vars.push_back((uint32_t)w);
-        OccList& P = occ[2 * w]; OccList& N = occ[2 * w + 1];
+        ListRef P = L(2 * w); ListRef N = L(2 * w + 1);
         p_refs.insert(p_refs.end(), LP(P), LP(P) + P.n); n_refs.insert(n_refs.end(), LP(N), LP(N) + N.n);
         p_off.push_back((uint32_t)p_refs.size()); n_off.push_back((uint32_t)n_refs.size());
         pair_off.push_back(pair_off.back() + (uint64_t)P.n * N.n);
@@ -1111,7 +1111,7 @@ static inline int indexOf(const std::vector<uint32_t>& a, uint32_t x)
 // anticipateElimination, BVE.cc:695-880; tryResolve sizes come from K5
 int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& resolvents)
 {
-    OccList& positive = occ[2 * v]; OccList& negative = occ[2 * v + 1];
+    ListRef positive = L(2 * v); ListRef negative = L(2 * v + 1);
     const bool hasDefinition = (p_limit < (int)positive.n || n_limit < (int)negative.n);
     lit_clauses = 0;
     int clausesToUse = 0;
@@ -1176,7 +1176,7 @@ int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& r
 void Engine::bveRemoveClauses(int x, int extLitOrNeg)
 {
     const bool useHeap = opt.bve_heap_updates > 0;
-    OccList& list = occ[x];
+    ListRef list = L(x);
     for (uint32_t i = 0; i < list.n; ++i) {
         uint32_t c = LP(list)[i];
         if (C[c].flag & F_DEL) { continue; }
@@ -1191,7 +1191,7 @@ void Engine::bveRemoveClauses(int x, int extLitOrNeg)
 void Engine::bveRemoveBlocked(int x, const std::vector<int>& stats)
 {
     const bool useHeap = opt.bve_heap_updates > 0;
-    OccList& list = occ[x];
+    ListRef list = L(x);
     for (uint32_t i = 0; i < list.n; ++i) {
         uint32_t c = LP(list)[i];
         if (C[c].flag & F_DEL) { continue; }
@@ -1209,7 +1209,7 @@ void Engine::bveRemoveBlocked(int x, const std::vector<int>& stats)
 int Engine::resolveSet(int v, int p_limit, int n_limit)
 {
     const bool useHeap = opt.bve_heap_updates > 0;
-    OccList& positive = occ[2 * v]; OccList& negative = occ[2 * v + 1];
+    ListRef positive = L(2 * v); ListRef negative = L(2 * v + 1);
     const bool hasDefinition = (p_limit < (int)positive.n || n_limit < (int)negative.n);
     PairEnt* pe = &pairsFor(v);
     // gather the pairs in reference order and fetch their resolvents with one K6 launch
@@ -1294,11 +1294,11 @@ void Engine::bveWorker()
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
         const int v = heapRemoveMin();
         if (assigns[v] != L_UNDEF) { continue; }
-        if (occ[2 * v].n == 0 && occ[2 * v + 1].n == 0) { continue; }
+        if (hot[2 * v].n == 0 && hot[2 * v + 1].n == 0) { continue; }
         if (frozen[v]) { continue; }
-        const bool cutoff = (occ[2 * v + 1].cnt > 10 && occ[2 * v].cnt > 10) || (dcount(v) > 15 && (occ[2 * v + 1].cnt > 5 || occ[2 * v].cnt > 5));
+        const bool cutoff = (hot[2 * v + 1].cnt > 10 && hot[2 * v].cnt > 10) || (dcount(v) > 15 && (hot[2 * v + 1].cnt > 5 || hot[2 * v].cnt > 5));
         if (!opt.bve_force_gates && !opt.bve_unlimited && cutoff) { ++bve_skippedVars; continue; }
-        int p_limit = (int)occ[2 * v].n, n_limit = (int)occ[2 * v + 1].n;
+        int p_limit = (int)hot[2 * v].n, n_limit = (int)hot[2 * v + 1].n;
         bool foundGate = false;
         if (opt.bve_gates) { foundGate = findGates(v, p_limit, n_limit); if (foundGate) { bve_foundGates++; } }
         if (!foundGate && opt.bve_fdepOnly) { continue; }
@@ -1306,14 +1306,14 @@ void Engine::bveWorker()
         ++bve_testedVars;
         int pos_count = 0, neg_count = 0;
         for (int s = 0; s < 2; ++s) {
-            OccList& li = occ[2 * v + s];
+            ListRef li = L(2 * v + s);
             for (uint32_t i = 0; i < li.n; ++i) {
                 if (C[LP(li)[i]].flag & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
                 if (s == 0) { ++pos_count; } else { ++neg_count; }
             }
         }
-        if (pos_stats.size() < occ[2 * v].n) { pos_stats.resize(occ[2 * v].n, 0); }
-        if (neg_stats.size() < occ[2 * v + 1].n) { neg_stats.resize(occ[2 * v + 1].n, 0); }
+        if (pos_stats.size() < hot[2 * v].n) { pos_stats.resize(hot[2 * v].n, 0); }
+        if (neg_stats.size() < hot[2 * v + 1].n) { neg_stats.resize(hot[2 * v + 1].n, 0); }
         int lit_clauses = 0, resolvents = 0;
         int ares = L_UNDEF;
         if (pos_count != 0 && neg_count != 0) {
@@ -1358,7 +1358,7 @@ uint32_t Engine::nextModStep()
 // addClausesToSubsumption, BVE.cc:1129-1141
 void Engine::addClausesToSubsumption(int x)
 {
-    OccList& li = occ[x];
+    ListRef li = L(x);
     for (uint32_t j = 0; j < li.n; ++j) {
         uint32_t d = LP(li)[j];
         if (!(C[d].flag & F_DEL) && !(C[d].flag & F_SUB)) { C[d].flag |= F_SUB | F_STR; subInitClause(d); }
@@ -1413,7 +1413,8 @@ void Engine::initData()
 {
     PhaseTimer pt(ph_init);
     const int n2 = 2 * nvars;
-    occ.assign((size_t)n2, OccList());
+    occ.assign((size_t)n2, OccList()); hot.assign((size_t)n2, LitHot()); stale.assign((size_t)n2, 0u);
+    stalebits.assign(((size_t)n2 >> 6) + 1, 0ull);
     modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
     var_touch.assign((size_t)std::max(nvars, 1), 0);
     modStep = 0; numberOfCls = 0; qhead = 0;
@@ -1424,8 +1425,8 @@ void Engine::initData()
     occ_pool.assign((size_t)off[n2] + 16, 0);
     if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
     for (int x = 0; x < n2; ++x) {
-        occ[x].off = off[x]; occ[x].n = occ[x].cap = off[x + 1] - off[x];
-        occ[x].cnt = (int32_t)occ[x].n;
+        occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];
+        hot[x].cnt = (int32_t)hot[x].n;
     }
     size_t kept = 0;
     for (size_t i = 0; i < clauses.size(); ++i) {

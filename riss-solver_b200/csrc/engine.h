@@ -52,9 +52,11 @@ struct Tech { int penalty = 0, peak = 0; bool modified = false; };
 struct Hit { uint32_t clause; int32_t lit; };
 
 // occurrence list: slice of one pooled array; grows by relocation to the pool end
-// plus the per-literal counter (lit_occurrence_count) and the number of deleted clauses still listed, packed so
-// that both literals of a variable share one 64-byte line (the commit walks are cache-miss bound)
-struct alignas(32) OccList { uint32_t off = 0, n = 0, cap = 0; int32_t cnt = 0; uint32_t stale = 0; uint32_t pad[3] = {0, 0, 0}; };
+// (the hot per-literal fields - lit_occurrence_count and the list length - live in a separate 8-byte record so
+// that the queue walks, which are bound by cache misses on them, touch 16 MB instead of 64 MB at 1M variables)
+struct OccList { uint32_t off = 0, cap = 0; };
+struct LitHot { int32_t cnt = 0; uint32_t n = 0; };
+struct ListRef { uint32_t& off; uint32_t& cap; uint32_t& n; };
 
 class Engine {
 public:
@@ -96,7 +98,13 @@ private:
 
     // ---------------- CoprocessorData mirror
     bool data_ready = false;
-    std::vector<OccList> occ; std::vector<uint32_t> occ_pool;
+    std::vector<OccList> occ; std::vector<LitHot> hot; std::vector<uint32_t> occ_pool;
+    std::vector<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
+    inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
+    inline bool hasStale(int x) const { return (stalebits[(uint32_t)x >> 6] >> (x & 63)) & 1; }
+    inline void staleInc(int x) { if (stale[x]++ == 0) { stalebits[(uint32_t)x >> 6] |= 1ull << (x & 63); } }
+    inline void staleDec(int x) { if (stale[x] > 0 && --stale[x] == 0) { stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); } }
+    inline void staleClear(int x) { stale[x] = 0; stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); }
     int numberOfCls = 0;
     std::vector<uint32_t> subq, strq; std::vector<int32_t> undo;
     std::vector<uint32_t> modTimer; uint32_t modStep = 0;
@@ -162,7 +170,7 @@ private:
     inline int value(int x) const { uint8_t a = assigns[x >> 1]; return a == L_UNDEF ? L_UNDEF : (a ^ (x & 1)); }
     inline int32_t* CL(uint32_t c) { return pool.data() + C[c].start; }
     inline const int32_t* CL(uint32_t c) const { return pool.data() + C[c].start; }
-    inline int dcount(int v) const { return occ[2 * v].cnt + occ[2 * v + 1].cnt; }
+    inline int dcount(int v) const { return hot[2 * v].cnt + hot[2 * v + 1].cnt; }
     void newVar();
     uint32_t allocClause(const int* lits, int n);
     void caFree(uint32_t c) { ca_wasted += 2 + C[c].size; }
@@ -175,7 +183,7 @@ private:
     void die(const char* msg) const;
 
     // occurrence lists
-    inline uint32_t* LP(const OccList& l) { return occ_pool.data() + l.off; }
+    inline uint32_t* LP(const ListRef& l) { return occ_pool.data() + l.off; }
     void occPush(int x, uint32_t c);
     void occSwapRemove(int x, uint32_t i);            // list[i] = back; pop  (+ stale bookkeeping)
     void occRelease(int x);

@@ -229,6 +229,7 @@ __global__ void k_occ_sort_long(const uint32_t* __restrict__ off, const uint32_t
 // the 3*10^5 hits of a full-queue pass cost more than the scan itself), so every block stages its hits in
 // shared memory and reserves their slots with ONE global atomic when it finishes.
 static constexpr int SINK_CAP = 96;
+
 struct HitSink {
     cp3g_hit* s_hits; uint32_t* s_n;
     cp3g_hit* out; uint32_t cap; uint32_t* nout;
@@ -420,10 +421,16 @@ __device__ __forceinline__ void bulk_candidate_inl(uint32_t sref, uint32_t dref,
     }
 }
 
-// Candidate-major form of the full-queue pass: one thread per occurrence entry *as the candidate*.  The
-// thread streams its own 16-byte entry (perfectly coalesced) and tests it against the few clauses that are
-// filed under this literal in the tagged CSR, i.e. the subsumers / strengtheners whose bulk scan walks this
-// list.  All 32 lanes work, trip counts are tiny and uniform, neighbours read the same tagged entries.
+// Candidate-major form of the full-queue pass: one lane per occurrence entry *as the candidate*.  The lane
+// streams its own 16-byte entry (perfectly coalesced) and tests it against the few clauses that are filed
+// under this literal in the tagged CSR, i.e. the subsumers / strengtheners whose bulk scan walks this list.
+// Warps are persistent and fully independent (no block barrier inside the loop - a barrier per tile cost 38 %
+// of the cycles, profiles/r01b): every warp owns a candidate queue and a hit buffer in shared memory.
+//   phase 1  signature/size filter on the 16-byte records; survivors go to the warp's queue
+//   phase 2  the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
+//            which would otherwise stall 31 lanes behind one)
+//   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
+static constexpr int WQ_CAP = 64, WH_CAP = 32;
 template <int KIND>
 __global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
         const OccEnt* __restrict__ occ_ent, const uint32_t* __restrict__ ent_lit, const uint32_t* __restrict__ delbits,
@@ -432,49 +439,93 @@ __global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ h
         unsigned long long* __restrict__ checks)
 {
     __shared__ unsigned long long sh_chk[8], sh_byt[8];
-    SINK_DECL;
+    __shared__ uint32_t q_s[8][WQ_CAP], q_d[8][WQ_CAP]; __shared__ int32_t q_l[8][WQ_CAP];
+    __shared__ cp3g_hit h_buf[8][WH_CAP];
+    __shared__ uint32_t q_n[8], h_n[8];
+    const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { q_n[w] = 0; h_n[w] = 0; }
+    __syncwarp();
     unsigned long long nchk = 0, nbytes = 0;
-    for (uint32_t tile = first + blockIdx.x * blockDim.x; tile < last; tile += gridDim.x * blockDim.x) {
-    const uint32_t j = tile + threadIdx.x;
-    if (j < last) {
-        const OccEnt en = occ_ent[j];
-        const int32_t l = (int32_t)ent_lit[j];
-        const uint32_t esz = en.szfl & SIZE_MASK;
-        const bool ddel = (delbits[en.ref >> 5] >> (en.ref & 31)) & 1u;
-        const unsigned long long dvar = var_fold(en.sig);
-        const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
-        for (int pass = 0; pass < npass; ++pass) {
-            const int32_t lx = pass == 0 ? l : (l ^ 1);         // the literal the strengthener is filed under
-            const uint32_t b = toff[lx], e = toff[lx + 1];
-            for (uint32_t k = b; k < e; ++k) {
-                const OccEnt s = tag[k];
-                if (s.ref == en.ref) { continue; }
-                nchk += 1; nbytes += 12 + 4 * esz;
-                const uint32_t sn = s.szfl & SIZE_MASK;
-                if (ddel || esz < sn) { continue; }
-                const unsigned long long miss = s.sig & ~en.sig;
-                if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                else { if ((miss & (miss - 1)) || (var_fold(s.sig) & ~dvar)) { continue; } }
-                if ((delbits[s.ref >> 5] >> (s.ref & 31)) & 1u) { continue; }
-                // pass 0: S holds l, any literal but ~l may be the flipped one; pass 1: S holds ~l, the flip is on l
-                bulk_candidate_inl<KIND>(s.ref, en.ref, pass == 0 ? -1 : l, pass == 0 ? (l ^ 1) : -1, hdr, lits, sink);
+    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + w, nwarps = gridDim.x * (blockDim.x >> 5);
+
+    auto verify = [&](uint32_t sref, uint32_t dref, int32_t l, int pass) {
+        // pass 0: S holds l, any literal but ~l may be the flipped one; pass 1: S holds ~l, the flip is on l
+        const ClauseHdr hs = hdr[sref], hd = hdr[dref];
+        if ((hs.szfl | hd.szfl) & FLAG_DEL) { return; }
+        const uint32_t sn = hs.szfl & SIZE_MASK, dn = hd.szfl & SIZE_MASK;
+        if (dn < sn) { return; }
+        int32_t f = -1; bool hit;
+        if (KIND == CP3G_SUBSUME) { hit = merge_subset(lits + hs.start, sn, lits + hd.start, dn); }
+        else {
+            f = merge_one_flip(lits + hs.start, sn, lits + hd.start, dn);
+            hit = f >= 0 && (pass == 0 ? f != (l ^ 1) : f == l);
+        }
+        if (hit) {
+            const uint32_t p = atomicAdd(&h_n[w], 1u);
+            if (p < (uint32_t)WH_CAP) { h_buf[w][p].req = sref; h_buf[w][p].clause = dref; h_buf[w][p].lit = f; }
+            else { const uint32_t g2 = atomicAdd(nout, 1u); if (g2 < cap) { out[g2].req = sref; out[g2].clause = dref; out[g2].lit = f; } }
+        }
+    };
+    auto flush_hits = [&]() {
+        __syncwarp();
+        const uint32_t n = min(h_n[w], (uint32_t)WH_CAP);
+        uint32_t base = 0;
+        if (lane == 0 && n) { base = atomicAdd(nout, n); }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < n && base + lane < cap) { out[base + lane] = h_buf[w][lane]; }
+        __syncwarp();
+        if (lane == 0) { h_n[w] = 0; }
+        __syncwarp();
+    };
+
+    for (uint32_t tile = first + gwarp * 32; tile < last; tile += nwarps * 32) {
+        const uint32_t j = tile + lane;
+        if (j < last) {
+            const OccEnt en = occ_ent[j];
+            const int32_t l = (int32_t)ent_lit[j];
+            const uint32_t esz = en.szfl & SIZE_MASK;
+            const bool ddel = (delbits[en.ref >> 5] >> (en.ref & 31)) & 1u;
+            const unsigned long long dvar = var_fold(en.sig);
+            const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+            for (int pass = 0; pass < npass; ++pass) {
+                const int32_t lx = pass == 0 ? l : (l ^ 1);         // the literal the strengthener is filed under
+                const uint32_t b = toff[lx], e = toff[lx + 1];
+                for (uint32_t k = b; k < e; ++k) {
+                    const OccEnt s = tag[k];
+                    if (s.ref == en.ref) { continue; }
+                    nchk += 1; nbytes += 12 + 4 * esz;
+                    const uint32_t sn = s.szfl & SIZE_MASK;
+                    if (ddel || esz < sn) { continue; }
+                    const unsigned long long miss = s.sig & ~en.sig;
+                    if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
+                    else { if ((miss & (miss - 1)) || (var_fold(s.sig) & ~dvar)) { continue; } }
+                    if ((delbits[s.ref >> 5] >> (s.ref & 31)) & 1u) { continue; }
+                    const uint32_t q = atomicAdd(&q_n[w], 1u);
+                    if (q < (uint32_t)WQ_CAP) { q_s[w][q] = s.ref; q_d[w][q] = en.ref; q_l[w][q] = (l << 1) | pass; }
+                    else { verify(s.ref, en.ref, l, pass); }
+                }
             }
         }
+        __syncwarp();
+        const uint32_t qn = min(q_n[w], (uint32_t)WQ_CAP);
+        if (qn >= 16u || tile + nwarps * 32 >= last) {            // verify when the queue is worth a full warp pass
+            for (uint32_t k = lane; k < qn; k += 32) { verify(q_s[w][k], q_d[w][k], q_l[w][k] >> 1, q_l[w][k] & 1); }
+            __syncwarp();
+            if (lane == 0) { q_n[w] = 0; }
+            __syncwarp();
+            if (h_n[w] >= (uint32_t)(WH_CAP / 2)) { flush_hits(); }
+        }
     }
-    __syncthreads();
-    if (sink_n >= (uint32_t)(SINK_CAP / 2)) { sink.flush(&sink_base); }      // uniform: sink_n is read after the barrier
-    }
+    flush_hits();
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
-    const int w = threadIdx.x >> 5;
-    if ((threadIdx.x & 31) == 0) { sh_chk[w] = nchk; sh_byt[w] = nbytes; }
+    if (lane == 0) { sh_chk[w] = nchk; sh_byt[w] = nbytes; }
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long a = 0, b2 = 0;
         for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a += sh_chk[k]; b2 += sh_byt[k]; }
         if (a) { atomicAdd(checks, a); atomicAdd(checks + 1, b2); }
     }
-    sink.flush(&sink_base);
 }
 
 // ------------------------------------------------------------------------------------------ K5 / K6
