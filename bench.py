@@ -173,7 +173,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--vars", type=int, default=1000000, help="variables of the C2 workload (clauses = 4.26x)")
-    ap.add_argument("--ref-vars", type=int, default=250000, help="bounded sample for the CPU reference legs")
+    ap.add_argument("--ref-vars", type=int, default=1000000, help="size of the sample the CPU reference legs run (default: the full workload)")
     ap.add_argument("--seed", type=int, default=12345)
     ap.add_argument("--mode", default="weak", choices=["weak", "sharded"],
                     help="N>1: weak = one independent formula per rank; sharded = one formula, scan requests "

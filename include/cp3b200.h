@@ -92,6 +92,9 @@ const char* cp3g_last_error(const cp3g* g);
  * lits = literal pool, start[i]/size[i] = clause i, flags bit0 = deleted (Clause::mark()). */
 int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t nclauses, const int32_t* lits, size_t nlits,
                 const uint32_t* start, const uint32_t* size, const uint8_t* flags);
+/* same, from 16-byte host records {start:u32, size:24|flags:8 (bit 0 = deleted), 2 words ignored} - lets a host that keeps
+ * such a clause table upload it with one copy */
+int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t nclauses, const int32_t* lits, size_t nlits, const void* records16);
 /* K1 sig_build + K2 occ_build: 64-bit clause signatures and the per-literal CSR occurrence lists in
  * ascending clause order (CoprocessorData::addClause order, CoprocessorTypes.h:812-833). */
 int cp3g_build(cp3g* g);

@@ -79,13 +79,34 @@ void Options::preset(const char* name)
 
 void Engine::ScanCache::clear() { std::fill(slot.begin(), slot.end(), -1); ent.clear(); hits.clear(); lits.clear(); bulk_all = false; }
 
-Engine::Engine() { sub_lim = opt.sub_limit; str_lim = opt.str_limit; }
+Engine::Engine()
+{
+    sub_lim = opt.sub_limit; str_lim = opt.str_limit;
+    const char* e = getenv("CP3_THREADS");
+    nthreads = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nthreads < 1) { nthreads = 1; }
+}
 Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
 
 void Engine::die(const char* msg) const
 {
     fprintf(stderr, "cp3b200: fatal: %s%s%s\n", msg, gpu ? " - " : "", gpu ? cp3g_last_error(gpu) : "");
     abort();
+}
+
+// contiguous chunks of [0,n) on the host cores (the statically inert part of the queue walks)
+template <class F> void Engine::parallelFor(size_t n, F f)
+{
+    const int T = (int)std::min<size_t>((size_t)nthreads, (n + 65535) / 65536);
+    if (T <= 1) { f((size_t)0, n, 0); return; }
+    std::vector<std::thread> th;
+    const size_t per = (n + T - 1) / T;
+    for (int t = 0; t < T; ++t) {
+        const size_t b = per * t, e = std::min(n, per * (t + 1));
+        if (b >= e) { break; }
+        th.emplace_back([=]() { f(b, e, t); });
+    }
+    for (auto& x : th) { x.join(); }
 }
 
 // ------------------------------------------------------------------------------------------------ solver side
@@ -221,10 +242,9 @@ void Engine::uploadAll()
 {
     ensureGpu();
     const uint32_t ncl = (uint32_t)C.size();
-    std::vector<uint8_t> fl(ncl); std::vector<uint32_t> cstart(ncl), csize(ncl);
-    for (uint32_t c = 0; c < ncl; ++c) { fl[c] = (C[c].flag & F_DEL) ? 1 : 0; cstart[c] = C[c].start; csize[c] = C[c].size; }
+    static_assert(sizeof(ClauseInfo) == 16, "ClauseInfo is uploaded as a packed 16-byte record");
     int64_t t0 = now_ns();
-    if (cp3g_upload(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), cstart.data(), csize.data(), fl.data()) != CP3G_OK) { die("upload failed"); }
+    if (cp3g_upload_packed(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), C.data()) != CP3G_OK) { die("upload failed"); }
     if (cp3g_build(gpu) != CP3G_OK) { die("occurrence build failed"); }
     host_ns_gpuwait += now_ns() - t0;
     dev_ncl = ncl; dev_uploaded = true;
@@ -517,8 +537,9 @@ void Engine::occRelease(int x) { hot[x].n = 0; staleClear(x); }
 
 void Engine::touchClauseVars(uint32_t c)
 {
+    if (!opt.bve) { return; }                       // only the BVE pair cache looks at var_touch
     const int32_t* l = CL(c);
-    for (uint32_t k = 0; k < C[c].size; ++k) { ++var_touch[l[k] >> 1]; }
+    for (uint32_t k = 0; k < C[c].size; ++k) { bveTouch(l[k] >> 1); }
 }
 
 void Engine::setDeleted(uint32_t c)
@@ -526,7 +547,8 @@ void Engine::setDeleted(uint32_t c)
     if (C[c].flag & F_DEL) { return; }
     C[c].flag |= F_DEL; delbits[c >> 6] |= 1ull << (c & 63); --n_live;
     const int32_t* l = CL(c);
-    for (uint32_t k = 0; k < C[c].size; ++k) { staleInc(l[k]); ++var_touch[l[k] >> 1]; }
+    for (uint32_t k = 0; k < C[c].size; ++k) { staleInc(l[k]); }
+    touchClauseVars(c);
     // literals removed by strengthening whose occurrence entry is still pending (Subsumption.cc:1400,1523)
     if (c < log_head.size()) {
         for (int32_t i = log_head[c]; i >= 0; i = log_nodes[i].next) { if (log_nodes[i].pending == pend_epoch) { staleInc(log_nodes[i].lit); } }
@@ -540,7 +562,7 @@ void Engine::noteShrunk(uint32_t c, int removedLit, bool pendingOcc)
     ++C[c].ver; C[c].stamp = scan_id;
     if (dev_uploaded && c < shrunk_mark.size() && !shrunk_mark[c]) { shrunk_mark[c] = 1; pend_shrunk.push_back(c); }
     else if (dev_uploaded && c >= shrunk_mark.size()) { /* not yet on the device: appended with current content */ }
-    touchClauseVars(c); ++var_touch[removedLit >> 1];
+    touchClauseVars(c); if (opt.bve) { bveTouch(removedLit >> 1); }
 }
 
 void Engine::removePosSorted(uint32_t c, int pos)
@@ -626,7 +648,7 @@ void Engine::dataAddClause(uint32_t c, bool useHeap)
     for (uint32_t i = 0; i < C[c].size; ++i) {
         occPush(l[i], c);
         hot[l[i]].cnt += 1;
-        ++var_touch[l[i] >> 1];
+        bveTouch(l[i] >> 1);
         if (useHeap && inHeap(l[i] >> 1)) { heapDown(hidx[l[i] >> 1]); }
     }
     numberOfCls++;
@@ -894,6 +916,33 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         prefetchStrengthenClosure();
     }
     int64_t t0 = now_ns();
+    // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
+    // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
+    // (a) has no candidate hit, (b) is no candidate target of anybody and (c) walks two lists without deleted
+    // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
+    // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
+    contrib.assign(strq.size(), -1);
+    static const size_t static_min = getenv("CP3_STATIC_MIN") ? (size_t)atoi(getenv("CP3_STATIC_MIN")) : 4096;
+    bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
+    if (static_valid) {
+        is_target.assign((C.size() >> 6) + 1, 0ull);
+        for (const Hit& h : c_str.hits) { is_target[h.clause >> 6] |= 1ull << (h.clause & 63); }
+        const size_t nq = strq.size();
+        parallelFor(nq, [&](size_t b, size_t e, int) {
+            for (size_t p2 = b; p2 < e; ++p2) {
+                const uint32_t c = strq[p2];
+                const ClauseInfo ci = C[c];
+                if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }                      // duplicate queue entry
+                if (c_str.slot[c] >= 0 || ((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0];
+                for (uint32_t j = 1; j < ci.size; ++j) { if (dcount(minT >> 1) > dcount(s2[j] >> 1)) { minT = s2[j]; } }
+                const int mn = minT, nm = minT ^ 1;
+                if (hasStale(mn) || hasStale(nm)) { continue; }
+                contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
+            }
+        });
+    }
     std::vector<uint32_t> localQueue;
     size_t end = strq.size();
     int ret = L_UNDEF; bool early = false;
@@ -901,6 +950,12 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         uint32_t cr;
         if (localQueue.empty()) {
             --end; cr = strq[end];
+            if (static_valid && contrib[end] >= 0 && !hasToPropagate() && (unlimited || str_steps + contrib[end] < str_lim)) {
+                str_steps += contrib[end];
+                C[cr].flag &= ~F_STR;
+                ++n_fast; ++n_static;
+                continue;
+            }
             if (end >= 16) {
                 const uint32_t c2 = strq[end - 16];
                 const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
@@ -948,6 +1003,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             }
         }
         if (hasToPropagate()) {
+            static_valid = false;            // counts and lists move now: the precomputed entries are void
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
             e = strHits(cr);                 // cr itself may have been shortened by the propagation
         }
@@ -968,6 +1024,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             }
         }
         if (hasToPropagate()) {
+            static_valid = false;
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
             t_sub.modified = t_sub.modified || t_up.modified;
         }
@@ -1068,17 +1125,25 @@ Engine::PairEnt& Engine::pairsFor(int v)
     if (pe.valid && pe.touch == var_touch[v]) { return pe; }
     flushDevice();
     ++n_pair_batches;
+    // batch: v plus every variable that waits in the heap with an outdated (or no) matrix
     std::vector<int> vs; vs.push_back(v);
-    const size_t look = std::min<size_t>(heap.size(), 256);
-    for (size_t i = 0; i < look; ++i) {
-        int w = heap[i];
-        if (w == v || assigns[w] != L_UNDEF || frozen[w]) { continue; }
-        if (hot[2 * w].n == 0 || hot[2 * w + 1].n == 0) { continue; }
-        if ((uint64_t)hot[2 * w].n * hot[2 * w + 1].n > 4096) { continue; }
+    uint64_t budget = 0;
+    size_t keep = 0;
+    for (size_t i = 0; i < bve_pending.size(); ++i) {
+        const int w = bve_pending[i];
+        if (w == v || !inHeap(w) || assigns[w] != L_UNDEF || frozen[w] || hot[2 * w].n == 0 || hot[2 * w + 1].n == 0) { bve_inpend[w] = 0; continue; }
+        const uint64_t np = (uint64_t)hot[2 * w].n * hot[2 * w + 1].n;
+        if (np > 4096) { bve_inpend[w] = 0; continue; }             // rare long lists: on demand only
+        // the reference's cut-off (BVE.cc:418-420) on the current counters: such variables are skipped anyway
+        const bool cutoff = (hot[2 * w + 1].cnt > 10 && hot[2 * w].cnt > 10) || (dcount(w) > 15 && (hot[2 * w + 1].cnt > 5 || hot[2 * w].cnt > 5));
+        if (cutoff && !opt.bve_unlimited && !opt.bve_gates) { bve_inpend[w] = 0; continue; }
+        if (budget + np > (64u << 20)) { bve_pending[keep++] = w; continue; }   // next batch
         auto it = pair_cache.find(w);
-        if (it != pair_cache.end() && it->second.valid && it->second.touch == var_touch[w]) { continue; }
+        if (it != pair_cache.end() && it->second.valid && it->second.touch == var_touch[w]) { bve_inpend[w] = 0; continue; }
+        budget += np; bve_inpend[w] = 0;
         vs.push_back(w);
     }
+    bve_pending.resize(keep);
     std::vector<uint32_t> vars, p_off{0}, n_off{0}, p_refs, n_refs; std::vector<uint64_t> pair_off{0};
     for (int w : vs) {
         vars.push_back((uint32_t)w);
@@ -1092,12 +1157,50 @@ Engine::PairEnt& Engine::pairsFor(int v)
     if (cp3g_bve_pairs(gpu, (uint32_t)vars.size(), vars.data(), p_off.data(), p_refs.data(), n_off.data(), n_refs.data(),
                        pair_off.data(), sizes.data()) != CP3G_OK) { die("bve_pairs failed"); }
     host_ns_gpuwait += now_ns() - t0;
+    // K6 in the same batch for the variables the decision rule (BVE.cc:532-548) will most likely eliminate:
+    // their resolvents are then already on the host when the ordered commit reaches them
+    std::vector<uint32_t> rv, rp, rn; std::vector<uint64_t> roff{0}; std::vector<size_t> rfirst(vs.size() + 1, 0); std::vector<uint8_t> want(vs.size(), 0);
+    for (size_t i = 0; i < vs.size(); ++i) {
+        rfirst[i] = rv.size();
+        const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i];
+        int res = 0;
+        for (uint64_t k = pair_off[i]; k < pair_off[i + 1]; ++k) { res += sizes[k] > 1; }
+        int slack = opt.bve_cgrow;
+        if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { slack += std::max(0, opt.bve_cgrow_t - bve_totallyAdded); }
+        if (res > (int)(np + nn) + slack || roff.back() > (32u << 20)) { continue; }
+        want[i] = 1;
+        for (uint32_t a = 0; a < np; ++a) for (uint32_t b = 0; b < nn; ++b) {
+            const int sz = sizes[pair_off[i] + (uint64_t)a * nn + b];
+            if (sz >= 1) { rv.push_back(vars[i]); rp.push_back(p_refs[p_off[i] + a]); rn.push_back(n_refs[n_off[i] + b]); roff.push_back(roff.back() + (uint64_t)sz); }
+        }
+    }
+    rfirst[vs.size()] = rv.size();
+    std::vector<int32_t> rlits(roff.back() + 1);
+    if (!rv.empty()) {
+        ++n_resolve_batches;
+        int64_t t1 = now_ns();
+        if (cp3g_bve_resolve(gpu, (uint32_t)rv.size(), rv.data(), rp.data(), rn.data(), roff.data(), rlits.data(), roff.back()) != CP3G_OK) { die("bve_resolve failed"); }
+        host_ns_gpuwait += now_ns() - t1;
+    }
     for (size_t i = 0; i < vs.size(); ++i) {
         PairEnt& q = pair_cache[vs[i]];
         q.touch = var_touch[vs[i]]; q.valid = true;
         q.pos.assign(p_refs.begin() + p_off[i], p_refs.begin() + p_off[i + 1]);
         q.neg.assign(n_refs.begin() + n_off[i], n_refs.begin() + n_off[i + 1]);
         q.sizes.assign(sizes.begin() + pair_off[i], sizes.begin() + pair_off[i + 1]);
+        q.has_res = want[i] != 0; q.roff.clear(); q.rlits.clear();
+        if (q.has_res) {
+            // roff: offset of pair (a,b) into rlits, in row-major pair order (only pairs with size >= 1 own literals)
+            const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i];
+            q.roff.assign((size_t)np * nn + 1, 0);
+            size_t r = rfirst[i]; const uint64_t base = roff[rfirst[i]];
+            for (uint64_t k = 0; k < (uint64_t)np * nn; ++k) {
+                q.roff[k] = (uint32_t)(roff[r] - base);
+                if (q.sizes[k] >= 1) { ++r; }
+            }
+            q.roff[(size_t)np * nn] = (uint32_t)(roff[r] - base);
+            q.rlits.assign(rlits.begin() + base, rlits.begin() + roff[rfirst[i + 1]]);
+        }
     }
     return pair_cache[v];
 }
@@ -1238,7 +1341,15 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
             }
         }
         rl.assign(off.back() + 1, 0);
-        if (!prs.empty()) {
+        if (!prs.empty() && pe->has_res) {
+            // prefetched with the K5 batch: copy out of the cache (pair (row, col) -> literals)
+            std::vector<int> col2(negative.n, -1);
+            for (uint32_t j = 0; j < negative.n; ++j) { col2[j] = indexOf(pe->neg, LP(negative)[j]); }
+            for (const Pr& q : prs) {
+                const size_t idx = (size_t)indexOf(pe->pos, LP(positive)[q.cp]) * pe->neg.size() + col2[q.cn];
+                memcpy(rl.data() + q.off, pe->rlits.data() + pe->roff[idx], sizeof(int32_t) * (size_t)q.size);
+            }
+        } else if (!prs.empty()) {
             ++n_resolve_batches;
             int64_t t0 = now_ns();
             if (cp3g_bve_resolve(gpu, (uint32_t)prs.size(), vv.data(), pr.data(), nr.data(), off.data(), rl.data(), off.back()) != CP3G_OK) { die("bve_resolve failed"); }
@@ -1375,6 +1486,7 @@ void Engine::sequentiellBVE()
     touched.clear();
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
         bve_modtime = nextModStep();
+        for (int w : heap) { if (!bve_inpend[w]) { bve_inpend[w] = 1; bve_pending.push_back(w); } }
         bveWorker();
         if (!ok) { return; }
         if (hasToPropagate()) {
@@ -1416,10 +1528,12 @@ void Engine::initData()
     occ.assign((size_t)n2, OccList()); hot.assign((size_t)n2, LitHot()); stale.assign((size_t)n2, 0u);
     stalebits.assign(((size_t)n2 >> 6) + 1, 0ull);
     modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
-    var_touch.assign((size_t)std::max(nvars, 1), 0);
+    var_touch.assign((size_t)std::max(nvars, 1), 0); bve_inpend.assign((size_t)std::max(nvars, 1), 0); bve_pending.clear();
     modStep = 0; numberOfCls = 0; qhead = 0;
     subq.clear(); strq.clear();
+    int64_t ti0 = now_ns();
     uploadAll();
+    ph_upload += now_ns() - ti0; ti0 = now_ns();
     std::vector<uint32_t> off((size_t)n2 + 1, 0);
     if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
     occ_pool.assign((size_t)off[n2] + 16, 0);
@@ -1428,6 +1542,7 @@ void Engine::initData()
         occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];
         hot[x].cnt = (int32_t)hot[x].n;
     }
+    ph_download += now_ns() - ti0;
     size_t kept = 0;
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i];
@@ -1449,7 +1564,7 @@ void Engine::preprocess()
     PhaseTimer ptot(ph_total);
     ensureGpu();                                  // fail before touching anything when there is no device
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
-    if (!solverSimplify()) { return; }
+    { PhaseTimer ps(ph_simplify); if (!solverSimplify()) { return; } }
     initData();
     int status = L_UNDEF;
     for (int it = 0; it < opt.iters; ++it) {
@@ -1538,7 +1653,9 @@ int64_t Engine::stat(const char* s) const
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
+    ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
+    ST("queue_static", n_static)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

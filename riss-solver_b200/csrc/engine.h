@@ -14,6 +14,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <thread>
 #include "../../include/cp3b200.h"
 
 namespace cp3 {
@@ -154,17 +155,23 @@ private:
     void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache);
     void prefetchStrengthenClosure();
     std::vector<int32_t> qtime;                      // strengthening queue: processing time of a pending clause
-    int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0;
+    int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0, n_static = 0;
+    std::vector<int32_t> contrib;                    // per queue position: step contribution of a statically inert entry, or -1
+    std::vector<uint64_t> is_target;                 // clauses that some cached hit may modify
+    int nthreads = 1;
+    template <class F> void parallelFor(size_t n, F f);
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
     // BVE pair cache
-    std::vector<uint32_t> var_touch;
-    struct PairEnt { uint32_t touch; std::vector<uint32_t> pos, neg; std::vector<int16_t> sizes; std::vector<int32_t> units; bool valid = false; };
+    std::vector<uint32_t> var_touch; std::vector<uint8_t> bve_inpend; std::vector<int> bve_pending;
+    inline void bveTouch(int v) { ++var_touch[v]; if (!bve_inpend[v] && inHeap(v)) { bve_inpend[v] = 1; bve_pending.push_back(v); } }
+    struct PairEnt { uint32_t touch; std::vector<uint32_t> pos, neg; std::vector<int16_t> sizes; bool valid = false;
+                     bool has_res = false; std::vector<uint32_t> roff; std::vector<int32_t> rlits; };   // prefetched resolvents (K6)
     std::unordered_map<int, PairEnt> pair_cache;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
     int64_t host_ns_commit = 0, host_ns_gpuwait = 0;
-    int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0;
+    int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0, ph_upload = 0, ph_download = 0, ph_simplify = 0;
 
     // ---------------- basics
     inline int value(int x) const { uint8_t a = assigns[x >> 1]; return a == L_UNDEF ? L_UNDEF : (a ^ (x & 1)); }

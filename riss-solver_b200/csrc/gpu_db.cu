@@ -614,6 +614,15 @@ __global__ void k_init_delbits(const ClauseHdr* __restrict__ hdr, uint32_t* __re
     for (uint32_t k = 0; k < 32 && w * 32 + k < ncl; ++k) { if (hdr[w * 32 + k].szfl & FLAG_DEL) { bits |= 1u << k; } }
     delbits[w] = bits;
 }
+// host clause records are {start:u32, size:24|flags:8, x, y}; flag bit 0 = deleted
+__global__ void k_make_hdr(const uint4* __restrict__ rec, ClauseHdr* __restrict__ hdr, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const uint4 r = rec[i];
+    ClauseHdr h; h.start = r.x; h.szfl = (r.y & SIZE_MASK) | (((r.y >> 24) & 1u) ? FLAG_DEL : 0u); h.sig = 0;
+    hdr[i] = h;
+}
 __global__ void k_gather_refs(const OccEnt* __restrict__ ent, uint32_t* __restrict__ refs, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -746,6 +755,31 @@ int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size
     g->lits.used = nlits; g->hdr.used = ncl; g->delbits.used = g->delbits.cap;
     g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * sizeof(ClauseHdr));
     return CP3G_OK;
+}
+
+static int finish_upload(cp3g* g, uint32_t ncl, size_t nlits)
+{
+    RESERVE(g->delbits, ((size_t)ncl + ncl / 4 + 1024) / 32 + 2, false);
+    CK(cudaMemsetAsync(g->delbits.p, 0, g->delbits.cap * sizeof(uint32_t), g->stream));
+    if (ncl) { k_init_delbits<<<grid_for((ncl + 31) / 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, 0, ncl); g->launches++; }
+    CK(cudaStreamSynchronize(g->stream));
+    g->lits.used = nlits; g->hdr.used = ncl; g->delbits.used = g->delbits.cap;
+    return CP3G_OK;
+}
+
+extern "C" int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t nlits, const void* records16)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    g->nvars = nvars; g->ncl = ncl; g->nlits = nlits; g->ncl_csr = 0; g->ovf_host.clear(); g->dirty_since_build = true;
+    RESERVE(g->lits, nlits + nlits / 4 + 1024, false);
+    RESERVE(g->hdr, (size_t)ncl + ncl / 4 + 1024, false);
+    RESERVE(g->occ_ent, (size_t)ncl + 1, false);                 // staging for the raw records (rebuilt by cp3g_build anyway)
+    CK(cudaMemcpyAsync(g->lits.p, lits, nlits * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemcpyAsync(g->occ_ent.p, records16, (size_t)ncl * 16, cudaMemcpyHostToDevice, g->stream));
+    if (ncl) { k_make_hdr<<<grid_for(ncl, 256), 256, 0, g->stream>>>(reinterpret_cast<const uint4*>(g->occ_ent.p), g->hdr.p, ncl); g->launches++; }
+    g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * 16);
+    return finish_upload(g, ncl, nlits);
 }
 
 static int build_csr(cp3g* g)

@@ -61,6 +61,16 @@ int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size
     for (uint32_t i = 0; i < ncl; ++i) { g->cl[i].assign(lits + start[i], lits + start[i] + size[i]); g->del[i] = flags ? (flags[i] & 1) : 0; }
     return CP3G_OK;
 }
+int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t, const void* rec)
+{
+    const uint32_t* r = (const uint32_t*)rec;
+    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0);
+    for (uint32_t i = 0; i < ncl; ++i) {
+        const uint32_t start = r[4 * i], sz = r[4 * i + 1] & 0xffffffu;
+        g->cl[i].assign(lits + start, lits + start + sz); g->del[i] = (r[4 * i + 1] >> 24) & 1u;
+    }
+    return CP3G_OK;
+}
 int cp3g_build(cp3g* g)
 {
     g->occ.assign(2 * (size_t)g->nvars, {});
