@@ -77,7 +77,11 @@ void Options::preset(const char* name)
     }
 }
 
-void Engine::ScanCache::clear() { std::fill(slot.begin(), slot.end(), -1); ent.clear(); hits.clear(); lits.clear(); bulk_all = false; }
+void Engine::ScanCache::clear()
+{
+    for (uint32_t c : used) { slot[c] = -1; }
+    used.clear(); ent.clear(); hits.clear(); lits.clear(); bulk_all = false;
+}
 
 Engine::Engine()
 {
@@ -95,9 +99,9 @@ void Engine::die(const char* msg) const
 }
 
 // contiguous chunks of [0,n) on the host cores (the statically inert part of the queue walks)
-template <class F> void Engine::parallelFor(size_t n, F f)
+template <class F> void Engine::parallelFor(size_t n, F f, size_t grain)
 {
-    const int T = (int)std::min<size_t>((size_t)nthreads, (n + 65535) / 65536);
+    const int T = (int)std::min<size_t>((size_t)nthreads, (n + grain - 1) / grain);
     if (T <= 1) { f((size_t)0, n, 0); return; }
     std::vector<std::thread> th;
     const size_t per = (n + T - 1) / T;
@@ -321,7 +325,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             while (h < n && hitbuf[h].req == c) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
             e.he = (uint32_t)cache.hits.size();
             e.next = cache.slot[c]; e.lit_off = e.lit_n = 0; e.time = 0;
-            cache.slot[c] = (int32_t)cache.ent.size();
+            cache.setSlot(c, (int32_t)cache.ent.size());
             cache.ent.push_back(e);
         }
         host_ns_gpuwait += now_ns() - t0;
@@ -353,7 +357,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             while (h < n && hitbuf[h].req == i) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
             e.he = (uint32_t)cache.hits.size();
             e.next = cache.slot[v[i]]; e.lit_off = e.lit_n = 0; e.time = 0;
-            cache.slot[v[i]] = (int32_t)cache.ent.size();
+            cache.setSlot(v[i], (int32_t)cache.ent.size());
             cache.ent.push_back(e);
         }
     }
@@ -406,7 +410,7 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
         e.lit_off = (uint32_t)cache.lits.size(); e.lit_n = reqs[i].n; e.time = reqs[i].time;
         cache.lits.insert(cache.lits.end(), spec_lits.begin() + reqs[i].off, spec_lits.begin() + reqs[i].off + reqs[i].n);
         e.next = cache.slot[reqs[i].clause];
-        cache.slot[reqs[i].clause] = (int32_t)cache.ent.size();
+        cache.setSlot(reqs[i].clause, (int32_t)cache.ent.size());
         cache.ent.push_back(e);
     }
 }
@@ -731,6 +735,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
                 if (lits[j] == nl) {
                     if (!sort) { removePosUnsorted(c, (int)j); } else { removePosSorted(c, (int)j); }
                     noteShrunk(c, nl, false);
+                    unpredictedEdit(c);
                     t_up.modified = true;
                     count++;
                     break;
@@ -855,6 +860,7 @@ void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, in
     occ_upd.push_back({other, lit});
     removePosSorted(other, pos);
     noteShrunk(other, lit, true);
+    unpredictedEdit(other);
     dirty_str.push_back(other);
     if (C[other].size == 1) {
         dataEnqueue(CL(other)[0]);
@@ -893,6 +899,44 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
     return e;
 }
 
+// Put one list that was cleaned up front back into its lazy state (nobody has walked it yet).
+void Engine::restoreOneList(int x)
+{
+    const int32_t i = pre_index[x];
+    if (i < 0 || scanned_dyn[x]) { return; }
+    const PreList& pl = pre_lists[i];
+    memcpy(occ_pool.data() + occ[x].off, pre_snap.data() + pl.snap_off, sizeof(uint32_t) * pl.old_n);
+    hot[x].n = pl.old_n;
+    for (uint32_t k = 0; k < pl.extra; ++k) { staleInc(x); }
+    str_steps -= pl.extra;
+    pre_index[x] = -1;
+}
+// A unit is about to be propagated: clauses will die, and the reference would clean the lists nobody has walked
+// yet together with those new deletions (swap-with-last cleaning is not associative).  Put every list that was
+// cleaned up front but not walked so far back into its lazy state; from here on the pass runs the plain lazy way.
+void Engine::rollbackPrecompact()
+{
+    if (!pre_active) { return; }
+    for (const PreList& pl : pre_lists) { restoreOneList(pl.lit); }
+    pre_active = false;
+}
+// The static plan assumed that clause c keeps its content until its turn (it was nobody's predicted target).
+// A hit that the speculative closure did not predict just changed it: c is no longer inert, and the lists it
+// was going to walk lose one certain walker - a list without any is put back into its lazy state.
+void Engine::unpredictedEdit(uint32_t c)
+{
+    if (!static_pass || c >= qtime.size() || qtime[c] < 0) { return; }
+    const size_t pos = static_nq - 1 - (size_t)qtime[c];
+    if (pos >= walk_min.size()) { return; }
+    contrib[pos] = -1;
+    const int mn = walk_min[pos];
+    if (mn < 0) { return; }
+    walk_min[pos] = -1;
+    for (int x : {mn, mn ^ 1}) {
+        if (walk_count[x] > 0 && --walk_count[x] == 0 && pre_active) { restoreOneList(x); }
+    }
+}
+
 // strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
 int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
@@ -909,7 +953,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
         scanClauses(CP3G_STRENGTHEN, ids, c_str);
         // processing time of the queue entries: the queue is drained from the back
-        qtime.assign(C.size(), -1);
+        if (qtime.size() < C.size()) { qtime.resize(C.size() + 1024, -1); }
         for (size_t i = 0; i < strq.size(); ++i) { qtime[strq[i]] = (int32_t)(strq.size() - 1 - i); }
         for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
         for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
@@ -928,12 +972,69 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         is_target.assign((C.size() >> 6) + 1, 0ull);
         for (const Hit& h : c_str.hits) { is_target[h.clause >> 6] |= 1ull << (h.clause & 63); }
         const size_t nq = strq.size();
-        parallelFor(nq, [&](size_t b, size_t e, int) {
+        // (1) lists that are certainly walked in this pass: the two lists of every pending clause whose content
+        //     cannot change before its turn (it is nobody's candidate target)
+        std::vector<uint8_t> walked((size_t)2 * nvars, 0);
+        std::vector<int64_t> bound((size_t)nthreads + 1, 0);
+        walk_min.assign(nq, -1); walk_count.assign((size_t)2 * nvars, 0u);
+        static_pass = true; static_nq = nq;
+        parallelFor(nq, [&](size_t b, size_t e, int t) {
+            int64_t bs = 0;
             for (size_t p2 = b; p2 < e; ++p2) {
                 const uint32_t c = strq[p2];
                 const ClauseInfo ci = C[c];
                 if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
                 if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }                      // duplicate queue entry
+                if ((is_target[c >> 6] >> (c & 63)) & 1) { continue; }
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0];
+                for (uint32_t j = 1; j < ci.size; ++j) { if (dcount(minT >> 1) > dcount(s2[j] >> 1)) { minT = s2[j]; } }
+                walked[minT] = 1; walked[minT ^ 1] = 1;
+                walk_min[p2] = minT;
+                __atomic_fetch_add(&walk_count[minT], 1u, __ATOMIC_RELAXED); __atomic_fetch_add(&walk_count[minT ^ 1], 1u, __ATOMIC_RELAXED);
+                bs += (int64_t)hot[minT].n + hot[minT ^ 1].n;
+            }
+            bound[t] = bs;
+        });
+        int64_t total_bound = 0; for (int64_t x : bound) { total_bound += x; }
+        // (2) the first walk of a list removes its deleted entries by swap-with-last (Subsumption.cc:1332-1335,
+        //     1432-1435); the resulting order depends only on the list and on which entries are deleted, and no
+        //     clause dies during this pass unless a unit shows up.  So the certainly-walked lists are cleaned
+        //     up front, on all cores, each costing one step per removed entry like the lazy walk would.
+        pre_lists.clear(); pre_snap.clear(); pre_active = false;
+        static const bool no_pre = getenv("CP3_NO_PRECOMPACT") != nullptr;
+        if (!no_pre && (unlimited || str_steps + 2 * total_bound < str_lim)) {
+            const size_t nlit = (size_t)2 * nvars;
+            const size_t words = (nlit + 63) / 64;
+            std::vector<std::vector<PreList>> tl((size_t)nthreads + 1); std::vector<std::vector<uint32_t>> ts((size_t)nthreads + 1);
+            parallelForG(words, 512, [&](size_t wb, size_t we, int t) {  // 64-literal granules: stalebits words are not shared
+                for (size_t x = wb * 64; x < std::min(nlit, we * 64); ++x) {
+                    if (!walked[x] || !hasStale((int)x)) { continue; }
+                    uint32_t* p = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n;
+                    PreList pl; pl.lit = (int)x; pl.snap_off = (uint32_t)ts[t].size(); pl.old_n = n; pl.extra = 0;
+                    ts[t].insert(ts[t].end(), p, p + n);                 // keep the lazy state: a unit may force us to take this back
+                    for (uint32_t j = 0; j < n;) { if (isDel(p[j])) { p[j] = p[n - 1]; --n; ++pl.extra; } else { ++j; } }
+                    hot[x].n = n; staleClear((int)x);
+                    tl[t].push_back(pl);
+                }
+            });
+            for (size_t t = 0; t < tl.size(); ++t) {
+                const uint32_t base = (uint32_t)pre_snap.size();
+                pre_snap.insert(pre_snap.end(), ts[t].begin(), ts[t].end());
+                for (PreList pl : tl[t]) { pl.snap_off += base; str_steps += pl.extra; pre_lists.push_back(pl); }
+            }
+            pre_active = !pre_lists.empty();
+            if (pre_active) {
+                scanned_dyn.assign(nlit, 0); pre_index.assign(nlit, -1);
+                for (size_t i = 0; i < pre_lists.size(); ++i) { pre_index[pre_lists[i].lit] = (int32_t)i; }
+            }
+        }
+        // (3) step contribution of the inert entries
+        parallelFor(nq, [&](size_t b, size_t e, int) {
+            for (size_t p2 = b; p2 < e; ++p2) {
+                const uint32_t c = strq[p2];
+                const ClauseInfo ci = C[c];
+                if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
                 if (c_str.slot[c] >= 0 || ((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }
                 const int32_t* s2 = pool.data() + ci.start; int minT = s2[0];
                 for (uint32_t j = 1; j < ci.size; ++j) { if (dcount(minT >> 1) > dcount(s2[j] >> 1)) { minT = s2[j]; } }
@@ -954,6 +1055,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 str_steps += contrib[end];
                 C[cr].flag &= ~F_STR;
                 ++n_fast; ++n_static;
+                if (pre_active) { const int mn = walk_min[end]; scanned_dyn[mn] = 1; scanned_dyn[mn ^ 1] = 1; }
                 continue;
             }
             if (end >= 16) {
@@ -980,9 +1082,11 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             str_steps += (hot[min].n ? (int64_t)hot[min].n - 1 : 0) + (int64_t)hot[nmin].n;
             C[cr].flag &= ~F_STR;
             ++n_fast;
+            if (pre_active) { scanned_dyn[min] = 1; scanned_dyn[nmin] = 1; }    // walked (found nothing to do)
             continue;
         }
         ++n_slow;
+        if (pre_active) { scanned_dyn[min] = 1; }
         // pass 1: occ(min) - the complementary literal is any literal but min
         {
             ListRef list = L(min);
@@ -1004,9 +1108,11 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         if (hasToPropagate()) {
             static_valid = false;            // counts and lists move now: the precomputed entries are void
+            rollbackPrecompact();
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
             e = strHits(cr);                 // cr itself may have been shortened by the propagation
         }
+        if (pre_active) { scanned_dyn[nmin] = 1; }
         // pass 2: occ(~min) - the complementary literal must be ~min
         {
             ListRef list_neg = L(nmin);
@@ -1025,6 +1131,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         if (hasToPropagate()) {
             static_valid = false;
+            rollbackPrecompact();
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
             t_sub.modified = t_sub.modified || t_up.modified;
         }
@@ -1034,6 +1141,10 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         updateOccurrences(useHeap, ignore);
         ret = ok ? L_UNDEF : L_FALSE;
     }
+    for (uint32_t c : strq) { if (c < qtime.size()) { qtime[c] = -1; } }
+    static_pass = false;
+    if (getenv("CP3_DEBUG_PRE")) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }
+    pre_active = false;
     host_ns_commit += now_ns() - t0;
     return ret;
 }
@@ -1121,8 +1232,8 @@ bool Engine::findGates(int v, int& p_limit, int& n_limit)
 // else one more batch (v plus the invalid variables near the top of the heap).
 Engine::PairEnt& Engine::pairsFor(int v)
 {
-    PairEnt& pe = pair_cache[v];
-    if (pe.valid && pe.touch == var_touch[v]) { return pe; }
+    if (pc_slot.size() < (size_t)nvars) { pc_slot.resize((size_t)nvars, -1); }
+    { PairEnt* pe0 = pairLookup(v); if (pe0 && pe0->valid && pe0->touch == var_touch[v]) { return *pe0; } }
     flushDevice();
     ++n_pair_batches;
     // batch: v plus every variable that waits in the heap with an outdated (or no) matrix
@@ -1136,10 +1247,9 @@ Engine::PairEnt& Engine::pairsFor(int v)
         if (np > 4096) { bve_inpend[w] = 0; continue; }             // rare long lists: on demand only
         // the reference's cut-off (BVE.cc:418-420) on the current counters: such variables are skipped anyway
         const bool cutoff = (hot[2 * w + 1].cnt > 10 && hot[2 * w].cnt > 10) || (dcount(w) > 15 && (hot[2 * w + 1].cnt > 5 || hot[2 * w].cnt > 5));
-        if (cutoff && !opt.bve_unlimited && !opt.bve_gates) { bve_inpend[w] = 0; continue; }
+        if (cutoff && !opt.bve_unlimited && !opt.bve_force_gates) { bve_inpend[w] = 0; continue; }
         if (budget + np > (64u << 20)) { bve_pending[keep++] = w; continue; }   // next batch
-        auto it = pair_cache.find(w);
-        if (it != pair_cache.end() && it->second.valid && it->second.touch == var_touch[w]) { bve_inpend[w] = 0; continue; }
+        { PairEnt* pw = pairLookup(w); if (pw && pw->valid && pw->touch == var_touch[w]) { bve_inpend[w] = 0; continue; } }
         budget += np; bve_inpend[w] = 0;
         vs.push_back(w);
     }
@@ -1182,30 +1292,39 @@ Engine::PairEnt& Engine::pairsFor(int v)
         if (cp3g_bve_resolve(gpu, (uint32_t)rv.size(), rv.data(), rp.data(), rn.data(), roff.data(), rlits.data(), roff.back()) != CP3G_OK) { die("bve_resolve failed"); }
         host_ns_gpuwait += now_ns() - t1;
     }
+    // one block per batch owns the data; the per-variable entries are views into it
+    pair_blocks.emplace_back(new PairBlock());
+    PairBlock& blk = *pair_blocks.back();
+    blk.roff.reserve(pair_off.back() + vs.size() + 1);
+    std::vector<size_t> roff_first(vs.size() + 1, 0), rl_first(vs.size() + 1, 0);
     for (size_t i = 0; i < vs.size(); ++i) {
-        PairEnt& q = pair_cache[vs[i]];
-        q.touch = var_touch[vs[i]]; q.valid = true;
-        q.pos.assign(p_refs.begin() + p_off[i], p_refs.begin() + p_off[i + 1]);
-        q.neg.assign(n_refs.begin() + n_off[i], n_refs.begin() + n_off[i + 1]);
-        q.sizes.assign(sizes.begin() + pair_off[i], sizes.begin() + pair_off[i + 1]);
-        q.has_res = want[i] != 0; q.roff.clear(); q.rlits.clear();
-        if (q.has_res) {
-            // roff: offset of pair (a,b) into rlits, in row-major pair order (only pairs with size >= 1 own literals)
-            const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i];
-            q.roff.assign((size_t)np * nn + 1, 0);
-            size_t r = rfirst[i]; const uint64_t base = roff[rfirst[i]];
-            for (uint64_t k = 0; k < (uint64_t)np * nn; ++k) {
-                q.roff[k] = (uint32_t)(roff[r] - base);
-                if (q.sizes[k] >= 1) { ++r; }
-            }
-            q.roff[(size_t)np * nn] = (uint32_t)(roff[r] - base);
-            q.rlits.assign(rlits.begin() + base, rlits.begin() + roff[rfirst[i + 1]]);
+        roff_first[i] = blk.roff.size(); rl_first[i] = (size_t)roff[rfirst[i]];
+        if (!want[i]) { continue; }
+        // roff: offset of pair (a,b) into this variable's literals, row-major (only pairs with size >= 1 own literals)
+        size_t r = rfirst[i]; const uint64_t base = roff[rfirst[i]];
+        for (uint64_t k = pair_off[i]; k < pair_off[i + 1]; ++k) {
+            blk.roff.push_back((uint32_t)(roff[r] - base));
+            if (sizes[k] >= 1) { ++r; }
         }
+        blk.roff.push_back((uint32_t)(roff[r] - base));
     }
-    return pair_cache[v];
+    roff_first[vs.size()] = blk.roff.size(); rl_first[vs.size()] = (size_t)roff.back();
+    blk.p_refs.swap(p_refs); blk.n_refs.swap(n_refs); blk.sizes.swap(sizes); blk.rlits.swap(rlits);
+    for (size_t i = 0; i < vs.size(); ++i) {
+        const int w = vs[i];
+        if (pc_slot[w] < 0) { pc_slot[w] = (int32_t)pc_ent.size(); pc_ent.emplace_back(); }
+        PairEnt& q = pc_ent[pc_slot[w]];
+        q.touch = var_touch[w]; q.valid = true; q.has_res = want[i] != 0;
+        q.pos = {blk.p_refs.data() + p_off[i], (size_t)(p_off[i + 1] - p_off[i])};
+        q.neg = {blk.n_refs.data() + n_off[i], (size_t)(n_off[i + 1] - n_off[i])};
+        q.sizes = {blk.sizes.data() + pair_off[i], (size_t)(pair_off[i + 1] - pair_off[i])};
+        q.roff = {blk.roff.data() + roff_first[i], roff_first[i + 1] - roff_first[i]};
+        q.rlits = {blk.rlits.data() + rl_first[i], (size_t)(roff[rfirst[i + 1]] - roff[rfirst[i]])};
+    }
+    return *pairLookup(v);
 }
 
-static inline int indexOf(const std::vector<uint32_t>& a, uint32_t x)
+template <class A> static inline int indexOf(const A& a, uint32_t x)
 {
     for (size_t i = 0; i < a.size(); ++i) { if (a[i] == x) { return (int)i; } }
     return -1;
@@ -1347,7 +1466,7 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
             for (uint32_t j = 0; j < negative.n; ++j) { col2[j] = indexOf(pe->neg, LP(negative)[j]); }
             for (const Pr& q : prs) {
                 const size_t idx = (size_t)indexOf(pe->pos, LP(positive)[q.cp]) * pe->neg.size() + col2[q.cn];
-                memcpy(rl.data() + q.off, pe->rlits.data() + pe->roff[idx], sizeof(int32_t) * (size_t)q.size);
+                memcpy(rl.data() + q.off, pe->rlits.p + pe->roff[idx], sizeof(int32_t) * (size_t)q.size);
             }
         } else if (!prs.empty()) {
             ++n_resolve_batches;
@@ -1512,7 +1631,7 @@ int Engine::bveProcess()
     if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
     const bool propagatedSomething = t_up.modified;
     sequentiellBVE();
-    pair_cache.clear();
+    pair_blocks.clear(); pc_ent.clear(); std::fill(pc_slot.begin(), pc_slot.end(), -1);
     if (!t_bve.modified) { unsuccessful(t_bve); }
     if (t_bve.modified || propagatedSomething) { successful(t_bve); }
     return ok ? L_UNDEF : L_FALSE;

@@ -15,6 +15,7 @@
 #include <unordered_map>
 #include <vector>
 #include <thread>
+#include <memory>
 #include "../../include/cp3b200.h"
 
 namespace cp3 {
@@ -145,7 +146,9 @@ private:
         // a full-queue bulk scan covers every clause that was live at that time: clauses without an entry had
         // no hit (no per-request record is kept for them)
         bool bulk_all = false; uint32_t bulk_scan = 0, bulk_ncl = 0; CacheEnt empty;
+        std::vector<uint32_t> used;                  // clauses whose slot is set (sparse reset: inner BVE calls are tiny)
         void clear();
+        inline void setSlot(uint32_t c, int32_t v) { if (slot[c] < 0) { used.push_back(c); } slot[c] = v; }
     };
     uint32_t n_live = 0;                             // clauses without F_DEL
     std::vector<uint64_t> delbits;                   // F_DEL as a cache-resident bitmap for the list walks
@@ -159,16 +162,31 @@ private:
     std::vector<int32_t> contrib;                    // per queue position: step contribution of a statically inert entry, or -1
     std::vector<uint64_t> is_target;                 // clauses that some cached hit may modify
     int nthreads = 1;
-    template <class F> void parallelFor(size_t n, F f);
+    // up-front cleaning of certainly-walked lists (strengtheningWorker) and what is needed to take it back
+    struct PreList { int lit; uint32_t snap_off, old_n, extra; };
+    std::vector<PreList> pre_lists; std::vector<uint32_t> pre_snap; std::vector<uint8_t> scanned_dyn;
+    std::vector<int32_t> pre_index, walk_min; std::vector<uint32_t> walk_count;   // per literal / per queue position
+    bool pre_active = false, static_pass = false; size_t static_nq = 0;
+    void rollbackPrecompact();
+    void restoreOneList(int x);
+    void unpredictedEdit(uint32_t c);               // a clause the static plan relied on was modified
+    template <class F> void parallelFor(size_t n, F f, size_t grain = 65536);
+    template <class F> void parallelForG(size_t n, size_t grain, F f) { parallelFor(n, f, grain); }
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
     // BVE pair cache
     std::vector<uint32_t> var_touch; std::vector<uint8_t> bve_inpend; std::vector<int> bve_pending;
     inline void bveTouch(int v) { ++var_touch[v]; if (!bve_inpend[v] && inHeap(v)) { bve_inpend[v] = 1; bve_pending.push_back(v); } }
-    struct PairEnt { uint32_t touch; std::vector<uint32_t> pos, neg; std::vector<int16_t> sizes; bool valid = false;
-                     bool has_res = false; std::vector<uint32_t> roff; std::vector<int32_t> rlits; };   // prefetched resolvents (K6)
-    std::unordered_map<int, PairEnt> pair_cache;
+    // K5/K6 results per variable: views into per-batch blocks (one allocation per batch, not per variable)
+    template <class T> struct Span { const T* p = nullptr; size_t n = 0; size_t size() const { return n; } const T& operator[](size_t i) const { return p[i]; } };
+    struct PairEnt { uint32_t touch = 0; bool valid = false, has_res = false;
+                     Span<uint32_t> pos, neg; Span<int16_t> sizes; Span<uint32_t> roff; Span<int32_t> rlits; };
+    struct PairBlock { std::vector<uint32_t> p_refs, n_refs, roff; std::vector<int16_t> sizes; std::vector<int32_t> rlits; };
+    std::vector<std::unique_ptr<PairBlock>> pair_blocks;
+    std::vector<int32_t> pc_slot; std::vector<PairEnt> pc_ent;
+    inline PairEnt* pairLookup(int v) { return (v < (int)pc_slot.size() && pc_slot[v] >= 0) ? &pc_ent[pc_slot[v]] : nullptr; }
+    std::vector<int> scratch_col;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
     int64_t host_ns_commit = 0, host_ns_gpuwait = 0;
     int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0, ph_upload = 0, ph_download = 0, ph_simplify = 0;

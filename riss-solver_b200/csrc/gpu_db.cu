@@ -32,6 +32,7 @@
 static constexpr uint32_t FLAG_DEL = 0x80000000u;
 static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
+static constexpr uint32_t PIN_HITS = 8192;
 
 struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
 struct __align__(16) OccEnt { uint32_t ref; uint32_t szfl; unsigned long long sig; };
@@ -660,6 +661,7 @@ struct cp3g {
     int rank = 0, world = 1; void* nccl = nullptr;
     int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0, scan_ns = 0, scan_alg_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint32_t* pin_cnt = nullptr; cp3g_hit* pin_hits = nullptr;          // pinned: counters + the first PIN_HITS hits come back with one sync
     void fail(const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); fprintf(stderr, "cp3b200: CUDA error %s\n", err.c_str()); }
 };
 
@@ -711,6 +713,7 @@ cp3g* cp3g_create(int device)
     cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (g->counters.reserve(16, false, g->stream)) { delete g; return nullptr; }
+    if (cudaHostAlloc((void**)&g->pin_cnt, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&g->pin_hits, PIN_HITS * sizeof(cp3g_hit), cudaHostAllocDefault) != cudaSuccess) { delete g; return nullptr; }
     return g;
 }
 
@@ -725,6 +728,7 @@ void cp3g_destroy(cp3g* g)
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
     cp3g_nccl_free(g->nccl);
+    if (g->pin_cnt) { cudaFreeHost(g->pin_cnt); } if (g->pin_hits) { cudaFreeHost(g->pin_hits); }
     cudaEventDestroy(g->ev0); cudaEventDestroy(g->ev1);
     cudaStreamDestroy(g->stream);
     delete g;
@@ -886,8 +890,7 @@ int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids)
     RESERVE(g->scratch_u32, n, false);
     CK(cudaMemcpyAsync(g->scratch_u32.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
     k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, g->scratch_u32.p, n);
-    CK(cudaStreamSynchronize(g->stream));
-    g->launches++; g->h2d += (int64_t)n * 4;
+    g->launches++; g->h2d += (int64_t)n * 4;        // stream ordered: the next scan on this stream sees it
     return CP3G_OK;
 }
 
@@ -904,7 +907,6 @@ int cp3g_shrink(cp3g* g, uint32_t n, const uint32_t* ids, const uint32_t* nstart
     CK(cudaMemcpyAsync(g->bl0.p, lits, nlits * 4, cudaMemcpyHostToDevice, g->stream));
     g->dirty_since_build = true;
     k_shrink<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->bu0.p, g->bu1.p, g->bu2.p, g->bl0.p, n);
-    CK(cudaStreamSynchronize(g->stream));
     g->launches++; g->h2d += (int64_t)n * 12 + (int64_t)nlits * 4;
     return CP3G_OK;
 }
@@ -936,7 +938,6 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
     CK(cudaMemcpyAsync(g->hdr.p + g->ncl, h.data(), (size_t)n * sizeof(ClauseHdr), cudaMemcpyHostToDevice, g->stream));
     RESERVE(g->ovf, g->ovf_host.size(), false);
     CK(cudaMemcpyAsync(g->ovf.p, g->ovf_host.data(), g->ovf_host.size() * 4, cudaMemcpyHostToDevice, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
     g->nlits += nlits; g->ncl += n; g->lits.used = g->nlits; g->hdr.used = g->ncl;
     g->h2d += (int64_t)(nlits * 4 + (size_t)n * sizeof(ClauseHdr) + g->ovf_host.size() * 4);
     // many young clauses make the brute-force part of k_scan expensive: fold them into the CSR
@@ -987,8 +988,10 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
         g->launches++;
     }
     t.stop();
-    uint32_t cnt[8];
-    CK(cudaMemcpyAsync(cnt, g->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
+    uint32_t* cnt = g->pin_cnt;
+    const uint32_t spec = (out != nullptr && g->world == 1) ? std::min<uint32_t>(cap, PIN_HITS) : 0u;
+    CK(cudaMemcpyAsync(cnt, g->counters.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (spec) { CK(cudaMemcpyAsync(g->pin_hits, g->hits.p, (size_t)spec * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream)); }
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     g->scan_ns += t.collect();
@@ -1001,8 +1004,11 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
         if (rr != CP3G_OK) { return rr; }
     } else if (n) {
-        CK(cudaMemcpyAsync(out, g->hits.p, (size_t)n * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
+        memcpy(out, g->pin_hits, (size_t)std::min(n, spec) * sizeof(cp3g_hit));
+        if (n > spec) {
+            CK(cudaMemcpyAsync(out + spec, g->hits.p + spec, (size_t)(n - spec) * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
+            CK(cudaStreamSynchronize(g->stream));
+        }
     }
     g->d2h += (int64_t)n * (int64_t)sizeof(cp3g_hit) + 32;
     if (nout) { *nout = n; }
