@@ -775,6 +775,181 @@ static inline const Hit* findHit(const std::vector<Hit>& hits, uint32_t hb, uint
     return (it != e && it->clause == clause) ? it : nullptr;
 }
 
+// Time-indexed form of the subsumption queue walk (subsumption_worker, Subsumption.cc:244-297) for large queues.
+//
+// The ordered walk is sequential only through three kinds of state, all of which are functions of *when the
+// subsumed clauses die*: (1) whether a subsumer is still alive at its turn, (2) lit_occurrence_count, which picks
+// the list a subsumer walks (removedClause decrements it at the moment of deletion), (3) which entries a walk
+// finds deleted and removes by swap-with-last.  Death times follow from the K3 hit lists alone - clause contents
+// do not change during this pass, so every hit is valid and a subsumer reaches every live superset through any of
+// its lists - by visiting ONLY the queue entries that have hits, in order (step 1, sequential, O(#hits)).
+// Everything else is then evaluated independently: the list choice of every queue entry against the counters
+// as of its own time (step 3, parallel over entries) and the lazy cleaning of every list that sees a deletion,
+// replayed over that list's walks in time order (step 4, parallel over lists).  The result - deleted set, final
+// list orders, step counter, doubly decremented counters - is identical to the ordered walk.
+bool Engine::subsumptionCommitParallel()
+{
+    const size_t nq = subq.size();
+    const int32_t INF = INT32_MAX;
+    const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr; int64_t tt = now_ns();
+    auto lap = [&](const char* w) { if (dbg) { int64_t n2 = now_ns(); fprintf(stderr, "  parsub %s %.1f ms\n", w, (n2 - tt) / 1e6); tt = n2; } };
+    if (sub_dtime.size() < C.size()) { sub_dtime.resize(C.size() + 1024, INF); sub_pos.resize(C.size() + 1024, -1); }
+    // step 0: queue position of every clause; a clause queued twice falls back to the ordered walk
+    bool dups = false;
+    parallelFor(nq, [&](size_t b, size_t e, int) {
+        for (size_t p = b; p < e; ++p) {
+            const int32_t old = __atomic_exchange_n(&sub_pos[subq[p]], (int32_t)p, __ATOMIC_RELAXED);
+            if (old >= 0) { dups = true; }
+        }
+    });
+    auto reset_pos = [&]() { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = -1; } }); };
+    if (dups) { reset_pos(); return false; }
+    lap("step0");
+    // step 1: death times.  Entries with hits, in processing order (time = nq-1-position).
+    std::vector<std::pair<int32_t, uint32_t>> hitters;           // (time, cache entry)
+    // the cache is keyed by clause: walk the clauses that own an entry
+    for (uint32_t c : c_sub.used) {
+        const int32_t slot = c_sub.slot[c];
+        if (slot < 0 || c_sub.ent[slot].hb == c_sub.ent[slot].he || sub_pos[c] < 0 || (C[c].flag & F_DEL)) { continue; }
+        hitters.push_back({(int32_t)(nq - 1 - (size_t)sub_pos[c]), (uint32_t)slot});
+    }
+    std::sort(hitters.begin(), hitters.end());
+    std::vector<uint32_t> dead;
+    for (const auto& h : hitters) {
+        const CacheEnt& e = c_sub.ent[h.second];
+        const uint32_t cr = subq[nq - 1 - (size_t)h.first];
+        if (sub_dtime[cr] < h.first) { continue; }                 // subsumed before its turn
+        for (uint32_t k = e.hb; k < e.he; ++k) {
+            const uint32_t d = c_sub.hits[k].clause;
+            if ((C[d].flag & F_DEL) || sub_dtime[d] != INF) { continue; }
+            sub_dtime[d] = h.first; dead.push_back(d);
+        }
+    }
+    lap("step1");
+    // step 2: per literal, the sorted death times of the clauses that contain it (bucketed by literal range,
+    //         64-aligned so that no two buckets share a word of the stale bitmap)
+    struct LT { int32_t lit, time; };
+    const size_t nlit = (size_t)2 * nvars;
+    const int NB = std::max(1, nthreads);
+    auto bucketLo = [&](int bk) -> int32_t { return (int32_t)std::min(nlit, ((nlit * (size_t)bk / NB) + 63) / 64 * 64); };
+    const size_t bwidth = std::max<size_t>(64, (nlit / NB) / 64 * 64);
+    auto bucketOf = [&](int x) -> int { int bk = (int)std::min<size_t>((size_t)NB - 1, (size_t)x / bwidth); while (bk > 0 && x < bucketLo(bk)) { --bk; } while (bk + 1 < NB && x >= bucketLo(bk + 1)) { ++bk; } return bk; };
+    std::vector<std::vector<LT>> dlb((size_t)NB);
+    if (dl_start.size() < nlit) { dl_start.assign(nlit, -1); dl_cnt.assign(nlit, 0u); }
+    parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
+        for (size_t bk = bb; bk < be; ++bk) {
+            const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
+            std::vector<LT>& v = dlb[bk];
+            for (uint32_t d : dead) { const int32_t* l = CL(d); for (uint32_t k = 0; k < C[d].size; ++k) { if (l[k] >= lo && l[k] < hi) { v.push_back({l[k], sub_dtime[d]}); } } }
+            std::sort(v.begin(), v.end(), [](const LT& a2, const LT& b2) { return a2.lit != b2.lit ? a2.lit < b2.lit : a2.time < b2.time; });
+            for (size_t i = 0; i < v.size(); ++i) { if (dl_start[v[i].lit] < 0) { dl_start[v[i].lit] = (int32_t)i; } ++dl_cnt[v[i].lit]; }
+        }
+    }, 1);
+    auto countAt = [&](int x, int32_t T) -> int32_t {               // lit_occurrence_count[x] as of time T
+        int32_t c = hot[x].cnt;
+        if (dl_cnt[x]) { const LT* q = dlb[bucketOf(x)].data() + dl_start[x]; for (uint32_t k = 0; k < dl_cnt[x] && q[k].time < T; ++k) { --c; } }
+        return c;
+    };
+    // step 3: every queue entry picks its list with the counters of its own time.  Walks of lists that never hold
+    // a deleted clause just add |list|-1 steps; the others become events for step 4.
+    struct Ev { int32_t lit, time; uint32_t pos; };
+    std::vector<std::vector<Ev>> tev((size_t)nthreads + 1); std::vector<int64_t> tsteps((size_t)nthreads + 1, 0);
+    parallelFor(nq, [&](size_t b, size_t e, int t) {
+        int64_t st = 0; std::vector<Ev>& ev = tev[t];
+        for (size_t p = b; p < e; ++p) {
+            const uint32_t cr = subq[p]; const ClauseInfo ci = C[cr];
+            if (ci.flag & F_DEL) { continue; }
+            const int32_t T = (int32_t)(nq - 1 - p);
+            if (sub_dtime[cr] < T) { continue; }
+            const int32_t* c = pool.data() + ci.start;
+            int mn = c[0]; int32_t best = countAt(mn, T);
+            for (uint32_t l = 1; l < ci.size; ++l) { const int32_t v = countAt(c[l], T); if (v < best) { best = v; mn = c[l]; } }
+            if (dl_cnt[mn] == 0 && !hasStale(mn)) { st += hot[mn].n ? (int64_t)hot[mn].n - 1 : 0; }
+            else { ev.push_back({mn, T, (uint32_t)p}); }
+        }
+        tsteps[t] = st;
+    });
+    int64_t steps = 0; for (int64_t x : tsteps) { steps += x; }
+    lap("step3");
+    // step 4: replay the walks of every list that holds a deleted clause, list by list, in time order
+    std::vector<int64_t> bsteps((size_t)NB, 0);
+    std::vector<std::vector<int32_t>> bwalked((size_t)NB);
+    parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
+        for (size_t bk = bb; bk < be; ++bk) {
+            const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
+            std::vector<Ev> mine;
+            for (const auto& v : tev) { for (const Ev& x : v) { if (x.lit >= lo && x.lit < hi) { mine.push_back(x); } } }
+            std::sort(mine.begin(), mine.end(), [](const Ev& a, const Ev& b) { return a.lit != b.lit ? a.lit < b.lit : a.time < b.time; });
+            int64_t st = 0;
+            for (size_t i = 0; i < mine.size();) {
+                const int x = mine[i].lit;
+                uint32_t* lp = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n; uint32_t removed = 0;
+                for (; i < mine.size() && mine[i].lit == x; ++i) {
+                    const uint32_t cr = subq[mine[i].pos]; const uint32_t cn = C[cr].size; const int32_t T = mine[i].time;
+                    for (uint32_t j = 0; j < n; ++j) {
+                        const uint32_t d = lp[j];
+                        if (d == cr) { continue; }
+                        ++st;
+                        if ((C[d].flag & F_DEL) || sub_dtime[d] < T) {          // found deleted: size filter first, then lazy removal
+                            if (C[d].size < cn) { continue; }
+                            lp[j] = lp[n - 1]; --n; --j; ++removed;
+                        }
+                    }
+                }
+                hot[x].n = n;
+                // deleted clauses still listed here afterwards = those before + the ones that died now - the removed
+                stale[x] = stale[x] + dl_cnt[x] - removed;
+                bwalked[bk].push_back(x);
+            }
+            // lists that hold a newly deleted clause but were not walked keep it: count it as stale.  Then the
+            // counters (removedClause twice per clause - Subsumption.cc:284,305) and the stale bitmap of this bucket.
+            const std::vector<LT>& v = dlb[bk]; size_t w = 0; const std::vector<int32_t>& wl = bwalked[bk];
+            for (size_t i = 0; i < v.size(); i += dl_cnt[v[i].lit]) {
+                const int x = v[i].lit;
+                while (w < wl.size() && wl[w] < x) { ++w; }
+                if (!(w < wl.size() && wl[w] == x)) { stale[x] += dl_cnt[x]; }
+                hot[x].cnt -= 2 * (int32_t)dl_cnt[x];
+                if (stale[x]) { stalebits[(uint32_t)x >> 6] |= 1ull << (x & 63); } else { stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); }
+            }
+            for (int32_t x : wl) { if (stale[x]) { stalebits[(uint32_t)x >> 6] |= 1ull << (x & 63); } else { stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); } }
+            bsteps[bk] = st;
+        }
+    }, 1);
+    for (int64_t x : bsteps) { steps += x; }
+    lap("step4");
+    // step 5: commit the deletions themselves
+    {
+        std::vector<int64_t> tlits((size_t)nthreads + 1, 0);
+        parallelFor(dead.size(), [&](size_t b2, size_t e2, int t) {
+            int64_t nl = 0;
+            for (size_t i = b2; i < e2; ++i) {
+                const uint32_t d = dead[i];
+                nl += C[d].size;
+                C[d].flag |= F_DEL;
+                __atomic_fetch_or(&delbits[d >> 6], 1ull << (d & 63), __ATOMIC_RELAXED);
+                const int32_t* l = CL(d);
+                for (uint32_t k = 0; k < C[d].size; ++k) { deletedVar(l[k] >> 1); }
+            }
+            tlits[t] = nl;
+        }, 8192);
+        int64_t nl = 0; for (int64_t x : tlits) { nl += x; }
+        subsumedClauses += (int)dead.size(); subsumedLiterals += (int)nl;
+        n_live -= (uint32_t)dead.size();
+        numberOfCls -= 2 * (int)dead.size(); ca_wasted += 2 * (2.0 * (double)dead.size() + (double)nl);
+        if (dev_uploaded) { pend_del.insert(pend_del.end(), dead.begin(), dead.end()); }
+        if (opt.bve) { for (uint32_t d : dead) { touchClauseVars(d); } }
+    }
+    if (!dead.empty()) { successful(t_sub); }
+    sub_steps += steps;
+    // sparse resets
+    for (uint32_t d : dead) { sub_dtime[d] = INF; }
+    for (const auto& v : dlb) { for (const LT& x : v) { dl_start[x.lit] = -1; dl_cnt[x.lit] = 0; } }
+    reset_pos();
+    lap("step5");
+    ++n_parsub;
+    return true;
+}
+
 // subsumption_worker, Subsumption.cc:220-314.  One bulk K3 scan answers every ordered_subsumes() of the
 // queue; the loop below replays the queue back to front.
 void Engine::subsumptionWorker(bool useHeap, int ignore)
@@ -791,6 +966,17 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
         scanClauses(CP3G_SUBSUME, ids, c_sub);
     }
     int64_t t0 = now_ns();
+    static const size_t parsub_min = getenv("CP3_PARSUB_MIN") ? (size_t)atoi(getenv("CP3_PARSUB_MIN")) : 65536;
+    if (!useHeap && subq.size() >= parsub_min) {
+        // step limit: the data-parallel form cannot stop in the middle of the queue; only use it far from the limit
+        int64_t bound = 0;
+        if (!unlimited) { for (uint32_t c : subq) { if (!(C[c].flag & F_DEL)) { int mx = 0; const int32_t* l = CL(c); for (uint32_t k = 0; k < C[c].size; ++k) { mx = std::max<int>(mx, (int)hot[l[k]].n); } bound += mx; } } }
+        if ((unlimited || sub_steps + bound < sub_lim) && subsumptionCommitParallel()) {
+            for (uint32_t c : subq) { C[c].flag &= ~F_SUB; }
+            host_ns_commit += now_ns() - t0;
+            return;
+        }
+    }
     size_t end = subq.size();
     sub_occ_updates.clear();
     const size_t PF = 16;                               // the walk is bound by cache misses on occ[lit]
@@ -1774,7 +1960,7 @@ int64_t Engine::stat(const char* s) const
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
-    ST("queue_static", n_static)
+    ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

@@ -243,6 +243,9 @@ private:
     int propagationProcess(bool sort, bool useHeap, int ignore);
     bool hasToPropagate() const { return (int)trail.size() != qhead; }
     void subsumptionWorker(bool useHeap, int ignore);
+    bool subsumptionCommitParallel();                // time-indexed, data-parallel form of the queue walk
+    std::vector<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt;
+    int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
     void updateOccurrences(bool useHeap, int ignore);
