@@ -292,10 +292,10 @@ void Engine::flushDevice()
 }
 
 // One GPU scan over the clauses `ids`; results land in `cache` keyed by clause and content version.
-void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache)
+void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache, int forceBulk)
 {
     if (ids.empty()) { return; }
-    flushDevice();
+    if (!scan_no_flush) { flushDevice(); }
     ++scan_id; ++n_scan_batches;
     if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
     // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
@@ -303,7 +303,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     for (uint32_t c : ids) { ((C[c].flag & F_DEL) ? dead : live).push_back(c); }
     int64_t t0 = now_ns();
     static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
-    if (dead.empty() && live.size() == n_live && n_live > bulk_min) {
+    if (forceBulk == 1 || (forceBulk < 0 && dead.empty() && live.size() == n_live && n_live > bulk_min)) {
         // the queue holds every live clause: full-queue bulk kernel (one thread per occurrence entry)
         uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, live.size() / 8));
         uint32_t n = 0; uint64_t chk = 0;
@@ -971,10 +971,29 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
         // step limit: the data-parallel form cannot stop in the middle of the queue; only use it far from the limit
         int64_t bound = 0;
         if (!unlimited) { for (uint32_t c : subq) { if (!(C[c].flag & F_DEL)) { int mx = 0; const int32_t* l = CL(c); for (uint32_t k = 0; k < C[c].size; ++k) { mx = std::max<int>(mx, (int)hot[l[k]].n); } bound += mx; } } }
-        if ((unlimited || sub_steps + bound < sub_lim) && subsumptionCommitParallel()) {
-            for (uint32_t c : subq) { C[c].flag &= ~F_SUB; }
-            host_ns_commit += now_ns() - t0;
-            return;
+        if (unlimited || sub_steps + bound < sub_lim) {
+            // the strengthening pass that follows needs nothing from this commit but the deleted flags (a hit on a
+            // clause that dies meanwhile is dropped at commit time): run its scan + closure concurrently
+            static const bool no_overlap = getenv("CP3_NO_OVERLAP") != nullptr;
+            std::thread helper; std::vector<uint32_t> sids; bool sbulk = false;
+            const bool ov = overlap_str && !no_overlap && nthreads > 1 && opt.strength && strq.size() >= parsub_min && !hasToPropagate();
+            if (ov) {
+                for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { sids.push_back(c); } }
+                std::sort(sids.begin(), sids.end());
+                sids.erase(std::unique(sids.begin(), sids.end()), sids.end());
+                static const uint32_t bulk_min2 = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
+                sbulk = sids.size() == n_live && n_live > bulk_min2;
+                flushDevice();
+                scan_no_flush = true;
+                helper = std::thread([this, &sids, sbulk]() { prepareStrengthening(sids, sbulk); });
+            }
+            const bool done = subsumptionCommitParallel();
+            if (ov) { helper.join(); scan_no_flush = false; str_prepared = true; ++n_overlap; }
+            if (done) {
+                for (uint32_t c : subq) { C[c].flag &= ~F_SUB; }
+                host_ns_commit += now_ns() - t0;
+                return;
+            }
         }
     }
     size_t end = subq.size();
@@ -1123,13 +1142,27 @@ void Engine::unpredictedEdit(uint32_t c)
     }
 }
 
+// K4 over the strengthening queue + speculative closure (first half of a strengthening pass)
+void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
+{
+    c_str.clear();
+    scanClauses(CP3G_STRENGTHEN, ids, c_str, scan_no_flush ? (bulk ? 1 : 0) : -1);
+    // processing time of the queue entries: the queue is drained from the back
+    if (qtime.size() < C.size()) { qtime.resize(C.size() + 1024, -1); }
+    for (size_t i = 0; i < strq.size(); ++i) { qtime[strq[i]] = (int32_t)(strq.size() - 1 - i); }
+    for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
+    for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
+    prefetchStrengthenClosure();
+}
+
 // strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
 int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_str);
     const bool unlimited = !opt.limited;
-    c_str.clear(); logClear(); dirty_str.clear();
-    if (opt.strength) {
+    logClear(); dirty_str.clear();
+    if (str_prepared) { str_prepared = false; }            // scan + closure were done while the subsumption commit ran
+    else if (opt.strength) {
         std::vector<uint32_t> ids;
         for (uint32_t c : strq) {
             if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
@@ -1137,14 +1170,8 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         std::sort(ids.begin(), ids.end());
         ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
-        scanClauses(CP3G_STRENGTHEN, ids, c_str);
-        // processing time of the queue entries: the queue is drained from the back
-        if (qtime.size() < C.size()) { qtime.resize(C.size() + 1024, -1); }
-        for (size_t i = 0; i < strq.size(); ++i) { qtime[strq[i]] = (int32_t)(strq.size() - 1 - i); }
-        for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
-        for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
-        prefetchStrengthenClosure();
-    }
+        prepareStrengthening(ids, false);
+    } else { c_str.clear(); }
     int64_t t0 = now_ns();
     // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
     // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
@@ -1338,7 +1365,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
 // Subsumption::process, Subsumption.cc:85-180
 bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
 {
-    t_sub.modified = false;
+    t_sub.modified = false; str_prepared = false;
     if (!ok) { return false; }
     if (!performSimplification(t_sub)) {
         clearQueue(subq, F_SUB); clearQueue(strq, F_STR);
@@ -1348,7 +1375,9 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
     if (!(str_steps + opt.call_inc < str_lim)) { str_lim += opt.call_inc; limitIncreases++; }
     while (ok && (!subq.empty() || !strq.empty())) {
         if (!subq.empty()) {
+            overlap_str = doStrengthen && !strq.empty();
             subsumptionWorker(useHeap, ignore);
+            overlap_str = false;
             clearQueue(subq, F_SUB);
         }
         if (!strq.empty()) {
@@ -1356,6 +1385,7 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
             strengtheningWorker(useHeap, ignore);
             clearQueue(strq, F_STR);
         }
+        str_prepared = false;
     }
     t_sub.modified = t_sub.modified || t_up.modified;   // propagation.appliedSomething(): its last call
     if (!t_sub.modified) { unsuccessful(t_sub); }
@@ -1960,7 +1990,7 @@ int64_t Engine::stat(const char* s) const
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
-    ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub)
+    ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("overlapped_str_scans", n_overlap)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

@@ -243,7 +243,12 @@ private:
     int propagationProcess(bool sort, bool useHeap, int ignore);
     bool hasToPropagate() const { return (int)trail.size() != qhead; }
     void subsumptionWorker(bool useHeap, int ignore);
-    bool subsumptionCommitParallel();                // time-indexed, data-parallel form of the queue walk
+    bool subsumptionCommitParallel();
+    // overlap: the strengthening scan + speculative closure of this fixpoint round run on a helper thread (GPU +
+    // one core) while the subsumption commit occupies the other cores
+    bool overlap_str = false, str_prepared = false, scan_no_flush = false;
+    void prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk);
+    int64_t n_overlap = 0;                // time-indexed, data-parallel form of the queue walk
     std::vector<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt;
     int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
@@ -267,7 +272,7 @@ private:
     void uploadAll();
     void flushDevice();
     // scan `ids` (clause indices, device content) and store the result in `cache`
-    void scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache);
+    void scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache, int forceBulk = -1);
     const CacheEnt* cached(const ScanCache& cache, uint32_t c) const;
     bool subHitValid(uint32_t c, uint32_t d, uint32_t scan) const;
     bool strHitValid(uint32_t s, uint32_t d, int f, uint32_t scan) const;
