@@ -133,27 +133,36 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
     for (int k = 0; k < SCAN_I; ++k) { if (base + k < n) { out[base + k] += add; } }
 }
 
+// Scatter only the 4-byte clause index: the refs of a list (avg 6.4 x 4 B) share one 32-byte sector and the whole
+// array (55 MB at C2) stays L2 resident, whereas scattering the 16-byte entries costs a DRAM read-modify-write per
+// partial sector (0.98 ms at C2, profiles/r01b).  The entries are written afterwards by k_occ_expand, coalesced.
 __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, OccEnt* __restrict__ ent,
-                           uint32_t* __restrict__ ent_lit)
+                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ refs)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
     const ClauseHdr h = hdr[i];
     if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
-    OccEnt e; e.ref = i; e.szfl = h.szfl & SIZE_MASK; e.sig = h.sig;
     for (uint32_t k = 0; k < sz; ++k) {
         const int32_t x = lits[h.start + k];
-        const uint32_t p = atomicAdd(&cursor[x], 1u);
-        ent[off[x] + p] = e;
-        ent_lit[off[x] + p] = (uint32_t)x;
+        refs[off[x] + atomicAdd(&cursor[x], 1u)] = i;
     }
+}
+// one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced
+__global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ refs, OccEnt* __restrict__ ent, uint32_t total)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    const uint32_t r = refs[i];
+    const ClauseHdr h = hdr[r];
+    OccEnt e; e.ref = r; e.szfl = h.szfl & SIZE_MASK; e.sig = h.sig;
+    ent[i] = e;
 }
 // The "tagged" CSR of the candidate-major bulk kernels: clause c is filed under the literal whose list a bulk
 // scan walks for it (xs for subsumption, xt for strengthening).  phase 0 counts, phase 1 fills.
 __global__ void k_tag(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                      const uint32_t* __restrict__ off, int phase,
+                      const uint32_t* __restrict__ off, int phase, int2* __restrict__ tagx,
                       uint32_t* __restrict__ cnt_sub, uint32_t* __restrict__ cnt_str,
                       const uint32_t* __restrict__ toff_sub, const uint32_t* __restrict__ toff_str,
                       OccEnt* __restrict__ tag_sub, OccEnt* __restrict__ tag_str)
@@ -164,62 +173,63 @@ __global__ void k_tag(const ClauseHdr* __restrict__ hdr, const int32_t* __restri
     if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
     if (sz == 0) { return; }
-    uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = 0, xt = 0;
-    for (uint32_t k = 0; k < sz; ++k) {
-        const int32_t x = lits[h.start + k];
-        const uint32_t len = off[x + 1] - off[x];
-        const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
-        if (len < bs) { bs = len; xs = x; }
-        if (both < bt) { bt = both; xt = x; }
-    }
-    if (phase == 0) { atomicAdd(&cnt_sub[xs], 1u); atomicAdd(&cnt_str[xt], 1u); }
-    else {
+    if (phase == 0) {
+        uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = 0, xt = 0;
+        for (uint32_t k = 0; k < sz; ++k) {
+            const int32_t x = lits[h.start + k];
+            const uint32_t len = off[x + 1] - off[x];
+            const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
+            if (len < bs) { bs = len; xs = x; }
+            if (both < bt) { bt = both; xt = x; }
+        }
+        tagx[c] = make_int2(xs, xt);
+        atomicAdd(&cnt_sub[xs], 1u); atomicAdd(&cnt_str[xt], 1u);
+    } else {
+        const int2 x = tagx[c];
         OccEnt e; e.ref = c; e.szfl = sz; e.sig = h.sig;
-        tag_sub[toff_sub[xs] + atomicAdd(&cnt_sub[xs], 1u)] = e;
-        tag_str[toff_str[xt] + atomicAdd(&cnt_str[xt], 1u)] = e;
+        tag_sub[toff_sub[x.x] + atomicAdd(&cnt_sub[x.x], 1u)] = e;
+        tag_str[toff_str[x.y] + atomicAdd(&cnt_str[x.y], 1u)] = e;
     }
 }
-// scatter order is nondeterministic; the reference order is ascending clause index -> sort every list
-__global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, OccEnt* __restrict__ ent,
-                                 uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
+// scatter order is nondeterministic; the reference order is ascending clause index -> sort every list.
+// The same pass writes the literal of each entry (constant per list).
+__global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, uint32_t* __restrict__ refs,
+                                 uint32_t* __restrict__ ent_lit, uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
 {
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= nlit) { return; }
     const uint32_t b = off[x], e = off[x + 1], len = e - b;
-    if (len < 2) { return; }
+    if (len == 0) { return; }
     if (len > SHORT_LIST) { long_lits[atomicAdd(nlong, 1u)] = x; return; }
     for (uint32_t i = b + 1; i < e; ++i) {
-        OccEnt key = ent[i];
+        const uint32_t key = refs[i];
         uint32_t j = i;
-        while (j > b && ent[j - 1].ref > key.ref) { ent[j] = ent[j - 1]; --j; }
-        ent[j] = key;
+        while (j > b && refs[j - 1] > key) { refs[j] = refs[j - 1]; --j; }
+        refs[j] = key;
     }
+    for (uint32_t i = b; i < e; ++i) { ent_lit[i] = x; }
 }
-// one block per long list: normalised bitonic sort on ref in global memory.  Every compare-exchange is
-// ascending (i < l keeps the smaller ref at i), so the virtual +inf padding above len never has to move
-// and pairs that touch it are simply skipped.
-__device__ __forceinline__ void ce_asc(OccEnt* a, uint32_t i, uint32_t l)
-{
-    OccEnt ei = a[i], el = a[l];
-    if (ei.ref > el.ref) { a[i] = el; a[l] = ei; }
-}
+// one block per long list: normalised bitonic sort in global memory.  Every compare-exchange is ascending
+// (i < l keeps the smaller ref at i), so the virtual +inf padding above len never has to move and pairs that
+// touch it are simply skipped.
 __global__ void k_occ_sort_long(const uint32_t* __restrict__ off, const uint32_t* __restrict__ long_lits,
-                                OccEnt* __restrict__ ent)
+                                uint32_t* __restrict__ refs, uint32_t* __restrict__ ent_lit)
 {
     const uint32_t x = long_lits[blockIdx.x];
-    OccEnt* a = ent + off[x];
+    uint32_t* a = refs + off[x];
     const uint32_t len = off[x + 1] - off[x];
+    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { ent_lit[off[x] + i] = x; }
     uint32_t p2 = 1; while (p2 < len) { p2 <<= 1; }
     for (uint32_t k = 2; k <= p2; k <<= 1) {
         for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
             const uint32_t l = i ^ (k - 1);
-            if (l > i && l < len) { ce_asc(a, i, l); }
+            if (l > i && l < len) { const uint32_t u = a[i], v = a[l]; if (u > v) { a[i] = v; a[l] = u; } }
         }
         __syncthreads();
         for (uint32_t j = k >> 2; j > 0; j >>= 1) {
             for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
                 const uint32_t l = i ^ j;
-                if (l > i && l < len) { ce_asc(a, i, l); }
+                if (l > i && l < len) { const uint32_t u = a[i], v = a[l]; if (u > v) { a[i] = v; a[l] = u; } }
             }
             __syncthreads();
         }
@@ -652,7 +662,7 @@ struct cp3g {
     size_t nlits = 0;
     DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent, tag_sub, tag_str; DevBuf<uint32_t> ent_lit, delbits, refs_tmp, toff_sub, toff_str, tcnt_sub, tcnt_str; bool dirty_since_build = true;
+    DevBuf<OccEnt> occ_ent, tag_sub, tag_str; DevBuf<int2> tagx; DevBuf<uint32_t> ent_lit, delbits, refs_tmp, toff_sub, toff_str, tcnt_sub, tcnt_str; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
     DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
@@ -723,7 +733,7 @@ void cp3g_destroy(cp3g* g)
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
-    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release(); g->delbits.release(); g->refs_tmp.release(); g->tag_sub.release(); g->tag_str.release(); g->toff_sub.release(); g->toff_str.release(); g->tcnt_sub.release(); g->tcnt_str.release();
+    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release(); g->delbits.release(); g->refs_tmp.release(); g->tag_sub.release(); g->tag_str.release(); g->tagx.release(); g->toff_sub.release(); g->toff_str.release(); g->tcnt_sub.release(); g->tcnt_str.release();
     g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
@@ -809,27 +819,32 @@ static int build_csr(cp3g* g)
     g->total_occ = total;
     RESERVE(g->occ_ent, (size_t)total + 1, false);
     RESERVE(g->ent_lit, (size_t)total + 1, false);
+    RESERVE(g->refs_tmp, (size_t)total + 1, false);
     CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     if (g->ncl) {
-        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->occ_ent.p, g->ent_lit.p);
-        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->occ_ent.p, g->long_lits.p, g->counters.p + 1);
+        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->refs_tmp.p);
+        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->ent_lit.p, g->long_lits.p, g->counters.p + 1);
         g->launches += 2;
     }
     uint32_t nlong = 0;
     CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
     if (nlong) {
-        k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->occ_ent.p);
+        k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p, g->ent_lit.p);
+        g->launches += 1;
+    }
+    if (total) {
+        k_occ_expand<<<grid_for(total, 256), 256, 0, g->stream>>>(g->hdr.p, g->refs_tmp.p, g->occ_ent.p, total);
         g->launches += 1;
     }
     if (g->ncl) {
         // tagged CSR for the candidate-major bulk kernels
         RESERVE(g->toff_sub, (size_t)nlit + 2, false); RESERVE(g->toff_str, (size_t)nlit + 2, false);
         RESERVE(g->tcnt_sub, (size_t)nlit + 2, false); RESERVE(g->tcnt_str, (size_t)nlit + 2, false);
-        RESERVE(g->tag_sub, (size_t)g->ncl + 1, false); RESERVE(g->tag_str, (size_t)g->ncl + 1, false);
+        RESERVE(g->tag_sub, (size_t)g->ncl + 1, false); RESERVE(g->tag_str, (size_t)g->ncl + 1, false); RESERVE(g->tagx, (size_t)g->ncl + 1, false);
         CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
         CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 0, g->tcnt_sub.p, g->tcnt_str.p,
+        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 0, g->tagx.p, g->tcnt_sub.p, g->tcnt_str.p,
                                                           nullptr, nullptr, nullptr, nullptr);
         for (int w = 0; w < 2; ++w) {
             uint32_t* cntp = w == 0 ? g->tcnt_sub.p : g->tcnt_str.p; uint32_t* offp = w == 0 ? g->toff_sub.p : g->toff_str.p;
@@ -839,7 +854,7 @@ static int build_csr(cp3g* g)
         }
         CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
         CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 1, g->tcnt_sub.p, g->tcnt_str.p,
+        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 1, g->tagx.p, g->tcnt_sub.p, g->tcnt_str.p,
                                                           g->toff_sub.p, g->toff_str.p, g->tag_sub.p, g->tag_str.p);
         g->launches += 8;
     }

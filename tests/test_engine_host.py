@@ -101,3 +101,17 @@ def test_freeze_blocks_elimination(mock):
     out = cp.output_stream()
     assert np.array_equal(out[2 * cp.output_units():], want.stream)
     cp.close()
+
+
+FORCED = {"CP3_PARSUB_MIN": "0", "CP3_STATIC_MIN": "0", "CP3_BULK_MIN": "0", "CP3_THREADS": "3"}
+
+
+def test_forced_parallel_paths_fuzz(mock):
+    """The data-parallel commit paths (time-indexed subsumption commit, static strengthening plan with up-front list
+    cleaning + rollback, full-queue bulk scans, scan/commit overlap) only switch on for large queues; force them on
+    tiny formulas (the thresholds are read once per process, hence the subprocess) and fuzz against the oracle."""
+    import subprocess, sys
+    env = dict(os.environ, **FORCED)
+    p = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_engine.py"), "250", "9001"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -182,3 +182,26 @@ def test_c2_size_properties(gen):
     b = run_gpu(full, SUSI + ["-no-cp3_limited"])
     assert b.stats["sub_subsumedClauses"] == 0 and b.stats["sub_removedLiterals"] == 0
     assert np.array_equal(b.stream, out)
+
+
+def test_forced_parallel_paths_on_gpu(gen):
+    """same fuzz as test_fuzz_small_instances with the large-queue code paths (bulk kernels k_bulk_cm, time-indexed
+    subsumption commit, static strengthening plan, scan/commit overlap) forced on; thresholds are read once per
+    process, hence the subprocess"""
+    import subprocess, sys
+    code = (
+        "import sys, os; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "import numpy as np\n"
+        "from harness import run_oracle, compare, load_gen\n"
+        "from test_gpu_parity import run_gpu\n"
+        "from fuzz_oracle import OPTSETS, random_instance\n"
+        "gen = load_gen(); rng = np.random.default_rng(77); bad = 0\n"
+        "for r in range(80):\n"
+        "    lits, sizes = random_instance(rng); stream = gen.csr_to_stream(lits, sizes)\n"
+        "    opts = OPTSETS[int(rng.integers(0, len(OPTSETS)))]\n"
+        "    d = compare(run_gpu(stream, opts), run_oracle(stream, opts))\n"
+        "    if d: bad += 1; print(r, opts, d[:3])\n"
+        "print('BAD', bad)\n") % (ROOT, ROOT)
+    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "BAD 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
