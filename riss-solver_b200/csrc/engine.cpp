@@ -77,6 +77,29 @@ void Options::preset(const char* name)
     }
 }
 
+// sort + unique of a clause id list; queues that were filled in clause order (the first round) are already sorted
+static void sortUnique(std::vector<uint32_t>& v)
+{
+    bool strictly = true;
+    for (size_t i = 1; i < v.size(); ++i) { if (v[i - 1] >= v[i]) { strictly = false; break; } }
+    if (strictly) { return; }
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+}
+
+// large hit lists arrive sorted by (request, clause) from the device (gpu_db.cu sort_hits); small or gathered ones are sorted here
+static void sortHits(std::vector<cp3g_hit>& h, uint32_t n)
+{
+    auto less = [](const cp3g_hit& a, const cp3g_hit& b) { return a.req != b.req ? a.req < b.req : a.clause < b.clause; };
+    if (!std::is_sorted(h.begin(), h.begin() + n, less)) { std::sort(h.begin(), h.begin() + n, less); }
+}
+
+struct DbgLap {
+    bool on; int64_t t; const char* who;
+    explicit DbgLap(const char* w) : on(getenv("CP3_DEBUG_PAR") != nullptr), t(on ? now_ns() : 0), who(w) {}
+    void operator()(const char* what) { if (on) { int64_t n2 = now_ns(); fprintf(stderr, "  %s %s %.1f ms\n", who, what, (n2 - t) / 1e6); t = n2; } }
+};
+
 void Engine::ScanCache::clear()
 {
     for (uint32_t c : used) { slot[c] = -1; }
@@ -295,17 +318,25 @@ void Engine::flushDevice()
 void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache, int forceBulk)
 {
     if (ids.empty()) { return; }
+    DbgLap lap(kind == CP3G_SUBSUME ? "scanClauses<sub>" : "scanClauses<str>");
     if (!scan_no_flush) { flushDevice(); }
+    lap("flush");
     ++scan_id; ++n_scan_batches;
     if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
     // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
-    std::vector<uint32_t> live, dead;
-    for (uint32_t c : ids) { ((C[c].flag & F_DEL) ? dead : live).push_back(c); }
-    int64_t t0 = now_ns();
     static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
-    if (forceBulk == 1 || (forceBulk < 0 && dead.empty() && live.size() == n_live && n_live > bulk_min)) {
+    bool bulk = forceBulk == 1;
+    if (forceBulk < 0 && ids.size() == n_live && n_live > bulk_min) {
+        bulk = true;
+        for (uint32_t c : ids) { if (C[c].flag & F_DEL) { bulk = false; break; } }
+    }
+    std::vector<uint32_t> live, dead;
+    if (!bulk) { for (uint32_t c : ids) { ((C[c].flag & F_DEL) ? dead : live).push_back(c); } }
+    lap("split");
+    int64_t t0 = now_ns();
+    if (bulk) {
         // the queue holds every live clause: full-queue bulk kernel (one thread per occurrence entry)
-        uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, live.size() / 8));
+        uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, ids.size() / 8));
         uint32_t n = 0; uint64_t chk = 0;
         for (;;) {
             hitbuf.resize(cap);
@@ -314,8 +345,9 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
             die("bulk scan failed");
         }
-        std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
-            return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+        lap("scan_all");
+        sortHits(hitbuf, n);
+        lap("sort hits");
         cache.bulk_all = true; cache.bulk_scan = scan_id; cache.bulk_ncl = (uint32_t)C.size();
         cache.empty.ver = 0; cache.empty.scan = scan_id; cache.empty.hb = cache.empty.he = 0; cache.empty.next = -1;
         cache.empty.lit_off = cache.empty.lit_n = 0; cache.empty.time = 0;
@@ -328,6 +360,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             cache.setSlot(c, (int32_t)cache.ent.size());
             cache.ent.push_back(e);
         }
+        lap("cache");
         host_ns_gpuwait += now_ns() - t0;
         return;
     }
@@ -349,8 +382,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
             die("scan failed");
         }
-        std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
-            return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+        sortHits(hitbuf, n);
         uint32_t h = 0;
         for (uint32_t i = 0; i < v.size(); ++i) {
             CacheEnt e; e.ver = C[v[i]].ver; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
@@ -361,6 +393,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             cache.ent.push_back(e);
         }
     }
+    lap("request scan");
     host_ns_gpuwait += now_ns() - t0;
 }
 
@@ -400,8 +433,8 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
         die("speculative scan failed");
     }
     host_ns_gpuwait += now_ns() - t0;
-    std::sort(hitbuf.begin(), hitbuf.begin() + n, [](const cp3g_hit& a, const cp3g_hit& b) {
-        return a.req != b.req ? a.req < b.req : a.clause < b.clause; });
+    if (getenv("CP3_DEBUG_PAR")) { fprintf(stderr, "  scanSpeculative gpu call %.1f ms, %zu reqs, %u hits\n", (now_ns() - t0) / 1e6, reqs.size(), n); }
+    sortHits(hitbuf, n);
     uint32_t h = 0;
     for (uint32_t i = 0; i < reqs.size(); ++i) {
         CacheEnt e; e.ver = UINT32_MAX; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
@@ -428,6 +461,7 @@ void Engine::prefetchStrengthenClosure()
     std::vector<Ev> evs;                                 // all predicted removals so far, sorted by (clause, time)
     std::unordered_set<uint64_t> requested;              // hash of (clause, content) already scanned
     size_t first_ent = 0;
+    DbgLap lap("closure");
     for (int round = 0; round < 8; ++round) {
         std::vector<uint32_t> changed;
         const size_t old_n = evs.size();
@@ -445,6 +479,7 @@ void Engine::prefetchStrengthenClosure()
         std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.clause != b.clause ? a.clause < b.clause : a.time < b.time; });
         std::sort(changed.begin(), changed.end());
         changed.erase(std::unique(changed.begin(), changed.end()), changed.end());
+        lap("evs+sorts");
         std::vector<SpecReq> reqs; spec_lits.clear();
         size_t p = 0;
         for (uint32_t d : changed) {
@@ -475,8 +510,10 @@ void Engine::prefetchStrengthenClosure()
                 reqs.push_back({d, off, nl, t});
             }
         }
+        lap("reqs");
         if (reqs.empty()) { break; }
         scanSpeculative(CP3G_STRENGTHEN, reqs, c_str);
+        lap("scanSpeculative");
     }
 }
 
@@ -956,15 +993,18 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_sub);
     const bool unlimited = !opt.limited;
+    DbgLap lap0("sub"); 
     c_sub.clear(); logClear();
+    lap0("clear");
     {
         std::vector<uint32_t> ids;
         ids.reserve(subq.size());
         for (uint32_t c : subq) { if (!(C[c].flag & F_DEL)) { ids.push_back(c); } }
-        std::sort(ids.begin(), ids.end());
-        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        sortUnique(ids);
+        lap0("ids");
         scanClauses(CP3G_SUBSUME, ids, c_sub);
     }
+    DbgLap lap("sub"); lap("start(after scan)");
     int64_t t0 = now_ns();
     static const size_t parsub_min = getenv("CP3_PARSUB_MIN") ? (size_t)atoi(getenv("CP3_PARSUB_MIN")) : 65536;
     if (!useHeap && subq.size() >= parsub_min) {
@@ -979,8 +1019,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
             const bool ov = overlap_str && !no_overlap && nthreads > 1 && opt.strength && strq.size() >= parsub_min && !hasToPropagate();
             if (ov) {
                 for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { sids.push_back(c); } }
-                std::sort(sids.begin(), sids.end());
-                sids.erase(std::unique(sids.begin(), sids.end()), sids.end());
+                sortUnique(sids);
                 static const uint32_t bulk_min2 = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
                 sbulk = sids.size() == n_live && n_live > bulk_min2;
                 flushDevice();
@@ -988,7 +1027,8 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
                 helper = std::thread([this, &sids, sbulk]() { prepareStrengthening(sids, sbulk); });
             }
             const bool done = subsumptionCommitParallel();
-            if (ov) { helper.join(); scan_no_flush = false; str_prepared = true; ++n_overlap; }
+            lap("commitParallel");
+            if (ov) { helper.join(); lap("helper join"); scan_no_flush = false; str_prepared = true; ++n_overlap; }
             if (done) {
                 for (uint32_t c : subq) { C[c].flag &= ~F_SUB; }
                 host_ns_commit += now_ns() - t0;
@@ -1058,6 +1098,7 @@ void Engine::updateOccurrences(bool useHeap, int ignore)
 void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos)
 {
     ++removedLiterals;
+    if (static_lazy && lazyPending(other)) { C[other].flag |= F_STR; }      // still waiting in the queue
     if (!(C[other].flag & F_SUB)) { C[other].flag |= F_SUB; subq.push_back(other); }
     if (!(C[other].flag & F_STR)) { localQueue.push_back(other); C[other].flag |= F_STR; }
     successful(t_sub);
@@ -1108,7 +1149,7 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
 void Engine::restoreOneList(int x)
 {
     const int32_t i = pre_index[x];
-    if (i < 0 || scanned_dyn[x]) { return; }
+    if (i < 0 || scanned_dyn[x] || (static_lazy && last_static_walk[x] > (int64_t)cur_end)) { return; }
     const PreList& pl = pre_lists[i];
     memcpy(occ_pool.data() + occ[x].off, pre_snap.data() + pl.snap_off, sizeof(uint32_t) * pl.old_n);
     hot[x].n = pl.old_n;
@@ -1124,6 +1165,22 @@ void Engine::rollbackPrecompact()
     if (!pre_active) { return; }
     for (const PreList& pl : pre_lists) { restoreOneList(pl.lit); }
     pre_active = false;
+}
+bool Engine::lazyPending(uint32_t c) const
+{
+    if (c >= qtime.size() || qtime[c] < 0) { return false; }
+    const size_t pos = static_nq - 1 - (size_t)qtime[c];
+    return pos < cur_end && pos < contrib.size() && contrib[pos] >= 0;
+}
+// The lazy static plan stops here: inert entries that still wait get their flag back, the lists walked by the
+// ones already passed are marked as walked.  From here on the pass runs entry by entry.
+void Engine::leaveLazy()
+{
+    if (!static_lazy) { return; }
+    static_lazy = false;
+    const size_t nq = static_nq, ce = std::min(cur_end + 1, nq);
+    parallelFor(ce, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { C[strq[p]].flag |= F_STR; } } });
+    if (pre_active) { for (size_t p = ce; p < nq; ++p) { if (contrib[p] >= 0 && walk_min[p] >= 0) { scanned_dyn[walk_min[p]] = 1; scanned_dyn[walk_min[p] ^ 1] = 1; } } }
 }
 // The static plan assumed that clause c keeps its content until its turn (it was nobody's predicted target).
 // A hit that the speculative closure did not predict just changed it: c is no longer inert, and the lists it
@@ -1145,14 +1202,23 @@ void Engine::unpredictedEdit(uint32_t c)
 // K4 over the strengthening queue + speculative closure (first half of a strengthening pass)
 void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
 {
+    DbgLap lap("prepStr");
     c_str.clear();
+    lap("clear");
     scanClauses(CP3G_STRENGTHEN, ids, c_str, scan_no_flush ? (bulk ? 1 : 0) : -1);
+    lap("scan");
     // processing time of the queue entries: the queue is drained from the back
     if (qtime.size() < C.size()) { qtime.resize(C.size() + 1024, -1); }
-    for (size_t i = 0; i < strq.size(); ++i) { qtime[strq[i]] = (int32_t)(strq.size() - 1 - i); }
+    // (a clause queued twice keeps the time of its last entry, like the sequential fill)
+    { bool inc = true; for (size_t i = 1; i < strq.size(); ++i) { if (strq[i - 1] >= strq[i]) { inc = false; break; } }
+      const size_t nq = strq.size();
+      if (inc) { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } }); }
+      else { for (size_t i = 0; i < nq; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } } }
     for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
     for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
+    lap("qtime");
     prefetchStrengthenClosure();
+    lap("closure");
 }
 
 // strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
@@ -1168,10 +1234,10 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
             ids.push_back(c);
         }
-        std::sort(ids.begin(), ids.end());
-        ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+        sortUnique(ids);
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
+    DbgLap lap("str"); lap("prepare");
     int64_t t0 = now_ns();
     // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
     // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
@@ -1209,6 +1275,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             bound[t] = bs;
         });
         int64_t total_bound = 0; for (int64_t x : bound) { total_bound += x; }
+        lap("static1");
         // (2) the first walk of a list removes its deleted entries by swap-with-last (Subsumption.cc:1332-1335,
         //     1432-1435); the resulting order depends only on the list and on which entries are deleted, and no
         //     clause dies during this pass unless a unit shows up.  So the certainly-walked lists are cleaned
@@ -1241,7 +1308,14 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 for (size_t i = 0; i < pre_lists.size(); ++i) { pre_index[pre_lists[i].lit] = (int32_t)i; }
             }
         }
-        // (3) step contribution of the inert entries
+        lap("precompact");
+        // (3) step contribution of the inert entries.  Far from the step limit their whole effect is applied here
+        //     (flag cleared, walked lists recorded) and the ordered walk below only adds the number up.
+        static const bool no_lazy = getenv("CP3_NO_LAZY") != nullptr;
+        const bool lazy = !no_lazy && (unlimited || str_steps + 2 * total_bound < str_lim);
+        static_lazy = lazy; n_lazy = 0; cur_end = nq;
+        if (lazy) { last_static_walk.assign((size_t)2 * nvars, -1); }
+        auto amax = [](int32_t* a, int32_t v) { int32_t o = __atomic_load_n(a, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(a, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} };
         parallelFor(nq, [&](size_t b, size_t e, int) {
             for (size_t p2 = b; p2 < e; ++p2) {
                 const uint32_t c = strq[p2];
@@ -1254,16 +1328,25 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 const int mn = minT, nm = minT ^ 1;
                 if (hasStale(mn) || hasStale(nm)) { continue; }
                 contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
+                if (lazy) { C[c].flag &= ~F_STR; amax(&last_static_walk[mn], (int32_t)p2); amax(&last_static_walk[nm], (int32_t)p2); }
             }
         });
     }
+    lap("contrib");
     std::vector<uint32_t> localQueue;
     size_t end = strq.size();
     int ret = L_UNDEF; bool early = false;
     for (; end > 0 && (unlimited || str_steps < str_lim);) {
         uint32_t cr;
         if (localQueue.empty()) {
-            --end; cr = strq[end];
+            --end; cur_end = end;
+            if (static_lazy) {
+                if (contrib[end] >= 0) {
+                    if (!hasToPropagate()) { str_steps += contrib[end]; ++n_lazy; continue; }
+                    leaveLazy();
+                }
+            }
+            cr = strq[end];
             if (static_valid && contrib[end] >= 0 && !hasToPropagate() && (unlimited || str_steps + contrib[end] < str_lim)) {
                 str_steps += contrib[end];
                 C[cr].flag &= ~F_STR;
@@ -1288,7 +1371,9 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         { const int32_t* s = CL(cr); minT = s[0];
           for (uint32_t j = 1; j < C[cr].size; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
         const int min = minT, nmin = lneg(minT);
+        const int64_t th0 = lap.on ? now_ns() : 0;
         const CacheEnt* e = strHits(cr);
+        if (lap.on) { dbg_hits_ns += now_ns() - th0; }
         if (e->hb == e->he && !hasStale(min) && !hasStale(nmin) && !hasToPropagate() &&
             (unlimited || str_steps + (int64_t)hot[min].n + (int64_t)hot[nmin].n < str_lim)) {
             // no candidate can hit and no list needs lazy cleaning: only the step counters move
@@ -1299,6 +1384,8 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             continue;
         }
         ++n_slow;
+        const int64_t ts0 = lap.on ? now_ns() : 0;
+        struct SlowT { int64_t t0; int64_t* acc; bool on; ~SlowT() { if (on) { *acc += now_ns() - t0; } } } slowt{ts0, &dbg_slow_ns, lap.on};
         if (pre_active) { scanned_dyn[min] = 1; }
         // pass 1: occ(min) - the complementary literal is any literal but min
         {
@@ -1320,6 +1407,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             }
         }
         if (hasToPropagate()) {
+            leaveLazy();
             static_valid = false;            // counts and lists move now: the precomputed entries are void
             rollbackPrecompact();
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
@@ -1343,6 +1431,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             }
         }
         if (hasToPropagate()) {
+            leaveLazy();
             static_valid = false;
             rollbackPrecompact();
             if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
@@ -1350,12 +1439,16 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         C[cr].flag &= ~F_STR;
     }
+    lap("ordered");
+    if (lap.on) { fprintf(stderr, "  str slow entries %.1f ms, strHits %.1f ms\n", dbg_slow_ns / 1e6, dbg_hits_ns / 1e6); dbg_slow_ns = 0; dbg_hits_ns = 0; }
     if (!early) {
         updateOccurrences(useHeap, ignore);
         ret = ok ? L_UNDEF : L_FALSE;
     }
+    lap("updateOcc");
     for (uint32_t c : strq) { if (c < qtime.size()) { qtime[c] = -1; } }
-    static_pass = false;
+    if (lap.on) { fprintf(stderr, "  str lazy entries %lld, lazy still on %d\n", (long long)n_lazy, (int)static_lazy); }
+    static_pass = false; static_lazy = false; n_fast += n_lazy; n_static += n_lazy; n_lazy = 0;
     if (getenv("CP3_DEBUG_PRE")) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }
     pre_active = false;
     host_ns_commit += now_ns() - t0;
@@ -1878,7 +1971,9 @@ void Engine::initData()
         hot[x].cnt = (int32_t)hot[x].n;
     }
     ph_download += now_ns() - ti0;
+    DbgLap lap("init"); 
     size_t kept = 0;
+    subq.reserve(clauses.size()); strq.reserve(clauses.size());
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i];
         if (C[c].flag & F_DEL) { continue; }
@@ -1887,6 +1982,7 @@ void Engine::initData()
         clauses[kept++] = c;
     }
     clauses.resize(kept);
+    lap("initClause loop");
     data_ready = true;
 }
 

@@ -167,6 +167,12 @@ private:
     std::vector<PreList> pre_lists; std::vector<uint32_t> pre_snap; std::vector<uint8_t> scanned_dyn;
     std::vector<int32_t> pre_index, walk_min; std::vector<uint32_t> walk_count;   // per literal / per queue position
     bool pre_active = false, static_pass = false; size_t static_nq = 0;
+    // lazy form of the static plan: the inert entries' F_STR flags are cleared up front (in parallel) and the ordered
+    // walk only adds their step contribution; cur_end = queue position being processed (everything above is done)
+    bool static_lazy = false; size_t cur_end = 0; int64_t n_lazy = 0;
+    std::vector<int32_t> last_static_walk;           // per literal: highest queue position of an inert entry that walks its list
+    void leaveLazy();                                // make the deferred state explicit (a unit is about to be propagated)
+    bool lazyPending(uint32_t c) const;              // inert entry whose turn has not come yet (its flag is logically still set)
     void rollbackPrecompact();
     void restoreOneList(int x);
     void unpredictedEdit(uint32_t c);               // a clause the static plan relied on was modified
@@ -188,7 +194,7 @@ private:
     inline PairEnt* pairLookup(int v) { return (v < (int)pc_slot.size() && pc_slot[v] >= 0) ? &pc_ent[pc_slot[v]] : nullptr; }
     std::vector<int> scratch_col;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
-    int64_t host_ns_commit = 0, host_ns_gpuwait = 0;
+    int64_t host_ns_commit = 0, host_ns_gpuwait = 0, dbg_slow_ns = 0, dbg_hits_ns = 0;
     int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0, ph_upload = 0, ph_download = 0, ph_simplify = 0;
 
     // ---------------- basics

@@ -15,6 +15,7 @@
 //   k_bve_pairs   K5  resolvent size per (pos,neg) pair (BVE.h:248-299)
 //   k_bve_resolve K6  resolvent generation (BVE.h:208-242)
 #include <cuda_runtime.h>
+#include <cub/device/device_merge_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -489,18 +490,30 @@ __global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ h
         __syncwarp();
     };
 
-    for (uint32_t tile = first + gwarp * 32; tile < last; tile += nwarps * 32) {
+    // software pipeline: the entry, its literal and the tag ranges of the NEXT tile are loaded before the current
+    // tile is processed, so the DRAM round trips of consecutive tiles overlap the filter loops
+    OccEnt en_n; en_n.ref = 0; en_n.szfl = 0; en_n.sig = 0; int32_t l_n = 0; uint32_t tb_n[2] = {0, 0}, te_n[2] = {0, 0};
+    auto fetch = [&](uint32_t tile) {
         const uint32_t j = tile + lane;
         if (j < last) {
-            const OccEnt en = occ_ent[j];
-            const int32_t l = (int32_t)ent_lit[j];
+            en_n = occ_ent[j]; l_n = (int32_t)ent_lit[j];
+            tb_n[0] = toff[l_n]; te_n[0] = toff[l_n + 1];
+            if (KIND == CP3G_STRENGTHEN) { tb_n[1] = toff[l_n ^ 1]; te_n[1] = toff[(l_n ^ 1) + 1]; }
+        }
+    };
+    if (first + gwarp * 32 < last) { fetch(first + gwarp * 32); }
+    for (uint32_t tile = first + gwarp * 32; tile < last; tile += nwarps * 32) {
+        const uint32_t j = tile + lane;
+        const OccEnt en = en_n; const int32_t l = l_n;
+        const uint32_t tb0 = tb_n[0], te0 = te_n[0], tb1 = tb_n[1], te1 = te_n[1];
+        if (tile + nwarps * 32 < last) { fetch(tile + nwarps * 32); }
+        if (j < last) {
             const uint32_t esz = en.szfl & SIZE_MASK;
             const bool ddel = (delbits[en.ref >> 5] >> (en.ref & 31)) & 1u;
             const unsigned long long dvar = var_fold(en.sig);
             const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
             for (int pass = 0; pass < npass; ++pass) {
-                const int32_t lx = pass == 0 ? l : (l ^ 1);         // the literal the strengthener is filed under
-                const uint32_t b = toff[lx], e = toff[lx + 1];
+                const uint32_t b = pass == 0 ? tb0 : tb1, e = pass == 0 ? te0 : te1;
                 for (uint32_t k = b; k < e; ++k) {
                     const OccEnt s = tag[k];
                     if (s.ref == en.ref) { continue; }
@@ -664,6 +677,7 @@ struct cp3g {
     DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
     DevBuf<OccEnt> occ_ent, tag_sub, tag_str; DevBuf<int2> tagx; DevBuf<uint32_t> ent_lit, delbits, refs_tmp, toff_sub, toff_str, tcnt_sub, tcnt_str; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
+    DevBuf<unsigned char> sort_tmp;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
     DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
     std::vector<uint32_t> ovf_host;
@@ -700,6 +714,21 @@ struct KTimer {
     int64_t collect() { float ms = 0; if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) { g->kernel_ns += (int64_t)(ms * 1e6); return (int64_t)(ms * 1e6); } return 0; }
 };
 
+// Hits leave the scan kernels in warp-completion order; the host commit consumes them grouped by request and
+// ordered by clause index (duplicate ties are decided by index), so they are sorted on the device before the copy.
+struct HitLess { __device__ bool operator()(const cp3g_hit& a, const cp3g_hit& b) const { return a.req != b.req ? a.req < b.req : a.clause < b.clause; } };
+static int sort_hits(cp3g* g, uint32_t n)
+{
+    size_t bytes = 0;
+    if (cub::DeviceMergeSort::SortKeys(nullptr, bytes, g->hits.p, (int)n, HitLess(), g->stream) != cudaSuccess) { g->fail("cub sort size", cudaGetLastError()); return CP3G_ERR_CUDA; }
+    RESERVE(g->sort_tmp, bytes + 16, false);
+    cudaError_t e = cub::DeviceMergeSort::SortKeys(g->sort_tmp.p, bytes, g->hits.p, (int)n, HitLess(), g->stream);
+    if (e != cudaSuccess) { g->fail("cub sort", e); return CP3G_ERR_CUDA; }
+    g->launches += 2;
+    return CP3G_OK;
+}
+static constexpr uint32_t SORT_ON_DEVICE_MIN = 2048;
+
 extern "C" {
 
 int cp3g_device_count(void)
@@ -734,7 +763,7 @@ void cp3g_destroy(cp3g* g)
     cudaStreamSynchronize(g->stream);
     g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
     g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release(); g->delbits.release(); g->refs_tmp.release(); g->tag_sub.release(); g->tag_str.release(); g->tagx.release(); g->toff_sub.release(); g->toff_str.release(); g->tcnt_sub.release(); g->tcnt_str.release();
-    g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
+    g->sort_tmp.release(); g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
     cp3g_nccl_free(g->nccl);
@@ -1018,6 +1047,11 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
     if (g->world > 1) {
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
         if (rr != CP3G_OK) { return rr; }
+    } else if (n >= SORT_ON_DEVICE_MIN) {
+        int rr = sort_hits(g, n);
+        if (rr != CP3G_OK) { return rr; }
+        CK(cudaMemcpyAsync(out, g->hits.p, (size_t)n * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
     } else if (n) {
         memcpy(out, g->pin_hits, (size_t)std::min(n, spec) * sizeof(cp3g_hit));
         if (n > spec) {
@@ -1036,9 +1070,15 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     if (!g) { return CP3G_ERR_NODEVICE; }
     if (nout) { *nout = 0; }
     cudaSetDevice(g->device);
+    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr;
+    auto tnow = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double td0 = dbg ? tnow() : 0;
+    auto dlap = [&](const char* w) { if (dbg) { double t2 = tnow(); fprintf(stderr, "    scan_all %s %.2f ms\n", w, t2 - td0); td0 = t2; } };
     if (g->dirty_since_build || !g->ovf_host.empty()) { int r = cp3g_build(g); if (r != CP3G_OK) { return r; } }
+    dlap("build");
     if (!g->total_occ) { if (checks) { *checks = 0; } return CP3G_OK; }
     RESERVE(g->hits, (size_t)cap + 1, false);
+    dlap("reserve hits");
     CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
     unsigned long long* dchecks = (unsigned long long*)(g->counters.p + 4);
     // multi-GPU: contiguous slice of the entry array per rank
@@ -1070,14 +1110,18 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     uint32_t n = cnt[0];
     uint64_t chk, ab; memcpy(&chk, &cnt[4], 8); memcpy(&ab, &cnt[6], 8);
     g->scan_requests += g->ncl; g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
+    dlap("kernel+sync");
     if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }
     if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
     if (g->world > 1) {
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
         if (rr != CP3G_OK) { return rr; }
     } else if (n) {
+        if (n >= SORT_ON_DEVICE_MIN) { int rr = sort_hits(g, n); if (rr != CP3G_OK) { return rr; } }
+        if (dbg) { cudaStreamSynchronize(g->stream); } dlap("sort");
         CK(cudaMemcpyAsync(out, g->hits.p, (size_t)n * sizeof(cp3g_hit), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
+        dlap("copy");
     }
     g->d2h += (int64_t)n * (int64_t)sizeof(cp3g_hit) + 32;
     if (nout) { *nout = n; }
