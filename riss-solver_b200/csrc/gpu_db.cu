@@ -3,8 +3,13 @@
 // HBM layout (DESIGN.md "data layout"):
 //   lits[]     int32 literal pool, clause i = lits[hdr[i].start .. +size), sorted by literal code 2*var+sign
 //   hdr[]      16-byte clause header {start:u32, size:24|flags:8, sig:u64}  - one 128-bit load per candidate
-//   occ_off[]  u32 CSR offsets per literal code (2*nvars+1), occ_ent[] 16-byte entries {ref,size|flags,sig}
-//              in ascending clause index (= CoprocessorData::addClause order, CoprocessorTypes.h:812-833)
+//   occ_off[]  u32 CSR offsets per literal code (2*nvars+1), occ_ent[] 16-byte entries {class:2|ref:30, size, sig}.
+//              Inside a list the entries are ordered by (class, clause index): the clauses whose full-queue scan
+//              walks THIS list ("tagged" for subsumption and/or strengthening) come first, so the list carries its
+//              own subsumer set as a prefix.  cp3g_download_occ returns plain ascending clause index
+//              (= CoprocessorData::addClause order, CoprocessorTypes.h:812-833)
+//   tiles[]    {first entry | aligned flag, first literal} per 128-entry tile of the entry array, rounded down to
+//              the start of the variable's list pair when that pair is short (full-queue kernels stage whole lists)
 //   ovf[]      clause indices appended after the last CSR build (BVE resolvents); scanned by every request
 //
 // Kernels (none uses tensor cores - there is no contraction on this path):
@@ -33,6 +38,11 @@
 static constexpr uint32_t FLAG_DEL = 0x80000000u;
 static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
+// occurrence entry: top two bits of `ref` = class of the clause in this list (see k_occ_fill)
+static constexpr uint32_t REF_MASK = 0x3fffffffu;
+static constexpr uint32_t CLS_NOSUB = 2u, CLS_NOSTR = 1u, CLS_NONE = 3u;
+// full-queue kernel tiling
+static constexpr uint32_t TILE = 128, GROUP_MAX = 32, TCAP = TILE + GROUP_MAX, OFFCAP = 128, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
 
 struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
@@ -62,15 +72,18 @@ __global__ void k_sig_build(ClauseHdr* __restrict__ hdr, const int32_t* __restri
 }
 
 // ------------------------------------------------------------------------------------------ K2
-__global__ void k_occ_count(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+__global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
                             uint32_t* __restrict__ cnt)
 {
+    // histogram of the literal occurrences; the same pass over the literals refreshes the clause signature (K1)
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
     const ClauseHdr h = hdr[i];
-    if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
-    for (uint32_t k = 0; k < sz; ++k) { atomicAdd(&cnt[lits[h.start + k]], 1u); }
+    unsigned long long s = 0;
+    const bool live = !(h.szfl & FLAG_DEL);
+    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = lits[h.start + k]; s |= lit_bit(x); if (live) { atomicAdd(&cnt[x], 1u); } }
+    if (s != h.sig) { hdr[i].sig = s; }
 }
 
 // exclusive scan, three small kernels (tile = 1024 threads x 4 items)
@@ -137,6 +150,12 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
 // Scatter only the 4-byte clause index: the refs of a list (avg 6.4 x 4 B) share one 32-byte sector and the whole
 // array (55 MB at C2) stays L2 resident, whereas scattering the 16-byte entries costs a DRAM read-modify-write per
 // partial sector (0.98 ms at C2, profiles/r01b).  The entries are written afterwards by k_occ_expand, coalesced.
+//
+// The two top bits of the scattered word carry the CLASS of clause i in that list.  A full-queue scan walks, for
+// clause i, the shortest list among its literals (subsumption, Subsumption.cc:244-256) resp. the shortest list pair
+// occ(x)+occ(~x) (strengthening, Subsumption.cc:1292-1299); i is "tagged" in exactly that list.  class = 0 tagged
+// for both, 1 subsumption only, 2 strengthening only, 3 not tagged; the per-list sort on the whole word then puts
+// the tagged clauses first, so every list carries the set of clauses that scan it as a prefix.
 __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
                            const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ refs)
 {
@@ -145,9 +164,18 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
     const ClauseHdr h = hdr[i];
     if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
+    uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = -1, xt = -1;
     for (uint32_t k = 0; k < sz; ++k) {
         const int32_t x = lits[h.start + k];
-        refs[off[x] + atomicAdd(&cursor[x], 1u)] = i;
+        const uint32_t len = off[x + 1] - off[x];
+        const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
+        if (len < bs) { bs = len; xs = x; }
+        if (both < bt) { bt = both; xt = x; }
+    }
+    for (uint32_t k = 0; k < sz; ++k) {
+        const int32_t x = lits[h.start + k];
+        const uint32_t cls = (x == xs ? 0u : CLS_NOSUB) | (x == xt ? 0u : CLS_NOSTR);
+        refs[off[x] + atomicAdd(&cursor[x], 1u)] = i | (cls << 30);
     }
 }
 // one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced
@@ -156,51 +184,35 @@ __global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* 
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) { return; }
     const uint32_t r = refs[i];
-    const ClauseHdr h = hdr[r];
+    const ClauseHdr h = hdr[r & REF_MASK];
     OccEnt e; e.ref = r; e.szfl = h.szfl & SIZE_MASK; e.sig = h.sig;
     ent[i] = e;
 }
-// The "tagged" CSR of the candidate-major bulk kernels: clause c is filed under the literal whose list a bulk
-// scan walks for it (xs for subsumption, xt for strengthening).  phase 0 counts, phase 1 fills.
-__global__ void k_tag(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                      const uint32_t* __restrict__ off, int phase, int2* __restrict__ tagx,
-                      uint32_t* __restrict__ cnt_sub, uint32_t* __restrict__ cnt_str,
-                      const uint32_t* __restrict__ toff_sub, const uint32_t* __restrict__ toff_str,
-                      OccEnt* __restrict__ tag_sub, OccEnt* __restrict__ tag_str)
+// Tile table of the full-queue kernels.  Tile t nominally starts at entry 128*t; the start is moved down to the
+// first entry of the variable's list pair (occ(2v), occ(2v+1)) when that pair is short, so that a tile consists
+// of whole list pairs (flag TILE_ALIGNED) and fits the shared-memory staging area.  Long lists keep the
+// nominal cut and are processed from global memory.
+__global__ void k_tiles(const uint32_t* __restrict__ off, uint32_t nlit, uint32_t total, uint32_t ntiles, uint2* __restrict__ tiles)
 {
-    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) { return; }
-    const ClauseHdr h = hdr[c];
-    if (h.szfl & FLAG_DEL) { return; }
-    const uint32_t sz = h.szfl & SIZE_MASK;
-    if (sz == 0) { return; }
-    if (phase == 0) {
-        uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = 0, xt = 0;
-        for (uint32_t k = 0; k < sz; ++k) {
-            const int32_t x = lits[h.start + k];
-            const uint32_t len = off[x + 1] - off[x];
-            const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
-            if (len < bs) { bs = len; xs = x; }
-            if (both < bt) { bt = both; xt = x; }
-        }
-        tagx[c] = make_int2(xs, xt);
-        atomicAdd(&cnt_sub[xs], 1u); atomicAdd(&cnt_str[xt], 1u);
-    } else {
-        const int2 x = tagx[c];
-        OccEnt e; e.ref = c; e.szfl = sz; e.sig = h.sig;
-        tag_sub[toff_sub[x.x] + atomicAdd(&cnt_sub[x.x], 1u)] = e;
-        tag_str[toff_str[x.y] + atomicAdd(&cnt_str[x.y], 1u)] = e;
-    }
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > ntiles) { return; }
+    const unsigned long long j64 = (unsigned long long)t * TILE;
+    if (t == ntiles || j64 >= total) { tiles[t] = make_uint2(total | TILE_ALIGNED, nlit); return; }
+    const uint32_t j = (uint32_t)j64;
+    uint32_t lo = 0, hi = nlit;                    // last x with off[x] <= j  (off[nlit] = total > j)
+    while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (off[mid] <= j) { lo = mid; } else { hi = mid; } }
+    const uint32_t x = lo, g = x & ~1u;
+    const uint32_t gs = off[g], ge = off[g + 2];
+    tiles[t] = (ge - gs <= GROUP_MAX) ? make_uint2(gs | TILE_ALIGNED, g) : make_uint2(j, x);
 }
-// scatter order is nondeterministic; the reference order is ascending clause index -> sort every list.
-// The same pass writes the literal of each entry (constant per list).
+// scatter order is nondeterministic; every list is sorted by (class, clause index) - the scattered word itself.
 __global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, uint32_t* __restrict__ refs,
-                                 uint32_t* __restrict__ ent_lit, uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
+                                 uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
 {
     uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= nlit) { return; }
     const uint32_t b = off[x], e = off[x + 1], len = e - b;
-    if (len == 0) { return; }
+    if (len < 2) { return; }
     if (len > SHORT_LIST) { long_lits[atomicAdd(nlong, 1u)] = x; return; }
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t key = refs[i];
@@ -208,18 +220,16 @@ __global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit
         while (j > b && refs[j - 1] > key) { refs[j] = refs[j - 1]; --j; }
         refs[j] = key;
     }
-    for (uint32_t i = b; i < e; ++i) { ent_lit[i] = x; }
 }
 // one block per long list: normalised bitonic sort in global memory.  Every compare-exchange is ascending
 // (i < l keeps the smaller ref at i), so the virtual +inf padding above len never has to move and pairs that
 // touch it are simply skipped.
 __global__ void k_occ_sort_long(const uint32_t* __restrict__ off, const uint32_t* __restrict__ long_lits,
-                                uint32_t* __restrict__ refs, uint32_t* __restrict__ ent_lit)
+                                uint32_t* __restrict__ refs)
 {
     const uint32_t x = long_lits[blockIdx.x];
     uint32_t* a = refs + off[x];
     const uint32_t len = off[x + 1] - off[x];
-    for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) { ent_lit[off[x] + i] = x; }
     uint32_t p2 = 1; while (p2 < len) { p2 <<= 1; }
     for (uint32_t k = 2; k <= p2; k <<= 1) {
         for (uint32_t i = threadIdx.x; i < len; i += blockDim.x) {
@@ -381,7 +391,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
     {
         const uint32_t b = occ_off[x], e = occ_off[x + 1];
         for (uint32_t i = b + lane; i < e; i += 32) {
-            const OccEnt en = occ_ent[i];
+            OccEnt en = occ_ent[i]; en.ref &= REF_MASK;
             if (en.ref != me) { nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK); }
             // a stale entry could flip on x itself; that hit belongs to the occ(~x) pass below
             test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, -1, x ^ 1, hdr, lits, r, sink);
@@ -391,7 +401,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
         const int32_t nx = x ^ 1;
         const uint32_t b = occ_off[nx], e = occ_off[nx + 1];
         for (uint32_t i = b + lane; i < e; i += 32) {
-            const OccEnt en = occ_ent[i];
+            OccEnt en = occ_ent[i]; en.ref &= REF_MASK;
             nchk += 1; nbytes += 12 + 4 * (en.szfl & SIZE_MASK);
             test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, sink);
         }
@@ -412,53 +422,75 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
     sink.flush(&sink_base);
 }
 
-// ------------------------------------------------------------------------------------------ K3 / K4 bulk
-// Full-queue pass (every live clause is a subsumer / strengthener).
-// rare path of k_bulk: the 16-byte entry of the candidate passed size + signature filters
-template <int KIND>
-__device__ __forceinline__ void bulk_candidate_inl(uint32_t sref, uint32_t dref, int32_t need_flip, int32_t forbid_flip,
-                                            const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
-                                            const HitSink& sink)
+// ------------------------------------------------------------------------------------------ K3 / K4 full queue
+// mbarrier + bulk-copy (TMA engine, UBLKCP) helpers: one elected lane moves a contiguous tile global -> shared
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, uint32_t count)
 {
-    const ClauseHdr hs = hdr[sref], hd = hdr[dref];
-    if ((hs.szfl | hd.szfl) & FLAG_DEL) { return; }
-    const uint32_t sn = hs.szfl & SIZE_MASK, dn = hd.szfl & SIZE_MASK;
-    if (dn < sn) { return; }
-    const int32_t* S = lits + hs.start; const int32_t* D = lits + hd.start;
-    if (KIND == CP3G_SUBSUME) {
-        if (merge_subset(S, sn, D, dn)) { sink.emit(sref, dref, -1); }
-    } else {
-        const int32_t f = merge_one_flip(S, sn, D, dn);
-        if (f >= 0 && (need_flip < 0 || f == need_flip) && f != forbid_flip) { sink.emit(sref, dref, f); }
-    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(b)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* b)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    } while (!ok);
 }
 
-// Candidate-major form of the full-queue pass: one lane per occurrence entry *as the candidate*.  The lane
-// streams its own 16-byte entry (perfectly coalesced) and tests it against the few clauses that are filed
-// under this literal in the tagged CSR, i.e. the subsumers / strengtheners whose bulk scan walks this list.
-// Warps are persistent and fully independent (no block barrier inside the loop - a barrier per tile cost 38 %
-// of the cycles, profiles/r01b): every warp owns a candidate queue and a hit buffer in shared memory.
-//   phase 1  signature/size filter on the 16-byte records; survivors go to the warp's queue
+// Full-queue pass (every live clause is a subsumer / strengthener), candidate-major: one lane per occurrence entry
+// *as the candidate* D.  The clauses whose full-queue scan walks list x are exactly the entries of x with the
+// matching class bit clear (k_occ_fill), and they sit at the front of the list - so the subsumer set of a candidate
+// is a prefix of its own list and, for a short list, lies in the same tile.
+//
+// Warps are persistent and fully independent (no block barrier in the loop).  Each warp owns a double-buffered
+// staging area: the tile (<= 159 entries x 16 B, whole list pairs, k_tiles) and the CSR offsets of its lists are
+// moved global -> shared by the bulk-copy engine (cp.async.bulk + mbarrier) one tile ahead of the processing.
+//   phase 1  every lane takes entries p = lane, lane+32, ..: finds its list (binary search in the staged offsets),
+//            tests the tagged prefix (from shared memory) with size + signature filters; survivors are queued
 //   phase 2  the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
 //            which would otherwise stall 31 lanes behind one)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
-static constexpr int WQ_CAP = 64, WH_CAP = 32;
-template <int KIND>
-__global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
-        const OccEnt* __restrict__ occ_ent, const uint32_t* __restrict__ ent_lit, const uint32_t* __restrict__ delbits,
-        const uint32_t* __restrict__ toff, const OccEnt* __restrict__ tag,
-        uint32_t first, uint32_t last, cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
-        unsigned long long* __restrict__ checks)
+static constexpr int WQ_CAP = 64, WH_CAP = 32, FQ_WARPS = 4;
+struct TileDesc { uint32_t s, n, x0, xe, xa, noff; };
+__device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
 {
-    __shared__ unsigned long long sh_chk[8], sh_byt[8];
-    __shared__ uint32_t q_s[8][WQ_CAP], q_d[8][WQ_CAP]; __shared__ int32_t q_l[8][WQ_CAP];
-    __shared__ cp3g_hit h_buf[8][WH_CAP];
-    __shared__ uint32_t q_n[8], h_n[8];
+    TileDesc d;
+    d.s = a.x & ~TILE_ALIGNED; d.n = (b.x & ~TILE_ALIGNED) - d.s; d.x0 = a.y;
+    d.xe = (b.x & TILE_ALIGNED) ? b.y : b.y + 1;                       // occ_off[xe] >= end of the tile
+    d.xa = d.x0 & ~3u;                                                   // 16-byte aligned source for the bulk copy
+    const uint32_t cnt = (d.xe - d.xa + 1 + 3) & ~3u;
+    d.noff = cnt <= OFFCAP ? cnt : 0u;                                   // 0: too many (empty) lists, offsets stay global
+    return d;
+}
+template <int KIND>
+__global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+        const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent, const uint2* __restrict__ tiles,
+        const uint32_t* __restrict__ delbits, uint32_t tile_first, uint32_t tile_last,
+        cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout, unsigned long long* __restrict__ checks)
+{
+    __shared__ __align__(16) OccEnt e_s[FQ_WARPS][2][TCAP];
+    __shared__ __align__(16) uint32_t o_s[FQ_WARPS][2][OFFCAP];
+    __shared__ __align__(8) unsigned long long bar[FQ_WARPS][2];
+    __shared__ unsigned long long sh_chk[FQ_WARPS], sh_byt[FQ_WARPS];
+    __shared__ uint32_t q_s[FQ_WARPS][WQ_CAP], q_d[FQ_WARPS][WQ_CAP]; __shared__ int32_t q_l[FQ_WARPS][WQ_CAP];
+    __shared__ cp3g_hit h_buf[FQ_WARPS][WH_CAP];
+    __shared__ uint32_t q_n[FQ_WARPS], h_n[FQ_WARPS];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { q_n[w] = 0; h_n[w] = 0; }
+    if (lane == 0) { q_n[w] = 0; h_n[w] = 0; mbar_init(&bar[w][0], 1); mbar_init(&bar[w][1], 1); }
     __syncwarp();
     unsigned long long nchk = 0, nbytes = 0;
-    const uint32_t gwarp = blockIdx.x * (blockDim.x >> 5) + w, nwarps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t gwarp = blockIdx.x * FQ_WARPS + w, nwarps = gridDim.x * FQ_WARPS;
 
     auto verify = [&](uint32_t sref, uint32_t dref, int32_t l, int pass) {
         // pass 0: S holds l, any literal but ~l may be the flipped one; pass 1: S holds ~l, the flip is on l
@@ -489,55 +521,73 @@ __global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ h
         if (lane == 0) { h_n[w] = 0; }
         __syncwarp();
     };
-
-    // software pipeline: the entry, its literal and the tag ranges of the NEXT tile are loaded before the current
-    // tile is processed, so the DRAM round trips of consecutive tiles overlap the filter loops
-    OccEnt en_n; en_n.ref = 0; en_n.szfl = 0; en_n.sig = 0; int32_t l_n = 0; uint32_t tb_n[2] = {0, 0}, te_n[2] = {0, 0};
-    auto fetch = [&](uint32_t tile) {
-        const uint32_t j = tile + lane;
-        if (j < last) {
-            en_n = occ_ent[j]; l_n = (int32_t)ent_lit[j];
-            tb_n[0] = toff[l_n]; te_n[0] = toff[l_n + 1];
-            if (KIND == CP3G_STRENGTHEN) { tb_n[1] = toff[l_n ^ 1]; te_n[1] = toff[(l_n ^ 1) + 1]; }
-        }
+    auto issue = [&](const TileDesc& d, int b) {          // lane 0 only
+        const uint32_t bytes_e = d.n * (uint32_t)sizeof(OccEnt), bytes_o = d.noff * 4u;
+        mbar_expect_tx(&bar[w][b], bytes_e + bytes_o);
+        bulk_g2s(&e_s[w][b][0], occ_ent + d.s, bytes_e, &bar[w][b]);
+        if (bytes_o) { bulk_g2s(&o_s[w][b][0], occ_off + d.xa, bytes_o, &bar[w][b]); }
     };
-    if (first + gwarp * 32 < last) { fetch(first + gwarp * 32); }
-    for (uint32_t tile = first + gwarp * 32; tile < last; tile += nwarps * 32) {
-        const uint32_t j = tile + lane;
-        const OccEnt en = en_n; const int32_t l = l_n;
-        const uint32_t tb0 = tb_n[0], te0 = te_n[0], tb1 = tb_n[1], te1 = te_n[1];
-        if (tile + nwarps * 32 < last) { fetch(tile + nwarps * 32); }
-        if (j < last) {
-            const uint32_t esz = en.szfl & SIZE_MASK;
-            const bool ddel = (delbits[en.ref >> 5] >> (en.ref & 31)) & 1u;
-            const unsigned long long dvar = var_fold(en.sig);
-            const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
-            for (int pass = 0; pass < npass; ++pass) {
-                const uint32_t b = pass == 0 ? tb0 : tb1, e = pass == 0 ? te0 : te1;
-                for (uint32_t k = b; k < e; ++k) {
-                    const OccEnt s = tag[k];
-                    if (s.ref == en.ref) { continue; }
-                    nchk += 1; nbytes += 12 + 4 * esz;
-                    const uint32_t sn = s.szfl & SIZE_MASK;
-                    if (ddel || esz < sn) { continue; }
-                    const unsigned long long miss = s.sig & ~en.sig;
-                    if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                    else { if ((miss & (miss - 1)) || (var_fold(s.sig) & ~dvar)) { continue; } }
-                    if ((delbits[s.ref >> 5] >> (s.ref & 31)) & 1u) { continue; }
-                    const uint32_t q = atomicAdd(&q_n[w], 1u);
-                    if (q < (uint32_t)WQ_CAP) { q_s[w][q] = s.ref; q_d[w][q] = en.ref; q_l[w][q] = (l << 1) | pass; }
-                    else { verify(s.ref, en.ref, l, pass); }
+
+    uint32_t t = tile_first + gwarp;
+    if (t < tile_last) {
+        TileDesc cur = make_desc(tiles[t], tiles[t + 1]), nxt = cur;
+        if (t + nwarps < tile_last) { nxt = make_desc(tiles[t + nwarps], tiles[t + nwarps + 1]); }
+        if (lane == 0 && cur.n) { issue(cur, 0); }
+        uint32_t phase = 0;                                  // bit b = parity the next fill of buffer b completes
+        for (uint32_t it = 0; t < tile_last; t += nwarps, ++it) {
+            const int b = it & 1;
+            const bool more = t + nwarps < tile_last;
+            if (lane == 0 && more && nxt.n) { issue(nxt, b ^ 1); }
+            TileDesc nn = nxt;
+            if (t + 2 * nwarps < tile_last) { nn = make_desc(tiles[t + 2 * nwarps], tiles[t + 2 * nwarps + 1]); }
+            if (cur.n) {
+                mbar_wait(&bar[w][b], (phase >> b) & 1u); phase ^= 1u << b;
+                const OccEnt* es = e_s[w][b]; const uint32_t* os = o_s[w][b];
+                const uint32_t s = cur.s, n = cur.n, xa = cur.xa, noff = cur.noff;
+                auto OFF = [&](uint32_t x) -> uint32_t { return (x - xa < noff) ? os[x - xa] : occ_off[x]; };
+                auto ENT = [&](uint32_t i) -> OccEnt { return (i - s < n) ? es[i - s] : occ_ent[i]; };
+                for (uint32_t p = lane; p < n; p += 32) {
+                    const OccEnt en = es[p];
+                    const uint32_t j = s + p, dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
+                    uint32_t lo = cur.x0, hi = cur.xe;           // last x with off[x] <= j
+                    while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (OFF(mid) <= j) { lo = mid; } else { hi = mid; } }
+                    const uint32_t x = lo;
+                    const unsigned long long dvar = var_fold(en.sig);
+                    const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+                    for (int pass = 0; pass < npass; ++pass) {
+                        const uint32_t xx = pass == 0 ? x : (x ^ 1u);
+                        const uint32_t kb = OFF(xx), ke = OFF(xx + 1);
+                        for (uint32_t k = kb; k < ke; ++k) {
+                            const OccEnt sc = ENT(k);
+                            const uint32_t cls = sc.ref >> 30;
+                            if (KIND == CP3G_SUBSUME) { if (cls & CLS_NOSUB) { break; } }
+                            else { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSTR) { continue; } }
+                            const uint32_t sref = sc.ref & REF_MASK;
+                            if (sref == dref) { continue; }
+                            nchk += 1; nbytes += 12 + 4 * esz;
+                            const uint32_t sn = sc.szfl & SIZE_MASK;
+                            if (esz < sn) { continue; }
+                            const unsigned long long miss = sc.sig & ~en.sig;
+                            if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
+                            else { if ((miss & (miss - 1)) || (var_fold(sc.sig) & ~dvar)) { continue; } }
+                            if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { continue; }
+                            const uint32_t q = atomicAdd(&q_n[w], 1u);
+                            if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | (uint32_t)pass); }
+                            else { verify(sref, dref, (int32_t)x, pass); }
+                        }
+                    }
                 }
             }
-        }
-        __syncwarp();
-        const uint32_t qn = min(q_n[w], (uint32_t)WQ_CAP);
-        if (qn >= 16u || tile + nwarps * 32 >= last) {            // verify when the queue is worth a full warp pass
-            for (uint32_t k = lane; k < qn; k += 32) { verify(q_s[w][k], q_d[w][k], q_l[w][k] >> 1, q_l[w][k] & 1); }
-            __syncwarp();
-            if (lane == 0) { q_n[w] = 0; }
-            __syncwarp();
-            if (h_n[w] >= (uint32_t)(WH_CAP / 2)) { flush_hits(); }
+            __syncwarp();                                  // all reads of buffer b are done before it is refilled
+            const uint32_t qn = min(q_n[w], (uint32_t)WQ_CAP);
+            if (qn >= 16u || !more) {                      // verify when the queue is worth a full warp pass
+                for (uint32_t k = lane; k < qn; k += 32) { verify(q_s[w][k], q_d[w][k], q_l[w][k] >> 1, q_l[w][k] & 1); }
+                __syncwarp();
+                if (lane == 0) { q_n[w] = 0; }
+                __syncwarp();
+                if (h_n[w] >= (uint32_t)(WH_CAP / 2)) { flush_hits(); }
+            }
+            cur = nxt; nxt = nn;
         }
     }
     flush_hits();
@@ -547,7 +597,7 @@ __global__ void __launch_bounds__(256) k_bulk_cm(const ClauseHdr* __restrict__ h
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long a = 0, b2 = 0;
-        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a += sh_chk[k]; b2 += sh_byt[k]; }
+        for (int k = 0; k < FQ_WARPS; ++k) { a += sh_chk[k]; b2 += sh_byt[k]; }
         if (a) { atomicAdd(checks, a); atomicAdd(checks + 1, b2); }
     }
 }
@@ -650,7 +700,7 @@ __global__ void k_make_hdr(const uint4* __restrict__ rec, ClauseHdr* __restrict_
 __global__ void k_gather_refs(const OccEnt* __restrict__ ent, uint32_t* __restrict__ refs, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { refs[i] = ent[i].ref; }
+    if (i < n) { refs[i] = ent[i].ref & REF_MASK; }
 }
 __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits, const uint32_t* __restrict__ ids,
                          const uint32_t* __restrict__ nstart, const uint32_t* __restrict__ nsize,
@@ -675,7 +725,7 @@ struct cp3g {
     size_t nlits = 0;
     DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent, tag_sub, tag_str; DevBuf<int2> tagx; DevBuf<uint32_t> ent_lit, delbits, refs_tmp, toff_sub, toff_str, tcnt_sub, tcnt_str; bool dirty_since_build = true;
+    DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<unsigned char> sort_tmp;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
@@ -762,7 +812,7 @@ void cp3g_destroy(cp3g* g)
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
-    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->ent_lit.release(); g->delbits.release(); g->refs_tmp.release(); g->tag_sub.release(); g->tag_str.release(); g->tagx.release(); g->toff_sub.release(); g->toff_str.release(); g->tcnt_sub.release(); g->tcnt_str.release();
+    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->tiles.release(); g->delbits.release(); g->refs_tmp.release();
     g->sort_tmp.release(); g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
     g->bs0.release(); g->bl0.release();
@@ -828,7 +878,7 @@ extern "C" int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const i
 static int build_csr(cp3g* g)
 {
     const uint32_t nlit = 2 * g->nvars;
-    RESERVE(g->occ_off, (size_t)nlit + 2, false);
+    RESERVE(g->occ_off, (size_t)nlit + 8, false);          // +8: the staged offset window of a tile is read in 16-byte units
     RESERVE(g->occ_tmp, (size_t)nlit + 2, false);
     const uint32_t ntiles = (nlit + 1 + SCAN_TILE - 1) / SCAN_TILE;
     RESERVE(g->tile_sum, (size_t)ntiles + 1, false);
@@ -847,45 +897,28 @@ static int build_csr(cp3g* g)
     CK(cudaStreamSynchronize(g->stream));
     g->total_occ = total;
     RESERVE(g->occ_ent, (size_t)total + 1, false);
-    RESERVE(g->ent_lit, (size_t)total + 1, false);
     RESERVE(g->refs_tmp, (size_t)total + 1, false);
     CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     if (g->ncl) {
         k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->refs_tmp.p);
-        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->ent_lit.p, g->long_lits.p, g->counters.p + 1);
+        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
         g->launches += 2;
     }
+    // tile table of the full-queue kernels (independent of the sort)
+    g->ntiles = (total + TILE - 1) / TILE;
+    RESERVE(g->tiles, (size_t)g->ntiles + 2, false);
+    k_tiles<<<grid_for((size_t)g->ntiles + 1, 256), 256, 0, g->stream>>>(g->occ_off.p, nlit, total, g->ntiles, g->tiles.p);
+    g->launches += 1;
     uint32_t nlong = 0;
     CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
     if (nlong) {
-        k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p, g->ent_lit.p);
+        k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p);
         g->launches += 1;
     }
     if (total) {
         k_occ_expand<<<grid_for(total, 256), 256, 0, g->stream>>>(g->hdr.p, g->refs_tmp.p, g->occ_ent.p, total);
         g->launches += 1;
-    }
-    if (g->ncl) {
-        // tagged CSR for the candidate-major bulk kernels
-        RESERVE(g->toff_sub, (size_t)nlit + 2, false); RESERVE(g->toff_str, (size_t)nlit + 2, false);
-        RESERVE(g->tcnt_sub, (size_t)nlit + 2, false); RESERVE(g->tcnt_str, (size_t)nlit + 2, false);
-        RESERVE(g->tag_sub, (size_t)g->ncl + 1, false); RESERVE(g->tag_str, (size_t)g->ncl + 1, false); RESERVE(g->tagx, (size_t)g->ncl + 1, false);
-        CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 0, g->tagx.p, g->tcnt_sub.p, g->tcnt_str.p,
-                                                          nullptr, nullptr, nullptr, nullptr);
-        for (int w = 0; w < 2; ++w) {
-            uint32_t* cntp = w == 0 ? g->tcnt_sub.p : g->tcnt_str.p; uint32_t* offp = w == 0 ? g->toff_sub.p : g->toff_str.p;
-            k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(cntp, offp, nlit + 1, g->tile_sum.p);
-            k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 3);
-            k_scan_add<<<ntiles, SCAN_T, 0, g->stream>>>(offp, nlit + 1, g->tile_sum.p);
-        }
-        CK(cudaMemsetAsync(g->tcnt_sub.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        CK(cudaMemsetAsync(g->tcnt_str.p, 0, ((size_t)nlit + 2) * 4, g->stream));
-        k_tag<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, 1, g->tagx.p, g->tcnt_sub.p, g->tcnt_str.p,
-                                                          g->toff_sub.p, g->toff_str.p, g->tag_sub.p, g->tag_str.p);
-        g->launches += 8;
     }
     CK(cudaGetLastError());
     g->ncl_csr = g->ncl;
@@ -917,8 +950,15 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
     g->d2h += (int64_t)(((size_t)nlit + 1) * sizeof(uint32_t));
     if (refs && g->total_occ) {
         RESERVE(g->refs_tmp, g->total_occ, false);
+        // device lists are ordered (class, clause index); the reference order is plain ascending clause index
         k_gather_refs<<<grid_for(g->total_occ, 256), 256, 0, g->stream>>>(g->occ_ent.p, g->refs_tmp.p, g->total_occ);
-        g->launches++;
+        CK(cudaMemsetAsync(g->counters.p + 1, 0, sizeof(uint32_t), g->stream));
+        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
+        uint32_t nlong = 0;
+        CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        if (nlong) { k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p); g->launches++; }
+        g->launches += 2;
         CK(cudaMemcpyAsync(refs, g->refs_tmp.p, (size_t)g->total_occ * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
         g->d2h += (int64_t)g->total_occ * 4;
@@ -1081,23 +1121,23 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     dlap("reserve hits");
     CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
     unsigned long long* dchecks = (unsigned long long*)(g->counters.p + 4);
-    // multi-GPU: contiguous slice of the entry array per rank
-    uint32_t eb = 0, ee = g->total_occ;
+    // multi-GPU: contiguous slice of the tile table per rank
+    uint32_t tb = 0, te = g->ntiles;
     if (g->world > 1) {
-        const uint64_t per = (((uint64_t)g->total_occ + g->world - 1) / g->world + 255) / 256 * 256;
-        eb = (uint32_t)std::min<uint64_t>(g->total_occ, per * g->rank);
-        ee = (uint32_t)std::min<uint64_t>(g->total_occ, per * (g->rank + 1));
+        const uint64_t per = ((uint64_t)g->ntiles + g->world - 1) / g->world;
+        tb = (uint32_t)std::min<uint64_t>(g->ntiles, per * g->rank);
+        te = (uint32_t)std::min<uint64_t>(g->ntiles, per * (g->rank + 1));
     }
     KTimer t(g);
-    if (ee > eb) {
-        // persistent grid: 8 blocks of 256 threads per SM, each block strides over 256-entry tiles
-        const unsigned blocks = std::min<unsigned>(grid_for(ee - eb, 256), (unsigned)g->num_sms * 8u);
+    if (te > tb) {
+        // persistent grid: 7 blocks of 4 independent warps per SM (29 KB of staging per block), warps stride over tiles
+        const unsigned blocks = std::min<unsigned>(grid_for(te - tb, FQ_WARPS), (unsigned)g->num_sms * 7u);
         if (kind == CP3G_SUBSUME) {
-            k_bulk_cm<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_ent.p, g->ent_lit.p, g->delbits.p,
-                g->toff_sub.p, g->tag_sub.p, eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+            k_full<CP3G_SUBSUME><<<blocks, FQ_WARPS * 32, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->tiles.p,
+                g->delbits.p, tb, te, g->hits.p, cap, g->counters.p, dchecks);
         } else {
-            k_bulk_cm<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_ent.p, g->ent_lit.p, g->delbits.p,
-                g->toff_str.p, g->tag_str.p, eb, ee, g->hits.p, cap, g->counters.p, dchecks);
+            k_full<CP3G_STRENGTHEN><<<blocks, FQ_WARPS * 32, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->tiles.p,
+                g->delbits.p, tb, te, g->hits.p, cap, g->counters.p, dchecks);
         }
         g->launches++;
     }
