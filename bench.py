@@ -292,7 +292,7 @@ def main():
     # DRAM bytes per launch of the dominant kernel from the last `ncu --set full` capture (profiles/), or None
     TRAFFIC = None
     try:
-        TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_bulk_cm_bytes_per_launch")
+        TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_full_bytes_per_launch")
     except Exception:
         pass
     if rank == 0:
@@ -309,17 +309,17 @@ def main():
             "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": f"BASELINE configs[1]: planted random 3-SAT {args.vars} vars / {sizes.size} clauses "
                                    f"(2% duplicates, 3% supersets, 3% flipped copies), seed {args.seed}, subsumption+strengthening fixpoint",
-                       "value_leg": "device-resident bulk pass: K1 sig + K2 occ CSR + K3 + K4 over the full queue, CUDA events",
+                       "value_leg": "device-resident bulk pass: K1 signatures + K2 occurrence CSR build + K3 + K4 over the full queue, CUDA events on the library stream",
                        "l2": "working set (occ entries + headers + literals, ~350 MB) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
                        "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank" if args.mode == "weak"
                                        else f"{world} ranks, one formula: scan requests partitioned, hits all-gathered over NCCL"))},
-            "roofline": {"bound": "hbm", "kernel": "k_bulk_cm (K3+K4 full-queue form, both launches)", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "k_full (K3+K4 full-queue form, both launches)", "achieved": achieved, "peak": peak,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC,
                          "algorithmic_bytes_per_launch": alg_bytes / 2, "launch_ms": scan_ns * 1e-6 / 2,
                          "per_kernel": {
-                             "k_bulk_cm<subsume>": {"ms": mean("k3_ns") * 1e-6, "checks": mean("k3_checks"), "GB/s": mean("k3_bytes") / max(mean("k3_ns"), 1.0)},
-                             "k_bulk_cm<strengthen>": {"ms": mean("k4_ns") * 1e-6, "checks": mean("k4_checks"), "GB/s": mean("k4_bytes") / max(mean("k4_ns"), 1.0)},
+                             "k_full<subsume>": {"ms": mean("k3_ns") * 1e-6, "checks": mean("k3_checks"), "GB/s": mean("k3_bytes") / max(mean("k3_ns"), 1.0)},
+                             "k_full<strengthen>": {"ms": mean("k4_ns") * 1e-6, "checks": mean("k4_checks"), "GB/s": mean("k4_bytes") / max(mean("k4_ns"), 1.0)},
                              "K1+K2 build": {"ms": mean("build_ns") * 1e-6}}},
             "e2e": {"value": checks / T, "unit": UNIT, "ms_per_step": T * 1e3, "h2d_bytes_per_step": st["gpu_h2d_bytes"],
                     "d2h_bytes_per_step": st["gpu_d2h_bytes"], "checks_per_step": checks,

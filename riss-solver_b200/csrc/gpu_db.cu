@@ -13,8 +13,10 @@
 //   ovf[]      clause indices appended after the last CSR build (BVE resolvents); scanned by every request
 //
 // Kernels (none uses tensor cores - there is no contraction on this path):
-//   k_sig_build   K1  64-bit literal signature per clause (new accelerating filter; never changes results)
-//   k_occ_*       K2  histogram -> exclusive scan -> scatter -> per-list sort
+//   k_occ_count   K1+K2  64-bit literal signature per clause (new accelerating filter; never changes results)
+//                 fused with the occurrence histogram
+//   k_occ_*       K2  exclusive scan -> scatter of (class, clause) words -> per-list sort -> tile table -> expand
+//   k_full<KIND>  K3/K4 full-queue pass: candidate-major over bulk-copy staged tiles of the entry array
 //   k_scan<KIND>  K3/K4 request-driven signature filter + sorted-literal merge (Subsumption.cc:244-297,
 //                 1276-1521; Clause::ordered_subsumes SolverTypes.h:1003)
 //   k_bve_pairs   K5  resolvent size per (pos,neg) pair (BVE.h:248-299)
@@ -28,6 +30,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <type_traits>
 #include <chrono>
 
 #include "../../include/cp3b200.h"
@@ -59,19 +62,7 @@ __device__ __forceinline__ unsigned long long var_fold(unsigned long long s)
     return (s | (s >> 1)) & 0x5555555555555555ull;
 }
 
-// ------------------------------------------------------------------------------------------ K1
-__global__ void k_sig_build(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t first, uint32_t n)
-{
-    uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) { return; }
-    ClauseHdr h = hdr[i];
-    const uint32_t sz = h.szfl & SIZE_MASK;
-    unsigned long long s = 0;
-    for (uint32_t k = 0; k < sz; ++k) { s |= lit_bit(lits[h.start + k]); }
-    hdr[i].sig = s;
-}
-
-// ------------------------------------------------------------------------------------------ K2
+// ------------------------------------------------------------------------------------------ K1 + K2
 __global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
                             uint32_t* __restrict__ cnt)
 {
@@ -178,14 +169,24 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
         refs[off[x] + atomicAdd(&cursor[x], 1u)] = i | (cls << 30);
     }
 }
-// one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced
-__global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ refs, OccEnt* __restrict__ ent, uint32_t total)
+// one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced.
+// The top byte of the size word gets dx = (literal of the entry's list) - (first literal of its tile), saturating
+// at 255, so that the full-queue kernels find the list of a staged entry without a search.  The search happens
+// here instead, over the handful of offsets of the tile (neighbouring threads walk the same cached words).
+__global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ refs, OccEnt* __restrict__ ent, uint32_t total,
+                             const uint32_t* __restrict__ off, const uint2* __restrict__ tiles)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) { return; }
     const uint32_t r = refs[i];
+    uint32_t t = i / TILE;
+    uint2 a = tiles[t], b = tiles[t + 1];
+    if (i >= (b.x & ~TILE_ALIGNED)) { a = b; b = tiles[t + 2]; }
+    uint32_t lo = a.y, hi = (b.x & TILE_ALIGNED) ? b.y : b.y + 1;         // last x with off[x] <= i
+    while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (off[mid] <= i) { lo = mid; } else { hi = mid; } }
+    const uint32_t dx = min(lo - a.y, 255u);
     const ClauseHdr h = hdr[r & REF_MASK];
-    OccEnt e; e.ref = r; e.szfl = h.szfl & SIZE_MASK; e.sig = h.sig;
+    OccEnt e; e.ref = r; e.szfl = (h.szfl & SIZE_MASK) | (dx << 24); e.sig = h.sig;
     ent[i] = e;
 }
 // Tile table of the full-queue kernels.  Tile t nominally starts at entry 128*t; the start is moved down to the
@@ -462,7 +463,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
 //            which would otherwise stall 31 lanes behind one)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
 static constexpr int WQ_CAP = 64, WH_CAP = 32, FQ_WARPS = 4;
-struct TileDesc { uint32_t s, n, x0, xe, xa, noff; };
+struct TileDesc { uint32_t s, n, x0, xe, xa, noff; bool pure; };
 __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
 {
     TileDesc d;
@@ -471,6 +472,7 @@ __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
     d.xa = d.x0 & ~3u;                                                   // 16-byte aligned source for the bulk copy
     const uint32_t cnt = (d.xe - d.xa + 1 + 3) & ~3u;
     d.noff = cnt <= OFFCAP ? cnt : 0u;                                   // 0: too many (empty) lists, offsets stay global
+    d.pure = (a.x & b.x & TILE_ALIGNED) && d.noff;                       // whole short list pairs, offsets staged
     return d;
 }
 template <int KIND>
@@ -544,38 +546,56 @@ __global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restr
                 mbar_wait(&bar[w][b], (phase >> b) & 1u); phase ^= 1u << b;
                 const OccEnt* es = e_s[w][b]; const uint32_t* os = o_s[w][b];
                 const uint32_t s = cur.s, n = cur.n, xa = cur.xa, noff = cur.noff;
-                auto OFF = [&](uint32_t x) -> uint32_t { return (x - xa < noff) ? os[x - xa] : occ_off[x]; };
-                auto ENT = [&](uint32_t i) -> OccEnt { return (i - s < n) ? es[i - s] : occ_ent[i]; };
-                for (uint32_t p = lane; p < n; p += 32) {
-                    const OccEnt en = es[p];
-                    const uint32_t j = s + p, dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
-                    uint32_t lo = cur.x0, hi = cur.xe;           // last x with off[x] <= j
-                    while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (OFF(mid) <= j) { lo = mid; } else { hi = mid; } }
-                    const uint32_t x = lo;
+                // One candidate entry against the tagged prefix of list x (pass 0) and of list x^1 (pass 1).
+                // PURE: the tile consists of whole short list pairs and its offsets are staged - every access
+                // below is a shared-memory load without range checks.  Otherwise each access picks shared/global.
+                auto candidate = [&](auto pure_tag, const OccEnt en, uint32_t x) {
+                    constexpr bool PURE = decltype(pure_tag)::value;
+                    auto OFF = [&](uint32_t y) -> uint32_t { return (PURE || y - xa < noff) ? os[y - xa] : occ_off[y]; };
+                    const uint32_t dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
                     const unsigned long long dvar = var_fold(en.sig);
+                    uint32_t cnt = 0;
                     const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
                     for (int pass = 0; pass < npass; ++pass) {
                         const uint32_t xx = pass == 0 ? x : (x ^ 1u);
                         const uint32_t kb = OFF(xx), ke = OFF(xx + 1);
                         for (uint32_t k = kb; k < ke; ++k) {
-                            const OccEnt sc = ENT(k);
-                            const uint32_t cls = sc.ref >> 30;
+                            const bool in = PURE || k - s < n;
+                            const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
+                            const uint32_t cls = a.x >> 30;
                             if (KIND == CP3G_SUBSUME) { if (cls & CLS_NOSUB) { break; } }
                             else { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSTR) { continue; } }
-                            const uint32_t sref = sc.ref & REF_MASK;
+                            const uint32_t sref = a.x & REF_MASK;
                             if (sref == dref) { continue; }
-                            nchk += 1; nbytes += 12 + 4 * esz;
-                            const uint32_t sn = sc.szfl & SIZE_MASK;
-                            if (esz < sn) { continue; }
-                            const unsigned long long miss = sc.sig & ~en.sig;
+                            cnt += 1;
+                            if (esz < (a.y & SIZE_MASK)) { continue; }
+                            const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
+                            const unsigned long long miss = ssig & ~en.sig;
                             if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                            else { if ((miss & (miss - 1)) || (var_fold(sc.sig) & ~dvar)) { continue; } }
+                            else { if ((miss & (miss - 1)) || (var_fold(ssig) & ~dvar)) { continue; } }
                             if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { continue; }
                             const uint32_t q = atomicAdd(&q_n[w], 1u);
                             if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | (uint32_t)pass); }
                             else { verify(sref, dref, (int32_t)x, pass); }
                         }
                     }
+                    nchk += cnt; nbytes += (unsigned long long)cnt * (12 + 4 * esz);
+                };
+                // a tile is pure iff both of its cuts are aligned to list pairs and its offsets are staged
+                const bool pure = cur.pure;
+                for (uint32_t p = lane; p < n; p += 32) {
+                    const OccEnt en = es[p];
+                    const uint32_t dx = en.szfl >> 24;
+                    uint32_t x = cur.x0 + dx;
+                    if (dx == 255u) {                                // far from the tile's first literal (runs of empty lists)
+                        const uint32_t j = s + p;
+                        uint32_t lo = x, hi = cur.xe;               // last x with off[x] <= j
+                        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= j) { lo = mid; } else { hi = mid; } }
+                        x = lo;
+                        candidate(std::false_type(), en, x);
+                    }
+                    else if (pure) { candidate(std::true_type(), en, x); }
+                    else { candidate(std::false_type(), en, x); }
                 }
             }
             __syncwarp();                                  // all reads of buffer b are done before it is refilled
@@ -906,8 +926,8 @@ static int build_csr(cp3g* g)
     }
     // tile table of the full-queue kernels (independent of the sort)
     g->ntiles = (total + TILE - 1) / TILE;
-    RESERVE(g->tiles, (size_t)g->ntiles + 2, false);
-    k_tiles<<<grid_for((size_t)g->ntiles + 1, 256), 256, 0, g->stream>>>(g->occ_off.p, nlit, total, g->ntiles, g->tiles.p);
+    RESERVE(g->tiles, (size_t)g->ntiles + 3, false);
+    k_tiles<<<grid_for((size_t)g->ntiles + 2, 256), 256, 0, g->stream>>>(g->occ_off.p, nlit, total, g->ntiles + 1, g->tiles.p);
     g->launches += 1;
     uint32_t nlong = 0;
     CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
@@ -917,7 +937,7 @@ static int build_csr(cp3g* g)
         g->launches += 1;
     }
     if (total) {
-        k_occ_expand<<<grid_for(total, 256), 256, 0, g->stream>>>(g->hdr.p, g->refs_tmp.p, g->occ_ent.p, total);
+        k_occ_expand<<<grid_for(total, 256), 256, 0, g->stream>>>(g->hdr.p, g->refs_tmp.p, g->occ_ent.p, total, g->occ_off.p, g->tiles.p);
         g->launches += 1;
     }
     CK(cudaGetLastError());
@@ -932,7 +952,6 @@ int cp3g_build(cp3g* g)
     if (!g) { return CP3G_ERR_NODEVICE; }
     cudaSetDevice(g->device);
     KTimer t(g);
-    if (g->ncl) { k_sig_build<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, 0, g->ncl); g->launches++; }
     int r = build_csr(g);
     t.stop();
     CK(cudaStreamSynchronize(g->stream));

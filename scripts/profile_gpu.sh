@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
 echo "launch list rc=$?"
 ARGS2="--steps 1 --warmup 0 --no-cpu-baseline"
 python bench.py $ARGS2 > gpurun_out/plain_bench2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:k_bulk_cm -c 2 -o gpurun_out/prof_bulk_cm \
+ncu --set full --clock-control none --import-source on -k regex:k_full -c 2 -o gpurun_out/prof_full \
     python bench.py $ARGS2 > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out/

@@ -138,6 +138,49 @@ def test_k3_subsumed_set_matches_oracle_snapshot(gen):
     assert checks > 0
 
 
+def _hits_key(h):
+    o = np.lexsort((h["lit"], h["clause"], h["req"]))
+    return np.stack([h["req"][o], h["clause"][o], h["lit"][o].astype(np.int64)], 1)
+
+
+@pytest.mark.parametrize("shape", ["uniform", "zipf", "community", "sparse_vars", "very_sparse_vars", "one_long_pair"])
+def test_k3_k4_full_queue_kernel_equals_request_kernel(gen, shape):
+    """k_full (tile-staged, class-prefixed lists) against k_scan (one warp per request) on the same snapshot: same
+    hit set and the same number of checks.  The shapes hit every tile flavour: pure tiles, lists longer than a tile,
+    more lists per tile than the staged offset window holds, and list distances that saturate the dx byte."""
+    if shape == "uniform":
+        lits, sizes = gen.random_ksat(6000, 25000, 3, seed=31, dup=0.03, sup=0.05, flip=0.05)
+    elif shape == "zipf":
+        lits, sizes = gen.random_ksat(6000, 25000, 3, seed=32, zipf_s=1.1, dup=0.03, sup=0.05, flip=0.05)
+    elif shape == "community":
+        lits, sizes = gen.community_ksat(8000, 40000, seed=33)
+    elif shape in ("sparse_vars", "very_sparse_vars"):
+        lits, sizes = gen.random_ksat(3000, 12000, 3, seed=34, dup=0.03, sup=0.05, flip=0.05)
+        gap = 7 if shape == "sparse_vars" else 401          # runs of empty occurrence lists between used variables
+        lits = (np.sign(lits) * ((np.abs(lits) - 1) * gap + 1)).astype(np.int32)
+    else:
+        rng = np.random.default_rng(35)                      # every clause holds variable 1: two lists of ~6000 entries
+        m = 12000
+        other = rng.integers(2, 400, size=(m, 2))
+        other[:, 1] = np.where(other[:, 1] == other[:, 0], other[:, 0] + 1, other[:, 1])
+        rows = np.concatenate([np.ones((m, 1), np.int64), other], 1) * rng.choice([-1, 1], size=(m, 3))
+        lits = rows.reshape(-1).astype(np.int32); sizes = np.full(m, 3, np.int64)
+    n = int(np.abs(lits).max())
+    svc = rs.ScanService(); svc.upload(n, _sorted_clauses(lits, sizes), sizes); svc.build()
+    ids = np.arange(sizes.size, dtype=np.uint32)
+    for kind in (rs.SUBSUME, rs.STRENGTHEN):
+        a, ca = svc.scan_all(kind)
+        b, cb = svc.scan(kind, ids, cap=max(1 << 16, 4 * a.size))
+        assert ca == cb and ca > 0
+        assert np.array_equal(_hits_key(a), _hits_key(b))
+    # the host-visible occurrence lists stay in clause order although the device lists are (class, clause) ordered
+    off, refs = svc.download_occ()
+    codes = _sorted_clauses(lits, sizes)
+    clause_of = np.repeat(np.arange(sizes.size, dtype=np.uint32), sizes)
+    assert np.array_equal(refs, clause_of[np.lexsort((clause_of, codes))])
+    svc.close()
+
+
 def test_k5_resolvent_counts_match_oracle_snapshot(gen):
     lits, sizes = gen.community_ksat(3000, 12000, seed=4, planted=False)
     stream = gen.csr_to_stream(lits, sizes)
@@ -185,7 +228,7 @@ def test_c2_size_properties(gen):
 
 
 def test_forced_parallel_paths_on_gpu(gen):
-    """same fuzz as test_fuzz_small_instances with the large-queue code paths (bulk kernels k_bulk_cm, time-indexed
+    """same fuzz as test_fuzz_small_instances with the large-queue code paths (full-queue kernels k_full, time-indexed
     subsumption commit, static strengthening plan, scan/commit overlap) forced on; thresholds are read once per
     process, hence the subprocess"""
     import subprocess, sys
