@@ -43,7 +43,7 @@ static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
 // occurrence entry: top two bits of `ref` = class of the clause in this list (see k_occ_fill)
 static constexpr uint32_t REF_MASK = 0x3fffffffu;
-static constexpr uint32_t CLS_NOSUB = 2u, CLS_NOSTR = 1u, CLS_NONE = 3u;
+static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 // full-queue kernel tiling
 static constexpr uint32_t TILE = 128, GROUP_MAX = 32, TCAP = TILE + GROUP_MAX, OFFCAP = 128, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
@@ -145,8 +145,9 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
 // The two top bits of the scattered word carry the CLASS of clause i in that list.  A full-queue scan walks, for
 // clause i, the shortest list among its literals (subsumption, Subsumption.cc:244-256) resp. the shortest list pair
 // occ(x)+occ(~x) (strengthening, Subsumption.cc:1292-1299); i is "tagged" in exactly that list.  class = 0 tagged
-// for both, 1 subsumption only, 2 strengthening only, 3 not tagged; the per-list sort on the whole word then puts
-// the tagged clauses first, so every list carries the set of clauses that scan it as a prefix.
+// for both, 1 strengthening only, 2 subsumption only, 3 not tagged; the per-list sort on the whole word then puts
+// the tagged clauses first, so every list carries the set of clauses that scan it as a prefix (the strengtheners
+// exactly, K4 being the more expensive pass; K3 skips the few class-1 entries).
 __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
                            const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ refs)
 {
@@ -553,7 +554,7 @@ __global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restr
                     constexpr bool PURE = decltype(pure_tag)::value;
                     auto OFF = [&](uint32_t y) -> uint32_t { return (PURE || y - xa < noff) ? os[y - xa] : occ_off[y]; };
                     const uint32_t dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
-                    const unsigned long long dvar = var_fold(en.sig);
+                    const unsigned long long dboth = var_fold(en.sig) * 3ull;     // both polarity bits of every variable of D
                     uint32_t cnt = 0;
                     const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
                     for (int pass = 0; pass < npass; ++pass) {
@@ -563,8 +564,8 @@ __global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restr
                             const bool in = PURE || k - s < n;
                             const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
                             const uint32_t cls = a.x >> 30;
-                            if (KIND == CP3G_SUBSUME) { if (cls & CLS_NOSUB) { break; } }
-                            else { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSTR) { continue; } }
+                            if (KIND == CP3G_SUBSUME) { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSUB) { continue; } }
+                            else { if (cls & CLS_NOSTR) { break; } }
                             const uint32_t sref = a.x & REF_MASK;
                             if (sref == dref) { continue; }
                             cnt += 1;
@@ -572,7 +573,7 @@ __global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restr
                             const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
                             const unsigned long long miss = ssig & ~en.sig;
                             if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                            else { if ((miss & (miss - 1)) || (var_fold(ssig) & ~dvar)) { continue; } }
+                            else { if ((ssig & ~dboth) || (miss & (miss - 1))) { continue; } }
                             if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { continue; }
                             const uint32_t q = atomicAdd(&q_n[w], 1u);
                             if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | (uint32_t)pass); }
