@@ -642,14 +642,14 @@ __device__ __forceinline__ int resolvent_size(const int32_t* __restrict__ P, uin
     }
     return r;
 }
-__global__ void k_bve_pairs(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t nv,
+__global__ void k_bve_pairs(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t vfirst, uint32_t nv,
                             const uint32_t* __restrict__ vars, const uint32_t* __restrict__ p_off,
                             const uint32_t* __restrict__ p_refs, const uint32_t* __restrict__ n_off,
                             const uint32_t* __restrict__ n_refs, const unsigned long long* __restrict__ pair_off,
                             int16_t* __restrict__ sizes)
 {
-    // one warp per variable, lanes over the pos x neg pairs
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // one warp per variable of this rank's range [vfirst, nv), lanes over the pos x neg pairs
+    const uint32_t warp = vfirst + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const uint32_t lane = threadIdx.x & 31;
     if (warp >= nv) { return; }
     const uint32_t pb = p_off[warp], np = p_off[warp + 1] - pb;
@@ -668,12 +668,12 @@ __global__ void k_bve_pairs(const ClauseHdr* __restrict__ hdr, const int32_t* __
         sizes[base + t] = (int16_t)s;
     }
 }
-__global__ void k_bve_resolve(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t npairs,
+__global__ void k_bve_resolve(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t first, uint32_t npairs,
                               const uint32_t* __restrict__ vars, const uint32_t* __restrict__ p_refs,
                               const uint32_t* __restrict__ n_refs, const unsigned long long* __restrict__ out_off,
                               int32_t* __restrict__ out_lits)
 {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = first + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= npairs) { return; }
     const ClauseHdr hp = hdr[p_refs[t]], hn = hdr[n_refs[t]];
     const int32_t* P = lits + hp.start; const int32_t* N = lits + hn.start;
@@ -1205,9 +1205,28 @@ int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p
     CK(cudaMemcpyAsync(g->bu3.p, n_off, ((size_t)nv + 1) * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bu4.p, n_refs, nn * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bq0.p, pair_off, ((size_t)nv + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    // multi-GPU: contiguous variable ranges balanced by the number of (pos,neg) pairs; the size slices are
+    // all-gathered in place so that every rank commits from the identical matrix
+    uint32_t vb = 0, ve = nv; std::vector<size_t> boff;
+    if (g->world > 1) {
+        boff.assign((size_t)g->world + 1, 0);
+        std::vector<uint32_t> cut((size_t)g->world + 1, nv);
+        cut[0] = 0;
+        for (int r = 1; r < g->world; ++r) {
+            const uint64_t want = total * (uint64_t)r / (uint64_t)g->world;
+            cut[r] = (uint32_t)(std::lower_bound(pair_off, pair_off + nv + 1, want) - pair_off);
+            if (cut[r] > nv) { cut[r] = nv; }
+            if (cut[r] < cut[r - 1]) { cut[r] = cut[r - 1]; }
+        }
+        for (int r = 0; r <= g->world; ++r) { boff[r] = (size_t)pair_off[cut[r]] * sizeof(int16_t); }
+        vb = cut[g->rank]; ve = cut[g->rank + 1];
+    }
     KTimer t(g);
-    k_bve_pairs<<<grid_for((size_t)nv * 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, nv, g->bu0.p, g->bu1.p, g->bu2.p,
-            g->bu3.p, g->bu4.p, g->bq0.p, g->bs0.p);
+    if (ve > vb) {
+        k_bve_pairs<<<grid_for((size_t)(ve - vb) * 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, vb, ve, g->bu0.p, g->bu1.p, g->bu2.p,
+                g->bu3.p, g->bu4.p, g->bq0.p, g->bs0.p);
+    }
+    if (g->world > 1 && cp3g_nccl_allgatherv_inplace(g->nccl, g->stream, g->bs0.p, boff.data()) != CP3G_OK) { g->err = "nccl all-gather-v (K5 sizes) failed"; return CP3G_ERR_CUDA; }
     t.stop();
     CK(cudaMemcpyAsync(sizes, g->bs0.p, total * sizeof(int16_t), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
@@ -1229,9 +1248,27 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
     CK(cudaMemcpyAsync(g->bu2.p, p_refs, (size_t)npairs * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bu4.p, n_refs, (size_t)npairs * 4, cudaMemcpyHostToDevice, g->stream));
     CK(cudaMemcpyAsync(g->bq0.p, out_off, ((size_t)npairs + 1) * 8, cudaMemcpyHostToDevice, g->stream));
+    // multi-GPU: contiguous pair ranges balanced by resolvent literals, literal streams all-gathered in place
+    uint32_t pb = 0, pe = npairs; std::vector<size_t> boff;
+    if (g->world > 1) {
+        boff.assign((size_t)g->world + 1, 0);
+        std::vector<uint32_t> cut((size_t)g->world + 1, npairs);
+        cut[0] = 0;
+        for (int r = 1; r < g->world; ++r) {
+            const uint64_t want = (uint64_t)nlits * (uint64_t)r / (uint64_t)g->world;
+            cut[r] = (uint32_t)(std::lower_bound(out_off, out_off + npairs + 1, want) - out_off);
+            if (cut[r] > npairs) { cut[r] = npairs; }
+            if (cut[r] < cut[r - 1]) { cut[r] = cut[r - 1]; }
+        }
+        for (int r = 0; r <= g->world; ++r) { boff[r] = (size_t)out_off[cut[r]] * sizeof(int32_t); }
+        pb = cut[g->rank]; pe = cut[g->rank + 1];
+    }
     KTimer t(g);
-    k_bve_resolve<<<grid_for(npairs, 128), 128, 0, g->stream>>>(g->hdr.p, g->lits.p, npairs, g->bu0.p, g->bu2.p, g->bu4.p,
-            g->bq0.p, g->bl0.p);
+    if (pe > pb) {
+        k_bve_resolve<<<grid_for(pe - pb, 128), 128, 0, g->stream>>>(g->hdr.p, g->lits.p, pb, pe, g->bu0.p, g->bu2.p, g->bu4.p,
+                g->bq0.p, g->bl0.p);
+    }
+    if (g->world > 1 && cp3g_nccl_allgatherv_inplace(g->nccl, g->stream, g->bl0.p, boff.data()) != CP3G_OK) { g->err = "nccl all-gather-v (K6 literals) failed"; return CP3G_ERR_CUDA; }
     t.stop();
     CK(cudaMemcpyAsync(out_lits, g->bl0.p, nlits * 4, cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));

@@ -117,3 +117,21 @@ int cp3g_nccl_gather_hits(void* comm, cudaStream_t st, const cp3g_hit* dhits, ui
     *nout = (uint32_t)total;
     return CP3G_OK;
 }
+
+// all-gather-v in place: rank r owns bytes [off[r], off[r+1]) of the device buffer `dbuf`, whose layout every rank
+// knows (the partition is a pure function of the request); afterwards all ranks hold the whole buffer.  Used for
+// the per-pair resolvent sizes (K5) and the resolvent literal streams (K6) of a variable batch.
+int cp3g_nccl_allgatherv_inplace(void* comm, cudaStream_t st, void* dbuf, const size_t* off)
+{
+    Comm* c = (Comm*)comm; Api* a = api();
+    if (!c || !a) { return CP3G_ERR_NODEVICE; }
+    a->GroupStart();
+    for (int r = 0; r < c->world; ++r) {
+        const size_t bytes = off[r + 1] - off[r];
+        if (!bytes) { continue; }
+        char* ptr = (char*)dbuf + off[r];
+        a->Broadcast(ptr, ptr, bytes, ncclUint8, r, c->comm, st);
+    }
+    if (a->GroupEnd() != 0) { return CP3G_ERR_CUDA; }
+    return CP3G_OK;
+}

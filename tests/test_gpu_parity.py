@@ -248,3 +248,15 @@ def test_forced_parallel_paths_on_gpu(gen):
     env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3")
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "BAD 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_sharded_mode_two_gpus_matches_oracle():
+    """one formula over 2 ranks (scan slices, BVE variable batches; NCCL all-gather-v of hits, pair sizes and
+    resolvents): every rank's ordered result equals the oracle's.  Needs 2 GPUs; skipped on a 1-GPU box."""
+    import subprocess, sys
+    if rs.load().cp3g_device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "sharded_parity.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "SHARDED_PARITY OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

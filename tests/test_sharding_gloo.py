@@ -1,6 +1,8 @@
 """N>1 host logic on CPU (gloo, world_size 2): the request partition and hit all-gather of the sharded scan
 (gpu_db.cu cp3g_scan: contiguous slices `per = ceil(nreq / world)`, nccl_comm.cpp all-gather-v) produce the same
-hit set on every rank as one unsharded scan, and the max-over-ranks / sum-over-ranks reductions bench.py uses."""
+hit set on every rank as one unsharded scan; the variable partition of the BVE pair matrix (cp3g_bve_pairs) is
+balanced and its gathered slices equal the unsharded matrix; and the max-over-ranks / sum-over-ranks reductions
+bench.py uses."""
 import os
 import subprocess
 import sys
@@ -50,6 +52,25 @@ for kind in (rs.SUBSUME, rs.STRENGTHEN):
     lo = digest.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     hi = digest.clone(); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     assert torch.equal(lo, hi)
+# K5 (BVE pair sizes): the variable range rule of cp3g_bve_pairs - contiguous ranges cut where the running
+# number of (pos,neg) pairs crosses total*r/world - and the in-place all-gather-v of the size slices
+off, refs = svc.download_occ()
+n = int(np.abs(lits).max())
+vs = np.arange(n, dtype=np.uint32)
+pos = [refs[off[2 * x]:off[2 * x + 1]] for x in range(n)]
+neg = [refs[off[2 * x + 1]:off[2 * x + 2]] for x in range(n)]
+pair_off, full_sz = svc.bve_pairs(vs, pos, neg)
+total = int(pair_off[-1])
+cut = [0] + [int(np.searchsorted(pair_off, total * r // world, side="left")) for r in range(1, world)] + [n]
+for r in range(1, world + 1):
+    cut[r] = max(min(cut[r], n), cut[r - 1])
+vb, ve = cut[rank], cut[rank + 1]
+_, my_sz = svc.bve_pairs(vs[vb:ve], pos[vb:ve], neg[vb:ve])
+parts = [None] * world
+dist.all_gather_object(parts, my_sz)
+assert np.array_equal(np.concatenate(parts), full_sz)
+sizes_per_rank = [int(pair_off[cut[r + 1]] - pair_off[cut[r]]) for r in range(world)]
+assert max(sizes_per_rank) <= total // world + int(np.diff(pair_off).max()) + 1     # balanced up to one variable
 # the reductions bench.py reports: time = max over ranks, work = sum over ranks
 t = torch.tensor([1.0 + rank], dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
 w = torch.tensor([10.0], dtype=torch.float64); dist.all_reduce(w, op=dist.ReduceOp.SUM)
