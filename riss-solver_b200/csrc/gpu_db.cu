@@ -64,16 +64,18 @@ __device__ __forceinline__ unsigned long long var_fold(unsigned long long s)
 
 // ------------------------------------------------------------------------------------------ K1 + K2
 __global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                            uint32_t* __restrict__ cnt)
+                            uint32_t* __restrict__ cnt, uint32_t* __restrict__ rank)
 {
-    // histogram of the literal occurrences; the same pass over the literals refreshes the clause signature (K1)
+    // histogram of the literal occurrences; the same pass over the literals refreshes the clause signature (K1).
+    // The value the atomic returns is kept as the occurrence's (arbitrary) rank inside its list, stored next to the
+    // literal - the scatter pass then needs no second round of atomics.
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
     const ClauseHdr h = hdr[i];
     const uint32_t sz = h.szfl & SIZE_MASK;
     unsigned long long s = 0;
     const bool live = !(h.szfl & FLAG_DEL);
-    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = lits[h.start + k]; s |= lit_bit(x); if (live) { atomicAdd(&cnt[x], 1u); } }
+    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = lits[h.start + k]; s |= lit_bit(x); if (live) { rank[h.start + k] = atomicAdd(&cnt[x], 1u); } }
     if (s != h.sig) { hdr[i].sig = s; }
 }
 
@@ -149,7 +151,7 @@ __global__ void k_scan_add(uint32_t* __restrict__ out, uint32_t n, const uint32_
 // the tagged clauses first, so every list carries the set of clauses that scan it as a prefix (the strengtheners
 // exactly, K4 being the more expensive pass; K3 skips the few class-1 entries).
 __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
-                           const uint32_t* __restrict__ off, uint32_t* __restrict__ cursor, uint32_t* __restrict__ refs)
+                           const uint32_t* __restrict__ off, const uint32_t* __restrict__ rank, uint32_t* __restrict__ refs)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
@@ -167,7 +169,7 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
     for (uint32_t k = 0; k < sz; ++k) {
         const int32_t x = lits[h.start + k];
         const uint32_t cls = (x == xs ? 0u : CLS_NOSUB) | (x == xt ? 0u : CLS_NOSTR);
-        refs[off[x] + atomicAdd(&cursor[x], 1u)] = i | (cls << 30);
+        refs[off[x] + rank[h.start + k]] = i | (cls << 30);
     }
 }
 // one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced.
@@ -208,20 +210,33 @@ __global__ void k_tiles(const uint32_t* __restrict__ off, uint32_t nlit, uint32_
     tiles[t] = (ge - gs <= GROUP_MAX) ? make_uint2(gs | TILE_ALIGNED, g) : make_uint2(j, x);
 }
 // scatter order is nondeterministic; every list is sorted by (class, clause index) - the scattered word itself.
-__global__ void k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, uint32_t* __restrict__ refs,
+static constexpr uint32_t SORT_LISTS = 128, SORT_CAP = 4096;
+__global__ void __launch_bounds__(SORT_LISTS) k_occ_sort_short(const uint32_t* __restrict__ off, uint32_t nlit, uint32_t* __restrict__ refs,
                                  uint32_t* __restrict__ long_lits, uint32_t* __restrict__ nlong)
 {
-    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= nlit) { return; }
-    const uint32_t b = off[x], e = off[x + 1], len = e - b;
-    if (len < 2) { return; }
-    if (len > SHORT_LIST) { long_lits[atomicAdd(nlong, 1u)] = x; return; }
-    for (uint32_t i = b + 1; i < e; ++i) {
-        const uint32_t key = refs[i];
-        uint32_t j = i;
-        while (j > b && refs[j - 1] > key) { refs[j] = refs[j - 1]; --j; }
-        refs[j] = key;
+    // one thread per list, insertion sort; the lists of a block are contiguous in refs[], so the block stages that
+    // range in shared memory (coalesced in, coalesced out) unless a long list makes it too large
+    __shared__ uint32_t sh[SORT_CAP];
+    const uint32_t x0 = blockIdx.x * SORT_LISTS, x = x0 + threadIdx.x, xe = min(x0 + SORT_LISTS, nlit);
+    const uint32_t rb = off[x0], rn = off[xe] - rb;
+    const bool staged = rn <= SORT_CAP;
+    if (staged) { for (uint32_t i = threadIdx.x; i < rn; i += SORT_LISTS) { sh[i] = refs[rb + i]; } }
+    __syncthreads();
+    if (x < nlit) {
+        const uint32_t b = off[x], len = off[x + 1] - b;
+        if (len > SHORT_LIST) { long_lits[atomicAdd(nlong, 1u)] = x; }
+        else if (len >= 2) {
+            uint32_t* a = staged ? sh + (b - rb) : refs + b;
+            for (uint32_t i = 1; i < len; ++i) {
+                const uint32_t key = a[i];
+                uint32_t j = i;
+                while (j > 0 && a[j - 1] > key) { a[j] = a[j - 1]; --j; }
+                a[j] = key;
+            }
+        }
     }
+    __syncthreads();
+    if (staged) { for (uint32_t i = threadIdx.x; i < rn; i += SORT_LISTS) { refs[rb + i] = sh[i]; } }
 }
 // one block per long list: normalised bitonic sort in global memory.  Every compare-exchange is ascending
 // (i < l keeps the smaller ref at i), so the virtual +inf padding above len never has to move and pairs that
@@ -745,7 +760,7 @@ struct cp3g {
     uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
     size_t nlits = 0;
     DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
-    DevBuf<uint32_t> occ_off, occ_tmp, tile_sum, long_lits, ovf, scratch_u32;
+    DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, tile_sum, long_lits, ovf, scratch_u32;
     DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<unsigned char> sort_tmp;
@@ -832,7 +847,7 @@ void cp3g_destroy(cp3g* g)
     if (!g) { return; }
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
-    g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->tile_sum.release();
+    g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->occ_rank.release(); g->tile_sum.release();
     g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->tiles.release(); g->delbits.release(); g->refs_tmp.release();
     g->sort_tmp.release(); g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
     g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
@@ -907,7 +922,8 @@ static int build_csr(cp3g* g)
     CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
     if (g->ncl) {
-        k_occ_count<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_tmp.p);
+        RESERVE(g->occ_rank, g->nlits + 1, false);
+        k_occ_count<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_tmp.p, g->occ_rank.p);
     }
     k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(g->occ_tmp.p, g->occ_off.p, nlit + 1, g->tile_sum.p);
     k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 2);
@@ -919,10 +935,9 @@ static int build_csr(cp3g* g)
     g->total_occ = total;
     RESERVE(g->occ_ent, (size_t)total + 1, false);
     RESERVE(g->refs_tmp, (size_t)total + 1, false);
-    CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     if (g->ncl) {
-        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_tmp.p, g->refs_tmp.p);
-        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
+        k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_rank.p, g->refs_tmp.p);
+        k_occ_sort_short<<<grid_for(nlit, SORT_LISTS), SORT_LISTS, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
         g->launches += 2;
     }
     // tile table of the full-queue kernels (independent of the sort)
@@ -973,7 +988,7 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
         // device lists are ordered (class, clause index); the reference order is plain ascending clause index
         k_gather_refs<<<grid_for(g->total_occ, 256), 256, 0, g->stream>>>(g->occ_ent.p, g->refs_tmp.p, g->total_occ);
         CK(cudaMemsetAsync(g->counters.p + 1, 0, sizeof(uint32_t), g->stream));
-        k_occ_sort_short<<<grid_for(nlit, 128), 128, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
+        k_occ_sort_short<<<grid_for(nlit, SORT_LISTS), SORT_LISTS, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
         uint32_t nlong = 0;
         CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
