@@ -780,14 +780,17 @@ template <class T> int DevBuf<T>::reserve(size_t n, bool keep, cudaStream_t st)
     if (n <= cap) { return 0; }
     size_t ncap = std::max(n, cap + cap / 2 + 64);
     T* np = nullptr;
-    cudaError_t e = cudaMalloc((void**)&np, ncap * sizeof(T));
+    // stream-ordered allocation from the device's default pool (its release threshold is lifted in cp3g_create):
+    // buffers of a destroyed handle go back to the pool, so the next CPinit/CPpreprocess in the process does not pay
+    // for mapping several hundred MB again
+    cudaError_t e = cudaMallocAsync((void**)&np, ncap * sizeof(T), st);
     if (e != cudaSuccess) { return (int)e; }
-    if (keep && p && used) { cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st); cudaStreamSynchronize(st); }
-    if (p) { cudaFree(p); }
+    if (keep && p && used) { cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st); }
+    if (p) { cudaFreeAsync(p, st); }
     p = np; cap = ncap;
     return 0;
 }
-template <class T> void DevBuf<T>::release() { if (p) { cudaFree(p); } p = nullptr; cap = used = 0; }
+template <class T> void DevBuf<T>::release(cudaStream_t st) { if (p) { cudaFreeAsync(p, st); } p = nullptr; cap = used = 0; }
 
 #define RESERVE(buf, n, keep) do { int _r = (buf).reserve((n), (keep), g->stream); if (_r) { g->fail("cudaMalloc", (cudaError_t)_r); return CP3G_ERR_CUDA; } } while (0)
 
@@ -837,6 +840,10 @@ cp3g* cp3g_create(int device)
     if (cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking) != cudaSuccess) { delete g; return nullptr; }
     cudaEventCreate(&g->ev0); cudaEventCreate(&g->ev1);
     cudaDeviceGetAttribute(&g->num_sms, cudaDevAttrMultiProcessorCount, device);
+    {   // keep freed blocks in the default memory pool instead of returning them to the driver at every sync
+        cudaMemPool_t pool = nullptr; unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
+    }
     if (g->counters.reserve(16, false, g->stream)) { delete g; return nullptr; }
     if (cudaHostAlloc((void**)&g->pin_cnt, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&g->pin_hits, PIN_HITS * sizeof(cp3g_hit), cudaHostAllocDefault) != cudaSuccess) { delete g; return nullptr; }
     return g;
@@ -847,11 +854,12 @@ void cp3g_destroy(cp3g* g)
     if (!g) { return; }
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
-    g->lits.release(); g->hdr.release(); g->occ_off.release(); g->occ_tmp.release(); g->occ_rank.release(); g->tile_sum.release();
-    g->long_lits.release(); g->ovf.release(); g->scratch_u32.release(); g->occ_ent.release(); g->tiles.release(); g->delbits.release(); g->refs_tmp.release();
-    g->sort_tmp.release(); g->req_self.release(); g->req_off.release(); g->req_lits.release(); g->hits.release(); g->counters.release();
-    g->bu0.release(); g->bu1.release(); g->bu2.release(); g->bu3.release(); g->bu4.release(); g->bq0.release();
-    g->bs0.release(); g->bl0.release();
+    g->lits.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->tile_sum.release(g->stream);
+    g->long_lits.release(g->stream); g->ovf.release(g->stream); g->scratch_u32.release(g->stream); g->occ_ent.release(g->stream); g->tiles.release(g->stream); g->delbits.release(g->stream); g->refs_tmp.release(g->stream);
+    g->sort_tmp.release(g->stream); g->req_self.release(g->stream); g->req_off.release(g->stream); g->req_lits.release(g->stream); g->hits.release(g->stream); g->counters.release(g->stream);
+    g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
+    g->bs0.release(g->stream); g->bl0.release(g->stream);
+    cudaStreamSynchronize(g->stream);
     cp3g_nccl_free(g->nccl);
     if (g->pin_cnt) { cudaFreeHost(g->pin_cnt); } if (g->pin_hits) { cudaFreeHost(g->pin_hits); }
     cudaEventDestroy(g->ev0); cudaEventDestroy(g->ev1);

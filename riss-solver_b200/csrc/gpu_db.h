@@ -5,11 +5,11 @@
 #include <stdint.h>
 #include "../../include/cp3b200.h"
 
-// growable device buffer (cudaMalloc; grows by 1.5x, optionally keeping the first `used` elements)
+// growable device buffer (cudaMallocAsync on the handle stream; grows by 1.5x, optionally keeping the first `used` elements)
 template <class T> struct DevBuf {
     T* p = nullptr; size_t cap = 0; size_t used = 0;
     int reserve(size_t n, bool keep, cudaStream_t st);
-    void release();
+    void release(cudaStream_t st);
 };
 
 // NCCL plumbing (nccl_comm.cpp; libnccl is dlopen()ed so the library loads on hosts without it)
