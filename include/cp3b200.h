@@ -133,6 +133,15 @@ int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p
 int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs,
                      const uint32_t* n_refs, const uint64_t* out_off, int32_t* out_lits, size_t nlits);
 
+/* K7: Dense::compress (coprocessor/techniques/Dense.cc:26-238, countLiterals Dense.h:92-121, compressClauses
+ * Dense.cc:406-450).  A variable stays iff it occurs in a live clause or keep[v] != 0 (frozen / kept assignment);
+ * the survivors are renumbered densely in order (mapping[v] = v - #removed before v, UINT32_MAX for removed).
+ * When the formula is not compact (Dense.h:124-127: some variable is removed and frag_percent <= 1 + removed*100/nvars)
+ * every literal of every live clause is rewritten in HBM and the literal pool (nlits ints, same offsets as uploaded /
+ * appended) is copied to lits_out; *compressed tells whether that happened.  The device then holds nvars_new variables. */
+int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping, uint32_t* nvars_new, int* compressed,
+               int32_t* lits_out, size_t nlits);
+
 /* multi-GPU plumbing: NCCL communicator over the ranks' devices (bootstrap id from rank 0) */
 int cp3g_nccl_unique_id(void* out128);
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);

@@ -53,6 +53,7 @@ struct cp3o {
     int64_t bve_limit;
     int bve_unlimited, bve_strength, bve_gates, bve_force_gates, bve_fdepOnly, bve_heap;
     int bve_cgrow, bve_cgrow_t, bve_BCElim, bve_heap_updates, bve_early, bce_only;
+    int opt_dense, dense_frag, dense_keep_set;   /* CP3Config.cc:100,344,345 */
     double gc_frac;
     /* solver side (riss/core/Solver.h): assignment, trail, clauses vector, arena accounting */
     int nvars, ok, qhead;
@@ -85,6 +86,9 @@ struct cp3o {
     uint32_t* ma; uint32_t ma_step;             /* data.ma, MarkArray SolverTypes.h:1120 */
     struct { int cr, l; } *occ_upd; int occ_upd_n, occ_upd_cap; /* strength_occ_updates */
     ivec sub_occ_updates;
+    /* Dense / Riss::Compression (riss/utils/Compression.h): mapping[orig var] = compressed var or -1 (removed),
+     * value of the removed assigned variables; empty until a compression happened */
+    int comp_nvars; int* comp_map; unsigned char* comp_val;
 };
 
 /* ------------------------------------------------------------------ basics */
@@ -1049,6 +1053,88 @@ static void init_data(cp3o* o)
     o->data_ready = 1;
 }
 
+/* ------------------------------------------------------------------ Dense::compress (techniques/Dense.cc:26-238)
+ * Variables that occur in no clause (and are not frozen) are dropped, the others are renumbered densely
+ * (mapping[var] = var - #dropped before it), every clause literal is rewritten, assigned dropped variables move
+ * from the trail into the compression object.  Called as the very last step of preprocess() (Coprocessor.cc:492-496). */
+static void dense_compress(cp3o* o)
+{
+    if (propagation_process(o, 0, 0, VAR_UNDEF) == L_FALSE) { o->ok = 0; }      /* Dense.cc:28 */
+    if (!o->ok) { return; }
+    const int n = o->nvars;
+    unsigned* count = (unsigned*)calloc((size_t)(n > 0 ? n : 1), sizeof(unsigned));
+    for (int i = 0; i < o->clauses.n; ++i) {                                      /* countLiterals, Dense.h:92-121 */
+        const int c = o->clauses.v[i];
+        if (o->cflag[c] & F_DEL) { continue; }
+        const int* l = CL(o, c);
+        for (int j = 0; j < o->csize[c]; ++j) { count[LVAR(l[j])]++; }
+    }
+    int* mapping = (int*)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+    unsigned char* val = (unsigned char*)malloc((size_t)(n > 0 ? n : 1));
+    int diff = 0;
+    for (int v = 0; v < n; ++v) {                                                 /* Dense.cc:49-87 */
+        mapping[v] = -1; val[v] = L_UNDEF;
+        if (count[v] != 0 || o->frozen[v] || (o->dense_keep_set && o->assigns[v] != L_UNDEF)) { mapping[v] = v - diff; }
+        else { diff++; if (o->assigns[v] != L_UNDEF) { val[v] = o->assigns[v]; } }
+    }
+    /* isCompact, Dense.h:124-127 (integer division as in the reference) */
+    if (diff == 0 || ((double)o->dense_frag > 1.0 + (double)(((unsigned)diff * 100u) / (unsigned)n))) {
+        free(count); free(mapping); free(val);
+        return;
+    }
+    o->comp_nvars = n; o->comp_map = mapping; o->comp_val = val;                /* compression.update */
+    for (int i = 0; i < o->clauses.n; ++i) {                                      /* compressClauses, Dense.cc:406-450 */
+        const int c = o->clauses.v[i];
+        if (o->cflag[c] & F_DEL) { continue; }
+        int* l = CL(o, c);
+        for (int j = 0; j < o->csize[c]; ++j) { l[j] = 2 * mapping[LVAR(l[j])] + (l[j] & 1); }
+    }
+    int j = 0;                                                                    /* trail, Dense.cc:121-150 */
+    for (int i = 0; i < o->trail.n; ++i) {
+        const int x = o->trail.v[i], v = LVAR(x);
+        if (count[v] != 0 || o->frozen[v] || o->dense_keep_set) { o->trail.v[j++] = 2 * mapping[v] + (x & 1); }
+        else { o->assigns[v] = L_UNDEF; }
+    }
+    o->trail.n = j; o->qhead = j;                                                 /* propagation.reset */
+    for (int v = 0; v < n; ++v) {                                                 /* moveVar, CoprocessorTypes.h:693-729 */
+        const int to = mapping[v];
+        if (to >= 0 && to != v) { o->assigns[to] = o->assigns[v]; o->assigns[v] = L_UNDEF; o->frozen[to] = o->frozen[v]; o->frozen[v] = 0; }
+    }
+    o->nvars = n - diff;
+    free(count);
+}
+
+/* Dense::decompress (Dense.cc:240-318): model over the compressed variables -> model over the original ones.
+ * model[v] in {L_TRUE, L_FALSE}; the caller provides room for cp3o_model_vars() entries. */
+int cp3o_model_vars(const cp3o* o) { return o->comp_map ? o->comp_nvars : o->nvars; }
+void cp3o_decompress_model(const cp3o* o, unsigned char* model, int have)
+{
+    if (!o->comp_map) { return; }
+    for (int v = have; v < o->comp_nvars; ++v) { model[v] = L_FALSE; }            /* growTo(nvars, l_False) */
+    for (int v = o->comp_nvars - 1; v >= 0; --v) {
+        const int c = o->comp_map[v];
+        if (c < 0) { if (o->comp_val[v] != L_UNDEF) { model[v] = o->comp_val[v]; } }
+        else if (c != v) { model[v] = model[c]; }
+    }
+}
+/* Preprocessor::extendModel (Coprocessor.cc:1214-1240): Dense::decompress, then CoprocessorData::extendModel
+ * (CoprocessorTypes.h:1665-1764) - walk the undo stack backwards; an entry none of whose literals is satisfied gets
+ * its first literal (the blocking literal) satisfied.  `model` has room for cp3o_model_vars() entries. */
+void cp3o_extend_model(const cp3o* o, unsigned char* model, int have)
+{
+    const int n = cp3o_model_vars(o);
+    cp3o_decompress_model(o, model, have);
+    if (!o->comp_map) { for (int v = have; v < n; ++v) { model[v] = L_TRUE; } }
+    for (int v = 0; v < n; ++v) { if (model[v] == L_UNDEF) { model[v] = L_TRUE; } }
+    for (int i = o->undo.n - 1; i >= 0; --i) {
+        const int d = o->undo.v[i];
+        if (d == 0) { const int s = o->undo.v[i + 1]; model[(s < 0 ? -s : s) - 1] = s < 0 ? L_FALSE : L_TRUE; continue; }
+        const int v = (d < 0 ? -d : d) - 1;
+        if (model[v] == (d < 0 ? L_FALSE : L_TRUE)) { while (o->undo.v[i] != 0) { --i; } }
+    }
+}
+int cp3o_compressed_var(const cp3o* o, int v) { return o->comp_map ? (v < o->comp_nvars ? o->comp_map[v] : -1) : v; }
+
 void cp3o_init_only(cp3o* o)
 {
     if (!solver_simplify(o)) { return; }
@@ -1080,6 +1166,7 @@ void cp3o_preprocess(cp3o* o)
         if (!o->ok) { break; }
     }
     if (o->ok && has_to_propagate(o)) { propagation_process(o, 0, 0, VAR_UNDEF); }
+    if (o->opt_dense) { dense_compress(o); }                                      /* Coprocessor.cc:492-496 */
     /* reSetupSolver, CoprocessorTypes.h:937-1008: drop deleted clauses, keep order */
     if (o->ok) { filter_deleted(o, &o->clauses); }
 }
@@ -1191,7 +1278,8 @@ int cp3o_option(cp3o* o, const char* opt)
     BOPT("cp3_limited", limited) BOPT("cp3_strength", strength)
     BOPT("bve_unlimited", bve_unlimited) BOPT("bve_strength", bve_strength) BOPT("bve_gates", bve_gates)
     BOPT("bve_force_gates", bve_force_gates) BOPT("bve_fdepOnly", bve_fdepOnly) BOPT("bve_BCElim", bve_BCElim)
-    BOPT("bve_early", bve_early) BOPT("bce_only", bce_only)
+    BOPT("bve_early", bve_early) BOPT("bce_only", bce_only) BOPT("dense", opt_dense) BOPT("cp3_keep_set", dense_keep_set)
+    IOPT("cp3_dense_frag", dense_frag)
     IOPT("cp3_iters", iters) IOPT("cp3_vars", cp3_vars) IOPT("cp3_cls", cp3_cls) IOPT("cp3_lits", cp3_lits)
     IOPT("cp3_call_inc", call_inc) IOPT("cp3_bve_limit", bve_limit) IOPT("cp3_bve_heap", bve_heap)
     IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t) IOPT("bve_heap_updates", bve_heap_updates)
@@ -1211,6 +1299,6 @@ void cp3o_free(cp3o* o)
     free(o->pool); free(o->cstart); free(o->csize); free(o->cflag);
     free(o->trail.v); free(o->clauses.v); free(o->cur.v); free(o->subq.v); free(o->strq.v); free(o->undo.v);
     free(o->heap); free(o->hidx); free(o->pos_stats.v); free(o->neg_stats.v); free(o->resolvent.v);
-    free(o->touched.v); free(o->occ_upd); free(o->sub_occ_updates.v);
+    free(o->touched.v); free(o->occ_upd); free(o->sub_occ_updates.v); free(o->comp_map); free(o->comp_val);
     free(o);
 }

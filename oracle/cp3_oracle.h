@@ -36,6 +36,13 @@ size_t  cp3o_ntrail(const cp3o* o);
 /* extension (undo) stack, DIMACS literals, 0 = entry separator (CoprocessorTypes.h:1615-1655) */
 size_t  cp3o_undo(const cp3o* o, int32_t* out, size_t cap);
 int64_t cp3o_stat(const cp3o* o, const char* name);
+/* -dense (Dense.cc): number of variables a model must cover after decompression, the decompression itself
+ * (model[v] = 0 true / 1 false, `have` entries filled in compressed numbering) and the variable map (-1 = removed) */
+int     cp3o_model_vars(const cp3o* o);
+void    cp3o_decompress_model(const cp3o* o, unsigned char* model, int have);
+int     cp3o_compressed_var(const cp3o* o, int orig_var);
+/* Preprocessor::extendModel (Coprocessor.cc:1214-1240): decompress, then replay the undo stack */
+void    cp3o_extend_model(const cp3o* o, unsigned char* model, int have);
 
 /* --- kernel-level oracles on a pristine snapshot (after initializePreprocessor + sortClauses) --- */
 /* prepare the occurrence-list data base without running any technique */

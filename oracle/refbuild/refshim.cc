@@ -182,6 +182,17 @@ int main(int argc, char** argv)
     fprintf(fo, "undo %d", (int)undo.size());
     for (size_t i = 0; i < undo.size(); ++i) { fprintf(fo, " %d", undo[i] == lit_Undef ? 0 : toDimacs(undo[i])); }
     fprintf(fo, "\n");
+    // model extension (Preprocessor::extendModel, Coprocessor.cc:1214: Dense::decompress + undo replay) applied to a
+    // fixed pseudo-random assignment of the simplified formula's variables that agrees with the trail
+    if (S->okay()) {
+        vec<lbool> model;
+        for (int v = 0; v < S->nVars(); ++v) { model.push(((((unsigned)(v + 1)) * 2654435761u) >> 13) & 1u ? l_True : l_False); }
+        for (int i = 0; i < S->trail.size(); ++i) { model[var(S->trail[i])] = sign(S->trail[i]) ? l_False : l_True; }
+        pp->extendModel(model);
+        fprintf(fo, "xmodel %d", model.size());
+        for (int v = 0; v < model.size(); ++v) { fprintf(fo, " %d", model[v] == l_True ? 1 : 0); }
+        fprintf(fo, "\n");
+    }
     fclose(fo);
     return 0;
 }

@@ -27,7 +27,7 @@ CP_SYMBOLS = [
 CP3G_SYMBOLS = [
     "cp3g_device_count", "cp3g_create", "cp3g_destroy", "cp3g_last_error", "cp3g_upload", "cp3g_upload_packed", "cp3g_build",
     "cp3g_download_occ", "cp3g_set_deleted", "cp3g_shrink", "cp3g_append", "cp3g_scan", "cp3g_scan_all", "cp3g_bve_pairs",
-    "cp3g_bve_resolve", "cp3g_nccl_unique_id", "cp3g_nccl_init", "cp3g_counter",
+    "cp3g_bve_resolve", "cp3g_dense", "cp3g_nccl_unique_id", "cp3g_nccl_init", "cp3g_counter",
 ]
 
 

@@ -87,7 +87,7 @@ int64_t CPstat(void* p, const char* name) { return H(p)->eng.stat(name); }
 int CPsetDistributed(void* p, int rank, int world, const void* id) { return H(p)->eng.setDistributed(rank, world, id); }
 
 void CPfreezeVariable(void* p, int variable) { H(p)->eng.freeze(variable < 0 ? -variable : variable); }
-int CPgetReplaceLiteral(void*, int oldLit) { return oldLit; }    // no Dense / EE on this path: identity
+int CPgetReplaceLiteral(void* p, int oldLit) { const int r = H(p)->eng.importLit(oldLit); return r == 0 ? oldLit : r; }   // libcoprocessorc.cc:198-203
 
 void CPresetModel(void* p) { H(p)->model.clear(); H(p)->modelLit = 0; }
 void CPpushModelBool(void* p, int pol) { H(p)->model.push_back(pol == 0 ? cp3::L_FALSE : cp3::L_TRUE); }

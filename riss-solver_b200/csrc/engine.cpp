@@ -38,7 +38,8 @@ int Options::parse(const char* o)
     BOPT("cp3_limited", limited) BOPT("cp3_strength", strength) BOPT("cp3_stats", stats)
     BOPT("bve_unlimited", bve_unlimited) BOPT("bve_strength", bve_strength) BOPT("bve_gates", bve_gates)
     BOPT("bve_force_gates", bve_force_gates) BOPT("bve_fdepOnly", bve_fdepOnly) BOPT("bve_BCElim", bve_BCElim)
-    BOPT("bve_early", bve_early) BOPT("bce_only", bce_only)
+    BOPT("bve_early", bve_early) BOPT("bce_only", bce_only) BOPT("dense", dense) BOPT("cp3_keep_set", dense_keep_set)
+    IOPT("cp3_dense_frag", dense_frag)
     IOPT("cp3_iters", iters) IOPT("cp3_vars", cp3_vars) IOPT("cp3_cls", cp3_cls) IOPT("cp3_lits", cp3_lits)
     IOPT("cp3_sub_limit", sub_limit) IOPT("cp3_str_limit", str_limit) IOPT("cp3_call_inc", call_inc)
     IOPT("cp3_bve_limit", bve_limit) IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t)
@@ -54,7 +55,8 @@ int Options::parse(const char* o)
          name == "cp3_sub_inpInc" || name == "cp3_bve_inpInc" || name == "cp3_bve_verbose" || name == "cp3_bve_learnt_growth" ||
          name == "cp3_bve_resolve_learnts" || name == "cp3_verbose" || name == "cp3_susi_vars" || name == "cp3_susi_cls" ||
          name == "cp3_susi_lits" || name == "cp3_bve_vars" || name == "cp3_bve_cls" || name == "cp3_bve_lits") && eq) { return 1; }
-    if (name == "par_bve_min_upd" || name == "dense" || name == "inprocess") { return neg ? 1 : -1; }
+    if (name == "par_bve_min_upd" || name == "inprocess" || name == "dense_inp") { return neg ? 1 : -1; }
+    if (name == "cp3_dense_debug" && eq) { return 1; }
 #undef BOPT
 #undef IOPT
     return 0;
@@ -1584,8 +1586,12 @@ Engine::PairEnt& Engine::pairsFor(int v)
         const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i];
         int res = 0;
         for (uint64_t k = pair_off[i]; k < pair_off[i + 1]; ++k) { res += sizes[k] > 1; }
+        // the global growth allowance (bve_cgrow_t - totallyAdded, BVE.cc:532-540) is shared by ALL later
+        // eliminations: taken at face value it would predict every variable of the batch as eliminable and spend
+        // the prefetch budget on resolvents nobody asks for.  Only a small part of it is granted per variable; the
+        // few clause-increasing eliminations beyond that fetch their resolvents on demand.
         int slack = opt.bve_cgrow;
-        if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { slack += std::max(0, opt.bve_cgrow_t - bve_totallyAdded); }
+        if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { slack += std::min(8, std::max(0, opt.bve_cgrow_t - bve_totallyAdded)); }
         if (res > (int)(np + nn) + slack || roff.back() > (32u << 20)) { continue; }
         want[i] = 1;
         for (uint32_t a = 0; a < np; ++a) for (uint32_t b = 0; b < nn; ++b) {
@@ -1779,12 +1785,12 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
             }
         } else if (!prs.empty()) {
             ++n_resolve_batches;
+            flushDevice();                       // only the on-demand fetch needs the device copy up to date
             int64_t t0 = now_ns();
             if (cp3g_bve_resolve(gpu, (uint32_t)prs.size(), vv.data(), pr.data(), nr.data(), off.data(), rl.data(), off.back()) != CP3G_OK) { die("bve_resolve failed"); }
             host_ns_gpuwait += now_ns() - t0;
         }
     };
-    flushDevice();
     fetch(0, 0);
     size_t k = 0;
     for (uint32_t cp = 0; cp < positive.n; ++cp) {
@@ -1808,7 +1814,6 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
                     t_bve.modified = t_bve.modified || t_up.modified;
                     if (positive.n == 0 || negative.n == 0) { return L_UNDEF; }
                     const bool pdel = (C[p].flag & F_DEL) != 0;
-                    flushDevice();
                     pe = &pairsFor(v);
                     // continue behind (cp,cn); a deleted p ends its row (BVE.cc:942-944)
                     if (pdel) { fetch(cp + 1, 0); k = 0; break; }
@@ -1986,6 +1991,54 @@ void Engine::initData()
     data_ready = true;
 }
 
+// Dense::compress, coprocessor/techniques/Dense.cc:26-238.  The data-parallel part - which variables still occur,
+// the dense renumbering (a prefix sum) and the rewrite of every clause literal - runs on the device (K7,
+// cp3g_dense); the host moves the per-variable solver state and the trail like CoprocessorData::moveVar
+// (CoprocessorTypes.h:693-729) and keeps the map for Dense::decompress.
+void Engine::denseCompress()
+{
+    if (propagationProcess(false, false, VAR_UNDEF) == L_FALSE) { ok = false; }      // Dense.cc:28
+    if (!ok || nvars == 0) { return; }
+    flushDevice();
+    const int n = nvars;
+    std::vector<uint8_t> keep((size_t)n, 0);
+    for (int v = 0; v < n; ++v) { keep[v] = frozen[v] || (opt.dense_keep_set && assigns[v] != L_UNDEF); }
+    std::vector<uint32_t> mapping((size_t)n, 0);
+    uint32_t nv_new = (uint32_t)n; int compressed = 0;
+    int64_t t0 = now_ns();
+    if (cp3g_dense(gpu, keep.data(), opt.dense_frag, mapping.data(), &nv_new, &compressed, pool.data(), pool.size()) != CP3G_OK) { die("dense failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    if (!compressed) { return; }                                                     // isCompact, Dense.h:124-127
+    comp_map.assign((size_t)n, -1); comp_val.assign((size_t)n, (uint8_t)L_UNDEF);
+    for (int v = 0; v < n; ++v) {
+        if (mapping[v] != 0xffffffffu) { comp_map[v] = (int32_t)mapping[v]; }
+        else if (assigns[v] != L_UNDEF) { comp_val[v] = assigns[v]; }
+    }
+    // trail (Dense.cc:121-150): literals of removed variables leave it - their value lives in the compression
+    size_t j = 0;
+    for (size_t i = 0; i < trail.size(); ++i) {
+        const int x = trail[i], v = x >> 1;
+        if (comp_map[v] >= 0) { trail[j++] = 2 * comp_map[v] + (x & 1); }
+        else { assigns[v] = L_UNDEF; }
+    }
+    trail.resize(j); qhead = (int)j;                                                 // propagation.reset
+    for (int v = 0; v < n; ++v) {                                                    // moveVar
+        const int to = comp_map[v];
+        if (to >= 0 && to != v) { assigns[to] = assigns[v]; assigns[v] = L_UNDEF; frozen[to] = frozen[v]; frozen[v] = 0; }
+    }
+    nvars = (int)nv_new;
+    assigns.resize((size_t)nvars); frozen.resize((size_t)nvars);
+    data_ready = false;                                                              // occurrence data is void (data.destroy follows)
+}
+
+int Engine::importLit(int d) const
+{
+    const int v = (d < 0 ? -d : d) - 1;
+    if (comp_map.empty()) { return d; }
+    if (v >= (int)comp_map.size() || comp_map[v] < 0) { return 0; }
+    return d < 0 ? -(comp_map[v] + 1) : comp_map[v] + 1;
+}
+
 void Engine::preprocess()
 {
     // Coprocessor.cc:1002-1006: data.nVars() is still 0 before data.init() and nTotLits() only counts learnt
@@ -2014,6 +2067,7 @@ void Engine::preprocess()
         if (!ok) { break; }
     }
     if (ok && hasToPropagate()) { propagationProcess(false, false, VAR_UNDEF); }
+    if (opt.dense) { denseCompress(); }           // very last step, Coprocessor.cc:492-496
     if (ok) { filterDeleted(clauses); }           // reSetupSolver, CoprocessorTypes.h:937-1008
     if (opt.stats) {
         fprintf(stderr, "c [STAT] SuSi(1) %d cls,  with %d lits, %d strengthed\n", subsumedClauses, subsumedLiterals, removedLiterals);
@@ -2049,9 +2103,32 @@ size_t Engine::undoStack(int32_t* out, size_t cap) const
 // backwards; an entry [blocking literal, rest...] that is not satisfied flips its blocking literal.
 void Engine::extendModel(std::vector<uint8_t>& model) const
 {
+    if (!comp_map.empty()) {
+        // Dense::decompress, Dense.cc:240-318: backwards, because names only grow on the way back
+        const size_t n0 = comp_map.size();
+        if (model.size() < n0) { model.resize(n0, (uint8_t)L_FALSE); }
+        for (long v = (long)n0 - 1; v >= 0; --v) {
+            const int c = comp_map[(size_t)v];
+            if (c < 0) { if (comp_val[(size_t)v] != L_UNDEF) { model[(size_t)v] = comp_val[(size_t)v]; } }
+            else if (c != v) { model[(size_t)v] = model[(size_t)c]; }
+        }
+        for (auto& m : model) { if (m == L_UNDEF) { m = L_TRUE; } }
+        // the trail is in compressed names; its values were copied above with the variables they belong to
+        const std::vector<int32_t>& cm = comp_map;
+        std::vector<int> inv((size_t)nvars, -1);
+        for (size_t v = 0; v < n0; ++v) { if (cm[v] >= 0) { inv[(size_t)cm[v]] = (int)v; } }
+        for (int x : trail) { if (inv[(size_t)(x >> 1)] >= 0) { model[(size_t)inv[(size_t)(x >> 1)]] = (uint8_t)(x & 1); } }
+        extendByUndo(model);
+        return;
+    }
     if (model.size() < (size_t)nvars) { model.resize((size_t)nvars, L_TRUE); }
     for (auto& m : model) { if (m == L_UNDEF) { m = L_TRUE; } }
     for (int x : trail) { model[x >> 1] = (uint8_t)(x & 1); }
+    extendByUndo(model);
+}
+
+void Engine::extendByUndo(std::vector<uint8_t>& model) const
+{
     long i = (long)undo.size() - 1;
     while (i >= 0) {
         long j = i;

@@ -42,6 +42,7 @@ struct Options {
     int bve_heap = 0, bve_cgrow = 0, bve_cgrow_t = 1000, bve_heap_updates = 1;
     int threads = 0;
     bool stats = false;
+    bool dense = false, dense_keep_set = false; int dense_frag = 0;   // -dense, -cp3_keep_set, -cp3_dense_frag (CP3Config.cc:100,344,345)
     double gc_frac = 0.20;
     int device = 0;              // -cp3_gpu_device=N
     // returns 1 known & applied, 0 unknown, -1 known but unsupported value on the GPU path
@@ -71,6 +72,9 @@ public:
     void addStream(const int32_t* s, size_t n);
     void freeze(int dimacsVar);
     void preprocess();
+    // Dense (coprocessor/techniques/Dense.cc): DIMACS literal of the compressed formula for a literal of the original
+    // one (Preprocessor::importLit, Coprocessor.cc:1174-1187; 0 = no replacement)
+    int importLit(int dimacsLit) const;
     bool okay() const { return ok; }
     int nVars() const { return nvars; }
     size_t output(int32_t* out, size_t cap) const;
@@ -86,6 +90,11 @@ public:
 private:
     // ---------------- solver state
     int nvars = 0; bool ok = true; int qhead = 0;
+    // Riss::Compression (riss/utils/Compression.h): mapping[original var] = compressed var or -1, and the values
+    // of the removed assigned variables; empty until Dense compressed the formula
+    std::vector<int32_t> comp_map; std::vector<uint8_t> comp_val;
+    void denseCompress();
+    void extendByUndo(std::vector<uint8_t>& model) const;
     std::vector<uint8_t> assigns, frozen;
     std::vector<int> trail;
     std::vector<int32_t> pool;                       // literal pool (codes)

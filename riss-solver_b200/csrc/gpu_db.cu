@@ -752,6 +752,40 @@ __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits
     hdr[ids[i]] = h;
 }
 
+// ------------------------------------------------------------------------------------------ K7 Dense
+// variable v occurs in a live clause (countLiterals, Dense.h:92-121; only "occurs at all" matters)
+__global__ void k_dense_mark(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n, uint32_t* __restrict__ keep)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = hdr[i];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    for (uint32_t k = 0; k < sz; ++k) { keep[((uint32_t)lits[h.start + k]) >> 1] = 1u; }      // same value from every writer
+}
+__global__ void k_dense_keep(const unsigned char* __restrict__ extra, uint32_t nvars, uint32_t* __restrict__ keep)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nvars && extra[v]) { keep[v] = 1u; }
+}
+// mapping[v] = exclusive prefix sum of keep[] where keep[v], UINT32_MAX otherwise (Dense.cc:49-87: var - diff)
+__global__ void k_dense_map(const uint32_t* __restrict__ keep, const uint32_t* __restrict__ pre, uint32_t nvars, uint32_t* __restrict__ mapping)
+{
+    uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < nvars) { mapping[v] = keep[v] ? pre[v] : 0xffffffffu; }
+}
+// compressClauses, Dense.cc:406-450: literals of live clauses, polarity kept.  The map is monotone, so the
+// clauses stay sorted.
+__global__ void k_dense_rewrite(const ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits, uint32_t n, const uint32_t* __restrict__ mapping)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = hdr[i];
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    for (uint32_t k = 0; k < sz; ++k) { const uint32_t x = (uint32_t)lits[h.start + k]; lits[h.start + k] = (int32_t)(2u * mapping[x >> 1] + (x & 1u)); }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 struct cp3g {
     int device = 0; int num_sms = 148;
@@ -1067,8 +1101,11 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
     CK(cudaMemcpyAsync(g->ovf.p, g->ovf_host.data(), g->ovf_host.size() * 4, cudaMemcpyHostToDevice, g->stream));
     g->nlits += nlits; g->ncl += n; g->lits.used = g->nlits; g->hdr.used = g->ncl;
     g->h2d += (int64_t)(nlits * 4 + (size_t)n * sizeof(ClauseHdr) + g->ovf_host.size() * 4);
-    // many young clauses make the brute-force part of k_scan expensive: fold them into the CSR
-    if (g->ovf_host.size() > 2048) { return build_csr(g); }
+    // many young clauses make the brute-force part of k_scan expensive: fold them into the CSR.  A rebuild costs
+    // time proportional to the whole data base (20 ms at 54 M clauses), the brute force time proportional to the
+    // overflow list per request - so the list may grow with the data base: ncl/256, within [2048, 65536].
+    const size_t fold_at = std::min<size_t>(65536, std::max<size_t>(2048, g->ncl / 256));
+    if (g->ovf_host.size() > fold_at) { return build_csr(g); }
     return CP3G_OK;
 }
 
@@ -1301,6 +1338,53 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
     return CP3G_OK;
 }
 
+int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping, uint32_t* nvars_new, int* compressed,
+               int32_t* lits_out, size_t nlits)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    const uint32_t nv = g->nvars;
+    if (compressed) { *compressed = 0; }
+    if (nvars_new) { *nvars_new = nv; }
+    if (nv == 0) { return CP3G_OK; }
+    if (nlits != g->nlits) { g->err = "cp3g_dense: host and device literal pools differ in size"; return CP3G_ERR_ARG; }
+    const uint32_t ntiles = (nv + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    RESERVE(g->bu0, (size_t)nv + 2, false); RESERVE(g->bu1, (size_t)nv + 2, false); RESERVE(g->bu2, (size_t)nv + 2, false);
+    RESERVE(g->tile_sum, (size_t)ntiles + 1, false);
+    RESERVE(g->scratch_u32, ((size_t)nv + 3) / 4 + 1, false);
+    KTimer t(g);
+    CK(cudaMemsetAsync(g->bu0.p, 0, ((size_t)nv + 2) * sizeof(uint32_t), g->stream));
+    CK(cudaMemcpyAsync(g->scratch_u32.p, keep, nv, cudaMemcpyHostToDevice, g->stream));
+    if (g->ncl) { k_dense_mark<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->bu0.p); g->launches++; }
+    k_dense_keep<<<grid_for(nv, 256), 256, 0, g->stream>>>(reinterpret_cast<const unsigned char*>(g->scratch_u32.p), nv, g->bu0.p);
+    k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(g->bu0.p, g->bu1.p, nv + 1, g->tile_sum.p);
+    k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 2);
+    k_scan_add<<<ntiles, SCAN_T, 0, g->stream>>>(g->bu1.p, nv + 1, g->tile_sum.p);
+    k_dense_map<<<grid_for(nv, 256), 256, 0, g->stream>>>(g->bu0.p, g->bu1.p, nv, g->bu2.p);
+    g->launches += 5;
+    uint32_t kept = 0;
+    CK(cudaMemcpyAsync(&kept, g->counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(mapping, g->bu2.p, (size_t)nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->h2d += nv; g->d2h += (int64_t)nv * 4 + 4;
+    const uint32_t diff = nv - kept;
+    // isCompact, Dense.h:124-127 (integer division as there)
+    const bool compact = diff == 0 || ((double)frag_percent > 1.0 + (double)((diff * 100u) / nv));
+    if (!compact) {
+        if (g->ncl) { k_dense_rewrite<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->bu2.p); g->launches++; }
+        CK(cudaMemcpyAsync(lits_out, g->lits.p, nlits * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+        g->d2h += (int64_t)nlits * 4;
+        g->nvars = kept; g->dirty_since_build = true;            // signatures and occurrence lists are void now
+        if (compressed) { *compressed = 1; }
+        if (nvars_new) { *nvars_new = kept; }
+    }
+    t.stop();
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    t.collect();
+    return CP3G_OK;
+}
+
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128)
 {
     if (!g) { return CP3G_ERR_NODEVICE; }
@@ -1324,6 +1408,8 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "scan_ns")) { return g->scan_ns; }
     if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }
+    if (!strcmp(name, "nlits")) { return (int64_t)g->nlits; }
+    if (!strcmp(name, "nvars")) { return g->nvars; }
     if (!strcmp(name, "total_occ")) { return g->total_occ; }
     return -1;
 }

@@ -2,7 +2,7 @@
 tests/mock) vs the CPU oracle.  python tests/fuzz_engine.py [rounds] [seed]"""
 import os, subprocess, sys
 import numpy as np
-from harness import run_oracle, compare, load_gen, Result, STAT_NAMES, ROOT
+from harness import run_oracle, compare, load_gen, Result, STAT_NAMES, ROOT, engine_xmodel
 import riss_solver_b200 as rs
 from fuzz_oracle import OPTSETS, random_instance
 
@@ -21,6 +21,7 @@ def run_engine(stream, opts, lib=None) -> Result:
     out = cp.output_stream(); nt = cp.output_units()
     res = Result(int(cp.ok()), cp.n_vars(), out[0:2 * nt:2].copy(), out[2 * nt:].copy(), cp.undo(),
                  {k: cp.stat(k) for k in STAT_NAMES})
+    res.xmodel = engine_xmodel(cp, res.nvars, res.trail)
     res.extra = {k: cp.stat(k) for k in ("scan_batches", "scan_ondemand", "queue_fast", "queue_slow", "pair_batches", "resolve_batches", "gpu_launches")}
     cp.close()
     return res

@@ -21,6 +21,9 @@ OPTSETS = [
     ["-enabled_cp3", "-subsimp", "-bve", "-bve_heap_updates=0"],
     ["-enabled_cp3", "-subsimp", "-bve", "-bve_early"],
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-cp3_iters=2"],
+    ["-enabled_cp3", "-up", "-subsimp", "-bve", "-dense", "-no-cp3_limited"],
+    ["-enabled_cp3", "-subsimp", "-dense"],
+    ["-enabled_cp3", "-up", "-subsimp", "-bve", "-dense", "-cp3_dense_frag=20"],
 ]
 
 

@@ -28,6 +28,7 @@ NOSTR = ["-enabled_cp3", "-subsimp", "-no-cp3_strength"]
 FULL = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]
 BVE = ["-enabled_cp3", "-subsimp", "-bve"]
 LOCAL = ["-enabled_cp3", "-subsimp", "-bve", "-no-bve_gates", "-bve_cgrow=0", "-bve_cgrow_t=0", "-no-cp3_limited"]
+DENSE = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-dense", "-no-cp3_limited"]      # Riss427-style: ... then Dense
 
 cases = []
 
@@ -36,12 +37,13 @@ def add(name, stream, opts):
     r = run_ref(stream, opts)
     cases.append({"name": name, "options": opts, "input": np.asarray(stream).tolist(), "ok": r.ok, "nvars": r.nvars,
                   "trail": r.trail.tolist(), "stream": r.stream.tolist(), "undo": r.undo.tolist(),
+                  "xmodel": None if r.xmodel is None else r.xmodel.tolist(),
                   "stats": {k: int(r.stats[k]) for k in STAT_NAMES if k in r.stats}})
 
 
 ref_cnfs = "/root/reference/regression/cnfs"
 for f in ("sat", "unsat"):
-    for tag, o in (("susi", SUSI), ("bve", BVE), ("full", FULL)):
+    for tag, o in (("susi", SUSI), ("bve", BVE), ("full", FULL), ("dense", DENSE)):
         add(f"regression_{f}_{tag}", dimacs(os.path.join(ref_cnfs, f + ".cnf")), o)
 # the hand vectors of SURVEY.md 8(c): duplicate tie rule, order dependence of strengthening
 add("dup_tie_last_survives", np.array([1, 2, 0, 3, 4, 0, 1, 2, 0, 1, 2, 5, 0, 5, 6, 0], np.int32), NOSTR)
@@ -50,12 +52,14 @@ add("double_decrement_counts", np.array([1, 2, 0, 1, 2, 3, 0, 3, 4, 0], np.int32
 for seed in (1, 2, 3):
     l, s = gen.random_ksat(300, 1278, 3, seed=seed, dup=0.04, sup=0.06, flip=0.06)
     st = gen.csr_to_stream(l, s)
-    for tag, o in (("susi", SUSI), ("nostr", NOSTR), ("full", FULL), ("local", LOCAL)):
+    for tag, o in (("susi", SUSI), ("nostr", NOSTR), ("full", FULL), ("local", LOCAL), ("dense", DENSE)):
         add(f"planted3sat_s{seed}_{tag}", st, o)
 l, s = gen.community_ksat(400, 1800, seed=20260001)
 st = gen.csr_to_stream(l, s)
-for tag, o in (("susi", SUSI), ("full", FULL), ("bve", BVE)):
+for tag, o in (("susi", SUSI), ("full", FULL), ("bve", BVE), ("dense", DENSE), ("dense_frag", DENSE + ["-cp3_dense_frag=30"])):
     add(f"community_{tag}", st, o)
+# variable gaps in the input: Dense without any simplification
+add("gaps_dense_only", np.array([3, -7, 0, 7, 12, -20, 0, -3, 20, 0], np.int32), ["-enabled_cp3", "-dense"])
 l, s = gen.random_ksat(200, 900, 3, seed=777, zipf_s=1.1)
 add("zipf_susi", gen.csr_to_stream(l, s), SUSI)
 json.dump({"generator": "tests/golden/make_golden.py", "reference": "nmanthey/riss-solver via oracle/_ref/refshim", "cases": cases},

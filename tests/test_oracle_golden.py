@@ -15,8 +15,9 @@ ANT = json.load(open(os.path.join(HERE, "golden", "anticipate.json")))["cases"]
 
 
 def golden_result(c) -> Result:
+    xm = c.get("xmodel")
     return Result(c["ok"], c["nvars"], np.array(c["trail"], np.int32), np.array(c["stream"], np.int32),
-                  np.array(c["undo"], np.int32), dict(c["stats"]))
+                  np.array(c["undo"], np.int32), dict(c["stats"]), None if xm is None else np.array(xm, np.uint8))
 
 
 @pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
