@@ -80,6 +80,7 @@ def load(path: str | None = None) -> C.CDLL:
     L.cp3g_scan_all.restype = C.c_int
     L.cp3g_bve_pairs.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, vp, vp]; L.cp3g_bve_pairs.restype = C.c_int
     L.cp3g_bve_resolve.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, vp, i32p, C.c_size_t]; L.cp3g_bve_resolve.restype = C.c_int
+    L.cp3g_dense.argtypes = [vp, vp, C.c_int, u32p, u32p, C.POINTER(C.c_int), i32p, C.c_size_t]; L.cp3g_dense.restype = C.c_int
     L.cp3g_nccl_unique_id.argtypes = [vp]; L.cp3g_nccl_unique_id.restype = C.c_int
     L.cp3g_nccl_init.argtypes = [vp, C.c_int, C.c_int, vp]; L.cp3g_nccl_init.restype = C.c_int
     L.cp3g_counter.argtypes = [vp, C.c_char_p]; L.cp3g_counter.restype = C.c_int64

@@ -1835,6 +1835,10 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
 void Engine::bveWorker()
 {
     const bool unlimited = !opt.limited;
+    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr;
+    int64_t tg = 0, tc = 0, ta = 0, tr = 0, trm = 0, ts = 0, tl = dbg ? now_ns() : 0;
+    auto lapt = [&](int64_t& acc) { if (dbg) { const int64_t n2 = now_ns(); acc += n2 - tl; tl = n2; } };
+    struct Rep { bool on; int64_t &tg, &tc, &ta, &tr, &trm, &ts; ~Rep() { if (on) { fprintf(stderr, "  bveWorker: heap+gates %.1f ms, clean %.1f, anticipate %.1f, resolveSet %.1f, removeClauses %.1f, inner subsumption %.1f\n", tg / 1e6, tc / 1e6, ta / 1e6, tr / 1e6, trm / 1e6, ts / 1e6); } } } rep{dbg, tg, tc, ta, tr, trm, ts};
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
         const int v = heapRemoveMin();
         if (assigns[v] != L_UNDEF) { continue; }
@@ -1848,6 +1852,7 @@ void Engine::bveWorker()
         if (!foundGate && opt.bve_fdepOnly) { continue; }
         if (!opt.bve_unlimited && !foundGate && cutoff) { ++bve_skippedVars; continue; }
         ++bve_testedVars;
+        lapt(tg);
         int pos_count = 0, neg_count = 0;
         for (int s = 0; s < 2; ++s) {
             ListRef li = L(2 * v + s);
@@ -1860,6 +1865,7 @@ void Engine::bveWorker()
         if (neg_stats.size() < hot[2 * v + 1].n) { neg_stats.resize(hot[2 * v + 1].n, 0); }
         int lit_clauses = 0, resolvents = 0;
         int ares = L_UNDEF;
+        lapt(tc);
         if (pos_count != 0 && neg_count != 0) {
             ++bve_anticipations;
             ares = anticipate(v, p_limit, n_limit, lit_clauses, resolvents);
@@ -1869,6 +1875,7 @@ void Engine::bveWorker()
             bveRemoveBlocked(2 * v, pos_stats);
             bveRemoveBlocked(2 * v + 1, neg_stats);
         }
+        lapt(ta);
         int compareNumber = pos_count + neg_count + opt.bve_cgrow;
         if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { compareNumber += opt.bve_cgrow_t - bve_totallyAdded; }
         bool reducedClss = resolvents <= compareNumber;
@@ -1878,15 +1885,19 @@ void Engine::bveWorker()
             if (resolvents < pos_count + neg_count) { bve_nDec++; }
             else if (resolvents > pos_count + neg_count) { bve_nInc++; }
             else { bve_nKeep++; }
+            lapt(tg);
             if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; }
+            lapt(tr);
             ++bve_eliminatedVars;
             bveRemoveClauses(2 * v, -1);
             if (assigns[v] == L_UNDEF) { bveRemoveClauses(2 * v + 1, 2 * v + 1); extLit(2 * v); }
             else { bveRemoveClauses(2 * v + 1, -1); }
             occRelease(2 * v); occRelease(2 * v + 1);
+            lapt(trm);
             if (opt.bve_heap_updates > 0) { subsumptionProcess(opt.bve_strength, true, v); }
             else { subsumptionProcess(opt.bve_strength, false, VAR_UNDEF); }
             t_bve.modified = t_bve.modified || t_sub.modified;
+            lapt(ts);
             if (!ok) { return; }
         }
         std::fill(pos_stats.begin(), pos_stats.end(), 0); std::fill(neg_stats.begin(), neg_stats.end(), 0);
