@@ -45,7 +45,16 @@ static constexpr int SHORT_LIST = 48;
 static constexpr uint32_t REF_MASK = 0x3fffffffu;
 static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 // full-queue kernel tiling
-static constexpr uint32_t TILE = 128, GROUP_MAX = 32, TCAP = TILE + GROUP_MAX, OFFCAP = 128, TILE_ALIGNED = 0x80000000u;
+#ifndef CP3_TILE
+#define CP3_TILE 128
+#endif
+#ifndef CP3_DCHUNK
+#define CP3_DCHUNK 8
+#endif
+#ifndef CP3_MINBLOCKS
+#define CP3_MINBLOCKS 6
+#endif
+static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = 32, TCAP = TILE + GROUP_MAX, OFFCAP = TILE, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
 
 struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
@@ -479,6 +488,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
 //            which would otherwise stall 31 lanes behind one)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
 static constexpr int WQ_CAP = 64, WH_CAP = 32, FQ_WARPS = 4;
+static constexpr uint32_t WORK_CAP = 2 * TILE, DCHUNK = CP3_DCHUNK;     // flat work list per tile: (subsumer, <= 8 consecutive candidates)
 struct TileDesc { uint32_t s, n, x0, xe, xa, noff; bool pure; };
 __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
 {
@@ -492,13 +502,14 @@ __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
     return d;
 }
 template <int KIND>
-__global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+__global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
         const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent, const uint2* __restrict__ tiles,
         const uint32_t* __restrict__ delbits, uint32_t tile_first, uint32_t tile_last,
         cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout, unsigned long long* __restrict__ checks)
 {
-    __shared__ __align__(16) OccEnt e_s[FQ_WARPS][2][TCAP];
+    __shared__ __align__(16) OccEnt e_s[FQ_WARPS][2][TCAP + DCHUNK];      // + DCHUNK: a unit may read (and ignore) past its chunk
     __shared__ __align__(16) uint32_t o_s[FQ_WARPS][2][OFFCAP];
+    __shared__ uint32_t vf_s[FQ_WARPS][TCAP], work_s[FQ_WARPS][WORK_CAP];
     __shared__ __align__(8) unsigned long long bar[FQ_WARPS][2];
     __shared__ unsigned long long sh_chk[FQ_WARPS], sh_byt[FQ_WARPS];
     __shared__ uint32_t q_s[FQ_WARPS][WQ_CAP], q_d[FQ_WARPS][WQ_CAP]; __shared__ int32_t q_l[FQ_WARPS][WQ_CAP];
@@ -562,56 +573,180 @@ __global__ void __launch_bounds__(FQ_WARPS * 32) k_full(const ClauseHdr* __restr
                 mbar_wait(&bar[w][b], (phase >> b) & 1u); phase ^= 1u << b;
                 const OccEnt* es = e_s[w][b]; const uint32_t* os = o_s[w][b];
                 const uint32_t s = cur.s, n = cur.n, xa = cur.xa, noff = cur.noff;
-                // One candidate entry against the tagged prefix of list x (pass 0) and of list x^1 (pass 1).
-                // PURE: the tile consists of whole short list pairs and its offsets are staged - every access
-                // below is a shared-memory load without range checks.  Otherwise each access picks shared/global.
-                auto candidate = [&](auto pure_tag, const OccEnt en, uint32_t x) {
-                    constexpr bool PURE = decltype(pure_tag)::value;
-                    auto OFF = [&](uint32_t y) -> uint32_t { return (PURE || y - xa < noff) ? os[y - xa] : occ_off[y]; };
-                    const uint32_t dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
-                    const unsigned long long dboth = var_fold(en.sig) * 3ull;     // both polarity bits of every variable of D
-                    uint32_t cnt = 0;
-                    const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
-                    for (int pass = 0; pass < npass; ++pass) {
-                        const uint32_t xx = pass == 0 ? x : (x ^ 1u);
-                        const uint32_t kb = OFF(xx), ke = OFF(xx + 1);
-                        for (uint32_t k = kb; k < ke; ++k) {
-                            const bool in = PURE || k - s < n;
-                            const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
-                            const uint32_t cls = a.x >> 30;
-                            if (KIND == CP3G_SUBSUME) { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSUB) { continue; } }
-                            else { if (cls & CLS_NOSTR) { break; } }
-                            const uint32_t sref = a.x & REF_MASK;
-                            if (sref == dref) { continue; }
-                            cnt += 1;
-                            if (esz < (a.y & SIZE_MASK)) { continue; }
-                            const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
-                            const unsigned long long miss = ssig & ~en.sig;
-                            if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                            else { if ((ssig & ~dboth) || (miss & (miss - 1))) { continue; } }
-                            if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { continue; }
-                            const uint32_t q = atomicAdd(&q_n[w], 1u);
-                            if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | (uint32_t)pass); }
-                            else { verify(sref, dref, (int32_t)x, pass); }
+                // A tile is pure iff both of its cuts are aligned to list pairs and its offsets are staged: then every
+                // list that meets the tile lies in it together with its complementary list.
+                //
+                // The pairs to test are (tagged entry S of list x) x (entries D of list x, and of list x^1 for
+                // strengthening), D in this tile.  Three forms:
+                //  flat     (pure tiles - all of them unless the literal frequencies are skewed) One lane per ENTRY first:
+                //           a tagged entry emits work units (S, <= 8 consecutive D) into the warp's list; then one lane
+                //           per UNIT keeps S in registers and tests its chunk from shared memory in straight-line code.
+                //           Every lane does the same amount of work, whatever the tag counts of the lists are.
+                //  segment  (tiles that lie inside ONE long list) 32 tagged entries of that list / its complement at a
+                //           time, coalesced from global memory, one per lane; each walks the whole tile, all lanes
+                //           reading the same candidate (shared-memory broadcast).
+                //  entry    (the rest: tiles cut by a long list, work list overflow) one lane per candidate D walks the
+                //           tagged prefix of its list, every access picking shared or global memory.
+                const bool pure = cur.pure;
+                uint32_t* vf = vf_s[w]; uint32_t* work = work_s[w];
+                auto OFF = [&](uint32_t y) -> uint32_t { return (y - xa < noff) ? os[y - xa] : occ_off[y]; };
+                auto enqueue = [&](uint32_t sref, uint32_t dref, uint32_t x, uint32_t pass) {
+                    if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { return; }
+                    const uint32_t q = atomicAdd(&q_n[w], 1u);
+                    if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | pass); }
+                    else { verify(sref, dref, (int32_t)x, (int)pass); }
+                };
+                auto entry_form = [&]() {
+                    for (uint32_t p = lane; p < n; p += 32) {
+                        const OccEnt en = es[p];
+                        const uint32_t dx = en.szfl >> 24;
+                        uint32_t x = cur.x0 + dx;
+                        if (dx == 255u) {                            // far from the tile's first literal (runs of empty lists)
+                            uint32_t lo = x, hi = cur.xe;           // last x with off[x] <= s + p
+                            while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= s + p) { lo = mid; } else { hi = mid; } }
+                            x = lo;
+                        }
+                        const uint32_t dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
+                        const unsigned long long dboth = var_fold(en.sig) * 3ull;     // both polarity bits of every variable of D
+                        uint32_t cnt = 0;
+                        const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+                        for (int pass = 0; pass < npass; ++pass) {
+                            const uint32_t xx = pass == 0 ? x : (x ^ 1u);
+                            const uint32_t kb = OFF(xx), ke = OFF(xx + 1);
+                            for (uint32_t k = kb; k < ke; ++k) {
+                                const bool in = k - s < n;
+                                const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
+                                const uint32_t cls = a.x >> 30;
+                                if (KIND == CP3G_SUBSUME) { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSUB) { continue; } }
+                                else { if (cls & CLS_NOSTR) { break; } }
+                                const uint32_t sref = a.x & REF_MASK;
+                                if (sref == dref) { continue; }
+                                cnt += 1;
+                                if (esz < (a.y & SIZE_MASK)) { continue; }
+                                const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
+                                const unsigned long long miss = ssig & ~en.sig;
+                                if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
+                                else { if ((ssig & ~dboth) || (miss & (miss - 1))) { continue; } }
+                                enqueue(sref, dref, x, (uint32_t)pass);
+                            }
+                        }
+                        nchk += cnt; nbytes += (unsigned long long)cnt * (12 + 4 * esz);
+                    }
+                };
+                if (pure) {
+                    const uint32_t xb = cur.x0 - xa;
+                    uint32_t U = 0; bool fits = true;
+                    // one lane per entry: a tagged entry S emits its units, every entry gets its 32-bit variable signature
+                    for (uint32_t base = 0; base < n; base += 32) {
+                        const uint32_t p = base + lane;
+                        uint32_t cnt = 0, kb = 0, len = 0, kb1 = 0, len1 = 0;
+                        if (p < n) {
+                            const OccEnt en = es[p];
+                            const unsigned long long f = var_fold(en.sig);
+                            vf[p] = (uint32_t)f | ((uint32_t)(f >> 32) << 1);          // exact packing of the folded signature
+                            if (!((en.ref >> 30) & (KIND == CP3G_SUBSUME ? CLS_NOSUB : CLS_NOSTR))) {
+                                const uint32_t xi = xb + (en.szfl >> 24);
+                                kb = os[xi] - s; len = os[xi + 1] - os[xi];
+                                cnt = (len + DCHUNK - 1) / DCHUNK;
+                                if (KIND == CP3G_STRENGTHEN) {
+                                    const uint32_t xj = xi ^ 1u;                 // the complementary list (tile starts at an even literal)
+                                    kb1 = os[xj] - s; len1 = os[xj + 1] - os[xj];
+                                    cnt += (len1 + DCHUNK - 1) / DCHUNK;
+                                }
+                            }
+                        }
+                        uint32_t inc = cnt;
+#pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) { const uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) { inc += t2; } }
+                        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+                        if (U + tot > WORK_CAP) { fits = false; break; }
+                        uint32_t o = U + inc - cnt;
+                        for (uint32_t c = 0; c < len; c += DCHUNK) { work[o++] = p | ((kb + c) << 8) | (min(DCHUNK, len - c) << 16); }
+                        if (KIND == CP3G_STRENGTHEN) {
+                            for (uint32_t c = 0; c < len1; c += DCHUNK) { work[o++] = p | ((kb1 + c) << 8) | (min(DCHUNK, len1 - c) << 16) | (1u << 20); }
+                        }
+                        U += tot;
+                    }
+                    __syncwarp();
+                    if (fits) {
+                        for (uint32_t u = lane; u < U; u += 32) {
+                            const uint32_t wk = work[u];
+                            const uint32_t sidx = wk & 255u, d0 = (wk >> 8) & 255u, cnt = (wk >> 16) & 15u, pass = wk >> 20;
+                            const OccEnt S = es[sidx];
+                            const uint32_t sref = S.ref & REF_MASK, sn = S.szfl & SIZE_MASK, svf = vf[sidx];
+                            uint32_t c = 0, szsum = 0, cand = 0;
+                            // straight-line over the chunk: all loads are issued up front, one rare branch at the end
+#pragma unroll
+                            for (uint32_t i = 0; i < DCHUNK; ++i) {
+                                const uint32_t d = d0 + i;
+                                const uint2 dd = *reinterpret_cast<const uint2*>(&es[d]);
+                                const uint32_t esz = dd.y & SIZE_MASK;
+                                const bool live = i < cnt && (dd.x & REF_MASK) != sref;
+                                c += live; szsum += live ? esz : 0u;
+                                cand |= (uint32_t)(live && esz >= sn && (svf & ~vf[d]) == 0u) << i;
+                            }
+                            nchk += c; nbytes += 12ull * c + 4ull * szsum;
+                            while (cand) {
+                                const uint32_t i = __ffs(cand) - 1; cand &= cand - 1;
+                                const uint32_t d = d0 + i;
+                                const uint2 dd = *reinterpret_cast<const uint2*>(&es[d]);
+                                const unsigned long long miss = S.sig & ~es[d].sig;
+                                if (KIND == CP3G_SUBSUME ? miss != 0 : (miss & (miss - 1)) != 0) { continue; }
+                                enqueue(sref, dd.x & REF_MASK, cur.x0 + (dd.y >> 24), pass);     // pure tile: dx is exact
+                            }
+                        }
+                    } else { entry_form(); }
+                } else {
+                    // the list of the first entry (uniform over the warp); does it cover the whole tile?
+                    const uint32_t dx0 = es[0].szfl >> 24;
+                    uint32_t y = cur.x0 + dx0;
+                    if (dx0 == 255u) {
+                        uint32_t lo = y, hi = cur.xe;
+                        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= s) { lo = mid; } else { hi = mid; } }
+                        y = lo;
+                    }
+                    const uint32_t lb = OFF(y), le = OFF(y + 1);
+                    if (le < s + n) { entry_form(); }
+                    else {
+                        for (uint32_t p = lane; p < n; p += 32) {
+                            const unsigned long long f = var_fold(es[p].sig);
+                            vf[p] = (uint32_t)f | ((uint32_t)(f >> 32) << 1);
+                        }
+                        __syncwarp();
+                        const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+                        for (int pass = 0; pass < npass; ++pass) {
+                            const uint32_t sl = pass == 0 ? y : (y ^ 1u);
+                            const uint32_t sb = pass == 0 ? lb : OFF(sl), se = pass == 0 ? le : OFF(sl + 1);
+                            for (uint32_t k0 = sb; k0 < se; k0 += 32) {
+                                const uint32_t k = k0 + lane;
+                                OccEnt S; S.ref = 0xffffffffu; S.szfl = 0; S.sig = 0;
+                                if (k < se) { if (k - s < n) { S = es[k - s]; } else { S = occ_ent[k]; } }
+                                const uint32_t cls = S.ref >> 30;
+                                const bool tagged = !(cls & (KIND == CP3G_SUBSUME ? CLS_NOSUB : CLS_NOSTR));
+                                if (tagged) {
+                                    const uint32_t sref = S.ref & REF_MASK, sn = S.szfl & SIZE_MASK;
+                                    const unsigned long long sf = var_fold(S.sig);
+                                    const uint32_t svf = (uint32_t)sf | ((uint32_t)(sf >> 32) << 1);
+                                    uint32_t c = 0; unsigned long long szsum = 0;
+                                    for (uint32_t d = 0; d < n; ++d) {
+                                        const uint2 dd = *reinterpret_cast<const uint2*>(&es[d]);
+                                        const uint32_t dref = dd.x & REF_MASK, esz = dd.y & SIZE_MASK;
+                                        const bool live = dref != sref;
+                                        c += live; szsum += live ? esz : 0u;
+                                        if (live && esz >= sn && (svf & ~vf[d]) == 0u) {
+                                            const unsigned long long miss = S.sig & ~es[d].sig;
+                                            if (KIND == CP3G_SUBSUME ? miss != 0 : (miss & (miss - 1)) != 0) { continue; }
+                                            enqueue(sref, dref, y, (uint32_t)pass);
+                                        }
+                                    }
+                                    nchk += c; nbytes += 12ull * c + 4ull * szsum;
+                                }
+                                // the tagged classes are a prefix (strengtheners) resp. everything below class 3 (subsumers)
+                                const bool more_s = KIND == CP3G_STRENGTHEN ? tagged : (cls != CLS_NONE);
+                                if (!__any_sync(0xffffffffu, more_s)) { break; }
+                            }
                         }
                     }
-                    nchk += cnt; nbytes += (unsigned long long)cnt * (12 + 4 * esz);
-                };
-                // a tile is pure iff both of its cuts are aligned to list pairs and its offsets are staged
-                const bool pure = cur.pure;
-                for (uint32_t p = lane; p < n; p += 32) {
-                    const OccEnt en = es[p];
-                    const uint32_t dx = en.szfl >> 24;
-                    uint32_t x = cur.x0 + dx;
-                    if (dx == 255u) {                                // far from the tile's first literal (runs of empty lists)
-                        const uint32_t j = s + p;
-                        uint32_t lo = x, hi = cur.xe;               // last x with off[x] <= j
-                        while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= j) { lo = mid; } else { hi = mid; } }
-                        x = lo;
-                        candidate(std::false_type(), en, x);
-                    }
-                    else if (pure) { candidate(std::true_type(), en, x); }
-                    else { candidate(std::false_type(), en, x); }
                 }
             }
             __syncwarp();                                  // all reads of buffer b are done before it is refilled
@@ -1210,8 +1345,9 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     }
     KTimer t(g);
     if (te > tb) {
-        // persistent grid: 7 blocks of 4 independent warps per SM (29 KB of staging per block), warps stride over tiles
-        const unsigned blocks = std::min<unsigned>(grid_for(te - tb, FQ_WARPS), (unsigned)g->num_sms * 7u);
+        // persistent grid: 5 blocks of 4 independent warps per SM (40 KB of staging + work lists per block), warps stride over tiles
+        static const unsigned per_sm = getenv("CP3_FQ_BLOCKS") ? (unsigned)atoi(getenv("CP3_FQ_BLOCKS")) : (unsigned)CP3_MINBLOCKS;
+        const unsigned blocks = std::min<unsigned>(grid_for(te - tb, FQ_WARPS), (unsigned)g->num_sms * per_sm);
         if (kind == CP3G_SUBSUME) {
             k_full<CP3G_SUBSUME><<<blocks, FQ_WARPS * 32, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->tiles.p,
                 g->delbits.p, tb, te, g->hits.p, cap, g->counters.p, dchecks);
