@@ -1342,6 +1342,12 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         uint32_t cr;
         if (localQueue.empty()) {
             --end; cur_end = end;
+            if (end >= 24 && contrib[end - 24] < 0) {           // look ahead past the inert entries: the next real one
+                const ClauseInfo& c2 = C[strq[end - 24]]; const int32_t* l2 = pool.data() + c2.start;
+                const uint32_t n2 = std::min<uint32_t>(c2.size, 6);
+                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
+                if (strq[end - 24] < c_str.slot.size()) { const int32_t sl = c_str.slot[strq[end - 24]]; if (sl >= 0) { __builtin_prefetch(&c_str.ent[(size_t)sl]); } }
+            }
             if (static_lazy) {
                 if (contrib[end] >= 0) {
                     if (!hasToPropagate()) { str_steps += contrib[end]; ++n_lazy; continue; }

@@ -71,6 +71,19 @@ __device__ __forceinline__ unsigned long long var_fold(unsigned long long s)
     return (s | (s >> 1)) & 0x5555555555555555ull;
 }
 
+// streaming (evict-first) accesses for data that is read or written exactly once per build pass, so that the tables
+// the passes gather from at random (offsets, counters, refs, clause headers) stay resident in the 126 MB L2
+__device__ __forceinline__ ClauseHdr ld_stream(const ClauseHdr* p)
+{
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+    ClauseHdr h; h.start = v.x; h.szfl = v.y; h.sig = (unsigned long long)v.z | ((unsigned long long)v.w << 32);
+    return h;
+}
+__device__ __forceinline__ void st_stream(OccEnt* p, const OccEnt& e)
+{
+    __stcs(reinterpret_cast<uint4*>(p), make_uint4(e.ref, e.szfl, (uint32_t)e.sig, (uint32_t)(e.sig >> 32)));
+}
+
 // ------------------------------------------------------------------------------------------ K1 + K2
 __global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
                             uint32_t* __restrict__ cnt, uint32_t* __restrict__ rank)
@@ -80,11 +93,11 @@ __global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restri
     // literal - the scatter pass then needs no second round of atomics.
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
-    const ClauseHdr h = hdr[i];
+    const ClauseHdr h = ld_stream(hdr + i);
     const uint32_t sz = h.szfl & SIZE_MASK;
     unsigned long long s = 0;
     const bool live = !(h.szfl & FLAG_DEL);
-    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = lits[h.start + k]; s |= lit_bit(x); if (live) { rank[h.start + k] = atomicAdd(&cnt[x], 1u); } }
+    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = __ldcs(lits + h.start + k); s |= lit_bit(x); if (live) { __stcs(rank + h.start + k, atomicAdd(&cnt[x], 1u)); } }
     if (s != h.sig) { hdr[i].sig = s; }
 }
 
@@ -164,7 +177,7 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) { return; }
-    const ClauseHdr h = hdr[i];
+    const ClauseHdr h = ld_stream(hdr + i);
     if (h.szfl & FLAG_DEL) { return; }
     const uint32_t sz = h.szfl & SIZE_MASK;
     uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = -1, xt = -1;
@@ -178,7 +191,7 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
     for (uint32_t k = 0; k < sz; ++k) {
         const int32_t x = lits[h.start + k];
         const uint32_t cls = (x == xs ? 0u : CLS_NOSUB) | (x == xt ? 0u : CLS_NOSTR);
-        refs[off[x] + rank[h.start + k]] = i | (cls << 30);
+        refs[off[x] + __ldcs(rank + h.start + k)] = i | (cls << 30);
     }
 }
 // one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced.
@@ -190,7 +203,7 @@ __global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* 
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) { return; }
-    const uint32_t r = refs[i];
+    const uint32_t r = __ldcs(refs + i);
     uint32_t t = i / TILE;
     uint2 a = tiles[t], b = tiles[t + 1];
     if (i >= (b.x & ~TILE_ALIGNED)) { a = b; b = tiles[t + 2]; }
@@ -199,7 +212,7 @@ __global__ void k_occ_expand(const ClauseHdr* __restrict__ hdr, const uint32_t* 
     const uint32_t dx = min(lo - a.y, 255u);
     const ClauseHdr h = hdr[r & REF_MASK];
     OccEnt e; e.ref = r; e.szfl = (h.szfl & SIZE_MASK) | (dx << 24); e.sig = h.sig;
-    ent[i] = e;
+    st_stream(ent + i, e);
 }
 // Tile table of the full-queue kernels.  Tile t nominally starts at entry 128*t; the start is moved down to the
 // first entry of the variable's list pair (occ(2v), occ(2v+1)) when that pair is short, so that a tile consists
