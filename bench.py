@@ -185,6 +185,9 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # one engine per rank: split the host cores between the ranks of this node (the ordered commit uses a thread pool)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    os.environ.setdefault("CP3_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))))
     import torch
     import torch.distributed as dist
     import riss_solver_b200 as rs
@@ -311,6 +314,7 @@ def main():
                                    f"(2% duplicates, 3% supersets, 3% flipped copies), seed {args.seed}, subsumption+strengthening fixpoint",
                        "value_leg": "device-resident bulk pass: K1 signatures + K2 occurrence CSR build + K3 + K4 over the full queue, CUDA events on the library stream",
                        "l2": "working set (occ entries + headers + literals, ~350 MB) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
+                       "host_threads_per_rank": int(os.environ["CP3_THREADS"]),
                        "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank" if args.mode == "weak"
                                        else f"{world} ranks, one formula: scan requests partitioned, hits all-gathered over NCCL"))},
             "roofline": {"bound": "hbm", "kernel": "k_full (K3+K4 full-queue form, both launches)", "achieved": achieved, "peak": peak,
