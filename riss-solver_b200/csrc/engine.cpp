@@ -138,6 +138,16 @@ template <class F> void Engine::parallelFor(size_t n, F f, size_t grain)
     for (auto& x : th) { x.join(); }
 }
 
+template <class P> void Engine::parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred)
+{
+    const size_t n = src.size();
+    std::vector<size_t> cnt((size_t)nthreads + 2, 0);
+    parallelFor(n, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t i = b; i < e; ++i) { c += pred(src[i]) ? 1 : 0; } cnt[(size_t)t + 1] = c; });
+    for (size_t t = 1; t < cnt.size(); ++t) { cnt[t] += cnt[t - 1]; }
+    out.resize(cnt.back());
+    parallelFor(n, [&](size_t b, size_t e, int t) { size_t o = cnt[(size_t)t]; for (size_t i = b; i < e; ++i) { if (pred(src[i])) { out[o++] = src[i]; } } });
+}
+
 // ------------------------------------------------------------------------------------------------ solver side
 void Engine::newVar()
 {
@@ -240,6 +250,14 @@ bool Engine::solverSimplify()
     if (qhead < (int)trail.size() && !ingestPropagate()) { ok = false; return false; }
     if ((int)trail.size() == simpDB_assigns || simpDB_props > 0) { return true; }
     size_t j = 0; int64_t lits = 0;
+    if (trail.empty()) {                          // nothing is assigned: no clause can be satisfied, only the literal count is needed
+        std::vector<int64_t> part((size_t)nthreads + 1, 0);
+        parallelFor(clauses.size(), [&](size_t b, size_t e, int t) { int64_t a = 0; for (size_t i = b; i < e; ++i) { a += C[clauses[i]].size; } part[(size_t)t] = a; });
+        for (int64_t a : part) { lits += a; }
+        if (ca_wasted > ca_size * opt.gc_frac) { ca_size -= ca_wasted; ca_wasted = 0; }
+        simpDB_assigns = 0; simpDB_props = lits;
+        return true;
+    }
     for (size_t i = 0; i < clauses.size(); ++i) {
         uint32_t c = clauses[i]; const int32_t* l = CL(c); bool sat = false;
         for (uint32_t k = 0; k < C[c].size; ++k) { if (value(l[k]) == L_TRUE) { sat = true; break; } }
@@ -329,8 +347,9 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
     bool bulk = forceBulk == 1;
     if (forceBulk < 0 && ids.size() == n_live && n_live > bulk_min) {
-        bulk = true;
-        for (uint32_t c : ids) { if (C[c].flag & F_DEL) { bulk = false; break; } }
+        bool any_del = false;
+        parallelFor(ids.size(), [&](size_t b, size_t e, int) { bool d = false; for (size_t i = b; i < e && !d; ++i) { d = (C[ids[i]].flag & F_DEL) != 0; } if (d) { any_del = true; } });
+        bulk = !any_del;
     }
     std::vector<uint32_t> live, dead;
     if (!bulk) { for (uint32_t c : ids) { ((C[c].flag & F_DEL) ? dead : live).push_back(c); } }
@@ -1000,8 +1019,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     lap0("clear");
     {
         std::vector<uint32_t> ids;
-        ids.reserve(subq.size());
-        for (uint32_t c : subq) { if (!(C[c].flag & F_DEL)) { ids.push_back(c); } }
+        parallelFilter(subq, ids, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
         sortUnique(ids);
         lap0("ids");
         scanClauses(CP3G_SUBSUME, ids, c_sub);
@@ -1994,16 +2012,16 @@ void Engine::initData()
     }
     ph_download += now_ns() - ti0;
     DbgLap lap("init"); 
-    size_t kept = 0;
-    subq.reserve(clauses.size()); strq.reserve(clauses.size());
-    for (size_t i = 0; i < clauses.size(); ++i) {
-        uint32_t c = clauses[i];
-        if (C[c].flag & F_DEL) { continue; }
-        numberOfCls++;
-        subInitClause(c);
-        clauses[kept++] = c;
+    {   // every live clause: count it, queue it per its flags (Subsumption::initClause), drop the deleted ones
+        std::vector<uint32_t> live;
+        parallelFilter(clauses, live, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
+        clauses.swap(live);
+        numberOfCls += (int)clauses.size();
+        std::vector<uint32_t> qs, qt;
+        parallelFilter(clauses, qs, [&](uint32_t c) { return (C[c].flag & F_SUB) != 0; });
+        parallelFilter(clauses, qt, [&](uint32_t c) { return (C[c].flag & F_STR) != 0; });
+        subq.insert(subq.end(), qs.begin(), qs.end()); strq.insert(strq.end(), qt.begin(), qt.end());
     }
-    clauses.resize(kept);
     lap("initClause loop");
     data_ready = true;
 }

@@ -187,6 +187,8 @@ private:
     void unpredictedEdit(uint32_t c);               // a clause the static plan relied on was modified
     template <class F> void parallelFor(size_t n, F f, size_t grain = 65536);
     template <class F> void parallelForG(size_t n, size_t grain, F f) { parallelFor(n, f, grain); }
+    // stable parallel filter: out = [x in src | pred(x)] (count per chunk, prefix, write)
+    template <class P> void parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred);
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
