@@ -893,19 +893,19 @@ bool Engine::subsumptionCommitParallel()
     const size_t bwidth = std::max<size_t>(64, (nlit / NB) / 64 * 64);
     auto bucketOf = [&](int x) -> int { int bk = (int)std::min<size_t>((size_t)NB - 1, (size_t)x / bwidth); while (bk > 0 && x < bucketLo(bk)) { --bk; } while (bk + 1 < NB && x >= bucketLo(bk + 1)) { ++bk; } return bk; };
     std::vector<std::vector<LT>> dlb((size_t)NB);
-    if (dl_start.size() < nlit) { dl_start.assign(nlit, -1); dl_cnt.assign(nlit, 0u); }
+    if (dl_start.size() < nlit) { dl_start.assign(nlit, -1); dl_cnt.assign(nlit, 0u); dl_any.assign((nlit >> 6) + 1, 0ull); }
     parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
         for (size_t bk = bb; bk < be; ++bk) {
             const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
             std::vector<LT>& v = dlb[bk];
             for (uint32_t d : dead) { const int32_t* l = CL(d); for (uint32_t k = 0; k < C[d].size; ++k) { if (l[k] >= lo && l[k] < hi) { v.push_back({l[k], sub_dtime[d]}); } } }
             std::sort(v.begin(), v.end(), [](const LT& a2, const LT& b2) { return a2.lit != b2.lit ? a2.lit < b2.lit : a2.time < b2.time; });
-            for (size_t i = 0; i < v.size(); ++i) { if (dl_start[v[i].lit] < 0) { dl_start[v[i].lit] = (int32_t)i; } ++dl_cnt[v[i].lit]; }
+            for (size_t i = 0; i < v.size(); ++i) { if (dl_start[v[i].lit] < 0) { dl_start[v[i].lit] = (int32_t)i; dl_any[(uint32_t)v[i].lit >> 6] |= 1ull << (v[i].lit & 63); } ++dl_cnt[v[i].lit]; }
         }
     }, 1);
     auto countAt = [&](int x, int32_t T) -> int32_t {               // lit_occurrence_count[x] as of time T
         int32_t c = hot[x].cnt;
-        if (dl_cnt[x]) { const LT* q = dlb[bucketOf(x)].data() + dl_start[x]; for (uint32_t k = 0; k < dl_cnt[x] && q[k].time < T; ++k) { --c; } }
+        if ((dl_any[(uint32_t)x >> 6] >> (x & 63)) & 1ull) { const LT* q = dlb[bucketOf(x)].data() + dl_start[x]; for (uint32_t k = 0; k < dl_cnt[x] && q[k].time < T; ++k) { --c; } }
         return c;
     };
     // step 3: every queue entry picks its list with the counters of its own time.  Walks of lists that never hold
@@ -922,7 +922,7 @@ bool Engine::subsumptionCommitParallel()
             const int32_t* c = pool.data() + ci.start;
             int mn = c[0]; int32_t best = countAt(mn, T);
             for (uint32_t l = 1; l < ci.size; ++l) { const int32_t v = countAt(c[l], T); if (v < best) { best = v; mn = c[l]; } }
-            if (dl_cnt[mn] == 0 && !hasStale(mn)) { st += hot[mn].n ? (int64_t)hot[mn].n - 1 : 0; }
+            if (!((dl_any[(uint32_t)mn >> 6] >> (mn & 63)) & 1ull) && !hasStale(mn)) { st += hot[mn].n ? (int64_t)hot[mn].n - 1 : 0; }
             else { ev.push_back({mn, T, (uint32_t)p}); }
         }
         tsteps[t] = st;
@@ -1001,7 +1001,7 @@ bool Engine::subsumptionCommitParallel()
     sub_steps += steps;
     // sparse resets
     for (uint32_t d : dead) { sub_dtime[d] = INF; }
-    for (const auto& v : dlb) { for (const LT& x : v) { dl_start[x.lit] = -1; dl_cnt[x.lit] = 0; } }
+    for (const auto& v : dlb) { for (const LT& x : v) { dl_start[x.lit] = -1; dl_cnt[x.lit] = 0; dl_any[(uint32_t)x.lit >> 6] = 0ull; } }
     reset_pos();
     lap("step5");
     ++n_parsub;
@@ -2012,15 +2012,29 @@ void Engine::initData()
     }
     ph_download += now_ns() - ti0;
     DbgLap lap("init"); 
-    {   // every live clause: count it, queue it per its flags (Subsumption::initClause), drop the deleted ones
-        std::vector<uint32_t> live;
-        parallelFilter(clauses, live, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
-        clauses.swap(live);
-        numberOfCls += (int)clauses.size();
-        std::vector<uint32_t> qs, qt;
-        parallelFilter(clauses, qs, [&](uint32_t c) { return (C[c].flag & F_SUB) != 0; });
-        parallelFilter(clauses, qt, [&](uint32_t c) { return (C[c].flag & F_STR) != 0; });
-        subq.insert(subq.end(), qs.begin(), qs.end()); strq.insert(strq.end(), qt.begin(), qt.end());
+    {   // every live clause: count it, queue it per its flags (Subsumption::initClause), drop the deleted ones.
+        // Right after the ingest every clause is live and carries both flags: then the queues are copies.
+        std::vector<size_t> part((size_t)nthreads + 1, 0);
+        parallelFor(clauses.size(), [&](size_t b, size_t e, int t) {
+            size_t a = 0;
+            for (size_t i = b; i < e; ++i) { const uint8_t f = C[clauses[i]].flag; a += (!(f & F_DEL) && (f & F_SUB) && (f & F_STR)) ? 1 : 0; }
+            part[(size_t)t] = a;
+        });
+        size_t full = 0; for (size_t a : part) { full += a; }
+        if (full == clauses.size()) {
+            numberOfCls += (int)clauses.size();
+            subq.insert(subq.end(), clauses.begin(), clauses.end()); strq.insert(strq.end(), clauses.begin(), clauses.end());
+        } else {
+            size_t kept = 0;
+            for (size_t i = 0; i < clauses.size(); ++i) {
+                uint32_t c = clauses[i];
+                if (C[c].flag & F_DEL) { continue; }
+                numberOfCls++;
+                subInitClause(c);
+                clauses[kept++] = c;
+            }
+            clauses.resize(kept);
+        }
     }
     lap("initClause loop");
     data_ready = true;

@@ -266,7 +266,7 @@ private:
     bool overlap_str = false, str_prepared = false, scan_no_flush = false;
     void prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk);
     int64_t n_overlap = 0;                // time-indexed, data-parallel form of the queue walk
-    std::vector<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt;
+    std::vector<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
     int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
