@@ -142,6 +142,13 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
 int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping, uint32_t* nvars_new, int* compressed,
                int32_t* lits_out, size_t nlits);
 
+/* K8: stream compaction of the clause arena (CoprocessorData::garbageCollect / relocAll, CoprocessorTypes.h:1396-1550;
+ * ClauseAllocator::reloc).  The literals of the live clauses are packed in clause order (exclusive scan of the live
+ * sizes, gather), the holes left by deleted and shortened clauses disappear.  new_start[i] (nclauses entries) is the
+ * new pool offset of clause i (deleted clauses become empty), lits_out receives the packed pool, *nlits_new its
+ * length; pass lits_out == NULL to compact the device copy only. */
+int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_cap, size_t* nlits_new);
+
 /* multi-GPU plumbing: NCCL communicator over the ranks' devices (bootstrap id from rank 0) */
 int cp3g_nccl_unique_id(void* out128);
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);

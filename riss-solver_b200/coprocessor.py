@@ -211,6 +211,13 @@ class ScanService:
                                          off.ctypes.data, out.ctypes.data, int(off[-1])), "bve_resolve")
         return off, out[:int(off[-1])]
 
+    def compact(self, download=True):
+        """K8: pack the clause arena (garbageCollect / relocAll); returns (new_start[nclauses], packed literal pool)"""
+        ncl = int(self.counter("nclauses")); nl = int(self.counter("nlits"))
+        ns = np.zeros(max(ncl, 1), dtype=np.uint32); out = np.zeros(max(nl, 1), dtype=np.int32); n = C.c_size_t(0)
+        self._ck(self.L.cp3g_compact(self.g, ns.ctypes.data, out.ctypes.data if download else None, out.size, C.byref(n)), "compact")
+        return ns[:ncl], out[:int(n.value)]
+
     def counter(self, name):
         return int(self.L.cp3g_counter(self.g, name.encode()))
 

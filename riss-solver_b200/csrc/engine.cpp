@@ -761,6 +761,25 @@ void Engine::checkGarbage()
     double sz = 0;
     for (uint32_t c : clauses) { sz += 2 + C[c].size; }
     ca_size = sz; ca_wasted = 0;
+    // relocAll: the arena itself.  The device packs its copy (K8: scan of the live sizes + gather); the host mirror is
+    // packed by the same rule - clause order, live sizes - so both keep identical offsets without a transfer.
+    if (dev_uploaded) {
+        flushDevice();
+        std::vector<int32_t> np; np.reserve(pool.size());
+        for (size_t c = 0; c < C.size(); ++c) {
+            const uint32_t ns = (uint32_t)np.size();
+            if (C[c].flag & F_DEL) { C[c].size = 0; }
+            else { np.insert(np.end(), pool.begin() + C[c].start, pool.begin() + C[c].start + C[c].size); }
+            C[c].start = ns;
+        }
+        pool.swap(np);
+        size_t nl = 0;
+        int64_t t0 = now_ns();
+        if (cp3g_compact(gpu, nullptr, nullptr, 0, &nl) != CP3G_OK) { die("arena compaction failed"); }
+        host_ns_gpuwait += now_ns() - t0;
+        if (nl != pool.size()) { die("arena compaction: host and device pools differ"); }
+        ++n_compactions;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ Propagation::process (Propagation.cc:32-131)
@@ -2209,7 +2228,7 @@ int64_t Engine::stat(const char* s) const
     ST("up_removedClauses", up_removedClauses) ST("up_removedLiterals", up_removedLiterals)
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
-    ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches)
+    ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches) ST("arena_compactions", n_compactions)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
     ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("overlapped_str_scans", n_overlap)

@@ -138,6 +138,7 @@ private:
     // ---------------- device replica + scan cache
     cp3g* gpu = nullptr;
     bool dev_uploaded = false;
+    int64_t n_compactions = 0;
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
     std::vector<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far

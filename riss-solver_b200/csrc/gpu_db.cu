@@ -900,6 +900,28 @@ __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits
     hdr[ids[i]] = h;
 }
 
+// ------------------------------------------------------------------------------------------ K8 arena compaction
+// live size of every clause (0 for deleted) -> exclusive scan -> new pool offsets
+__global__ void k_compact_sizes(const ClauseHdr* __restrict__ hdr, uint32_t n, uint32_t* __restrict__ sz)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) { sz[i] = (i < n && !(hdr[i].szfl & FLAG_DEL)) ? (hdr[i].szfl & SIZE_MASK) : 0u; }
+}
+// gather: one thread per clause moves its literals to the packed pool and rewrites the header; deleted clauses
+// become empty (their literals are dropped)
+__global__ void k_compact_move(ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ src, int32_t* __restrict__ dst,
+                               const uint32_t* __restrict__ nstart, uint32_t n)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    ClauseHdr h = hdr[i];
+    const uint32_t ns = nstart[i];
+    if (h.szfl & FLAG_DEL) { h.szfl = FLAG_DEL; }
+    else { const uint32_t sz = h.szfl & SIZE_MASK; for (uint32_t k = 0; k < sz; ++k) { dst[ns + k] = src[h.start + k]; } }
+    h.start = ns;
+    hdr[i] = h;
+}
+
 // ------------------------------------------------------------------------------------------ K7 Dense
 // variable v occurs in a live clause (countLiterals, Dense.h:92-121; only "occurs at all" matters)
 __global__ void k_dense_mark(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n, uint32_t* __restrict__ keep)
@@ -941,7 +963,7 @@ struct cp3g {
     std::string err;
     uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
     size_t nlits = 0;
-    DevBuf<int32_t> lits; DevBuf<ClauseHdr> hdr;
+    DevBuf<int32_t> lits, lits2; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, tile_sum, long_lits, ovf, scratch_u32;
     DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
@@ -1036,7 +1058,7 @@ void cp3g_destroy(cp3g* g)
     if (!g) { return; }
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
-    g->lits.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->tile_sum.release(g->stream);
+    g->lits.release(g->stream); g->lits2.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->tile_sum.release(g->stream);
     g->long_lits.release(g->stream); g->ovf.release(g->stream); g->scratch_u32.release(g->stream); g->occ_ent.release(g->stream); g->tiles.release(g->stream); g->delbits.release(g->stream); g->refs_tmp.release(g->stream);
     g->sort_tmp.release(g->stream); g->req_self.release(g->stream); g->req_off.release(g->stream); g->req_lits.release(g->stream); g->hits.release(g->stream); g->counters.release(g->stream);
     g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
@@ -1531,6 +1553,44 @@ int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     t.collect();
+    return CP3G_OK;
+}
+
+int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_cap, size_t* nlits_new)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    const uint32_t n = g->ncl;
+    if (nlits_new) { *nlits_new = g->nlits; }
+    if (n == 0) { return CP3G_OK; }
+    const uint32_t ntiles = (n + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    RESERVE(g->bu0, (size_t)n + 2, false); RESERVE(g->bu1, (size_t)n + 2, false);
+    RESERVE(g->tile_sum, (size_t)ntiles + 1, false);
+    RESERVE(g->lits2, g->lits.cap, false);
+    KTimer t(g);
+    k_compact_sizes<<<grid_for((size_t)n + 1, 256), 256, 0, g->stream>>>(g->hdr.p, n, g->bu0.p);
+    k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(g->bu0.p, g->bu1.p, n + 1, g->tile_sum.p);
+    k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 2);
+    k_scan_add<<<ntiles, SCAN_T, 0, g->stream>>>(g->bu1.p, n + 1, g->tile_sum.p);
+    k_compact_move<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->lits2.p, g->bu1.p, n);
+    g->launches += 5;
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, g->counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (new_start) { CK(cudaMemcpyAsync(new_start, g->bu1.p, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream)); g->d2h += (int64_t)n * 4; }
+    t.stop();
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    t.collect();
+    std::swap(g->lits.p, g->lits2.p); std::swap(g->lits.cap, g->lits2.cap);
+    g->nlits = total; g->lits.used = total;
+    // the occurrence CSR stays valid: its entries name clauses, and every literal access goes through hdr[].start
+    if (nlits_new) { *nlits_new = total; }
+    if (lits_out) {
+        if (lits_cap < total) { g->err = "cp3g_compact: output buffer too small"; return CP3G_ERR_ARG; }
+        CK(cudaMemcpyAsync(lits_out, g->lits.p, (size_t)total * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        g->d2h += (int64_t)total * 4;
+    }
     return CP3G_OK;
 }
 

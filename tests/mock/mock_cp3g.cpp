@@ -201,6 +201,19 @@ int cp3g_dense(cp3g* g, const uint8_t* keep, int frag, uint32_t* mapping, uint32
     g->nvars = kept; *compressed = 1; *nvars_new = kept; g->launches += 7;
     return CP3G_OK;
 }
+int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_cap, size_t* nlits_new)
+{
+    size_t pos = 0;
+    for (size_t i = 0; i < g->cl.size(); ++i) {
+        g->start[i] = pos; if (new_start) { new_start[i] = (uint32_t)pos; }
+        if (g->del[i]) { g->cl[i].clear(); continue; }
+        if (lits_out) { if (pos + g->cl[i].size() > lits_cap) { return CP3G_ERR_ARG; } std::copy(g->cl[i].begin(), g->cl[i].end(), lits_out + pos); }
+        pos += g->cl[i].size();
+    }
+    g->nlits = pos; if (nlits_new) { *nlits_new = pos; }
+    g->launches += 5;
+    return CP3G_OK;
+}
 int cp3g_nccl_unique_id(void* out) { memset(out, 0, 128); return CP3G_OK; }
 int cp3g_nccl_init(cp3g*, int, int, const void*) { return CP3G_OK; }
 int64_t cp3g_counter(const cp3g* g, const char* name)

@@ -211,6 +211,53 @@ def test_k3_k4_full_queue_kernel_equals_request_kernel(gen, shape):
     svc.close()
 
 
+def test_k8_arena_compaction(gen):
+    """K8 (garbageCollect / relocAll): after deleting and shortening clauses the packed pool is exactly the live
+    literals in clause order, the offsets are their prefix sums, and the scans answer as before the move."""
+    lits, sizes = gen.random_ksat(5000, 21000, 3, seed=51, dup=0.04, sup=0.06, flip=0.06)
+    codes = _sorted_clauses(lits, sizes)
+    n = int(np.abs(lits).max()); m = sizes.size
+    svc = rs.ScanService(); svc.upload(n, codes, sizes); svc.build()
+    rng = np.random.default_rng(52)
+    dele = np.sort(rng.choice(m, size=m // 5, replace=False)).astype(np.uint32)
+    svc.set_deleted(dele)
+    ids = np.arange(m, dtype=np.uint32)
+    before = {k: svc.scan(k, ids) for k in (rs.SUBSUME, rs.STRENGTHEN)}
+    ns, pool = svc.compact()
+    live = np.ones(m, bool); live[dele] = False
+    starts = np.cumsum(sizes) - sizes
+    want = np.concatenate([codes[starts[i]:starts[i] + sizes[i]] for i in np.flatnonzero(live)])
+    assert np.array_equal(pool, want)
+    assert np.array_equal(ns, (np.cumsum(np.where(live, sizes, 0)) - np.where(live, sizes, 0)).astype(np.uint32))
+    for k in (rs.SUBSUME, rs.STRENGTHEN):
+        a, ca = svc.scan(k, ids[live])
+        b, cb = before[k]
+        keep = live[b["req"]]                                  # requests of deleted clauses are gone now
+        # request indices changed (live subset): compare by clause ids
+        got = np.stack([ids[live][a["req"]], a["clause"], a["lit"].astype(np.int64)], 1)
+        exp = np.stack([b["req"][keep], b["clause"][keep], b["lit"][keep].astype(np.int64)], 1)
+        assert np.array_equal(got[np.lexsort(got.T[::-1])], exp[np.lexsort(exp.T[::-1])])
+    # a second compaction is a no-op, and the full-queue kernels still agree with the request kernel
+    ns2, pool2 = svc.compact()
+    assert np.array_equal(ns2, ns) and np.array_equal(pool2, pool)
+    a, _ = svc.scan_all(rs.SUBSUME); b, _ = svc.scan(rs.SUBSUME, ids[live])
+    b["req"] = ids[live][b["req"]]
+    assert np.array_equal(_hits_key(a), _hits_key(b))
+    svc.close()
+
+
+def test_engine_compacts_the_arena_in_bve_runs(gen):
+    """checkGarbage -> K8 inside CPpreprocess: several technique rounds with BVE waste > 20 % of the arena"""
+    hit = 0
+    for seed in (1, 3):
+        lits, sizes = gen.community_ksat(3000, 15000, seed=seed)
+        stream = gen.csr_to_stream(lits, sizes)
+        for opts in (FULL + ["-cp3_iters=3"], ["-enabled_cp3", "-subsimp", "-bve", "-bve_unlimited", "-bve_cgrow=2", "-cp3_iters=2"], DENSE + ["-cp3_iters=3"]):
+            cp = rs.Coprocessor(opts); cp.add_stream(stream); cp.preprocess(); hit += cp.stat("arena_compactions"); cp.close()
+            assert compare(run_gpu(stream, opts), run_oracle(stream, opts)) == []
+    assert hit > 0
+
+
 def test_k5_resolvent_counts_match_oracle_snapshot(gen):
     lits, sizes = gen.community_ksat(3000, 12000, seed=4, planted=False)
     stream = gen.csr_to_stream(lits, sizes)
