@@ -337,3 +337,34 @@ def test_sharded_mode_two_gpus_matches_oracle():
                         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "scripts", "sharded_parity.py")],
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "SHARDED_PARITY OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("opts", [FULL, DENSE])
+def test_gpu_output_is_equisatisfiable_riss_cross_check(gen, opts):
+    """satisfiability cross-checked by riss (oracle/_ref/riss-core travels with the snapshot): same verdict on the input
+    and on the formula CPpreprocess returns; a model of the latter, pushed through CPpostprocessModel, satisfies the input"""
+    import satcheck
+    if not satcheck.have_riss():
+        pytest.skip("oracle/_ref/riss-core not built")
+    verdicts = set()
+    for seed in range(10):
+        n = 120
+        lits, sizes = gen.random_ksat(n, int(n * (3.9 + 0.1 * seed)), 3, seed=500 + seed, dup=0.03, sup=0.05, flip=0.05)
+        stream = gen.csr_to_stream(lits, sizes)
+        cp = rs.Coprocessor(opts); cp.add_stream(stream); cp.preprocess()
+        rc0, _ = satcheck.solve(stream, n)
+        if not cp.ok():
+            assert rc0 == 20
+            cp.close(); verdicts.add(20); continue
+        out = cp.output_stream()
+        rc1, model = satcheck.solve(out, max(cp.n_vars(), 1))
+        assert rc0 == rc1, (seed, rc0, rc1)
+        verdicts.add(rc0)
+        if rc1 == 10:
+            full = cp.extend_model([l for l in model if abs(l) <= cp.n_vars()])
+            bits = np.zeros(max(len(full), n), np.uint8)
+            for l in full:
+                bits[abs(l) - 1] = 1 if l > 0 else 0
+            assert satcheck.satisfies(stream, bits), seed
+        cp.close()
+    assert verdicts == {10, 20}
