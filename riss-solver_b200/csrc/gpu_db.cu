@@ -23,6 +23,7 @@
 //   k_bve_resolve K6  resolvent generation (BVE.h:208-242)
 #include <cuda_runtime.h>
 #include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -97,7 +98,11 @@ __global__ void k_occ_count(ClauseHdr* __restrict__ hdr, const int32_t* __restri
     const uint32_t sz = h.szfl & SIZE_MASK;
     unsigned long long s = 0;
     const bool live = !(h.szfl & FLAG_DEL);
-    for (uint32_t k = 0; k < sz; ++k) { const int32_t x = __ldcs(lits + h.start + k); s |= lit_bit(x); if (live) { __stcs(rank + h.start + k, atomicAdd(&cnt[x], 1u)); } }
+    if (rank != nullptr) {
+        for (uint32_t k = 0; k < sz; ++k) { const int32_t x = __ldcs(lits + h.start + k); s |= lit_bit(x); if (live) { __stcs(rank + h.start + k, atomicAdd(&cnt[x], 1u)); } }
+    } else {          // sort path (large data bases): only the histogram
+        for (uint32_t k = 0; k < sz; ++k) { const int32_t x = __ldcs(lits + h.start + k); s |= lit_bit(x); if (live) { atomicAdd(&cnt[x], 1u); } }
+    }
     if (s != h.sig) { hdr[i].sig = s; }
 }
 
@@ -193,6 +198,44 @@ __global__ void k_occ_fill(const ClauseHdr* __restrict__ hdr, const int32_t* __r
         const uint32_t cls = (x == xs ? 0u : CLS_NOSUB) | (x == xt ? 0u : CLS_NOSTR);
         refs[off[x] + __ldcs(rank + h.start + k)] = i | (cls << 30);
     }
+}
+// Large data bases (the refs array does not fit the L2: at 54 M clauses the random 4-byte scatter of k_occ_fill moves
+// 163 bytes of DRAM traffic per occurrence): the occurrences are SORTED instead.  key = literal << 2 | class, value =
+// clause index, written at the literal's own pool slot (coalesced); a stable LSD radix sort (cub) then yields every
+// list in (class, clause index) order - pool slots ascend with the clause index - without atomics or per-list sorts.
+__global__ void k_occ_keys(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t n,
+                           const uint32_t* __restrict__ off, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = ld_stream(hdr + i);
+    if (h.szfl & FLAG_DEL) { return; }
+    const uint32_t sz = h.szfl & SIZE_MASK;
+    uint32_t bs = 0xffffffffu, bt = 0xffffffffu; int32_t xs = -1, xt = -1;
+    for (uint32_t k = 0; k < sz; ++k) {
+        const int32_t x = lits[h.start + k];
+        const uint32_t len = off[x + 1] - off[x];
+        const uint32_t both = len + off[(x ^ 1) + 1] - off[x ^ 1];
+        if (len < bs) { bs = len; xs = x; }
+        if (both < bt) { bt = both; xt = x; }
+    }
+    for (uint32_t k = 0; k < sz; ++k) {
+        const int32_t x = lits[h.start + k];
+        const uint32_t cls = (x == xs ? 0u : CLS_NOSUB) | (x == xt ? 0u : CLS_NOSTR);
+        __stcs(keys + h.start + k, ((uint32_t)x << 2) | cls);
+        __stcs(vals + h.start + k, i);
+    }
+}
+__global__ void k_refs_from_sorted(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t total, uint32_t* __restrict__ refs)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) { refs[i] = __ldcs(vals + i) | ((__ldcs(keys + i) & 3u) << 30); }
+}
+// pool slots must ascend with the clause index for the stable sort to give clause order
+__global__ void k_check_monotone(const ClauseHdr* __restrict__ hdr, uint32_t n, uint32_t* __restrict__ bad)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 < n && hdr[i + 1].start < hdr[i].start + (hdr[i].szfl & SIZE_MASK) && !(hdr[i].szfl & FLAG_DEL) && !(hdr[i + 1].szfl & FLAG_DEL)) { *bad = 1u; }
 }
 // one thread per entry: gather size + signature of the referenced clause, write the 16-byte entry coalesced.
 // The top byte of the size word gets dx = (literal of the entry's list) - (first literal of its tile), saturating
@@ -964,7 +1007,7 @@ struct cp3g {
     uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
     size_t nlits = 0;
     DevBuf<int32_t> lits, lits2; DevBuf<ClauseHdr> hdr;
-    DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, tile_sum, long_lits, ovf, scratch_u32;
+    DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, srt_v, srt_k2, srt_v2, tile_sum, long_lits, ovf, scratch_u32;
     DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<unsigned char> sort_tmp;
@@ -1058,7 +1101,7 @@ void cp3g_destroy(cp3g* g)
     if (!g) { return; }
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
-    g->lits.release(g->stream); g->lits2.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->tile_sum.release(g->stream);
+    g->lits.release(g->stream); g->lits2.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->srt_v.release(g->stream); g->srt_k2.release(g->stream); g->srt_v2.release(g->stream); g->tile_sum.release(g->stream);
     g->long_lits.release(g->stream); g->ovf.release(g->stream); g->scratch_u32.release(g->stream); g->occ_ent.release(g->stream); g->tiles.release(g->stream); g->delbits.release(g->stream); g->refs_tmp.release(g->stream);
     g->sort_tmp.release(g->stream); g->req_self.release(g->stream); g->req_off.release(g->stream); g->req_lits.release(g->stream); g->hits.release(g->stream); g->counters.release(g->stream);
     g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
@@ -1133,9 +1176,21 @@ static int build_csr(cp3g* g)
     RESERVE(g->long_lits, (size_t)nlit + 1, false);
     CK(cudaMemsetAsync(g->occ_tmp.p, 0, ((size_t)nlit + 2) * sizeof(uint32_t), g->stream));
     CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
+    // scatter path while the refs array stays L2 resident, sort path beyond (CP3_K2_SORT=0/1 forces one)
+    static const int force_sort = getenv("CP3_K2_SORT") ? atoi(getenv("CP3_K2_SORT")) : -1;
+    bool use_sort = force_sort >= 0 ? force_sort != 0 : g->nlits * sizeof(uint32_t) > (size_t)(96u << 20);
+    if (nlit >= (1u << 30) || g->nlits >= (size_t)0x7fffffff || g->ncl == 0) { use_sort = false; }
+    if (use_sort) {
+        k_check_monotone<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->ncl, g->counters.p + 3);
+        uint32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, g->counters.p + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+        g->launches += 1;
+        if (bad) { use_sort = false; }
+    }
     if (g->ncl) {
-        RESERVE(g->occ_rank, g->nlits + 1, false);
-        k_occ_count<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_tmp.p, g->occ_rank.p);
+        if (!use_sort) { RESERVE(g->occ_rank, g->nlits + 1, false); }
+        k_occ_count<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_tmp.p, use_sort ? nullptr : g->occ_rank.p);
     }
     k_scan_tiles<<<ntiles, SCAN_T, 0, g->stream>>>(g->occ_tmp.p, g->occ_off.p, nlit + 1, g->tile_sum.p);
     k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, ntiles, g->counters.p + 2);
@@ -1147,7 +1202,24 @@ static int build_csr(cp3g* g)
     g->total_occ = total;
     RESERVE(g->occ_ent, (size_t)total + 1, false);
     RESERVE(g->refs_tmp, (size_t)total + 1, false);
-    if (g->ncl) {
+    bool sorted_by_radix = false;
+    if (g->ncl && use_sort) {
+        const size_t ns = g->nlits;
+        RESERVE(g->occ_rank, ns + 1, false); RESERVE(g->srt_v, ns + 1, false); RESERVE(g->srt_k2, ns + 1, false); RESERVE(g->srt_v2, ns + 1, false);
+        CK(cudaMemsetAsync(g->occ_rank.p, 0xff, ns * sizeof(uint32_t), g->stream));      // unused pool slots sort to the end
+        k_occ_keys<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_rank.p, g->srt_v.p);
+        int end_bit = 2; while (end_bit < 32 && (1ull << (end_bit - 2)) < (unsigned long long)nlit) { ++end_bit; }
+        end_bit = 32;                                  // the 0xffffffff filler keys need every bit
+        size_t bytes = 0;
+        cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, bytes, g->occ_rank.p, g->srt_k2.p, g->srt_v.p, g->srt_v2.p, (int)ns, 0, end_bit, g->stream);
+        if (e != cudaSuccess) { g->fail("cub radix sort size", e); return CP3G_ERR_CUDA; }
+        RESERVE(g->sort_tmp, bytes + 16, false);
+        e = cub::DeviceRadixSort::SortPairs(g->sort_tmp.p, bytes, g->occ_rank.p, g->srt_k2.p, g->srt_v.p, g->srt_v2.p, (int)ns, 0, end_bit, g->stream);
+        if (e != cudaSuccess) { g->fail("cub radix sort", e); return CP3G_ERR_CUDA; }
+        if (total) { k_refs_from_sorted<<<grid_for(total, 256), 256, 0, g->stream>>>(g->srt_k2.p, g->srt_v2.p, total, g->refs_tmp.p); }
+        g->launches += 6;
+        sorted_by_radix = true;
+    } else if (g->ncl) {
         k_occ_fill<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ncl, g->occ_off.p, g->occ_rank.p, g->refs_tmp.p);
         k_occ_sort_short<<<grid_for(nlit, SORT_LISTS), SORT_LISTS, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
         g->launches += 2;
@@ -1158,8 +1230,10 @@ static int build_csr(cp3g* g)
     k_tiles<<<grid_for((size_t)g->ntiles + 2, 256), 256, 0, g->stream>>>(g->occ_off.p, nlit, total, g->ntiles + 1, g->tiles.p);
     g->launches += 1;
     uint32_t nlong = 0;
-    CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
-    CK(cudaStreamSynchronize(g->stream));
+    if (!sorted_by_radix) {
+        CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+        CK(cudaStreamSynchronize(g->stream));
+    }
     if (nlong) {
         k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p);
         g->launches += 1;
