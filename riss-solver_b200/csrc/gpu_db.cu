@@ -565,7 +565,7 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
 {
     __shared__ __align__(16) OccEnt e_s[FQ_WARPS][2][TCAP + DCHUNK];      // + DCHUNK: a unit may read (and ignore) past its chunk
     __shared__ __align__(16) uint32_t o_s[FQ_WARPS][2][OFFCAP];
-    __shared__ uint32_t vf_s[FQ_WARPS][TCAP], work_s[FQ_WARPS][WORK_CAP];
+    __shared__ uint32_t vf_s[FQ_WARPS][TCAP + DCHUNK], work_s[FQ_WARPS][WORK_CAP];    // + DCHUNK: see e_s
     __shared__ __align__(8) unsigned long long bar[FQ_WARPS][2];
     __shared__ unsigned long long sh_chk[FQ_WARPS], sh_byt[FQ_WARPS];
     __shared__ uint32_t q_s[FQ_WARPS][WQ_CAP], q_d[FQ_WARPS][WQ_CAP]; __shared__ int32_t q_l[FQ_WARPS][WQ_CAP];
