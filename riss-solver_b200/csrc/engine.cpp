@@ -483,7 +483,12 @@ void Engine::prefetchStrengthenClosure()
     std::unordered_set<uint64_t> requested;              // hash of (clause, content) already scanned
     size_t first_ent = 0;
     DbgLap lap("closure");
-    for (int round = 0; round < 8; ++round) {
+    // Speculation is only worth its scans while they are cheap next to the full-queue pass: a request costs the
+    // length of its shortest list pair (long on skewed inputs), and after a unit shows up most predictions are void.
+    // Budget: four times the occurrence count of the data base; what is not prefetched is scanned on demand.
+    int64_t spec_budget = 4 * (int64_t)pool.size();
+    bool budget_left = true;
+    for (int round = 0; round < 8 && budget_left; ++round) {
         std::vector<uint32_t> changed;
         const size_t old_n = evs.size();
         for (size_t ei = first_ent; ei < c_str.ent.size(); ++ei) {
@@ -509,7 +514,7 @@ void Engine::prefetchStrengthenClosure()
             while (q < evs.size() && evs[q].clause == d) { ++q; }
             const Ev* ev = evs.data() + p; const size_t m = q - p;
             p = q;
-            if ((C[d].flag & F_DEL) || m == 0) { continue; }
+            if ((C[d].flag & F_DEL) || m == 0 || !budget_left) { continue; }
             const bool pending = (C[d].flag & F_STR) && d < qtime.size() && qtime[d] >= 0;
             const double own = pending ? (double)qtime[d] : -1.0;
             size_t k0 = 0;
@@ -528,6 +533,10 @@ void Engine::prefetchStrengthenClosure()
                 const uint32_t nl = (uint32_t)spec_lits.size() - off;
                 if (nl != C[d].size - k || !requested.insert(hsh).second) { spec_lits.resize(off); continue; }
                 const double t = (pending && k == k0) ? own : std::max(own, ev[k - 1].time) + 1e-3 * (round + 1);
+                uint32_t walk = 0xffffffffu;
+                for (uint32_t i = 0; i < nl; ++i) { const int x = spec_lits[off + i]; walk = std::min(walk, hot[x].n + hot[x ^ 1].n); }
+                spec_budget -= walk;
+                if (spec_budget < 0) { budget_left = false; spec_lits.resize(off); break; }
                 reqs.push_back({d, off, nl, t});
             }
         }
