@@ -931,8 +931,13 @@ bool Engine::subsumptionCommitParallel()
             for (size_t i = 0; i < v.size(); ++i) { if (dl_start[v[i].lit] < 0) { dl_start[v[i].lit] = (int32_t)i; dl_any[(uint32_t)v[i].lit >> 6] |= 1ull << (v[i].lit & 63); } ++dl_cnt[v[i].lit]; }
         }
     }, 1);
+    // 2-byte copy of the counters as of the pass start (cache resident); out-of-range values read the original
+    std::vector<int16_t> cnt16(nlit);
+    parallelFor(nlit, [&](size_t b, size_t e, int) {
+        for (size_t x = b; x < e; ++x) { const int32_t c = hot[x].cnt; cnt16[x] = (c > 32000 || c < -32000) ? INT16_MIN : (int16_t)c; }
+    });
     auto countAt = [&](int x, int32_t T) -> int32_t {               // lit_occurrence_count[x] as of time T
-        int32_t c = hot[x].cnt;
+        int32_t c = cnt16[(size_t)x]; if (c == INT16_MIN) { c = hot[x].cnt; }
         if ((dl_any[(uint32_t)x >> 6] >> (x & 63)) & 1ull) { const LT* q = dlb[bucketOf(x)].data() + dl_start[x]; for (uint32_t k = 0; k < dl_cnt[x] && q[k].time < T; ++k) { --c; } }
         return c;
     };
@@ -1299,6 +1304,13 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         is_target.assign((C.size() >> 6) + 1, 0ull);
         for (const Hit& h : c_str.hits) { is_target[h.clause >> 6] |= 1ull << (h.clause & 63); }
         const size_t nq = strq.size();
+        // the counters are frozen while this plan is valid: a 2-byte copy per variable (2 MB at 1 M variables) keeps
+        // the min-count choices of the two passes below in the cores' caches; out-of-range values read the original
+        std::vector<int16_t> dc16((size_t)std::max(nvars, 1));
+        parallelFor((size_t)nvars, [&](size_t b, size_t e, int) {
+            for (size_t v = b; v < e; ++v) { const int d = dcount((int)v); dc16[v] = (d > 32000 || d < -32000) ? INT16_MIN : (int16_t)d; }
+        });
+        auto dcq = [&](int v) -> int { const int16_t q = dc16[(size_t)v]; return q == INT16_MIN ? dcount(v) : (int)q; };
         // (1) lists that are certainly walked in this pass: the two lists of every pending clause whose content
         //     cannot change before its turn (it is nobody's candidate target)
         std::vector<uint8_t> walked((size_t)2 * nvars, 0);
@@ -1313,11 +1325,12 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
                 if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }                      // duplicate queue entry
                 if ((is_target[c >> 6] >> (c & 63)) & 1) { continue; }
-                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0];
-                for (uint32_t j = 1; j < ci.size; ++j) { if (dcount(minT >> 1) > dcount(s2[j] >> 1)) { minT = s2[j]; } }
-                walked[minT] = 1; walked[minT ^ 1] = 1;
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0]; int best = dcq(minT >> 1);
+                for (uint32_t j = 1; j < ci.size; ++j) { const int dj = dcq(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
+                // (only lists that hold deleted entries can be pre-compacted: the walker count and the mark matter for them alone)
                 walk_min[p2] = minT;
-                __atomic_fetch_add(&walk_count[minT], 1u, __ATOMIC_RELAXED); __atomic_fetch_add(&walk_count[minT ^ 1], 1u, __ATOMIC_RELAXED);
+                if (hasStale(minT)) { walked[minT] = 1; __atomic_fetch_add(&walk_count[minT], 1u, __ATOMIC_RELAXED); }
+                if (hasStale(minT ^ 1)) { walked[minT ^ 1] = 1; __atomic_fetch_add(&walk_count[minT ^ 1], 1u, __ATOMIC_RELAXED); }
                 bs += (int64_t)hot[minT].n + hot[minT ^ 1].n;
             }
             bound[t] = bs;
@@ -1371,8 +1384,8 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
                 if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
                 if (c_str.slot[c] >= 0 || ((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }
-                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0];
-                for (uint32_t j = 1; j < ci.size; ++j) { if (dcount(minT >> 1) > dcount(s2[j] >> 1)) { minT = s2[j]; } }
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0]; int best = dcq(minT >> 1);
+                for (uint32_t j = 1; j < ci.size; ++j) { const int dj = dcq(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
                 const int mn = minT, nm = minT ^ 1;
                 if (hasStale(mn) || hasStale(nm)) { continue; }
                 contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
