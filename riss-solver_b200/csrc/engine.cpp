@@ -1725,7 +1725,7 @@ int Engine::anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& r
     }
     bool binariesOnly = false;
     PairEnt* pe = &pairsFor(v);
-    std::vector<int> col;                         // column of negative[cn] in the K5 matrix
+    std::vector<int>& col = bve_col;             // column of negative[cn] in the K5 matrix (reused: no allocation per variable)
     auto remap = [&]() { col.assign(negative.n, -1); for (uint32_t j = 0; j < negative.n; ++j) { col[j] = indexOf(pe->neg, LP(negative)[j]); } };
     remap();
     for (uint32_t cp = 0; cp < positive.n; ++cp) {
@@ -1815,12 +1815,13 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
     const bool hasDefinition = (p_limit < (int)positive.n || n_limit < (int)negative.n);
     PairEnt* pe = &pairsFor(v);
     // gather the pairs in reference order and fetch their resolvents with one K6 launch
-    struct Pr { uint32_t cp, cn; int size; uint64_t off; };
-    std::vector<Pr> prs; std::vector<int32_t> rl;
+    typedef BvePr Pr;
+    std::vector<Pr>& prs = bve_prs; std::vector<int32_t>& rl = bve_rl;       // reused buffers: no allocation per variable
     auto fetch = [&](uint32_t cp0, uint32_t cn0) {
         prs.clear();
-        std::vector<uint32_t> vv, pr, nr; std::vector<uint64_t> off{0};
-        std::vector<int> col(negative.n, -1);
+        std::vector<uint32_t>& vv = bve_vv; std::vector<uint32_t>& pr = bve_pr; std::vector<uint32_t>& nr = bve_nr; std::vector<uint64_t>& off = bve_off;
+        vv.clear(); pr.clear(); nr.clear(); off.clear(); off.push_back(0);
+        std::vector<int>& col = bve_col; col.assign(negative.n, -1);
         for (uint32_t j = 0; j < negative.n; ++j) { col[j] = indexOf(pe->neg, LP(negative)[j]); }
         for (uint32_t cp = cp0; cp < positive.n; ++cp) {
             const uint32_t p = LP(positive)[cp];
@@ -1842,10 +1843,10 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
         rl.assign(off.back() + 1, 0);
         if (!prs.empty() && pe->has_res) {
             // prefetched with the K5 batch: copy out of the cache (pair (row, col) -> literals)
-            std::vector<int> col2(negative.n, -1);
-            for (uint32_t j = 0; j < negative.n; ++j) { col2[j] = indexOf(pe->neg, LP(negative)[j]); }
+            uint32_t last_cp = 0xffffffffu; size_t row2 = 0;
             for (const Pr& q : prs) {
-                const size_t idx = (size_t)indexOf(pe->pos, LP(positive)[q.cp]) * pe->neg.size() + col2[q.cn];
+                if (q.cp != last_cp) { last_cp = q.cp; row2 = (size_t)indexOf(pe->pos, LP(positive)[q.cp]); }
+                const size_t idx = row2 * pe->neg.size() + (size_t)col[q.cn];
                 memcpy(rl.data() + q.off, pe->rlits.p + pe->roff[idx], sizeof(int32_t) * (size_t)q.size);
             }
         } else if (!prs.empty()) {

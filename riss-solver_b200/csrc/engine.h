@@ -139,6 +139,8 @@ private:
     cp3g* gpu = nullptr;
     bool dev_uploaded = false;
     int64_t n_compactions = 0;
+    struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
+    std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
     std::vector<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far
