@@ -488,7 +488,8 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
             test_candidate<KIND>(en.ref, en.szfl, en.sig, me, S, sn, ssig, nx, -1, hdr, lits, r, sink);
         }
     }
-    // clauses younger than the CSR (resolvents): brute force, they are few
+    // clauses younger than the CSR (resolvents): brute force.  A short overflow list is walked here; a long one is
+    // left to k_scan_ovf, which spreads (request, chunk of the list) pairs over the whole grid
     for (uint32_t i = lane; i < novf; i += 32) {
         const uint32_t ref = ovf[i];
         const ClauseHdr h = hdr[ref];
@@ -500,6 +501,54 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
     if (lane == 0 && nchk) { atomicAdd(checks, nchk); atomicAdd(checks + 1, nbytes); }
     // (one same-address atomic pair per request: fine for the small incremental batches this kernel serves;
     //  full-queue passes go through k_bulk, which reduces per block)
+    }
+    sink.flush(&sink_base);
+}
+
+// Overflow part of a request scan for long overflow lists: one warp per (request, 512-entry chunk of the list), so
+// the brute force over the young clauses is spread over the grid instead of being one warp's serial loop of
+// dependent header gathers (260 us per launch at 21 k young clauses).
+static constexpr uint32_t OVF_CHUNK = 512, OVF_INLINE_MAX = 1024;
+template <int KIND>
+__global__ void __launch_bounds__(256) k_scan_ovf(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
+        const uint32_t* __restrict__ ovf, uint32_t novf, uint32_t nchunks,
+        uint32_t req_begin, uint32_t req_end, const uint32_t* __restrict__ self,
+        const uint32_t* __restrict__ req_off, const int32_t* __restrict__ req_lits,
+        cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout,
+        unsigned long long* __restrict__ checks)
+{
+    SINK_DECL;
+    const unsigned long long widx = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t r = req_begin + (uint32_t)(widx / nchunks), chunk = (uint32_t)(widx % nchunks);
+    bool live = r < req_end;
+    uint32_t me = 0; const int32_t* S = nullptr; uint32_t sn = 0;
+    if (live) {
+        me = self[r];
+        if (req_lits != nullptr) { S = req_lits + req_off[r]; sn = req_off[r + 1] - req_off[r]; }
+        else {
+            const ClauseHdr h = hdr[me];
+            if (h.szfl & FLAG_DEL) { live = false; }
+            S = lits + h.start; sn = h.szfl & SIZE_MASK;
+        }
+        if (sn == 0) { live = false; }
+    }
+    if (live) {
+        unsigned long long ssig = 0;
+        for (uint32_t k = lane; k < sn; k += 32) { ssig |= lit_bit(S[k]); }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { ssig |= __shfl_xor_sync(0xffffffffu, ssig, d); }
+        unsigned long long nchk = 0, nbytes = 0;
+        const uint32_t b = chunk * OVF_CHUNK, e = min(novf, b + OVF_CHUNK);
+        for (uint32_t i = b + lane; i < e; i += 32) {
+            const uint32_t ref = ovf[i];
+            const ClauseHdr h = hdr[ref];
+            if (ref != me) { nchk += 1; nbytes += 12 + 4 * (h.szfl & SIZE_MASK); }
+            test_candidate<KIND>(ref, h.szfl, h.sig, me, S, sn, ssig, -1, -1, hdr, lits, r, sink);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
+        if (lane == 0 && nchk) { atomicAdd(checks, nchk); atomicAdd(checks + 1, nbytes); }
     }
     sink.flush(&sink_base);
 }
@@ -1386,14 +1435,30 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
     if (re > rb) {
         const unsigned blocks = grid_for((size_t)(re - rb) * 32, 256);
         const int32_t* rl = req_lits ? g->req_lits.p : nullptr;
+        const uint32_t novf = (uint32_t)g->ovf_host.size();
+        const bool split = novf > OVF_INLINE_MAX;                 // long overflow list: its own grid-wide kernel
+        const uint32_t novf_inline = split ? 0u : novf;
         if (kind == CP3G_SUBSUME) {
             k_scan<CP3G_SUBSUME><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ovf.p,
-                (uint32_t)g->ovf_host.size(), rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+                novf_inline, rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
         } else {
             k_scan<CP3G_STRENGTHEN><<<blocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->ovf.p,
-                (uint32_t)g->ovf_host.size(), rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+                novf_inline, rb, re, g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
         }
         g->launches++;
+        if (split) {
+            const uint32_t nchunks = (novf + OVF_CHUNK - 1) / OVF_CHUNK;
+            const unsigned long long warps = (unsigned long long)(re - rb) * nchunks;
+            const unsigned oblocks = (unsigned)((warps * 32 + 255) / 256);
+            if (kind == CP3G_SUBSUME) {
+                k_scan_ovf<CP3G_SUBSUME><<<oblocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ovf.p, novf, nchunks, rb, re,
+                    g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+            } else {
+                k_scan_ovf<CP3G_STRENGTHEN><<<oblocks, 256, 0, g->stream>>>(g->hdr.p, g->lits.p, g->ovf.p, novf, nchunks, rb, re,
+                    g->req_self.p, g->req_off.p, rl, g->hits.p, cap, g->counters.p, dchecks);
+            }
+            g->launches++;
+        }
     }
     t.stop();
     uint32_t* cnt = g->pin_cnt;
