@@ -15,12 +15,16 @@
 // Kernels (none uses tensor cores - there is no contraction on this path):
 //   k_occ_count   K1+K2  64-bit literal signature per clause (new accelerating filter; never changes results)
 //                 fused with the occurrence histogram
-//   k_occ_*       K2  exclusive scan -> scatter of (class, clause) words -> per-list sort -> tile table -> expand
-//   k_full<KIND>  K3/K4 full-queue pass: candidate-major over bulk-copy staged tiles of the entry array
+//   k_occ_*       K2  exclusive scan -> scatter of (class, clause) words -> per-list sort -> tile table -> expand;
+//                 large data bases: (literal, class) keys + stable cub radix sort instead of scatter + per-list sort
+//   k_full<KIND>  K3/K4 full-queue pass over bulk-copy (cp.async.bulk + mbarrier) staged tiles of the entry array:
+//                 flat (subsumer, candidate-chunk) work list per tile; segment / entry forms for cut tiles
 //   k_scan<KIND>  K3/K4 request-driven signature filter + sorted-literal merge (Subsumption.cc:244-297,
-//                 1276-1521; Clause::ordered_subsumes SolverTypes.h:1003)
+//                 1276-1521; Clause::ordered_subsumes SolverTypes.h:1003); k_scan_ovf for long lists of young clauses
 //   k_bve_pairs   K5  resolvent size per (pos,neg) pair (BVE.h:248-299)
 //   k_bve_resolve K6  resolvent generation (BVE.h:208-242)
+//   k_dense_*     K7  Dense::compress: mark occurring variables, prefix-sum renumbering, literal rewrite (Dense.cc:26-238)
+//   k_compact_*   K8  arena stream compaction: scan of the live sizes + gather (garbageCollect, CoprocessorTypes.h:1396)
 #include <cuda_runtime.h>
 #include <cub/device/device_merge_sort.cuh>
 #include <cub/device/device_radix_sort.cuh>
@@ -500,7 +504,7 @@ __global__ void __launch_bounds__(256) k_scan(const ClauseHdr* __restrict__ hdr,
     for (int d = 16; d > 0; d >>= 1) { nchk += __shfl_xor_sync(0xffffffffu, nchk, d); nbytes += __shfl_xor_sync(0xffffffffu, nbytes, d); }
     if (lane == 0 && nchk) { atomicAdd(checks, nchk); atomicAdd(checks + 1, nbytes); }
     // (one same-address atomic pair per request: fine for the small incremental batches this kernel serves;
-    //  full-queue passes go through k_bulk, which reduces per block)
+    //  full-queue passes go through k_full, which reduces per block)
     }
     sink.flush(&sink_base);
 }
