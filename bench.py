@@ -9,9 +9,10 @@ candidate) pair taken from an occurrence list (Subsumption.cc:268,1330,1431).
   value  checks/s of the device-resident bulk pass: clause arena already in HBM, K1 signatures + K2 occurrence
          CSR + K3 full-queue subsumption scan + K4 full-queue strengthening scan, timed with CUDA events on the
          library's stream (cp3g_* scan service, hits stay on the device).
-  e2e    checks/s through the reference-facing C ABI (CPpreprocess on HOST buffers): upload, all scans, ordered
-         commit on the host, download - the whole fixpoint; checks = the reference-defined step counters, which
-         parity makes identical to the reference's.
+  e2e    checks/s through the reference-facing C ABI on HOST buffers: CPaddLits of the DIMACS stream (host -> device
+         inside the timed region), CPpreprocess (all scans, ordered commit on the host), read-back of the output CNF -
+         the whole fixpoint; checks = the reference-defined step counters, which parity makes identical to the
+         reference's.  (The reference arm times Preprocessor::preprocess() only, its own ingest is not charged.)
   --impl reference   the reference's own CPU Coprocessor (oracle/_ref, unmodified sources) on a bounded sample of
          the same workload with all host threads (-cp3_threads), same metric.
 
@@ -254,12 +255,12 @@ def main():
     # ---------------- leg 2: end to end through the C ABI (host buffers in, host buffers out)
     def e2e_step():
         cp = rs.Coprocessor(opts)
-        cp.add_stream(stream)                         # host-side ingest (CPaddLit stream), not timed
         uid = fresh_uid()
         if uid is not None and cp.set_distributed(rank, world, uid) != 0:
             raise SystemExit("CPsetDistributed failed (NCCL communicator)")
         barrier()
         t0 = time.perf_counter()
+        cp.add_stream(stream)                         # CPaddLits: the DIMACS stream from host memory (device bulk ingest K0)
         cp.preprocess()
         out = cp.output_stream()                      # device->host results are part of the call; read the CNF back
         barrier()
@@ -313,6 +314,7 @@ def main():
             "config": {"workload": f"BASELINE configs[1]: planted random 3-SAT {args.vars} vars / {sizes.size} clauses "
                                    f"(2% duplicates, 3% supersets, 3% flipped copies), seed {args.seed}, subsumption+strengthening fixpoint",
                        "value_leg": "device-resident bulk pass: K1 signatures + K2 occurrence CSR build + K3 + K4 over the full queue, CUDA events on the library stream",
+                       "e2e_leg": "CPaddLits (DIMACS stream from host memory) + CPpreprocess + output read-back, wall clock per step",
                        "l2": "working set (occ entries + headers + literals, ~350 MB) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
                        "host_threads_per_rank": int(os.environ["CP3_THREADS"]),
                        "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank" if args.mode == "weak"

@@ -142,6 +142,17 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
 int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping, uint32_t* nvars_new, int* compressed,
                int32_t* lits_out, size_t nlits);
 
+/* K0: bulk ingest of a DIMACS literal stream, 0 terminates a clause (the CPaddLit sequence, libcoprocessorc.cc:251-266 ->
+ * Solver::addClause_, riss/core/Solver.cc:409-499, for a solver without assignments): per clause sort by literal code,
+ * drop duplicate literals, drop tautologies; the clause arena is built on the device exactly as cp3g_upload_packed would
+ * receive it from a host that ingested the stream literal by literal.  `n` must end on a terminating 0.
+ * *status: 0 = done; 1 = some clause becomes unit or empty (unit propagation while clauses are added is order dependent)
+ * or is longer than 4096 literals - the device data base is left empty, ingest on the host instead. */
+int cp3g_ingest(cp3g* g, const int32_t* stream, size_t n, uint32_t* nvars, uint32_t* nclauses, size_t* nlits, int* status);
+/* copy the arena to the host: lits[nlits] and 16-byte records {start:u32, size:24|flags:8 (bit 0 deleted, bits 1-2 the
+ * can_subsume / can_strengthen flags of a fresh clause), 0, 0} - the layout cp3g_upload_packed takes */
+int cp3g_download_arena(cp3g* g, int32_t* lits, void* records16);
+
 /* K8: stream compaction of the clause arena (CoprocessorData::garbageCollect / relocAll, CoprocessorTypes.h:1396-1550;
  * ClauseAllocator::reloc).  The literals of the live clauses are packed in clause order (exclusive scan of the live
  * sizes, gather), the holes left by deleted and shortened clauses disappear.  new_start[i] (nclauses entries) is the

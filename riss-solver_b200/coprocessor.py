@@ -211,6 +211,22 @@ class ScanService:
                                          off.ctypes.data, out.ctypes.data, int(off[-1])), "bve_resolve")
         return off, out[:int(off[-1])]
 
+    def ingest(self, stream):
+        """K0: build the device arena from a DIMACS literal stream; returns (status, nvars, nclauses, nlits) -
+        status 1 = the stream needs the sequential host ingest (unit / empty clause)"""
+        st = np.ascontiguousarray(stream, dtype=np.int32)
+        nv = C.c_uint32(0); nc = C.c_uint32(0); nl = C.c_size_t(0); status = C.c_int(1)
+        self._ck(self.L.cp3g_ingest(self.g, st.ctypes.data, st.size, C.byref(nv), C.byref(nc), C.byref(nl), C.byref(status)), "ingest")
+        return int(status.value), int(nv.value), int(nc.value), int(nl.value)
+
+    def download_arena(self):
+        """(literal pool, starts, sizes, flags) of the device data base"""
+        ncl = int(self.counter("nclauses")); nl = int(self.counter("nlits"))
+        lits = np.zeros(max(nl, 1), dtype=np.int32); rec = np.zeros((max(ncl, 1), 4), dtype=np.uint32)
+        self._ck(self.L.cp3g_download_arena(self.g, lits.ctypes.data, rec.ctypes.data), "download_arena")
+        rec = rec[:ncl]
+        return lits[:nl], rec[:, 0].copy(), (rec[:, 1] & 0xffffff).astype(np.uint32), (rec[:, 1] >> 24).astype(np.uint8)
+
     def compact(self, download=True):
         """K8: pack the clause arena (garbageCollect / relocAll); returns (new_start[nclauses], packed literal pool)"""
         ncl = int(self.counter("nclauses")); nl = int(self.counter("nlits"))

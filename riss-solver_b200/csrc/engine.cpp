@@ -234,7 +234,37 @@ void Engine::addLit(int x)
     while (nvars < v) { newVar(); }
     cur.push_back(2 * (v - 1) + (x < 0));
 }
-void Engine::addStream(const int32_t* s, size_t n) { for (size_t i = 0; i < n; ++i) { addLit(s[i]); } }
+// Bulk ingest.  A long stream into an empty solver goes to the device (K0 cp3g_ingest: per-clause sort, duplicate
+// literals, tautologies - Solver::addClause_ without assignments); the arena comes back for the host mirror and stays
+// on the device for the preprocessing that follows.  A stream with unit or empty clauses (unit propagation while
+// adding is order dependent), short streams and later additions take the literal-by-literal path.
+void Engine::addStream(const int32_t* s, size_t n)
+{
+    static const size_t bulk_min = getenv("CP3_INGEST_MIN") ? (size_t)atoll(getenv("CP3_INGEST_MIN")) : (size_t)262144;
+    if (n >= bulk_min && C.empty() && cur.empty() && trail.empty() && ok && !ing_built && clauses.empty() && cp3g_device_count() > 0) {
+        size_t m = n;
+        while (m > 0 && s[m - 1] != 0) { --m; }                    // complete clauses only
+        if (m) {
+            ensureGpu();
+            uint32_t nv = 0, nc = 0; size_t nl = 0; int st = 1;
+            int64_t t0 = now_ns();
+            if (cp3g_ingest(gpu, s, m, &nv, &nc, &nl, &st) != CP3G_OK) { die("bulk ingest failed"); }
+            if (st == 0) {
+                if ((int)nv > nvars) { assigns.resize((size_t)nv, (uint8_t)L_UNDEF); frozen.resize((size_t)nv, 0); nvars = (int)nv; }
+                pool.resize(nl); C.resize(nc);
+                if (cp3g_download_arena(gpu, pool.data(), C.data()) != CP3G_OK) { die("arena download failed"); }
+                clauses.resize(nc);
+                parallelFor(nc, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { clauses[i] = (uint32_t)i; C[i].stamp = scan_id; } });
+                n_live = nc; ca_size += 2.0 * (double)nc + (double)nl;
+                if (((size_t)nc >> 6) >= delbits.size()) { delbits.resize(((size_t)nc >> 6) + 1024, 0); }
+                dev_arena_ncl = nc; dev_arena_valid = true; ++n_bulk_ingests;
+                s += m; n -= m;
+            }
+            host_ns_gpuwait += now_ns() - t0;
+        }
+    }
+    for (size_t i = 0; i < n; ++i) { addLit(s[i]); }
+}
 void Engine::freeze(int dv) { while (nvars < dv) { newVar(); } frozen[dv - 1] = 1; }
 int Engine::litValue(int d) const
 {
@@ -291,7 +321,12 @@ void Engine::uploadAll()
     const uint32_t ncl = (uint32_t)C.size();
     static_assert(sizeof(ClauseInfo) == 16, "ClauseInfo is uploaded as a packed 16-byte record");
     int64_t t0 = now_ns();
-    if (cp3g_upload_packed(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), C.data()) != CP3G_OK) { die("upload failed"); }
+    // the arena is still on the device from the bulk ingest unless something was added, deleted or assigned since
+    const bool resident = dev_arena_valid && dev_arena_ncl == ncl && n_live == ncl && trail.empty() &&
+                          cp3g_counter(gpu, "nclauses") == (int64_t)ncl && cp3g_counter(gpu, "nlits") == (int64_t)pool.size() &&
+                          cp3g_counter(gpu, "nvars") == (int64_t)nvars;
+    dev_arena_valid = false;
+    if (!resident && cp3g_upload_packed(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), C.data()) != CP3G_OK) { die("upload failed"); }
     if (cp3g_build(gpu) != CP3G_OK) { die("occurrence build failed"); }
     host_ns_gpuwait += now_ns() - t0;
     dev_ncl = ncl; dev_uploaded = true;
@@ -2252,6 +2287,7 @@ int64_t Engine::stat(const char* s) const
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches) ST("arena_compactions", n_compactions)
+    ST("bulk_ingests", n_bulk_ingests)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
     ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("overlapped_str_scans", n_overlap)

@@ -138,7 +138,8 @@ private:
     // ---------------- device replica + scan cache
     cp3g* gpu = nullptr;
     bool dev_uploaded = false;
-    int64_t n_compactions = 0;
+    int64_t n_compactions = 0, n_bulk_ingests = 0;
+    uint32_t dev_arena_ncl = 0; bool dev_arena_valid = false;       // the device still holds the arena of the bulk ingest
     struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
     std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device

@@ -996,6 +996,89 @@ __global__ void k_shrink(ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits
     hdr[ids[i]] = h;
 }
 
+// ------------------------------------------------------------------------------------------ K0 bulk ingest
+static constexpr uint32_t ING_MAX_CLAUSE = 4096, ING_LOCAL = 32;
+// clause delimiters of the DIMACS stream + largest variable
+__global__ void k_ing_mark(const int32_t* __restrict__ S, uint32_t n, uint32_t* __restrict__ flag, uint32_t* __restrict__ maxvar)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t v = 0;
+    if (i < n) { const int32_t x = S[i]; flag[i] = x == 0 ? 1u : 0u; v = (uint32_t)(x < 0 ? -x : x); }
+    else if (i == n) { flag[i] = 0u; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { v = max(v, __shfl_xor_sync(0xffffffffu, v, d)); }
+    if ((threadIdx.x & 31) == 0 && v) { atomicMax(maxvar, v); }
+}
+__global__ void k_ing_ends(const int32_t* __restrict__ S, uint32_t n, const uint32_t* __restrict__ cid, uint32_t* __restrict__ cend)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && S[i] == 0) { cend[cid[i]] = i; }
+}
+// Solver::addClause_ (Solver.cc:409-499) without assignments: sort, drop duplicates, detect tautologies.  One thread
+// per raw clause; the normalised literals are left at the clause's own stream positions in `codes`.
+__global__ void k_ing_norm(const int32_t* __restrict__ S, const uint32_t* __restrict__ cend, uint32_t nraw,
+                           int32_t* __restrict__ codes, uint32_t* __restrict__ rsize, uint32_t* __restrict__ keep, uint32_t* __restrict__ status)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nraw) { return; }
+    if (c == nraw) { rsize[c] = 0; keep[c] = 0; return; }
+    const uint32_t b = c ? cend[c - 1] + 1 : 0u, e = cend[c], len = e - b;
+    rsize[c] = 0; keep[c] = 0;
+    if (len == 0 || len > ING_MAX_CLAUSE) { *status = 1u; return; }
+    auto code = [&](uint32_t i) -> int32_t { const int32_t x = S[b + i]; return x < 0 ? 2 * (-x - 1) + 1 : 2 * (x - 1); };
+    uint32_t j = 0; bool taut = false;
+    if (len <= ING_LOCAL) {
+        int32_t a[ING_LOCAL];
+        for (uint32_t i = 0; i < len; ++i) {
+            const int32_t key = code(i); uint32_t k = i;
+            while (k > 0 && a[k - 1] > key) { a[k] = a[k - 1]; --k; }
+            a[k] = key;
+        }
+        int32_t p = -2;
+        for (uint32_t i = 0; i < len; ++i) {
+            if (a[i] == (p ^ 1) && p >= 0) { taut = true; break; }
+            if (a[i] != p) { p = a[i]; codes[b + j++] = p; }
+        }
+    } else {
+        int32_t* a = codes + b;
+        for (uint32_t i = 0; i < len; ++i) {
+            const int32_t key = code(i); uint32_t k = i;
+            while (k > 0 && a[k - 1] > key) { a[k] = a[k - 1]; --k; }
+            a[k] = key;
+        }
+        int32_t p = -2;
+        for (uint32_t i = 0; i < len; ++i) {
+            const int32_t x = a[i];
+            if (x == (p ^ 1) && p >= 0) { taut = true; break; }
+            if (x != p) { p = x; a[j++] = p; }
+        }
+    }
+    if (taut) { return; }                      // dropped, like addClause_ returning true early
+    if (j == 1) { *status = 1u; return; }
+    rsize[c] = j; keep[c] = 1u;
+}
+__global__ void k_ing_pack(const uint32_t* __restrict__ cend, uint32_t nraw, const int32_t* __restrict__ codes,
+                           const uint32_t* __restrict__ rsize, const uint32_t* __restrict__ kid, const uint32_t* __restrict__ nstart,
+                           ClauseHdr* __restrict__ hdr, int32_t* __restrict__ lits)
+{
+    uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nraw) { return; }
+    const uint32_t sz = rsize[c];
+    if (!sz) { return; }
+    const uint32_t b = c ? cend[c - 1] + 1 : 0u, ns = nstart[c];
+    for (uint32_t k = 0; k < sz; ++k) { lits[ns + k] = codes[b + k]; }
+    ClauseHdr h; h.start = ns; h.szfl = sz; h.sig = 0;
+    hdr[kid[c]] = h;
+}
+__global__ void k_arena_records(const ClauseHdr* __restrict__ hdr, uint32_t n, uint4* __restrict__ rec)
+{
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    const ClauseHdr h = hdr[i];
+    const uint32_t fl = (h.szfl & FLAG_DEL) ? 1u : 0u;
+    rec[i] = make_uint4(h.start, (h.szfl & SIZE_MASK) | ((fl | 2u | 4u) << 24), 0u, 0u);
+}
+
 // ------------------------------------------------------------------------------------------ K8 arena compaction
 // live size of every clause (0 for deleted) -> exclusive scan -> new pool offsets
 __global__ void k_compact_sizes(const ClauseHdr* __restrict__ hdr, uint32_t n, uint32_t* __restrict__ sz)
@@ -1696,6 +1779,83 @@ int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     t.collect();
+    return CP3G_OK;
+}
+
+// exclusive scan of n u32 values (in -> out) on the handle stream; the total lands in counters[2]
+static int scan_u32(cp3g* g, const uint32_t* in, uint32_t* out, size_t n)
+{
+    const uint32_t nt = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    RESERVE(g->tile_sum, (size_t)nt + 1, false);
+    k_scan_tiles<<<nt, SCAN_T, 0, g->stream>>>(in, out, (uint32_t)n, g->tile_sum.p);
+    k_scan_sums<<<1, 1024, 0, g->stream>>>(g->tile_sum.p, nt, g->counters.p + 2);
+    k_scan_add<<<nt, SCAN_T, 0, g->stream>>>(out, (uint32_t)n, g->tile_sum.p);
+    g->launches += 3;
+    return CP3G_OK;
+}
+
+int cp3g_ingest(cp3g* g, const int32_t* stream, size_t n, uint32_t* nvars, uint32_t* nclauses, size_t* nlits, int* status)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    if (status) { *status = 1; }
+    if (n == 0 || n >= (size_t)0xfffffff0u || stream[n - 1] != 0) { return CP3G_OK; }
+    const uint32_t N = (uint32_t)n;
+    DevBuf<int32_t>& S = g->bl0;                     // the stream; bu0 = flags / sizes, bu1 = scans, bu2 = clause ends
+    RESERVE(S, n + 1, false); RESERVE(g->bu0, n + 2, false); RESERVE(g->bu1, n + 2, false);
+    CK(cudaMemcpyAsync(S.p, stream, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    g->h2d += (int64_t)n * 4;
+    CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
+    KTimer t(g);
+    k_ing_mark<<<grid_for(n + 1, 256), 256, 0, g->stream>>>(S.p, N, g->bu0.p, g->counters.p + 5);
+    if (scan_u32(g, g->bu0.p, g->bu1.p, n + 1) != CP3G_OK) { return CP3G_ERR_CUDA; }
+    uint32_t head[8];
+    CK(cudaMemcpyAsync(head, g->counters.p, sizeof(head), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    const uint32_t nraw = head[2], maxvar = head[5];
+    RESERVE(g->bu2, (size_t)nraw + 2, false); RESERVE(g->bu3, (size_t)nraw + 2, false); RESERVE(g->bu4, (size_t)nraw + 2, false);
+    RESERVE(g->lits2, n + 1, false);                 // normalised literals at their stream positions
+    k_ing_ends<<<grid_for(n, 256), 256, 0, g->stream>>>(S.p, N, g->bu1.p, g->bu2.p);
+    // bu0 := rsize, bu3 := keep
+    k_ing_norm<<<grid_for((size_t)nraw + 1, 128), 128, 0, g->stream>>>(S.p, g->bu2.p, nraw, g->lits2.p, g->bu0.p, g->bu3.p, g->counters.p + 6);
+    g->launches += 3;
+    CK(cudaMemcpyAsync(head, g->counters.p, sizeof(head), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    if (head[6]) { t.stop(); CK(cudaStreamSynchronize(g->stream)); t.collect(); return CP3G_OK; }      // units / empty / huge clause: host ingest
+    // clause ids (scan of keep -> bu4) and pool offsets (scan of rsize -> bu1)
+    if (scan_u32(g, g->bu3.p, g->bu4.p, (size_t)nraw + 1) != CP3G_OK) { return CP3G_ERR_CUDA; }
+    uint32_t kept = 0;
+    CK(cudaMemcpyAsync(&kept, g->counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    if (scan_u32(g, g->bu0.p, g->bu1.p, (size_t)nraw + 1) != CP3G_OK) { return CP3G_ERR_CUDA; }
+    uint32_t total = 0;
+    CK(cudaMemcpyAsync(&total, g->counters.p + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    g->nvars = maxvar; g->ncl = kept; g->nlits = total; g->ncl_csr = 0; g->ovf_host.clear(); g->dirty_since_build = true;
+    RESERVE(g->lits, (size_t)total + total / 4 + 1024, false);
+    RESERVE(g->hdr, (size_t)kept + kept / 4 + 1024, false);
+    if (nraw) { k_ing_pack<<<grid_for(nraw, 256), 256, 0, g->stream>>>(g->bu2.p, nraw, g->lits2.p, g->bu0.p, g->bu4.p, g->bu1.p, g->hdr.p, g->lits.p); g->launches++; }
+    t.stop();
+    int r = finish_upload(g, kept, total);
+    t.collect();
+    if (r != CP3G_OK) { return r; }
+    if (nvars) { *nvars = maxvar; } if (nclauses) { *nclauses = kept; } if (nlits) { *nlits = total; }
+    if (status) { *status = 0; }
+    return CP3G_OK;
+}
+
+int cp3g_download_arena(cp3g* g, int32_t* lits, void* records16)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    if (g->ncl) {
+        RESERVE(g->refs_tmp, (size_t)g->ncl * 4 + 4, false);     // staging for the 16-byte records (a build-time temporary)
+        k_arena_records<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->ncl, reinterpret_cast<uint4*>(g->refs_tmp.p));
+        g->launches++;
+        CK(cudaMemcpyAsync(records16, g->refs_tmp.p, (size_t)g->ncl * 16, cudaMemcpyDeviceToHost, g->stream));
+    }
+    if (g->nlits) { CK(cudaMemcpyAsync(lits, g->lits.p, g->nlits * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream)); }
+    CK(cudaStreamSynchronize(g->stream));
+    g->d2h += (int64_t)g->nlits * 4 + (int64_t)g->ncl * 16;
     return CP3G_OK;
 }
 

@@ -201,6 +201,40 @@ int cp3g_dense(cp3g* g, const uint8_t* keep, int frag, uint32_t* mapping, uint32
     g->nvars = kept; *compressed = 1; *nvars_new = kept; g->launches += 7;
     return CP3G_OK;
 }
+int cp3g_ingest(cp3g* g, const int32_t* S, size_t n, uint32_t* nvars, uint32_t* nclauses, size_t* nlits, int* status)
+{
+    *status = 1;
+    if (n == 0 || S[n - 1] != 0) { return CP3G_OK; }
+    std::vector<std::vector<int32_t>> cl; std::vector<int32_t> cur; uint32_t maxv = 0;
+    for (size_t i = 0; i < n; ++i) {
+        const int32_t x = S[i];
+        if (x != 0) { const uint32_t v = (uint32_t)(x < 0 ? -x : x); maxv = std::max(maxv, v); cur.push_back(x < 0 ? 2 * (-x - 1) + 1 : 2 * (x - 1)); continue; }
+        if (cur.empty() || cur.size() > 4096) { return CP3G_OK; }
+        std::sort(cur.begin(), cur.end());
+        std::vector<int32_t> out; bool taut = false; int32_t p = -2;
+        for (int32_t y : cur) { if (p >= 0 && y == (p ^ 1)) { taut = true; break; } if (y != p) { p = y; out.push_back(y); } }
+        cur.clear();
+        if (taut) { continue; }
+        if (out.size() == 1) { return CP3G_OK; }
+        cl.push_back(out);
+    }
+    g->nvars = maxv; g->cl.swap(cl); g->del.assign(g->cl.size(), 0); g->start.assign(g->cl.size(), 0); g->occ.clear();
+    size_t pos = 0;
+    for (size_t i = 0; i < g->cl.size(); ++i) { g->start[i] = pos; pos += g->cl[i].size(); }
+    g->nlits = pos;
+    *nvars = maxv; *nclauses = (uint32_t)g->cl.size(); *nlits = pos; *status = 0;
+    g->launches += 8;
+    return CP3G_OK;
+}
+int cp3g_download_arena(cp3g* g, int32_t* lits, void* records16)
+{
+    uint32_t* r = (uint32_t*)records16;
+    for (size_t i = 0; i < g->cl.size(); ++i) {
+        std::copy(g->cl[i].begin(), g->cl[i].end(), lits + g->start[i]);
+        r[4 * i] = (uint32_t)g->start[i]; r[4 * i + 1] = (uint32_t)g->cl[i].size() | (((g->del[i] ? 1u : 0u) | 6u) << 24); r[4 * i + 2] = r[4 * i + 3] = 0;
+    }
+    return CP3G_OK;
+}
 int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_cap, size_t* nlits_new)
 {
     size_t pos = 0;
@@ -221,6 +255,9 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "launches")) { return g->launches; }
     if (!strcmp(name, "scan_requests")) { return g->requests; }
     if (!strcmp(name, "scan_checks")) { return g->checks; }
+    if (!strcmp(name, "nclauses")) { return (int64_t)g->cl.size(); }
+    if (!strcmp(name, "nlits")) { return (int64_t)g->nlits; }
+    if (!strcmp(name, "nvars")) { return (int64_t)g->nvars; }
     return 0;
 }
 }

@@ -103,7 +103,7 @@ def test_freeze_blocks_elimination(mock):
     cp.close()
 
 
-FORCED = {"CP3_PARSUB_MIN": "0", "CP3_STATIC_MIN": "0", "CP3_BULK_MIN": "0", "CP3_THREADS": "3"}
+FORCED = {"CP3_PARSUB_MIN": "0", "CP3_STATIC_MIN": "0", "CP3_BULK_MIN": "0", "CP3_THREADS": "3", "CP3_INGEST_MIN": "0"}
 
 
 def test_forced_parallel_paths_fuzz(mock):

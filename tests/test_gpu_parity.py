@@ -211,6 +211,42 @@ def test_k3_k4_full_queue_kernel_equals_request_kernel(gen, shape):
     svc.close()
 
 
+def test_k0_bulk_ingest_matches_addclause_semantics(gen):
+    """K0 against a plain restatement of Solver::addClause_ without assignments (sort by literal code, drop duplicate
+    literals, drop tautologies); streams with a unit or an empty clause are handed back to the host"""
+    rng = np.random.default_rng(61)
+    lits, sizes = gen.random_ksat(3000, 14000, 3, seed=62, dup=0.05, sup=0.08, flip=0.08)
+    rows = []
+    ends = np.cumsum(sizes); starts = ends - sizes
+    for s0, e0 in zip(starts.tolist(), ends.tolist()):
+        r = lits[s0:e0].tolist()
+        u = rng.random()
+        if u < 0.05: r = r + [r[0]]                           # duplicate literal
+        elif u < 0.10: r = r + [-r[1]]                        # tautology
+        elif u < 0.12: r = r + rng.integers(1, 3000, size=40).tolist()    # longer than the register path
+        rng.shuffle(r)
+        rows.append(r)
+    stream = np.array([x for r in rows for x in r + [0]], np.int32)
+    want_l, want_s = [], []
+    for r in rows:
+        codes = sorted({2 * (abs(x) - 1) + (x < 0) for x in r})
+        if any((c ^ 1) in codes for c in codes): continue
+        want_l += codes; want_s.append(len(codes))
+    svc = rs.ScanService()
+    st, nv, nc, nl = svc.ingest(stream)
+    assert st == 0 and nv == int(np.abs(stream).max()) and nc == len(want_s) and nl == len(want_l)
+    pool, start, size, flags = svc.download_arena()
+    assert np.array_equal(size, np.array(want_s, np.uint32)) and np.array_equal(pool, np.array(want_l, np.int32))
+    assert np.array_equal(start, (np.cumsum(want_s) - np.array(want_s)).astype(np.uint32)) and np.all(flags == 6)
+    # the arena is a complete data base: build + scan answer like an uploaded copy
+    svc.build(); a, ca = svc.scan_all(rs.SUBSUME)
+    svc2 = rs.ScanService(); svc2.upload(nv, np.array(want_l, np.int32), np.array(want_s, np.int64)); svc2.build(); b, cb = svc2.scan_all(rs.SUBSUME)
+    assert ca == cb and np.array_equal(_hits_key(a), _hits_key(b))
+    for bad in ([1, 2, 0, 3, 0, 4, 5, 0], [1, 2, 0, 0, 4, 5, 0], [1, 1, 0, 2, 3, 0]):      # unit, empty, unit after dedupe
+        assert svc.ingest(np.array(bad, np.int32))[0] == 1
+    svc.close(); svc2.close()
+
+
 def test_k8_arena_compaction(gen):
     """K8 (garbageCollect / relocAll): after deleting and shortening clauses the packed pool is exactly the live
     literals in clause order, the offsets are their prefix sums, and the scans answer as before the move."""
@@ -305,9 +341,9 @@ def test_c2_size_properties(gen):
 
 
 def test_forced_parallel_paths_on_gpu(gen):
-    """same fuzz as test_fuzz_small_instances with the large-queue code paths (full-queue kernels k_full, time-indexed
-    subsumption commit, static strengthening plan, scan/commit overlap) forced on; thresholds are read once per
-    process, hence the subprocess"""
+    """same fuzz as test_fuzz_small_instances with the large-queue code paths (device bulk ingest K0, full-queue kernels
+    k_full, time-indexed subsumption commit, static strengthening plan, scan/commit overlap) forced on; thresholds are
+    read once per process, hence the subprocess"""
     import subprocess, sys
     code = (
         "import sys, os; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
@@ -322,7 +358,7 @@ def test_forced_parallel_paths_on_gpu(gen):
         "    d = compare(run_gpu(stream, opts), run_oracle(stream, opts))\n"
         "    if d: bad += 1; print(r, opts, d[:3])\n"
         "print('BAD', bad)\n") % (ROOT, ROOT)
-    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3")
+    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3", CP3_INGEST_MIN="0")
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "BAD 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
