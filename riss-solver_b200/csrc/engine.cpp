@@ -2206,16 +2206,46 @@ void Engine::preprocess()
 
 size_t Engine::output(int32_t* out, size_t cap) const
 {
-    size_t k = 0;
-    auto emit = [&](int32_t x) { if (k < cap) { out[k] = x; } ++k; };
-    for (int x : trail) { emit(toDimacs(x)); emit(0); }
-    for (uint32_t c : clauses) {
-        if (C[c].flag & F_DEL) { continue; }
-        const int32_t* l = CL(c);
-        for (uint32_t j = 0; j < C[c].size; ++j) { emit(toDimacs(l[j])); }
-        emit(0);
+    // trail units first, then solver->clauses in order (libcoprocessorc.cc:80-108); sizes per chunk, prefix, parallel fill
+    Engine* self = const_cast<Engine*>(this);
+    const size_t nc = clauses.size();
+    const size_t T = (size_t)std::max(1, nthreads);
+    std::vector<size_t> part(T + 1, 0);
+    self->parallelFor(nc, [&](size_t b, size_t e, int t) {
+        size_t a = 0;
+        for (size_t i = b; i < e; ++i) { const ClauseInfo& ci = C[clauses[i]]; if (!(ci.flag & F_DEL)) { a += (size_t)ci.size + 1; } }
+        part[(size_t)t + 1] = a;
+    });
+    for (size_t t = 1; t <= T; ++t) { part[t] += part[t - 1]; }      // (the second parallelFor below splits [0,nc) the same way)
+    const size_t total = 2 * trail.size() + part[T];
+    if (out == nullptr || cap < total) {
+        if (out != nullptr) {                        // short buffer: fill what fits, literal by literal
+            size_t k = 0;
+            auto emit = [&](int32_t x) { if (k < cap) { out[k] = x; } ++k; };
+            for (int x : trail) { emit(toDimacs(x)); emit(0); }
+            for (uint32_t c : clauses) {
+                if (C[c].flag & F_DEL) { continue; }
+                const int32_t* l = CL(c);
+                for (uint32_t j = 0; j < C[c].size; ++j) { emit(toDimacs(l[j])); }
+                emit(0);
+            }
+        }
+        return total;
     }
-    return k;
+    size_t k = 0;
+    for (int x : trail) { out[k++] = toDimacs(x); out[k++] = 0; }
+    const size_t base = k;
+    self->parallelFor(nc, [&](size_t b, size_t e, int t) {
+        size_t o = base + part[(size_t)t];
+        for (size_t i = b; i < e; ++i) {
+            const ClauseInfo& ci = C[clauses[i]];
+            if (ci.flag & F_DEL) { continue; }
+            const int32_t* l = pool.data() + ci.start;
+            for (uint32_t j = 0; j < ci.size; ++j) { out[o++] = toDimacs(l[j]); }
+            out[o++] = 0;
+        }
+    });
+    return total;
 }
 size_t Engine::nLiveClauses() const { size_t n = 0; for (uint32_t c : clauses) { n += !(C[c].flag & F_DEL); } return n; }
 size_t Engine::nLiveLits() const { size_t n = 0; for (uint32_t c : clauses) { if (!(C[c].flag & F_DEL)) { n += C[c].size; } } return n; }
