@@ -13,10 +13,21 @@
 namespace {
 struct Handle {                         // struct libcp3, libcoprocessorc.cc:12-24
     cp3::Engine eng;
+    // CPaddLit calls into a still empty solver are buffered and handed over as ONE stream (device bulk ingest K0)
+    // by the first call that looks at the solver; nothing observable depends on when the clauses arrive
+    std::vector<int32_t> pend; bool buffering = true;
     std::vector<int32_t> out; size_t outPos = 0; bool outReady = false;
     std::vector<uint8_t> model; size_t modelLit = 0;
 };
 inline Handle* H(void* p) { return (Handle*)p; }
+inline void sync(Handle* h)
+{
+    h->buffering = false;
+    if (h->pend.empty()) { return; }
+    std::vector<int32_t> s; s.swap(h->pend);
+    h->eng.addStream(s.data(), s.size());
+}
+inline Handle* HS(void* p) { Handle* h = (Handle*)p; sync(h); return h; }      // handle with the buffered literals delivered
 void applyOption(Handle* h, const char* o, bool strict)
 {
     int r = h->eng.opt.parse(o);
@@ -47,7 +58,7 @@ void* CPinit(const char* presetConfig)
     return h;
 }
 void CPdestroy(void** p) { if (p && *p) { delete H(*p); *p = nullptr; } }
-void CPpreprocess(void* p) { H(p)->eng.preprocess(); H(p)->outReady = false; }
+void CPpreprocess(void* p) { HS(p)->eng.preprocess(); H(p)->outReady = false; }
 
 void CPparseOptions(void* p, int* argc, char** argv, int strict)
 {
@@ -68,26 +79,30 @@ void CPparseOptionString(void* p, char* s)
     while (is >> tok) { applyOption(H(p), tok.c_str(), false); }
 }
 void CPsetPresetConfig(void* p, const char* preset) { H(p)->eng.opt.preset(preset); }
-void CPaddLit(void* p, int lit) { H(p)->eng.addLit(lit); H(p)->outReady = false; }
-void CPaddLits(void* p, const int32_t* s, size_t n) { H(p)->eng.addStream(s, n); H(p)->outReady = false; }
+void CPaddLit(void* p, int lit)
+{
+    Handle* h = H(p); h->outReady = false;
+    if (h->buffering) { h->pend.push_back(lit); } else { h->eng.addLit(lit); }
+}
+void CPaddLits(void* p, const int32_t* s, size_t n) { HS(p)->eng.addStream(s, n); H(p)->outReady = false; }
 float CPversion(void*) { return 7.1f; }
 
-int CPhasNextOutputLit(void* p) { ensureOutput(H(p)); return H(p)->outPos < H(p)->out.size() ? 1 : 0; }
+int CPhasNextOutputLit(void* p) { ensureOutput(HS(p)); return H(p)->outPos < H(p)->out.size() ? 1 : 0; }
 int CPnextOutputLit(void* p)
 {
-    Handle* h = H(p); ensureOutput(h);
+    Handle* h = HS(p); ensureOutput(h);
     if (h->outPos >= h->out.size()) { return 0; }
     return h->out[h->outPos++];
 }
-void CPresetOutput(void* p) { H(p)->outReady = false; ensureOutput(H(p)); }
-size_t CPgetOutput(void* p, int32_t* out, size_t cap) { return H(p)->eng.output(out, cap); }
-size_t CPoutputUnits(void* p) { return H(p)->eng.nTrail(); }
-size_t CPgetUndo(void* p, int32_t* out, size_t cap) { return H(p)->eng.undoStack(out, cap); }
-int64_t CPstat(void* p, const char* name) { return H(p)->eng.stat(name); }
+void CPresetOutput(void* p) { HS(p)->outReady = false; ensureOutput(H(p)); }
+size_t CPgetOutput(void* p, int32_t* out, size_t cap) { return HS(p)->eng.output(out, cap); }
+size_t CPoutputUnits(void* p) { return HS(p)->eng.nTrail(); }
+size_t CPgetUndo(void* p, int32_t* out, size_t cap) { return HS(p)->eng.undoStack(out, cap); }
+int64_t CPstat(void* p, const char* name) { return HS(p)->eng.stat(name); }
 int CPsetDistributed(void* p, int rank, int world, const void* id) { return H(p)->eng.setDistributed(rank, world, id); }
 
-void CPfreezeVariable(void* p, int variable) { H(p)->eng.freeze(variable < 0 ? -variable : variable); }
-int CPgetReplaceLiteral(void* p, int oldLit) { const int r = H(p)->eng.importLit(oldLit); return r == 0 ? oldLit : r; }   // libcoprocessorc.cc:198-203
+void CPfreezeVariable(void* p, int variable) { HS(p)->eng.freeze(variable < 0 ? -variable : variable); }
+int CPgetReplaceLiteral(void* p, int oldLit) { const int r = HS(p)->eng.importLit(oldLit); return r == 0 ? oldLit : r; }   // libcoprocessorc.cc:198-203
 
 void CPresetModel(void* p) { H(p)->model.clear(); H(p)->modelLit = 0; }
 void CPpushModelBool(void* p, int pol) { H(p)->model.push_back(pol == 0 ? cp3::L_FALSE : cp3::L_TRUE); }
@@ -98,7 +113,7 @@ void CPgiveModelLit(void* p, int literal)
     while (h->model.size() <= v) { h->model.push_back(cp3::L_UNDEF); }
     h->model[v] = literal > 0 ? cp3::L_TRUE : cp3::L_FALSE;
 }
-void CPpostprocessModel(void* p) { H(p)->eng.extendModel(H(p)->model); }
+void CPpostprocessModel(void* p) { HS(p)->eng.extendModel(H(p)->model); }
 int CPgetFinalModelLit(void* p)
 {
     Handle* h = H(p);
@@ -109,10 +124,10 @@ int CPgetFinalModelLit(void* p)
     return 0;
 }
 int CPmodelVariables(void* p) { return (int)H(p)->model.size(); }
-int CPnVars(void* p) { return H(p)->eng.nVars(); }
-int CPnClss(void* p) { return (int)(H(p)->eng.nLiveClauses() + H(p)->eng.nTrail()); }
-int CPnLits(void* p) { return (int)(H(p)->eng.nLiveLits() + H(p)->eng.nTrail()); }
-int CPok(void* p) { return H(p)->eng.okay() ? 1 : 0; }
-int CPlitFalsified(void* p, int lit) { return H(p)->eng.litValue(lit) == cp3::L_FALSE ? 1 : 0; }
+int CPnVars(void* p) { return HS(p)->eng.nVars(); }
+int CPnClss(void* p) { return (int)(HS(p)->eng.nLiveClauses() + H(p)->eng.nTrail()); }
+int CPnLits(void* p) { return (int)(HS(p)->eng.nLiveLits() + H(p)->eng.nTrail()); }
+int CPok(void* p) { return HS(p)->eng.okay() ? 1 : 0; }
+int CPlitFalsified(void* p, int lit) { return HS(p)->eng.litValue(lit) == cp3::L_FALSE ? 1 : 0; }
 
 } // extern "C"
