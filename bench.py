@@ -209,6 +209,7 @@ def main():
     codes = to_codes_sorted(lits, sizes)
     opts = SUSI + [f"-cp3_gpu_device={local}"]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    stream = torch.from_numpy(np.ascontiguousarray(stream, dtype=np.int32)).pin_memory().numpy()   # e2e input: pinned host memory
 
     def fresh_uid():
         # one ncclUniqueId per communicator: every Coprocessor instance of the sharded mode gets its own
