@@ -115,3 +115,32 @@ def test_forced_parallel_paths_fuzz(mock):
     p = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.abspath(__file__)), "fuzz_engine.py"), "250", "9001"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "0 mismatches" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+def test_literal_by_literal_clients_get_the_bulk_ingest(mock, gen):
+    """CPaddLit into an empty solver is buffered and delivered as one stream (K0) by the first observing call; the
+    result equals the literal-by-literal ingest, tautologies / duplicate literals / a trailing partial clause included"""
+    import subprocess, sys
+    code = (
+        "import sys, os; sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))\n"
+        "import numpy as np\n"
+        "import riss_solver_b200 as rs\n"
+        "from harness import load_gen\n"
+        "gen = load_gen(); lib = %r\n"
+        "lits, sizes = gen.random_ksat(400, 1700, 3, seed=8, dup=0.05, sup=0.05, flip=0.05)\n"
+        "stream = np.concatenate([gen.csr_to_stream(lits, sizes), np.array([5, -5, 6, 0, 7, 7, 8, 0, 9, 10], np.int32)])\n"
+        "outs = []\n"
+        "for mode in ('lit', 'stream'):\n"
+        "    cp = rs.Coprocessor(['-enabled_cp3', '-up', '-subsimp', '-bve'], lib_path=lib)\n"
+        "    if mode == 'lit':\n"
+        "        for x in stream.tolist(): cp.add_lit(x)\n"
+        "    else: cp.add_stream(stream)\n"
+        "    cp.add_lit(11); cp.add_lit(0)                      # completes the trailing clause (9 10 11)\n"
+        "    n0 = cp.n_vars(); cp.preprocess()\n"
+        "    outs.append((n0, cp.stat('bulk_ingests'), cp.output_stream().tolist(), cp.undo().tolist())); cp.close()\n"
+        "assert outs[0][1] == 1 and outs[1][1] == 1, (outs[0][1], outs[1][1])\n"
+        "assert outs[0][0] == outs[1][0] and outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]\n"
+        "print('INGEST_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.dirname(os.path.abspath(__file__))), mock)
+    env = dict(os.environ, CP3_INGEST_MIN="0")
+    p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and "INGEST_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
