@@ -59,7 +59,22 @@ static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 #ifndef CP3_MINBLOCKS
 #define CP3_MINBLOCKS 6
 #endif
-static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = 32, TCAP = TILE + GROUP_MAX, OFFCAP = TILE, TILE_ALIGNED = 0x80000000u;
+#ifndef CP3_GROUPMAX
+#define CP3_GROUPMAX 32
+#endif
+#ifndef CP3_OFFCAP
+#define CP3_OFFCAP CP3_TILE
+#endif
+#ifndef CP3_WORKCAP
+#define CP3_WORKCAP (2 * CP3_TILE)
+#endif
+#ifndef CP3_WQ
+#define CP3_WQ 64
+#endif
+#ifndef CP3_WH
+#define CP3_WH 32
+#endif
+static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = CP3_GROUPMAX, TCAP = TILE + GROUP_MAX, OFFCAP = CP3_OFFCAP, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
 
 struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
@@ -596,8 +611,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
 //   phase 2  the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
 //            which would otherwise stall 31 lanes behind one)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
-static constexpr int WQ_CAP = 64, WH_CAP = 32, FQ_WARPS = 4;
-static constexpr uint32_t WORK_CAP = 2 * TILE, DCHUNK = CP3_DCHUNK;     // flat work list per tile: (subsumer, <= 8 consecutive candidates)
+static constexpr int WQ_CAP = CP3_WQ, WH_CAP = CP3_WH, FQ_WARPS = 4;
+static constexpr uint32_t WORK_CAP = CP3_WORKCAP, DCHUNK = CP3_DCHUNK;     // flat work list per tile: (subsumer, <= 8 consecutive candidates)
 struct TileDesc { uint32_t s, n, x0, xe, xa, noff; bool pure; };
 __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
 {
