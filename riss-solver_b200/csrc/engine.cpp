@@ -1332,7 +1332,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     // (a) has no candidate hit, (b) is no candidate target of anybody and (c) walks two lists without deleted
     // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
     // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
-    contrib.assign(strq.size(), -1);
+    contrib.assign(strq.size(), -1); contrib_t.assign(strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
     static const size_t static_min = getenv("CP3_STATIC_MIN") ? (size_t)atoi(getenv("CP3_STATIC_MIN")) : 4096;
     bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
     if (static_valid) {
@@ -1418,11 +1418,23 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 const ClauseInfo ci = C[c];
                 if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
                 if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
-                if (c_str.slot[c] >= 0 || ((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }
+                const bool target = ((is_target[c >> 6] >> (c & 63)) & 1) != 0;
+                if (c_str.slot[c] >= 0) {
+                    // a record exists: own hits, or - for a candidate target - only the predicted shorter versions
+                    if (!target) { continue; }
+                    const CacheEnt* e0 = cached(c_str, c);
+                    if (!e0 || e0->hb != e0->he) { continue; }
+                }
                 const int32_t* s2 = pool.data() + ci.start; int minT = s2[0]; int best = dcq(minT >> 1);
                 for (uint32_t j = 1; j < ci.size; ++j) { const int dj = dcq(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
                 const int mn = minT, nm = minT ^ 1;
                 if (hasStale(mn) || hasStale(nm)) { continue; }
+                if (target) {
+                    // somebody's candidate target without hits of its own: inert as well IF its content is still the
+                    // planned one when its turn comes (checked there by the content version)
+                    contrib_t[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n); tmin[p2] = mn; plan_ver[p2] = ci.ver;
+                    continue;
+                }
                 contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
                 if (lazy) { C[c].flag &= ~F_STR; amax(&last_static_walk[mn], (int32_t)p2); amax(&last_static_walk[nm], (int32_t)p2); }
             }
@@ -1454,6 +1466,15 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 C[cr].flag &= ~F_STR;
                 ++n_fast; ++n_static;
                 if (pre_active) { const int mn = walk_min[end]; scanned_dyn[mn] = 1; scanned_dyn[mn ^ 1] = 1; }
+                continue;
+            }
+            if (static_valid && contrib_t[end] >= 0 && !hasToPropagate() && C[cr].ver == plan_ver[end] &&
+                (C[cr].flag & (F_STR | F_DEL)) == F_STR && opt.strength && (unlimited || str_steps + contrib_t[end] + 1 < str_lim)) {
+                // unchanged candidate target without own hits: what the walk below would do is add up two clean lists
+                str_steps += contrib_t[end];
+                C[cr].flag &= ~F_STR;
+                ++n_fast; ++n_tfast;
+                if (pre_active) { scanned_dyn[tmin[end]] = 1; scanned_dyn[tmin[end] ^ 1] = 1; }
                 continue;
             }
             if (end >= 16) {
@@ -2317,7 +2338,7 @@ int64_t Engine::stat(const char* s) const
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches) ST("arena_compactions", n_compactions)
-    ST("bulk_ingests", n_bulk_ingests)
+    ST("bulk_ingests", n_bulk_ingests) ST("queue_target_fast", n_tfast)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
     ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("overlapped_str_scans", n_overlap)

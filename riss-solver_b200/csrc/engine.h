@@ -138,7 +138,7 @@ private:
     // ---------------- device replica + scan cache
     cp3g* gpu = nullptr;
     bool dev_uploaded = false;
-    int64_t n_compactions = 0, n_bulk_ingests = 0;
+    int64_t n_compactions = 0, n_bulk_ingests = 0, n_tfast = 0;
     uint32_t dev_arena_ncl = 0; bool dev_arena_valid = false;       // the device still holds the arena of the bulk ingest
     struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
     std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
@@ -173,6 +173,7 @@ private:
     std::vector<int32_t> qtime;                      // strengthening queue: processing time of a pending clause
     int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0, n_static = 0;
     std::vector<int32_t> contrib;                    // per queue position: step contribution of a statically inert entry, or -1
+    std::vector<int32_t> contrib_t, tmin; std::vector<uint32_t> plan_ver;   // same for candidate targets, valid while the content version is the planned one
     std::vector<uint64_t> is_target;                 // clauses that some cached hit may modify
     int nthreads = 1;
     // up-front cleaning of certainly-walked lists (strengtheningWorker) and what is needed to take it back
