@@ -1320,6 +1320,8 @@ extern "C" int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const i
 
 static int build_csr(cp3g* g)
 {
+    // occurrence entries carry the clause index in 30 bits (two class bits on top): refuse larger data bases loudly
+    if (g->ncl > REF_MASK || g->nvars >= (1u << 30)) { g->err = "data base too large for the 30-bit clause references"; fprintf(stderr, "cp3b200: %s\n", g->err.c_str()); return CP3G_ERR_ARG; }
     const uint32_t nlit = 2 * g->nvars;
     RESERVE(g->occ_off, (size_t)nlit + 8, false);          // +8: the staged offset window of a tile is read in 16-byte units
     RESERVE(g->occ_tmp, (size_t)nlit + 2, false);
