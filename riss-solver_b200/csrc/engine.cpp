@@ -932,12 +932,22 @@ bool Engine::subsumptionCommitParallel()
     if (sub_dtime.size() < C.size()) { sub_dtime.resize(C.size() + 1024, INF); sub_pos.resize(C.size() + 1024, -1); }
     // step 0: queue position of every clause; a clause queued twice falls back to the ordered walk
     bool dups = false;
+    bool increasing = true;                              // a queue in clause order (the first round) cannot hold duplicates
     parallelFor(nq, [&](size_t b, size_t e, int) {
-        for (size_t p = b; p < e; ++p) {
-            const int32_t old = __atomic_exchange_n(&sub_pos[subq[p]], (int32_t)p, __ATOMIC_RELAXED);
-            if (old >= 0) { dups = true; }
-        }
+        bool inc = true;
+        for (size_t p = std::max<size_t>(b, 1); p < e && inc; ++p) { inc = subq[p - 1] < subq[p]; }
+        if (!inc) { increasing = false; }
     });
+    if (increasing) {
+        parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = (int32_t)p; } });
+    } else {
+        parallelFor(nq, [&](size_t b, size_t e, int) {
+            for (size_t p = b; p < e; ++p) {
+                const int32_t old = __atomic_exchange_n(&sub_pos[subq[p]], (int32_t)p, __ATOMIC_RELAXED);
+                if (old >= 0) { dups = true; }
+            }
+        });
+    }
     auto reset_pos = [&]() { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = -1; } }); };
     if (dups) { reset_pos(); return false; }
     lap("step0");
@@ -994,9 +1004,10 @@ bool Engine::subsumptionCommitParallel()
     // step 3: every queue entry picks its list with the counters of its own time.  Walks of lists that never hold
     // a deleted clause just add |list|-1 steps; the others become events for step 4.
     struct Ev { int32_t lit, time; uint32_t pos; };
-    std::vector<std::vector<Ev>> tev((size_t)nthreads + 1); std::vector<int64_t> tsteps((size_t)nthreads + 1, 0);
+    // events are filed per (producing thread, literal bucket), so that step 4 reads only what belongs to its bucket
+    std::vector<std::vector<Ev>> tev(((size_t)nthreads + 1) * (size_t)NB); std::vector<int64_t> tsteps((size_t)nthreads + 1, 0);
     parallelFor(nq, [&](size_t b, size_t e, int t) {
-        int64_t st = 0; std::vector<Ev>& ev = tev[t];
+        int64_t st = 0; std::vector<Ev>* ev = &tev[(size_t)t * (size_t)NB];
         for (size_t p = b; p < e; ++p) {
             const uint32_t cr = subq[p]; const ClauseInfo ci = C[cr];
             if (ci.flag & F_DEL) { continue; }
@@ -1006,7 +1017,7 @@ bool Engine::subsumptionCommitParallel()
             int mn = c[0]; int32_t best = countAt(mn, T);
             for (uint32_t l = 1; l < ci.size; ++l) { const int32_t v = countAt(c[l], T); if (v < best) { best = v; mn = c[l]; } }
             if (!((dl_any[(uint32_t)mn >> 6] >> (mn & 63)) & 1ull) && !hasStale(mn)) { st += hot[mn].n ? (int64_t)hot[mn].n - 1 : 0; }
-            else { ev.push_back({mn, T, (uint32_t)p}); }
+            else { ev[bucketOf(mn)].push_back({mn, T, (uint32_t)p}); }
         }
         tsteps[t] = st;
     });
@@ -1019,7 +1030,8 @@ bool Engine::subsumptionCommitParallel()
         for (size_t bk = bb; bk < be; ++bk) {
             const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
             std::vector<Ev> mine;
-            for (const auto& v : tev) { for (const Ev& x : v) { if (x.lit >= lo && x.lit < hi) { mine.push_back(x); } } }
+            for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) { const std::vector<Ev>& v = tev[t2 * (size_t)NB + bk]; mine.insert(mine.end(), v.begin(), v.end()); }
+            (void)lo; (void)hi;
             std::sort(mine.begin(), mine.end(), [](const Ev& a, const Ev& b) { return a.lit != b.lit ? a.lit < b.lit : a.time < b.time; });
             int64_t st = 0;
             for (size_t i = 0; i < mine.size();) {
