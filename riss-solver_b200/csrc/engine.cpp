@@ -377,7 +377,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     if (!scan_no_flush) { flushDevice(); }
     lap("flush");
     ++scan_id; ++n_scan_batches;
-    if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
+    pgrow(cache.slot, C.size(), -1);
     // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
     static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
     bool bulk = forceBulk == 1;
@@ -470,7 +470,7 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
 {
     if (reqs.empty()) { return; }
     ++scan_id; ++n_scan_batches; ++n_spec_rounds; n_spec_requests += (int64_t)reqs.size();
-    if (cache.slot.size() < C.size()) { cache.slot.resize(C.size(), -1); }
+    pgrow(cache.slot, C.size(), -1);
     std::vector<uint32_t> self(reqs.size()), roff(reqs.size() + 1); std::vector<int32_t> rl;
     roff[0] = 0;
     for (size_t i = 0; i < reqs.size(); ++i) {
@@ -824,7 +824,7 @@ void Engine::checkGarbage()
     // packed by the same rule - clause order, live sizes - so both keep identical offsets without a transfer.
     if (dev_uploaded) {
         flushDevice();
-        std::vector<int32_t> np; np.reserve(pool.size());
+        RawVec<int32_t> np; np.reserve(pool.size());
         for (size_t c = 0; c < C.size(); ++c) {
             const uint32_t ns = (uint32_t)np.size();
             if (C[c].flag & F_DEL) { C[c].size = 0; }
@@ -929,7 +929,7 @@ bool Engine::subsumptionCommitParallel()
     const int32_t INF = INT32_MAX;
     const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr; int64_t tt = now_ns();
     auto lap = [&](const char* w) { if (dbg) { int64_t n2 = now_ns(); fprintf(stderr, "  parsub %s %.1f ms\n", w, (n2 - tt) / 1e6); tt = n2; } };
-    if (sub_dtime.size() < C.size()) { sub_dtime.resize(C.size() + 1024, INF); sub_pos.resize(C.size() + 1024, -1); }
+    if (sub_dtime.size() < C.size()) { pgrow(sub_dtime, C.size() + 1024, INF); pgrow(sub_pos, C.size() + 1024, -1); }
     // step 0: queue position of every clause; a clause queued twice falls back to the ordered walk
     bool dups = false;
     bool increasing = true;                              // a queue in clause order (the first round) cannot hold duplicates
@@ -1244,7 +1244,7 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
         }
     }
     std::vector<uint32_t> ids;
-    if (c_str.slot.size() < C.size()) { c_str.slot.resize(C.size(), -1); }
+    pgrow(c_str.slot, C.size(), -1);
     for (uint32_t c : dirty_str) {
         if (c == cr || (C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
         if (cached(c_str, c)) { continue; }
@@ -1323,7 +1323,7 @@ void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
     scanClauses(CP3G_STRENGTHEN, ids, c_str, scan_no_flush ? (bulk ? 1 : 0) : -1);
     lap("scan");
     // processing time of the queue entries: the queue is drained from the back
-    if (qtime.size() < C.size()) { qtime.resize(C.size() + 1024, -1); }
+    if (qtime.size() < C.size()) { pgrow(qtime, C.size() + 1024, -1); }
     // (a clause queued twice keeps the time of its last entry, like the sequential fill)
     { bool inc = true; for (size_t i = 1; i < strq.size(); ++i) { if (strq[i - 1] >= strq[i]) { inc = false; break; } }
       const size_t nq = strq.size();
@@ -1359,7 +1359,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     // (a) has no candidate hit, (b) is no candidate target of anybody and (c) walks two lists without deleted
     // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
     // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
-    contrib.assign(strq.size(), -1); contrib_t.assign(strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
+    pfill(contrib, strq.size(), -1); pfill(contrib_t, strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
     static const size_t static_min = getenv("CP3_STATIC_MIN") ? (size_t)atoi(getenv("CP3_STATIC_MIN")) : 4096;
     bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
     if (static_valid) {
@@ -1377,7 +1377,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         //     cannot change before its turn (it is nobody's candidate target)
         std::vector<uint8_t> walked((size_t)2 * nvars, 0);
         std::vector<int64_t> bound((size_t)nthreads + 1, 0);
-        walk_min.assign(nq, -1); walk_count.assign((size_t)2 * nvars, 0u);
+        pfill(walk_min, nq, -1); walk_count.assign((size_t)2 * nvars, 0u);
         static_pass = true; static_nq = nq;
         parallelFor(nq, [&](size_t b, size_t e, int t) {
             int64_t bs = 0;
@@ -2129,7 +2129,7 @@ void Engine::initData()
     ph_upload += now_ns() - ti0; ti0 = now_ns();
     std::vector<uint32_t> off((size_t)n2 + 1, 0);
     if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
-    occ_pool.assign((size_t)off[n2] + 16, 0);
+    occ_pool.resize((size_t)off[n2] + 16);                 // filled by the download below
     if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
     for (int x = 0; x < n2; ++x) {
         occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];

@@ -52,6 +52,17 @@ struct Options {
 
 struct Tech { int penalty = 0, peak = 0; bool modified = false; };
 
+// std::vector whose resize() leaves trivially constructible elements uninitialised: the big work arrays are filled by a
+// device download or by a parallel loop right after they are sized, a serial zero fill first would only cost bandwidth
+template <class T> struct NoInitAlloc : std::allocator<T> {
+    template <class U> struct rebind { typedef NoInitAlloc<U> other; };
+    NoInitAlloc() = default;
+    template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    template <class U> void construct(U* p) { (void)p; }
+    template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
+
 struct Hit { uint32_t clause; int32_t lit; };
 
 // occurrence list: slice of one pooled array; grows by relocation to the pool end
@@ -97,10 +108,10 @@ private:
     void extendByUndo(std::vector<uint8_t>& model) const;
     std::vector<uint8_t> assigns, frozen;
     std::vector<int> trail;
-    std::vector<int32_t> pool;                       // literal pool (codes)
+    RawVec<int32_t> pool;                            // literal pool (codes)
     // per clause: pool offset, size + flags, edit counter, scan count at the last edit - one 16-byte record
     struct ClauseInfo { uint32_t start; uint32_t size : 24; uint32_t flag : 8; uint32_t ver; uint32_t stamp; };
-    std::vector<ClauseInfo> C;
+    RawVec<ClauseInfo> C;
     std::vector<uint32_t> clauses;                   // solver->clauses
     double ca_size = 0, ca_wasted = 0;
     int simpDB_assigns = -1; int64_t simpDB_props = 0;
@@ -109,7 +120,7 @@ private:
 
     // ---------------- CoprocessorData mirror
     bool data_ready = false;
-    std::vector<OccList> occ; std::vector<LitHot> hot; std::vector<uint32_t> occ_pool;
+    std::vector<OccList> occ; std::vector<LitHot> hot; RawVec<uint32_t> occ_pool;
     std::vector<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
     inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
     inline bool hasStale(int x) const { return (stalebits[(uint32_t)x >> 6] >> (x & 63)) & 1; }
@@ -155,7 +166,7 @@ private:
     // scanned by id, or by the literal content itself (ver == UINT32_MAX) for speculative versions
     struct CacheEnt { uint32_t ver, scan, hb, he; int32_t next; uint32_t lit_off, lit_n; double time; };
     struct ScanCache {
-        std::vector<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; std::vector<int32_t> lits;
+        RawVec<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; std::vector<int32_t> lits;
         // a full-queue bulk scan covers every clause that was live at that time: clauses without an entry had
         // no hit (no per-request record is kept for them)
         bool bulk_all = false; uint32_t bulk_scan = 0, bulk_ncl = 0; CacheEnt empty;
@@ -170,16 +181,16 @@ private:
     std::vector<int32_t> spec_lits;
     void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache);
     void prefetchStrengthenClosure();
-    std::vector<int32_t> qtime;                      // strengthening queue: processing time of a pending clause
+    RawVec<int32_t> qtime;                           // strengthening queue: processing time of a pending clause
     int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0, n_static = 0;
-    std::vector<int32_t> contrib;                    // per queue position: step contribution of a statically inert entry, or -1
-    std::vector<int32_t> contrib_t, tmin; std::vector<uint32_t> plan_ver;   // same for candidate targets, valid while the content version is the planned one
+    RawVec<int32_t> contrib;                         // per queue position: step contribution of a statically inert entry, or -1
+    RawVec<int32_t> contrib_t, tmin; RawVec<uint32_t> plan_ver;   // same for candidate targets, valid while the content version is the planned one
     std::vector<uint64_t> is_target;                 // clauses that some cached hit may modify
     int nthreads = 1;
     // up-front cleaning of certainly-walked lists (strengtheningWorker) and what is needed to take it back
     struct PreList { int lit; uint32_t snap_off, old_n, extra; };
     std::vector<PreList> pre_lists; std::vector<uint32_t> pre_snap; std::vector<uint8_t> scanned_dyn;
-    std::vector<int32_t> pre_index, walk_min; std::vector<uint32_t> walk_count;   // per literal / per queue position
+    std::vector<int32_t> pre_index; RawVec<int32_t> walk_min; std::vector<uint32_t> walk_count;   // per literal / per queue position
     bool pre_active = false, static_pass = false; size_t static_nq = 0;
     // lazy form of the static plan: the inert entries' F_STR flags are cleared up front (in parallel) and the ordered
     // walk only adds their step contribution; cur_end = queue position being processed (everything above is done)
@@ -193,6 +204,10 @@ private:
     template <class F> void parallelFor(size_t n, F f, size_t grain = 65536);
     template <class F> void parallelForG(size_t n, size_t grain, F f) { parallelFor(n, f, grain); }
     // stable parallel filter: out = [x in src | pred(x)] (count per chunk, prefix, write)
+    // size a work array and fill it on all cores
+    template <class V, class T> void pfill(V& v, size_t n, T val) { v.resize(n); parallelFor(n, [&](size_t b, size_t e, int) { std::fill(v.begin() + (std::ptrdiff_t)b, v.begin() + (std::ptrdiff_t)e, val); }); }
+    // grow a work array to n elements, new elements = val (existing ones are kept)
+    template <class V, class T> void pgrow(V& v, size_t n, T val) { const size_t o = v.size(); if (n <= o) { return; } v.resize(n); parallelFor(n - o, [&](size_t b, size_t e, int) { std::fill(v.begin() + (std::ptrdiff_t)(o + b), v.begin() + (std::ptrdiff_t)(o + e), val); }); }
     template <class P> void parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred);
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
@@ -271,7 +286,7 @@ private:
     bool overlap_str = false, str_prepared = false, scan_no_flush = false;
     void prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk);
     int64_t n_overlap = 0;                // time-indexed, data-parallel form of the queue walk
-    std::vector<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
+    RawVec<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
     int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
