@@ -981,7 +981,7 @@ bool Engine::subsumptionCommitParallel()
     const size_t bwidth = std::max<size_t>(64, (nlit / NB) / 64 * 64);
     auto bucketOf = [&](int x) -> int { int bk = (int)std::min<size_t>((size_t)NB - 1, (size_t)x / bwidth); while (bk > 0 && x < bucketLo(bk)) { --bk; } while (bk + 1 < NB && x >= bucketLo(bk + 1)) { ++bk; } return bk; };
     std::vector<std::vector<LT>> dlb((size_t)NB);
-    if (dl_start.size() < nlit) { dl_start.assign(nlit, -1); dl_cnt.assign(nlit, 0u); dl_any.assign((nlit >> 6) + 1, 0ull); }
+    if (dl_start.size() < nlit) { pfill(dl_start, nlit, -1); pfill(dl_cnt, nlit, 0u); dl_any.assign((nlit >> 6) + 1, 0ull); }
     parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
         for (size_t bk = bb; bk < be; ++bk) {
             const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
@@ -1377,7 +1377,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         //     cannot change before its turn (it is nobody's candidate target)
         std::vector<uint8_t> walked((size_t)2 * nvars, 0);
         std::vector<int64_t> bound((size_t)nthreads + 1, 0);
-        pfill(walk_min, nq, -1); walk_count.assign((size_t)2 * nvars, 0u);
+        pfill(walk_min, nq, -1); pfill(walk_count, (size_t)2 * nvars, 0u);
         static_pass = true; static_nq = nq;
         parallelFor(nq, [&](size_t b, size_t e, int t) {
             int64_t bs = 0;
@@ -2118,7 +2118,7 @@ void Engine::initData()
 {
     PhaseTimer pt(ph_init);
     const int n2 = 2 * nvars;
-    occ.assign((size_t)n2, OccList()); hot.assign((size_t)n2, LitHot()); stale.assign((size_t)n2, 0u);
+    pfill(occ, (size_t)n2, OccList()); pfill(hot, (size_t)n2, LitHot()); stale.assign((size_t)n2, 0u);
     stalebits.assign(((size_t)n2 >> 6) + 1, 0ull);
     modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
     var_touch.assign((size_t)std::max(nvars, 1), 0); bve_inpend.assign((size_t)std::max(nvars, 1), 0); bve_pending.clear();

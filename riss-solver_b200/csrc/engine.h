@@ -120,7 +120,7 @@ private:
 
     // ---------------- CoprocessorData mirror
     bool data_ready = false;
-    std::vector<OccList> occ; std::vector<LitHot> hot; RawVec<uint32_t> occ_pool;
+    RawVec<OccList> occ; RawVec<LitHot> hot; RawVec<uint32_t> occ_pool;
     std::vector<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
     inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
     inline bool hasStale(int x) const { return (stalebits[(uint32_t)x >> 6] >> (x & 63)) & 1; }
@@ -190,7 +190,7 @@ private:
     // up-front cleaning of certainly-walked lists (strengtheningWorker) and what is needed to take it back
     struct PreList { int lit; uint32_t snap_off, old_n, extra; };
     std::vector<PreList> pre_lists; std::vector<uint32_t> pre_snap; std::vector<uint8_t> scanned_dyn;
-    std::vector<int32_t> pre_index; RawVec<int32_t> walk_min; std::vector<uint32_t> walk_count;   // per literal / per queue position
+    std::vector<int32_t> pre_index; RawVec<int32_t> walk_min; RawVec<uint32_t> walk_count;   // per literal / per queue position
     bool pre_active = false, static_pass = false; size_t static_nq = 0;
     // lazy form of the static plan: the inert entries' F_STR flags are cleared up front (in parallel) and the ordered
     // walk only adds their step contribution; cur_end = queue position being processed (everything above is done)
@@ -286,7 +286,7 @@ private:
     bool overlap_str = false, str_prepared = false, scan_no_flush = false;
     void prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk);
     int64_t n_overlap = 0;                // time-indexed, data-parallel form of the queue walk
-    RawVec<int32_t> sub_dtime, sub_pos; std::vector<int32_t> dl_start; std::vector<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
+    RawVec<int32_t> sub_dtime, sub_pos; RawVec<int32_t> dl_start; RawVec<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
     int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
