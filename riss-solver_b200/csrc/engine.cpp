@@ -1008,6 +1008,7 @@ bool Engine::subsumptionCommitParallel()
     std::vector<std::vector<Ev>> tev(((size_t)nthreads + 1) * (size_t)NB); std::vector<int64_t> tsteps((size_t)nthreads + 1, 0);
     parallelFor(nq, [&](size_t b, size_t e, int t) {
         int64_t st = 0; std::vector<Ev>* ev = &tev[(size_t)t * (size_t)NB];
+        for (int k = 0; k < NB; ++k) { ev[k].reserve((e - b) / (size_t)NB / 2 + 64); }     // about half of the entries walk a list with deaths
         for (size_t p = b; p < e; ++p) {
             const uint32_t cr = subq[p]; const ClauseInfo ci = C[cr];
             if (ci.flag & F_DEL) { continue; }
@@ -1030,6 +1031,7 @@ bool Engine::subsumptionCommitParallel()
         for (size_t bk = bb; bk < be; ++bk) {
             const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
             std::vector<Ev> mine;
+            { size_t tot = 0; for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) { tot += tev[t2 * (size_t)NB + bk].size(); } mine.reserve(tot); }
             for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) { const std::vector<Ev>& v = tev[t2 * (size_t)NB + bk]; mine.insert(mine.end(), v.begin(), v.end()); }
             (void)lo; (void)hi;
             std::sort(mine.begin(), mine.end(), [](const Ev& a, const Ev& b) { return a.lit != b.lit ? a.lit < b.lit : a.time < b.time; });
