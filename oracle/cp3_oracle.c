@@ -20,6 +20,8 @@
 
 /* ------------------------------------------------------------------ small containers */
 typedef struct { int* v; int n, cap; } ivec;
+typedef struct { int cref, blocker, bin; } watcher_t;     /* Riss::Watcher: clause, blocking literal, binary flag */
+typedef struct { watcher_t* v; int n, cap; } wvec;
 static void iv_push(ivec* a, int x)
 {
     if (a->n == a->cap) {
@@ -37,6 +39,7 @@ static void iv_release(ivec* a) { free(a->v); a->v = NULL; a->n = a->cap = 0; }
 #define F_DEL 1u
 #define F_SUB 2u
 #define F_STR 4u
+#define F_PERM 8u   /* literal order changed by Solver::propagate, see ingest_propagate */
 #define L_TRUE 0
 #define L_FALSE 1
 #define L_UNDEF 2
@@ -64,10 +67,11 @@ struct cp3o {
     ivec clauses;                               /* solver->clauses */
     double ca_size, ca_wasted;                  /* RegionAllocator size()/wasted() in 32-bit words */
     int simpDB_assigns; int64_t simpDB_props;
-    ivec* ing_occ; int ing_built;               /* stand-in for the solver's watches during CPaddLit */
+    wvec* watches; int ing_built;               /* two-watched-literal lists while clauses are added (see ingest_propagate) */
+    ivec permuted;                              /* clauses whose literal order propagate() changed; re-sorted by sortClauses */
     ivec cur;                                   /* clause under construction */
     /* CoprocessorData (coprocessor/CoprocessorTypes.h:59-412) */
-    int data_ready;
+    int data_ready; int data_nvars;            /* CoprocessorData::numberOfVars: 0 until the first data.init() */
     ivec* occ; int* cnt; int numberOfCls;
     ivec subq, strq, undo;
     uint32_t* modTimer; uint32_t modStep;
@@ -106,8 +110,8 @@ static void new_var(cp3o* o)
     o->frozen = (unsigned char*)realloc(o->frozen, (size_t)n);
     o->assigns[n - 1] = L_UNDEF; o->frozen[n - 1] = 0;
     if (o->ing_built) {
-        o->ing_occ = (ivec*)realloc(o->ing_occ, sizeof(ivec) * 2 * (size_t)n);
-        memset(&o->ing_occ[2 * (n - 1)], 0, 2 * sizeof(ivec));
+        o->watches = (wvec*)realloc(o->watches, sizeof(wvec) * 2 * (size_t)n);
+        memset(&o->watches[2 * (n - 1)], 0, 2 * sizeof(wvec));
     }
     o->nvars = n;
 }
@@ -165,36 +169,83 @@ static void remove_pos_unsorted(cp3o* o, int c, int pos)
 /* ------------------------------------------------------------------ ingest: Solver::addClause_ (Solver.cc:409-499) */
 static int cmp_int(const void* a, const void* b) { int x = *(const int*)a, y = *(const int*)b; return (x > y) - (x < y); }
 
-/* Stand-in for Solver::propagate() at decision level 0 while clauses are being added.  The reference
- * walks two-watched-literal lists; the implied literal SET is the same, the trail ORDER of implied
- * literals may differ (documented in DESIGN.md: inputs with unit clauses compare canonically). */
+/* Solver::propagate(true) at decision level 0 while clauses are being added (riss/core/Solver.cc:1809-1937) over the
+ * two-watched-literal lists of Solver::attachClause (Solver.cc:692-708).  The TRAIL ORDER of implied literals is a
+ * function of the watch-list order, the blocker literals and the way propagate() permutes the literals of the clauses
+ * it visits (c[0]/c[1] swap, new watch moved to c[1]) - all restated here.  The permuted clauses are put back into
+ * sorted order where the reference does it: Preprocessor::sortClauses (Coprocessor.cc:118,1447-1463).
+ * watches[p] holds the clauses that watch ~p.  The lists are built at the first unit (until then no clause has been
+ * visited, so every clause watches its first two sorted literals, attached in clause order). */
+static void wv_push(wvec* a, watcher_t w)
+{
+    if (a->n == a->cap) { a->cap = a->cap ? 2 * a->cap : 4; a->v = (watcher_t*)realloc(a->v, sizeof(watcher_t) * (size_t)a->cap); }
+    a->v[a->n++] = w;
+}
+static void attach_clause(cp3o* o, int c)
+{
+    const int* l = CL(o, c); const int bin = o->csize[c] == 2;
+    watcher_t w0 = {c, l[1], bin}, w1 = {c, l[0], bin};
+    wv_push(&o->watches[LNEG(l[0])], w0);
+    wv_push(&o->watches[LNEG(l[1])], w1);
+}
+static void note_permuted(cp3o* o, int c)
+{
+    if (!(o->cflag[c] & F_PERM)) { o->cflag[c] |= F_PERM; iv_push(&o->permuted, c); }
+}
 static int ingest_propagate(cp3o* o)
 {
     if (!o->ing_built) {
-        o->ing_occ = (ivec*)calloc((size_t)(2 * o->nvars > 0 ? 2 * o->nvars : 1), sizeof(ivec));
+        o->watches = (wvec*)calloc((size_t)(2 * o->nvars > 0 ? 2 * o->nvars : 1), sizeof(wvec));
         o->ing_built = 1;
-        for (int i = 0; i < o->clauses.n; ++i) {
-            int c = o->clauses.v[i]; int* l = CL(o, c);
-            for (int j = 0; j < o->csize[c]; ++j) { iv_push(&o->ing_occ[l[j]], c); }
-        }
+        for (int i = 0; i < o->clauses.n; ++i) { attach_clause(o, o->clauses.v[i]); }
     }
+    wvec* W = o->watches;
+    int confl = 0;
     while (o->qhead < o->trail.n) {
-        int p = o->trail.v[o->qhead++];
-        ivec* ws = &o->ing_occ[LNEG(p)];
-        for (int i = 0; i < ws->n; ++i) {
-            int c = ws->v[i]; int* l = CL(o, c);
-            int unassigned = -1, nun = 0, sat = 0;
-            for (int j = 0; j < o->csize[c]; ++j) {
-                int v = value_lit(o, l[j]);
-                if (v == L_TRUE) { sat = 1; break; }
-                if (v == L_UNDEF) { unassigned = l[j]; ++nun; }
+        const int p = o->trail.v[o->qhead++];
+        wvec* ws = &W[p];
+        int i = 0, j = 0; const int end = ws->n;
+        while (i != end) {
+            watcher_t wi = ws->v[i];
+            if (wi.bin) {
+                const int vi = value_lit(o, wi.blocker);
+                if (vi == L_FALSE) {                        /* opt_long_conflict is off: stop at the first conflict */
+                    confl = 1;
+                    while (i < end) { ws->v[j++] = ws->v[i++]; }
+                    ws->n = j;
+                    return 0;
+                } else if (vi == L_UNDEF) { unchecked_enqueue(o, wi.blocker); }
+                ws->v[j++] = ws->v[i++];
+                continue;
             }
-            if (sat) { continue; }
-            if (nun == 0) { return 0; }
-            if (nun == 1) { unchecked_enqueue(o, unassigned); }
+            if (value_lit(o, wi.blocker) == L_TRUE) { ws->v[j++] = ws->v[i++]; continue; }
+            const int c = wi.cref; int* l = CL(o, c); const int n = o->csize[c];
+            const int false_lit = LNEG(p);
+            if (l[0] == false_lit) { l[0] = l[1]; l[1] = false_lit; note_permuted(o, c); }
+            i++;
+            const int first = l[0];
+            watcher_t w = {c, first, 0};
+            if (first != wi.blocker && value_lit(o, first) == L_TRUE) { ws->v[j++] = w; continue; }
+            int moved = 0;
+            for (int k = 2; k < n; ++k) {
+                if (value_lit(o, l[k]) != L_FALSE) {
+                    l[1] = l[k]; l[k] = false_lit; note_permuted(o, c);
+                    wv_push(&W[LNEG(l[1])], w);
+                    ws = &W[p];                             /* (the push cannot touch W[p]: l[1] != ~p) */
+                    moved = 1; break;
+                }
+            }
+            if (moved) { continue; }
+            ws->v[j++] = w;
+            if (value_lit(o, first) == L_FALSE) {
+                confl = 1;
+                o->qhead = o->trail.n;
+                while (i < end) { ws->v[j++] = ws->v[i++]; }
+            } else { unchecked_enqueue(o, first); }
         }
+        ws->n = j;
     }
-    return 1;
+    return !confl;
 }
 
 static void add_clause(cp3o* o, int* ps, int n)
@@ -216,7 +267,7 @@ static void add_clause(cp3o* o, int* ps, int n)
     }
     int c = alloc_clause(o, ps, n);
     iv_push(&o->clauses, c);
-    if (o->ing_built) { for (int i = 0; i < n; ++i) { iv_push(&o->ing_occ[ps[i]], c); } }
+    if (o->ing_built) { attach_clause(o, c); }
 }
 
 void cp3o_add(cp3o* o, const int32_t* s, size_t n)
@@ -638,8 +689,9 @@ static int subsumption_process(cp3o* o, int doStrengthen, int use_heap, int igno
         clear_queue(o, &o->strq, F_STR);
         return 0;
     }
-    /* size gate (Subsumption.cc:102) needs nTotLits() > cp3_susi_lits; tot_literals only counts learnt
-     * literals (riss/core/Solver.cc:1431) and is 0 while preprocessing, so the gate never fires */
+    /* size gate Subsumption.cc:102 (cp3_susi_vars && cp3_susi_cls && cp3_susi_lits): nTotLits() is 0 here - cleanSolver()
+     * (Coprocessor.cc:1395-1406) zeroes clauses_literals before any technique runs - so the conjunction never holds.
+     * Verified against the compiled reference with all three limits set to 10. */
     if (!(o->sub_steps + o->call_inc < o->sub_lim)) { o->sub_lim += o->call_inc; o->limitIncreases++; }
     if (!(o->str_steps + o->call_inc < o->str_lim)) { o->str_lim += o->call_inc; o->limitIncreases++; }
     while (o->ok && (o->subq.n > 0 || o->strq.n > 0)) {
@@ -1049,8 +1101,13 @@ static void init_data(cp3o* o)
         o->clauses.v[kept++] = c;
     }
     o->clauses.n = kept;
-    /* clauses are already sorted by toInt(lit): addClause_ sorts (Solver.cc:415), so sortClauses is a no-op */
-    o->data_ready = 1;
+    /* sortClauses (Coprocessor.cc:118,1447-1463): addClause_ sorts (Solver.cc:415), only the clauses propagate() permuted need it */
+    for (int i = 0; i < o->permuted.n; ++i) {
+        int c = o->permuted.v[i];
+        qsort(CL(o, c), (size_t)o->csize[c], sizeof(int), cmp_int); o->cflag[c] &= ~F_PERM;
+    }
+    o->permuted.n = 0;
+    o->data_ready = 1; o->data_nvars = o->nvars;
 }
 
 /* ------------------------------------------------------------------ Dense::compress (techniques/Dense.cc:26-238)
@@ -1100,7 +1157,7 @@ static void dense_compress(cp3o* o)
         const int to = mapping[v];
         if (to >= 0 && to != v) { o->assigns[to] = o->assigns[v]; o->assigns[v] = L_UNDEF; o->frozen[to] = o->frozen[v]; o->frozen[v] = 0; }
     }
-    o->nvars = n - diff;
+    o->nvars = n - diff; o->data_nvars = o->nvars;                              /* CoprocessorTypes.h:725 */
     free(count);
 }
 
@@ -1143,15 +1200,21 @@ void cp3o_init_only(cp3o* o)
 
 void cp3o_preprocess(cp3o* o)
 {
-    /* Coprocessor.cc:1002-1006: data.nVars() is still 0 before data.init() and nTotLits() only counts
-     * learnt literals, so only the clause-count gate can fire on the first preprocess() call */
-    if (o->limited && o->clauses.n > o->cp3_cls) { return; }
+    /* Coprocessor.cc:1002-1006: the size gates.  data.nVars() is CoprocessorData::numberOfVars - still 0 before the first
+     * data.init(); nTotLits() = clauses_literals + learnts_literals (riss/core/Solver.h:1867), the literals of all attached
+     * clauses (Solver::attachClause, Solver.cc:706-707): every stored clause here, there are no learnt clauses */
+    if (o->limited) {
+        uint32_t totlits = 0;
+        for (int i = 0; i < o->clauses.n; ++i) { totlits += (uint32_t)o->csize[o->clauses.v[i]]; }
+        if ((uint32_t)o->data_nvars > (uint32_t)o->cp3_vars || o->clauses.n > o->cp3_cls || totlits > (uint32_t)o->cp3_lits) { return; }
+    }
     if (!o->enabled) { return; }
     if (!solver_simplify(o)) { return; }
     init_data(o);
     int status = L_UNDEF;
     for (int it = 0; it < o->iters; ++it) {
         if (o->opt_up) { if (status == L_UNDEF) { status = propagation_process(o, 1, 0, VAR_UNDEF); } }
+        check_garbage(o);                       /* unconditional checkpoints behind the UP / XOR / ENT blocks, Coprocessor.cc:156,171 */
         if (!o->ok) { break; }
         if (o->opt_subsimp) {
             if (status == L_UNDEF) { subsumption_process(o, 1, 0, VAR_UNDEF); }
@@ -1281,6 +1344,9 @@ int cp3o_option(cp3o* o, const char* opt)
     BOPT("bve_early", bve_early) BOPT("bce_only", bce_only) BOPT("dense", opt_dense) BOPT("cp3_keep_set", dense_keep_set)
     IOPT("cp3_dense_frag", dense_frag)
     IOPT("cp3_iters", iters) IOPT("cp3_vars", cp3_vars) IOPT("cp3_cls", cp3_cls) IOPT("cp3_lits", cp3_lits)
+    /* technique-level size gates: accepted, without effect (see subsumption_process) */
+    if ((!strcmp(name, "cp3_susi_vars") || !strcmp(name, "cp3_susi_cls") || !strcmp(name, "cp3_susi_lits") ||
+         !strcmp(name, "cp3_bve_vars") || !strcmp(name, "cp3_bve_cls") || !strcmp(name, "cp3_bve_lits")) && eq) { return 1; }
     IOPT("cp3_call_inc", call_inc) IOPT("cp3_bve_limit", bve_limit) IOPT("cp3_bve_heap", bve_heap)
     IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t) IOPT("bve_heap_updates", bve_heap_updates)
     if (!strcmp(name, "cp3_sub_limit") && eq) { o->sub_limit = o->sub_lim = val; return 1; }
@@ -1294,7 +1360,8 @@ void cp3o_free(cp3o* o)
 {
     if (!o) { return; }
     if (o->occ) { for (int x = 0; x < 2 * o->nvars; ++x) { free(o->occ[x].v); } free(o->occ); }
-    if (o->ing_occ) { for (int x = 0; x < 2 * o->nvars; ++x) { free(o->ing_occ[x].v); } free(o->ing_occ); }
+    if (o->watches) { for (int x = 0; x < 2 * o->nvars; ++x) { free(o->watches[x].v); } free(o->watches); }
+    free(o->permuted.v);
     free(o->cnt); free(o->modTimer); free(o->ma); free(o->assigns); free(o->frozen);
     free(o->pool); free(o->cstart); free(o->csize); free(o->cflag);
     free(o->trail.v); free(o->clauses.v); free(o->cur.v); free(o->subq.v); free(o->strq.v); free(o->undo.v);

@@ -18,10 +18,14 @@ SUBSUME, STRENGTHEN = 0, 1
 
 class Coprocessor:
     def __init__(self, options=(), preset: str | None = None, lib_path: str | None = None):
+        """`options` and `preset` both go to CPinit: like the reference's command line they are parsed BEFORE the
+        preprocessor is constructed.  That matters: cp3_limited and the step limits (cp3_sub_limit, cp3_str_limit,
+        cp3_call_inc, cp3_bve_limit) are read by the constructors only (libcoprocessorc.cc:35-46); given to
+        parse_options() afterwards they are accepted and have no effect - in the reference and here alike."""
         self.L = _lib.load(lib_path)
-        self.h = C.c_void_p(self.L.CPinit(preset.encode() if preset else None))
-        if options:
-            self.parse_options(options)
+        opts = options.split() if isinstance(options, str) else list(options)
+        init = ":".join(x for x in ([preset] if preset else []) + ([" ".join(opts)] if opts else []))
+        self.h = C.c_void_p(self.L.CPinit(init.encode() if init else None))
 
     # --- libcoprocessorc.h calls
     def parse_options(self, options):

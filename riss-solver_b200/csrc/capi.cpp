@@ -19,6 +19,14 @@ struct Handle {                         // struct libcp3, libcoprocessorc.cc:12-
     std::vector<int32_t> pend; bool buffering = true;
     std::vector<int32_t> out; size_t outPos = 0; bool outReady = false;
     std::vector<uint8_t> model; size_t modelLit = 0;
+    // The reference builds Solver + Preprocessor inside CPinit (libcoprocessorc.cc:35-46); a few options are read by those
+    // constructors only: cp3_limited (CoprocessorData::hasLimit, Coprocessor.cc:29 / CoprocessorTypes.h:614), the Stepper
+    // limits cp3_sub_limit / cp3_str_limit / cp3_call_inc (Subsumption.cc:22-24) and cp3_bve_limit (BVE.cc:23).  Given to
+    // CPinit (preset name or option string) they count, given to CPparseOption* / CPsetPresetConfig afterwards they are
+    // accepted and have no effect.  Same here: the values of CPinit time are put back after every later parse.
+    struct Ctor { bool limited; int64_t sub_limit, str_limit, bve_limit; int call_inc; } ctor;
+    void capture() { const cp3::Options& o = eng.opt; ctor = {o.limited, o.sub_limit, o.str_limit, o.bve_limit, o.call_inc}; }
+    void restore() { cp3::Options& o = eng.opt; o.limited = ctor.limited; o.sub_limit = ctor.sub_limit; o.str_limit = ctor.str_limit; o.bve_limit = ctor.bve_limit; o.call_inc = ctor.call_inc; }
 };
 inline Handle* H(void* p) { return (Handle*)p; }
 inline void sync(Handle* h)
@@ -32,6 +40,7 @@ inline Handle* HS(void* p) { Handle* h = (Handle*)p; sync(h); return h; }      /
 void applyOption(Handle* h, const char* o, bool strict)
 {
     int r = h->eng.opt.parse(o);
+    h->restore();
     if (r < 0) {
         fprintf(stderr, "cp3b200: option %s selects a reference code path the GPU drop-in does not provide\n", o);
         if (strict) { exit(1); }
@@ -52,17 +61,17 @@ void ensureOutput(Handle* h)
 
 extern "C" {
 
-// The engine's work arrays are hundreds of MB that live for one CPpreprocess.  With glibc's defaults every one of
-// them is mmap()ed, page-faulted in and unmapped again - 90 ms of a 0.6 s run at 4.6 M clauses.  Like the device pool
-// (cp3g_create lifts its release threshold) the host heap keeps its working set: large blocks come from the heap
-// instead of mmap and the heap is not trimmed.  CP3_KEEP_HEAP=0 leaves the process' allocator policy alone.
+// The engine's work arrays are hundreds of MB that live for one CPpreprocess.  With glibc's defaults every one of them is
+// mmap()ed, page-faulted in and unmapped again - 90 ms of a 0.6 s run at 4.6 M clauses.  A host that calls CPpreprocess
+// repeatedly can opt in to keeping that working set in the heap (large blocks from the heap instead of mmap, no trimming)
+// with CP3_KEEP_HEAP=1.  It is NOT the default: a drop-in library must not change its host's allocator policy.
 static void keepHostHeapOnce()
 {
     static bool done = false;
     if (done) { return; }
     done = true;
     const char* e = getenv("CP3_KEEP_HEAP");
-    if (e && atoi(e) == 0) { return; }
+    if (!e || atoi(e) == 0) { return; }
     mallopt(M_MMAP_MAX, 0);
     mallopt(M_TRIM_THRESHOLD, INT_MAX);
 }
@@ -72,6 +81,7 @@ void* CPinit(const char* presetConfig)
     keepHostHeapOnce();
     Handle* h = new Handle();
     if (presetConfig) { h->eng.opt.preset(presetConfig); }
+    h->capture();
     return h;
 }
 void CPdestroy(void** p) { if (p && *p) { delete H(*p); *p = nullptr; } }
@@ -84,6 +94,7 @@ void CPparseOptions(void* p, int* argc, char** argv, int strict)
     int j = 1;
     for (int i = 1; i < *argc; ++i) {
         int r = H(p)->eng.opt.parse(argv[i]);
+        H(p)->restore();
         if (r == 0) { if (strict && argv[i][0] == '-') { fprintf(stderr, "ERROR! Unknown flag \"%s\"\n", argv[i]); exit(1); } argv[j++] = argv[i]; }
         else if (r < 0) { applyOption(H(p), argv[i], strict != 0); }
     }
@@ -95,7 +106,7 @@ void CPparseOptionString(void* p, char* s)
     std::string tok;
     while (is >> tok) { applyOption(H(p), tok.c_str(), false); }
 }
-void CPsetPresetConfig(void* p, const char* preset) { H(p)->eng.opt.preset(preset); }
+void CPsetPresetConfig(void* p, const char* preset) { H(p)->eng.opt.preset(preset); H(p)->restore(); }
 void CPaddLit(void* p, int lit)
 {
     Handle* h = H(p); h->outReady = false;
@@ -123,9 +134,13 @@ int CPgetReplaceLiteral(void* p, int oldLit) { const int r = HS(p)->eng.importLi
 
 void CPresetModel(void* p) { H(p)->model.clear(); H(p)->modelLit = 0; }
 void CPpushModelBool(void* p, int pol) { H(p)->model.push_back(pol == 0 ? cp3::L_FALSE : cp3::L_TRUE); }
+// libcoprocessorc.cc:139-147.  DELIBERATE FIX: the reference maps a negative literal -k to variable index k+1 (mkLit(-literal + 1),
+// a sign slip - model round trips through negative literals hit the wrong variable); here -k means "variable k is false", which is
+// what the header documents.  Positive literals behave identically.  0 is ignored (the reference writes model[-1]).
 void CPgiveModelLit(void* p, int literal)
 {
     Handle* h = H(p);
+    if (literal == 0) { return; }
     size_t v = (size_t)(literal < 0 ? -literal : literal) - 1;
     while (h->model.size() <= v) { h->model.push_back(cp3::L_UNDEF); }
     h->model[v] = literal > 0 ? cp3::L_TRUE : cp3::L_FALSE;

@@ -62,18 +62,47 @@ int Options::parse(const char* o)
     return 0;
 }
 
-// the presets of riss/utils/Config.h that only touch this path (plain_SUSI :377, plain_BVE :381)
+// Presets (Config::setPreset, riss/utils/Config.h:97-560) that reach this path.  A preset is an option string; the options
+// of the path are applied, the techniques the GPU drop-in does not provide are named on stderr (once per preset), so that
+// nobody mistakes the result for the reference's full pipeline.  plain_SUSI :377, plain_BVE :381, BVEEARLY :383,
+// Riss427 :317, Riss427nd :315, Riss427-NoCLE :319, 505 / 505-M :542.
 void Options::preset(const char* name)
 {
     if (!name) { return; }
+    struct P { const char* name; const char* path; const char* rest; };
+    static const P table[] = {
+        {"plain_SUSI", "-enabled_cp3 -cp3_stats -subsimp", ""},
+        {"plain_BVE", "-enabled_cp3 -cp3_stats -bve", ""},
+        {"plain_UP", "-enabled_cp3 -cp3_stats -up", ""},
+        {"BVEEARLY", "-bve_early", ""},
+        {"Riss427", "-enabled_cp3 -cp3_stats -bve -dense", "-fm -unhide -bce (-bce-cle)"},
+        {"Riss427nd", "-enabled_cp3 -cp3_stats -bve", "-fm -unhide -bce (-bce-cle)"},
+        {"RissND427", "-enabled_cp3 -cp3_stats -bve", "-fm -unhide -bce (-bce-cle)"},
+        {"Riss427-NoCLE", "-enabled_cp3 -cp3_stats -bve -dense", "-fm -unhide"},
+        {"505", "-enabled_cp3 -cp3_stats -bve -dense -cp3_iters=2 -bve_early", "-fm -unhide -bce (-bce-cle) -xor -ee and the search options"},
+        {"505-M", "-enabled_cp3 -cp3_stats -bve -dense -cp3_iters=2 -bve_early", "-fm -unhide -bce (-bce-cle) -xor -ee and the search options"},
+    };
+    auto parseString = [&](const std::string& opts) {
+        size_t q = 0;
+        while (q < opts.size()) { size_t e = opts.find(' ', q); if (e == std::string::npos) { e = opts.size(); } if (e > q) { parse(opts.substr(q, e - q).c_str()); } q = e + 1; }
+    };
     std::string n(name);
     size_t pos = 0;
-    while (pos <= n.size()) {
+    while (pos <= n.size()) {                              // Config::setPreset: tokens separated by ':'
         size_t c = n.find(':', pos);
         std::string one = n.substr(pos, c == std::string::npos ? std::string::npos : c - pos);
-        if (one == "plain_SUSI") { enabled = true; subsimp = true; }
-        else if (one == "plain_BVE") { enabled = true; bve = true; }
-        else if (one == "plain_UP") { enabled = true; up = true; }
+        bool known = false;
+        for (const P& p : table) {
+            if (one != p.name) { continue; }
+            known = true;
+            parseString(p.path);
+            if (p.rest[0]) { fprintf(stderr, "cp3b200: preset %s: applied \"%s\"; techniques of this preset outside the GPU path are NOT run: %s\n", p.name, p.path, p.rest); }
+        }
+        // Config::addPreset, riss/utils/Config.h:736-739: a token that names no preset is parsed as an option string
+        if (!known && !one.empty()) {
+            if (one.find('-') != std::string::npos) { parseString(one); }
+            else { fprintf(stderr, "cp3b200: preset %s is not known to the GPU path and has no effect\n", one.c_str()); }
+        }
         if (c == std::string::npos) { break; }
         pos = c + 1;
     }
@@ -152,7 +181,7 @@ template <class P> void Engine::parallelFilter(const std::vector<uint32_t>& src,
 void Engine::newVar()
 {
     assigns.push_back(L_UNDEF); frozen.push_back(0);
-    if (ing_built) { ing_occ.emplace_back(); ing_occ.emplace_back(); }
+    if (ing_built) { watches.emplace_back(); watches.emplace_back(); }
     ++nvars;
 }
 
@@ -181,32 +210,79 @@ int Engine::dataEnqueue(int x)
     return L_UNDEF;
 }
 
-// level-0 propagation while clauses are added (stand-in for Solver::propagate over watches; the implied
-// literal set is the same, the trail order of implied literals may differ - DESIGN.md "input units")
+// Solver::attachClause, riss/core/Solver.cc:692-708
+void Engine::attachClause(uint32_t c)
+{
+    const int32_t* l = CL(c); const uint32_t bin = C[c].size == 2 ? 0x80000000u : 0u;
+    watches[lneg(l[0])].push_back({c | bin, l[1]});
+    watches[lneg(l[1])].push_back({c | bin, l[0]});
+}
+// Preprocessor::sortClauses (Coprocessor.cc:118,1447-1463): addClause_ sorts every clause, only those propagate() permuted need it
+void Engine::sortPermuted()
+{
+    for (uint32_t c : permuted) { std::sort(CL(c), CL(c) + C[c].size); perm_mark[c] = 0; }
+    permuted.clear();
+}
+
+// Solver::propagate(true) at level 0 while clauses are added, riss/core/Solver.cc:1809-1937.  The trail order of implied
+// literals is a function of the watch-list order, the blocker literals and the way propagate() permutes the clauses it
+// visits (c[0]/c[1] swap, new watch moved to c[1]); all of it is restated here, so inputs with unit clauses give the
+// reference's trail (and with it the reference's strengthening / BVE order).
 bool Engine::ingestPropagate()
 {
     if (!ing_built) {
-        ing_occ.assign(2 * (size_t)nvars, {});
+        watches.assign(2 * (size_t)nvars, {});
         ing_built = true;
-        for (uint32_t c : clauses) { for (uint32_t k = 0; k < C[c].size; ++k) { ing_occ[CL(c)[k]].push_back(c); } }
+        for (uint32_t c : clauses) { attachClause(c); }
     }
+    auto notePermuted = [&](uint32_t c) {
+        if (perm_mark.size() <= c) { perm_mark.resize(C.size() + 1024, 0); }
+        if (!perm_mark[c]) { perm_mark[c] = 1; permuted.push_back(c); }
+    };
+    bool confl = false;
     while (qhead < (int)trail.size()) {
-        int p = trail[qhead++];
-        const std::vector<uint32_t>& ws = ing_occ[lneg(p)];
-        for (size_t i = 0; i < ws.size(); ++i) {
-            uint32_t c = ws[i]; const int32_t* l = CL(c);
-            int un = -1, nun = 0; bool sat = false;
-            for (uint32_t k = 0; k < C[c].size; ++k) {
-                int v = value(l[k]);
-                if (v == L_TRUE) { sat = true; break; }
-                if (v == L_UNDEF) { un = l[k]; ++nun; }
+        const int p = trail[qhead++];
+        size_t i = 0, j = 0; const size_t end = watches[p].size();
+        while (i != end) {
+            std::vector<Watcher>& ws = watches[p];             // (pushes below go to other lists; the outer vector does not grow here)
+            const Watcher wi = ws[i];
+            if (wi.cref & 0x80000000u) {
+                const int vi = value(wi.blocker);
+                if (vi == L_FALSE) {                            // opt_long_conflict is off: stop at the first conflict
+                    while (i < end) { ws[j++] = ws[i++]; }
+                    ws.resize(j);
+                    return false;
+                } else if (vi == L_UNDEF) { uncheckedEnqueue(wi.blocker); }
+                ws[j++] = ws[i++];
+                continue;
             }
-            if (sat) { continue; }
-            if (nun == 0) { return false; }
-            if (nun == 1) { uncheckedEnqueue(un); }
+            if (value(wi.blocker) == L_TRUE) { ws[j++] = ws[i++]; continue; }
+            const uint32_t c = wi.cref; int32_t* l = CL(c); const uint32_t n = C[c].size;
+            const int false_lit = lneg(p);
+            if (l[0] == false_lit) { l[0] = l[1]; l[1] = false_lit; notePermuted(c); }
+            i++;
+            const int first = l[0];
+            const Watcher w{c, first};
+            if (first != wi.blocker && value(first) == L_TRUE) { ws[j++] = w; continue; }
+            bool moved = false;
+            for (uint32_t k = 2; k < n; ++k) {
+                if (value(l[k]) != L_FALSE) {
+                    l[1] = l[k]; l[k] = false_lit; notePermuted(c);
+                    watches[lneg(l[1])].push_back(w);          // never watches[p]: l[1] != ~p
+                    moved = true; break;
+                }
+            }
+            if (moved) { continue; }
+            ws[j++] = w;
+            if (value(first) == L_FALSE) {
+                confl = true;
+                qhead = (int)trail.size();
+                while (i < end) { ws[j++] = ws[i++]; }
+            } else { uncheckedEnqueue(first); }
         }
+        watches[p].resize(j);
     }
-    return true;
+    return !confl;
 }
 
 // Solver::addClause_, riss/core/Solver.cc:409-499
@@ -224,7 +300,7 @@ void Engine::addClauseIngest(std::vector<int>& ps)
     if (j == 1) { uncheckedEnqueue(ps[0]); ok = ingestPropagate(); return; }
     uint32_t c = allocClause(ps.data(), j);
     clauses.push_back(c);
-    if (ing_built) { for (int i = 0; i < j; ++i) { ing_occ[ps[i]].push_back(c); } }
+    if (ing_built) { attachClause(c); }
 }
 
 void Engine::addLit(int x)
@@ -265,7 +341,7 @@ void Engine::addStream(const int32_t* s, size_t n)
     }
     for (size_t i = 0; i < n; ++i) { addLit(s[i]); }
 }
-void Engine::freeze(int dv) { while (nvars < dv) { newVar(); } frozen[dv - 1] = 1; }
+void Engine::freeze(int dv) { if (dv <= 0) { return; } while (nvars < dv) { newVar(); } frozen[dv - 1] = 1; }   // freezeExtern(0) is a no-op
 int Engine::litValue(int d) const
 {
     int v = d < 0 ? -d : d;
@@ -1616,6 +1692,9 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
         clearQueue(subq, F_SUB); clearQueue(strq, F_STR);
         return false;
     }
+    // (the technique-level size gates - Subsumption.cc:102, BVE.cc:180-184: cp3_susi_* / cp3_bve_* - can never fire: they need
+    //  nTotLits() > limit, and cleanSolver() (Coprocessor.cc:1395-1406) zeroes clauses_literals before any technique runs;
+    //  verified against the compiled reference with all limits set to 10.  The options are accepted and have no effect.)
     if (!(sub_steps + opt.call_inc < sub_lim)) { sub_lim += opt.call_inc; limitIncreases++; }
     if (!(str_steps + opt.call_inc < str_lim)) { str_lim += opt.call_inc; limitIncreases++; }
     while (ok && (!subq.empty() || !strq.empty())) {
@@ -2164,7 +2243,7 @@ void Engine::initData()
         }
     }
     lap("initClause loop");
-    data_ready = true;
+    data_ready = true; data_nvars = nvars;
 }
 
 // Dense::compress, coprocessor/techniques/Dense.cc:26-238.  The data-parallel part - which variables still occur,
@@ -2202,7 +2281,7 @@ void Engine::denseCompress()
         const int to = comp_map[v];
         if (to >= 0 && to != v) { assigns[to] = assigns[v]; assigns[v] = L_UNDEF; frozen[to] = frozen[v]; frozen[v] = 0; }
     }
-    nvars = (int)nv_new;
+    nvars = (int)nv_new; data_nvars = nvars;                                         // CoprocessorTypes.h:725
     assigns.resize((size_t)nvars); frozen.resize((size_t)nvars);
     data_ready = false;                                                              // occurrence data is void (data.destroy follows)
 }
@@ -2217,18 +2296,26 @@ int Engine::importLit(int d) const
 
 void Engine::preprocess()
 {
-    // Coprocessor.cc:1002-1006: data.nVars() is still 0 before data.init() and nTotLits() only counts learnt
-    // literals, so only the clause-count gate can fire here
-    if (opt.limited && (int64_t)clauses.size() > opt.cp3_cls) { return; }
+    // Coprocessor.cc:1002-1006, the size gates.  data.nVars() is CoprocessorData::numberOfVars (0 before the first
+    // data.init()); nTotLits() = clauses_literals + learnts_literals (riss/core/Solver.h:1867): the literals of all attached
+    // clauses (Solver.cc:706-707), i.e. of every stored clause - there are no learnt clauses on this path
+    if (opt.limited) {
+        std::vector<uint64_t> part((size_t)nthreads + 1, 0);
+        parallelFor(clauses.size(), [&](size_t b, size_t e, int t) { uint64_t a = 0; for (size_t i = b; i < e; ++i) { a += C[clauses[i]].size; } part[(size_t)t] = a; });
+        uint64_t totlits = 0; for (uint64_t a : part) { totlits += a; }
+        if ((uint32_t)data_nvars > (uint32_t)opt.cp3_vars || (int64_t)clauses.size() > (int64_t)opt.cp3_cls || (uint32_t)totlits > (uint32_t)opt.cp3_lits) { return; }
+    }
     if (!opt.enabled) { return; }
     PhaseTimer ptot(ph_total);
     ensureGpu();                                  // fail before touching anything when there is no device
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
     { PhaseTimer ps(ph_simplify); if (!solverSimplify()) { return; } }
+    sortPermuted();
     initData();
     int status = L_UNDEF;
     for (int it = 0; it < opt.iters; ++it) {
         if (opt.up) { if (status == L_UNDEF) { status = propagationProcess(true, false, VAR_UNDEF); } }
+        checkGarbage();                               // unconditional checkpoints behind the UP / XOR / ENT blocks, Coprocessor.cc:156,171
         if (!ok) { break; }
         if (opt.subsimp) {
             if (status == L_UNDEF) { subsumptionProcess(true, false, VAR_UNDEF); }

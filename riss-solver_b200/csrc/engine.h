@@ -116,10 +116,17 @@ private:
     double ca_size = 0, ca_wasted = 0;
     int simpDB_assigns = -1; int64_t simpDB_props = 0;
     std::vector<int> cur;
-    std::vector<std::vector<uint32_t>> ing_occ; bool ing_built = false;
+    // two-watched-literal lists while clauses are added (Solver::attachClause / propagate, riss/core/Solver.cc:692-708,1809-1937):
+    // watches[p] = clauses that watch ~p; built at the first unit.  propagate() permutes the literals of the clauses it
+    // visits; those are re-sorted where the reference does it (Preprocessor::sortClauses, Coprocessor.cc:118)
+    struct Watcher { uint32_t cref; int32_t blocker; };          // top bit of cref: binary clause
+    std::vector<std::vector<Watcher>> watches; bool ing_built = false;
+    std::vector<uint32_t> permuted; std::vector<uint8_t> perm_mark;
+    void attachClause(uint32_t c);
+    void sortPermuted();
 
     // ---------------- CoprocessorData mirror
-    bool data_ready = false;
+    bool data_ready = false; int data_nvars = 0;      // CoprocessorData::numberOfVars: 0 until the first data.init()
     RawVec<OccList> occ; RawVec<LitHot> hot; RawVec<uint32_t> occ_pool;
     std::vector<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
     inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
