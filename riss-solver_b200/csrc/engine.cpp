@@ -320,6 +320,18 @@ void Engine::addStream(const int32_t* s, size_t n)
     if (n >= bulk_min && C.empty() && cur.empty() && trail.empty() && ok && !ing_built && clauses.empty() && cp3g_device_count() > 0) {
         size_t m = n;
         while (m > 0 && s[m - 1] != 0) { --m; }                    // complete clauses only
+        {   // ... and only up to the first clause with fewer than two literals: a unit starts unit propagation, whose effect on
+            // the clauses behind it is order dependent (two-watched-literal lists) - that part goes literal by literal
+            std::vector<size_t> first((size_t)nthreads + 1, m);
+            parallelFor(m, [&](size_t b, size_t e, int t) {
+                for (size_t i = b; i < e; ++i) {
+                    if (s[i] != 0) { continue; }
+                    if (i == 0 || s[i - 1] == 0 || i == 1 || s[i - 2] == 0) { first[(size_t)t] = (i == 0 || s[i - 1] == 0) ? i : i - 1; break; }
+                }
+            }, 1u << 20);
+            for (size_t f : first) { m = std::min(m, f); }
+            if (m < bulk_min) { m = 0; }
+        }
         if (m) {
             ensureGpu();
             uint32_t nv = 0, nc = 0; size_t nl = 0; int st = 1;

@@ -1577,10 +1577,12 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
     uint64_t chk, ab; memcpy(&chk, &cnt[4], 8); memcpy(&ab, &cnt[6], 8);
     g->scan_requests += (re - rb); g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
     if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }   // count only
-    if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
+    // sharded: the overflow decision is taken on the GATHERED counts, identically on every rank (a rank that returned early on
+    // its local count would leave the others alone in the collective); `cap` is the same everywhere - replicated host state
+    if (g->world == 1 && n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
     if (g->world > 1) {
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
-        if (rr != CP3G_OK) { return rr; }
+        if (rr != CP3G_OK) { if (nout) { *nout = n; } return rr; }
     } else if (n >= SORT_ON_DEVICE_MIN) {
         int rr = sort_hits(g, n);
         if (rr != CP3G_OK) { return rr; }
@@ -1647,10 +1649,12 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     g->scan_requests += g->ncl; g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
     dlap("kernel+sync");
     if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }
-    if (n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
+    // sharded: the overflow decision is taken on the GATHERED counts, identically on every rank (a rank that returned early on
+    // its local count would leave the others alone in the collective); `cap` is the same everywhere - replicated host state
+    if (g->world == 1 && n > cap) { if (nout) { *nout = n; } return CP3G_ERR_OVERFLOW; }
     if (g->world > 1) {
         int rr = cp3g_nccl_gather_hits(g->nccl, g->stream, g->hits.p, n, cap, out, &n, &chk);
-        if (rr != CP3G_OK) { return rr; }
+        if (rr != CP3G_OK) { if (nout) { *nout = n; } return rr; }
     } else if (n) {
         if (n >= SORT_ON_DEVICE_MIN) { int rr = sort_hits(g, n); if (rr != CP3G_OK) { return rr; } }
         if (dbg) { cudaStreamSynchronize(g->stream); } dlap("sort");

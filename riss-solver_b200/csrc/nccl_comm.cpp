@@ -6,6 +6,7 @@
 #include <dlfcn.h>
 #include <stdio.h>
 #include <string.h>
+#include <algorithm>
 #include <vector>
 #include "gpu_db.h"
 
@@ -96,7 +97,9 @@ int cp3g_nccl_gather_hits(void* comm, cudaStream_t st, const cp3g_hit* dhits, ui
     for (int r = 0; r < W; ++r) { offs[r] = total; total += all[4 * r]; chk += (uint64_t)all[4 * r + 1] | ((uint64_t)all[4 * r + 2] << 32); }
     offs[W] = total;
     *checks = chk;
-    if (total > cap) { *nout = (uint32_t)total; return CP3G_ERR_OVERFLOW; }
+    // every rank sees the same counts and the same cap, so every rank takes the same branch here (a local count above
+    // cap is included: total >= it).  The caller retries with a cap derived from `total` alone.
+    if (total > cap) { *nout = (uint32_t)std::min<uint64_t>(total, 0xffffffffull); return CP3G_ERR_OVERFLOW; }
     if (total > c->gather_cap) {
         if (c->dgather) { cudaFree(c->dgather); }
         c->gather_cap = total + total / 2 + 1024;
