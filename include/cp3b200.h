@@ -122,6 +122,20 @@ int cp3g_scan(cp3g* g, int kind, uint32_t nreq, const uint32_t* self, const uint
  * of its subsumers.  Rebuilds signatures + CSR first when clauses were edited since the last cp3g_build. */
 int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout, uint64_t* checks);
 
+/* The first subsumption pass COMMITTED on the device (commit.cu): Subsumption::subsumption_worker, Subsumption.cc:244-313, for the
+ * state right after Preprocessor::initializePreprocessor - every live clause in the queue in clause order, occurrence lists
+ * pristine (cp3g_build, nothing edited since).  Runs K3 over the full queue and then, on the device, the death time of every
+ * subsumed clause, the list choice of every queue entry with lit_occurrence_count as of its own turn, and the replay of the
+ * lazily cleaned lists (swap-with-last, size filter, step counter) - the result of the reference's ordered walk.
+ * *status 0: committed - *ndead clauses subsumed (*nlits literals), *steps subsumption steps, *checks K3 checks; the device
+ * marked them deleted.  *status 1: not applicable (a list holding a subsumed clause is longer than max_list, sharded mode,
+ * clauses appended since the build): nothing was changed, use cp3g_scan_all and commit on the host. */
+int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead, uint64_t* nlits, uint64_t* steps, uint64_t* checks);
+/* results of the committed pass: dead[ndead] clause ids (any order), list_n[2*nvars] / list_stale[2*nvars] = length of every
+ * list and number of deleted clauses still listed in it, refs = the lists at the offsets of cp3g_download_occ in their
+ * post-pass order (first list_n[x] entries of list x).  NULL skips an output. */
+int cp3g_sub_pass_fetch(cp3g* g, uint32_t* dead, uint32_t* list_n, uint32_t* list_stale, uint32_t* refs);
+
 /* K5: resolvent anticipation for candidate variables.  Variable i owns pos refs p_off[i]..p_off[i+1] and
  * neg refs n_off[i]..n_off[i+1] (host list order).  sizes[pair_off[i] + a*nneg + b] = number of literals
  * of the resolvent of pos a and neg b on vars[i], -1 for a tautology (BVE.h:248-299), -2 when a parent is
@@ -164,7 +178,7 @@ int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_ca
 int cp3g_nccl_unique_id(void* out128);
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);
 
-/* counters: "launches", "kernel_ns" (all kernels, CUDA events), "scan_ns" (K3/K4 only), "h2d_bytes", "d2h_bytes",
+/* counters: "launches", "kernel_ns" (all kernels, CUDA events), "scan_ns" (K3/K4 only), "commit_ns" (device pass commit), "h2d_bytes", "d2h_bytes",
  * "scan_requests", "scan_checks", "scan_alg_bytes" (sum over checks of 4 + 8 + 4*#D) */
 int64_t cp3g_counter(const cp3g* g, const char* name);
 

@@ -191,6 +191,21 @@ class ScanService:
             a = np.frombuffer(out, dtype=np.dtype([("req", "<u4"), ("clause", "<u4"), ("lit", "<i4")]), count=n.value).copy()
             return a, int(chk.value)
 
+    def sub_pass(self, max_list=4096):
+        """first subsumption pass committed on the device (cp3g_sub_pass): returns None when not applicable, else a dict with
+        the subsumed clause ids (sorted), literal total, step count and the post-pass lists (off, n, stale, refs)"""
+        st = C.c_int(1); nd = C.c_uint32(0); nl = C.c_uint64(0); steps = C.c_uint64(0); chk = C.c_uint64(0)
+        self._ck(self.L.cp3g_sub_pass(self.g, int(max_list), C.byref(st), C.byref(nd), C.byref(nl), C.byref(steps), C.byref(chk)), "sub_pass")
+        if st.value != 0:
+            return None
+        off = np.zeros(2 * self.nvars + 1, dtype=np.uint32)
+        self._ck(self.L.cp3g_download_occ(self.g, off.ctypes.data, None), "download_occ")
+        dead = np.zeros(max(nd.value, 1), dtype=np.uint32); n = np.zeros(2 * self.nvars, dtype=np.uint32); stale = np.zeros(2 * self.nvars, dtype=np.uint32)
+        refs = np.zeros(max(int(off[-1]), 1), dtype=np.uint32)
+        self._ck(self.L.cp3g_sub_pass_fetch(self.g, dead.ctypes.data, n.ctypes.data, stale.ctypes.data, refs.ctypes.data), "sub_pass_fetch")
+        return {"dead": np.sort(dead[:nd.value]), "lits": int(nl.value), "steps": int(steps.value), "checks": int(chk.value),
+                "off": off, "n": n, "stale": stale, "refs": refs[:int(off[-1])]}
+
     def bve_pairs(self, vars_, pos_lists, neg_lists):
         vars_ = np.ascontiguousarray(vars_, dtype=np.uint32)
         p_off = np.zeros(vars_.size + 1, dtype=np.uint32); n_off = np.zeros(vars_.size + 1, dtype=np.uint32)

@@ -898,6 +898,7 @@ void Engine::filterDeleted(std::vector<uint32_t>& a)
 void Engine::checkGarbage()
 {
     if (!(ca_wasted > ca_size * opt.gc_frac)) { return; }
+    ensureHostLists();
     filterDeleted(subq); filterDeleted(strq);
     for (int x = 0; x < 2 * nvars; ++x) {
         ListRef l = L(x); uint32_t* p = LP(l); uint32_t j = 0;
@@ -934,6 +935,7 @@ int Engine::propagationProcess(bool sort, bool useHeap, int ignore)
 {
     t_up.modified = false;
     if (!ok) { return L_FALSE; }
+    if (up_last < (int)trail.size()) { ensureHostLists(); }
     for (; up_last < (int)trail.size(); up_last++) {
         const int l = trail[up_last];
         {
@@ -1193,6 +1195,77 @@ bool Engine::subsumptionCommitParallel()
     return true;
 }
 
+// The lists K2 built (clause order, CoprocessorTypes.h:812-833) come to the host when somebody first needs them.
+void Engine::ensureHostLists()
+{
+    if (!lists_on_device) { return; }
+    lists_on_device = false;
+    const int n2 = 2 * nvars;
+    int64_t t0 = now_ns();
+    std::vector<uint32_t> off((size_t)n2 + 1, 0);
+    if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
+    ph_download += now_ns() - t0; host_ns_gpuwait += now_ns() - t0;
+}
+
+// First subsumption pass, committed by the device (cp3g_sub_pass, commit.cu): the queue holds every live clause in clause
+// order and the lists are pristine.  The host receives the subsumed set, the step counter and the lists in their post-pass
+// order and does the O(#subsumed) bookkeeping of subsumptionCommitParallel's last step.
+bool Engine::subsumptionCommitDevice()
+{
+    static const bool off_env = getenv("CP3_NO_DEVCOMMIT") != nullptr;
+    static const uint32_t max_list = getenv("CP3_DEVCOMMIT_MAXLIST") ? (uint32_t)atoi(getenv("CP3_DEVCOMMIT_MAXLIST")) : 4096u;
+    if (off_env || !lists_on_device || !dev_uploaded || !pend_del.empty() || !pend_shrunk.empty() || dev_ncl != C.size()) { return false; }
+    const size_t nq = subq.size();
+    if (nq != n_live || nq == 0) { return false; }
+    bool ok_q = true;                                    // every entry live and flagged, strictly increasing clause index
+    parallelFor(nq, [&](size_t b, size_t e, int) {
+        bool good = true;
+        for (size_t p = b; p < e && good; ++p) { const ClauseInfo& ci = C[subq[p]]; good = !(ci.flag & F_DEL) && (ci.flag & F_SUB) && (p == 0 || subq[p - 1] < subq[p]); }
+        if (!good) { ok_q = false; }
+    });
+    if (!ok_q) { return false; }
+    DbgLap lap("devsub");
+    int status = 1; uint32_t ndead = 0; uint64_t nlits = 0, steps = 0, checks = 0;
+    int64_t t0 = now_ns();
+    if (cp3g_sub_pass(gpu, max_list, &status, &ndead, &nlits, &steps, &checks) != CP3G_OK) { die("device subsumption pass failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    lap("cp3g_sub_pass");
+    if (status != 0) { return false; }
+    ++scan_id; ++n_scan_batches; ++n_devsub;
+    const size_t nlit = (size_t)2 * nvars;
+    std::vector<uint32_t> dead(ndead); RawVec<uint32_t> ln, ls; ln.resize(nlit); ls.resize(nlit);
+    t0 = now_ns();
+    if (cp3g_sub_pass_fetch(gpu, dead.data(), ln.data(), ls.data(), occ_pool.data()) != CP3G_OK) { die("device subsumption pass: fetch failed"); }
+    host_ns_gpuwait += now_ns() - t0; ph_download += now_ns() - t0;
+    lists_on_device = false;
+    lap("fetch");
+    parallelForG((nlit + 63) / 64, 512, [&](size_t wb, size_t we, int) {      // 64-literal granules: stalebits words are not shared
+        for (size_t x = wb * 64; x < std::min(nlit, we * 64); ++x) {
+            hot[x].n = ln[x]; stale[x] = ls[x];
+            if (ls[x]) { stalebits[x >> 6] |= 1ull << (x & 63); }
+        }
+    });
+    parallelFor(dead.size(), [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            const uint32_t d = dead[i];
+            C[d].flag |= F_DEL;
+            __atomic_fetch_or(&delbits[d >> 6], 1ull << (d & 63), __ATOMIC_RELAXED);
+            const int32_t* l = CL(d);
+            // removedClause twice per subsumed clause (Subsumption.cc:284,305)
+            for (uint32_t k = 0; k < C[d].size; ++k) { deletedVar(l[k] >> 1); __atomic_fetch_sub(&hot[l[k]].cnt, 2, __ATOMIC_RELAXED); }
+        }
+    }, 8192);
+    subsumedClauses += (int)ndead; subsumedLiterals += (int)nlits;
+    n_live -= ndead;
+    numberOfCls -= 2 * (int)ndead; ca_wasted += 2 * (2.0 * (double)ndead + (double)nlits);
+    if (opt.bve) { for (uint32_t d : dead) { touchClauseVars(d); } }
+    if (ndead) { successful(t_sub); }
+    sub_steps += (int64_t)steps;
+    parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { C[subq[p]].flag &= ~F_SUB; } });
+    lap("bookkeeping");
+    return true;
+}
+
 // subsumption_worker, Subsumption.cc:220-314.  One bulk K3 scan answers every ordered_subsumes() of the
 // queue; the loop below replays the queue back to front.
 void Engine::subsumptionWorker(bool useHeap, int ignore)
@@ -1202,6 +1275,25 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     DbgLap lap0("sub"); 
     c_sub.clear(); logClear();
     lap0("clear");
+    if (lists_on_device) {
+        static const size_t parsub_min0 = getenv("CP3_PARSUB_MIN") ? (size_t)atoi(getenv("CP3_PARSUB_MIN")) : 65536;
+        bool far = unlimited;
+        if (!far && !useHeap && subq.size() >= parsub_min0) {      // the device commit cannot stop in the middle of the queue: only far from the step limit
+            std::vector<int64_t> part((size_t)nthreads + 1, 0);
+            parallelFor(subq.size(), [&](size_t b, size_t e, int t) {
+                int64_t a = 0;
+                for (size_t p = b; p < e; ++p) { const ClauseInfo& ci = C[subq[p]]; if (ci.flag & F_DEL) { continue; } uint32_t mx = 0; const int32_t* l = pool.data() + ci.start; for (uint32_t k = 0; k < ci.size; ++k) { mx = std::max(mx, hot[l[k]].n); } a += mx; }
+                part[(size_t)t] = a;
+            });
+            int64_t bound = 0; for (int64_t a : part) { bound += a; }
+            far = sub_steps + bound < sub_lim;
+        }
+        if (!useHeap && subq.size() >= parsub_min0 && far) {
+            const int64_t t00 = now_ns();
+            if (subsumptionCommitDevice()) { host_ns_commit += now_ns() - t00; lap0("device commit"); return; }
+        }
+        ensureHostLists();
+    }
     {
         std::vector<uint32_t> ids;
         parallelFilter(subq, ids, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
@@ -1395,6 +1487,7 @@ void Engine::unpredictedEdit(uint32_t c)
     if (!static_pass || c >= qtime.size() || qtime[c] < 0) { return; }
     const size_t pos = static_nq - 1 - (size_t)qtime[c];
     if (pos >= walk_min.size()) { return; }
+    if (static_lazy && contrib[pos] >= 0 && pos < cur_end) { lazy_flipped.push((uint32_t)pos); }     // it is a real entry from now on
     contrib[pos] = -1;
     const int mn = walk_min[pos];
     if (mn < 0) { return; }
@@ -1431,6 +1524,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_str);
     const bool unlimited = !opt.limited;
+    ensureHostLists();
     logClear(); dirty_str.clear();
     if (str_prepared) { str_prepared = false; }            // scan + closure were done while the subsumption commit ran
     else if (opt.strength) {
@@ -1558,12 +1652,44 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         });
     }
     lap("contrib");
+    // In lazy mode the walk visits only the entries that are not inert ("real": own hits, candidate targets, deleted or
+    // unflagged clauses, lists with deleted entries); the inert runs in between are added up from their contributions.
+    std::vector<uint32_t> reals; lazy_flipped = std::priority_queue<uint32_t>();
+    if (static_lazy) {
+        const size_t nq = strq.size();
+        std::vector<size_t> cntp((size_t)nthreads + 2, 0);
+        parallelFor(nq, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t i = b; i < e; ++i) { c += contrib[i] < 0 ? 1 : 0; } cntp[(size_t)t + 1] = c; });
+        for (size_t t = 1; t < cntp.size(); ++t) { cntp[t] += cntp[t - 1]; }
+        reals.resize(cntp.back());
+        parallelFor(nq, [&](size_t b, size_t e, int t) { size_t o = cntp[(size_t)t]; for (size_t i = b; i < e; ++i) { if (contrib[i] < 0) { reals[o++] = (uint32_t)i; } } });
+    }
+    size_t ri = reals.size();                                       // reals[0..ri) are still ahead (the walk goes down)
+    lap("reals");
     std::vector<uint32_t> localQueue;
     size_t end = strq.size();
     int ret = L_UNDEF; bool early = false;
     for (; end > 0 && (unlimited || str_steps < str_lim);) {
         uint32_t cr;
         if (localQueue.empty()) {
+            if (static_lazy && hasToPropagate()) { cur_end = end; leaveLazy(); }
+            if (static_lazy) {
+                // next real entry below `end`: from the plan, or one that an unpredicted hit turned real meanwhile
+                while (ri > 0 && reals[ri - 1] >= end) { --ri; }
+                while (!lazy_flipped.empty() && lazy_flipped.top() >= end) { lazy_flipped.pop(); }
+                long nxt = ri > 0 ? (long)reals[ri - 1] : -1;
+                if (!lazy_flipped.empty() && (long)lazy_flipped.top() > nxt) { nxt = (long)lazy_flipped.top(); }
+                int64_t run = 0;
+                for (size_t p = (size_t)(nxt + 1); p < end; ++p) { run += contrib[p]; }      // all inert: contributions >= 0
+                str_steps += run; n_lazy += (int64_t)(end - (size_t)(nxt + 1));
+                if (nxt < 0) { end = 0; cur_end = 0; break; }
+                end = (size_t)nxt + 1;                               // the shared code below steps onto it
+                if (ri > 8) {                                        // look ahead: the clause, its counters and its scan record
+                    const uint32_t c2 = strq[reals[ri - 8]]; const ClauseInfo& ci2 = C[c2];
+                    __builtin_prefetch(&ci2);
+                    if (ri > 4) { const ClauseInfo& c3 = C[strq[reals[ri - 4]]]; const int32_t* l3 = pool.data() + c3.start; const uint32_t n3 = std::min<uint32_t>(c3.size, 6); for (uint32_t k = 0; k < n3; ++k) { __builtin_prefetch(&hot[l3[k] & ~1]); } }
+                    if (c2 < c_str.slot.size()) { __builtin_prefetch(&c_str.slot[c2]); }
+                }
+            }
             --end; cur_end = end;
             if (end >= 24 && contrib[end - 24] < 0) {           // look ahead past the inert entries: the next real one
                 const ClauseInfo& c2 = C[strq[end - 24]]; const int32_t* l2 = pool.data() + c2.start;
@@ -2194,6 +2320,7 @@ void Engine::sequentiellBVE()
 int Engine::bveProcess()
 {
     if (!performSimplification(t_bve)) { return L_UNDEF; }
+    ensureHostLists();
     for (int v = 0; v < nvars; ++v) { if (modTimer[v] >= bve_modtime && !inHeap(v)) { heapInsert(v); } }
     if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return L_FALSE; }
     const bool propagatedSomething = t_up.modified;
@@ -2222,8 +2349,8 @@ void Engine::initData()
     ph_upload += now_ns() - ti0; ti0 = now_ns();
     std::vector<uint32_t> off((size_t)n2 + 1, 0);
     if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
-    occ_pool.resize((size_t)off[n2] + 16);                 // filled by the download below
-    if (cp3g_download_occ(gpu, off.data(), occ_pool.data()) != CP3G_OK) { die("download_occ failed"); }
+    occ_pool.resize((size_t)off[n2] + 16);                 // filled by ensureHostLists() / the device-side commit of the first pass
+    lists_on_device = true;
     for (int x = 0; x < n2; ++x) {
         occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];
         hot[x].cnt = (int32_t)hot[x].n;
@@ -2469,7 +2596,7 @@ int64_t Engine::stat(const char* s) const
     ST("bulk_ingests", n_bulk_ingests) ST("queue_target_fast", n_tfast)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
-    ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("overlapped_str_scans", n_overlap)
+    ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("device_sub_passes", n_devsub) ST("overlapped_str_scans", n_overlap)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

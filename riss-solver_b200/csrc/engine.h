@@ -14,6 +14,7 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+#include <queue>
 #include <thread>
 #include <memory>
 #include "../../include/cp3b200.h"
@@ -202,6 +203,7 @@ private:
     // lazy form of the static plan: the inert entries' F_STR flags are cleared up front (in parallel) and the ordered
     // walk only adds their step contribution; cur_end = queue position being processed (everything above is done)
     bool static_lazy = false; size_t cur_end = 0; int64_t n_lazy = 0;
+    std::priority_queue<uint32_t> lazy_flipped;      // inert entries below the walk that an unpredicted hit turned into real ones
     std::vector<int32_t> last_static_walk;           // per literal: highest queue position of an inert entry that walks its list
     void leaveLazy();                                // make the deferred state explicit (a unit is about to be propagated)
     bool lazyPending(uint32_t c) const;              // inert entry whose turn has not come yet (its flag is logically still set)
@@ -288,6 +290,11 @@ private:
     bool hasToPropagate() const { return (int)trail.size() != qhead; }
     void subsumptionWorker(bool useHeap, int ignore);
     bool subsumptionCommitParallel();
+    // the occurrence lists as K2 built them are still on the device only (nobody on the host has looked at them yet): the first
+    // subsumption pass can then be committed by the device (cp3g_sub_pass), which hands back the lists in their post-pass order
+    bool lists_on_device = false; int64_t n_devsub = 0;
+    void ensureHostLists();
+    bool subsumptionCommitDevice();
     // overlap: the strengthening scan + speculative closure of this fixpoint round run on a helper thread (GPU +
     // one core) while the subsumption commit occupies the other cores
     bool overlap_str = false, str_prepared = false, scan_no_flush = false;

@@ -41,13 +41,8 @@
 #include "../../include/cp3b200.h"
 #include "gpu_db.h"
 
-#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g->fail(#call, _e); return CP3G_ERR_CUDA; } } while (0)
-
-static constexpr uint32_t FLAG_DEL = 0x80000000u;
-static constexpr uint32_t SIZE_MASK = 0x00ffffffu;
 static constexpr int SHORT_LIST = 48;
 // occurrence entry: top two bits of `ref` = class of the clause in this list (see k_occ_fill)
-static constexpr uint32_t REF_MASK = 0x3fffffffu;
 static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 // full-queue kernel tiling
 #ifndef CP3_TILE
@@ -77,8 +72,6 @@ static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = CP3_GROUPMAX, TCAP = TILE + GROUP_MAX, OFFCAP = CP3_OFFCAP, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
 
-struct __align__(16) ClauseHdr { uint32_t start; uint32_t szfl; unsigned long long sig; };
-struct __align__(16) OccEnt { uint32_t ref; uint32_t szfl; unsigned long long sig; };
 
 __host__ __device__ __forceinline__ unsigned long long lit_bit(int32_t x)
 {
@@ -1151,57 +1144,7 @@ __global__ void k_dense_rewrite(const ClauseHdr* __restrict__ hdr, int32_t* __re
     for (uint32_t k = 0; k < sz; ++k) { const uint32_t x = (uint32_t)lits[h.start + k]; lits[h.start + k] = (int32_t)(2u * mapping[x >> 1] + (x & 1u)); }
 }
 
-// ------------------------------------------------------------------------------------------ host side
-struct cp3g {
-    int device = 0; int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    uint32_t nvars = 0, ncl = 0, ncl_csr = 0;
-    size_t nlits = 0;
-    DevBuf<int32_t> lits, lits2; DevBuf<ClauseHdr> hdr;
-    DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, srt_v, srt_k2, srt_v2, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
-    DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
-    DevBuf<unsigned char> sort_tmp;
-    DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)
-    DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
-    std::vector<uint32_t> ovf_host;
-    uint32_t total_occ = 0;
-    int rank = 0, world = 1; void* nccl = nullptr;
-    int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0, scan_ns = 0, scan_alg_bytes = 0;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    uint32_t* pin_cnt = nullptr; cp3g_hit* pin_hits = nullptr;          // pinned: counters + the first PIN_HITS hits come back with one sync
-    void fail(const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); fprintf(stderr, "cp3b200: CUDA error %s\n", err.c_str()); }
-};
-
-template <class T> int DevBuf<T>::reserve(size_t n, bool keep, cudaStream_t st)
-{
-    if (n <= cap) { return 0; }
-    size_t ncap = std::max(n, cap + cap / 2 + 64);
-    T* np = nullptr;
-    // stream-ordered allocation from the device's default pool (its release threshold is lifted in cp3g_create):
-    // buffers of a destroyed handle go back to the pool, so the next CPinit/CPpreprocess in the process does not pay
-    // for mapping several hundred MB again
-    cudaError_t e = cudaMallocAsync((void**)&np, ncap * sizeof(T), st);
-    if (e != cudaSuccess) { return (int)e; }
-    if (keep && p && used) { cudaMemcpyAsync(np, p, used * sizeof(T), cudaMemcpyDeviceToDevice, st); }
-    if (p) { cudaFreeAsync(p, st); }
-    p = np; cap = ncap;
-    return 0;
-}
-template <class T> void DevBuf<T>::release(cudaStream_t st) { if (p) { cudaFreeAsync(p, st); } p = nullptr; cap = used = 0; }
-
-#define RESERVE(buf, n, keep) do { int _r = (buf).reserve((n), (keep), g->stream); if (_r) { g->fail("cudaMalloc", (cudaError_t)_r); return CP3G_ERR_CUDA; } } while (0)
-
-static inline unsigned grid_for(size_t n, int block) { return (unsigned)((n + block - 1) / block); }
-
-struct KTimer {
-    cp3g* g;
-    explicit KTimer(cp3g* g_) : g(g_) { cudaEventRecord(g->ev0, g->stream); }
-    void stop() { cudaEventRecord(g->ev1, g->stream); }
-    int64_t collect() { float ms = 0; if (cudaEventElapsedTime(&ms, g->ev0, g->ev1) == cudaSuccess) { g->kernel_ns += (int64_t)(ms * 1e6); return (int64_t)(ms * 1e6); } return 0; }
-};
-
+// ------------------------------------------------------------------------------------------ host side (struct cp3g: gpu_db.h)
 // Hits leave the scan kernels in warp-completion order; the host commit consumes them grouped by request and
 // ordered by clause index (duplicate ties are decided by index), so they are sorted on the device before the copy.
 struct HitLess { __device__ bool operator()(const cp3g_hit& a, const cp3g_hit& b) const { return a.req != b.req ? a.req < b.req : a.clause < b.clause; } };
@@ -1216,6 +1159,31 @@ static int sort_hits(cp3g* g, uint32_t n)
     return CP3G_OK;
 }
 static constexpr uint32_t SORT_ON_DEVICE_MIN = 2048;
+
+// refs_tmp := the occurrence lists in the reference's order, plain ascending clause index (CoprocessorData::addClause order,
+// CoprocessorTypes.h:812-833); the device lists themselves are ordered (class, clause index)
+int dev_host_order_lists(cp3g* g)
+{
+    const uint32_t nlit = 2 * g->nvars;
+    if (!g->total_occ) { return CP3G_OK; }
+    RESERVE(g->refs_tmp, g->total_occ, false);
+    k_gather_refs<<<grid_for(g->total_occ, 256), 256, 0, g->stream>>>(g->occ_ent.p, g->refs_tmp.p, g->total_occ);
+    CK(cudaMemsetAsync(g->counters.p + 1, 0, sizeof(uint32_t), g->stream));
+    k_occ_sort_short<<<grid_for(nlit, SORT_LISTS), SORT_LISTS, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
+    uint32_t nlong = 0;
+    CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    if (nlong) { k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p); g->launches++; }
+    g->launches += 2;
+    return CP3G_OK;
+}
+int dev_set_deleted(cp3g* g, const uint32_t* dev_ids, uint32_t n)
+{
+    if (!n) { return CP3G_OK; }
+    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, dev_ids, n);
+    g->launches++;
+    return CP3G_OK;
+}
 
 extern "C" {
 
@@ -1258,6 +1226,8 @@ void cp3g_destroy(cp3g* g)
     g->sort_tmp.release(g->stream); g->req_self.release(g->stream); g->req_off.release(g->stream); g->req_lits.release(g->stream); g->hits.release(g->stream); g->counters.release(g->stream);
     g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
     g->bs0.release(g->stream); g->bl0.release(g->stream);
+    g->sp_da.release(g->stream); g->sp_db.release(g->stream); g->sp_chosen.release(g->stream); g->sp_dltime.release(g->stream); g->sp_dlcnt.release(g->stream); g->sp_dloff.release(g->stream);
+    g->sp_dlfill.release(g->stream); g->sp_n.release(g->stream); g->sp_stale.release(g->stream); g->sp_dead.release(g->stream); g->sp_refs.release(g->stream);
     cudaStreamSynchronize(g->stream);
     cp3g_nccl_free(g->nccl);
     if (g->pin_cnt) { cudaFreeHost(g->pin_cnt); } if (g->pin_hits) { cudaFreeHost(g->pin_hits); }
@@ -1424,16 +1394,8 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
     CK(cudaStreamSynchronize(g->stream));
     g->d2h += (int64_t)(((size_t)nlit + 1) * sizeof(uint32_t));
     if (refs && g->total_occ) {
-        RESERVE(g->refs_tmp, g->total_occ, false);
-        // device lists are ordered (class, clause index); the reference order is plain ascending clause index
-        k_gather_refs<<<grid_for(g->total_occ, 256), 256, 0, g->stream>>>(g->occ_ent.p, g->refs_tmp.p, g->total_occ);
-        CK(cudaMemsetAsync(g->counters.p + 1, 0, sizeof(uint32_t), g->stream));
-        k_occ_sort_short<<<grid_for(nlit, SORT_LISTS), SORT_LISTS, 0, g->stream>>>(g->occ_off.p, nlit, g->refs_tmp.p, g->long_lits.p, g->counters.p + 1);
-        uint32_t nlong = 0;
-        CK(cudaMemcpyAsync(&nlong, g->counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
-        if (nlong) { k_occ_sort_long<<<nlong, 1024, 0, g->stream>>>(g->occ_off.p, g->long_lits.p, g->refs_tmp.p); g->launches++; }
-        g->launches += 2;
+        int r = dev_host_order_lists(g);
+        if (r != CP3G_OK) { return r; }
         CK(cudaMemcpyAsync(refs, g->refs_tmp.p, (size_t)g->total_occ * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
         CK(cudaStreamSynchronize(g->stream));
         g->d2h += (int64_t)g->total_occ * 4;
@@ -1805,7 +1767,7 @@ int cp3g_dense(cp3g* g, const uint8_t* keep, int frag_percent, uint32_t* mapping
 }
 
 // exclusive scan of n u32 values (in -> out) on the handle stream; the total lands in counters[2]
-static int scan_u32(cp3g* g, const uint32_t* in, uint32_t* out, size_t n)
+int scan_u32(cp3g* g, const uint32_t* in, uint32_t* out, size_t n)
 {
     const uint32_t nt = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
     RESERVE(g->tile_sum, (size_t)nt + 1, false);
@@ -1940,6 +1902,7 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "scan_requests")) { return g->scan_requests; }
     if (!strcmp(name, "scan_checks")) { return g->scan_checks; }
     if (!strcmp(name, "scan_ns")) { return g->scan_ns; }
+    if (!strcmp(name, "commit_ns")) { return g->commit_ns; }
     if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }
     if (!strcmp(name, "nlits")) { return (int64_t)g->nlits; }

@@ -15,6 +15,8 @@ struct cp3g {
     std::vector<size_t> start; size_t nlits = 0;          // pool offsets as uploaded / appended (cp3g_dense writes the pool back)
     std::vector<std::vector<uint32_t>> occ;
     int64_t launches = 0, requests = 0, checks = 0;
+    // result of the last cp3g_sub_pass
+    bool sp_valid = false; std::vector<uint32_t> sp_dead, sp_n, sp_stale; std::vector<std::vector<uint32_t>> sp_lists;
     std::string err;
 };
 
@@ -85,6 +87,50 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
     uint32_t o = 0;
     for (size_t x = 0; x < g->occ.size(); ++x) { off[x] = o; if (refs) { std::copy(g->occ[x].begin(), g->occ[x].end(), refs + o); } o += (uint32_t)g->occ[x].size(); }
     off[g->occ.size()] = o;
+    return CP3G_OK;
+}
+// The device-side commit of the first subsumption pass, mocked by the plain ordered walk it must reproduce
+// (Subsumption::subsumption_worker, Subsumption.cc:244-313) over the pristine lists.
+int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead, uint64_t* nlits, uint64_t* steps, uint64_t* checks)
+{
+    *status = 1; g->sp_valid = false;
+    if (g->cl.empty()) { return CP3G_OK; }
+    cp3g_build(g);
+    std::vector<std::vector<uint32_t>> L = g->occ;
+    std::vector<int> cnt(L.size());
+    for (size_t x = 0; x < L.size(); ++x) { cnt[x] = (int)L[x].size(); }
+    std::vector<uint8_t> del = g->del; std::vector<uint32_t> dead; uint64_t st = 0, nl = 0;
+    for (uint32_t c = (uint32_t)g->cl.size(); c-- > 0;) {
+        if (del[c]) { continue; }
+        const std::vector<int32_t>& C = g->cl[c];
+        int32_t mn = C[0];
+        for (size_t k = 1; k < C.size(); ++k) { if (cnt[C[k]] < cnt[mn]) { mn = C[k]; } }
+        std::vector<uint32_t>& li = L[mn];
+        for (size_t i = 0; i < li.size(); ++i) {
+            const uint32_t d = li[i];
+            if (d == c) { continue; }
+            ++st;
+            if (g->cl[d].size() < C.size()) { continue; }
+            if (del[d]) { li[i] = li.back(); li.pop_back(); --i; continue; }
+            if (subset(C, g->cl[d])) { del[d] = 1; dead.push_back(d); nl += g->cl[d].size(); for (int32_t x : g->cl[d]) { --cnt[x]; } }
+        }
+    }
+    // the kernel refuses lists with subsumed clauses that are longer than max_list
+    for (uint32_t d : dead) { for (int32_t x : g->cl[d]) { if (g->occ[x].size() > max_list) { return CP3G_OK; } } }
+    g->sp_dead = dead; g->sp_lists = L; g->sp_n.assign(L.size(), 0); g->sp_stale.assign(L.size(), 0);
+    for (size_t x = 0; x < L.size(); ++x) { g->sp_n[x] = (uint32_t)L[x].size(); for (uint32_t d : L[x]) { g->sp_stale[x] += del[d] && !g->del[d]; } }
+    for (uint32_t d : dead) { g->del[d] = 1; }
+    g->sp_valid = true; g->launches += 12;
+    *status = 0; *ndead = (uint32_t)dead.size(); *nlits = nl; *steps = st; if (checks) { *checks = st; }
+    return CP3G_OK;
+}
+int cp3g_sub_pass_fetch(cp3g* g, uint32_t* dead, uint32_t* list_n, uint32_t* list_stale, uint32_t* refs)
+{
+    if (!g->sp_valid) { return CP3G_ERR_ARG; }
+    if (dead) { std::copy(g->sp_dead.begin(), g->sp_dead.end(), dead); }
+    if (list_n) { std::copy(g->sp_n.begin(), g->sp_n.end(), list_n); }
+    if (list_stale) { std::copy(g->sp_stale.begin(), g->sp_stale.end(), list_stale); }
+    if (refs) { uint32_t o = 0; for (size_t x = 0; x < g->occ.size(); ++x) { std::copy(g->sp_lists[x].begin(), g->sp_lists[x].end(), refs + o); o += (uint32_t)g->occ[x].size(); } }
     return CP3G_OK;
 }
 int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids) { for (uint32_t i = 0; i < n; ++i) { g->del[ids[i]] = 1; } return CP3G_OK; }

@@ -316,27 +316,62 @@ def test_k5_resolvent_counts_match_oracle_snapshot(gen):
     s = sz[int(pair_off[v]):int(pair_off[v + 1])].reshape(len(pos[v]), len(neg[v]))
     ai, bi = np.nonzero(s > 1)
     o2, rl = svc.bve_resolve(np.full(ai.size, v, np.uint32), np.asarray(pos[v])[ai], np.asarray(neg[v])[bi], s[ai, bi])
+    codes = _sorted_clauses(lits, sizes); cstart = np.concatenate([[0], np.cumsum(sizes)])
     for k in range(ai.size):
         r = rl[int(o2[k]):int(o2[k + 1])]
         assert np.all(np.diff(r) > 0) and not np.any((r >> 1) == v)
+        # the literals themselves: BoundedVariableElimination::resolve (BVE.h:208-242) = sorted union of both parents minus the pivot
+        p = int(np.asarray(pos[v])[ai[k]]); q = int(np.asarray(neg[v])[bi[k]])
+        want_r = np.union1d(codes[cstart[p]:cstart[p + 1]], codes[cstart[q]:cstart[q + 1]])
+        assert np.array_equal(r, want_r[(want_r >> 1) != v]), (v, p, q)
 
 
-def test_c2_size_properties(gen):
-    """BASELINE config 2 (1M vars / 4.26M clauses + planted redundancy): idempotence and soundness properties
-    that do not need the oracle at this size."""
+def test_device_subsumption_commit_matches_the_ordered_walk(gen):
+    """cp3g_sub_pass (commit.cu) against the plain ordered walk of Subsumption::subsumption_worker over the same pristine lists
+    (tests/mock runs it sequentially): subsumed set, literal total, step counter, and every occurrence list in its post-pass
+    ORDER (lazy swap-with-last cleaning) with its count of deleted entries left behind."""
+    from fuzz_engine import build_mock
+    mock = build_mock()
+    cases = [gen.random_ksat(30000, 127800, 3, seed=21, dup=0.04, sup=0.06, flip=0.02),
+             gen.community_ksat(20000, 100000, seed=22),
+             gen.random_ksat(3000, 12780, 3, seed=23, zipf_s=0.9, dup=0.05, sup=0.08)]
+    for lits, sizes in cases:
+        n = int(np.abs(lits).max()); codes = _sorted_clauses(lits, sizes)
+        res = []
+        for lib in (None, mock):
+            svc = rs.ScanService(lib_path=lib); svc.upload(n, codes, sizes); svc.build()
+            res.append(svc.sub_pass(max_list=1 << 20)); svc.close()
+        a, b = res
+        assert a is not None and b is not None
+        assert np.array_equal(a["dead"], b["dead"]) and a["dead"].size > 0
+        assert a["lits"] == b["lits"] and a["steps"] == b["steps"]
+        assert np.array_equal(a["off"], b["off"]) and np.array_equal(a["n"], b["n"]) and np.array_equal(a["stale"], b["stale"])
+        for x in np.flatnonzero(a["n"] != (a["off"][1:] - a["off"][:-1])).tolist() + list(range(0, 2 * n, 97)):
+            o = int(a["off"][x]); k = int(a["n"][x])
+            assert np.array_equal(a["refs"][o:o + k], b["refs"][o:o + k]), x
+
+
+def test_c2_full_size_ordered_against_the_reference(gen):
+    """BASELINE configs[1] at full size (1M vars / 4.26M clauses + planted redundancy): ordered output stream, trail and every
+    counter against the sequential reference (oracle/_ref/refshim, ~7 s) when it was built; else against the C oracle.
+    Plus the size-independent properties: no duplicate survives, a second pass over the fixpoint changes nothing."""
+    from harness import have_ref, run_ref
     lits, sizes = gen.random_ksat(1000000, 4260000, 3, seed=12345)
     stream = gen.csr_to_stream(lits, sizes)
-    a = run_gpu(stream, SUSI + ["-no-cp3_limited"])
+    opts = SUSI + ["-no-cp3_limited"]
+    a = run_gpu(stream, opts)
     assert a.ok == 1
+    b = run_ref(stream, opts) if have_ref() else run_oracle(stream, opts)
+    assert np.array_equal(a.trail, b.trail) and np.array_equal(a.stream, b.stream)
+    for k in STAT_NAMES:
+        assert a.stats[k] == b.stats[k], k
     out = a.stream
-    # every planted duplicate / superset must be gone: the output has no two identical clauses
     z = np.flatnonzero(out == 0); osz = np.diff(np.concatenate([[-1], z])) - 1
     assert osz.size < sizes.size and a.stats["sub_subsumedClauses"] > 0.04 * 4260000
-    # idempotence: a second pass over the fixpoint removes nothing
     full = np.concatenate([np.stack([a.trail, np.zeros_like(a.trail)], 1).reshape(-1), out]).astype(np.int32)
-    b = run_gpu(full, SUSI + ["-no-cp3_limited"])
-    assert b.stats["sub_subsumedClauses"] == 0 and b.stats["sub_removedLiterals"] == 0
-    assert np.array_equal(b.stream, out)
+    c = run_gpu(full, opts)
+    assert c.stats["sub_subsumedClauses"] == 0 and c.stats["sub_removedLiterals"] == 0
+    assert np.array_equal(c.stream, out)
 
 
 def test_forced_parallel_paths_on_gpu(gen):
