@@ -602,11 +602,11 @@ void Engine::prefetchStrengthenClosure()
 {
     PhaseTimer pt(ph_prefetch);
     struct Ev { uint32_t clause; int32_t lit; double time; };
-    std::vector<Ev> evs;                                 // all predicted removals so far, sorted by (clause, time)
-    // hash of (clause, content) already scanned: open addressing (the node-based set cost 40 % of the request pass)
+    // hash of (clause, content) already scanned: open addressing (the node-based set cost 40 % of the request pass).
+    // One set per worker; a clause always belongs to the same worker (fixed clause-index ranges), so no set is shared.
     struct HashSet {
         std::vector<uint64_t> t; size_t n = 0;
-        HashSet() : t(1u << 16, 0ull) {}
+        HashSet() : t(1u << 12, 0ull) {}
         bool insert(uint64_t h) {                           // true if new
             if (h == 0) { h = 0x9E3779B97F4A7C15ull; }
             if (2 * (n + 1) > t.size()) {
@@ -618,7 +618,12 @@ void Engine::prefetchStrengthenClosure()
             if (t[i] == h) { return false; }
             t[i] = h; ++n; return true;
         }
-    } requested;
+    };
+    const int W = std::max(1, nthreads);
+    const uint32_t ncl = (uint32_t)C.size();
+    const uint32_t width = ncl / (uint32_t)W + 1;               // worker w owns the clauses [w*width, (w+1)*width)
+    std::vector<HashSet> requested((size_t)W);
+    std::vector<std::vector<Ev>> evs((size_t)W);                 // per worker: predicted removals of its clauses, sorted by (clause, time)
     size_t first_ent = 0;
     DbgLap lap("closure");
     // Speculation is only worth its scans while they are cheap next to the full-queue pass: a request costs the
@@ -626,59 +631,84 @@ void Engine::prefetchStrengthenClosure()
     // Budget: four times the occurrence count of the data base; what is not prefetched is scanned on demand.
     int64_t spec_budget = 4 * (int64_t)pool.size();
     bool budget_left = true;
+    struct Req { uint32_t clause, off, n, walk; double time; };
     for (int round = 0; round < 8 && budget_left; ++round) {
-        std::vector<uint32_t> changed;
-        const size_t old_n = evs.size();
-        for (size_t ei = first_ent; ei < c_str.ent.size(); ++ei) {
-            const CacheEnt& e = c_str.ent[ei];
-            for (uint32_t h = e.hb; h < e.he; ++h) { evs.push_back({c_str.hits[h].clause, c_str.hits[h].lit, e.time}); }
-        }
-        first_ent = c_str.ent.size();
-        if (evs.size() == old_n) { break; }
-        for (size_t i = old_n; i < evs.size(); ++i) { changed.push_back(evs[i].clause); }
-        // a literal can be removed once: keep the earliest prediction per (clause, literal)
-        std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) {
-            return a.clause != b.clause ? a.clause < b.clause : (a.lit != b.lit ? a.lit < b.lit : a.time < b.time); });
-        evs.erase(std::unique(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.clause == b.clause && a.lit == b.lit; }), evs.end());
-        std::sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.clause != b.clause ? a.clause < b.clause : a.time < b.time; });
-        std::sort(changed.begin(), changed.end());
-        changed.erase(std::unique(changed.begin(), changed.end()), changed.end());
-        lap("evs+sorts");
-        std::vector<SpecReq> reqs; spec_lits.clear();
-        size_t p = 0;
-        for (uint32_t d : changed) {
-            while (p < evs.size() && evs[p].clause < d) { ++p; }
-            size_t q = p;
-            while (q < evs.size() && evs[q].clause == d) { ++q; }
-            const Ev* ev = evs.data() + p; const size_t m = q - p;
-            p = q;
-            if ((C[d].flag & F_DEL) || m == 0 || !budget_left) { continue; }
-            const bool pending = (C[d].flag & F_STR) && d < qtime.size() && qtime[d] >= 0;
-            const double own = pending ? (double)qtime[d] : -1.0;
-            size_t k0 = 0;
-            if (pending) { while (k0 < m && ev[k0].time < own) { ++k0; } }
-            for (size_t k = std::max<size_t>(k0, 1); k <= m && k <= 6; ++k) {
-                if (C[d].size < k + 2) { break; }          // would be a unit: handled by propagation, never scanned
-                // content = current literals minus the first k predicted removals
-                uint64_t hsh = 1469598103934665603ull ^ d;
-                const uint32_t off = (uint32_t)spec_lits.size();
-                const int32_t* l = CL(d);
-                for (uint32_t i = 0; i < C[d].size; ++i) {
-                    bool rm = false;
-                    for (size_t j = 0; j < k; ++j) { if (ev[j].lit == l[i]) { rm = true; break; } }
-                    if (!rm) { spec_lits.push_back(l[i]); hsh = (hsh ^ (uint32_t)l[i]) * 1099511628211ull; }
-                }
-                const uint32_t nl = (uint32_t)spec_lits.size() - off;
-                if (nl != C[d].size - k || !requested.insert(hsh)) { spec_lits.resize(off); continue; }
-                const double t = (pending && k == k0) ? own : std::max(own, ev[k - 1].time) + 1e-3 * (round + 1);
-                uint32_t walk = 0xffffffffu;
-                for (uint32_t i = 0; i < nl; ++i) { const int x = spec_lits[off + i]; walk = std::min(walk, hot[x].n + hot[x ^ 1].n); }
-                spec_budget -= walk;
-                if (spec_budget < 0) { budget_left = false; spec_lits.resize(off); break; }
-                reqs.push_back({d, off, nl, t});
+        // (1) the hits of the cache entries that are new since the last round become events of the target's owner
+        const size_t ne = c_str.ent.size();
+        if (ne == first_ent) { break; }
+        std::vector<std::vector<Ev>> fresh((size_t)W * (size_t)W);          // [producer][owner]
+        parallelFor(ne - first_ent, [&](size_t b2, size_t e2, int t) {
+            std::vector<Ev>* out = &fresh[(size_t)t * (size_t)W];
+            for (size_t ei = first_ent + b2; ei < first_ent + e2; ++ei) {
+                const CacheEnt& e = c_str.ent[ei];
+                for (uint32_t h = e.hb; h < e.he; ++h) { const Hit& x = c_str.hits[h]; out[x.clause / width].push_back({x.clause, x.lit, e.time}); }
             }
+        }, 4096);
+        first_ent = ne;
+        size_t nfresh = 0; for (const auto& v : fresh) { nfresh += v.size(); }
+        if (nfresh == 0) { break; }
+        // (2)+(3) per owner: merge, keep the earliest prediction per (clause, literal), order by (clause, time), then build the
+        //         requests of the clauses that got a new event: current content minus the first k predicted removals
+        std::vector<std::vector<Req>> wreq((size_t)W); std::vector<std::vector<int32_t>> wlits((size_t)W);
+        parallelFor((size_t)W, [&](size_t wb, size_t we, int) {
+            for (size_t w = wb; w < we; ++w) {
+                std::vector<Ev>& ev = evs[w];
+                std::vector<uint32_t> changed;
+                for (int t = 0; t < W; ++t) { const std::vector<Ev>& f = fresh[(size_t)t * (size_t)W + w]; for (const Ev& x : f) { changed.push_back(x.clause); } ev.insert(ev.end(), f.begin(), f.end()); }
+                if (changed.empty()) { continue; }
+                std::sort(ev.begin(), ev.end(), [](const Ev& a2, const Ev& b2) {
+                    return a2.clause != b2.clause ? a2.clause < b2.clause : (a2.lit != b2.lit ? a2.lit < b2.lit : a2.time < b2.time); });
+                ev.erase(std::unique(ev.begin(), ev.end(), [](const Ev& a2, const Ev& b2) { return a2.clause == b2.clause && a2.lit == b2.lit; }), ev.end());
+                std::sort(ev.begin(), ev.end(), [](const Ev& a2, const Ev& b2) { return a2.clause != b2.clause ? a2.clause < b2.clause : a2.time < b2.time; });
+                std::sort(changed.begin(), changed.end());
+                changed.erase(std::unique(changed.begin(), changed.end()), changed.end());
+                std::vector<Req>& reqs = wreq[w]; std::vector<int32_t>& sl = wlits[w]; HashSet& seen = requested[w];
+                size_t p = 0;
+                for (uint32_t d : changed) {
+                    while (p < ev.size() && ev[p].clause < d) { ++p; }
+                    size_t q = p;
+                    while (q < ev.size() && ev[q].clause == d) { ++q; }
+                    const Ev* e1 = ev.data() + p; const size_t m = q - p;
+                    p = q;
+                    if ((C[d].flag & F_DEL) || m == 0) { continue; }
+                    const bool pending = (C[d].flag & F_STR) && d < qtime.size() && qtime[d] >= 0;
+                    const double own = pending ? (double)qtime[d] : -1.0;
+                    size_t k0 = 0;
+                    if (pending) { while (k0 < m && e1[k0].time < own) { ++k0; } }
+                    for (size_t k = std::max<size_t>(k0, 1); k <= m && k <= 6; ++k) {
+                        if (C[d].size < k + 2) { break; }          // would be a unit: handled by propagation, never scanned
+                        // content = current literals minus the first k predicted removals
+                        uint64_t hsh = 1469598103934665603ull ^ d;
+                        const uint32_t off = (uint32_t)sl.size();
+                        const int32_t* l = CL(d);
+                        for (uint32_t i = 0; i < C[d].size; ++i) {
+                            bool rm = false;
+                            for (size_t j = 0; j < k; ++j) { if (e1[j].lit == l[i]) { rm = true; break; } }
+                            if (!rm) { sl.push_back(l[i]); hsh = (hsh ^ (uint32_t)l[i]) * 1099511628211ull; }
+                        }
+                        const uint32_t nl = (uint32_t)sl.size() - off;
+                        if (nl != C[d].size - k || !seen.insert(hsh)) { sl.resize(off); continue; }
+                        const double t = (pending && k == k0) ? own : std::max(own, e1[k - 1].time) + 1e-3 * (round + 1);
+                        uint32_t walk = 0xffffffffu;
+                        for (uint32_t i = 0; i < nl; ++i) { const int x = sl[off + i]; walk = std::min(walk, hot[x].n + hot[x ^ 1].n); }
+                        reqs.push_back({d, off, nl, walk, t});
+                    }
+                }
+            }
+        }, 1);
+        lap("events+requests");
+        // (4) one request list in clause order, cut where the budget ends
+        std::vector<SpecReq> reqs; spec_lits.clear();
+        for (int w = 0; w < W && budget_left; ++w) {
+            const uint32_t base = (uint32_t)spec_lits.size(); size_t used = 0;
+            for (const Req& r : wreq[(size_t)w]) {
+                spec_budget -= r.walk;
+                if (spec_budget < 0) { budget_left = false; break; }
+                reqs.push_back({r.clause, base + r.off, r.n, r.time}); used = (size_t)r.off + r.n;
+            }
+            spec_lits.insert(spec_lits.end(), wlits[(size_t)w].begin(), wlits[(size_t)w].begin() + (std::ptrdiff_t)used);
         }
-        lap("reqs");
+        lap("merge");
         if (reqs.empty()) { break; }
         scanSpeculative(CP3G_STRENGTHEN, reqs, c_str);
         lap("scanSpeculative");
