@@ -147,6 +147,24 @@ int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p
 int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs,
                      const uint32_t* n_refs, const uint64_t* out_off, int32_t* out_lits, size_t nlits);
 
+/* K5': the whole per-variable evaluation of bve_worker (BVE.cc:388-637) for a batch of candidate variables, one warp each
+ * (bve_eval.cu): gate detection with list reordering (findGates, BVE.cc:1143-1267; use_gates = -bve_gates), lazy removal of the
+ * deleted entries by swap-with-last (BVE.cc:474-489), resolvent anticipation over the pairs the gate limits leave
+ * (anticipateElimination, BVE.cc:695-880).  Variable i owns p_refs[p_off[i]..p_off[i+1]) / n_refs[...] in the host's current
+ * list ORDER; both arrays are rewritten in place with the cleaned, reordered lists (first pos_n / neg_n entries), p_stats /
+ * n_stats (may be NULL) receive the per-clause resolvent counts (pos_stats / neg_stats, a clause with 0 is blocked,
+ * BVE.cc:1053-1090).  CP3G_BVE_HOST in flags: a unit or empty resolvent exists or a list exceeds the kernel's capacity - the
+ * record is void, evaluate this variable through cp3g_bve_pairs. */
+typedef struct { int32_t p_limit, n_limit; uint32_t pos_n, neg_n, resolvents, lit_clauses, steps, flags; } cp3g_bve_rec;
+enum { CP3G_BVE_GATE = 1, CP3G_BVE_HOST = 2 };
+int cp3g_bve_eval(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, uint32_t* p_refs, const uint32_t* n_off, uint32_t* n_refs,
+                  int use_gates, cp3g_bve_rec* recs, uint16_t* p_stats, uint16_t* n_stats);
+/* K6': resolvents of the batch variables sel[0..nsel) (indices into the last cp3g_bve_eval batch) in resolveSet's order
+ * (BVE.cc:892-1046).  Variable sel[k] has recs[].resolvents resolvents with recs[].lit_clauses literals in total: the caller
+ * passes their prefix sums res_off / lit_off (nsel+1 entries); out_sizes[res_off[k]..) = size per resolvent, out_lits[lit_off[k]..)
+ * = their literals back to back. */
+int cp3g_bve_stream(cp3g* g, uint32_t nsel, const uint32_t* sel, const uint64_t* res_off, const uint64_t* lit_off, uint16_t* out_sizes, int32_t* out_lits);
+
 /* K7: Dense::compress (coprocessor/techniques/Dense.cc:26-238, countLiterals Dense.h:92-121, compressClauses
  * Dense.cc:406-450).  A variable stays iff it occurs in a live clause or keep[v] != 0 (frozen / kept assignment);
  * the survivors are renumbered densely in order (mapping[v] = v - #removed before v, UINT32_MAX for removed).
@@ -178,7 +196,7 @@ int cp3g_compact(cp3g* g, uint32_t* new_start, int32_t* lits_out, size_t lits_ca
 int cp3g_nccl_unique_id(void* out128);
 int cp3g_nccl_init(cp3g* g, int rank, int world, const void* id128);
 
-/* counters: "launches", "kernel_ns" (all kernels, CUDA events), "scan_ns" (K3/K4 only), "commit_ns" (device pass commit), "h2d_bytes", "d2h_bytes",
+/* counters: "launches", "kernel_ns" (all kernels, CUDA events), "scan_ns" (K3/K4 only), "commit_ns" (device pass commit), "bve_ns" (K5'/K6'), "h2d_bytes", "d2h_bytes",
  * "scan_requests", "scan_checks", "scan_alg_bytes" (sum over checks of 4 + 8 + 4*#D) */
 int64_t cp3g_counter(const cp3g* g, const char* name);
 

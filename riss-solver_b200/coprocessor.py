@@ -220,6 +220,30 @@ class ScanService:
                                        n_off.ctypes.data, n_refs.ctypes.data, pair_off.ctypes.data, sizes.ctypes.data), "bve_pairs")
         return pair_off, sizes[:int(pair_off[-1])]
 
+    def bve_eval(self, vars_, pos_lists, neg_lists, use_gates=True, stream=True):
+        """K5'/K6' (cp3g_bve_eval / cp3g_bve_stream): per variable the record (p_limit, n_limit, pos_n, neg_n, resolvents, lit_clauses,
+        steps, flags), the rewritten lists, the per-clause statistics and - for every variable without the HOST flag - its resolvents"""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.uint32)
+        nv = vars_.size
+        p_off = np.zeros(nv + 1, dtype=np.uint32); n_off = np.zeros(nv + 1, dtype=np.uint32)
+        for i, (p, n) in enumerate(zip(pos_lists, neg_lists)):
+            p_off[i + 1] = p_off[i] + len(p); n_off[i + 1] = n_off[i] + len(n)
+        cat = lambda ls: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint32) for x in ls]) if len(ls) else np.zeros(0, np.uint32), dtype=np.uint32)
+        p_refs = np.concatenate([cat(pos_lists), np.zeros(1, np.uint32)]); n_refs = np.concatenate([cat(neg_lists), np.zeros(1, np.uint32)])
+        recs = np.zeros((max(nv, 1), 8), dtype=np.int32); pst = np.zeros(p_refs.size + 1, np.uint16); nst = np.zeros(n_refs.size + 1, np.uint16)
+        self._ck(self.L.cp3g_bve_eval(self.g, nv, vars_.ctypes.data, p_off.ctypes.data, p_refs.ctypes.data, n_off.ctypes.data, n_refs.ctypes.data,
+                                      1 if use_gates else 0, recs.ctypes.data, pst.ctypes.data, nst.ctypes.data), "bve_eval")
+        recs = recs[:nv]
+        out = {"recs": recs, "p_off": p_off, "n_off": n_off, "p_refs": p_refs, "n_refs": n_refs, "p_stats": pst, "n_stats": nst}
+        if stream:
+            sel = np.flatnonzero((recs[:, 7] & 2) == 0).astype(np.uint32)
+            res_off = np.zeros(sel.size + 1, dtype=np.uint64); lit_off = np.zeros(sel.size + 1, dtype=np.uint64)
+            res_off[1:] = np.cumsum(recs[sel, 4].astype(np.uint64)); lit_off[1:] = np.cumsum(recs[sel, 5].astype(np.uint64))
+            rsz = np.zeros(int(res_off[-1]) + 1, np.uint16); rl = np.zeros(int(lit_off[-1]) + 1, np.int32)
+            self._ck(self.L.cp3g_bve_stream(self.g, sel.size, sel.ctypes.data, res_off.ctypes.data, lit_off.ctypes.data, rsz.ctypes.data, rl.ctypes.data), "bve_stream")
+            out.update(sel=sel, res_off=res_off, lit_off=lit_off, rsz=rsz[:int(res_off[-1])], rlits=rl[:int(lit_off[-1])])
+        return out
+
     def bve_resolve(self, vars_, p_refs, n_refs, sizes):
         vars_ = np.ascontiguousarray(vars_, dtype=np.uint32)
         p = np.ascontiguousarray(p_refs, dtype=np.uint32); n = np.ascontiguousarray(n_refs, dtype=np.uint32)

@@ -399,6 +399,7 @@ void Engine::ensureGpu()
 int Engine::setDistributed(int rank, int world, const void* id)
 {
     ensureGpu();
+    sharded = world > 1;
     return cp3g_nccl_init(gpu, rank, world, id);
 }
 
@@ -771,6 +772,9 @@ void Engine::occSwapRemove(int x, uint32_t i)
     ListRef l = L(x); uint32_t* p = LP(l);
     if (isDel(p[i])) { staleDec(x); }
     p[i] = p[l.n - 1]; l.n--;
+    // a walk that lazily cleans a list reorders it without changing any clause of the variable: its K5' record (evaluated on
+    // the old order) is void, let it ride along with the next batch instead of being found stale when the variable is popped
+    if (in_bve_worker) { bveTouch(x >> 1); }
 }
 void Engine::occRelease(int x) { hot[x].n = 0; staleClear(x); }
 
@@ -1948,7 +1952,7 @@ Engine::PairEnt& Engine::pairsFor(int v)
     std::vector<int> vs; vs.push_back(v);
     uint64_t budget = 0;
     size_t keep = 0;
-    for (size_t i = 0; i < bve_pending.size(); ++i) {
+    for (size_t i = 0; i < (pairs_single ? 0 : bve_pending.size()); ++i) {
         const int w = bve_pending[i];
         if (w == v || !inHeap(w) || assigns[w] != L_UNDEF || frozen[w] || hot[2 * w].n == 0 || hot[2 * w + 1].n == 0) { bve_inpend[w] = 0; continue; }
         const uint64_t np = (uint64_t)hot[2 * w].n * hot[2 * w + 1].n;
@@ -1961,7 +1965,7 @@ Engine::PairEnt& Engine::pairsFor(int v)
         budget += np; bve_inpend[w] = 0;
         vs.push_back(w);
     }
-    bve_pending.resize(keep);
+    if (!pairs_single) { bve_pending.resize(keep); }
     std::vector<uint32_t> vars, p_off{0}, n_off{0}, p_refs, n_refs; std::vector<uint64_t> pair_off{0};
     for (int w : vs) {
         vars.push_back((uint32_t)w);
@@ -2034,6 +2038,91 @@ Engine::PairEnt& Engine::pairsFor(int v)
         q.rlits = {blk.rlits.data() + rl_first[i], (size_t)(roff[rfirst[i + 1]] - roff[rfirst[i]])};
     }
     return *pairLookup(v);
+}
+
+// K5'/K6' for variable v: cached while its clauses and lists are unchanged, else one more batch - v plus every variable that
+// waits in the heap without a valid record.  The kernel evaluates gates, cleaning and anticipation per variable; for the
+// variables the decision rule (BVE.cc:532-548) will most likely eliminate the resolvents come along as a literal stream.
+Engine::EvalEnt* Engine::evalFor(int v)
+{
+    if (ev_slot.size() < (size_t)nvars) { ev_slot.resize((size_t)nvars, -1); }
+    auto fresh = [&](int w) -> EvalEnt* { const int32_t sl = ev_slot[w]; if (sl < 0) { return nullptr; } EvalEnt* e = &ev_ent[(size_t)sl]; return (e->valid && e->touch == var_touch[w]) ? e : nullptr; };
+    if (EvalEnt* e = fresh(v)) { return e; }
+    static const uint32_t LCAP = 64;
+    if (hot[2 * v].n > LCAP || hot[2 * v + 1].n > LCAP) { return nullptr; }
+    flushDevice();
+    ++n_eval_batches;
+    std::vector<int> vs; vs.push_back(v);
+    uint64_t budget = 0; size_t keep = 0;
+    for (size_t i = 0; i < bve_pending.size(); ++i) {
+        const int w = bve_pending[i];
+        if (w == v || !inHeap(w) || assigns[w] != L_UNDEF || frozen[w] || hot[2 * w].n == 0 || hot[2 * w + 1].n == 0) { bve_inpend[w] = 0; continue; }
+        if (hot[2 * w].n > LCAP || hot[2 * w + 1].n > LCAP) { bve_inpend[w] = 0; continue; }
+        const uint64_t np = (uint64_t)hot[2 * w].n * hot[2 * w + 1].n;
+        // the reference's cut-off (BVE.cc:418-420) on the current counters: such variables are skipped anyway
+        const bool cutoff = (hot[2 * w + 1].cnt > 10 && hot[2 * w].cnt > 10) || (dcount(w) > 15 && (hot[2 * w + 1].cnt > 5 || hot[2 * w].cnt > 5));
+        if (cutoff && !opt.bve_unlimited && !opt.bve_force_gates) { bve_inpend[w] = 0; continue; }
+        if (budget + np > (256u << 20)) { bve_pending[keep++] = w; continue; }   // next batch
+        if (fresh(w)) { bve_inpend[w] = 0; continue; }
+        budget += np; bve_inpend[w] = 0;
+        vs.push_back(w);
+    }
+    bve_pending.resize(keep);
+    eval_blocks.emplace_back(new EvalBlock());
+    EvalBlock& blk = *eval_blocks.back();
+    const size_t nv = vs.size();
+    std::vector<uint32_t> vars(nv), p_off(nv + 1, 0), n_off(nv + 1, 0);
+    for (size_t i = 0; i < nv; ++i) { vars[i] = (uint32_t)vs[i]; p_off[i + 1] = p_off[i] + hot[2 * vs[i]].n; n_off[i + 1] = n_off[i] + hot[2 * vs[i] + 1].n; }
+    blk.p0.resize(p_off[nv]); blk.n0.resize(n_off[nv]);
+    parallelFor(nv, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            const int w = vs[i];
+            memcpy(blk.p0.data() + p_off[i], occ_pool.data() + occ[2 * w].off, sizeof(uint32_t) * hot[2 * w].n);
+            memcpy(blk.n0.data() + n_off[i], occ_pool.data() + occ[2 * w + 1].off, sizeof(uint32_t) * hot[2 * w + 1].n);
+        }
+    }, 16384);
+    blk.p1 = blk.p0; blk.n1 = blk.n0; blk.pst.resize(blk.p0.size() + 1); blk.nst.resize(blk.n0.size() + 1);
+    std::vector<cp3g_bve_rec> recs(nv);
+    int64_t t0 = now_ns();
+    if (cp3g_bve_eval(gpu, (uint32_t)nv, vars.data(), p_off.data(), blk.p1.data(), n_off.data(), blk.n1.data(), opt.bve_gates ? 1 : 0,
+                      recs.data(), blk.pst.data(), blk.nst.data()) != CP3G_OK) { die("bve_eval failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    // resolvent streams for the likely eliminations.  The global growth allowance (bve_cgrow_t - totallyAdded, BVE.cc:532-540) is
+    // shared by ALL later eliminations: only a small part of it is granted per variable here; the few clause-increasing
+    // eliminations beyond that fetch their resolvents through the pair-matrix path.
+    int slack = opt.bve_cgrow;
+    if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { slack += std::min(8, std::max(0, opt.bve_cgrow_t - bve_totallyAdded)); }
+    std::vector<uint32_t> sel; std::vector<uint64_t> res_off{0}, lit_off{0};
+    for (size_t i = 0; i < nv; ++i) {
+        const cp3g_bve_rec& r = recs[i];
+        if ((r.flags & CP3G_BVE_HOST) || r.resolvents == 0 || opt.bve_BCElim) { continue; }
+        if ((int64_t)r.resolvents > (int64_t)r.pos_n + r.neg_n + slack || lit_off.back() > (64u << 20)) { continue; }
+        sel.push_back((uint32_t)i); res_off.push_back(res_off.back() + r.resolvents); lit_off.push_back(lit_off.back() + r.lit_clauses);
+    }
+    blk.rsz.resize(res_off.back() + 1); blk.rlits.resize(lit_off.back() + 1);
+    if (!sel.empty()) {
+        ++n_resolve_batches;
+        int64_t t1 = now_ns();
+        if (cp3g_bve_stream(gpu, (uint32_t)sel.size(), sel.data(), res_off.data(), lit_off.data(), blk.rsz.data(), blk.rlits.data()) != CP3G_OK) { die("bve_stream failed"); }
+        host_ns_gpuwait += now_ns() - t1;
+    }
+    size_t si = 0;
+    for (size_t i = 0; i < nv; ++i) {
+        const int w = vs[i];
+        if (ev_slot[w] < 0) { ev_slot[w] = (int32_t)ev_ent.size(); ev_ent.emplace_back(); }
+        EvalEnt& q = ev_ent[(size_t)ev_slot[w]];
+        q.touch = var_touch[w]; q.valid = true; q.rec = recs[i];
+        q.pos0 = {blk.p0.data() + p_off[i], (size_t)(p_off[i + 1] - p_off[i])}; q.neg0 = {blk.n0.data() + n_off[i], (size_t)(n_off[i + 1] - n_off[i])};
+        q.pos1 = {blk.p1.data() + p_off[i], (size_t)recs[i].pos_n}; q.neg1 = {blk.n1.data() + n_off[i], (size_t)recs[i].neg_n};
+        q.pst = {blk.pst.data() + p_off[i], (size_t)recs[i].pos_n}; q.nst = {blk.nst.data() + n_off[i], (size_t)recs[i].neg_n};
+        q.has_stream = si < sel.size() && sel[si] == (uint32_t)i;
+        if (q.has_stream) {
+            q.rsz = {blk.rsz.data() + res_off[si], (size_t)(res_off[si + 1] - res_off[si])};
+            q.rlits = {blk.rlits.data() + lit_off[si], (size_t)(lit_off[si + 1] - lit_off[si])};
+            ++si;
+        } else { q.rsz = {}; q.rlits = {}; }
+    }
+    return fresh(v);
 }
 
 template <class A> static inline int indexOf(const A& a, uint32_t x)
@@ -2229,34 +2318,154 @@ int Engine::resolveSet(int v, int p_limit, int n_limit)
     return L_UNDEF;
 }
 
+// One step of the staged prefetcher (engine.h).  Candidates = the variables in the first levels of the heap.
+void Engine::bvePrefetchStep()
+{
+    // retire finished / stale entries, advance the others by one dependency level
+    int keep = 0;
+    for (int i = 0; i < bve_pf_n; ++i) {
+        BvePf e = bve_pf[i];
+        const int v = e.var;
+        if (!inHeap(v)) { continue; }
+        switch (e.stage) {
+        case 0:                                                   // counters arrived: list descriptors, K5 record slot
+            {   // a variable the cut-off (BVE.cc:418-420) will skip needs nothing else
+                const bool cutoff = (hot[2 * v + 1].cnt > 10 && hot[2 * v].cnt > 10) || (dcount(v) > 15 && (hot[2 * v + 1].cnt > 5 || hot[2 * v].cnt > 5));
+                if ((cutoff && !opt.bve_unlimited && !opt.bve_force_gates && !opt.bve_gates) || assigns[v] != L_UNDEF || frozen[v]) { e.stage = 4; break; }
+                if (cutoff && !opt.bve_unlimited && !opt.bve_force_gates && (hot[2 * v].n > 24 || hot[2 * v + 1].n > 24)) { e.stage = 4; break; }
+            }
+            __builtin_prefetch(&occ[2 * v]);
+            if ((size_t)v < pc_slot.size()) { __builtin_prefetch(&pc_slot[v]); }
+            __builtin_prefetch(&var_touch[v]);
+            break;
+        case 1: {                                                 // descriptors arrived: the lists themselves, the record
+            if (hot[2 * v].n) { __builtin_prefetch(&occ_pool[occ[2 * v].off]); }
+            if (hot[2 * v + 1].n) { __builtin_prefetch(&occ_pool[occ[2 * v + 1].off]); }
+            if ((size_t)v < pc_slot.size() && pc_slot[v] >= 0) { __builtin_prefetch(&pc_ent[(size_t)pc_slot[v]]); }
+            break; }
+        case 2: {                                                 // lists arrived: clause headers; record arrived: its matrix
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint32_t n = std::min<uint32_t>(hot[2 * v + s2].n, 12); const uint32_t* lp = occ_pool.data() + occ[2 * v + s2].off;
+                for (uint32_t k = 0; k < n; ++k) { if (lp[k] < C.size()) { __builtin_prefetch(&C[lp[k]]); } }
+            }
+            if ((size_t)v < pc_slot.size() && pc_slot[v] >= 0) {
+                const PairEnt& pe = pc_ent[(size_t)pc_slot[v]];
+                if (pe.valid) { __builtin_prefetch(pe.sizes.p); __builtin_prefetch(pe.pos.p); __builtin_prefetch(pe.neg.p); }
+            }
+            break; }
+        case 3: {                                                 // headers arrived: literals of the short clauses (gate detection reads them)
+            for (int s2 = 0; s2 < 2; ++s2) {
+                const uint32_t n = std::min<uint32_t>(hot[2 * v + s2].n, 12); const uint32_t* lp = occ_pool.data() + occ[2 * v + s2].off;
+                for (uint32_t k = 0; k < n; ++k) { if (lp[k] < C.size() && C[lp[k]].size <= 4) { __builtin_prefetch(&pool[C[lp[k]].start]); } }
+            }
+            break; }
+        default: break;
+        }
+        if (e.stage < 4) { ++e.stage; }
+        bve_pf[keep++] = e;
+    }
+    bve_pf_n = keep;
+    // the percolation of the next pops compares the counters of the first levels
+    { const int lv = (int)std::min<size_t>(heap.size(), 31); for (int i = 7; i < lv; ++i) { __builtin_prefetch(&hot[2 * heap[(size_t)i]]); } }
+    // new candidates: the variables that can become the root within the next two or three pops
+    const int top = (int)std::min<size_t>(heap.size(), 7);
+    for (int i = 0; i < top && bve_pf_n < 16; ++i) {
+        const int v = heap[(size_t)i];
+        bool have = false;
+        for (int k = 0; k < bve_pf_n; ++k) { if (bve_pf[k].var == v) { have = true; break; } }
+        if (have) { continue; }
+        __builtin_prefetch(&hot[2 * v]); __builtin_prefetch(&assigns[v]); __builtin_prefetch(&frozen[v]);
+        bve_pf[bve_pf_n++] = {v, 0};
+    }
+}
+
 // bve_worker, BVE.cc:388-637
 void Engine::bveWorker()
 {
     const bool unlimited = !opt.limited;
-    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr;
+    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr || getenv("CP3_DEBUG_BVE") != nullptr;
     int64_t tg = 0, tc = 0, ta = 0, tr = 0, trm = 0, ts = 0, tl = dbg ? now_ns() : 0;
     auto lapt = [&](int64_t& acc) { if (dbg) { const int64_t n2 = now_ns(); acc += n2 - tl; tl = n2; } };
     struct Rep { bool on; int64_t &tg, &tc, &ta, &tr, &trm, &ts; ~Rep() { if (on) { fprintf(stderr, "  bveWorker: heap+gates %.1f ms, clean %.1f, anticipate %.1f, resolveSet %.1f, removeClauses %.1f, inner subsumption %.1f\n", tg / 1e6, tc / 1e6, ta / 1e6, tr / 1e6, trm / 1e6, ts / 1e6); } } } rep{dbg, tg, tc, ta, tr, trm, ts};
+    static const bool no_eval = getenv("CP3_NO_BVE_EVAL") != nullptr;
+    const bool use_eval = !no_eval && !opt.bve_early && !sharded;       // (-bve_early makes the anticipation depend on the global growth budget)
+    pairs_single = use_eval;
+    struct InWorker { bool& f; explicit InWorker(bool& x) : f(x) { f = true; } ~InWorker() { f = false; } } in_worker(in_bve_worker);
+    static const bool no_pf = getenv("CP3_NO_BVE_PREFETCH") != nullptr;
+    bve_pf_n = 0;
+    size_t skip_run = 0, skip_check_at = 1024;
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
+        if (!no_pf) { bvePrefetchStep(); }
         const int v = heapRemoveMin();
         if (assigns[v] != L_UNDEF) { continue; }
         if (hot[2 * v].n == 0 && hot[2 * v + 1].n == 0) { continue; }
         if (frozen[v]) { continue; }
         const bool cutoff = (hot[2 * v + 1].cnt > 10 && hot[2 * v].cnt > 10) || (dcount(v) > 15 && (hot[2 * v + 1].cnt > 5 || hot[2 * v].cnt > 5));
-        if (!opt.bve_force_gates && !opt.bve_unlimited && cutoff) { ++bve_skippedVars; continue; }
+        if (!opt.bve_force_gates && !opt.bve_unlimited && cutoff) {
+            ++bve_skippedVars;
+            // The heap hands out the variables with few occurrences first; behind them come millions that the cut-off
+            // (BVE.cc:418-420) skips one by one - pops without any effect but this counter.  After a run of skips, check the
+            // whole rest of the heap at once (all cores): if every variable left would be skipped or passed over, count them
+            // and empty the heap - the same final state as popping them.
+            if (++skip_run >= skip_check_at && heap.size() > 4096) {
+                std::vector<int64_t> nsk((size_t)nthreads + 1, 0); bool all = true;
+                parallelFor(heap.size(), [&](size_t b, size_t e, int t) {
+                    int64_t c = 0; bool good = true;
+                    for (size_t i = b; i < e && good; ++i) {
+                        const int w = heap[i];
+                        if (assigns[w] != L_UNDEF || (hot[2 * w].n == 0 && hot[2 * w + 1].n == 0) || frozen[w]) { continue; }
+                        const bool co = (hot[2 * w + 1].cnt > 10 && hot[2 * w].cnt > 10) || (dcount(w) > 15 && (hot[2 * w + 1].cnt > 5 || hot[2 * w].cnt > 5));
+                        if (co) { ++c; } else { good = false; }
+                    }
+                    nsk[(size_t)t] = c; if (!good) { all = false; }
+                }, 65536);
+                if (all) { for (int64_t c : nsk) { bve_skippedVars += (int)c; } heapClear(); break; }
+                skip_check_at = skip_run * 2;                        // not yet: try again after twice as many skips
+            }
+            continue;
+        }
         int p_limit = (int)hot[2 * v].n, n_limit = (int)hot[2 * v + 1].n;
         bool foundGate = false;
-        if (opt.bve_gates) { foundGate = findGates(v, p_limit, n_limit); if (foundGate) { bve_foundGates++; } }
+        // The device evaluated gates, cleaning and anticipation of this variable on its lists as they were at batch time
+        // (K5', bve_eval.cu); the record stands while no clause of v changed (touch counter) and the two lists are still the
+        // very same sequences (a lazy cleaning by somebody else's walk reorders a list without touching the variable).
+        EvalEnt* ee = use_eval ? evalFor(v) : nullptr;
+        if (ee != nullptr) {
+            const bool same = !(ee->rec.flags & CP3G_BVE_HOST) && ee->pos0.n == hot[2 * v].n && ee->neg0.n == hot[2 * v + 1].n &&
+                              !memcmp(ee->pos0.p, occ_pool.data() + occ[2 * v].off, sizeof(uint32_t) * ee->pos0.n) &&
+                              !memcmp(ee->neg0.p, occ_pool.data() + occ[2 * v + 1].off, sizeof(uint32_t) * ee->neg0.n);
+            if (!same) { if (ee->rec.flags & CP3G_BVE_HOST) { ++n_eval_host; } else { ++n_eval_stale; } ee = nullptr; }
+        }
+        if (ee != nullptr) {
+            foundGate = (ee->rec.flags & CP3G_BVE_GATE) != 0; p_limit = ee->rec.p_limit; n_limit = ee->rec.n_limit;
+            if (foundGate) { bve_foundGates++; }
+        } else if (opt.bve_gates) { foundGate = findGates(v, p_limit, n_limit); if (foundGate) { bve_foundGates++; } }
         if (!foundGate && opt.bve_fdepOnly) { continue; }
         if (!opt.bve_unlimited && !foundGate && cutoff) { ++bve_skippedVars; continue; }
         ++bve_testedVars;
         lapt(tg);
         int pos_count = 0, neg_count = 0;
-        for (int s = 0; s < 2; ++s) {
-            ListRef li = L(2 * v + s);
-            for (uint32_t i = 0; i < li.n; ++i) {
-                if (C[LP(li)[i]].flag & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
-                if (s == 0) { ++pos_count; } else { ++neg_count; }
+        if (ee != nullptr) {
+            // the lists in their reordered + cleaned form; every entry that left was a deleted clause
+            for (int s = 0; s < 2; ++s) {
+                const int x = 2 * v + s; const Span<uint32_t>& nl = s == 0 ? ee->pos1 : ee->neg1;
+                const uint32_t removed = hot[x].n - (uint32_t)nl.n;
+                memcpy(occ_pool.data() + occ[x].off, nl.p, sizeof(uint32_t) * nl.n);
+                hot[x].n = (uint32_t)nl.n;
+                if (removed) { if (stale[x] > removed) { stale[x] -= removed; } else { staleClear(x); } }
+            }
+            pos_count = (int)ee->pos1.n; neg_count = (int)ee->neg1.n;
+            // evaluating the lists in this form again gives the same record (the gate clauses are in front already, nothing is left to
+            // clean): it stays valid for the next time v comes out of the heap untouched
+            ee->pos0 = ee->pos1; ee->neg0 = ee->neg1;
+            ++n_eval_used;
+        } else {
+            for (int s = 0; s < 2; ++s) {
+                ListRef li = L(2 * v + s);
+                for (uint32_t i = 0; i < li.n; ++i) {
+                    if (C[LP(li)[i]].flag & F_DEL) { occSwapRemove(2 * v + s, i); --i; continue; }
+                    if (s == 0) { ++pos_count; } else { ++neg_count; }
+                }
             }
         }
         if (pos_stats.size() < hot[2 * v].n) { pos_stats.resize(hot[2 * v].n, 0); }
@@ -2266,8 +2475,13 @@ void Engine::bveWorker()
         lapt(tc);
         if (pos_count != 0 && neg_count != 0) {
             ++bve_anticipations;
-            ares = anticipate(v, p_limit, n_limit, lit_clauses, resolvents);
-            if (ares == L_FALSE) { return; }
+            if (ee != nullptr) {
+                bve_steps += ee->rec.steps; lit_clauses = (int)ee->rec.lit_clauses; resolvents = (int)ee->rec.resolvents;
+                if (opt.bve_BCElim) { for (size_t k = 0; k < ee->pst.n; ++k) { pos_stats[k] = ee->pst[k]; } for (size_t k = 0; k < ee->nst.n; ++k) { neg_stats[k] = ee->nst[k]; } }
+            } else {
+                ares = anticipate(v, p_limit, n_limit, lit_clauses, resolvents);
+                if (ares == L_FALSE) { return; }
+            }
         }
         if (ares == L_UNDEF && opt.bve_BCElim) {
             bveRemoveBlocked(2 * v, pos_stats);
@@ -2284,7 +2498,22 @@ void Engine::bveWorker()
             else if (resolvents > pos_count + neg_count) { bve_nInc++; }
             else { bve_nKeep++; }
             lapt(tg);
-            if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; }
+            if (ee != nullptr && ee->has_stream && !opt.bve_BCElim) {
+                // resolveSet (BVE.cc:892-1046) from the K6' stream: the resolvents in the reference's order, nothing to look up
+                const bool useHeap = opt.bve_heap_updates > 0;
+                bve_steps += ee->rec.steps;
+                const int32_t* rl = ee->rlits.p;
+                for (size_t k = 0; k < ee->rsz.n; ++k) {
+                    const int sz = ee->rsz[k];
+                    const uint32_t cr = allocClause(rl, sz);
+                    dataAddClause(cr, useHeap);
+                    clauses.push_back(cr);
+                    subInitClause(cr);
+                    ++bve_createdClauses; bve_createdLiterals += sz;
+                    rl += sz;
+                }
+                ++n_stream_used;
+            } else if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; }
             lapt(tr);
             ++bve_eliminatedVars;
             bveRemoveClauses(2 * v, -1);
@@ -2318,31 +2547,92 @@ void Engine::addClausesToSubsumption(int x)
     }
 }
 
+// addClausesToSubsumption (BVE.cc:1129-1141) over both lists of every touched variable, in order: a live clause that is not in
+// the subsumption queue yet is queued (both queues) where the walk meets it FIRST.  For many touched variables the first
+// occurrences are found on all cores: every list entry has a rank in the sequential walk, the smallest rank per clause wins.
+void Engine::addTouchedToSubsumption()
+{
+    const size_t nt = touched.size();
+    std::vector<uint64_t> off(2 * nt + 1, 0);
+    for (size_t i = 0; i < nt; ++i) { off[2 * i + 1] = off[2 * i] + hot[2 * touched[i]].n; off[2 * i + 2] = off[2 * i + 1] + hot[2 * touched[i] + 1].n; }
+    const uint64_t total = off[2 * nt];
+    static const uint64_t par_min = getenv("CP3_TOUCHED_MIN") ? (uint64_t)atoll(getenv("CP3_TOUCHED_MIN")) : 262144;
+    if (total < par_min || total >= 0xffffffffull || nthreads < 2) {
+        for (int v : touched) { addClausesToSubsumption(2 * v); addClausesToSubsumption(2 * v + 1); }
+        return;
+    }
+    pgrow(first_rank, C.size() + 1024, 0xffffffffu);
+    auto forEntries = [&](size_t b, size_t e, auto&& f) {              // lists b..e-1 of the walk (list 2i = positive list of touched[i])
+        for (size_t li = b; li < e; ++li) {
+            const int x = 2 * touched[li >> 1] + (int)(li & 1);
+            const uint32_t* p = occ_pool.data() + occ[x].off; const uint32_t n = hot[x].n;
+            for (uint32_t j = 0; j < n; ++j) { f(p[j], (uint32_t)(off[li] + j)); }
+        }
+    };
+    parallelFor(2 * nt, [&](size_t b, size_t e, int) {
+        forEntries(b, e, [&](uint32_t d, uint32_t r) {
+            if ((C[d].flag & F_DEL) || (C[d].flag & F_SUB)) { return; }
+            uint32_t o = __atomic_load_n(&first_rank[d], __ATOMIC_RELAXED);
+            while (r < o && !__atomic_compare_exchange_n(&first_rank[d], &o, r, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+        });
+    }, 4096);
+    std::vector<size_t> cnt((size_t)nthreads + 2, 0);
+    parallelFor(2 * nt, [&](size_t b, size_t e, int t) {
+        size_t c = 0;
+        forEntries(b, e, [&](uint32_t d, uint32_t r) { c += first_rank[d] == r ? 1 : 0; });
+        cnt[(size_t)t + 1] = c;
+    });
+    for (size_t t = 1; t < cnt.size(); ++t) { cnt[t] += cnt[t - 1]; }
+    const size_t s0 = subq.size(), q0 = strq.size(), add = cnt.back();
+    subq.resize(s0 + add); strq.resize(q0 + add);
+    parallelFor(2 * nt, [&](size_t b, size_t e, int t) {
+        size_t o = cnt[(size_t)t];
+        forEntries(b, e, [&](uint32_t d, uint32_t r) { if (first_rank[d] == r) { subq[s0 + o] = d; strq[q0 + o] = d; ++o; } });
+    });
+    parallelFor(add, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { const uint32_t d = subq[s0 + i]; C[d].flag |= F_SUB | F_STR; first_rank[d] = 0xffffffffu; } });
+}
+
 // sequentiellBVE, BVE.cc:316-381
 void Engine::sequentiellBVE()
 {
     const bool unlimited = !opt.limited;
+    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr || getenv("CP3_DEBUG_BVE") != nullptr;
+    int64_t tl = dbg ? now_ns() : 0;
+    auto lapb = [&](const char* w) { if (dbg) { const int64_t n2 = now_ns(); fprintf(stderr, "  seqBVE %s %.1f ms\n", w, (n2 - tl) / 1e6); tl = n2; } };
     subsumptionProcess(opt.bve_strength, false, VAR_UNDEF);
     t_bve.modified = t_bve.modified || t_sub.modified;
     if (!ok) { return; }
+    lapb("first subsumption");
     touched.clear();
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
         bve_modtime = nextModStep();
         for (int w : heap) { if (!bve_inpend[w]) { bve_inpend[w] = 1; bve_pending.push_back(w); } }
+        lapb("pending");
         bveWorker();
+        lapb("worker");
         if (!ok) { return; }
         if (hasToPropagate()) {
             if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { return; }
             t_bve.modified = t_bve.modified || t_up.modified;
         }
         checkGarbage();
-        for (int v = 0; v < nvars; ++v) { if (modTimer[v] >= bve_modtime) { touched.push_back(v); } }
-        for (int v : touched) { addClausesToSubsumption(2 * v); addClausesToSubsumption(2 * v + 1); }
+        lapb("propagate+gc");
+        {   // getActiveVariables (CoprocessorTypes.h:1169-1187): stable parallel filter over the variables
+            std::vector<size_t> cntv((size_t)nthreads + 2, 0);
+            parallelFor((size_t)nvars, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t v = b; v < e; ++v) { c += modTimer[v] >= bve_modtime ? 1 : 0; } cntv[(size_t)t + 1] = c; });
+            for (size_t t = 1; t < cntv.size(); ++t) { cntv[t] += cntv[t - 1]; }
+            touched.resize(cntv.back());
+            parallelFor((size_t)nvars, [&](size_t b, size_t e, int t) { size_t o = cntv[(size_t)t]; for (size_t v = b; v < e; ++v) { if (modTimer[v] >= bve_modtime) { touched[o++] = (int)v; } } });
+        }
+        addTouchedToSubsumption();
+        lapb("touched");
         subsumptionProcess(opt.bve_strength, false, VAR_UNDEF);
         t_bve.modified = t_bve.modified || t_sub.modified;
+        lapb("subsumption");
         heapClear();
         for (int v : touched) { heapInsert(v); }
         touched.clear();
+        lapb("heap");
     }
 }
 
@@ -2356,6 +2646,7 @@ int Engine::bveProcess()
     const bool propagatedSomething = t_up.modified;
     sequentiellBVE();
     pair_blocks.clear(); pc_ent.clear(); std::fill(pc_slot.begin(), pc_slot.end(), -1);
+    eval_blocks.clear(); ev_ent.clear(); std::fill(ev_slot.begin(), ev_slot.end(), -1);
     if (!t_bve.modified) { unsuccessful(t_bve); }
     if (t_bve.modified || propagatedSomething) { successful(t_bve); }
     return ok ? L_UNDEF : L_FALSE;
@@ -2622,6 +2913,7 @@ int64_t Engine::stat(const char* s) const
     ST("up_removedClauses", up_removedClauses) ST("up_removedLiterals", up_removedLiterals)
     ST("bve_foundGates", bve_foundGates)
     ST("scan_batches", n_scan_batches) ST("scan_ondemand", n_ondemand) ST("queue_fast", n_fast) ST("queue_slow", n_slow)
+    ST("eval_batches", n_eval_batches) ST("eval_used", n_eval_used) ST("eval_host", n_eval_host) ST("eval_stale", n_eval_stale) ST("stream_used", n_stream_used)
     ST("pair_batches", n_pair_batches) ST("resolve_batches", n_resolve_batches) ST("arena_compactions", n_compactions)
     ST("bulk_ingests", n_bulk_ingests) ST("queue_target_fast", n_tfast)
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)

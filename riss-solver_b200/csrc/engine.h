@@ -233,6 +233,17 @@ private:
     std::vector<int32_t> pc_slot; std::vector<PairEnt> pc_ent;
     inline PairEnt* pairLookup(int v) { return (v < (int)pc_slot.size() && pc_slot[v] >= 0) ? &pc_ent[pc_slot[v]] : nullptr; }
     std::vector<int> scratch_col;
+    // K5'/K6' results per variable (cp3g_bve_eval / cp3g_bve_stream): the whole bve_worker evaluation of a variable on the
+    // lists as they were at batch time.  Valid while the touch counter and the two lists themselves are unchanged.
+    struct EvalEnt { uint32_t touch = 0; bool valid = false, has_stream = false; cp3g_bve_rec rec;
+                     Span<uint32_t> pos0, neg0, pos1, neg1; Span<uint16_t> pst, nst, rsz; Span<int32_t> rlits; };
+    struct EvalBlock { std::vector<uint32_t> p0, n0, p1, n1; std::vector<uint16_t> pst, nst, rsz; std::vector<int32_t> rlits; };
+    std::vector<std::unique_ptr<EvalBlock>> eval_blocks; std::vector<int32_t> ev_slot; std::vector<EvalEnt> ev_ent;
+    EvalEnt* evalFor(int v);                            // cached record of v, or one more batch (v + the waiting heap variables)
+    bool in_bve_worker = false;
+    bool sharded = false;                               // scan service split over several ranks (CPsetDistributed)
+    bool pairs_single = false;                          // the pair-matrix path serves single variables only (fallback of the evaluation)
+    int64_t n_eval_batches = 0, n_eval_used = 0, n_eval_host = 0, n_eval_stale = 0, n_stream_used = 0;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
     int64_t host_ns_commit = 0, host_ns_gpuwait = 0, dbg_slow_ns = 0, dbg_hits_ns = 0;
     int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0, ph_upload = 0, ph_download = 0, ph_simplify = 0;
@@ -313,10 +324,18 @@ private:
     void bveRemoveBlocked(int x, const std::vector<int>& stats);
     int resolveSet(int v, int p_limit, int n_limit);
     void bveWorker();
+    // The BVE commit is bound by cache misses of the host mirror (one variable = its counters, two lists, the headers of
+    // their clauses, the K5 record - some 25 dependent lines at 10 M variables).  The next variables are the ones near the
+    // top of the heap: a small staged prefetcher walks them one dependency level per loop iteration.  Side-effect free.
+    struct BvePf { int var; int stage; };
+    BvePf bve_pf[16]; int bve_pf_n = 0;
+    void bvePrefetchStep();
     void sequentiellBVE();
     int bveProcess();
     uint32_t nextModStep();
     void addClausesToSubsumption(int x);
+    void addTouchedToSubsumption();
+    RawVec<uint32_t> first_rank;                     // per clause: rank of its first occurrence in the walk over the touched lists
 
     // device interaction
     void ensureGpu();

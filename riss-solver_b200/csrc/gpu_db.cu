@@ -1227,6 +1227,7 @@ void cp3g_destroy(cp3g* g)
     g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
     g->bs0.release(g->stream); g->bl0.release(g->stream);
     g->sp_da.release(g->stream); g->sp_db.release(g->stream); g->sp_chosen.release(g->stream); g->sp_dltime.release(g->stream); g->sp_dlcnt.release(g->stream); g->sp_dloff.release(g->stream);
+    g->ev_recs.release(g->stream); g->ev_pst.release(g->stream); g->ev_nst.release(g->stream); g->ev_rsz.release(g->stream); g->ev_loff.release(g->stream);
     g->sp_dlfill.release(g->stream); g->sp_n.release(g->stream); g->sp_stale.release(g->stream); g->sp_dead.release(g->stream); g->sp_refs.release(g->stream);
     cudaStreamSynchronize(g->stream);
     cp3g_nccl_free(g->nccl);
@@ -1903,6 +1904,7 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "scan_checks")) { return g->scan_checks; }
     if (!strcmp(name, "scan_ns")) { return g->scan_ns; }
     if (!strcmp(name, "commit_ns")) { return g->commit_ns; }
+    if (!strcmp(name, "bve_ns")) { return g->bve_ns; }
     if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }
     if (!strcmp(name, "nlits")) { return (int64_t)g->nlits; }

@@ -16,6 +16,8 @@ struct cp3g {
     std::vector<std::vector<uint32_t>> occ;
     int64_t launches = 0, requests = 0, checks = 0;
     // result of the last cp3g_sub_pass
+    // last cp3g_bve_eval batch (cp3g_bve_stream reads it)
+    std::vector<uint32_t> ev_vars, ev_poff, ev_prefs, ev_noff, ev_nrefs; std::vector<cp3g_bve_rec> ev_recs;
     bool sp_valid = false; std::vector<uint32_t> sp_dead, sp_n, sp_stale; std::vector<std::vector<uint32_t>> sp_lists;
     std::string err;
 };
@@ -225,6 +227,100 @@ int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint3
     for (uint32_t t = 0; t < npairs; ++t) {
         std::vector<int32_t> r; res_size(g->cl[p_refs[t]], g->cl[n_refs[t]], (int32_t)(vars[t] << 1), &r);
         for (size_t k = 0; k < r.size() && out_off[t] + k < out_off[t + 1]; ++k) { out_lits[out_off[t] + k] = r[k]; }
+    }
+    return CP3G_OK;
+}
+// K5' mocked by the plain per-variable sequence of bve_worker: findGates (BVE.cc:1143-1267) on the lists as given, lazy removal
+// of deleted entries (BVE.cc:474-489), anticipateElimination (BVE.cc:695-880)
+static bool mock_find_gates(cp3g* g, int v, std::vector<uint32_t>& pos, std::vector<uint32_t>& neg, int& p_limit, int& n_limit)
+{
+    if (pos.size() < 3 && neg.size() < 3) { return false; }
+    if (pos.size() < 2 || neg.size() < 2) { return false; }
+    for (int pn = 0; pn < 2; ++pn) {
+        const int32_t pLit = 2 * v + (pn != 0), nLit = 2 * v + (pn == 0);
+        std::vector<uint32_t>& pList = pn == 0 ? pos : neg; std::vector<uint32_t>& nList = pn == 0 ? neg : pos;
+        int& pClauses = pn == 0 ? p_limit : n_limit; int& nClauses = pn == 0 ? n_limit : p_limit;
+        std::vector<int32_t> marks;
+        auto marked = [&](int32_t x) { return std::find(marks.begin(), marks.end(), x) != marks.end(); };
+        for (uint32_t c : pList) {
+            if (g->del[c] || g->cl[c].size() != 2) { continue; }
+            const int32_t other = g->cl[c][0] == pLit ? g->cl[c][1] : g->cl[c][0];
+            if (!marked(other ^ 1)) { marks.push_back(other ^ 1); }
+        }
+        for (size_t i = 0; i < nList.size(); ++i) {
+            const uint32_t c = nList[i];
+            if (g->del[c]) { continue; }
+            size_t j = 0;
+            for (; j < g->cl[c].size(); ++j) { if (g->cl[c][j] == nLit) { continue; } if (!marked(g->cl[c][j])) { break; } }
+            if (j == g->cl[c].size()) {
+                pClauses = (int)g->cl[c].size() - 1; nClauses = 1;
+                for (int32_t x : g->cl[c]) { marks.erase(std::remove(marks.begin(), marks.end(), x), marks.end()); }
+                std::swap(nList[0], nList[i]);
+                size_t placed = 0;
+                for (size_t k = 0; k < pList.size(); ++k) {
+                    const uint32_t c2 = pList[k];
+                    if (g->del[c2] || g->cl[c2].size() != 2) { continue; }
+                    const int32_t other = g->cl[c2][0] == pLit ? g->cl[c2][1] : g->cl[c2][0];
+                    if (!marked(other ^ 1)) { std::swap(pList[placed], pList[k]); placed++; marks.push_back(other ^ 1); }
+                }
+                return true;
+            }
+        }
+    }
+    return false;
+}
+int cp3g_bve_eval(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, uint32_t* p_refs, const uint32_t* n_off, uint32_t* n_refs,
+                  int use_gates, cp3g_bve_rec* recs, uint16_t* p_stats, uint16_t* n_stats)
+{
+    g->launches++;
+    for (uint32_t i = 0; i < nv; ++i) {
+        std::vector<uint32_t> pos(p_refs + p_off[i], p_refs + p_off[i + 1]), neg(n_refs + n_off[i], n_refs + n_off[i + 1]);
+        cp3g_bve_rec r; r.p_limit = (int)pos.size(); r.n_limit = (int)neg.size(); r.resolvents = r.lit_clauses = r.steps = r.flags = 0;
+        r.pos_n = (uint32_t)pos.size(); r.neg_n = (uint32_t)neg.size();
+        if (pos.size() > 64 || neg.size() > 64) { r.flags = CP3G_BVE_HOST; recs[i] = r; continue; }      // the kernel's list capacity
+        int p_limit = r.p_limit, n_limit = r.n_limit;
+        const bool found = use_gates && mock_find_gates(g, (int)vars[i], pos, neg, p_limit, n_limit);
+        for (size_t k = 0; k < pos.size(); ++k) { if (g->del[pos[k]]) { pos[k] = pos.back(); pos.pop_back(); --k; } }
+        for (size_t k = 0; k < neg.size(); ++k) { if (g->del[neg[k]]) { neg[k] = neg.back(); neg.pop_back(); --k; } }
+        const bool hasDef = p_limit < (int)pos.size() || n_limit < (int)neg.size();
+        std::vector<uint16_t> ps(pos.size(), 0), ns(neg.size(), 0); bool special = false;
+        for (size_t a = 0; a < pos.size(); ++a) for (size_t b = 0; b < neg.size(); ++b) {
+            if ((int)a >= p_limit && (int)b >= n_limit) { continue; }
+            if (hasDef && (int)a < p_limit && (int)b < n_limit) { continue; }
+            ++r.steps;
+            const int sz = res_size(g->cl[pos[a]], g->cl[neg[b]], (int32_t)(vars[i] << 1), nullptr);
+            if (sz > 1) { ++r.resolvents; r.lit_clauses += (uint32_t)sz; ++ps[a]; ++ns[b]; }
+            else if (sz == 0 || sz == 1) { special = true; }
+        }
+        r.p_limit = p_limit; r.n_limit = n_limit; r.pos_n = (uint32_t)pos.size(); r.neg_n = (uint32_t)neg.size();
+        r.flags = (found ? CP3G_BVE_GATE : 0u) | (special ? CP3G_BVE_HOST : 0u);
+        recs[i] = r;
+        std::copy(pos.begin(), pos.end(), p_refs + p_off[i]); std::copy(neg.begin(), neg.end(), n_refs + n_off[i]);
+        if (p_stats) { std::copy(ps.begin(), ps.end(), p_stats + p_off[i]); }
+        if (n_stats) { std::copy(ns.begin(), ns.end(), n_stats + n_off[i]); }
+    }
+    g->ev_vars.assign(vars, vars + nv); g->ev_poff.assign(p_off, p_off + nv + 1); g->ev_noff.assign(n_off, n_off + nv + 1);
+    g->ev_prefs.assign(p_refs, p_refs + p_off[nv]); g->ev_nrefs.assign(n_refs, n_refs + n_off[nv]); g->ev_recs.assign(recs, recs + nv);
+    return CP3G_OK;
+}
+int cp3g_bve_stream(cp3g* g, uint32_t nsel, const uint32_t* sel, const uint64_t* res_off, const uint64_t* lit_off, uint16_t* out_sizes, int32_t* out_lits)
+{
+    g->launches++;
+    for (uint32_t k = 0; k < nsel; ++k) {
+        const uint32_t i = sel[k]; const cp3g_bve_rec& r = g->ev_recs[i];
+        const uint32_t* pos = g->ev_prefs.data() + g->ev_poff[i]; const uint32_t* neg = g->ev_nrefs.data() + g->ev_noff[i];
+        const bool hasDef = r.p_limit < (int)r.pos_n || r.n_limit < (int)r.neg_n;
+        uint64_t ro = res_off[k], lo = lit_off[k];
+        for (uint32_t a = 0; a < r.pos_n; ++a) for (uint32_t b = 0; b < r.neg_n; ++b) {
+            if ((int)a >= r.p_limit && (int)b >= r.n_limit) { continue; }
+            if (hasDef && (int)a < r.p_limit && (int)b < r.n_limit) { continue; }
+            std::vector<int32_t> out;
+            const int sz = res_size(g->cl[pos[a]], g->cl[neg[b]], (int32_t)(g->ev_vars[i] << 1), &out);
+            if (sz <= 0) { continue; }
+            if (ro >= res_off[k + 1] || lo + out.size() > lit_off[k + 1]) { g->err = "stream overflow"; return CP3G_ERR_ARG; }
+            out_sizes[ro++] = (uint16_t)sz;
+            for (int32_t x : out) { out_lits[lo++] = x; }
+        }
     }
     return CP3G_OK;
 }

@@ -102,7 +102,7 @@ def test_freeze_blocks_elimination(mock):
     cp.close()
 
 
-FORCED = {"CP3_PARSUB_MIN": "0", "CP3_STATIC_MIN": "0", "CP3_BULK_MIN": "0", "CP3_THREADS": "3", "CP3_INGEST_MIN": "0"}
+FORCED = {"CP3_PARSUB_MIN": "0", "CP3_STATIC_MIN": "0", "CP3_BULK_MIN": "0", "CP3_THREADS": "3", "CP3_INGEST_MIN": "0", "CP3_TOUCHED_MIN": "0"}
 
 
 def test_forced_parallel_paths_fuzz(mock):
@@ -140,6 +140,6 @@ def test_literal_by_literal_clients_get_the_bulk_ingest(mock, gen):
         "assert outs[0][1] == 1 and outs[1][1] == 1, (outs[0][1], outs[1][1])\n"
         "assert outs[0][0] == outs[1][0] and outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]\n"
         "print('INGEST_OK')\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.dirname(os.path.abspath(__file__))), mock)
-    env = dict(os.environ, CP3_INGEST_MIN="0")
+    env = dict(os.environ, CP3_INGEST_MIN="0", CP3_TOUCHED_MIN="0")
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert p.returncode == 0 and "INGEST_OK" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

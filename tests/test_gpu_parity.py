@@ -351,6 +351,49 @@ def test_device_subsumption_commit_matches_the_ordered_walk(gen):
             assert np.array_equal(a["refs"][o:o + k], b["refs"][o:o + k]), x
 
 
+def test_bve_evaluation_kernels_match_the_per_variable_sequence(gen):
+    """K5'/K6' (bve_eval.cu: gate detection with list reordering, lazy cleaning, anticipation, resolvent streams) against the plain
+    per-variable sequence of bve_worker run on the CPU (tests/mock): records, rewritten list ORDER, per-clause statistics, and
+    the resolvent literals of every variable.  Lists are shuffled and a tenth of the clauses is deleted, so that the reordering
+    by gates and the swap-with-last cleaning are exercised."""
+    from fuzz_engine import build_mock
+    mock = build_mock()
+    rng = np.random.default_rng(99)
+    l2, s2 = gen.random_ksat(4000, 9000, 2, seed=31, planted=False)
+    l3, s3 = gen.community_ksat(4000, 14000, seed=32)
+    # planted AND gates x = a & b:  (-x a) (-x b) (x -a -b), plus two more clauses on x so that the lists are long enough
+    gl, gs = [], []
+    for x in range(4001, 4401):
+        a_, b_, c_, d_, e_, f_ = (rng.choice(4000, size=6, replace=False) + 1).tolist()
+        for cl in ([-x, a_], [-x, b_], [x, -a_, -b_], [x, c_, d_], [-x, e_, -f_]):
+            gl.extend(cl); gs.append(len(cl))
+    lits = np.concatenate([l2, l3, np.array(gl, np.int32)]); sizes = np.concatenate([s2, s3, np.array(gs, np.int32)])
+    lits, sizes = gen.permute_clauses(rng, lits, sizes)
+    n = int(np.abs(lits).max()); codes = _sorted_clauses(lits, sizes)
+    dele = np.flatnonzero(rng.random(sizes.size) < 0.1).astype(np.uint32)
+    res = []
+    for lib in (None, mock):
+        svc = rs.ScanService(lib_path=lib); svc.upload(n, codes, sizes); svc.build()
+        off, refs = svc.download_occ()
+        svc.set_deleted(dele)
+        r2 = np.random.default_rng(5)
+        pos = [r2.permutation(refs[off[2 * v]:off[2 * v + 1]]) for v in range(n)]
+        neg = [r2.permutation(refs[off[2 * v + 1]:off[2 * v + 2]]) for v in range(n)]
+        res.append(svc.bve_eval(np.arange(n, dtype=np.uint32), pos, neg, use_gates=True)); svc.close()
+    a, b = res
+    assert np.array_equal(a["recs"], b["recs"])
+    assert (a["recs"][:, 7] & 1).sum() > 20 and (a["recs"][:, 7] & 2).sum() > 0        # gates were found, some variables are left to the host
+    for i in range(n):
+        if a["recs"][i, 7] & 2:
+            continue
+        for side, key, st in (("p_off", "p_refs", "p_stats"), ("n_off", "n_refs", "n_stats")):
+            o = int(a[side][i]); k = int(a["recs"][i, 2 if side == "p_off" else 3])
+            assert np.array_equal(a[key][o:o + k], b[key][o:o + k]), (i, side)
+            assert np.array_equal(a[st][o:o + k], b[st][o:o + k]), (i, side)
+    assert np.array_equal(a["sel"], b["sel"]) and np.array_equal(a["rsz"], b["rsz"]) and np.array_equal(a["rlits"], b["rlits"])
+    assert a["rsz"].size > 1000
+
+
 def test_c2_full_size_ordered_against_the_reference(gen):
     """BASELINE configs[1] at full size (1M vars / 4.26M clauses + planted redundancy): ordered output stream, trail and every
     counter against the sequential reference (oracle/_ref/refshim, ~7 s) when it was built; else against the C oracle.
@@ -392,7 +435,7 @@ def test_forced_parallel_paths_on_gpu(gen):
         "    d = compare(run_gpu(stream, opts), run_oracle(stream, opts))\n"
         "    if d: bad += 1; print(r, opts, d[:3])\n"
         "print('BAD', bad)\n") % (ROOT, ROOT)
-    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3", CP3_INGEST_MIN="0")
+    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3", CP3_INGEST_MIN="0", CP3_TOUCHED_MIN="0")
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "BAD 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
