@@ -2045,14 +2045,31 @@ Engine::PairEnt& Engine::pairsFor(int v)
 // variables the decision rule (BVE.cc:532-548) will most likely eliminate the resolvents come along as a literal stream.
 Engine::EvalEnt* Engine::evalFor(int v)
 {
-    if (ev_slot.size() < (size_t)nvars) { ev_slot.resize((size_t)nvars, -1); }
-    auto fresh = [&](int w) -> EvalEnt* { const int32_t sl = ev_slot[w]; if (sl < 0) { return nullptr; } EvalEnt* e = &ev_ent[(size_t)sl]; return (e->valid && e->touch == var_touch[w]) ? e : nullptr; };
-    if (EvalEnt* e = fresh(v)) { return e; }
+    if (ev_ref.size() < (size_t)nvars) { const size_t o = ev_ref.size(); ev_ref.resize((size_t)nvars); parallelFor((size_t)nvars - o, [&](size_t b, size_t e, int) { for (size_t i = o + b; i < o + e; ++i) { ev_ref[i] = EvRef{-1, 0u, 0u, 0u}; } }); }
+    auto fresh = [&](int w) -> bool { const EvRef& r = ev_ref[(size_t)w]; return r.blk >= 0 && r.touch == var_touch[w]; };
+    auto view = [&](int w) -> EvalEnt* {
+        const EvRef& r = ev_ref[(size_t)w]; const EvalBlock& blk = *eval_blocks[(size_t)r.blk]; const size_t i = r.idx;
+        EvalEnt& q = ev_view; q.rec = blk.recs[i];
+        const uint32_t* p1 = blk.p1.data() + blk.p_off[i]; const uint32_t* n1 = blk.n1.data() + blk.n_off[i];
+        q.pos1 = {p1, (size_t)q.rec.pos_n}; q.neg1 = {n1, (size_t)q.rec.neg_n};
+        if (r.applied) { q.pos0 = q.pos1; q.neg0 = q.neg1; }
+        else { q.pos0 = {blk.p0.data() + blk.p_off[i], (size_t)(blk.p_off[i + 1] - blk.p_off[i])}; q.neg0 = {blk.n0.data() + blk.n_off[i], (size_t)(blk.n_off[i + 1] - blk.n_off[i])}; }
+        q.pst = {blk.pst.data() + blk.p_off[i], (size_t)q.rec.pos_n}; q.nst = {blk.nst.data() + blk.n_off[i], (size_t)q.rec.neg_n};
+        const int32_t si = blk.sidx[i];
+        q.has_stream = si >= 0;
+        if (si >= 0) { q.rsz = {blk.rsz.data() + blk.res_off[(size_t)si], (size_t)(blk.res_off[(size_t)si + 1] - blk.res_off[(size_t)si])};
+                       q.rlits = {blk.rlits.data() + blk.lit_off[(size_t)si], (size_t)(blk.lit_off[(size_t)si + 1] - blk.lit_off[(size_t)si])}; }
+        else { q.rsz = {}; q.rlits = {}; }
+        return &q;
+    };
+    if (fresh(v)) { return view(v); }
     static const uint32_t LCAP = 64;
     if (hot[2 * v].n > LCAP || hot[2 * v + 1].n > LCAP) { return nullptr; }
     flushDevice();
     ++n_eval_batches;
-    std::vector<int> vs; vs.push_back(v);
+    eval_blocks.emplace_back(new EvalBlock());
+    EvalBlock& blk = *eval_blocks.back();
+    std::vector<uint32_t>& vars = blk.vars; vars.push_back((uint32_t)v);
     uint64_t budget = 0; size_t keep = 0;
     for (size_t i = 0; i < bve_pending.size(); ++i) {
         const int w = bve_pending[i];
@@ -2065,38 +2082,41 @@ Engine::EvalEnt* Engine::evalFor(int v)
         if (budget + np > (256u << 20)) { bve_pending[keep++] = w; continue; }   // next batch
         if (fresh(w)) { bve_inpend[w] = 0; continue; }
         budget += np; bve_inpend[w] = 0;
-        vs.push_back(w);
+        vars.push_back((uint32_t)w);
     }
     bve_pending.resize(keep);
-    eval_blocks.emplace_back(new EvalBlock());
-    EvalBlock& blk = *eval_blocks.back();
-    const size_t nv = vs.size();
-    std::vector<uint32_t> vars(nv), p_off(nv + 1, 0), n_off(nv + 1, 0);
-    for (size_t i = 0; i < nv; ++i) { vars[i] = (uint32_t)vs[i]; p_off[i + 1] = p_off[i] + hot[2 * vs[i]].n; n_off[i + 1] = n_off[i] + hot[2 * vs[i] + 1].n; }
-    blk.p0.resize(p_off[nv]); blk.n0.resize(n_off[nv]);
+    const size_t nv = vars.size();
+    std::vector<uint32_t>& p_off = blk.p_off; std::vector<uint32_t>& n_off = blk.n_off;
+    p_off.assign(nv + 1, 0); n_off.assign(nv + 1, 0);
+    for (size_t i = 0; i < nv; ++i) { p_off[i + 1] = p_off[i] + hot[2 * vars[i]].n; n_off[i + 1] = n_off[i] + hot[2 * vars[i] + 1].n; }
+    blk.p0.resize(p_off[nv] + 1); blk.n0.resize(n_off[nv] + 1); blk.p1.resize(p_off[nv] + 1); blk.n1.resize(n_off[nv] + 1);
+    blk.pst.resize(p_off[nv] + 1); blk.nst.resize(n_off[nv] + 1);
     parallelFor(nv, [&](size_t b, size_t e, int) {
         for (size_t i = b; i < e; ++i) {
-            const int w = vs[i];
+            const int w = (int)vars[i];
             memcpy(blk.p0.data() + p_off[i], occ_pool.data() + occ[2 * w].off, sizeof(uint32_t) * hot[2 * w].n);
             memcpy(blk.n0.data() + n_off[i], occ_pool.data() + occ[2 * w + 1].off, sizeof(uint32_t) * hot[2 * w + 1].n);
+            memcpy(blk.p1.data() + p_off[i], blk.p0.data() + p_off[i], sizeof(uint32_t) * hot[2 * w].n);
+            memcpy(blk.n1.data() + n_off[i], blk.n0.data() + n_off[i], sizeof(uint32_t) * hot[2 * w + 1].n);
         }
     }, 16384);
-    blk.p1 = blk.p0; blk.n1 = blk.n0; blk.pst.resize(blk.p0.size() + 1); blk.nst.resize(blk.n0.size() + 1);
-    std::vector<cp3g_bve_rec> recs(nv);
+    std::vector<cp3g_bve_rec>& recs = blk.recs; recs.resize(nv);
     int64_t t0 = now_ns();
     if (cp3g_bve_eval(gpu, (uint32_t)nv, vars.data(), p_off.data(), blk.p1.data(), n_off.data(), blk.n1.data(), opt.bve_gates ? 1 : 0,
-                      recs.data(), blk.pst.data(), blk.nst.data()) != CP3G_OK) { die("bve_eval failed"); }
+                      recs.data(), opt.bve_BCElim ? blk.pst.data() : nullptr, opt.bve_BCElim ? blk.nst.data() : nullptr) != CP3G_OK) { die("bve_eval failed"); }
     host_ns_gpuwait += now_ns() - t0;
     // resolvent streams for the likely eliminations.  The global growth allowance (bve_cgrow_t - totallyAdded, BVE.cc:532-540) is
     // shared by ALL later eliminations: only a small part of it is granted per variable here; the few clause-increasing
     // eliminations beyond that fetch their resolvents through the pair-matrix path.
     int slack = opt.bve_cgrow;
     if (opt.bve_cgrow_t != INT32_MAX && opt.bve_cgrow_t > opt.bve_cgrow) { slack += std::min(8, std::max(0, opt.bve_cgrow_t - bve_totallyAdded)); }
-    std::vector<uint32_t> sel; std::vector<uint64_t> res_off{0}, lit_off{0};
+    std::vector<uint32_t> sel; std::vector<uint64_t>& res_off = blk.res_off; std::vector<uint64_t>& lit_off = blk.lit_off;
+    res_off.assign(1, 0); lit_off.assign(1, 0); blk.sidx.assign(nv, -1);
     for (size_t i = 0; i < nv; ++i) {
         const cp3g_bve_rec& r = recs[i];
         if ((r.flags & CP3G_BVE_HOST) || r.resolvents == 0 || opt.bve_BCElim) { continue; }
         if ((int64_t)r.resolvents > (int64_t)r.pos_n + r.neg_n + slack || lit_off.back() > (64u << 20)) { continue; }
+        blk.sidx[i] = (int32_t)sel.size();
         sel.push_back((uint32_t)i); res_off.push_back(res_off.back() + r.resolvents); lit_off.push_back(lit_off.back() + r.lit_clauses);
     }
     blk.rsz.resize(res_off.back() + 1); blk.rlits.resize(lit_off.back() + 1);
@@ -2106,23 +2126,9 @@ Engine::EvalEnt* Engine::evalFor(int v)
         if (cp3g_bve_stream(gpu, (uint32_t)sel.size(), sel.data(), res_off.data(), lit_off.data(), blk.rsz.data(), blk.rlits.data()) != CP3G_OK) { die("bve_stream failed"); }
         host_ns_gpuwait += now_ns() - t1;
     }
-    size_t si = 0;
-    for (size_t i = 0; i < nv; ++i) {
-        const int w = vs[i];
-        if (ev_slot[w] < 0) { ev_slot[w] = (int32_t)ev_ent.size(); ev_ent.emplace_back(); }
-        EvalEnt& q = ev_ent[(size_t)ev_slot[w]];
-        q.touch = var_touch[w]; q.valid = true; q.rec = recs[i];
-        q.pos0 = {blk.p0.data() + p_off[i], (size_t)(p_off[i + 1] - p_off[i])}; q.neg0 = {blk.n0.data() + n_off[i], (size_t)(n_off[i + 1] - n_off[i])};
-        q.pos1 = {blk.p1.data() + p_off[i], (size_t)recs[i].pos_n}; q.neg1 = {blk.n1.data() + n_off[i], (size_t)recs[i].neg_n};
-        q.pst = {blk.pst.data() + p_off[i], (size_t)recs[i].pos_n}; q.nst = {blk.nst.data() + n_off[i], (size_t)recs[i].neg_n};
-        q.has_stream = si < sel.size() && sel[si] == (uint32_t)i;
-        if (q.has_stream) {
-            q.rsz = {blk.rsz.data() + res_off[si], (size_t)(res_off[si + 1] - res_off[si])};
-            q.rlits = {blk.rlits.data() + lit_off[si], (size_t)(lit_off[si + 1] - lit_off[si])};
-            ++si;
-        } else { q.rsz = {}; q.rlits = {}; }
-    }
-    return fresh(v);
+    const int32_t bi = (int32_t)eval_blocks.size() - 1;
+    parallelFor(nv, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { const uint32_t w = vars[i]; ev_ref[w] = EvRef{bi, (uint32_t)i, var_touch[w], 0u}; } }, 16384);
+    return fresh(v) ? view(v) : nullptr;
 }
 
 template <class A> static inline int indexOf(const A& a, uint32_t x)
@@ -2457,7 +2463,7 @@ void Engine::bveWorker()
             pos_count = (int)ee->pos1.n; neg_count = (int)ee->neg1.n;
             // evaluating the lists in this form again gives the same record (the gate clauses are in front already, nothing is left to
             // clean): it stays valid for the next time v comes out of the heap untouched
-            ee->pos0 = ee->pos1; ee->neg0 = ee->neg1;
+            ev_ref[(size_t)v].applied = 1;
             ++n_eval_used;
         } else {
             for (int s = 0; s < 2; ++s) {
@@ -2498,11 +2504,33 @@ void Engine::bveWorker()
             else if (resolvents > pos_count + neg_count) { bve_nInc++; }
             else { bve_nKeep++; }
             lapt(tg);
+            // The elimination touches, per literal of every resolvent and of every parent clause, the counters, the list tail, the
+            // heap slot and the touch record of that literal's variable - dependent cache misses on a 10 M variable mirror.  They
+            // are requested level by level ahead of their use (side-effect free).
+            auto prefetchParents = [&](int stage) {
+                for (int s2 = 0; s2 < 2; ++s2) {
+                    const uint32_t* lp = occ_pool.data() + occ[2 * v + s2].off; const uint32_t n = std::min<uint32_t>(hot[2 * v + s2].n, 24);
+                    for (uint32_t k = 0; k < n; ++k) {
+                        const uint32_t c = lp[k];
+                        if (stage == 0) { __builtin_prefetch(&C[c]); if (c < log_head.size()) { __builtin_prefetch(&log_head[c]); } }
+                        else if (stage == 1) { __builtin_prefetch(&pool[C[c].start]); }
+                        else {
+                            const int32_t* l = pool.data() + C[c].start; const uint32_t m = std::min<uint32_t>(C[c].size, 8);
+                            for (uint32_t j = 0; j < m; ++j) { const int x = l[j], w = x >> 1; __builtin_prefetch(&hot[x]); __builtin_prefetch(&hidx[w]); __builtin_prefetch(&modTimer[w]); __builtin_prefetch(&stale[x]); __builtin_prefetch(&var_touch[w]); __builtin_prefetch(&bve_inpend[w]); }
+                        }
+                    }
+                }
+            };
+            prefetchParents(0);
             if (ee != nullptr && ee->has_stream && !opt.bve_BCElim) {
                 // resolveSet (BVE.cc:892-1046) from the K6' stream: the resolvents in the reference's order, nothing to look up
                 const bool useHeap = opt.bve_heap_updates > 0;
                 bve_steps += ee->rec.steps;
                 const int32_t* rl = ee->rlits.p;
+                for (size_t k = 0; k < ee->rlits.n; ++k) { const int x = rl[k], w = x >> 1; __builtin_prefetch(&hot[x]); __builtin_prefetch(&occ[x]); __builtin_prefetch(&var_touch[w]); __builtin_prefetch(&hidx[w]); __builtin_prefetch(&bve_inpend[w]); }
+                prefetchParents(1);
+                for (size_t k = 0; k < ee->rlits.n; ++k) { const int x = rl[k]; __builtin_prefetch(&occ_pool[(size_t)occ[x].off + hot[x].n]); const int hi = hidx[x >> 1]; if (hi >= 0) { __builtin_prefetch(&heap[(size_t)hi]); } }
+                prefetchParents(2);
                 for (size_t k = 0; k < ee->rsz.n; ++k) {
                     const int sz = ee->rsz[k];
                     const uint32_t cr = allocClause(rl, sz);
@@ -2513,7 +2541,7 @@ void Engine::bveWorker()
                     rl += sz;
                 }
                 ++n_stream_used;
-            } else if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; }
+            } else { prefetchParents(1); if (resolveSet(v, p_limit, n_limit) == L_FALSE) { return; } prefetchParents(2); }
             lapt(tr);
             ++bve_eliminatedVars;
             bveRemoveClauses(2 * v, -1);
@@ -2646,7 +2674,7 @@ int Engine::bveProcess()
     const bool propagatedSomething = t_up.modified;
     sequentiellBVE();
     pair_blocks.clear(); pc_ent.clear(); std::fill(pc_slot.begin(), pc_slot.end(), -1);
-    eval_blocks.clear(); ev_ent.clear(); std::fill(ev_slot.begin(), ev_slot.end(), -1);
+    eval_blocks.clear(); ev_ref.clear();
     if (!t_bve.modified) { unsuccessful(t_bve); }
     if (t_bve.modified || propagatedSomething) { successful(t_bve); }
     return ok ? L_UNDEF : L_FALSE;

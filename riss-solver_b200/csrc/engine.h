@@ -235,10 +235,14 @@ private:
     std::vector<int> scratch_col;
     // K5'/K6' results per variable (cp3g_bve_eval / cp3g_bve_stream): the whole bve_worker evaluation of a variable on the
     // lists as they were at batch time.  Valid while the touch counter and the two lists themselves are unchanged.
-    struct EvalEnt { uint32_t touch = 0; bool valid = false, has_stream = false; cp3g_bve_rec rec;
-                     Span<uint32_t> pos0, neg0, pos1, neg1; Span<uint16_t> pst, nst, rsz; Span<int32_t> rlits; };
-    struct EvalBlock { std::vector<uint32_t> p0, n0, p1, n1; std::vector<uint16_t> pst, nst, rsz; std::vector<int32_t> rlits; };
-    std::vector<std::unique_ptr<EvalBlock>> eval_blocks; std::vector<int32_t> ev_slot; std::vector<EvalEnt> ev_ent;
+    struct EvalEnt { bool has_stream = false; cp3g_bve_rec rec;
+                     Span<uint32_t> pos0, neg0, pos1, neg1; Span<uint16_t> pst, nst, rsz; Span<int32_t> rlits; };   // a view, built on demand
+    struct EvalBlock { std::vector<uint32_t> vars, p_off, n_off; std::vector<cp3g_bve_rec> recs; RawVec<uint32_t> p0, n0, p1, n1; RawVec<uint16_t> pst, nst;
+                       std::vector<int32_t> sidx; std::vector<uint64_t> res_off, lit_off; RawVec<uint16_t> rsz; RawVec<int32_t> rlits; };
+    // per variable: where its record lives (16 bytes; the records themselves stay in the batch blocks).  applied: the lists
+    // already have the rewritten form (the record was used once), compare against that form from now on
+    struct EvRef { int32_t blk; uint32_t idx, touch, applied; };
+    std::vector<std::unique_ptr<EvalBlock>> eval_blocks; RawVec<EvRef> ev_ref; EvalEnt ev_view;
     EvalEnt* evalFor(int v);                            // cached record of v, or one more batch (v + the waiting heap variables)
     bool in_bve_worker = false;
     bool sharded = false;                               // scan service split over several ranks (CPsetDistributed)
