@@ -1,22 +1,32 @@
 #!/usr/bin/env python
-"""bench.py - headline benchmark of the Coprocessor GPU hot path (BASELINE.json: subsumption checks/s).
+"""bench.py - headline benchmark of the Coprocessor GPU hot path (BASELINE.json: subsumption checks/s, simplify wall time,
+% of the HBM roofline).
 
-Workload (config.workload): BASELINE configs[1] - synthetic random 3-SAT, 1M vars / 4.26M clauses with planted
-duplicates / supersets / one-literal-flipped copies (seed 12345): subsumption + strengthening
-fixpoint.  A "check" is the reference's own unit: one Stepper::increaseSteps(1), i.e. one (subsumer|strengthener,
-candidate) pair taken from an occurrence list (Subsumption.cc:268,1330,1431).
+A "check" is the reference's own unit: one Stepper::increaseSteps(1) - one (subsumer | strengthener, candidate) pair taken from
+an occurrence list (Subsumption.cc:268,1330,1431) or one (pos, neg) clause pair of a BVE candidate (BVE.cc:756,910).  Parity
+makes these counters identical to the reference's, so checks/s of both arms divide the same number by their own time.
 
-  value  checks/s of the device-resident bulk pass: clause arena already in HBM, K1 signatures + K2 occurrence
-         CSR + K3 full-queue subsumption scan + K4 full-queue strengthening scan, timed with CUDA events on the
-         library's stream (cp3g_* scan service, hits stay on the device).
-  e2e    checks/s through the reference-facing C ABI on HOST buffers: CPaddLits of the DIMACS stream (host -> device
-         inside the timed region), CPpreprocess (all scans, ordered commit on the host), read-back of the output CNF -
-         the whole fixpoint; checks = the reference-defined step counters, which parity makes identical to the
-         reference's.  (The reference arm times Preprocessor::preprocess() only, its own ingest is not charged.)
-  --impl reference   the reference's own CPU Coprocessor (oracle/_ref, unmodified sources) on a bounded sample of
-         the same workload with all host threads (-cp3_threads), same metric.
+A "step" is one whole simplification fixpoint over one formula:
 
-One JSON line on stdout (rank 0).
+  value  checks / time of CPpreprocess alone: the clause arena is already resident in HBM (CPaddLits put it there), the timed
+         region is the fixpoint itself - every kernel launch, every ordered commit, results on the host.  Like for like with
+         the reference arm, which times Preprocessor::preprocess() only.
+  e2e    checks / time of CPaddLits (DIMACS stream in pinned HOST memory -> device bulk ingest) + CPpreprocess + read-back of
+         the simplified CNF into a host buffer: what a client of libcoprocessorc.h pays.
+  roofline  the full-queue kernel k_full (K3 subsumption + K4 strengthening launches inside the timed steps): ALGORITHMIC bytes
+         per launch (4 + 8 + 4*#D per check, counted by the kernel) / launch duration (CUDA events on the
+         library's stream), against MEASURED_PEAKS.json; `per_kernel` lists every kernel family of the step the same way.
+
+--config c2 (default)  BASELINE configs[1]: planted random 3-SAT, 1M vars / 4.26M clauses, subsumption + strengthening fixpoint.
+                       At N=1 the default run appends one fixpoint at BASELINE configs[2] scale under the key "c3"
+                       (community k-SAT 10M vars / 54M clauses, -up -subsimp -bve): the target configuration takes ~20 s per
+                       step, so it is measured once per run, not K times (DESIGN.md "Measurement").
+--config c3            configs[2] as the K-step workload.
+--config zipf          configs[4]: literal-frequency skew sweep, one JSON line per exponent s.
+--impl reference       the reference's own CPU Coprocessor (oracle/_ref, unmodified sources, all host threads) on the same
+                       workload and metric.
+
+One JSON line on stdout (rank 0) - except --config zipf.
 """
 from __future__ import annotations
 
@@ -34,16 +44,34 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "subsumption+strengthening checks/s (reference Stepper steps)"
+METRIC = "simplification checks/s over the whole fixpoint (reference Stepper steps: subsumption + strengthening + BVE)"
 UNIT = "checks/s"
 REFSHIM = os.path.join(ROOT, "oracle", "_ref", "refshim")
 SUSI = ["-enabled_cp3", "-subsimp", "-no-cp3_limited"]
+FULL = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]
+CHECK_STATS = ("sub_subsSteps", "sub_strengthSteps", "bve_steps")
 
 
-def workload(n_vars: int, seed: int):
-    import riss_solver_b200 as rs
-    lits, sizes = rs.gen.random_ksat(n_vars, int(4.26 * n_vars), 3, seed=seed)
-    return lits, sizes, rs.gen.csr_to_stream(lits, sizes)
+class Config:
+    def __init__(self, name, n_vars):
+        self.name, self.n = name, n_vars
+        self.opts = SUSI if name in ("c2", "zipf") else FULL
+
+    def generate(self, seed_offset=0, zipf_s=0.0):
+        import riss_solver_b200 as rs
+        if self.name == "c3":
+            lits, sizes = rs.gen.community_ksat(self.n, 5 * self.n, seed=20260001 + seed_offset)
+        else:
+            lits, sizes = rs.gen.random_ksat(self.n, int(4.26 * self.n), 3, seed=(12345 if zipf_s == 0 else 777) + seed_offset, zipf_s=zipf_s)
+        return lits, sizes, rs.gen.csr_to_stream(lits, sizes)
+
+    def workload(self):
+        """the string both arms print: what is simplified, with which options"""
+        if self.name == "c3":
+            return (f"BASELINE configs[2]: community-attachment k-SAT {self.n} vars / {5 * self.n} base clauses, k in 3/4/5 (50/30/20 %), 5 % rare variables, "
+                    f"+2 % duplicates, 3 % supersets, 3 % flipped copies, seed 20260001; unit propagation + subsumption + strengthening + BVE to the fixpoint ({' '.join(FULL)})")
+        return (f"BASELINE configs[1]: planted random 3-SAT {self.n} vars / {int(4.26 * self.n)} base clauses +2 % duplicates, 3 % supersets, 3 % flipped copies, "
+                f"seed 12345; subsumption + strengthening to the fixpoint ({' '.join(SUSI)})")
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -81,7 +109,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-# ------------------------------------------------------------------------------------------------ reference arm
+# ------------------------------------------------------------------------------------------------ reference on the host cores
 def run_refshim(stream, opts, tag):
     with tempfile.TemporaryDirectory() as td:
         inp = os.path.join(td, f"{tag}.bin"); out = os.path.join(td, "out.txt")
@@ -97,63 +125,64 @@ def run_refshim(stream, opts, tag):
         return st
 
 
-def cpu_baseline(sample_vars: int, seed: int):
-    """sequential reference (the parity oracle's source of truth) on a bounded sample, one host core"""
+def checks_of(st):
+    return sum(st.get(k, 0) for k in CHECK_STATS)
+
+
+def cpu_baseline(cfg: Config, sample: Config):
+    """the sequential reference (the parity oracle's source of truth) on a bounded sample of the workload, one host core"""
+    _, sizes, stream = sample.generate()
+    what = f"{sample.name} shape, {sample.n} vars / {sizes.size} clauses ({'the full workload' if sample.n == cfg.n else 'bounded sample of the workload'}), options {' '.join(sample.opts)}"
     if not os.path.exists(REFSHIM):
         # the compiled reference did not travel: time the plain-C port instead
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from harness import Oracle
-        _, _, stream = workload(sample_vars, seed)
-        o = Oracle(SUSI); o.add(stream)
+        o = Oracle(sample.opts); o.add(stream)
         t = time.time(); o.preprocess(); dt = time.time() - t
         r = o.result(); o.close()
-        checks = r.stats["sub_subsSteps"] + r.stats["sub_strengthSteps"]
-        return {"value": checks / dt, "unit": UNIT, "cores": 1, "kind": "port",
-                "sample": f"planted 3-SAT {sample_vars} vars / {int(4.26 * sample_vars)} clauses, seed {seed}, {dt:.2f} s"}
-    _, _, stream = workload(sample_vars, seed)
-    st = run_refshim(stream, SUSI, "cpu")
-    checks = st["sub_subsSteps"] + st["sub_strengthSteps"]
-    return {"value": checks / st["seconds"], "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"planted 3-SAT {sample_vars} vars / {int(4.26 * sample_vars)} clauses, seed {seed}, sequential "
-                      f"Preprocessor::preprocess() {st['seconds']:.2f} s, {int(checks)} checks"}
+        return {"value": checks_of(r.stats) / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt, "sample": what}
+    st = run_refshim(stream, sample.opts, "cpu")
+    return {"value": checks_of(st) / st["seconds"], "unit": UNIT, "cores": 1, "kind": "reference", "seconds": st["seconds"],
+            "sample": what + f"; sequential Preprocessor::preprocess() {st['seconds']:.2f} s, {int(checks_of(st))} checks"}
 
 
-def reference_arm(args):
+def reference_arm(args, cfg: Config):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if not os.path.exists(REFSHIM):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refshim missing (reference not built)"}))
         return
-    nv = args.ref_vars
-    _, _, stream = workload(nv, args.seed)
+    # c2 runs the full workload (2.5 s per step with the thread pool); c3 a tenth of it (the full one takes minutes per step)
+    sample = cfg if cfg.name != "c3" else Config("c3", max(1, cfg.n // 10))
+    _, sizes, stream = sample.generate()
     cores = os.cpu_count() or 1
-    seq = run_refshim(stream, SUSI, "seq")                       # untimed: the step counters of this sample
-    checks = seq["sub_subsSteps"] + seq["sub_strengthSteps"]
-    opts = SUSI + ([f"-cp3_threads={cores - 1}", "-cp3_par_subs=2", "-cp3_par_strength=2"] if cores > 1 else [])
+    seq = run_refshim(stream, sample.opts, "seq")                 # untimed: the step counters of this sample (thread-independent unit)
+    checks = checks_of(seq)
+    par = [f"-cp3_threads={cores - 1}", "-cp3_par_subs=2", "-cp3_par_strength=2"] if cores > 1 else []
     times = []
     for i in range(args.warmup + args.steps):
-        st = run_refshim(stream, opts, "par")
+        st = run_refshim(stream, sample.opts + par, "par")
         if i >= args.warmup:
             times.append(st["seconds"])
     T = float(np.mean(times))
     v = checks / T
-    sample = (f"planted 3-SAT {nv} vars / {int(4.26 * nv)} clauses, seed {args.seed}; unmodified reference "
-              f"Preprocessor::preprocess() with -cp3_threads={cores - 1} -cp3_par_subs=2 -cp3_par_strength=2; "
-              f"checks = sequential step counters of the same sample ({int(checks)})")
+    desc = (f"{sample.n} vars / {sizes.size} clauses ({'the full workload' if sample.n == cfg.n else 'a tenth of the workload: bounded sample'}); unmodified reference "
+            f"Preprocessor::preprocess() with {' '.join(par) or 'one thread'}; checks = sequential step counters of the same input ({int(checks)}); "
+            f"sequential run of the same input {seq['seconds']:.2f} s")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": f"C2-shape planted random 3-SAT sample, {nv} vars / {int(4.26 * nv)} clauses, subsumption+strengthening fixpoint",
-                   "parallelism": f"cpu pthreads x{cores - 1}"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "config": {"workload": cfg.workload(), "parallelism": f"cpu pthreads x{max(cores - 1, 1)}", "sample": desc},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference", "sample": desc, "sequential_seconds": seq["seconds"]},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
 # ------------------------------------------------------------------------------------------------ our arm
 def to_codes_sorted(lits, sizes):
+    """DIMACS literals -> Riss literal codes 2*var+sign, every clause sorted (what cp3g_upload expects; used by scripts/)"""
     v = np.abs(lits).astype(np.int64) - 1
     codes = (2 * v + (lits < 0)).astype(np.int32)
     k = int(sizes.max())
@@ -167,28 +196,81 @@ def to_codes_sorted(lits, sizes):
     return out
 
 
+KERNEL_FAMILIES = [   # (label, ns counter, algorithmic-bytes counter)
+    ("K0 k_ing_* (bulk ingest)", "gpu_ingest_ns", "gpu_ingest_bytes"),
+    ("K1+K2 k_occ_* (signatures + occurrence lists)", "gpu_build_ns", "gpu_build_bytes"),
+    ("K3 k_full<subsume>", "gpu_full0_ns", "gpu_full0_bytes"),
+    ("K4 k_full<strengthen>", "gpu_full1_ns", "gpu_full1_bytes"),
+    ("commit k_sp_* (device pass commit)", "gpu_commit_ns", "gpu_commit_bytes"),
+    ("K5'+K6' k_bve_eval/k_bve_stream", "gpu_bve_ns", "gpu_bve_bytes"),
+]
+STEP_STATS = ["sub_subsSteps", "sub_strengthSteps", "bve_steps", "gpu_launches", "gpu_h2d_bytes", "gpu_d2h_bytes", "sub_subsumedClauses", "sub_removedLiterals",
+              "bve_eliminatedVars", "scan_batches", "scan_ondemand", "device_sub_passes", "eval_batches", "gpu_kernel_ns", "gpu_scan_ns",
+              "gpu_full0_checks", "gpu_full1_checks", "gpu_full0_launches", "gpu_full1_launches", "gpu_build_count"] + [k for f in KERNEL_FAMILIES for k in f[1:]]
+
+
+def fixpoint_step(rs, opts, stream, barrier, distributed=None):
+    """one step: CPinit(options) -> CPaddLits -> CPpreprocess -> CPgetOutput; returns (t_add, t_preprocess, t_output, stats, output size)"""
+    cp = rs.Coprocessor(opts)
+    if distributed is not None:
+        rank, world, uid = distributed
+        if cp.set_distributed(rank, world, uid) != 0:
+            raise SystemExit("CPsetDistributed failed (NCCL communicator)")
+    barrier()
+    t0 = time.perf_counter()
+    cp.add_stream(stream)                         # CPaddLits: the DIMACS stream from pinned host memory (device bulk ingest K0)
+    t1 = time.perf_counter()
+    cp.preprocess()                               # the fixpoint
+    t2 = time.perf_counter()
+    out = cp.output_stream()                      # the simplified CNF in a host buffer
+    barrier()
+    t3 = time.perf_counter()
+    st = {k: cp.stat(k) for k in STEP_STATS}
+    cp.close()
+    return t1 - t0, t2 - t1, t3 - t2, st, int(out.size)
+
+
+def roofline_of(steps_stats, peak, peak_src, traffic):
+    tot = {k: float(np.mean([s[k] for s in steps_stats])) for k in STEP_STATS}
+    per = {}
+    for label, kns, kby in KERNEL_FAMILIES:
+        if tot[kns] <= 0:
+            continue
+        per[label] = {"ms_per_step": tot[kns] * 1e-6, "algorithmic_GB_per_step": tot[kby] * 1e-9, "GB/s": tot[kby] / tot[kns], "frac": tot[kby] / tot[kns] / peak}
+    nl = max(tot["gpu_full0_launches"] + tot["gpu_full1_launches"], 1.0)
+    fb = tot["gpu_full0_bytes"] + tot["gpu_full1_bytes"]; fn = tot["gpu_full0_ns"] + tot["gpu_full1_ns"]
+    achieved = fb / fn if fn > 0 else 0.0                          # bytes / ns = GB/s
+    return {"bound": "hbm", "kernel": "k_full (full-queue K3 + K4 launches of the timed steps)", "achieved": achieved, "peak": peak, "peak_source": peak_src,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": fb / nl, "launch_ms": fn * 1e-6 / nl,
+            "launches_per_step": nl, "checks_per_launch": (tot["gpu_full0_checks"] + tot["gpu_full1_checks"]) / nl, "per_kernel": per}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--vars", type=int, default=1000000, help="variables of the C2 workload (clauses = 4.26x)")
-    ap.add_argument("--ref-vars", type=int, default=1000000, help="size of the sample the CPU reference legs run (default: the full workload)")
-    ap.add_argument("--seed", type=int, default=12345)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "zipf"])
+    ap.add_argument("--vars", type=int, default=0, help="variables of the workload (default: 1M for c2/zipf, 10M for c3)")
     ap.add_argument("--mode", default="weak", choices=["weak", "sharded"],
-                    help="N>1: weak = one independent formula per rank; sharded = one formula, scan requests "
-                         "partitioned over the ranks and hits all-gathered over NCCL")
+                    help="N>1: weak = one independent formula per rank (each rank its own GPU and share of the host cores); sharded = one formula, "
+                         "scan requests partitioned over the ranks and hits all-gathered over NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c3", action="store_true", help="skip the configs[2]-scale fixpoint that the default c2 run appends at N=1")
+    ap.add_argument("--c3-vars", type=int, default=10000000)
     args = ap.parse_args()
+    cfg = Config(args.config, args.vars or (10000000 if args.config == "c3" else 1000000))
     if args.impl == "reference":
-        return reference_arm(args)
+        return reference_arm(args, cfg)
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # one engine per rank: split the host cores between the ranks of this node (the ordered commit uses a thread pool)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     os.environ.setdefault("CP3_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))))
+    # a process that calls CPpreprocess repeatedly keeps the engine's work arrays in its heap (opt-in, capi.cpp)
+    os.environ.setdefault("CP3_KEEP_HEAP", "1")
     import torch
     import torch.distributed as dist
     import riss_solver_b200 as rs
@@ -203,141 +285,120 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    seed = args.seed + (rank if args.mode == "weak" else 0)
-    lits, sizes, stream = workload(args.vars, seed)
-    nvars = int(np.abs(lits).max())
-    codes = to_codes_sorted(lits, sizes)
-    opts = SUSI + [f"-cp3_gpu_device={local}"]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
-    stream = torch.from_numpy(np.ascontiguousarray(stream, dtype=np.int32)).pin_memory().numpy()   # e2e input: pinned host memory
-
     def fresh_uid():
         # one ncclUniqueId per communicator: every Coprocessor instance of the sharded mode gets its own
         if not (world > 1 and args.mode == "sharded"):
             return None
         box = [rs.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        return box[0]
+        return (rank, world, box[0])
 
-    # ---------------- leg 1: device-resident bulk pass (value, roofline)
-    svc = rs.ScanService(local)
-    svc.upload(nvars, codes, sizes)
-    ids = np.arange(sizes.size, dtype=np.uint32)
-    # algorithmic bytes of one check: 4 (occ entry) + 8 (header) + 4*#D (candidate literals)
-    def resident_pass():
-        c0 = {k: svc.counter(k) for k in ("kernel_ns", "launches", "scan_ns", "scan_checks", "scan_alg_bytes")}
-        svc.build()
-        b = svc.counter("kernel_ns") - c0["kernel_ns"]
-        s0 = svc.counter("scan_ns"); a0 = svc.counter("scan_alg_bytes"); k0 = svc.counter("scan_checks")
-        svc.scan_all(rs.SUBSUME, count_only=True)
-        s1 = svc.counter("scan_ns"); a1 = svc.counter("scan_alg_bytes"); k1 = svc.counter("scan_checks")
-        svc.scan_all(rs.STRENGTHEN, count_only=True)
-        r = {k: svc.counter(k) - c0[k] for k in c0}
-        r.update(build_ns=b, k3_ns=s1 - s0, k3_bytes=a1 - a0, k3_checks=k1 - k0, k4_ns=svc.counter("scan_ns") - s1,
-                 k4_bytes=svc.counter("scan_alg_bytes") - a1, k4_checks=svc.counter("scan_checks") - k1)
-        return r
-
-    for _ in range(args.warmup):
-        flush.fill_(1); resident_pass()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    res = []
-    for _ in range(args.steps):
-        flush.fill_(1); torch.cuda.synchronize()
-        res.append(resident_pass())
-    barrier()
-    dev_ns = float(np.mean([r["kernel_ns"] for r in res]))
-    scan_ns = float(np.mean([r["scan_ns"] for r in res]))
-    dev_checks = float(np.mean([r["scan_checks"] for r in res]))
-    alg_bytes = float(np.mean([r["scan_alg_bytes"] for r in res]))
-    launches_res = int(np.mean([r["launches"] for r in res]))
-    svc.close()
-
-    # ---------------- leg 2: end to end through the C ABI (host buffers in, host buffers out)
-    def e2e_step():
-        cp = rs.Coprocessor(opts)
-        uid = fresh_uid()
-        if uid is not None and cp.set_distributed(rank, world, uid) != 0:
-            raise SystemExit("CPsetDistributed failed (NCCL communicator)")
-        barrier()
-        t0 = time.perf_counter()
-        cp.add_stream(stream)                         # CPaddLits: the DIMACS stream from host memory (device bulk ingest K0)
-        cp.preprocess()
-        out = cp.output_stream()                      # device->host results are part of the call; read the CNF back
-        barrier()
-        dt = time.perf_counter() - t0
-        st = {k: cp.stat(k) for k in ("sub_subsSteps", "sub_strengthSteps", "gpu_launches", "gpu_h2d_bytes", "gpu_d2h_bytes",
-                                      "sub_subsumedClauses", "sub_removedLiterals", "scan_batches", "scan_ondemand")}
-        cp.close()
-        return dt, st, out.size
-
-    for _ in range(args.warmup):
-        flush.fill_(1); e2e_step()
-    e2e = []
-    for _ in range(args.steps):
-        flush.fill_(1); e2e.append(e2e_step())
-    clocks = sampler.stop() if sampler else None
-    T = float(np.mean([x[0] for x in e2e]))
-    st = e2e[-1][1]
-    checks = st["sub_subsSteps"] + st["sub_strengthSteps"]
-
-    # max over ranks (time), sum over ranks (work)
-    if world > 1:
-        t = torch.tensor([T, dev_ns], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        T, dev_ns = float(t[0]), float(t[1])
-        w = torch.tensor([float(checks), dev_checks], device="cuda", dtype=torch.float64)
-        if args.mode == "weak":
-            dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        checks, dev_checks = float(w[0]), float(w[1])
-
-    def mean(k):
-        return float(np.mean([r[k] for r in res]))
-
-    # DRAM bytes per launch of the dominant kernel from the last `ncu --set full` capture (profiles/), or None
-    TRAFFIC = None
+    peaks = {}
     try:
-        TRAFFIC = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_full_bytes_per_launch")
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        pass
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def pinned(stream):
+        return torch.from_numpy(np.ascontiguousarray(stream, dtype=np.int32)).pin_memory().numpy()
+
+    def run_steps(c: Config, warmup, steps, zipf_s=0.0):
+        lits, sizes, stream = c.generate(seed_offset=(rank if args.mode == "weak" and world > 1 else 0), zipf_s=zipf_s)
+        del lits
+        stream = pinned(stream)
+        opts = c.opts + [f"-cp3_gpu_device={local}"]
+        for _ in range(warmup):
+            flush.fill_(1); fixpoint_step(rs, opts, stream, barrier, fresh_uid())
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        res = []
+        for _ in range(steps):
+            flush.fill_(1); torch.cuda.synchronize()
+            res.append(fixpoint_step(rs, opts, stream, barrier, fresh_uid()))
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        return sizes.size, int(stream.size), res, clocks
+
+    def summarize(res):
+        t_add = float(np.mean([r[0] for r in res])); t_pp = float(np.mean([r[1] for r in res])); t_out = float(np.mean([r[2] for r in res]))
+        st = res[-1][3]
+        return t_add, t_pp, t_out, st, float(checks_of(st))
+
+    if cfg.name == "zipf":
+        for s in (0.0, 0.5, 0.8, 1.0, 1.2):
+            ncl, nints, res, clocks = run_steps(cfg, 1, max(1, min(args.steps, 3)), zipf_s=s)
+            t_add, t_pp, t_out, st, checks = summarize(res)
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": checks / t_pp, "unit": UNIT, "n_gpus": world, "ms_per_step": t_pp * 1e3, "higher_is_better": True,
+                                  "dtype": "int32", "data": "synthetic",
+                                  "config": {"workload": f"BASELINE configs[4]: Zipf literal-frequency skew s={s}, C2 shape ({cfg.n} vars / {ncl} clauses), subsumption + strengthening fixpoint"},
+                                  "roofline": roofline_of([r[3] for r in res], peak, peak_src, None),
+                                  "e2e": {"value": checks / (t_add + t_pp + t_out), "unit": UNIT, "ms_per_step": (t_add + t_pp + t_out) * 1e3},
+                                  "checks_per_step": checks, "clocks": clocks}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ncl, nints, res, clocks = run_steps(cfg, args.warmup, args.steps)
+    t_add, t_pp, t_out, st, checks = summarize(res)
+    T_e2e = t_add + t_pp + t_out
+    # max over ranks (time), sum over ranks (work)
+    if world > 1:
+        t = torch.tensor([T_e2e, t_pp], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        T_e2e, t_pp = float(t[0]), float(t[1])
+        w = torch.tensor([checks], device="cuda", dtype=torch.float64)
+        if args.mode == "weak":
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        checks = float(w[0])
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = alg_bytes / scan_ns if scan_ns > 0 else 0.0                 # bytes/ns = GB/s
         line = {
-            "metric": METRIC, "value": dev_checks / (dev_ns * 1e-9), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ns * 1e-6, "higher_is_better": True,
-            "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: planted random 3-SAT {args.vars} vars / {sizes.size} clauses "
-                                   f"(2% duplicates, 3% supersets, 3% flipped copies), seed {args.seed}, subsumption+strengthening fixpoint",
-                       "value_leg": "device-resident bulk pass: K1 signatures + K2 occurrence CSR build + K3 + K4 over the full queue, CUDA events on the library stream",
-                       "e2e_leg": "CPaddLits (DIMACS stream from host memory) + CPpreprocess + output read-back, wall clock per step",
-                       "l2": "working set (occ entries + headers + literals, ~350 MB) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
+            "metric": METRIC, "value": checks / t_pp, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_pp * 1e3, "higher_is_better": True, "scaling": "weak" if args.mode == "weak" else "strong", "vs_baseline": None,
+            "dtype": "int32", "data": "synthetic",
+            "config": {"workload": cfg.workload(),
+                       "clauses": ncl, "value_leg": "CPpreprocess: the whole fixpoint, clause arena resident in HBM at the start (wall clock, barrier + device sync on both sides)",
+                       "e2e_leg": "CPaddLits (DIMACS stream in pinned host memory) + CPpreprocess + read-back of the simplified CNF",
+                       "l2": "working set (occurrence entries + headers + literals) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
                        "host_threads_per_rank": int(os.environ["CP3_THREADS"]),
-                       "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank" if args.mode == "weak"
+                       "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank (no data-path collective)" if args.mode == "weak"
                                        else f"{world} ranks, one formula: scan requests partitioned, hits all-gathered over NCCL"))},
-            "roofline": {"bound": "hbm", "kernel": "k_full (K3+K4 full-queue form, both launches)", "achieved": achieved, "peak": peak,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC,
-                         "algorithmic_bytes_per_launch": alg_bytes / 2, "launch_ms": scan_ns * 1e-6 / 2,
-                         "per_kernel": {
-                             "k_full<subsume>": {"ms": mean("k3_ns") * 1e-6, "checks": mean("k3_checks"), "GB/s": mean("k3_bytes") / max(mean("k3_ns"), 1.0)},
-                             "k_full<strengthen>": {"ms": mean("k4_ns") * 1e-6, "checks": mean("k4_checks"), "GB/s": mean("k4_bytes") / max(mean("k4_ns"), 1.0)},
-                             "K1+K2 build": {"ms": mean("build_ns") * 1e-6}}},
-            "e2e": {"value": checks / T, "unit": UNIT, "ms_per_step": T * 1e3, "h2d_bytes_per_step": st["gpu_h2d_bytes"],
-                    "d2h_bytes_per_step": st["gpu_d2h_bytes"], "checks_per_step": checks,
-                    "subsumed_clauses": st["sub_subsumedClauses"], "strengthened_literals": st["sub_removedLiterals"],
-                    "scan_batches": st["scan_batches"], "scan_ondemand": st["scan_ondemand"]},
-            "gpu_launches": launches_res * args.steps + sum(x[1]["gpu_launches"] for x in e2e),
+            "roofline": roofline_of([r[3] for r in res], peak, peak_src, traffic.get("k_full_bytes_per_launch")),
+            "e2e": {"value": checks / T_e2e, "unit": UNIT, "ms_per_step": T_e2e * 1e3, "add_ms": t_add * 1e3, "preprocess_ms": t_pp * 1e3, "output_ms": t_out * 1e3,
+                    "h2d_bytes_per_step": st["gpu_h2d_bytes"], "d2h_bytes_per_step": st["gpu_d2h_bytes"], "checks_per_step": checks / (world if args.mode == "weak" else 1),
+                    "subsumed_clauses": st["sub_subsumedClauses"], "strengthened_literals": st["sub_removedLiterals"], "eliminated_variables": st["bve_eliminatedVars"],
+                    "scan_batches": st["scan_batches"], "scan_ondemand": st["scan_ondemand"], "device_sub_passes": st["device_sub_passes"],
+                    "gpu_kernel_ms_per_step": st["gpu_kernel_ns"] * 1e-6},
+            "gpu_launches": int(sum(r[3]["gpu_launches"] for r in res)),
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args.ref_vars, args.seed)
-        print(json.dumps(line))
+            line["cpu_baseline"] = cpu_baseline(cfg, cfg if cfg.name != "c3" else Config("c3", max(1, cfg.n // 10)))
+        if world == 1 and cfg.name == "c2" and not args.no_c3:
+            # the target configuration, once per run (one untimed + one timed fixpoint)
+            c3 = Config("c3", args.c3_vars)
+            t0 = time.time()
+            ncl3, _, res3, _ = run_steps(c3, 1, 1)
+            a3, p3, o3, st3, chk3 = summarize(res3)
+            sec = {"workload": c3.workload(), "clauses": ncl3, "steps": 1, "warmup": 1, "value": chk3 / p3, "unit": UNIT, "preprocess_s": p3,
+                   "e2e": {"value": chk3 / (a3 + p3 + o3), "unit": UNIT, "seconds": a3 + p3 + o3, "add_s": a3, "output_s": o3,
+                           "h2d_bytes": st3["gpu_h2d_bytes"], "d2h_bytes": st3["gpu_d2h_bytes"]},
+                   "checks": chk3, "sub_subsSteps": st3["sub_subsSteps"], "sub_strengthSteps": st3["sub_strengthSteps"], "bve_steps": st3["bve_steps"],
+                   "subsumed_clauses": st3["sub_subsumedClauses"], "strengthened_literals": st3["sub_removedLiterals"], "eliminated_variables": st3["bve_eliminatedVars"],
+                   "gpu_launches": st3["gpu_launches"], "roofline": roofline_of([res3[-1][3]], peak, peak_src, traffic.get("k_full_c3_bytes_per_launch")),
+                   "section_seconds": time.time() - t0}
+            if not args.no_cpu_baseline:
+                sec["cpu_baseline"] = cpu_baseline(c3, Config("c3", max(1, c3.n // 10)))
+            line["c3"] = sec
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -245,6 +245,7 @@ int cp3g_bve_eval(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     g->bve_ns += t.collect();
+    g->bve_bytes += (int64_t)(np + nn) * (4 + 16 + 16) + (int64_t)nv * 32;      // per listed clause: reference, header, ~4 literals; one record per variable
     g->launches++; g->h2d += (int64_t)(nv * 12 + (np + nn) * 4); g->d2h += (int64_t)((size_t)nv * sizeof(cp3g_bve_rec) + (np + nn) * (4 + (p_stats ? 2 : 0)));
     g->ev_nv = nv;
     return CP3G_OK;
@@ -271,6 +272,7 @@ int cp3g_bve_stream(cp3g* g, uint32_t nsel, const uint32_t* sel, const uint64_t*
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     g->bve_ns += t.collect();
+    g->bve_bytes += (int64_t)(nres * 2 + nlit * 4);                               // the resolvents written
     g->launches++; g->h2d += (int64_t)nsel * 20; g->d2h += (int64_t)(nres * 2 + nlit * 4);
     return CP3G_OK;
 }

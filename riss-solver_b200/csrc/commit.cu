@@ -238,6 +238,9 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead_out, 
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
     g->commit_ns += t.collect();
+    // algorithmic bytes: the hits once per fixpoint round (12 B), per clause header + literals + death time + choice, per
+    // occurrence the pristine and the working list (read + written)
+    g->commit_bytes += 12ll * (int64_t)nh * 3 + (16ll + 8ll) * (int64_t)ncl + 4ll * (int64_t)g->nlits + 12ll * (int64_t)g->total_occ;
     g->sp_valid = true; g->sp_ndead = ndead;
     if (status) { *status = 0; }
     if (ndead_out) { *ndead_out = ndead; }

@@ -1382,7 +1382,9 @@ int cp3g_build(cp3g* g)
     int r = build_csr(g);
     t.stop();
     CK(cudaStreamSynchronize(g->stream));
-    t.collect();
+    g->build_ns += t.collect(); g->build_count++;
+    // algorithmic bytes of K1+K2: signature pass 16 + 4*#C per clause, list construction 2*4 per occurrence
+    g->build_bytes += 16ll * (int64_t)g->ncl + 4ll * (int64_t)g->nlits + 8ll * (int64_t)g->total_occ;
     return r;
 }
 
@@ -1606,9 +1608,11 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
     CK(cudaMemcpyAsync(cnt, g->counters.p, sizeof(cnt), cudaMemcpyDeviceToHost, g->stream));
     CK(cudaStreamSynchronize(g->stream));
     CK(cudaGetLastError());
-    g->scan_ns += t.collect();
+    const int64_t full_ns = t.collect();
+    g->scan_ns += full_ns;
     uint32_t n = cnt[0];
     uint64_t chk, ab; memcpy(&chk, &cnt[4], 8); memcpy(&ab, &cnt[6], 8);
+    { const int kk = kind == CP3G_SUBSUME ? 0 : 1; g->full_ns[kk] += full_ns; g->full_bytes[kk] += (int64_t)ab; g->full_checks[kk] += (int64_t)chk; g->full_launches[kk]++; }
     g->scan_requests += g->ncl; g->scan_checks += (int64_t)chk; g->scan_alg_bytes += (int64_t)ab;
     dlap("kernel+sync");
     if (out == nullptr) { if (nout) { *nout = n; } if (checks) { *checks = chk; } return CP3G_OK; }
@@ -1821,7 +1825,7 @@ int cp3g_ingest(cp3g* g, const int32_t* stream, size_t n, uint32_t* nvars, uint3
     if (nraw) { k_ing_pack<<<grid_for(nraw, 256), 256, 0, g->stream>>>(g->bu2.p, nraw, g->lits2.p, g->bu0.p, g->bu4.p, g->bu1.p, g->hdr.p, g->lits.p); g->launches++; }
     t.stop();
     int r = finish_upload(g, kept, total);
-    t.collect();
+    g->ingest_ns += t.collect(); g->ingest_bytes += 8ll * (int64_t)n + 16ll * (int64_t)g->ncl;        // 4 read + 4 written per stream literal, 16 per clause header
     if (r != CP3G_OK) { return r; }
     if (nvars) { *nvars = maxvar; } if (nclauses) { *nclauses = kept; } if (nlits) { *nlits = total; }
     if (status) { *status = 0; }
@@ -1904,6 +1908,20 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
     if (!strcmp(name, "scan_checks")) { return g->scan_checks; }
     if (!strcmp(name, "scan_ns")) { return g->scan_ns; }
     if (!strcmp(name, "commit_ns")) { return g->commit_ns; }
+    if (!strcmp(name, "commit_bytes")) { return g->commit_bytes; }
+    if (!strcmp(name, "build_ns")) { return g->build_ns; }
+    if (!strcmp(name, "build_bytes")) { return g->build_bytes; }
+    if (!strcmp(name, "build_count")) { return g->build_count; }
+    if (!strcmp(name, "ingest_ns")) { return g->ingest_ns; }
+    if (!strcmp(name, "ingest_bytes")) { return g->ingest_bytes; }
+    if (!strcmp(name, "bve_bytes")) { return g->bve_bytes; }
+    if (!strncmp(name, "full", 4) && (name[4] == '0' || name[4] == '1') && name[5] == '_') {
+        const int kk = name[4] - '0';
+        if (!strcmp(name + 6, "ns")) { return g->full_ns[kk]; }
+        if (!strcmp(name + 6, "bytes")) { return g->full_bytes[kk]; }
+        if (!strcmp(name + 6, "checks")) { return g->full_checks[kk]; }
+        if (!strcmp(name + 6, "launches")) { return g->full_launches[kk]; }
+    }
     if (!strcmp(name, "bve_ns")) { return g->bve_ns; }
     if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }

@@ -59,6 +59,10 @@ struct cp3g {
     uint32_t total_occ = 0;
     int rank = 0, world = 1; void* nccl = nullptr;
     int64_t launches = 0, kernel_ns = 0, h2d = 0, d2h = 0, scan_requests = 0, scan_checks = 0, scan_ns = 0, scan_alg_bytes = 0;
+    // per-kernel-family device times and ALGORITHMIC bytes for the roofline report: K1+K2 build, K0 ingest,
+    // k_full by kind (0 = K3 subsumption, 1 = K4 strengthening), device pass commit, K5'/K6'
+    int64_t build_ns = 0, build_bytes = 0, build_count = 0, ingest_ns = 0, ingest_bytes = 0, commit_bytes = 0, bve_bytes = 0;
+    int64_t full_ns[2] = {0, 0}, full_bytes[2] = {0, 0}, full_checks[2] = {0, 0}, full_launches[2] = {0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     uint32_t* pin_cnt = nullptr; cp3g_hit* pin_hits = nullptr;          // pinned: counters + the first PIN_HITS hits come back with one sync
     void fail(const char* what, cudaError_t e) { err = std::string(what) + ": " + cudaGetErrorString(e); fprintf(stderr, "cp3b200: CUDA error %s\n", err.c_str()); }
