@@ -1571,6 +1571,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
     DbgLap lap("str"); lap("prepare");
+    const bool fine = lap.on && getenv("CP3_DEBUG_FINE") != nullptr;          // per-entry timers (they cost as much as the entries)
     int64_t t0 = now_ns();
     // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
     // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
@@ -1699,11 +1700,78 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     }
     size_t ri = reals.size();                                       // reals[0..ri) are still ahead (the walk goes down)
     lap("reals");
+    // Walk plan of the real entries.  While the plan is valid (no unit, frozen counters, clean lists) the two list walks of an
+    // entry are a pure function of its content: the step count is the length of the two lists and the candidates that can
+    // hit are the cached hits in list order.  Both are evaluated here on all cores for the content the entry has NOW; the
+    // ordered walk below uses the record when the entry's turn comes and its content version is still the planned one, and
+    // then only validates and applies the candidate hits (the order-dependent part).  Everything else takes the walk itself.
+    struct PlanEnt { uint32_t ver, scan; int32_t min; uint32_t steps1, steps2, cb, c1, c2; uint32_t t; uint32_t lit_off, lit_n; int32_t alt; };
+    RawVec<PlanEnt> plan; std::vector<std::vector<Hit>> plan_c((size_t)nthreads + 1); std::vector<std::vector<PlanEnt>> plan_alt((size_t)nthreads + 1);
+    static const bool no_plan = getenv("CP3_NO_PLAN") != nullptr;
+    const bool planned = static_lazy && !no_plan && !reals.empty();
+    if (planned) {
+        const size_t nq = strq.size();
+        plan.resize(reals.size());
+        parallelFor(reals.size(), [&](size_t b, size_t e, int t) {
+            std::vector<Hit>& pc = plan_c[(size_t)t]; std::vector<PlanEnt>& pa = plan_alt[(size_t)t];
+            // the record of clause c with the content s2[0..n) whose cached hits are e0
+            auto build = [&](PlanEnt& pe, uint32_t c, const int32_t* s2, uint32_t n, const CacheEnt* e0) {
+                int minT = s2[0]; int best = dcount(minT >> 1);
+                for (uint32_t j = 1; j < n; ++j) { const int dj = dcount(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
+                const int mn = minT, nm = minT ^ 1;
+                if (hasStale(mn) || hasStale(nm)) { return; }
+                pe.scan = e0->scan; pe.t = (uint32_t)t;
+                pe.steps1 = hot[mn].n ? hot[mn].n - 1 : 0; pe.steps2 = hot[nm].n;
+                pe.cb = pe.c1 = pe.c2 = (uint32_t)pc.size();
+                if (e0->hb != e0->he) {
+                    const uint32_t* l1 = occ_pool.data() + occ[mn].off; const uint32_t n1 = hot[mn].n;
+                    for (uint32_t j = 0; j < n1; ++j) {
+                        if (l1[j] == c) { continue; }
+                        const Hit* h = findHit(c_str.hits, e0->hb, e0->he, l1[j]);
+                        if (h && h->lit != nm) { pc.push_back(*h); }
+                    }
+                    pe.c1 = (uint32_t)pc.size();
+                    const uint32_t* l2 = occ_pool.data() + occ[nm].off; const uint32_t n2 = hot[nm].n;
+                    for (uint32_t j = 0; j < n2; ++j) {
+                        const Hit* h = findHit(c_str.hits, e0->hb, e0->he, l2[j]);
+                        if (h && h->lit == nm) { pc.push_back(*h); }
+                    }
+                    pe.c2 = (uint32_t)pc.size();
+                }
+                pe.min = mn;
+            };
+            for (size_t i = b; i < e; ++i) {
+                PlanEnt& pe = plan[i]; pe.min = -1; pe.alt = -1; pe.lit_n = 0; pe.t = (uint32_t)t;
+                const size_t p2 = reals[i];
+                const uint32_t c = strq[p2];
+                const ClauseInfo ci = C[c];
+                pe.ver = ci.ver;
+                if ((ci.flag & (F_DEL | F_STR)) != F_STR || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
+                const CacheEnt* e0 = cached(c_str, c);
+                if (e0) { build(pe, c, pool.data() + ci.start, ci.size, e0); }
+                // a candidate target: also the shortened contents the closure predicted (records keyed by content)
+                if (((is_target[c >> 6] >> (c & 63)) & 1) && c < c_str.slot.size()) {
+                    for (int32_t k = c_str.slot[c]; k >= 0; k = c_str.ent[(size_t)k].next) {
+                        const CacheEnt& ce = c_str.ent[(size_t)k];
+                        if (ce.ver != UINT32_MAX || ce.lit_n < 2) { continue; }
+                        PlanEnt a; a.min = -1; a.ver = 0; a.alt = pe.alt; a.lit_off = ce.lit_off; a.lit_n = ce.lit_n;
+                        build(a, c, c_str.lits.data() + ce.lit_off, ce.lit_n, &ce);
+                        if (a.min >= 0) { pe.alt = (int32_t)pa.size(); pa.push_back(a); }
+                    }
+                }
+            }
+        }, 2048);
+    }
+    long cur_plan = -1;                                             // plan record of the entry being processed, if any
+    lap("plan");
     std::vector<uint32_t> localQueue;
     size_t end = strq.size();
     int ret = L_UNDEF; bool early = false;
     for (; end > 0 && (unlimited || str_steps < str_lim);) {
         uint32_t cr;
+        cur_plan = -1;
+        const int64_t tq0 = fine ? now_ns() : 0;
         if (localQueue.empty()) {
             if (static_lazy && hasToPropagate()) { cur_end = end; leaveLazy(); }
             if (static_lazy) {
@@ -1717,6 +1785,22 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 str_steps += run; n_lazy += (int64_t)(end - (size_t)(nxt + 1));
                 if (nxt < 0) { end = 0; cur_end = 0; break; }
                 end = (size_t)nxt + 1;                               // the shared code below steps onto it
+                if (planned && ri > 0 && (long)reals[ri - 1] == nxt) {
+                    cur_plan = (long)ri - 1;
+                    if (ri > 5) {                                    // look ahead: the clauses the next planned entries will edit
+                        const PlanEnt& pf = plan[ri - 5];
+                        if (pf.min >= 0) {
+                            const Hit* hc = plan_c[pf.t].data();
+                            for (uint32_t k = pf.cb; k < pf.c2; ++k) { const uint32_t o = hc[k].clause; __builtin_prefetch(&C[o]); if (o < log_head.size()) { __builtin_prefetch(&log_head[o]); } if (o < qtime.size()) { __builtin_prefetch(&qtime[o]); } if (o < shrunk_mark.size()) { __builtin_prefetch(&shrunk_mark[o]); } }
+                        }
+                    }
+                    if (ri > 2) {
+                        const PlanEnt& pf = plan[ri - 2];
+                        if (pf.min >= 0) { const Hit* hc = plan_c[pf.t].data(); for (uint32_t k = pf.cb; k < pf.c2; ++k) {
+                            const uint32_t o = hc[k].clause; __builtin_prefetch(pool.data() + C[o].start);
+                            if (o < qtime.size() && qtime[o] >= 0) { const size_t po = static_nq - 1 - (size_t)qtime[o]; if (po < contrib.size()) { __builtin_prefetch(&contrib[po]); __builtin_prefetch(&walk_min[po]); } } } }
+                    }
+                }
                 if (ri > 8) {                                        // look ahead: the clause, its counters and its scan record
                     const uint32_t c2 = strq[reals[ri - 8]]; const ClauseInfo& ci2 = C[c2];
                     __builtin_prefetch(&ci2);
@@ -1760,21 +1844,76 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
             }
         }
-        else { cr = localQueue.back(); localQueue.pop_back(); }
+        else {
+            cr = localQueue.back(); localQueue.pop_back();
+            // a clause that was strengthened after its own turn: the records of its predicted contents hang off its queue entry
+            if (planned && static_lazy && cr < qtime.size() && qtime[cr] >= 0) {
+                const uint32_t pos = (uint32_t)(static_nq - 1 - (size_t)qtime[cr]);
+                const auto it = std::lower_bound(reals.begin(), reals.end(), pos);
+                if (it != reals.end() && *it == pos) { cur_plan = (long)(it - reals.begin()); }
+            }
+        }
         if ((C[cr].flag & F_DEL) || !(C[cr].flag & F_STR)) { continue; }
         if (!opt.strength) { C[cr].flag &= ~F_STR; continue; }
         if (C[cr].size < 2) {
             if (C[cr].size == 1) { if (dataEnqueue(CL(cr)[0]) == L_FALSE) { break; } else { continue; } }
             else { ok = false; break; }
         }
-        int minT;
-        { const int32_t* s = CL(cr); minT = s[0];
+        // stage: how much of the two list walks the plan record has already done (0 none, 1 occ(min), 2 both)
+        int stage = 0; int minT = -1;
+        const int64_t tp0 = fine ? now_ns() : 0;
+        if (fine) { dbg_step_ns += tp0 - tq0; }
+        struct PlanT { int64_t t0; int64_t* acc; bool on; ~PlanT() { if (on) { *acc += now_ns() - t0; } } } plant{tp0, &dbg_plan_ns, fine && cur_plan >= 0};
+        if (cur_plan >= 0) {
+            const PlanEnt* pp = &plan[(size_t)cur_plan];
+            if (C[cr].ver != pp->ver || pp->min < 0) {             // not the planned content: one of the predicted versions?
+                const std::vector<PlanEnt>& pa = plan_alt[pp->t]; const PlanEnt* f = nullptr;
+                for (int32_t a = pp->alt; a >= 0; a = pa[(size_t)a].alt) {
+                    const PlanEnt& x = pa[(size_t)a];
+                    if (x.lit_n == C[cr].size && !memcmp(c_str.lits.data() + x.lit_off, CL(cr), sizeof(int32_t) * x.lit_n)) { f = &x; break; }
+                }
+                pp = f;
+                if (f) { ++n_spec_used; }
+            }
+            static const PlanEnt none{0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1};
+            const PlanEnt& pe = pp ? *pp : none;
+            if (pe.min >= 0 && static_valid && static_lazy && !hasToPropagate() && !hasStale(pe.min) && !hasStale(pe.min ^ 1) &&
+                (unlimited || str_steps + (int64_t)pe.steps1 + (int64_t)pe.steps2 + 1 < str_lim)) {
+                const Hit* hc = plan_c[pe.t].data();
+                minT = pe.min;
+                if (pe.cb == pe.c2) { ++n_fast; } else { ++n_slow; }
+                if (pre_active) { scanned_dyn[pe.min] = 1; }
+                str_steps += pe.steps1;
+                for (uint32_t k = pe.cb; k < pe.c1; ++k) {
+                    const uint32_t other = hc[k].clause;
+                    if (isDel(other) || !strHitValid(cr, other, hc[k].lit, pe.scan)) { continue; }
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == hc[k].lit) { pos = (int)k2; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+                stage = 1;
+                if (!hasToPropagate()) {
+                    if (pre_active) { scanned_dyn[pe.min ^ 1] = 1; }
+                    str_steps += pe.steps2;
+                    for (uint32_t k = pe.c1; k < pe.c2; ++k) {
+                        const uint32_t other = hc[k].clause;
+                        if (isDel(other) || !strHitValid(cr, other, hc[k].lit, pe.scan)) { continue; }
+                        const int32_t* t = CL(other); int pos = -1;
+                        for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == hc[k].lit) { pos = (int)k2; break; } }
+                        if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                    }
+                    stage = 2;
+                    if (!hasToPropagate()) { C[cr].flag &= ~F_STR; continue; }
+                }
+            }
+        }
+        if (stage == 0) { const int32_t* s = CL(cr); minT = s[0];
           for (uint32_t j = 1; j < C[cr].size; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
         const int min = minT, nmin = lneg(minT);
-        const int64_t th0 = lap.on ? now_ns() : 0;
+        const int64_t th0 = fine ? now_ns() : 0;
         const CacheEnt* e = strHits(cr);
-        if (lap.on) { dbg_hits_ns += now_ns() - th0; }
-        if (e->hb == e->he && !hasStale(min) && !hasStale(nmin) && !hasToPropagate() &&
+        if (fine) { dbg_hits_ns += now_ns() - th0; }
+        if (stage == 0 && e->hb == e->he && !hasStale(min) && !hasStale(nmin) && !hasToPropagate() &&
             (unlimited || str_steps + (int64_t)hot[min].n + (int64_t)hot[nmin].n < str_lim)) {
             // no candidate can hit and no list needs lazy cleaning: only the step counters move
             str_steps += (hot[min].n ? (int64_t)hot[min].n - 1 : 0) + (int64_t)hot[nmin].n;
@@ -1783,12 +1922,12 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             if (pre_active) { scanned_dyn[min] = 1; scanned_dyn[nmin] = 1; }    // walked (found nothing to do)
             continue;
         }
-        ++n_slow;
-        const int64_t ts0 = lap.on ? now_ns() : 0;
-        struct SlowT { int64_t t0; int64_t* acc; bool on; ~SlowT() { if (on) { *acc += now_ns() - t0; } } } slowt{ts0, &dbg_slow_ns, lap.on};
+        if (stage == 0) { ++n_slow; }
+        const int64_t ts0 = fine ? now_ns() : 0;
+        struct SlowT { int64_t t0; int64_t* acc; bool on; ~SlowT() { if (on) { *acc += now_ns() - t0; } } } slowt{ts0, &dbg_slow_ns, fine};
         if (pre_active) { scanned_dyn[min] = 1; }
         // pass 1: occ(min) - the complementary literal is any literal but min
-        {
+        if (stage < 1) {
             ListRef list = L(min);
             for (uint32_t j = 0; j < list.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list)[j];
@@ -1806,7 +1945,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 }
             }
         }
-        if (hasToPropagate()) {
+        if (stage < 2 && hasToPropagate()) {
             leaveLazy();
             static_valid = false;            // counts and lists move now: the precomputed entries are void
             rollbackPrecompact();
@@ -1815,7 +1954,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         }
         if (pre_active) { scanned_dyn[nmin] = 1; }
         // pass 2: occ(~min) - the complementary literal must be ~min
-        {
+        if (stage < 2) {
             ListRef list_neg = L(nmin);
             for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
                 const uint32_t other = LP(list_neg)[j];
@@ -1840,7 +1979,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         C[cr].flag &= ~F_STR;
     }
     lap("ordered");
-    if (lap.on) { fprintf(stderr, "  str slow entries %.1f ms, strHits %.1f ms\n", dbg_slow_ns / 1e6, dbg_hits_ns / 1e6); dbg_slow_ns = 0; dbg_hits_ns = 0; }
+    if (fine) { fprintf(stderr, "  str slow entries %.1f ms, strHits %.1f ms, stepping %.1f ms, planned entries (whole) %.1f ms\n", dbg_slow_ns / 1e6, dbg_hits_ns / 1e6, dbg_step_ns / 1e6, dbg_plan_ns / 1e6); dbg_slow_ns = 0; dbg_hits_ns = 0; dbg_step_ns = 0; dbg_plan_ns = 0; }
     if (!early) {
         updateOccurrences(useHeap, ignore);
         ret = ok ? L_UNDEF : L_FALSE;

@@ -249,7 +249,7 @@ private:
     bool pairs_single = false;                          // the pair-matrix path serves single variables only (fallback of the evaluation)
     int64_t n_eval_batches = 0, n_eval_used = 0, n_eval_host = 0, n_eval_stale = 0, n_stream_used = 0;
     int64_t n_scan_batches = 0, n_ondemand = 0, n_fast = 0, n_slow = 0, n_pair_batches = 0, n_resolve_batches = 0;
-    int64_t host_ns_commit = 0, host_ns_gpuwait = 0, dbg_slow_ns = 0, dbg_hits_ns = 0;
+    int64_t host_ns_commit = 0, host_ns_gpuwait = 0, dbg_slow_ns = 0, dbg_hits_ns = 0, dbg_step_ns = 0, dbg_plan_ns = 0;
     int64_t ph_init = 0, ph_sub = 0, ph_str = 0, ph_prefetch = 0, ph_total = 0, ph_upload = 0, ph_download = 0, ph_simplify = 0;
 
     // ---------------- basics
