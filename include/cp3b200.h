@@ -147,6 +147,14 @@ int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p
 int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs,
                      const uint32_t* n_refs, const uint64_t* out_off, int32_t* out_lits, size_t nlits);
 
+/* K9: stand-alone blocked clause elimination (coprocessor/techniques/BCE.cc:239-601).  Replaces every call of
+ * BlockedClauseElimination::tautologicResolvent (BCE.cc:624-646) of one BCE run: variable i owns pos refs p_off[i]..p_off[i+1]
+ * and neg refs n_off[i]..n_off[i+1] (host list order); row a of variable i is the W_i = ceil(nneg_i / 32) words
+ * masks[word_off[i] + a*W_i ..), bit b of the row is set iff the resolvent of pos clause a and neg clause b on vars[i] is NOT a
+ * tautology.  word_off[nv] = total number of words. */
+int cp3g_bce_masks(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
+                   const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* word_off, uint32_t* masks);
+
 /* K5': the whole per-variable evaluation of bve_worker (BVE.cc:388-637) for a batch of candidate variables, one warp each
  * (bve_eval.cu): gate detection with list reordering (findGates, BVE.cc:1143-1267; use_gates = -bve_gates), lazy removal of the
  * deleted entries by swap-with-last (BVE.cc:474-489), resolvent anticipation over the pairs the gate limits leave

@@ -57,6 +57,7 @@ struct cp3o {
     int bve_unlimited, bve_strength, bve_gates, bve_force_gates, bve_fdepOnly, bve_heap;
     int bve_cgrow, bve_cgrow_t, bve_BCElim, bve_heap_updates, bve_early, bce_only;
     int opt_dense, dense_frag, dense_keep_set;   /* CP3Config.cc:100,344,345 */
+    int opt_bce, bce_compl, bce_binary; int64_t bce_limit;   /* -bce, -bce-compl, -bce-bin, -bce-limit (CP3Config.cc:86,266-268) */
     double gc_frac;
     /* solver side (riss/core/Solver.h): assignment, trail, clauses vector, arena accounting */
     int nvars, ok, qhead;
@@ -76,7 +77,8 @@ struct cp3o {
     ivec subq, strq, undo;
     uint32_t* modTimer; uint32_t modStep;
     /* techniques */
-    tech_t t_sub, t_up, t_bve;
+    tech_t t_sub, t_up, t_bve, t_bce;
+    int bce_steps, bce_testedLits, bce_remBCE;  /* BCE.h:39-41 */
     int64_t sub_steps, str_steps, sub_lim, str_lim; int limitIncreases;
     int subsumedClauses, subsumedLiterals, removedLiterals;
     int up_last, up_removedClauses, up_removedLiterals;
@@ -1063,6 +1065,138 @@ static int bve_process(cp3o* o)
 
 /* ------------------------------------------------------------------ driver */
 /* Solver::simplify at level 0 (Solver.cc:2212-2268): drop satisfied clauses, keep false literals */
+/* ------------------------------------------------------------------ stand-alone BCE (coprocessor/techniques/BCE.cc)
+ * blocked clause elimination proper (-bce with the defaults -bce-bce -no-bce-cle -no-bce-cla -no-bce-bcm) */
+/* tautologicResolvent, BCE.cc:624-646: 1 iff resolving c (holds l) with d (holds ~l) on l gives a tautology */
+static int tautologic_resolvent(cp3o* o, int c, int d, int l)
+{
+    const int* C = CL(o, c); const int* D = CL(o, d); const int cn = o->csize[c], dn = o->csize[d];
+    int i = 0, j = 0;
+    while (i < cn && j < dn) {
+        if (C[i] == l) { i++; }
+        else if (D[j] == LNEG(l)) { j++; }
+        else if (C[i] == D[j]) { i++; j++; }
+        else if (C[i] == LNEG(D[j])) { return 1; }
+        else if (C[i] < D[j]) { i++; }
+        else { j++; }
+    }
+    return 0;
+}
+/* Riss::Heap<LitOrderBCEHeapLt> (riss/mtl/Heap.h:37-183, BCE.h:27-36): min-heap of literals keyed by the
+ * occurrence count of the complement (-bce-compl) or of the literal itself */
+typedef struct { int* h; int n; int* idx; } lheap_t;
+static inline int lheap_lt(const cp3o* o, int x, int y) { return o->bce_compl ? o->cnt[LNEG(x)] < o->cnt[LNEG(y)] : o->cnt[x] < o->cnt[y]; }
+static void lheap_up(cp3o* o, lheap_t* H, int i)
+{
+    int x = H->h[i], p = (i - 1) >> 1;
+    while (i != 0 && lheap_lt(o, x, H->h[p])) { H->h[i] = H->h[p]; H->idx[H->h[p]] = i; i = p; p = (p - 1) >> 1; }
+    H->h[i] = x; H->idx[x] = i;
+}
+static void lheap_down(cp3o* o, lheap_t* H, int i)
+{
+    int x = H->h[i];
+    while (2 * i + 1 < H->n) {
+        int l = 2 * i + 1, r = 2 * i + 2;
+        int child = (r < H->n && lheap_lt(o, H->h[r], H->h[l])) ? r : l;
+        if (!lheap_lt(o, H->h[child], x)) { break; }
+        H->h[i] = H->h[child]; H->idx[H->h[i]] = i; i = child;
+    }
+    H->h[i] = x; H->idx[x] = i;
+}
+static void lheap_insert(cp3o* o, lheap_t* H, int x) { H->idx[x] = H->n; H->h[H->n++] = x; lheap_up(o, H, H->idx[x]); }
+static int lheap_remove_min(cp3o* o, lheap_t* H)
+{
+    int x = H->h[0];
+    H->h[0] = H->h[H->n - 1]; H->idx[H->h[0]] = 0; H->idx[x] = -1; H->n--;
+    if (H->n > 1) { lheap_down(o, H, 0); }
+    return x;
+}
+/* blockedClauseElimination, BCE.cc:239-601 */
+static void blocked_clause_elimination(cp3o* o)
+{
+    const int nl = 2 * o->nvars;
+    lheap_t H; H.h = (int*)malloc(sizeof(int) * (size_t)(nl + 1)); H.idx = (int*)malloc(sizeof(int) * (size_t)(nl + 1)); H.n = 0;
+    for (int x = 0; x < nl; ++x) { H.idx[x] = -1; }
+    uint32_t* nextRound = (uint32_t*)calloc((size_t)nl + 1, sizeof(uint32_t)); uint32_t nr_step = 0;   /* MarkArray: all "current" at step 0 */
+    ivec nextRoundLits = {0, 0, 0};
+    for (int v = 0; v < o->nvars; ++v) {
+        if (o->frozen[v]) { continue; }
+        if (o->cnt[2 * v] > 0) { iv_push(&nextRoundLits, 2 * v); }
+        if (o->cnt[2 * v + 1] > 0) { iv_push(&nextRoundLits, 2 * v + 1); }
+    }
+    ++o->ma_step;                                           /* data.ma.nextStep(), BCE.cc:269 */
+    do {
+        for (int i = 0; i < nextRoundLits.n; ++i) {
+            const int l = nextRoundLits.v[i];
+            if (nextRound[l] != nr_step) { continue; }
+            lheap_insert(o, &H, l);
+        }
+        nextRoundLits.n = 0;
+        ++nr_step;
+        while (H.n > 0 && (!o->limited || o->bce_limit > o->bce_steps)) {
+            const int right = lheap_remove_min(o, &H);
+            if (o->frozen[LVAR(right)] || value_lit(o, right) != L_UNDEF) { continue; }
+            o->bce_testedLits++;
+            const int left = LNEG(right);
+            for (int i = 0; i < o->occ[right].n; ++i) {
+                if (has_to_propagate(o)) { break; }
+                const int c = o->occ[right].v[i];
+                if ((o->cflag[c] & F_DEL) || (!o->bce_binary && o->csize[c] == 2)) { continue; }
+                int isBlocked = (o->csize[c] > 2 || o->bce_binary);
+                if (!isBlocked) { break; }
+                for (int j = 0; j < o->occ[left].n; ++j) {
+                    if (has_to_propagate(o)) { break; }
+                    const int d = o->occ[left].v[j];
+                    if (o->cflag[d] & F_DEL) { continue; }
+                    o->bce_steps++;
+                    if (!tautologic_resolvent(o, c, d, right)) { isBlocked = 0; break; }
+                }
+                if (isBlocked) {
+                    o->cflag[c] |= F_DEL;
+                    removed_clause(o, c, 0, 0, VAR_UNDEF);
+                    o->bce_remBCE++;
+                    const int* l = CL(o, c);
+                    for (int k = 0; k < o->csize[c]; ++k) {
+                        const int nk = LNEG(l[k]);
+                        if (H.idx[nk] >= 0) { lheap_up(o, &H, H.idx[nk]); lheap_down(o, &H, H.idx[nk]); }
+                        else if (nextRound[nk] != nr_step) { iv_push(&nextRoundLits, nk); nextRound[nk] = nr_step; }
+                    }
+                    successful(&o->t_bce);
+                    ext_clause(o, c, right);
+                }
+                if (has_to_propagate(o)) {
+                    int prev = o->occ[right].n;
+                    propagation_process(o, 1, 0, VAR_UNDEF);
+                    o->t_bce.modified = o->t_bce.modified || o->t_up.modified;
+                    if (!o->ok) { goto done; }
+                    if (prev != o->occ[right].n) { i = -1; }
+                }
+            }
+            if (has_to_propagate(o)) {
+                propagation_process(o, 1, 0, VAR_UNDEF);
+                o->t_bce.modified = o->t_bce.modified || o->t_up.modified;
+                if (!o->ok) { goto done; }
+            }
+        }
+        check_garbage(o);
+    } while (nextRoundLits.n > 0 && (!o->limited || o->bce_limit > o->bce_steps));
+done:
+    free(H.h); free(H.idx); free(nextRound); iv_release(&nextRoundLits);
+}
+/* BlockedClauseElimination::process, BCE.cc:604-622 */
+static int bce_process(cp3o* o)
+{
+    if (!perform_simplification(&o->t_bce)) { return 0; }
+    o->t_bce.modified = 0;
+    /* (the size gate needs nTotLits() > cp3_bce_lits, which is 0 after cleanSolver: it never fires, like cp3_susi_* / cp3_bve_*) */
+    propagation_process(o, 1, 0, VAR_UNDEF);
+    o->t_bce.modified = o->t_bce.modified || o->t_up.modified;
+    if (!o->ok) { return o->t_bce.modified; }
+    blocked_clause_elimination(o);
+    return o->t_bce.modified;
+}
+
+
 static int solver_simplify(cp3o* o)
 {
     if (!o->ok) { return 0; }
@@ -1227,6 +1361,11 @@ void cp3o_preprocess(cp3o* o)
             check_garbage(o);
         }
         if (!o->ok) { break; }
+        if (o->opt_bce) {                                  /* Coprocessor.cc:345-352 */
+            if (status == L_UNDEF) { bce_process(o); }
+            check_garbage(o);
+        }
+        if (!o->ok) { break; }
     }
     if (o->ok && has_to_propagate(o)) { propagation_process(o, 0, 0, VAR_UNDEF); }
     if (o->opt_dense) { dense_compress(o); }                                      /* Coprocessor.cc:492-496 */
@@ -1272,6 +1411,7 @@ int64_t cp3o_stat(const cp3o* o, const char* s)
     ST("bve_totallyAddedClauses", o->bve_totallyAdded) ST("bve_steps", o->bve_steps)
     ST("up_removedClauses", o->up_removedClauses) ST("up_removedLiterals", o->up_removedLiterals)
     ST("bve_foundGates", o->bve_foundGates)
+    ST("bce_steps", o->bce_steps) ST("bce_testedLits", o->bce_testedLits) ST("bce_remBCE", o->bce_remBCE)
 #undef ST
     return -1;
 }
@@ -1318,6 +1458,7 @@ cp3o* cp3o_new(void)
     o->strength = 1; o->sub_limit = 300000000; o->str_limit = 300000000; o->call_inc = 200;
     o->bve_limit = 25000000; o->bve_strength = 1; o->bve_gates = 1; o->bve_cgrow = 0; o->bve_cgrow_t = 1000;
     o->bve_heap_updates = 1;
+    o->bce_compl = 1; o->bce_limit = 100000000;
     o->gc_frac = 0.20;
     o->simpDB_assigns = -1;
     o->sub_lim = o->sub_limit; o->str_lim = o->str_limit;
@@ -1343,10 +1484,12 @@ int cp3o_option(cp3o* o, const char* opt)
     BOPT("bve_force_gates", bve_force_gates) BOPT("bve_fdepOnly", bve_fdepOnly) BOPT("bve_BCElim", bve_BCElim)
     BOPT("bve_early", bve_early) BOPT("bce_only", bce_only) BOPT("dense", opt_dense) BOPT("cp3_keep_set", dense_keep_set)
     IOPT("cp3_dense_frag", dense_frag)
+    BOPT("bce", opt_bce) BOPT("bce-compl", bce_compl) BOPT("bce-bin", bce_binary) IOPT("bce-limit", bce_limit)
     IOPT("cp3_iters", iters) IOPT("cp3_vars", cp3_vars) IOPT("cp3_cls", cp3_cls) IOPT("cp3_lits", cp3_lits)
     /* technique-level size gates: accepted, without effect (see subsumption_process) */
     if ((!strcmp(name, "cp3_susi_vars") || !strcmp(name, "cp3_susi_cls") || !strcmp(name, "cp3_susi_lits") ||
-         !strcmp(name, "cp3_bve_vars") || !strcmp(name, "cp3_bve_cls") || !strcmp(name, "cp3_bve_lits")) && eq) { return 1; }
+         !strcmp(name, "cp3_bve_vars") || !strcmp(name, "cp3_bve_cls") || !strcmp(name, "cp3_bve_lits") ||
+         !strcmp(name, "cp3_bce_vars") || !strcmp(name, "cp3_bce_cls") || !strcmp(name, "cp3_bce_lits")) && eq) { return 1; }
     IOPT("cp3_call_inc", call_inc) IOPT("cp3_bve_limit", bve_limit) IOPT("cp3_bve_heap", bve_heap)
     IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t) IOPT("bve_heap_updates", bve_heap_updates)
     if (!strcmp(name, "cp3_sub_limit") && eq) { o->sub_limit = o->sub_lim = val; return 1; }

@@ -163,6 +163,9 @@ int main(int argc, char** argv)
     fprintf(fo, "stat bve_totallyAddedClauses %d\n", pp->bve.totallyAddedClauses);
     fprintf(fo, "stat bve_steps %lld\n", (long long)pp->bve.stepper.getCurrentSteps());
     fprintf(fo, "stat bve_seconds %.6f\n", pp->bve.processTime);
+    fprintf(fo, "stat bce_steps %d\n", pp->bce.bceSteps);
+    fprintf(fo, "stat bce_testedLits %d\n", pp->bce.testedLits);
+    fprintf(fo, "stat bce_remBCE %d\n", pp->bce.remBCE);
     fprintf(fo, "stat up_removedClauses %d\n", pp->propagation.removedClauses);
     fprintf(fo, "stat up_removedLiterals %d\n", pp->propagation.removedLiterals);
     if (mode == "time") { fclose(fo); return 0; }

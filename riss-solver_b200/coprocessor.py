@@ -220,6 +220,22 @@ class ScanService:
                                        n_off.ctypes.data, n_refs.ctypes.data, pair_off.ctypes.data, sizes.ctypes.data), "bve_pairs")
         return pair_off, sizes[:int(pair_off[-1])]
 
+    def bce_masks(self, vars_, pos_lists, neg_lists):
+        """K9 (cp3g_bce_masks): per variable a bit matrix rows = pos clauses, columns = neg clauses; bit set iff the resolvent
+        is not a tautology (BCE.cc:624-646).  Returns (word_off, masks)."""
+        vars_ = np.ascontiguousarray(vars_, dtype=np.uint32)
+        p_off = np.zeros(vars_.size + 1, dtype=np.uint32); n_off = np.zeros(vars_.size + 1, dtype=np.uint32)
+        w_off = np.zeros(vars_.size + 1, dtype=np.uint64)
+        for i, (p, n) in enumerate(zip(pos_lists, neg_lists)):
+            p_off[i + 1] = p_off[i] + len(p); n_off[i + 1] = n_off[i] + len(n)
+            w_off[i + 1] = w_off[i] + len(p) * ((len(n) + 31) // 32)
+        cat = lambda ls: np.ascontiguousarray(np.concatenate([np.asarray(x, dtype=np.uint32) for x in ls]) if len(ls) else np.zeros(0, np.uint32), dtype=np.uint32)
+        p_refs = cat(pos_lists); n_refs = cat(neg_lists)
+        masks = np.zeros(max(int(w_off[-1]), 1), dtype=np.uint32)
+        self._ck(self.L.cp3g_bce_masks(self.g, vars_.size, vars_.ctypes.data, p_off.ctypes.data, p_refs.ctypes.data,
+                                       n_off.ctypes.data, n_refs.ctypes.data, w_off.ctypes.data, masks.ctypes.data), "bce_masks")
+        return w_off, masks[:int(w_off[-1])]
+
     def bve_eval(self, vars_, pos_lists, neg_lists, use_gates=True, stream=True):
         """K5'/K6' (cp3g_bve_eval / cp3g_bve_stream): per variable the record (p_limit, n_limit, pos_n, neg_n, resolvents, lit_clauses,
         steps, flags), the rewritten lists, the per-clause statistics and - for every variable without the HOST flag - its resolvents"""

@@ -43,6 +43,7 @@ struct Options {
     int bve_heap = 0, bve_cgrow = 0, bve_cgrow_t = 1000, bve_heap_updates = 1;
     int threads = 0;
     bool stats = false;
+    bool bce = false, bce_bce = true, bce_compl = true, bce_binary = false; int64_t bce_limit = 100000000;   // -bce, -bce-bce, -bce-compl, -bce-bin, -bce-limit (CP3Config.cc:86,266-269)
     bool dense = false, dense_keep_set = false; int dense_frag = 0;   // -dense, -cp3_keep_set, -cp3_dense_frag (CP3Config.cc:100,344,345)
     double gc_frac = 0.20;
     int device = 0;              // -cp3_gpu_device=N
@@ -141,7 +142,8 @@ private:
     std::vector<uint32_t> ma; uint32_t ma_step = 0;
 
     // ---------------- technique state
-    Tech t_sub, t_up, t_bve;
+    Tech t_sub, t_up, t_bve, t_bce;
+    int bce_steps = 0, bce_testedLits = 0, bce_remBCE = 0; int64_t n_bce_batches = 0, n_bce_rows = 0;
     int64_t sub_steps = 0, str_steps = 0, sub_lim = 0, str_lim = 0; int limitIncreases = 0;
     int subsumedClauses = 0, subsumedLiterals = 0, removedLiterals = 0;
     int up_last = 0, up_removedClauses = 0, up_removedLiterals = 0;
@@ -157,7 +159,7 @@ private:
     // ---------------- device replica + scan cache
     cp3g* gpu = nullptr;
     bool dev_uploaded = false;
-    int64_t n_compactions = 0, n_bulk_ingests = 0, n_tfast = 0;
+    int64_t n_gc = 0, n_compactions = 0, n_bulk_ingests = 0, n_tfast = 0;
     uint32_t dev_arena_ncl = 0; bool dev_arena_valid = false;       // the device still holds the arena of the bulk ingest
     struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
     std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
@@ -336,6 +338,16 @@ private:
     void bvePrefetchStep();
     void sequentiellBVE();
     int bveProcess();
+    // stand-alone blocked clause elimination (coprocessor/techniques/BCE.cc).  K9 (cp3g_bce_masks) answers every
+    // tautologicResolvent() of the run at once: one bit per (clause with v, clause with ~v); clause contents and list orders
+    // do not change during BCE, so the masks of one batch serve all rounds.
+    RawVec<uint32_t> bce_masks; RawVec<uint64_t> bce_woff;      // per variable: first mask word, or UINT64_MAX (no mask: row on demand)
+    std::vector<uint32_t> bce_row; int bce_row_var = -1; uint32_t bce_row_idx = 0;
+    void bceBuildMasks();
+    const uint32_t* bceRow(int v, uint32_t posIdx);        // mask row of the posIdx-th clause of occ(+v) over occ(~v)
+    bool bceNonTaut(int right, uint32_t i, uint32_t j);    // resolvent of occ(right)[i] with occ(~right)[j] on right is not a tautology
+    void blockedClauseElimination();
+    bool bceProcess();
     uint32_t nextModStep();
     void addClausesToSubsumption(int x);
     void addTouchedToSubsumption();

@@ -1923,6 +1923,8 @@ int64_t cp3g_counter(const cp3g* g, const char* name)
         if (!strcmp(name + 6, "launches")) { return g->full_launches[kk]; }
     }
     if (!strcmp(name, "bve_ns")) { return g->bve_ns; }
+    if (!strcmp(name, "bce_ns")) { return g->bce_ns; }
+    if (!strcmp(name, "bce_bytes")) { return g->bce_bytes; }
     if (!strcmp(name, "scan_alg_bytes")) { return g->scan_alg_bytes; }
     if (!strcmp(name, "nclauses")) { return g->ncl; }
     if (!strcmp(name, "nlits")) { return (int64_t)g->nlits; }

@@ -55,6 +55,7 @@ struct cp3g {
     const int32_t* sp_dtime = nullptr; bool sp_valid = false; uint32_t sp_ndead = 0; int64_t commit_ns = 0;
     // device-side BVE evaluation (bve_eval.cu): the batch stays resident between cp3g_bve_eval and cp3g_bve_stream
     DevBuf<unsigned char> ev_recs; DevBuf<uint16_t> ev_pst, ev_nst, ev_rsz; DevBuf<unsigned long long> ev_loff; uint32_t ev_nv = 0; int64_t bve_ns = 0;
+    int64_t bce_ns = 0, bce_bytes = 0;                                 // K9 (bce.cu)
     std::vector<uint32_t> ovf_host;
     uint32_t total_occ = 0;
     int rank = 0, world = 1; void* nccl = nullptr;

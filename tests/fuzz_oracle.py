@@ -30,6 +30,12 @@ OPTSETS = [
     # size gates (Coprocessor.cc:1002-1006): sized to fire on part of the random instances
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-cp3_lits=400"],
     ["-enabled_cp3", "-subsimp", "-cp3_cls=150", "-cp3_vars=40"],
+    # stand-alone blocked clause elimination (BCE.cc), alone and behind the other techniques as in Riss427
+    ["-enabled_cp3", "-bce"],
+    ["-enabled_cp3", "-up", "-subsimp", "-bve", "-bce", "-no-cp3_limited"],
+    ["-enabled_cp3", "-bce", "-bce-bin", "-no-bce-compl"],
+    ["-enabled_cp3", "-subsimp", "-bce", "-bce-limit=30", "-cp3_iters=2"],
+    ["-enabled_cp3", "-bve", "-bce", "-dense", "-cp3_bce_vars=3", "-cp3_bce_cls=3", "-cp3_bce_lits=3"],
 ]
 
 

@@ -58,6 +58,15 @@ l, s = gen.community_ksat(400, 1800, seed=20260001)
 st = gen.csr_to_stream(l, s)
 for tag, o in (("susi", SUSI), ("full", FULL), ("bve", BVE), ("dense", DENSE), ("dense_frag", DENSE + ["-cp3_dense_frag=30"])):
     add(f"community_{tag}", st, o)
+# stand-alone blocked clause elimination (BCE.cc) and the Riss427-style pipeline around it
+BCE = ["-enabled_cp3", "-bce"]
+R427 = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-bce", "-dense", "-no-cp3_limited"]
+add("regression_sat_bce", dimacs(os.path.join(ref_cnfs, "sat.cnf")), BCE)
+add("community_bce", st, BCE)
+add("community_riss427", st, R427)
+l, s = gen.random_ksat(300, 1278, 3, seed=2, dup=0.04, sup=0.06, flip=0.06)
+add("planted3sat_s2_bce", gen.csr_to_stream(l, s), BCE)
+add("planted3sat_s2_bce_bin", gen.csr_to_stream(l, s), BCE + ["-bce-bin", "-no-bce-compl"])
 # variable gaps in the input: Dense without any simplification
 add("gaps_dense_only", np.array([3, -7, 0, 7, 12, -20, 0, -3, 20, 0], np.int32), ["-enabled_cp3", "-dense"])
 l, s = gen.random_ksat(200, 900, 3, seed=777, zipf_s=1.1)

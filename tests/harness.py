@@ -71,7 +71,7 @@ STAT_NAMES = ["sub_subsumedClauses", "sub_subsumedLiterals", "sub_removedLiteral
               "sub_strengthSteps", "bve_eliminatedVars", "bve_createdClauses", "bve_removedClauses",
               "bve_testedVars", "bve_anticipations", "bve_skippedVars", "bve_unitsEnqueued",
               "bve_removedBC", "bve_totallyAddedClauses", "bve_steps", "up_removedClauses",
-              "up_removedLiterals"]
+              "up_removedLiterals", "bce_steps", "bce_testedLits", "bce_remBCE"]
 
 
 class Result:

@@ -220,6 +220,22 @@ int cp3g_bve_pairs(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p
     }
     return CP3G_OK;
 }
+int cp3g_bce_masks(cp3g* g, uint32_t nv, const uint32_t* vars, const uint32_t* p_off, const uint32_t* p_refs,
+                   const uint32_t* n_off, const uint32_t* n_refs, const uint64_t* word_off, uint32_t* masks)
+{
+    g->launches++;
+    for (uint32_t i = 0; i < nv; ++i) {
+        const uint32_t np = p_off[i + 1] - p_off[i], nn = n_off[i + 1] - n_off[i], W = (nn + 31) / 32;
+        for (uint32_t a = 0; a < np; ++a) {
+            for (uint32_t w = 0; w < W; ++w) { masks[word_off[i] + (uint64_t)a * W + w] = 0; }
+            for (uint32_t b = 0; b < nn; ++b) {
+                const uint32_t p = p_refs[p_off[i] + a], n = n_refs[n_off[i] + b];
+                if (res_size(g->cl[p], g->cl[n], (int32_t)(vars[i] << 1), nullptr) >= 0) { masks[word_off[i] + (uint64_t)a * W + (b >> 5)] |= 1u << (b & 31); }
+            }
+        }
+    }
+    return CP3G_OK;
+}
 int cp3g_bve_resolve(cp3g* g, uint32_t npairs, const uint32_t* vars, const uint32_t* p_refs, const uint32_t* n_refs,
                      const uint64_t* out_off, int32_t* out_lits, size_t)
 {

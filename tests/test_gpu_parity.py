@@ -293,6 +293,38 @@ def test_engine_compacts_the_arena_in_bve_runs(gen):
     assert hit > 0
 
 
+def test_k9_blocked_clause_masks_match_tautology_check(gen):
+    """K9 (cp3g_bce_masks) bit by bit against tautologicResolvent (BCE.cc:624-646) restated in numpy, including lists longer
+    than one mask word (Zipf skew) and the K5 sizes of the same pairs (-1 = tautology)"""
+    lits, sizes = gen.random_ksat(400, 6000, 3, seed=11, zipf_s=1.0, planted=False)
+    n = int(np.abs(lits).max())
+    codes = _sorted_clauses(lits, sizes); cstart = np.concatenate([[0], np.cumsum(sizes)])
+    svc = rs.ScanService(); svc.upload(n, codes, sizes); svc.build()
+    off, refs = svc.download_occ()
+    vs = np.arange(n, dtype=np.uint32)
+    pos = [refs[off[2 * v]:off[2 * v + 1]] for v in range(n)]
+    neg = [refs[off[2 * v + 1]:off[2 * v + 2]] for v in range(n)]
+    w_off, masks = svc.bce_masks(vs, pos, neg)
+    pair_off, sz = svc.bve_pairs(vs, pos, neg)
+    assert max(len(x) for x in neg) > 64                       # rows of several words are covered
+    checked = 0
+    for v in range(n):
+        W = (len(neg[v]) + 31) // 32
+        for a, p in enumerate(pos[v]):
+            P = codes[cstart[p]:cstart[p + 1]]
+            for b, q in enumerate(neg[v]):
+                Q = codes[cstart[q]:cstart[q + 1]]
+                taut = bool(np.isin(P[(P >> 1) != v] ^ 1, Q).any())
+                bit = (int(masks[int(w_off[v]) + a * W + (b >> 5)]) >> (b & 31)) & 1
+                assert bit == (0 if taut else 1), (v, a, b)
+                assert (int(sz[int(pair_off[v]) + a * len(neg[v]) + b]) == -1) == taut
+                checked += 1
+            # bits beyond the row's last column stay clear
+            if len(neg[v]) % 32:
+                assert int(masks[int(w_off[v]) + a * W + W - 1]) >> (len(neg[v]) % 32) == 0
+    assert checked > 20000
+
+
 def test_k5_resolvent_counts_match_oracle_snapshot(gen):
     lits, sizes = gen.community_ksat(3000, 12000, seed=4, planted=False)
     stream = gen.csr_to_stream(lits, sizes)
