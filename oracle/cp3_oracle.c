@@ -301,7 +301,25 @@ static void successful(tech_t* t) { t->modified = 1; t->peak = 0; }
 static inline int dcount(const cp3o* o, int v) { return o->cnt[2 * v] + o->cnt[2 * v + 1]; } /* data[Var] */
 static inline int heap_lt(const cp3o* o, int x, int y)
 {   /* CoprocessorTypes.h:493-500; live keys */
-    return o->bve_heap == 0 ? dcount(o, x) < dcount(o, y) : dcount(o, x) > dcount(o, y);
+    const int h = o->bve_heap;
+    if (h == 0) { return dcount(o, x) < dcount(o, y); }
+    if (h == 1) { return dcount(o, x) > dcount(o, y); }
+    /* options 3-10, CoprocessorTypes.h:503-536: polarity ratio of the variable combined with its occurrence count */
+    const double xp = o->cnt[2 * x], xn = o->cnt[2 * x + 1], yp = o->cnt[2 * y], yn = o->cnt[2 * y + 1];
+    double rx = 0, ry = 0;
+    if (xp != 0 || xn != 0) { rx = xp > xn ? (xn != 0 ? xp / xn : xp * 1000) : (xp != 0 ? xn / xp : xn * 1000); }
+    if (yp != 0 || yn != 0) { ry = yp > yn ? (yn != 0 ? yp / yn : yp * 1000) : (yp != 0 ? yn / yp : yn * 1000); }
+    const int dx = dcount(o, x), dy = dcount(o, y);
+    switch (h) {
+    case 3: return (rx < ry) || (rx == ry && dx < dy);
+    case 4: return (rx < ry) || (rx == ry && dx > dy);
+    case 5: return (rx > ry) || (rx == ry && dx < dy);
+    case 6: return (rx > ry) || (rx == ry && dx > dy);
+    case 7: return (dx < dy) || (rx < ry && dx == dy);
+    case 8: return (dx > dy) || (rx < ry && dx == dy);
+    case 9: return (dx < dy) || (rx > ry && dx == dy);
+    default: return (dx > dy) || (rx > ry && dx == dy);
+    }
 }
 static inline int in_heap(const cp3o* o, int v) { return v < o->hidx_n && o->hidx[v] >= 0; }
 static void heap_up(cp3o* o, int i)

@@ -45,7 +45,7 @@ int Options::parse(const char* o)
     IOPT("cp3_sub_limit", sub_limit) IOPT("cp3_str_limit", str_limit) IOPT("cp3_call_inc", call_inc)
     IOPT("cp3_bve_limit", bve_limit) IOPT("bve_cgrow", bve_cgrow) IOPT("bve_cgrow_t", bve_cgrow_t)
     IOPT("bve_heap_updates", bve_heap_updates) IOPT("cp3_gpu_device", device)
-    if (name == "cp3_bve_heap" && eq) { if (val != 0 && val != 1) { return -1; } bve_heap = (int)val; return 1; }
+    if (name == "cp3_bve_heap" && eq) { if (val < 0 || val > 10 || val == 2) { return -1; } bve_heap = (int)val; return 1; }   // 2 = random order, no heap
     // options of the path whose non-default values select code the GPU path does not provide
     if (name == "cp3_threads" && eq) { threads = (int)val; return 1; }      // pthread pool is replaced by the GPU
     if (name == "naive_strength") { return neg ? 1 : -1; }

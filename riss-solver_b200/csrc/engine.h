@@ -294,7 +294,29 @@ private:
     void removePosUnsorted(uint32_t c, int pos);
 
     // heap (riss/mtl/Heap.h)
-    bool heapLt(int x, int y) const { return opt.bve_heap == 0 ? dcount(x) < dcount(y) : dcount(x) > dcount(y); }
+    // VarOrderBVEHeapLt, CoprocessorTypes.h:493-547: -cp3_bve_heap=0 fewest occurrences first, 1 most first, 3-10 the polarity
+    // ratio of the variable combined with its occurrence count (2 = random order without a heap: not provided)
+    bool heapLt(int x, int y) const
+    {
+        const int h = opt.bve_heap;
+        if (h == 0) { return dcount(x) < dcount(y); }
+        if (h == 1) { return dcount(x) > dcount(y); }
+        const double xp = hot[2 * x].cnt, xn = hot[2 * x + 1].cnt, yp = hot[2 * y].cnt, yn = hot[2 * y + 1].cnt;
+        double rx = 0, ry = 0;
+        if (xp != 0 || xn != 0) { rx = xp > xn ? (xn != 0 ? xp / xn : xp * 1000) : (xp != 0 ? xn / xp : xn * 1000); }
+        if (yp != 0 || yn != 0) { ry = yp > yn ? (yn != 0 ? yp / yn : yp * 1000) : (yp != 0 ? yn / yp : yn * 1000); }
+        const int dx = dcount(x), dy = dcount(y);
+        switch (h) {
+        case 3: return (rx < ry) || (rx == ry && dx < dy);
+        case 4: return (rx < ry) || (rx == ry && dx > dy);
+        case 5: return (rx > ry) || (rx == ry && dx < dy);
+        case 6: return (rx > ry) || (rx == ry && dx > dy);
+        case 7: return (dx < dy) || (rx < ry && dx == dy);
+        case 8: return (dx > dy) || (rx < ry && dx == dy);
+        case 9: return (dx < dy) || (rx > ry && dx == dy);
+        default: return (dx > dy) || (rx > ry && dx == dy);
+        }
+    }
     bool inHeap(int v) const { return v < (int)hidx.size() && hidx[v] >= 0; }
     void heapUp(int i); void heapDown(int i); void heapInsert(int v); void heapUpdate(int v);
     int heapRemoveMin(); void heapClear();

@@ -19,6 +19,9 @@ OPTSETS = [
     ["-enabled_cp3", "-subsimp", "-bve", "-no-bve_strength"],
     ["-enabled_cp3", "-subsimp", "-bve", "-cp3_bve_heap=1"],
     ["-enabled_cp3", "-subsimp", "-bve", "-bve_heap_updates=0"],
+    ["-enabled_cp3", "-subsimp", "-bve", "-cp3_bve_heap=3"],
+    ["-enabled_cp3", "-up", "-subsimp", "-bve", "-cp3_bve_heap=6", "-no-cp3_limited"],
+    ["-enabled_cp3", "-subsimp", "-bve", "-cp3_bve_heap=9", "-bve_heap_updates=2"],
     ["-enabled_cp3", "-subsimp", "-bve", "-bve_early"],
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-cp3_iters=2"],
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-dense", "-no-cp3_limited"],
