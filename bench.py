@@ -268,7 +268,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     # one engine per rank: split the host cores between the ranks of this node (the ordered commit uses a thread pool)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-    os.environ.setdefault("CP3_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // max(1, local_world)))))
+    os.environ.setdefault("CP3_THREADS", str(max(1, min(24, (os.cpu_count() or 1) // max(1, local_world)))))
     # a process that calls CPpreprocess repeatedly keeps the engine's work arrays in its heap (opt-in, capi.cpp)
     os.environ.setdefault("CP3_KEEP_HEAP", "1")
     import torch

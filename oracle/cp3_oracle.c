@@ -699,6 +699,69 @@ done_noupd:
     return ret;
 }
 
+/* fullStrengthening with -naive_strength, Subsumption.cc:1056-1197: the queue runs front to back; every literal of the
+ * strengthener is flipped in turn and the flipped clause is tested as a plain subset (the flipped literal must be found) */
+static int naive_strengthening(cp3o* o, int use_heap, int ignore)
+{
+    const int unlimited = !o->limited;
+    ivec localQueue = {0, 0, 0};
+    int ret = L_UNDEF;
+    for (int i = 0; i < o->strq.n;) {
+        int cr;
+        if (localQueue.n == 0) { cr = o->strq.v[i]; ++i; }
+        else { cr = localQueue.v[--localQueue.n]; }
+        if ((o->cflag[cr] & F_DEL) || !(o->cflag[cr] & F_STR)) { continue; }
+        if (!o->strength) { o->cflag[cr] &= ~F_STR; continue; }
+        const int cn = o->csize[cr];
+        int min = CL(o, cr)[0];
+        for (int j = 1; j < cn; ++j) {
+            const int x = CL(o, cr)[j];
+            if ((int64_t)o->cnt[min] * (cn - 1) + o->cnt[LNEG(min)] > (int64_t)o->cnt[x] * (cn - 1) + o->cnt[LNEG(x)]) { min = x; }
+        }
+        for (int j = 0; j < o->csize[cr] && (unlimited || o->str_steps < o->str_lim); ++j) {
+            const int neg_lit = LNEG(CL(o, cr)[j]);
+            CL(o, cr)[j] = neg_lit;
+            ivec* list = (neg_lit == LNEG(min)) ? &o->occ[neg_lit] : &o->occ[min];
+            for (int k = 0; k < list->n && (unlimited || o->str_steps < o->str_lim); ++k) {
+                const int other = list->v[k];
+                if (other == cr) { continue; }
+                o->str_steps++;
+                if (o->cflag[other] & F_DEL) { list->v[k] = list->v[list->n - 1]; list->n--; --k; continue; }
+                const int* c = CL(o, cr); const int* t = CL(o, other);
+                const int sn = o->csize[cr], tn = o->csize[other];
+                int l1 = 0, l2 = 0, pos = -1;
+                while (l1 < sn && l2 < tn) {
+                    if (c[l1] == t[l2]) { if (c[l1] == neg_lit) { pos = l2; } ++l1; ++l2; }
+                    else if (c[l1] < t[l2]) { break; }
+                    else { ++l2; }
+                }
+                if (l1 == sn && pos != -1) {
+                    ++o->removedLiterals;
+                    remove_pos_sorted(o, other, pos);
+                    o->t_sub.modified = 1;                               /* modifiedFormula = true: the penalty peak stays */
+                    if (o->csize[other] == 1) {
+                        o->cflag[other] |= F_DEL;
+                        data_enqueue(o, CL(o, other)[0]);
+                    } else {
+                        if (!(o->cflag[other] & F_SUB)) { o->cflag[other] |= F_SUB; iv_push(&o->subq, other); }
+                        if (!(o->cflag[other] & F_STR)) { iv_push(&localQueue, other); o->cflag[other] |= F_STR; }
+                        push_occ_update(o, other, neg_lit);
+                    }
+                }
+            }
+            CL(o, cr)[j] = LNEG(neg_lit);
+        }
+        if (has_to_propagate(o)) {
+            if (propagation_process(o, 1, 0, VAR_UNDEF) == L_FALSE) { o->ok = 0; ret = L_FALSE; goto done_noupd; }
+        }
+        o->cflag[cr] &= ~F_STR;
+    }
+    update_occurrences(o, use_heap, ignore);
+done_noupd:
+    iv_release(&localQueue);
+    return ret;
+}
+
 /* Subsumption::process, Subsumption.cc:85-180 */
 static int subsumption_process(cp3o* o, int doStrengthen, int use_heap, int ignore)
 {
@@ -721,7 +784,8 @@ static int subsumption_process(cp3o* o, int doStrengthen, int use_heap, int igno
         }
         if (o->strq.n > 0) {
             if (!doStrengthen) { clear_queue(o, &o->strq, F_STR); continue; }
-            strengthening_worker(o, use_heap, ignore);
+            if (o->naive_strength && o->all_strength_res == 0) { naive_strengthening(o, use_heap, ignore); }
+            else { strengthening_worker(o, use_heap, ignore); }
             clear_queue(o, &o->strq, F_STR);
         }
     }
@@ -1497,7 +1561,7 @@ int cp3o_option(cp3o* o, const char* opt)
 #define BOPT(n, f) if (!strcmp(name, n)) { o->f = !neg; return 1; }
 #define IOPT(n, f) if (!strcmp(name, n) && eq) { o->f = val; return 1; }
     BOPT("enabled_cp3", enabled) BOPT("up", opt_up) BOPT("subsimp", opt_subsimp) BOPT("bve", opt_bve)
-    BOPT("cp3_limited", limited) BOPT("cp3_strength", strength)
+    BOPT("cp3_limited", limited) BOPT("cp3_strength", strength) BOPT("naive_strength", naive_strength)
     BOPT("bve_unlimited", bve_unlimited) BOPT("bve_strength", bve_strength) BOPT("bve_gates", bve_gates)
     BOPT("bve_force_gates", bve_force_gates) BOPT("bve_fdepOnly", bve_fdepOnly) BOPT("bve_BCElim", bve_BCElim)
     BOPT("bve_early", bve_early) BOPT("bce_only", bce_only) BOPT("dense", opt_dense) BOPT("cp3_keep_set", dense_keep_set)

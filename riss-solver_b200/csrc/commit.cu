@@ -161,8 +161,8 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead_out, 
     cudaSetDevice(g->device);
     if (status) { *status = 1; }
     g->sp_valid = false;
-    if (g->world > 1 || g->ncl == 0) { return CP3G_OK; }             // sharded scans keep the host commit (hits are all-gathered)
-    // K3 over the full queue; the hits stay on the device
+    if (g->ncl == 0) { return CP3G_OK; }
+    // K3 over the full queue (sharded: this rank's slice of the tile table); the hits stay on the device
     uint32_t nh = 0; uint64_t chk = 0;
     uint32_t cap = (uint32_t)std::max<size_t>(g->hits.cap ? g->hits.cap - 1 : 0, std::max<size_t>(4096, g->ncl / 8));
     for (;;) {
@@ -170,6 +170,17 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead_out, 
         if (r != CP3G_OK) { return r; }
         if (nh <= cap) { break; }
         cap = nh + nh / 8 + 1024;
+    }
+    if (g->world > 1) {
+        // exchange step of the sharded pass: the slices' hit lists are all-gathered over NCCL on the stream that
+        // produced them and never leave the device; every rank then runs the commit kernels below on the identical list (the
+        // fixpoint over death times is independent of the order of the hits), so the replicas stay bit-identical
+        const cp3g_hit* all = nullptr; uint32_t total = 0;
+        int r = cp3g_nccl_gather_hits_device(g->nccl, g->stream, g->hits.p, nh, &all, &total, &chk);
+        if (r != CP3G_OK) { g->err = "nccl all-gather-v (K3 hits, device) failed"; return CP3G_ERR_CUDA; }
+        RESERVE(g->hits, (size_t)total + 1, false);
+        if (total) { CK(cudaMemcpyAsync(g->hits.p, all, (size_t)total * sizeof(cp3g_hit), cudaMemcpyDeviceToDevice, g->stream)); }
+        nh = total;
     }
     if (!g->ovf_host.empty() || g->ncl_csr != g->ncl || !g->total_occ) { return CP3G_OK; }
     const uint32_t ncl = g->ncl, nlit = 2 * g->nvars;

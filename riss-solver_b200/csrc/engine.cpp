@@ -48,7 +48,7 @@ int Options::parse(const char* o)
     if (name == "cp3_bve_heap" && eq) { if (val < 0 || val > 10 || val == 2) { return -1; } bve_heap = (int)val; return 1; }   // 2 = random order, no heap
     // options of the path whose non-default values select code the GPU path does not provide
     if (name == "cp3_threads" && eq) { threads = (int)val; return 1; }      // pthread pool is replaced by the GPU
-    if (name == "naive_strength") { return neg ? 1 : -1; }
+    BOPT("naive_strength", naive_strength)
     if (name == "all_strength_res" && eq) { return val == 0 ? 1 : -1; }
     if (name == "cp3_inpPrefL" || name == "cp3_lock_stats" || name == "bve_progress" || name == "bve_totalG") { return 1; }
     if ((name == "cp3_par_strength" || name == "cp3_par_subs" || name == "par_subs_counts" || name == "susi_chunk_size" ||
@@ -145,7 +145,7 @@ Engine::Engine()
 {
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
     const char* e = getenv("CP3_THREADS");
-    nthreads = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    nthreads = e ? atoi(e) : (int)std::min(24u, std::max(1u, std::thread::hardware_concurrency()));
     if (nthreads < 1) { nthreads = 1; }
 }
 Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
@@ -1999,6 +1999,80 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     return ret;
 }
 
+// fullStrengthening with -naive_strength, Subsumption.cc:1056-1197: the queue runs front to back, every literal of the
+// strengthener is flipped in turn and the walk goes over occ(min) - or occ(~min) when the flipped literal is min itself.  The
+// candidates a walk can hit are the K4 hits of the strengthener whose literal is the flipped one (K4 finds every clause that
+// contains the strengthener with exactly one literal complemented, whichever list pair it scanned).
+int Engine::naiveStrengthening(bool useHeap, int ignore)
+{
+    PhaseTimer pt(ph_str);
+    const bool unlimited = !opt.limited;
+    ensureHostLists();
+    logClear(); dirty_str.clear();
+    if (str_prepared) { str_prepared = false; }
+    else if (opt.strength) {
+        std::vector<uint32_t> ids;
+        for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { ids.push_back(c); } }
+        sortUnique(ids);
+        c_str.clear();
+        scanClauses(CP3G_STRENGTHEN, ids, c_str);
+    } else { c_str.clear(); }
+    const int64_t t0 = now_ns();
+    std::vector<uint32_t> localQueue;
+    int ret = L_UNDEF; bool early = false;
+    for (size_t i = 0; i < strq.size();) {
+        uint32_t cr;
+        if (localQueue.empty()) { cr = strq[i]; ++i; }
+        else { cr = localQueue.back(); localQueue.pop_back(); }
+        if ((C[cr].flag & F_DEL) || !(C[cr].flag & F_STR)) { continue; }
+        if (!opt.strength) { C[cr].flag &= ~F_STR; continue; }
+        const uint32_t cn = C[cr].size;
+        int min = CL(cr)[0];
+        for (uint32_t j = 1; j < cn; ++j) {
+            const int x = CL(cr)[j];
+            if ((int64_t)hot[min].cnt * (cn - 1) + hot[min ^ 1].cnt > (int64_t)hot[x].cnt * (cn - 1) + hot[x ^ 1].cnt) { min = x; }
+        }
+        const CacheEnt* e = cn >= 2 ? strHits(cr) : nullptr;
+        const uint32_t hb = e ? e->hb : 0, he = e ? e->he : 0, escan = e ? e->scan : 0;
+        for (uint32_t j = 0; j < cn && (unlimited || str_steps < str_lim); ++j) {
+            const int neg_lit = CL(cr)[j] ^ 1;
+            const int lx = (neg_lit == (min ^ 1)) ? neg_lit : min;
+            for (uint32_t k = 0; k < hot[lx].n && (unlimited || str_steps < str_lim); ++k) {
+                const uint32_t other = occ_pool[occ[lx].off + k];
+                if (other == cr) { continue; }
+                str_steps++;
+                if (isDel(other)) { occSwapRemove(lx, k); --k; continue; }
+                if (hb == he) { continue; }
+                const Hit* h = findHit(c_str.hits, hb, he, other);
+                if (!h || h->lit != neg_lit || !strHitValid(cr, other, h->lit, escan)) { continue; }
+                const int32_t* t = CL(other); int pos = -1;
+                for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == neg_lit) { pos = (int)k2; break; } }
+                if (pos < 0) { continue; }
+                ++removedLiterals;
+                removePosSorted(other, pos);
+                noteShrunk(other, neg_lit, true);
+                dirty_str.push_back(other);
+                t_sub.modified = true;                               // modifiedFormula = true: the penalty peak stays as it is
+                if (C[other].size == 1) {
+                    setDeleted(other);
+                    dataEnqueue(CL(other)[0]);
+                } else {
+                    if (!(C[other].flag & F_SUB)) { C[other].flag |= F_SUB; subq.push_back(other); }
+                    if (!(C[other].flag & F_STR)) { localQueue.push_back(other); C[other].flag |= F_STR; }
+                    occ_upd.push_back({other, neg_lit});
+                }
+            }
+        }
+        if (hasToPropagate()) {
+            if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { ok = false; ret = L_FALSE; early = true; break; }
+        }
+        C[cr].flag &= ~F_STR;
+    }
+    if (!early) { updateOccurrences(useHeap, ignore); }
+    host_ns_commit += now_ns() - t0;
+    return ret;
+}
+
 // Subsumption::process, Subsumption.cc:85-180
 bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
 {
@@ -2022,7 +2096,7 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
         }
         if (!strq.empty()) {
             if (!doStrengthen) { clearQueue(strq, F_STR); continue; }
-            strengtheningWorker(useHeap, ignore);
+            if (opt.naive_strength) { naiveStrengthening(useHeap, ignore); } else { strengtheningWorker(useHeap, ignore); }
             clearQueue(strq, F_STR);
         }
         str_prepared = false;
@@ -2685,7 +2759,9 @@ void Engine::bveWorker()
     auto lapt = [&](int64_t& acc) { if (dbg) { const int64_t n2 = now_ns(); acc += n2 - tl; tl = n2; } };
     struct Rep { bool on; int64_t &tg, &tc, &ta, &tr, &trm, &ts; ~Rep() { if (on) { fprintf(stderr, "  bveWorker: heap+gates %.1f ms, clean %.1f, anticipate %.1f, resolveSet %.1f, removeClauses %.1f, inner subsumption %.1f\n", tg / 1e6, tc / 1e6, ta / 1e6, tr / 1e6, trm / 1e6, ts / 1e6); } } } rep{dbg, tg, tc, ta, tr, trm, ts};
     static const bool no_eval = getenv("CP3_NO_BVE_EVAL") != nullptr;
-    const bool use_eval = !no_eval && !opt.bve_early && !sharded;       // (-bve_early makes the anticipation depend on the global growth budget)
+    // (-bve_early makes the anticipation depend on the global growth budget; in sharded mode every rank evaluates the whole batch -
+    //  the replicas hold the identical data base, nothing has to be exchanged)
+    const bool use_eval = !no_eval && !opt.bve_early;
     pairs_single = use_eval;
     struct InWorker { bool& f; explicit InWorker(bool& x) : f(x) { f = true; } ~InWorker() { f = false; } } in_worker(in_bve_worker);
     static const bool no_pf = getenv("CP3_NO_BVE_PREFETCH") != nullptr;

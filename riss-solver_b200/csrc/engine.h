@@ -35,7 +35,7 @@ struct Options {
     bool enabled = false, up = false, subsimp = false, bve = false, limited = true;
     int iters = 1;
     int cp3_vars = 5000000, cp3_cls = 30000000, cp3_lits = 50000000;
-    bool strength = true;
+    bool strength = true, naive_strength = false;      // -cp3_strength, -naive_strength (CP3Config.cc:560-561)
     int64_t sub_limit = 300000000, str_limit = 300000000; int call_inc = 200;
     int64_t bve_limit = 25000000;
     bool bve_unlimited = false, bve_strength = true, bve_gates = true, bve_force_gates = false,
@@ -342,6 +342,7 @@ private:
     RawVec<int32_t> sub_dtime, sub_pos; RawVec<int32_t> dl_start; RawVec<uint32_t> dl_cnt; std::vector<uint64_t> dl_any;   // dl_any: bitmap of dl_cnt != 0 (cache resident)
     int64_t n_parsub = 0;
     int strengtheningWorker(bool useHeap, int ignore);
+    int naiveStrengthening(bool useHeap, int ignore);
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
     void updateOccurrences(bool useHeap, int ignore);
     bool subsumptionProcess(bool doStrengthen, bool useHeap, int ignore);

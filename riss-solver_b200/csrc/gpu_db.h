@@ -23,6 +23,8 @@ void  cp3g_nccl_free(void* comm);
 // all-gather-v of the ranks' hit lists (device buffer `dhits`, n local hits) into host `out`
 int   cp3g_nccl_gather_hits(void* comm, cudaStream_t st, const cp3g_hit* dhits, uint32_t n, uint32_t cap,
                             cp3g_hit* out, uint32_t* nout, uint64_t* checks);
+// the same exchange with the gathered list left on the device (*dout: communicator-owned buffer), for the device-side pass commit
+int   cp3g_nccl_gather_hits_device(void* comm, cudaStream_t st, const cp3g_hit* dhits, uint32_t n, const cp3g_hit** dout, uint32_t* total, uint64_t* checks);
 // in-place all-gather-v of a device buffer whose per-rank byte ranges [off[r], off[r+1]) are known to every rank
 int   cp3g_nccl_allgatherv_inplace(void* comm, cudaStream_t st, void* dbuf, const size_t* off);
 

@@ -56,22 +56,30 @@ extern "C" int cp3g_nccl_unique_id(void* out128)
     return CP3G_OK;
 }
 
+// One communicator per process and (rank, world): building it and its first collective (NCCL connects the peers lazily) cost a few
+// hundred milliseconds - as much as a whole simplification - so a process that creates several handles in a row (one per CPinit)
+// keeps the first one.  Every rank of the job takes the same decision, so the cached communicators stay matched; the unique id of
+// a later call is simply not used.
+static Comm* g_cached = nullptr;
+
 void* cp3g_nccl_create(int rank, int world, const void* id128)
 {
     Api* a = api();
     if (!a) { return nullptr; }
+    if (g_cached && g_cached->rank == rank && g_cached->world == world) { return g_cached; }
     Comm* c = new Comm();
     ncclUniqueId id; memcpy(&id, id128, sizeof(id));
     ncclResult_t r = a->CommInitRank(&c->comm, world, id, rank);
     if (r != 0) { fprintf(stderr, "cp3b200: ncclCommInitRank: %s\n", a->GetErrorString(r)); delete c; return nullptr; }
     c->rank = rank; c->world = world;
     if (cudaMalloc((void**)&c->dcounts, sizeof(uint32_t) * 4 * (size_t)(world + 1)) != cudaSuccess) { delete c; return nullptr; }
+    if (!g_cached) { g_cached = c; }
     return c;
 }
 
 void cp3g_nccl_free(void* comm)
 {
-    if (!comm) { return; }
+    if (!comm || comm == g_cached) { return; }              // the cached communicator lives as long as the process
     Comm* c = (Comm*)comm; Api* a = api();
     if (a && c->comm) { a->CommDestroy(c->comm); }
     if (c->dcounts) { cudaFree(c->dcounts); }
@@ -118,6 +126,44 @@ int cp3g_nccl_gather_hits(void* comm, cudaStream_t st, const cp3g_hit* dhits, ui
         if (cudaStreamSynchronize(st) != cudaSuccess) { return CP3G_ERR_CUDA; }
     }
     *nout = (uint32_t)total;
+    return CP3G_OK;
+}
+
+// all-gather-v of the ranks' hit lists that STAYS on the device (the device-side pass commit consumes it): counts by ncclAllGather,
+// payload as one grouped broadcast per rank, all enqueued on the stream of the kernel that produced the hits.  *dout points into a
+// buffer owned by the communicator; *total = number of hits of all ranks, *checks is replaced by the sum over the ranks.
+int cp3g_nccl_gather_hits_device(void* comm, cudaStream_t st, const cp3g_hit* dhits, uint32_t n, const cp3g_hit** dout, uint32_t* total_out, uint64_t* checks)
+{
+    Comm* c = (Comm*)comm; Api* a = api();
+    if (!c || !a) { return CP3G_ERR_NODEVICE; }
+    const int W = c->world;
+    uint32_t mine[4] = { n, (uint32_t)(*checks & 0xffffffffu), (uint32_t)(*checks >> 32), 0 };
+    uint32_t* dmine = c->dcounts + 4 * (size_t)W;
+    if (cudaMemcpyAsync(dmine, mine, sizeof(mine), cudaMemcpyHostToDevice, st) != cudaSuccess) { return CP3G_ERR_CUDA; }
+    if (a->AllGather(dmine, c->dcounts, 4, ncclUint32, c->comm, st) != 0) { return CP3G_ERR_CUDA; }
+    std::vector<uint32_t> all(4 * (size_t)W);
+    if (cudaMemcpyAsync(all.data(), c->dcounts, all.size() * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) { return CP3G_ERR_CUDA; }
+    if (cudaStreamSynchronize(st) != cudaSuccess) { return CP3G_ERR_CUDA; }      // the sizes of the payload: one small read
+    uint64_t total = 0, chk = 0;
+    std::vector<uint64_t> offs((size_t)W + 1, 0);
+    for (int r = 0; r < W; ++r) { offs[r] = total; total += all[4 * r]; chk += (uint64_t)all[4 * r + 1] | ((uint64_t)all[4 * r + 2] << 32); }
+    *checks = chk;
+    if (total > 0xfffffff0ull) { return CP3G_ERR_OVERFLOW; }
+    if (total > c->gather_cap) {
+        if (c->dgather) { cudaFree(c->dgather); }
+        c->gather_cap = total + total / 2 + 1024;
+        if (cudaMalloc((void**)&c->dgather, c->gather_cap * sizeof(cp3g_hit)) != cudaSuccess) { c->dgather = nullptr; c->gather_cap = 0; return CP3G_ERR_CUDA; }
+    }
+    if (total) {
+        a->GroupStart();
+        for (int r = 0; r < W; ++r) {
+            const size_t bytes = (size_t)all[4 * r] * sizeof(cp3g_hit);
+            if (!bytes) { continue; }
+            a->Broadcast(dhits, c->dgather + offs[r], bytes, ncclUint8, r, c->comm, st);
+        }
+        if (a->GroupEnd() != 0) { return CP3G_ERR_CUDA; }
+    }
+    *dout = c->dgather; *total_out = (uint32_t)total;
     return CP3G_OK;
 }
 

@@ -33,6 +33,9 @@ OPTSETS = [
     # size gates (Coprocessor.cc:1002-1006): sized to fire on part of the random instances
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-cp3_lits=400"],
     ["-enabled_cp3", "-subsimp", "-cp3_cls=150", "-cp3_vars=40"],
+    # naive strengthening (fullStrengthening, Subsumption.cc:1056-1197)
+    ["-enabled_cp3", "-subsimp", "-naive_strength"],
+    ["-enabled_cp3", "-up", "-subsimp", "-bve", "-naive_strength", "-no-cp3_limited"],
     # stand-alone blocked clause elimination (BCE.cc), alone and behind the other techniques as in Riss427
     ["-enabled_cp3", "-bce"],
     ["-enabled_cp3", "-up", "-subsimp", "-bve", "-bce", "-no-cp3_limited"],
