@@ -1062,22 +1062,23 @@ bool Engine::subsumptionCommitParallel()
     // step 0: queue position of every clause; a clause queued twice falls back to the ordered walk
     bool dups = false;
     bool increasing = true;                              // a queue in clause order (the first round) cannot hold duplicates
+    const size_t qgrain = 4096;                          // queues of later rounds are short: small chunks keep all cores busy
     parallelFor(nq, [&](size_t b, size_t e, int) {
         bool inc = true;
         for (size_t p = std::max<size_t>(b, 1); p < e && inc; ++p) { inc = subq[p - 1] < subq[p]; }
         if (!inc) { increasing = false; }
-    });
+    }, qgrain);
     if (increasing) {
-        parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = (int32_t)p; } });
+        parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = (int32_t)p; } }, qgrain);
     } else {
         parallelFor(nq, [&](size_t b, size_t e, int) {
             for (size_t p = b; p < e; ++p) {
                 const int32_t old = __atomic_exchange_n(&sub_pos[subq[p]], (int32_t)p, __ATOMIC_RELAXED);
                 if (old >= 0) { dups = true; }
             }
-        });
+        }, qgrain);
     }
-    auto reset_pos = [&]() { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = -1; } }); };
+    auto reset_pos = [&]() { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { sub_pos[subq[p]] = -1; } }, qgrain); };
     if (dups) { reset_pos(); return false; }
     lap("step0");
     // step 1: death times.  Entries with hits, in processing order (time = nq-1-position).
@@ -1101,6 +1102,7 @@ bool Engine::subsumptionCommitParallel()
         }
     }
     lap("step1");
+    if (dbg) { fprintf(stderr, "  parsub nq %zu hitters %zu dead %zu\n", nq, hitters.size(), dead.size()); }
     // step 2: per literal, the sorted death times of the clauses that contain it (bucketed by literal range,
     //         64-aligned so that no two buckets share a word of the stale bitmap)
     struct LT { int32_t lit, time; };
@@ -1111,11 +1113,16 @@ bool Engine::subsumptionCommitParallel()
     auto bucketOf = [&](int x) -> int { int bk = (int)std::min<size_t>((size_t)NB - 1, (size_t)x / bwidth); while (bk > 0 && x < bucketLo(bk)) { --bk; } while (bk + 1 < NB && x >= bucketLo(bk + 1)) { ++bk; } return bk; };
     std::vector<std::vector<LT>> dlb((size_t)NB);
     if (dl_start.size() < nlit) { pfill(dl_start, nlit, -1); pfill(dl_cnt, nlit, 0u); dl_any.assign((nlit >> 6) + 1, 0ull); }
+    // (the dead clauses are read once, each producer files their literals per bucket; the bucket owners then merge and sort)
+    std::vector<std::vector<LT>> dparts(((size_t)nthreads + 1) * (size_t)NB);
+    parallelFor(dead.size(), [&](size_t b, size_t e, int t) {
+        std::vector<LT>* out = &dparts[(size_t)t * (size_t)NB];
+        for (size_t i = b; i < e; ++i) { const uint32_t d = dead[i]; const int32_t* l = CL(d); const int32_t dt = sub_dtime[d]; for (uint32_t k = 0; k < C[d].size; ++k) { out[bucketOf(l[k])].push_back({l[k], dt}); } }
+    }, 2048);
     parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
         for (size_t bk = bb; bk < be; ++bk) {
-            const int32_t lo = bucketLo((int)bk), hi = (bk + 1 == (size_t)NB) ? (int32_t)nlit : bucketLo((int)bk + 1);
             std::vector<LT>& v = dlb[bk];
-            for (uint32_t d : dead) { const int32_t* l = CL(d); for (uint32_t k = 0; k < C[d].size; ++k) { if (l[k] >= lo && l[k] < hi) { v.push_back({l[k], sub_dtime[d]}); } } }
+            for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) { const std::vector<LT>& src = dparts[t2 * (size_t)NB + bk]; v.insert(v.end(), src.begin(), src.end()); }
             std::sort(v.begin(), v.end(), [](const LT& a2, const LT& b2) { return a2.lit != b2.lit ? a2.lit < b2.lit : a2.time < b2.time; });
             for (size_t i = 0; i < v.size(); ++i) { if (dl_start[v[i].lit] < 0) { dl_start[v[i].lit] = (int32_t)i; dl_any[(uint32_t)v[i].lit >> 6] |= 1ull << (v[i].lit & 63); } ++dl_cnt[v[i].lit]; }
         }
@@ -1125,6 +1132,7 @@ bool Engine::subsumptionCommitParallel()
     parallelFor(nlit, [&](size_t b, size_t e, int) {
         for (size_t x = b; x < e; ++x) { const int32_t c = hot[x].cnt; cnt16[x] = (c > 32000 || c < -32000) ? INT16_MIN : (int16_t)c; }
     });
+    lap("step2");
     auto countAt = [&](int x, int32_t T) -> int32_t {               // lit_occurrence_count[x] as of time T
         int32_t c = cnt16[(size_t)x]; if (c == INT16_MIN) { c = hot[x].cnt; }
         if ((dl_any[(uint32_t)x >> 6] >> (x & 63)) & 1ull) { const LT* q = dlb[bucketOf(x)].data() + dl_start[x]; for (uint32_t k = 0; k < dl_cnt[x] && q[k].time < T; ++k) { --c; } }
@@ -1150,7 +1158,7 @@ bool Engine::subsumptionCommitParallel()
             else { ev[bucketOf(mn)].push_back({mn, T, (uint32_t)p}); }
         }
         tsteps[t] = st;
-    });
+    }, qgrain);
     int64_t steps = 0; for (int64_t x : tsteps) { steps += x; }
     lap("step3");
     // step 4: replay the walks of every list that holds a deleted clause, list by list, in time order
@@ -1416,6 +1424,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     // QUIRK: removedClause a second time per subsumed clause (Subsumption.cc:302-313); `ignore` lands in `update`
     for (uint32_t d : sub_occ_updates) { removedClause(d, useHeap, ignore != 0, VAR_UNDEF); }
     sub_occ_updates.clear();
+    lap("ordered walk");
     host_ns_commit += now_ns() - t0;
 }
 
@@ -1666,10 +1675,20 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         parallelFor(nq, [&](size_t b, size_t e, int) {
             for (size_t p2 = b; p2 < e; ++p2) {
                 const uint32_t c = strq[p2];
+                if (walk_min[p2] >= 0) {
+                    // pass (1) has seen this entry: live, flagged, nobody's candidate target - and it has chosen its literal
+                    if (c_str.slot[c] >= 0) { continue; }                   // a record exists: own hits
+                    const int mn = walk_min[p2], nm = mn ^ 1;
+                    if (hasStale(mn) || hasStale(nm)) { continue; }
+                    contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
+                    if (lazy) { C[c].flag &= ~F_STR; amax(&last_static_walk[mn], (int32_t)p2); amax(&last_static_walk[nm], (int32_t)p2); }
+                    continue;
+                }
+                if (!((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }   // not a target and not chosen in pass (1): dead, unflagged, duplicate
                 const ClauseInfo ci = C[c];
                 if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
                 if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
-                const bool target = ((is_target[c >> 6] >> (c & 63)) & 1) != 0;
+                const bool target = true;
                 if (c_str.slot[c] >= 0) {
                     // a record exists: own hits, or - for a candidate target - only the predicted shorter versions
                     if (!target) { continue; }
