@@ -79,7 +79,8 @@ def load(path: str | None = None) -> C.CDLL:
     L.cp3g_scan_all.argtypes = [vp, C.c_int, vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]
     L.cp3g_scan_all.restype = C.c_int
     L.cp3g_bve_pairs.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, vp, vp]; L.cp3g_bve_pairs.restype = C.c_int
-    L.cp3g_bce_masks.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, vp, u32p]; L.cp3g_bce_masks.restype = C.c_int
+    if hasattr(L, "cp3g_bce_masks"):      # (absent only in builds older than the header; tests/test_abi.py checks every declared symbol)
+        L.cp3g_bce_masks.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, vp, u32p]; L.cp3g_bce_masks.restype = C.c_int
     L.cp3g_bve_resolve.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, vp, i32p, C.c_size_t]; L.cp3g_bve_resolve.restype = C.c_int
     L.cp3g_sub_pass.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]; L.cp3g_sub_pass.restype = C.c_int
     L.cp3g_sub_pass_fetch.argtypes = [vp, u32p, u32p, u32p, u32p]; L.cp3g_sub_pass_fetch.restype = C.c_int

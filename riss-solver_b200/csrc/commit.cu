@@ -55,12 +55,24 @@ __global__ void k_sp_diff(const cp3g_hit* __restrict__ h, uint32_t n, const int3
 __global__ void k_sp_dead(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, const int32_t* __restrict__ dtime, uint32_t ncl,
                           uint32_t* __restrict__ dead, uint32_t* __restrict__ ndead, unsigned long long* __restrict__ nlits, uint32_t* __restrict__ dl_cnt)
 {
+    // the two global counters are same-address atomics (~1.4 ns each: 0.39 ms for the 2.8*10^5 subsumed clauses of C2): one per
+    // warp instead - ballot for the slots, shuffle reduction for the literal total
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncl || dtime[c] == T_INF) { return; }
-    const ClauseHdr h = hdr[c];
-    const uint32_t sz = h.szfl & SIZE_MASK;
-    dead[atomicAdd(ndead, 1u)] = c;
-    atomicAdd(nlits, (unsigned long long)sz);
+    const bool is_dead = c < ncl && dtime[c] != T_INF;
+    const unsigned m = __ballot_sync(0xffffffffu, is_dead);
+    if (m == 0) { return; }
+    const unsigned lane = threadIdx.x & 31;
+    uint32_t sz = 0; ClauseHdr h{};
+    if (is_dead) { h = hdr[c]; sz = h.szfl & SIZE_MASK; }
+    uint32_t tot = sz;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, d); }
+    uint32_t base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) { base = atomicAdd(ndead, (uint32_t)__popc(m)); atomicAdd(nlits, (unsigned long long)tot); }
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (!is_dead) { return; }
+    dead[base + __popc(m & ((1u << lane) - 1u))] = c;
     for (uint32_t k = 0; k < sz; ++k) { atomicAdd(&dl_cnt[lits[h.start + k]], 1u); }
 }
 __global__ void k_sp_dlfill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, const int32_t* __restrict__ dtime,

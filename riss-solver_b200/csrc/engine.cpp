@@ -411,6 +411,11 @@ int Engine::setDistributed(int rank, int world, const void* id)
 void Engine::uploadAll()
 {
     ensureGpu();
+    // occurrence entries carry the clause index in 30 bits (two class bits share the word): the reference's CRef reaches 2^31
+    // words, this path stops earlier - and says so before anything is uploaded
+    if (C.size() > 0x3fffffffull || (size_t)nvars >= (1ull << 30) || pool.size() >= 0x7fffffffull) {
+        die("data base too large for the GPU path: more than 2^30 clauses / variables or 2^31 literals (30-bit clause references)");
+    }
     const uint32_t ncl = (uint32_t)C.size();
     static_assert(sizeof(ClauseInfo) == 16, "ClauseInfo is uploaded as a packed 16-byte record");
     int64_t t0 = now_ns();
@@ -782,6 +787,16 @@ void Engine::occSwapRemove(int x, uint32_t i)
 }
 void Engine::occRelease(int x) { hot[x].n = 0; staleClear(x); }
 
+// the variables of many deleted clauses at once: while the BVE heap is empty (the passes in front of BVE) touching a variable is
+// just a counter increment - done on all cores; with a heap the pending list is filled in order
+void Engine::touchDeadClauses(const std::vector<uint32_t>& dead)
+{
+    if (!opt.bve) { return; }
+    if (!heap.empty() || dead.size() < 4096) { for (uint32_t d : dead) { touchClauseVars(d); } return; }
+    parallelFor(dead.size(), [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) { const uint32_t d = dead[i]; const int32_t* l = CL(d); for (uint32_t k = 0; k < C[d].size; ++k) { __atomic_fetch_add(&var_touch[(size_t)(l[k] >> 1)], 1u, __ATOMIC_RELAXED); } }
+    }, 8192);
+}
 void Engine::touchClauseVars(uint32_t c)
 {
     if (!opt.bve) { return; }                       // only the BVE pair cache looks at var_touch
@@ -1229,7 +1244,7 @@ bool Engine::subsumptionCommitParallel()
         n_live -= (uint32_t)dead.size();
         numberOfCls -= 2 * (int)dead.size(); ca_wasted += 2 * (2.0 * (double)dead.size() + (double)nl);
         if (dev_uploaded) { pend_del.insert(pend_del.end(), dead.begin(), dead.end()); }
-        if (opt.bve) { for (uint32_t d : dead) { touchClauseVars(d); } }
+        touchDeadClauses(dead);
     }
     if (!dead.empty()) { successful(t_sub); }
     sub_steps += steps;
@@ -1305,7 +1320,7 @@ bool Engine::subsumptionCommitDevice()
     subsumedClauses += (int)ndead; subsumedLiterals += (int)nlits;
     n_live -= ndead;
     numberOfCls -= 2 * (int)ndead; ca_wasted += 2 * (2.0 * (double)ndead + (double)nlits);
-    if (opt.bve) { for (uint32_t d : dead) { touchClauseVars(d); } }
+    touchDeadClauses(dead);
     if (ndead) { successful(t_sub); }
     sub_steps += (int64_t)steps;
     parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { C[subq[p]].flag &= ~F_SUB; } });

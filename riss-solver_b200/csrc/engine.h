@@ -296,10 +296,11 @@ private:
     // heap (riss/mtl/Heap.h)
     // VarOrderBVEHeapLt, CoprocessorTypes.h:493-547: -cp3_bve_heap=0 fewest occurrences first, 1 most first, 3-10 the polarity
     // ratio of the variable combined with its occurrence count (2 = random order without a heap: not provided)
-    bool heapLt(int x, int y) const
+    // (the default order stays a two-load inline compare: the heap walks call this ~10^8 times at 10 M variables)
+    bool heapLt(int x, int y) const { return opt.bve_heap == 0 ? dcount(x) < dcount(y) : heapLtOption(x, y); }
+    bool heapLtOption(int x, int y) const __attribute__((noinline))
     {
         const int h = opt.bve_heap;
-        if (h == 0) { return dcount(x) < dcount(y); }
         if (h == 1) { return dcount(x) > dcount(y); }
         const double xp = hot[2 * x].cnt, xn = hot[2 * x + 1].cnt, yp = hot[2 * y].cnt, yn = hot[2 * y + 1].cnt;
         double rx = 0, ry = 0;
@@ -336,6 +337,10 @@ private:
     bool subsumptionCommitDevice();
     // overlap: the strengthening scan + speculative closure of this fixpoint round run on a helper thread (GPU +
     // one core) while the subsumption commit occupies the other cores
+    // (the helper only READS what the committing threads write - deleted flags, list lengths - through plain loads of aligned
+    //  32-bit words: it may see a clause as live that dies a moment later, which monotonicity makes harmless for the RESULT - the
+    //  hit is dropped at commit time - but the speculation budget and request set, hence the counters spec_requests /
+    //  scan_ondemand / gpu_launches, are not reproducible from run to run while the overlap is on; CP3_NO_OVERLAP=1 pins them)
     bool overlap_str = false, str_prepared = false, scan_no_flush = false;
     void prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk);
     int64_t n_overlap = 0;                // time-indexed, data-parallel form of the queue walk
@@ -388,6 +393,7 @@ private:
     const CacheEnt* strHits(uint32_t cr);             // cached or on-demand strengthening hits of cr
     PairEnt& pairsFor(int v);
     void touchClauseVars(uint32_t c);
+    void touchDeadClauses(const std::vector<uint32_t>& dead);
 };
 
 } // namespace cp3

@@ -449,6 +449,32 @@ def test_c2_full_size_ordered_against_the_reference(gen):
     assert np.array_equal(c.stream, out)
 
 
+def test_c3_shape_bve_fixpoint_against_the_reference(gen):
+    """BASELINE configs[2] shape at a tenth of its size (community k-SAT 1M vars / 5.4M clauses, -up -subsimp -bve, the same
+    bounded sample bench.py's cpu_baseline times): every counter, the trail, the ORDERED clause stream, the undo stack and the
+    extended model against the sequential reference (oracle/_ref/refshim, ~14 s) when it was built; else against the C oracle.
+    The full-size configuration is compared through its counters by scripts/c3_point.py (158 s of reference time)."""
+    from harness import have_ref, run_ref
+    lits, sizes = gen.community_ksat(1000000, 5000000, seed=20260001)
+    stream = gen.csr_to_stream(lits, sizes)
+    a = run_gpu(stream, FULL)
+    assert a.ok == 1 and a.stats["bve_eliminatedVars"] > 10000
+    b = run_ref(stream, FULL) if have_ref() else run_oracle(stream, FULL)
+    assert compare(a, b) == []
+    # canonical form: the same multiset of clauses whatever the emission order (north_star: identical after canonical sorting)
+    import hashlib
+    def canon(st):
+        z = np.flatnonzero(st == 0); starts = np.concatenate([[0], z[:-1] + 1]); szs = z - starts
+        h = hashlib.sha256()
+        for k in np.unique(szs):
+            idx = np.flatnonzero(szs == k)
+            rows = st[(starts[idx][:, None] + np.arange(k)[None, :])]
+            rows = np.sort(rows, axis=1); rows = rows[np.lexsort(rows.T[::-1])]
+            h.update(rows.astype(np.int32).tobytes())
+        return h.hexdigest()
+    assert canon(a.stream) == canon(b.stream)
+
+
 def test_forced_parallel_paths_on_gpu(gen):
     """same fuzz as test_fuzz_small_instances with the large-queue code paths (device bulk ingest K0, full-queue kernels
     k_full, time-indexed subsumption commit, static strengthening plan, scan/commit overlap) forced on; thresholds are
