@@ -334,7 +334,9 @@ def main():
 
     if cfg.name == "zipf":
         for s in (0.0, 0.5, 0.8, 1.0, 1.2):
-            ncl, nints, res, clocks = run_steps(cfg, 1, max(1, min(args.steps, 3)), zipf_s=s)
+            # the fixpoint over degenerate lists (s >= 1: lists of 10^5-10^6 entries, 10^10-10^11 checks) takes minutes per step - one
+            # untimed-free step there; the kernel figures (roofline) are what this sweep is about
+            ncl, nints, res, clocks = run_steps(cfg, 1 if s < 1.0 else 0, max(1, min(args.steps, 3)) if s < 1.0 else 1, zipf_s=s)
             t_add, t_pp, t_out, st, checks = summarize(res)
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "value": checks / t_pp, "unit": UNIT, "n_gpus": world, "ms_per_step": t_pp * 1e3, "higher_is_better": True,

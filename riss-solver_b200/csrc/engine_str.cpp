@@ -1,0 +1,704 @@
+// engine_str.cpp - strengthening commit of the host engine (static plan, walk plans, ordered walk, naive variant) and
+// Subsumption::process.
+#include "engine_util.h"
+
+namespace cp3 {
+
+// updateOccurrences, Subsumption.cc:1530-1544
+void Engine::updateOccurrences(bool useHeap, int ignore)
+{
+    // from here on nothing is pending any more (setDeleted() consults pend_rm)
+    std::vector<OccUpd> ups; ups.swap(occ_upd);
+    ++pend_epoch;
+    for (const OccUpd& u : ups) {
+        if (removeClauseFrom(u.cr, u.l)) { removedLiteral(u.l, 1, useHeap, ignore != 0, VAR_UNDEF); }
+    }
+}
+
+// the hit branch of both passes, Subsumption.cc:1385-1413 / 1474-1508
+void Engine::strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos)
+{
+    ++removedLiterals;
+    if (static_lazy && lazyPending(other)) { C[other].flag |= F_STR; }      // still waiting in the queue
+    if (!(C[other].flag & F_SUB)) { C[other].flag |= F_SUB; subq.push_back(other); }
+    if (!(C[other].flag & F_STR)) { localQueue.push_back(other); C[other].flag |= F_STR; }
+    successful(t_sub);
+    const int lit = CL(other)[pos];
+    occ_upd.push_back({other, lit});
+    removePosSorted(other, pos);
+    noteShrunk(other, lit, true);
+    unpredictedEdit(other);
+    dirty_str.push_back(other);
+    if (C[other].size == 1) {
+        dataEnqueue(CL(other)[0]);
+        setDeleted(other);
+    }
+}
+
+// strengthening hits of cr for its current content: cached, or one more K4 batch (cr + the other pending
+// strengtheners that were edited after their scan)
+const Engine::CacheEnt* Engine::strHits(uint32_t cr)
+{
+    const CacheEnt* e = cached(c_str, cr);
+    if (e) { if (e->ver == UINT32_MAX) { ++n_spec_used; } return e; }
+    ++n_ondemand;
+    if (getenv("CP3_DEBUG_ONDEMAND") && n_ondemand < 12) {
+        fprintf(stderr, "ondemand cr=%u size=%u ver=%u stamp=%u flag=%u slot=%d bulk_all=%d bulk_scan=%u bulk_ncl=%u qtime=%d\n", cr, (unsigned)C[cr].size, C[cr].ver, C[cr].stamp,
+                (unsigned)C[cr].flag, cr < c_str.slot.size() ? c_str.slot[cr] : -9, (int)c_str.bulk_all, c_str.bulk_scan, c_str.bulk_ncl, cr < qtime.size() ? qtime[cr] : -9);
+        for (int32_t i = cr < c_str.slot.size() ? c_str.slot[cr] : -1; i >= 0; i = c_str.ent[i].next) {
+            fprintf(stderr, "   ent ver=%u n=%u time=%f hits=%u\n", c_str.ent[i].ver, c_str.ent[i].lit_n, c_str.ent[i].time, c_str.ent[i].he - c_str.ent[i].hb);
+        }
+    }
+    std::vector<uint32_t> ids;
+    pgrow(c_str.slot, C.size(), -1);
+    for (uint32_t c : dirty_str) {
+        if (c == cr || (C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
+        if (cached(c_str, c)) { continue; }
+        ids.push_back(c);
+    }
+    dirty_str.clear();
+    std::sort(ids.begin(), ids.end());
+    ids.erase(std::unique(ids.begin(), ids.end()), ids.end());
+    ids.insert(ids.begin(), cr);
+    scanClauses(CP3G_STRENGTHEN, ids, c_str);
+    e = cached(c_str, cr);
+    if (!e) { die("internal: strengthener without scan result"); }
+    return e;
+}
+
+// Put one list that was cleaned up front back into its lazy state (nobody has walked it yet).
+void Engine::restoreOneList(int x)
+{
+    const int32_t i = pre_index[x];
+    if (i < 0 || scanned_dyn[x] || (static_lazy && last_static_walk[x] > (int64_t)cur_end)) { return; }
+    const PreList& pl = pre_lists[i];
+    memcpy(occ_pool.data() + occ[x].off, pre_snap.data() + pl.snap_off, sizeof(uint32_t) * pl.old_n);
+    hot[x].n = pl.old_n;
+    for (uint32_t k = 0; k < pl.extra; ++k) { staleInc(x); }
+    str_steps -= pl.extra;
+    pre_index[x] = -1;
+}
+// A unit is about to be propagated: clauses will die, and the reference would clean the lists nobody has walked
+// yet together with those new deletions (swap-with-last cleaning is not associative).  Put every list that was
+// cleaned up front but not walked so far back into its lazy state; from here on the pass runs the plain lazy way.
+void Engine::rollbackPrecompact()
+{
+    if (!pre_active) { return; }
+    for (const PreList& pl : pre_lists) { restoreOneList(pl.lit); }
+    pre_active = false;
+}
+bool Engine::lazyPending(uint32_t c) const
+{
+    if (c >= qtime.size() || qtime[c] < 0) { return false; }
+    const size_t pos = static_nq - 1 - (size_t)qtime[c];
+    return pos < cur_end && pos < contrib.size() && contrib[pos] >= 0;
+}
+// The lazy static plan stops here: inert entries that still wait get their flag back, the lists walked by the
+// ones already passed are marked as walked.  From here on the pass runs entry by entry.
+void Engine::leaveLazy()
+{
+    if (!static_lazy) { return; }
+    static_lazy = false;
+    const size_t nq = static_nq, ce = std::min(cur_end + 1, nq);
+    parallelFor(ce, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { C[strq[p]].flag |= F_STR; } } });
+    if (pre_active) { for (size_t p = ce; p < nq; ++p) { if (contrib[p] >= 0 && walk_min[p] >= 0) { scanned_dyn[walk_min[p]] = 1; scanned_dyn[walk_min[p] ^ 1] = 1; } } }
+}
+// The static plan assumed that clause c keeps its content until its turn (it was nobody's predicted target).
+// A hit that the speculative closure did not predict just changed it: c is no longer inert, and the lists it
+// was going to walk lose one certain walker - a list without any is put back into its lazy state.
+void Engine::unpredictedEdit(uint32_t c)
+{
+    if (!static_pass || c >= qtime.size() || qtime[c] < 0) { return; }
+    const size_t pos = static_nq - 1 - (size_t)qtime[c];
+    if (pos >= walk_min.size()) { return; }
+    if (static_lazy && contrib[pos] >= 0 && pos < cur_end) { lazy_flipped.push((uint32_t)pos); }     // it is a real entry from now on
+    contrib[pos] = -1;
+    const int mn = walk_min[pos];
+    if (mn < 0) { return; }
+    walk_min[pos] = -1;
+    for (int x : {mn, mn ^ 1}) {
+        if (walk_count[x] > 0 && --walk_count[x] == 0 && pre_active) { restoreOneList(x); }
+    }
+}
+
+// K4 over the strengthening queue + speculative closure (first half of a strengthening pass)
+void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
+{
+    DbgLap lap("prepStr");
+    c_str.clear();
+    lap("clear");
+    scanClauses(CP3G_STRENGTHEN, ids, c_str, scan_no_flush ? (bulk ? 1 : 0) : -1);
+    lap("scan");
+    // processing time of the queue entries: the queue is drained from the back
+    if (qtime.size() < C.size()) { pgrow(qtime, C.size() + 1024, -1); }
+    // (a clause queued twice keeps the time of its last entry, like the sequential fill)
+    { bool inc = true; for (size_t i = 1; i < strq.size(); ++i) { if (strq[i - 1] >= strq[i]) { inc = false; break; } }
+      const size_t nq = strq.size();
+      if (inc) { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } }); }
+      else { for (size_t i = 0; i < nq; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } } }
+    for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
+    for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
+    lap("qtime");
+    prefetchStrengthenClosure();
+    lap("closure");
+}
+
+// strengthening_worker, Subsumption.cc:1250-1528 (all_strength_res == 0)
+int Engine::strengtheningWorker(bool useHeap, int ignore)
+{
+    PhaseTimer pt(ph_str);
+    const bool unlimited = !opt.limited;
+    ensureHostLists();
+    logClear(); dirty_str.clear();
+    if (str_prepared) { str_prepared = false; }            // scan + closure were done while the subsumption commit ran
+    else if (opt.strength) {
+        std::vector<uint32_t> ids;
+        for (uint32_t c : strq) {
+            if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
+            ids.push_back(c);
+        }
+        sortUnique(ids);
+        prepareStrengthening(ids, false);
+    } else { c_str.clear(); }
+    DbgLap lap("str"); lap("prepare");
+    const bool fine = lap.on && getenv("CP3_DEBUG_FINE") != nullptr;          // per-entry timers (they cost as much as the entries)
+    int64_t t0 = now_ns();
+    // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
+    // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
+    // (a) has no candidate hit, (b) is no candidate target of anybody and (c) walks two lists without deleted
+    // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
+    // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
+    pfill(contrib, strq.size(), -1); pfill(contrib_t, strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
+    static const size_t static_min = getenv("CP3_STATIC_MIN") ? (size_t)atoi(getenv("CP3_STATIC_MIN")) : 4096;
+    bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
+    if (static_valid) {
+        is_target.assign((C.size() >> 6) + 1, 0ull);
+        for (const Hit& h : c_str.hits) { is_target[h.clause >> 6] |= 1ull << (h.clause & 63); }
+        const size_t nq = strq.size();
+        // the counters are frozen while this plan is valid: a 2-byte copy per variable (2 MB at 1 M variables) keeps
+        // the min-count choices of the two passes below in the cores' caches; out-of-range values read the original
+        std::vector<int16_t> dc16((size_t)std::max(nvars, 1));
+        parallelFor((size_t)nvars, [&](size_t b, size_t e, int) {
+            for (size_t v = b; v < e; ++v) { const int d = dcount((int)v); dc16[v] = (d > 32000 || d < -32000) ? INT16_MIN : (int16_t)d; }
+        });
+        auto dcq = [&](int v) -> int { const int16_t q = dc16[(size_t)v]; return q == INT16_MIN ? dcount(v) : (int)q; };
+        // (1) lists that are certainly walked in this pass: the two lists of every pending clause whose content
+        //     cannot change before its turn (it is nobody's candidate target)
+        std::vector<uint8_t> walked((size_t)2 * nvars, 0);
+        std::vector<int64_t> bound((size_t)nthreads + 1, 0);
+        pfill(walk_min, nq, -1); pfill(walk_count, (size_t)2 * nvars, 0u);
+        static_pass = true; static_nq = nq;
+        parallelFor(nq, [&](size_t b, size_t e, int t) {
+            int64_t bs = 0;
+            for (size_t p2 = b; p2 < e; ++p2) {
+                const uint32_t c = strq[p2];
+                const ClauseInfo ci = C[c];
+                if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }                      // duplicate queue entry
+                if ((is_target[c >> 6] >> (c & 63)) & 1) { continue; }
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0]; int best = dcq(minT >> 1);
+                for (uint32_t j = 1; j < ci.size; ++j) { const int dj = dcq(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
+                // (only lists that hold deleted entries can be pre-compacted: the walker count and the mark matter for them alone)
+                walk_min[p2] = minT;
+                if (hasStale(minT)) { walked[minT] = 1; __atomic_fetch_add(&walk_count[minT], 1u, __ATOMIC_RELAXED); }
+                if (hasStale(minT ^ 1)) { walked[minT ^ 1] = 1; __atomic_fetch_add(&walk_count[minT ^ 1], 1u, __ATOMIC_RELAXED); }
+                bs += (int64_t)hot[minT].n + hot[minT ^ 1].n;
+            }
+            bound[t] = bs;
+        });
+        int64_t total_bound = 0; for (int64_t x : bound) { total_bound += x; }
+        lap("static1");
+        // (2) the first walk of a list removes its deleted entries by swap-with-last (Subsumption.cc:1332-1335,
+        //     1432-1435); the resulting order depends only on the list and on which entries are deleted, and no
+        //     clause dies during this pass unless a unit shows up.  So the certainly-walked lists are cleaned
+        //     up front, on all cores, each costing one step per removed entry like the lazy walk would.
+        pre_lists.clear(); pre_snap.clear(); pre_active = false;
+        static const bool no_pre = getenv("CP3_NO_PRECOMPACT") != nullptr;
+        if (!no_pre && (unlimited || str_steps + 2 * total_bound < str_lim)) {
+            const size_t nlit = (size_t)2 * nvars;
+            const size_t words = (nlit + 63) / 64;
+            std::vector<std::vector<PreList>> tl((size_t)nthreads + 1); std::vector<std::vector<uint32_t>> ts((size_t)nthreads + 1);
+            parallelForG(words, 512, [&](size_t wb, size_t we, int t) {  // 64-literal granules: stalebits words are not shared
+                for (size_t x = wb * 64; x < std::min(nlit, we * 64); ++x) {
+                    if (!walked[x] || !hasStale((int)x)) { continue; }
+                    uint32_t* p = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n;
+                    PreList pl; pl.lit = (int)x; pl.snap_off = (uint32_t)ts[t].size(); pl.old_n = n; pl.extra = 0;
+                    ts[t].insert(ts[t].end(), p, p + n);                 // keep the lazy state: a unit may force us to take this back
+                    for (uint32_t j = 0; j < n;) { if (isDel(p[j])) { p[j] = p[n - 1]; --n; ++pl.extra; } else { ++j; } }
+                    hot[x].n = n; staleClear((int)x);
+                    tl[t].push_back(pl);
+                }
+            });
+            for (size_t t = 0; t < tl.size(); ++t) {
+                const uint32_t base = (uint32_t)pre_snap.size();
+                pre_snap.insert(pre_snap.end(), ts[t].begin(), ts[t].end());
+                for (PreList pl : tl[t]) { pl.snap_off += base; str_steps += pl.extra; pre_lists.push_back(pl); }
+            }
+            pre_active = !pre_lists.empty();
+            if (pre_active) {
+                scanned_dyn.assign(nlit, 0); pre_index.assign(nlit, -1);
+                for (size_t i = 0; i < pre_lists.size(); ++i) { pre_index[pre_lists[i].lit] = (int32_t)i; }
+            }
+        }
+        lap("precompact");
+        // (3) step contribution of the inert entries.  Far from the step limit their whole effect is applied here
+        //     (flag cleared, walked lists recorded) and the ordered walk below only adds the number up.
+        static const bool no_lazy = getenv("CP3_NO_LAZY") != nullptr;
+        const bool lazy = !no_lazy && (unlimited || str_steps + 2 * total_bound < str_lim);
+        static_lazy = lazy; n_lazy = 0; cur_end = nq;
+        if (lazy) { last_static_walk.assign((size_t)2 * nvars, -1); }
+        auto amax = [](int32_t* a, int32_t v) { int32_t o = __atomic_load_n(a, __ATOMIC_RELAXED); while (o < v && !__atomic_compare_exchange_n(a, &o, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {} };
+        parallelFor(nq, [&](size_t b, size_t e, int) {
+            for (size_t p2 = b; p2 < e; ++p2) {
+                const uint32_t c = strq[p2];
+                if (walk_min[p2] >= 0) {
+                    // pass (1) has seen this entry: live, flagged, nobody's candidate target - and it has chosen its literal
+                    if (c_str.slot[c] >= 0) { continue; }                   // a record exists: own hits
+                    const int mn = walk_min[p2], nm = mn ^ 1;
+                    if (hasStale(mn) || hasStale(nm)) { continue; }
+                    contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
+                    if (lazy) { C[c].flag &= ~F_STR; amax(&last_static_walk[mn], (int32_t)p2); amax(&last_static_walk[nm], (int32_t)p2); }
+                    continue;
+                }
+                if (!((is_target[c >> 6] >> (c & 63)) & 1)) { continue; }   // not a target and not chosen in pass (1): dead, unflagged, duplicate
+                const ClauseInfo ci = C[c];
+                if ((ci.flag & F_DEL) || !(ci.flag & F_STR) || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
+                const bool target = true;
+                if (c_str.slot[c] >= 0) {
+                    // a record exists: own hits, or - for a candidate target - only the predicted shorter versions
+                    if (!target) { continue; }
+                    const CacheEnt* e0 = cached(c_str, c);
+                    if (!e0 || e0->hb != e0->he) { continue; }
+                }
+                const int32_t* s2 = pool.data() + ci.start; int minT = s2[0]; int best = dcq(minT >> 1);
+                for (uint32_t j = 1; j < ci.size; ++j) { const int dj = dcq(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
+                const int mn = minT, nm = minT ^ 1;
+                if (hasStale(mn) || hasStale(nm)) { continue; }
+                if (target) {
+                    // somebody's candidate target without hits of its own: inert as well IF its content is still the
+                    // planned one when its turn comes (checked there by the content version)
+                    contrib_t[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n); tmin[p2] = mn; plan_ver[p2] = ci.ver;
+                    continue;
+                }
+                contrib[p2] = (int32_t)((hot[mn].n ? hot[mn].n - 1 : 0) + hot[nm].n);
+                if (lazy) { C[c].flag &= ~F_STR; amax(&last_static_walk[mn], (int32_t)p2); amax(&last_static_walk[nm], (int32_t)p2); }
+            }
+        });
+    }
+    lap("contrib");
+    // In lazy mode the walk visits only the entries that are not inert ("real": own hits, candidate targets, deleted or
+    // unflagged clauses, lists with deleted entries); the inert runs in between are added up from their contributions.
+    std::vector<uint32_t> reals; lazy_flipped = std::priority_queue<uint32_t>();
+    if (static_lazy) {
+        const size_t nq = strq.size();
+        std::vector<size_t> cntp((size_t)nthreads + 2, 0);
+        parallelFor(nq, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t i = b; i < e; ++i) { c += contrib[i] < 0 ? 1 : 0; } cntp[(size_t)t + 1] = c; });
+        for (size_t t = 1; t < cntp.size(); ++t) { cntp[t] += cntp[t - 1]; }
+        reals.resize(cntp.back());
+        parallelFor(nq, [&](size_t b, size_t e, int t) { size_t o = cntp[(size_t)t]; for (size_t i = b; i < e; ++i) { if (contrib[i] < 0) { reals[o++] = (uint32_t)i; } } });
+    }
+    size_t ri = reals.size();                                       // reals[0..ri) are still ahead (the walk goes down)
+    lap("reals");
+    // Walk plan of the real entries.  While the plan is valid (no unit, frozen counters, clean lists) the two list walks of an
+    // entry are a pure function of its content: the step count is the length of the two lists and the candidates that can
+    // hit are the cached hits in list order.  Both are evaluated here on all cores for the content the entry has NOW; the
+    // ordered walk below uses the record when the entry's turn comes and its content version is still the planned one, and
+    // then only validates and applies the candidate hits (the order-dependent part).  Everything else takes the walk itself.
+    struct PlanEnt { uint32_t ver, scan; int32_t min; uint32_t steps1, steps2, cb, c1, c2; uint32_t t; uint32_t lit_off, lit_n; int32_t alt; };
+    RawVec<PlanEnt> plan; std::vector<std::vector<Hit>> plan_c((size_t)nthreads + 1); std::vector<std::vector<PlanEnt>> plan_alt((size_t)nthreads + 1);
+    static const bool no_plan = getenv("CP3_NO_PLAN") != nullptr;
+    const bool planned = static_lazy && !no_plan && !reals.empty();
+    if (planned) {
+        const size_t nq = strq.size();
+        plan.resize(reals.size());
+        parallelFor(reals.size(), [&](size_t b, size_t e, int t) {
+            std::vector<Hit>& pc = plan_c[(size_t)t]; std::vector<PlanEnt>& pa = plan_alt[(size_t)t];
+            // the record of clause c with the content s2[0..n) whose cached hits are e0
+            auto build = [&](PlanEnt& pe, uint32_t c, const int32_t* s2, uint32_t n, const CacheEnt* e0) {
+                int minT = s2[0]; int best = dcount(minT >> 1);
+                for (uint32_t j = 1; j < n; ++j) { const int dj = dcount(s2[j] >> 1); if (best > dj) { best = dj; minT = s2[j]; } }
+                const int mn = minT, nm = minT ^ 1;
+                if (hasStale(mn) || hasStale(nm)) { return; }
+                pe.scan = e0->scan; pe.t = (uint32_t)t;
+                pe.steps1 = hot[mn].n ? hot[mn].n - 1 : 0; pe.steps2 = hot[nm].n;
+                pe.cb = pe.c1 = pe.c2 = (uint32_t)pc.size();
+                if (e0->hb != e0->he) {
+                    const uint32_t* l1 = occ_pool.data() + occ[mn].off; const uint32_t n1 = hot[mn].n;
+                    for (uint32_t j = 0; j < n1; ++j) {
+                        if (l1[j] == c) { continue; }
+                        const Hit* h = findHit(c_str.hits, e0->hb, e0->he, l1[j]);
+                        if (h && h->lit != nm) { pc.push_back(*h); }
+                    }
+                    pe.c1 = (uint32_t)pc.size();
+                    const uint32_t* l2 = occ_pool.data() + occ[nm].off; const uint32_t n2 = hot[nm].n;
+                    for (uint32_t j = 0; j < n2; ++j) {
+                        const Hit* h = findHit(c_str.hits, e0->hb, e0->he, l2[j]);
+                        if (h && h->lit == nm) { pc.push_back(*h); }
+                    }
+                    pe.c2 = (uint32_t)pc.size();
+                }
+                pe.min = mn;
+            };
+            for (size_t i = b; i < e; ++i) {
+                PlanEnt& pe = plan[i]; pe.min = -1; pe.alt = -1; pe.lit_n = 0; pe.t = (uint32_t)t;
+                const size_t p2 = reals[i];
+                const uint32_t c = strq[p2];
+                const ClauseInfo ci = C[c];
+                pe.ver = ci.ver;
+                if ((ci.flag & (F_DEL | F_STR)) != F_STR || ci.size < 2) { continue; }
+                if (qtime[c] != (int32_t)(nq - 1 - p2)) { continue; }
+                const CacheEnt* e0 = cached(c_str, c);
+                if (e0) { build(pe, c, pool.data() + ci.start, ci.size, e0); }
+                // a candidate target: also the shortened contents the closure predicted (records keyed by content)
+                if (((is_target[c >> 6] >> (c & 63)) & 1) && c < c_str.slot.size()) {
+                    for (int32_t k = c_str.slot[c]; k >= 0; k = c_str.ent[(size_t)k].next) {
+                        const CacheEnt& ce = c_str.ent[(size_t)k];
+                        if (ce.ver != UINT32_MAX || ce.lit_n < 2) { continue; }
+                        PlanEnt a; a.min = -1; a.ver = 0; a.alt = pe.alt; a.lit_off = ce.lit_off; a.lit_n = ce.lit_n;
+                        build(a, c, c_str.lits.data() + ce.lit_off, ce.lit_n, &ce);
+                        if (a.min >= 0) { pe.alt = (int32_t)pa.size(); pa.push_back(a); }
+                    }
+                }
+            }
+        }, 2048);
+    }
+    long cur_plan = -1;                                             // plan record of the entry being processed, if any
+    lap("plan");
+    std::vector<uint32_t> localQueue;
+    size_t end = strq.size();
+    int ret = L_UNDEF; bool early = false;
+    for (; end > 0 && (unlimited || str_steps < str_lim);) {
+        uint32_t cr;
+        cur_plan = -1;
+        const int64_t tq0 = fine ? now_ns() : 0;
+        if (localQueue.empty()) {
+            if (static_lazy && hasToPropagate()) { cur_end = end; leaveLazy(); }
+            if (static_lazy) {
+                // next real entry below `end`: from the plan, or one that an unpredicted hit turned real meanwhile
+                while (ri > 0 && reals[ri - 1] >= end) { --ri; }
+                while (!lazy_flipped.empty() && lazy_flipped.top() >= end) { lazy_flipped.pop(); }
+                long nxt = ri > 0 ? (long)reals[ri - 1] : -1;
+                if (!lazy_flipped.empty() && (long)lazy_flipped.top() > nxt) { nxt = (long)lazy_flipped.top(); }
+                int64_t run = 0;
+                for (size_t p = (size_t)(nxt + 1); p < end; ++p) { run += contrib[p]; }      // all inert: contributions >= 0
+                str_steps += run; n_lazy += (int64_t)(end - (size_t)(nxt + 1));
+                if (nxt < 0) { end = 0; cur_end = 0; break; }
+                end = (size_t)nxt + 1;                               // the shared code below steps onto it
+                if (planned && ri > 0 && (long)reals[ri - 1] == nxt) {
+                    cur_plan = (long)ri - 1;
+                    if (ri > 5) {                                    // look ahead: the clauses the next planned entries will edit
+                        const PlanEnt& pf = plan[ri - 5];
+                        if (pf.min >= 0) {
+                            const Hit* hc = plan_c[pf.t].data();
+                            for (uint32_t k = pf.cb; k < pf.c2; ++k) { const uint32_t o = hc[k].clause; __builtin_prefetch(&C[o]); if (o < log_head.size()) { __builtin_prefetch(&log_head[o]); } if (o < qtime.size()) { __builtin_prefetch(&qtime[o]); } if (o < shrunk_mark.size()) { __builtin_prefetch(&shrunk_mark[o]); } }
+                        }
+                    }
+                    if (ri > 2) {
+                        const PlanEnt& pf = plan[ri - 2];
+                        if (pf.min >= 0) { const Hit* hc = plan_c[pf.t].data(); for (uint32_t k = pf.cb; k < pf.c2; ++k) {
+                            const uint32_t o = hc[k].clause; __builtin_prefetch(pool.data() + C[o].start);
+                            if (o < qtime.size() && qtime[o] >= 0) { const size_t po = static_nq - 1 - (size_t)qtime[o]; if (po < contrib.size()) { __builtin_prefetch(&contrib[po]); __builtin_prefetch(&walk_min[po]); } } } }
+                    }
+                }
+                if (ri > 8) {                                        // look ahead: the clause, its counters and its scan record
+                    const uint32_t c2 = strq[reals[ri - 8]]; const ClauseInfo& ci2 = C[c2];
+                    __builtin_prefetch(&ci2);
+                    if (ri > 4) { const ClauseInfo& c3 = C[strq[reals[ri - 4]]]; const int32_t* l3 = pool.data() + c3.start; const uint32_t n3 = std::min<uint32_t>(c3.size, 6); for (uint32_t k = 0; k < n3; ++k) { __builtin_prefetch(&hot[l3[k] & ~1]); } }
+                    if (c2 < c_str.slot.size()) { __builtin_prefetch(&c_str.slot[c2]); }
+                }
+            }
+            --end; cur_end = end;
+            if (end >= 24 && contrib[end - 24] < 0) {           // look ahead past the inert entries: the next real one
+                const ClauseInfo& c2 = C[strq[end - 24]]; const int32_t* l2 = pool.data() + c2.start;
+                const uint32_t n2 = std::min<uint32_t>(c2.size, 6);
+                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
+                if (strq[end - 24] < c_str.slot.size()) { const int32_t sl = c_str.slot[strq[end - 24]]; if (sl >= 0) { __builtin_prefetch(&c_str.ent[(size_t)sl]); } }
+            }
+            if (static_lazy) {
+                if (contrib[end] >= 0) {
+                    if (!hasToPropagate()) { str_steps += contrib[end]; ++n_lazy; continue; }
+                    leaveLazy();
+                }
+            }
+            cr = strq[end];
+            if (static_valid && contrib[end] >= 0 && !hasToPropagate() && (unlimited || str_steps + contrib[end] < str_lim)) {
+                str_steps += contrib[end];
+                C[cr].flag &= ~F_STR;
+                ++n_fast; ++n_static;
+                if (pre_active) { const int mn = walk_min[end]; scanned_dyn[mn] = 1; scanned_dyn[mn ^ 1] = 1; }
+                continue;
+            }
+            if (static_valid && contrib_t[end] >= 0 && !hasToPropagate() && C[cr].ver == plan_ver[end] &&
+                (C[cr].flag & (F_STR | F_DEL)) == F_STR && opt.strength && (unlimited || str_steps + contrib_t[end] + 1 < str_lim)) {
+                // unchanged candidate target without own hits: what the walk below would do is add up two clean lists
+                str_steps += contrib_t[end];
+                C[cr].flag &= ~F_STR;
+                ++n_fast; ++n_tfast;
+                if (pre_active) { scanned_dyn[tmin[end]] = 1; scanned_dyn[tmin[end] ^ 1] = 1; }
+                continue;
+            }
+            if (end >= 16) {
+                const uint32_t c2 = strq[end - 16];
+                const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
+                for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
+            }
+        }
+        else {
+            cr = localQueue.back(); localQueue.pop_back();
+            // a clause that was strengthened after its own turn: the records of its predicted contents hang off its queue entry
+            if (planned && static_lazy && cr < qtime.size() && qtime[cr] >= 0) {
+                const uint32_t pos = (uint32_t)(static_nq - 1 - (size_t)qtime[cr]);
+                const auto it = std::lower_bound(reals.begin(), reals.end(), pos);
+                if (it != reals.end() && *it == pos) { cur_plan = (long)(it - reals.begin()); }
+            }
+        }
+        if ((C[cr].flag & F_DEL) || !(C[cr].flag & F_STR)) { continue; }
+        if (!opt.strength) { C[cr].flag &= ~F_STR; continue; }
+        if (C[cr].size < 2) {
+            if (C[cr].size == 1) { if (dataEnqueue(CL(cr)[0]) == L_FALSE) { break; } else { continue; } }
+            else { ok = false; break; }
+        }
+        // stage: how much of the two list walks the plan record has already done (0 none, 1 occ(min), 2 both)
+        int stage = 0; int minT = -1;
+        const int64_t tp0 = fine ? now_ns() : 0;
+        if (fine) { dbg_step_ns += tp0 - tq0; }
+        struct PlanT { int64_t t0; int64_t* acc; bool on; ~PlanT() { if (on) { *acc += now_ns() - t0; } } } plant{tp0, &dbg_plan_ns, fine && cur_plan >= 0};
+        if (cur_plan >= 0) {
+            const PlanEnt* pp = &plan[(size_t)cur_plan];
+            if (C[cr].ver != pp->ver || pp->min < 0) {             // not the planned content: one of the predicted versions?
+                const std::vector<PlanEnt>& pa = plan_alt[pp->t]; const PlanEnt* f = nullptr;
+                for (int32_t a = pp->alt; a >= 0; a = pa[(size_t)a].alt) {
+                    const PlanEnt& x = pa[(size_t)a];
+                    if (x.lit_n == C[cr].size && !memcmp(c_str.lits.data() + x.lit_off, CL(cr), sizeof(int32_t) * x.lit_n)) { f = &x; break; }
+                }
+                pp = f;
+                if (f) { ++n_spec_used; }
+            }
+            static const PlanEnt none{0, 0, -1, 0, 0, 0, 0, 0, 0, 0, 0, -1};
+            const PlanEnt& pe = pp ? *pp : none;
+            if (pe.min >= 0 && static_valid && static_lazy && !hasToPropagate() && !hasStale(pe.min) && !hasStale(pe.min ^ 1) &&
+                (unlimited || str_steps + (int64_t)pe.steps1 + (int64_t)pe.steps2 + 1 < str_lim)) {
+                const Hit* hc = plan_c[pe.t].data();
+                minT = pe.min;
+                if (pe.cb == pe.c2) { ++n_fast; } else { ++n_slow; }
+                if (pre_active) { scanned_dyn[pe.min] = 1; }
+                str_steps += pe.steps1;
+                for (uint32_t k = pe.cb; k < pe.c1; ++k) {
+                    const uint32_t other = hc[k].clause;
+                    if (isDel(other) || !strHitValid(cr, other, hc[k].lit, pe.scan)) { continue; }
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == hc[k].lit) { pos = (int)k2; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+                stage = 1;
+                if (!hasToPropagate()) {
+                    if (pre_active) { scanned_dyn[pe.min ^ 1] = 1; }
+                    str_steps += pe.steps2;
+                    for (uint32_t k = pe.c1; k < pe.c2; ++k) {
+                        const uint32_t other = hc[k].clause;
+                        if (isDel(other) || !strHitValid(cr, other, hc[k].lit, pe.scan)) { continue; }
+                        const int32_t* t = CL(other); int pos = -1;
+                        for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == hc[k].lit) { pos = (int)k2; break; } }
+                        if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                    }
+                    stage = 2;
+                    if (!hasToPropagate()) { C[cr].flag &= ~F_STR; continue; }
+                }
+            }
+        }
+        if (stage == 0) { const int32_t* s = CL(cr); minT = s[0];
+          for (uint32_t j = 1; j < C[cr].size; ++j) { if (dcount(minT >> 1) > dcount(s[j] >> 1)) { minT = s[j]; } } }
+        const int min = minT, nmin = lneg(minT);
+        const int64_t th0 = fine ? now_ns() : 0;
+        const CacheEnt* e = strHits(cr);
+        if (fine) { dbg_hits_ns += now_ns() - th0; }
+        if (stage == 0 && e->hb == e->he && !hasStale(min) && !hasStale(nmin) && !hasToPropagate() &&
+            (unlimited || str_steps + (int64_t)hot[min].n + (int64_t)hot[nmin].n < str_lim)) {
+            // no candidate can hit and no list needs lazy cleaning: only the step counters move
+            str_steps += (hot[min].n ? (int64_t)hot[min].n - 1 : 0) + (int64_t)hot[nmin].n;
+            C[cr].flag &= ~F_STR;
+            ++n_fast;
+            if (pre_active) { scanned_dyn[min] = 1; scanned_dyn[nmin] = 1; }    // walked (found nothing to do)
+            continue;
+        }
+        if (stage == 0) { ++n_slow; }
+        const int64_t ts0 = fine ? now_ns() : 0;
+        struct SlowT { int64_t t0; int64_t* acc; bool on; ~SlowT() { if (on) { *acc += now_ns() - t0; } } } slowt{ts0, &dbg_slow_ns, fine};
+        if (pre_active) { scanned_dyn[min] = 1; }
+        // pass 1: occ(min) - the complementary literal is any literal but min
+        if (stage < 1) {
+            ListRef list = L(min);
+            for (uint32_t j = 0; j < list.n && (unlimited || str_steps < str_lim); ++j) {
+                const uint32_t other = LP(list)[j];
+                if (other == cr) { continue; }
+                str_steps++;
+                // (Subsumption.cc:1331 breaks on an empty clause; one can only exist after ok became false, and
+                //  every path that creates it returns before this loop is reached again)
+                if (isDel(other)) { occSwapRemove(min, j); --j; continue; }
+                if (e->hb == e->he) { continue; }
+                const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
+                if (h && h->lit != nmin && strHitValid(cr, other, h->lit, e->scan)) {
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k = 0; k < C[other].size; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+            }
+        }
+        if (stage < 2 && hasToPropagate()) {
+            leaveLazy();
+            static_valid = false;            // counts and lists move now: the precomputed entries are void
+            rollbackPrecompact();
+            if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
+            e = strHits(cr);                 // cr itself may have been shortened by the propagation
+        }
+        if (pre_active) { scanned_dyn[nmin] = 1; }
+        // pass 2: occ(~min) - the complementary literal must be ~min
+        if (stage < 2) {
+            ListRef list_neg = L(nmin);
+            for (uint32_t j = 0; j < list_neg.n && (unlimited || str_steps < str_lim); ++j) {
+                const uint32_t other = LP(list_neg)[j];
+                str_steps++;
+                if (isDel(other)) { occSwapRemove(nmin, j); --j; continue; }
+                if (e->hb == e->he) { continue; }
+                const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
+                if (h && h->lit == nmin && strHitValid(cr, other, h->lit, e->scan)) {
+                    const int32_t* t = CL(other); int pos = -1;
+                    for (uint32_t k = 0; k < C[other].size; ++k) { if (t[k] == h->lit) { pos = (int)k; break; } }
+                    if (pos >= 0) { strengthenHit(localQueue, other, pos); }
+                }
+            }
+        }
+        if (hasToPropagate()) {
+            leaveLazy();
+            static_valid = false;
+            rollbackPrecompact();
+            if (propagationProcess(true, useHeap, ignore) == L_FALSE) { ret = L_FALSE; early = true; break; }
+            t_sub.modified = t_sub.modified || t_up.modified;
+        }
+        C[cr].flag &= ~F_STR;
+    }
+    lap("ordered");
+    if (fine) { fprintf(stderr, "  str slow entries %.1f ms, strHits %.1f ms, stepping %.1f ms, planned entries (whole) %.1f ms\n", dbg_slow_ns / 1e6, dbg_hits_ns / 1e6, dbg_step_ns / 1e6, dbg_plan_ns / 1e6); dbg_slow_ns = 0; dbg_hits_ns = 0; dbg_step_ns = 0; dbg_plan_ns = 0; }
+    if (!early) {
+        updateOccurrences(useHeap, ignore);
+        ret = ok ? L_UNDEF : L_FALSE;
+    }
+    lap("updateOcc");
+    for (uint32_t c : strq) { if (c < qtime.size()) { qtime[c] = -1; } }
+    if (lap.on) { fprintf(stderr, "  str lazy entries %lld, lazy still on %d\n", (long long)n_lazy, (int)static_lazy); }
+    static_pass = false; static_lazy = false; n_fast += n_lazy; n_static += n_lazy; n_lazy = 0;
+    if (getenv("CP3_DEBUG_PRE")) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }
+    pre_active = false;
+    host_ns_commit += now_ns() - t0;
+    return ret;
+}
+
+// fullStrengthening with -naive_strength, Subsumption.cc:1056-1197: the queue runs front to back, every literal of the
+// strengthener is flipped in turn and the walk goes over occ(min) - or occ(~min) when the flipped literal is min itself.  The
+// candidates a walk can hit are the K4 hits of the strengthener whose literal is the flipped one (K4 finds every clause that
+// contains the strengthener with exactly one literal complemented, whichever list pair it scanned).
+int Engine::naiveStrengthening(bool useHeap, int ignore)
+{
+    PhaseTimer pt(ph_str);
+    const bool unlimited = !opt.limited;
+    ensureHostLists();
+    logClear(); dirty_str.clear();
+    if (str_prepared) { str_prepared = false; }
+    else if (opt.strength) {
+        std::vector<uint32_t> ids;
+        for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { ids.push_back(c); } }
+        sortUnique(ids);
+        c_str.clear();
+        scanClauses(CP3G_STRENGTHEN, ids, c_str);
+    } else { c_str.clear(); }
+    const int64_t t0 = now_ns();
+    std::vector<uint32_t> localQueue;
+    int ret = L_UNDEF; bool early = false;
+    for (size_t i = 0; i < strq.size();) {
+        uint32_t cr;
+        if (localQueue.empty()) { cr = strq[i]; ++i; }
+        else { cr = localQueue.back(); localQueue.pop_back(); }
+        if ((C[cr].flag & F_DEL) || !(C[cr].flag & F_STR)) { continue; }
+        if (!opt.strength) { C[cr].flag &= ~F_STR; continue; }
+        const uint32_t cn = C[cr].size;
+        int min = CL(cr)[0];
+        for (uint32_t j = 1; j < cn; ++j) {
+            const int x = CL(cr)[j];
+            if ((int64_t)hot[min].cnt * (cn - 1) + hot[min ^ 1].cnt > (int64_t)hot[x].cnt * (cn - 1) + hot[x ^ 1].cnt) { min = x; }
+        }
+        const CacheEnt* e = cn >= 2 ? strHits(cr) : nullptr;
+        const uint32_t hb = e ? e->hb : 0, he = e ? e->he : 0, escan = e ? e->scan : 0;
+        for (uint32_t j = 0; j < cn && (unlimited || str_steps < str_lim); ++j) {
+            const int neg_lit = CL(cr)[j] ^ 1;
+            const int lx = (neg_lit == (min ^ 1)) ? neg_lit : min;
+            for (uint32_t k = 0; k < hot[lx].n && (unlimited || str_steps < str_lim); ++k) {
+                const uint32_t other = occ_pool[occ[lx].off + k];
+                if (other == cr) { continue; }
+                str_steps++;
+                if (isDel(other)) { occSwapRemove(lx, k); --k; continue; }
+                if (hb == he) { continue; }
+                const Hit* h = findHit(c_str.hits, hb, he, other);
+                if (!h || h->lit != neg_lit || !strHitValid(cr, other, h->lit, escan)) { continue; }
+                const int32_t* t = CL(other); int pos = -1;
+                for (uint32_t k2 = 0; k2 < C[other].size; ++k2) { if (t[k2] == neg_lit) { pos = (int)k2; break; } }
+                if (pos < 0) { continue; }
+                ++removedLiterals;
+                removePosSorted(other, pos);
+                noteShrunk(other, neg_lit, true);
+                dirty_str.push_back(other);
+                t_sub.modified = true;                               // modifiedFormula = true: the penalty peak stays as it is
+                if (C[other].size == 1) {
+                    setDeleted(other);
+                    dataEnqueue(CL(other)[0]);
+                } else {
+                    if (!(C[other].flag & F_SUB)) { C[other].flag |= F_SUB; subq.push_back(other); }
+                    if (!(C[other].flag & F_STR)) { localQueue.push_back(other); C[other].flag |= F_STR; }
+                    occ_upd.push_back({other, neg_lit});
+                }
+            }
+        }
+        if (hasToPropagate()) {
+            if (propagationProcess(true, false, VAR_UNDEF) == L_FALSE) { ok = false; ret = L_FALSE; early = true; break; }
+        }
+        C[cr].flag &= ~F_STR;
+    }
+    if (!early) { updateOccurrences(useHeap, ignore); }
+    host_ns_commit += now_ns() - t0;
+    return ret;
+}
+
+// Subsumption::process, Subsumption.cc:85-180
+bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
+{
+    t_sub.modified = false; str_prepared = false;
+    if (!ok) { return false; }
+    if (!performSimplification(t_sub)) {
+        clearQueue(subq, F_SUB); clearQueue(strq, F_STR);
+        return false;
+    }
+    // (the technique-level size gates - Subsumption.cc:102, BVE.cc:180-184: cp3_susi_* / cp3_bve_* - can never fire: they need
+    //  nTotLits() > limit, and cleanSolver() (Coprocessor.cc:1395-1406) zeroes clauses_literals before any technique runs;
+    //  verified against the compiled reference with all limits set to 10.  The options are accepted and have no effect.)
+    if (!(sub_steps + opt.call_inc < sub_lim)) { sub_lim += opt.call_inc; limitIncreases++; }
+    if (!(str_steps + opt.call_inc < str_lim)) { str_lim += opt.call_inc; limitIncreases++; }
+    while (ok && (!subq.empty() || !strq.empty())) {
+        if (!subq.empty()) {
+            overlap_str = doStrengthen && !strq.empty();
+            subsumptionWorker(useHeap, ignore);
+            overlap_str = false;
+            clearQueue(subq, F_SUB);
+        }
+        if (!strq.empty()) {
+            if (!doStrengthen) { clearQueue(strq, F_STR); continue; }
+            if (opt.naive_strength) { naiveStrengthening(useHeap, ignore); } else { strengtheningWorker(useHeap, ignore); }
+            clearQueue(strq, F_STR);
+        }
+        str_prepared = false;
+    }
+    t_sub.modified = t_sub.modified || t_up.modified;   // propagation.appliedSomething(): its last call
+    if (!t_sub.modified) { unsuccessful(t_sub); }
+    return t_sub.modified;
+}
+
+} // namespace cp3

@@ -13,7 +13,11 @@ cases = [("planted 3-SAT 100k", gen.random_ksat(100000, 426000, 3, seed=71), FUL
          ("community 100k limited", gen.community_ksat(100000, 500000, seed=74), ["-enabled_cp3", "-subsimp", "-bve"]),
          ("zipf 0.9 60k susi", gen.random_ksat(60000, 255600, 3, seed=75, zipf_s=0.9), ["-enabled_cp3", "-subsimp", "-no-cp3_limited"]),
          ("zipf 0.7 60k full", gen.random_ksat(60000, 255600, 3, seed=76, zipf_s=0.7), FULL),
-         ("4-SAT 80k", gen.random_ksat(80000, 700000, 4, seed=77), FULL + ["-bve_BCElim"])]
+         ("4-SAT 80k", gen.random_ksat(80000, 700000, 4, seed=77), FULL + ["-bve_BCElim"]),
+         ("community 100k riss427-style + bce", gen.community_ksat(100000, 500000, seed=78), FULL + ["-bce", "-dense"]),
+         ("planted 3-SAT 100k bce only", gen.random_ksat(100000, 426000, 3, seed=79), ["-enabled_cp3", "-bce", "-no-cp3_limited"]),
+         ("planted 3-SAT 100k naive strengthening", gen.random_ksat(100000, 426000, 3, seed=80), ["-enabled_cp3", "-subsimp", "-naive_strength", "-no-cp3_limited"]),
+         ("community 100k heap order 5", gen.community_ksat(100000, 500000, seed=81), FULL + ["-cp3_bve_heap=5"])]
 bad = 0
 for name, (lits, sizes), opts in cases:
     stream = gen.csr_to_stream(lits, sizes)

@@ -17,7 +17,7 @@ cases["all binary"] = gen.csr_to_stream(*gen.random_ksat(500, 800, 2, seed=8))
 cases["wide clauses k=9"] = gen.csr_to_stream(*gen.random_ksat(3000, 9000, 9, seed=9))
 bad = 0
 for name, st in cases.items():
-    for opts in (FULL, FULL + ["-dense"]):
+    for opts in (FULL, FULL + ["-dense"], FULL + ["-bce"]):
         a = run_engine(st, opts); b = run_oracle(st, opts)
         hu = bool(((np.diff(np.concatenate([[-1], np.flatnonzero(st == 0)])) - 1) == 1).any()) if st.size else False
         d = compare(a, b)

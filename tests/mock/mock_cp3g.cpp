@@ -1,7 +1,7 @@
 // mock_cp3g.cpp - TEST INFRASTRUCTURE ONLY.  A CPU stand-in for the cp3g_* scan service so that the host
-// engine's ordered-commit logic (riss-solver_b200/csrc/engine.cpp) can be differential-tested against the
+// engine's ordered-commit logic (riss-solver_b200/csrc/engine*.cpp) can be differential-tested against the
 // oracle on machines without a GPU (`pytest -m "not gpu"`).  It is compiled into tests/_build/
-// libcp3b200_mock.so together with engine.cpp and capi.cpp; the product library libcp3b200.so never
+// libcp3b200_mock.so together with engine*.cpp and capi.cpp; the product library libcp3b200.so never
 // contains it and has no CPU path.  The mock answers exactly what the kernels answer (sets of hits).
 #include <algorithm>
 #include <cstring>

@@ -1,4 +1,4 @@
-"""Host logic of the product (ordered-commit engine + C ABI, riss-solver_b200/csrc/engine.cpp, capi.cpp) linked
+"""Host logic of the product (ordered-commit engine + C ABI, riss-solver_b200/csrc/engine*.cpp, capi.cpp) linked
 against the CPU mock of the scan service (tests/mock) - no GPU needed.  The mock answers what the kernels answer,
 so these tests pin the commit order, the bookkeeping quirks and the speculative-closure cache against the oracle."""
 import json
