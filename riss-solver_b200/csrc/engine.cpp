@@ -14,8 +14,7 @@ void Engine::ScanCache::clear()
 Engine::Engine()
 {
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
-    const char* e = getenv("CP3_THREADS");
-    nthreads = e ? atoi(e) : (int)std::min(24u, std::max(1u, std::thread::hardware_concurrency()));
+    nthreads = tune.threads;
     if (nthreads < 1) { nthreads = 1; }
 }
 Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
@@ -165,7 +164,7 @@ void Engine::addLit(int x)
 // adding is order dependent), short streams and later additions take the literal-by-literal path.
 void Engine::addStream(const int32_t* s, size_t n)
 {
-    static const size_t bulk_min = getenv("CP3_INGEST_MIN") ? (size_t)atoll(getenv("CP3_INGEST_MIN")) : (size_t)262144;
+    const size_t bulk_min = tune.ingest_min;
     if (n >= bulk_min && C.empty() && cur.empty() && trail.empty() && ok && !ing_built && clauses.empty() && cp3g_device_count() > 0) {
         size_t m = n;
         while (m > 0 && s[m - 1] != 0) { --m; }                    // complete clauses only
@@ -322,7 +321,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
     ++scan_id; ++n_scan_batches;
     pgrow(cache.slot, C.size(), -1);
     // deleted clauses that still act as strengthener (Subsumption.cc:1438) must be sent by content
-    static const uint32_t bulk_min = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
+    const uint32_t bulk_min = tune.bulk_min;
     bool bulk = forceBulk == 1;
     if (forceBulk < 0 && ids.size() == n_live && n_live > bulk_min) {
         bool any_del = false;
@@ -432,7 +431,7 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
         die("speculative scan failed");
     }
     host_ns_gpuwait += now_ns() - t0;
-    if (getenv("CP3_DEBUG_PAR")) { fprintf(stderr, "  scanSpeculative gpu call %.1f ms, %zu reqs, %u hits\n", (now_ns() - t0) / 1e6, reqs.size(), n); }
+    if (tune.debug_par) { fprintf(stderr, "  scanSpeculative gpu call %.1f ms, %zu reqs, %u hits\n", (now_ns() - t0) / 1e6, reqs.size(), n); }
     sortHits(hitbuf, n);
     uint32_t h = 0;
     for (uint32_t i = 0; i < reqs.size(); ++i) {

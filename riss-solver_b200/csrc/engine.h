@@ -54,6 +54,22 @@ struct Options {
 
 struct Tech { int penalty = 0, peak = 0; bool modified = false; };
 
+// Size thresholds and switches of the host engine: where a data-parallel form takes over from the plain ordered walk.  One place,
+// read from the environment once per engine (CP3_<NAME>); the tests force the large-queue forms onto tiny formulas with them.
+struct Tuning {
+    int threads;                 // CP3_THREADS: host cores of the parallel phases (default: all, at most 24)
+    size_t ingest_min;           // CP3_INGEST_MIN: stream length from which CPaddLits goes through the device bulk ingest K0
+    uint32_t bulk_min;           // CP3_BULK_MIN: live clauses from which a queue of all of them is scanned by the full-queue kernel
+    size_t parsub_min;           // CP3_PARSUB_MIN: queue length from which the subsumption commit is time-indexed (device or all cores)
+    size_t static_min;           // CP3_STATIC_MIN: queue length from which a strengthening pass gets the static plan
+    uint64_t touched_min;        // CP3_TOUCHED_MIN: occurrences from which the touched-variable queueing of BVE runs on all cores
+    uint32_t devcommit_maxlist;  // CP3_DEVCOMMIT_MAXLIST: longest list with deaths that one device thread may replay
+    uint64_t bce_maxwords;       // CP3_BCE_MAXWORDS: K9 mask words per variable in the batch (longer: rows on demand)
+    bool no_devcommit, no_overlap, no_precompact, no_lazy, no_plan, no_bve_eval, no_bve_prefetch;   // CP3_NO_<...>=1: switch one form off
+    bool debug_par, debug_bve, debug_fine, debug_ondemand, debug_pre;                                // CP3_DEBUG_<...>: phase timers on stderr
+    Tuning();
+};
+
 // std::vector whose resize() leaves trivially constructible elements uninitialised: the big work arrays are filled by a
 // device download or by a parallel loop right after they are sized, a serial zero fill first would only cost bandwidth
 template <class T> struct NoInitAlloc : std::allocator<T> {
@@ -79,6 +95,7 @@ public:
     Engine();
     ~Engine();
     Options opt;
+    const Tuning tune;
 
     // --- Solver-side interface used by the CP* layer
     void addLit(int dimacsLit);

@@ -13,7 +13,7 @@ void Engine::bceBuildMasks()
     const size_t nv = (size_t)nvars;
     bce_woff.resize(nv + 1); bce_row_var = -1;
     std::vector<uint32_t> vars, p_off{0}, n_off{0}; std::vector<uint64_t> w_off{0};
-    static const uint64_t row_cap = getenv("CP3_BCE_MAXWORDS") ? (uint64_t)atoll(getenv("CP3_BCE_MAXWORDS")) : (1ull << 22);   // words per variable
+    const uint64_t row_cap = tune.bce_maxwords;                      // words per variable
     for (size_t v = 0; v < nv; ++v) {
         bce_woff[v] = UINT64_MAX;
         const uint32_t np = hot[2 * v].n, nn = hot[2 * v + 1].n;

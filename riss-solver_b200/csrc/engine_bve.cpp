@@ -499,17 +499,17 @@ void Engine::bvePrefetchStep()
 void Engine::bveWorker()
 {
     const bool unlimited = !opt.limited;
-    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr || getenv("CP3_DEBUG_BVE") != nullptr;
+    const bool dbg = tune.debug_par || tune.debug_bve;
     int64_t tg = 0, tc = 0, ta = 0, tr = 0, trm = 0, ts = 0, tl = dbg ? now_ns() : 0;
     auto lapt = [&](int64_t& acc) { if (dbg) { const int64_t n2 = now_ns(); acc += n2 - tl; tl = n2; } };
     struct Rep { bool on; int64_t &tg, &tc, &ta, &tr, &trm, &ts; ~Rep() { if (on) { fprintf(stderr, "  bveWorker: heap+gates %.1f ms, clean %.1f, anticipate %.1f, resolveSet %.1f, removeClauses %.1f, inner subsumption %.1f\n", tg / 1e6, tc / 1e6, ta / 1e6, tr / 1e6, trm / 1e6, ts / 1e6); } } } rep{dbg, tg, tc, ta, tr, trm, ts};
-    static const bool no_eval = getenv("CP3_NO_BVE_EVAL") != nullptr;
+    const bool no_eval = tune.no_bve_eval;
     // (-bve_early makes the anticipation depend on the global growth budget; in sharded mode every rank evaluates the whole batch -
     //  the replicas hold the identical data base, nothing has to be exchanged)
     const bool use_eval = !no_eval && !opt.bve_early;
     pairs_single = use_eval;
     struct InWorker { bool& f; explicit InWorker(bool& x) : f(x) { f = true; } ~InWorker() { f = false; } } in_worker(in_bve_worker);
-    static const bool no_pf = getenv("CP3_NO_BVE_PREFETCH") != nullptr;
+    const bool no_pf = tune.no_bve_prefetch;
     bve_pf_n = 0;
     size_t skip_run = 0, skip_check_at = 1024;
     while (!heap.empty() && (bve_steps < opt.bve_limit || unlimited)) {
@@ -696,7 +696,7 @@ void Engine::addTouchedToSubsumption()
     std::vector<uint64_t> off(2 * nt + 1, 0);
     for (size_t i = 0; i < nt; ++i) { off[2 * i + 1] = off[2 * i] + hot[2 * touched[i]].n; off[2 * i + 2] = off[2 * i + 1] + hot[2 * touched[i] + 1].n; }
     const uint64_t total = off[2 * nt];
-    static const uint64_t par_min = getenv("CP3_TOUCHED_MIN") ? (uint64_t)atoll(getenv("CP3_TOUCHED_MIN")) : 262144;
+    const uint64_t par_min = tune.touched_min;
     if (total < par_min || total >= 0xffffffffull || nthreads < 2) {
         for (int v : touched) { addClausesToSubsumption(2 * v); addClausesToSubsumption(2 * v + 1); }
         return;
@@ -736,7 +736,7 @@ void Engine::addTouchedToSubsumption()
 void Engine::sequentiellBVE()
 {
     const bool unlimited = !opt.limited;
-    static const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr || getenv("CP3_DEBUG_BVE") != nullptr;
+    const bool dbg = tune.debug_par || tune.debug_bve;
     int64_t tl = dbg ? now_ns() : 0;
     auto lapb = [&](const char* w) { if (dbg) { const int64_t n2 = now_ns(); fprintf(stderr, "  seqBVE %s %.1f ms\n", w, (n2 - tl) / 1e6); tl = n2; } };
     subsumptionProcess(opt.bve_strength, false, VAR_UNDEF);

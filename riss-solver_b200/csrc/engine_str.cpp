@@ -42,7 +42,7 @@ const Engine::CacheEnt* Engine::strHits(uint32_t cr)
     const CacheEnt* e = cached(c_str, cr);
     if (e) { if (e->ver == UINT32_MAX) { ++n_spec_used; } return e; }
     ++n_ondemand;
-    if (getenv("CP3_DEBUG_ONDEMAND") && n_ondemand < 12) {
+    if (tune.debug_ondemand && n_ondemand < 12) {
         fprintf(stderr, "ondemand cr=%u size=%u ver=%u stamp=%u flag=%u slot=%d bulk_all=%d bulk_scan=%u bulk_ncl=%u qtime=%d\n", cr, (unsigned)C[cr].size, C[cr].ver, C[cr].stamp,
                 (unsigned)C[cr].flag, cr < c_str.slot.size() ? c_str.slot[cr] : -9, (int)c_str.bulk_all, c_str.bulk_scan, c_str.bulk_ncl, cr < qtime.size() ? qtime[cr] : -9);
         for (int32_t i = cr < c_str.slot.size() ? c_str.slot[cr] : -1; i >= 0; i = c_str.ent[i].next) {
@@ -161,7 +161,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
     DbgLap lap("str"); lap("prepare");
-    const bool fine = lap.on && getenv("CP3_DEBUG_FINE") != nullptr;          // per-entry timers (they cost as much as the entries)
+    const bool fine = lap.on && tune.debug_fine;          // per-entry timers (they cost as much as the entries)
     int64_t t0 = now_ns();
     // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
     // are frozen during this pass (occurrence updates are deferred, Subsumption.cc:1400,1523), so an entry that
@@ -169,7 +169,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
     // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
     pfill(contrib, strq.size(), -1); pfill(contrib_t, strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
-    static const size_t static_min = getenv("CP3_STATIC_MIN") ? (size_t)atoi(getenv("CP3_STATIC_MIN")) : 4096;
+    const size_t static_min = tune.static_min;
     bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
     if (static_valid) {
         is_target.assign((C.size() >> 6) + 1, 0ull);
@@ -213,7 +213,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         //     clause dies during this pass unless a unit shows up.  So the certainly-walked lists are cleaned
         //     up front, on all cores, each costing one step per removed entry like the lazy walk would.
         pre_lists.clear(); pre_snap.clear(); pre_active = false;
-        static const bool no_pre = getenv("CP3_NO_PRECOMPACT") != nullptr;
+        const bool no_pre = tune.no_precompact;
         if (!no_pre && (unlimited || str_steps + 2 * total_bound < str_lim)) {
             const size_t nlit = (size_t)2 * nvars;
             const size_t words = (nlit + 63) / 64;
@@ -243,7 +243,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         lap("precompact");
         // (3) step contribution of the inert entries.  Far from the step limit their whole effect is applied here
         //     (flag cleared, walked lists recorded) and the ordered walk below only adds the number up.
-        static const bool no_lazy = getenv("CP3_NO_LAZY") != nullptr;
+        const bool no_lazy = tune.no_lazy;
         const bool lazy = !no_lazy && (unlimited || str_steps + 2 * total_bound < str_lim);
         static_lazy = lazy; n_lazy = 0; cur_end = nq;
         if (lazy) { last_static_walk.assign((size_t)2 * nvars, -1); }
@@ -307,7 +307,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     // then only validates and applies the candidate hits (the order-dependent part).  Everything else takes the walk itself.
     struct PlanEnt { uint32_t ver, scan; int32_t min; uint32_t steps1, steps2, cb, c1, c2; uint32_t t; uint32_t lit_off, lit_n; int32_t alt; };
     RawVec<PlanEnt> plan; std::vector<std::vector<Hit>> plan_c((size_t)nthreads + 1); std::vector<std::vector<PlanEnt>> plan_alt((size_t)nthreads + 1);
-    static const bool no_plan = getenv("CP3_NO_PLAN") != nullptr;
+    const bool no_plan = tune.no_plan;
     const bool planned = static_lazy && !no_plan && !reals.empty();
     if (planned) {
         const size_t nq = strq.size();
@@ -588,7 +588,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     for (uint32_t c : strq) { if (c < qtime.size()) { qtime[c] = -1; } }
     if (lap.on) { fprintf(stderr, "  str lazy entries %lld, lazy still on %d\n", (long long)n_lazy, (int)static_lazy); }
     static_pass = false; static_lazy = false; n_fast += n_lazy; n_static += n_lazy; n_lazy = 0;
-    if (getenv("CP3_DEBUG_PRE")) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }
+    if (tune.debug_pre) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }
     pre_active = false;
     host_ns_commit += now_ns() - t0;
     return ret;

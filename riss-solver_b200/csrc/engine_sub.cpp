@@ -27,7 +27,7 @@ bool Engine::subsumptionCommitParallel()
 {
     const size_t nq = subq.size();
     const int32_t INF = INT32_MAX;
-    const bool dbg = getenv("CP3_DEBUG_PAR") != nullptr; int64_t tt = now_ns();
+    const bool dbg = tune.debug_par; int64_t tt = now_ns();
     auto lap = [&](const char* w) { if (dbg) { int64_t n2 = now_ns(); fprintf(stderr, "  parsub %s %.1f ms\n", w, (n2 - tt) / 1e6); tt = n2; } };
     if (sub_dtime.size() < C.size()) { pgrow(sub_dtime, C.size() + 1024, INF); pgrow(sub_pos, C.size() + 1024, -1); }
     // step 0: queue position of every clause; a clause queued twice falls back to the ordered walk
@@ -230,8 +230,8 @@ void Engine::ensureHostLists()
 // order and does the O(#subsumed) bookkeeping of subsumptionCommitParallel's last step.
 bool Engine::subsumptionCommitDevice()
 {
-    static const bool off_env = getenv("CP3_NO_DEVCOMMIT") != nullptr;
-    static const uint32_t max_list = getenv("CP3_DEVCOMMIT_MAXLIST") ? (uint32_t)atoi(getenv("CP3_DEVCOMMIT_MAXLIST")) : 4096u;
+    const bool off_env = tune.no_devcommit;
+    const uint32_t max_list = tune.devcommit_maxlist;
     if (off_env || !lists_on_device || !dev_uploaded || !pend_del.empty() || !pend_shrunk.empty() || dev_ncl != C.size()) { return false; }
     const size_t nq = subq.size();
     if (nq != n_live || nq == 0) { return false; }
@@ -294,7 +294,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     c_sub.clear(); logClear();
     lap0("clear");
     if (lists_on_device) {
-        static const size_t parsub_min0 = getenv("CP3_PARSUB_MIN") ? (size_t)atoi(getenv("CP3_PARSUB_MIN")) : 65536;
+        const size_t parsub_min0 = tune.parsub_min;
         bool far = unlimited;
         if (!far && !useHeap && subq.size() >= parsub_min0) {      // the device commit cannot stop in the middle of the queue: only far from the step limit
             std::vector<int64_t> part((size_t)nthreads + 1, 0);
@@ -321,7 +321,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     }
     DbgLap lap("sub"); lap("start(after scan)");
     int64_t t0 = now_ns();
-    static const size_t parsub_min = getenv("CP3_PARSUB_MIN") ? (size_t)atoi(getenv("CP3_PARSUB_MIN")) : 65536;
+    const size_t parsub_min = tune.parsub_min;
     if (!useHeap && subq.size() >= parsub_min) {
         // step limit: the data-parallel form cannot stop in the middle of the queue; only use it far from the limit
         int64_t bound = 0;
@@ -329,13 +329,13 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
         if (unlimited || sub_steps + bound < sub_lim) {
             // the strengthening pass that follows needs nothing from this commit but the deleted flags (a hit on a
             // clause that dies meanwhile is dropped at commit time): run its scan + closure concurrently
-            static const bool no_overlap = getenv("CP3_NO_OVERLAP") != nullptr;
+            const bool no_overlap = tune.no_overlap;
             std::thread helper; std::vector<uint32_t> sids; bool sbulk = false;
             const bool ov = overlap_str && !no_overlap && nthreads > 1 && opt.strength && strq.size() >= parsub_min && !hasToPropagate();
             if (ov) {
                 for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { sids.push_back(c); } }
                 sortUnique(sids);
-                static const uint32_t bulk_min2 = getenv("CP3_BULK_MIN") ? (uint32_t)atoi(getenv("CP3_BULK_MIN")) : 4096u;
+                const uint32_t bulk_min2 = tune.bulk_min;
                 sbulk = sids.size() == n_live && n_live > bulk_min2;
                 flushDevice();
                 scan_no_flush = true;
