@@ -2,8 +2,22 @@
 // CoprocessorData bookkeeping, unit propagation, Dense and the preprocess() driver.  The techniques live in engine_sub.cpp
 // (subsumption), engine_str.cpp (strengthening), engine_bve.cpp (BVE), engine_bce.cpp (BCE).  Reference lines are cited per function.
 #include "engine_util.h"
+#include <sys/mman.h>
+#include <new>
 
 namespace cp3 {
+
+void* hugeAlloc(size_t bytes)
+{
+    void* p;
+    if (bytes >= ((size_t)4 << 20)) {
+        const size_t al = (size_t)2 << 20, sz = (bytes + al - 1) & ~(al - 1);
+        p = aligned_alloc(al, sz);
+        if (p) { madvise(p, sz, MADV_HUGEPAGE); }
+    } else { p = malloc(bytes ? bytes : 1); }
+    if (!p) { throw std::bad_alloc(); }
+    return p;
+}
 
 void Engine::ScanCache::clear()
 {

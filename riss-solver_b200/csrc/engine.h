@@ -11,6 +11,7 @@
 // quirks (Subsumption.cc:85-180,220-314,1250-1544; Propagation.cc:32-131; BVE.cc:170-637).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -72,10 +73,16 @@ struct Tuning {
 
 // std::vector whose resize() leaves trivially constructible elements uninitialised: the big work arrays are filled by a
 // device download or by a parallel loop right after they are sized, a serial zero fill first would only cost bandwidth
+// Blocks of 4 MB and more are 2 MB aligned and marked MADV_HUGEPAGE: the queue walks and per-literal gathers are random accesses
+// over arrays of 50-900 MB, where every access misses a 4 KB-page TLB (and the first touch faults page by page).  Only the engine's
+// own blocks are touched - no process-wide policy.
+void* hugeAlloc(size_t bytes);
 template <class T> struct NoInitAlloc : std::allocator<T> {
     template <class U> struct rebind { typedef NoInitAlloc<U> other; };
     NoInitAlloc() = default;
     template <class U> NoInitAlloc(const NoInitAlloc<U>&) {}
+    T* allocate(size_t n) { return (T*)hugeAlloc(n * sizeof(T)); }
+    void deallocate(T* p, size_t) { free(p); }
     template <class U> void construct(U* p) { (void)p; }
     template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
 };

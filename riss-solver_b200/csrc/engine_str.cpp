@@ -401,7 +401,9 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                             if (o < qtime.size() && qtime[o] >= 0) { const size_t po = static_nq - 1 - (size_t)qtime[o]; if (po < contrib.size()) { __builtin_prefetch(&contrib[po]); __builtin_prefetch(&walk_min[po]); } } } }
                     }
                 }
-                if (ri > 8) {                                        // look ahead: the clause, its counters and its scan record
+                if (planned) {                                       // the record of a planned entry needs its clause header only
+                    if (ri > 10) { const uint32_t c2 = strq[reals[ri - 10]]; __builtin_prefetch(&C[c2]); }
+                } else if (ri > 8) {                                 // look ahead: the clause, its counters and its scan record
                     const uint32_t c2 = strq[reals[ri - 8]]; const ClauseInfo& ci2 = C[c2];
                     __builtin_prefetch(&ci2);
                     if (ri > 4) { const ClauseInfo& c3 = C[strq[reals[ri - 4]]]; const int32_t* l3 = pool.data() + c3.start; const uint32_t n3 = std::min<uint32_t>(c3.size, 6); for (uint32_t k = 0; k < n3; ++k) { __builtin_prefetch(&hot[l3[k] & ~1]); } }
@@ -409,7 +411,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 }
             }
             --end; cur_end = end;
-            if (end >= 24 && contrib[end - 24] < 0) {           // look ahead past the inert entries: the next real one
+            if (!static_lazy && end >= 24 && contrib[end - 24] < 0) {           // look ahead past the inert entries: the next real one
                 const ClauseInfo& c2 = C[strq[end - 24]]; const int32_t* l2 = pool.data() + c2.start;
                 const uint32_t n2 = std::min<uint32_t>(c2.size, 6);
                 for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
@@ -438,7 +440,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                 if (pre_active) { scanned_dyn[tmin[end]] = 1; scanned_dyn[tmin[end] ^ 1] = 1; }
                 continue;
             }
-            if (end >= 16) {
+            if (!static_lazy && end >= 16) {
                 const uint32_t c2 = strq[end - 16];
                 const int32_t* l2 = CL(c2); const uint32_t n2 = std::min<uint32_t>(C[c2].size, 6);
                 for (uint32_t k = 0; k < n2; ++k) { __builtin_prefetch(&hot[l2[k] & ~1]); }
