@@ -87,6 +87,15 @@ template <class T> struct NoInitAlloc : std::allocator<T> {
     template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*)p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
 };
 template <class T> using RawVec = std::vector<T, NoInitAlloc<T>>;
+// the same blocks for vectors that keep std::vector's value initialisation (per-clause / per-variable tables that are read at random)
+template <class T> struct HugeAlloc : std::allocator<T> {
+    template <class U> struct rebind { typedef HugeAlloc<U> other; };
+    HugeAlloc() = default;
+    template <class U> HugeAlloc(const HugeAlloc<U>&) {}
+    T* allocate(size_t n) { return (T*)hugeAlloc(n * sizeof(T)); }
+    void deallocate(T* p, size_t) { free(p); }
+};
+template <class T> using HVec = std::vector<T, HugeAlloc<T>>;
 
 struct Hit { uint32_t clause; int32_t lit; };
 
@@ -154,7 +163,7 @@ private:
     // ---------------- CoprocessorData mirror
     bool data_ready = false; int data_nvars = 0;      // CoprocessorData::numberOfVars: 0 until the first data.init()
     RawVec<OccList> occ; RawVec<LitHot> hot; RawVec<uint32_t> occ_pool;
-    std::vector<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
+    HVec<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
     inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
     inline bool hasStale(int x) const { return (stalebits[(uint32_t)x >> 6] >> (x & 63)) & 1; }
     inline void staleInc(int x) { if (stale[x]++ == 0) { stalebits[(uint32_t)x >> 6] |= 1ull << (x & 63); } }
@@ -162,7 +171,7 @@ private:
     inline void staleClear(int x) { stale[x] = 0; stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); }
     int numberOfCls = 0;
     std::vector<uint32_t> subq, strq; std::vector<int32_t> undo;
-    std::vector<uint32_t> modTimer; uint32_t modStep = 0;
+    HVec<uint32_t> modTimer; uint32_t modStep = 0;
     std::vector<uint32_t> ma; uint32_t ma_step = 0;
 
     // ---------------- technique state
@@ -172,7 +181,7 @@ private:
     int subsumedClauses = 0, subsumedLiterals = 0, removedLiterals = 0;
     int up_last = 0, up_removedClauses = 0, up_removedLiterals = 0;
     uint32_t bve_modtime = 0; int64_t bve_steps = 0;
-    std::vector<int> heap, hidx;
+    HVec<int> heap, hidx;
     int bve_removedClauses = 0, bve_removedLiterals = 0, bve_createdClauses = 0, bve_createdLiterals = 0,
         bve_testedVars = 0, bve_anticipations = 0, bve_eliminatedVars = 0, bve_removedBC = 0, bve_skippedVars = 0,
         bve_unitsEnqueued = 0, bve_foundGates = 0, bve_nInc = 0, bve_nDec = 0, bve_nKeep = 0, bve_totallyAdded = 0;
@@ -188,11 +197,11 @@ private:
     struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
     std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
-    std::vector<uint8_t> shrunk_mark;
+    HVec<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far
     // literals removed per clause during the current pass: per-clause chains in one flat node array
     struct LogNode { uint32_t stamp; int32_t lit; int32_t next; uint32_t pending; };
-    std::vector<LogNode> log_nodes; std::vector<int32_t> log_head; std::vector<uint32_t> log_touched;
+    HVec<LogNode> log_nodes; HVec<int32_t> log_head; std::vector<uint32_t> log_touched;
     uint32_t pend_epoch = 1;                         // LogNode.pending == pend_epoch: occ entry removal still pending
     void logClear();
     void logPush(uint32_t c, int lit, bool pendingOcc);
@@ -200,7 +209,7 @@ private:
     // scanned by id, or by the literal content itself (ver == UINT32_MAX) for speculative versions
     struct CacheEnt { uint32_t ver, scan, hb, he; int32_t next; uint32_t lit_off, lit_n; double time; };
     struct ScanCache {
-        RawVec<int32_t> slot; std::vector<CacheEnt> ent; std::vector<Hit> hits; std::vector<int32_t> lits;
+        RawVec<int32_t> slot; HVec<CacheEnt> ent; HVec<Hit> hits; HVec<int32_t> lits;
         // a full-queue bulk scan covers every clause that was live at that time: clauses without an entry had
         // no hit (no per-request record is kept for them)
         bool bulk_all = false; uint32_t bulk_scan = 0, bulk_ncl = 0; CacheEnt empty;
@@ -248,7 +257,7 @@ private:
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
     // BVE pair cache
-    std::vector<uint32_t> var_touch; std::vector<uint8_t> bve_inpend; std::vector<int> bve_pending;
+    HVec<uint32_t> var_touch; HVec<uint8_t> bve_inpend; std::vector<int> bve_pending;
     inline void bveTouch(int v) { ++var_touch[v]; if (!bve_inpend[v] && inHeap(v)) { bve_inpend[v] = 1; bve_pending.push_back(v); } }
     // K5/K6 results per variable: views into per-batch blocks (one allocation per batch, not per variable)
     template <class T> struct Span { const T* p = nullptr; size_t n = 0; size_t size() const { return n; } const T& operator[](size_t i) const { return p[i]; } };

@@ -48,7 +48,7 @@ static inline bool containsLit(const int32_t* l, uint32_t n, int x)
     return std::binary_search(l, l + n, x);
 }
 
-static inline const Hit* findHit(const std::vector<Hit>& hits, uint32_t hb, uint32_t he, uint32_t clause)
+template <class V> static inline const Hit* findHit(const V& hits, uint32_t hb, uint32_t he, uint32_t clause)
 {
     const Hit* b = hits.data() + hb; const Hit* e = hits.data() + he;
     const Hit* it = std::lower_bound(b, e, clause, [](const Hit& h, uint32_t c) { return h.clause < c; });
