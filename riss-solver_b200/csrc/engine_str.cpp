@@ -391,14 +391,16 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
                         const PlanEnt& pf = plan[ri - 5];
                         if (pf.min >= 0) {
                             const Hit* hc = plan_c[pf.t].data();
-                            for (uint32_t k = pf.cb; k < pf.c2; ++k) { const uint32_t o = hc[k].clause; __builtin_prefetch(&C[o]); if (o < log_head.size()) { __builtin_prefetch(&log_head[o]); } if (o < qtime.size()) { __builtin_prefetch(&qtime[o]); } if (o < shrunk_mark.size()) { __builtin_prefetch(&shrunk_mark[o]); } }
+                            for (uint32_t k = pf.cb; k < pf.c2; ++k) { const uint32_t o = hc[k].clause; __builtin_prefetch(&C[o], 1); if (o < log_head.size()) { __builtin_prefetch(&log_head[o], 1); } if (o < qtime.size()) { __builtin_prefetch(&qtime[o]); } if (o < shrunk_mark.size()) { __builtin_prefetch(&shrunk_mark[o], 1); } }
                         }
+                        // an entry with predicted contents compares its literals with them when its turn comes
+                        if (pf.alt >= 0) { __builtin_prefetch(pool.data() + C[strq[reals[ri - 5]]].start); __builtin_prefetch(c_str.lits.data() + plan_alt[pf.t][(size_t)pf.alt].lit_off); }
                     }
                     if (ri > 2) {
                         const PlanEnt& pf = plan[ri - 2];
                         if (pf.min >= 0) { const Hit* hc = plan_c[pf.t].data(); for (uint32_t k = pf.cb; k < pf.c2; ++k) {
-                            const uint32_t o = hc[k].clause; __builtin_prefetch(pool.data() + C[o].start);
-                            if (o < qtime.size() && qtime[o] >= 0) { const size_t po = static_nq - 1 - (size_t)qtime[o]; if (po < contrib.size()) { __builtin_prefetch(&contrib[po]); __builtin_prefetch(&walk_min[po]); } } } }
+                            const uint32_t o = hc[k].clause; __builtin_prefetch(pool.data() + C[o].start, 1);
+                            if (o < qtime.size() && qtime[o] >= 0) { const size_t po = static_nq - 1 - (size_t)qtime[o]; if (po < contrib.size()) { __builtin_prefetch(&contrib[po], 1); __builtin_prefetch(&walk_min[po]); } } } }
                     }
                 }
                 if (planned) {                                       // the record of a planned entry needs its clause header only
