@@ -19,6 +19,26 @@ void* hugeAlloc(size_t bytes)
     return p;
 }
 
+void Engine::sortUniqueIds(std::vector<uint32_t>& ids)
+{
+    if (ids.size() < std::max<size_t>(tune.par_min, 2) || nthreads < 2) { sortUnique(ids); return; }
+    bool inc = true;
+    for (size_t i = 1; i < ids.size() && inc; ++i) { inc = ids[i - 1] < ids[i]; }
+    if (inc) { return; }
+    // mark, count per chunk of words, extract in order
+    const size_t words = (C.size() + 63) / 64;
+    std::vector<uint64_t> bm(words, 0ull);
+    parallelFor(ids.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { __atomic_fetch_or(&bm[ids[i] >> 6], 1ull << (ids[i] & 63), __ATOMIC_RELAXED); } }, 8192);
+    std::vector<size_t> cnt((size_t)nthreads + 2, 0);
+    parallelFor(words, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t w = b; w < e; ++w) { c += (size_t)__builtin_popcountll(bm[w]); } cnt[(size_t)t + 1] = c; }, 4096);
+    for (size_t t = 1; t < cnt.size(); ++t) { cnt[t] += cnt[t - 1]; }
+    ids.resize(cnt.back());
+    parallelFor(words, [&](size_t b, size_t e, int t) {
+        size_t o = cnt[(size_t)t];
+        for (size_t w = b; w < e; ++w) { uint64_t x = bm[w]; while (x) { ids[o++] = (uint32_t)(w * 64 + (size_t)__builtin_ctzll(x)); x &= x - 1; } }
+    }, 4096);
+}
+
 void Engine::ScanCache::clear()
 {
     for (uint32_t c : used) { slot[c] = -1; }
@@ -363,6 +383,31 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
         cache.bulk_all = true; cache.bulk_scan = scan_id; cache.bulk_ncl = (uint32_t)C.size();
         cache.empty.ver = 0; cache.empty.scan = scan_id; cache.empty.hb = cache.empty.he = 0; cache.empty.next = -1;
         cache.empty.lit_off = cache.empty.lit_n = 0; cache.empty.time = 0;
+        if (n >= std::max<size_t>(tune.par_min, 1) && nthreads > 1 && cache.hits.empty() && cache.ent.empty()) {
+            // one record per run of equal `req` in the sorted hit list, built on all cores: run starts counted per chunk, prefix, fill
+            cache.hits.resize(n);
+            std::vector<size_t> cnt((size_t)nthreads + 2, 0);
+            parallelFor(n, [&](size_t b, size_t e, int t) {
+                size_t c2 = 0;
+                for (size_t h = b; h < e; ++h) { cache.hits[h] = Hit{hitbuf[h].clause, hitbuf[h].lit}; c2 += (h == 0 || hitbuf[h].req != hitbuf[h - 1].req) ? 1 : 0; }
+                cnt[(size_t)t + 1] = c2;
+            }, 8192);
+            for (size_t t = 1; t < cnt.size(); ++t) { cnt[t] += cnt[t - 1]; }
+            const size_t ne = cnt.back();
+            cache.ent.resize(ne); const size_t used0 = cache.used.size(); cache.used.resize(used0 + ne);
+            parallelFor(n, [&](size_t b, size_t e, int t) {
+                size_t k = cnt[(size_t)t];
+                for (size_t h = b; h < e; ++h) {
+                    if (!(h == 0 || hitbuf[h].req != hitbuf[h - 1].req)) { continue; }
+                    const uint32_t c = hitbuf[h].req;
+                    size_t he = h + 1; while (he < n && hitbuf[he].req == c) { ++he; }
+                    CacheEnt& en = cache.ent[k];
+                    en.ver = C[c].ver; en.scan = scan_id; en.hb = (uint32_t)h; en.he = (uint32_t)he; en.next = -1; en.lit_off = en.lit_n = 0; en.time = 0;
+                    cache.slot[c] = (int32_t)k; cache.used[used0 + k] = c;           // (the cache was empty: no slot of this scan is set yet)
+                    ++k;
+                }
+            }, 8192);
+        } else {
         for (uint32_t h = 0; h < n;) {
             const uint32_t c = hitbuf[h].req;
             CacheEnt e; e.ver = C[c].ver; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
@@ -371,6 +416,7 @@ void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& 
             e.next = cache.slot[c]; e.lit_off = e.lit_n = 0; e.time = 0;
             cache.setSlot(c, (int32_t)cache.ent.size());
             cache.ent.push_back(e);
+        }
         }
         lap("cache");
         host_ns_gpuwait += now_ns() - t0;

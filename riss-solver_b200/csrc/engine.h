@@ -65,6 +65,7 @@ struct Tuning {
     size_t static_min;           // CP3_STATIC_MIN: queue length from which a strengthening pass gets the static plan
     uint64_t touched_min;        // CP3_TOUCHED_MIN: occurrences from which the touched-variable queueing of BVE runs on all cores
     uint32_t devcommit_maxlist;  // CP3_DEVCOMMIT_MAXLIST: longest list with deaths that one device thread may replay
+    size_t par_min;              // CP3_PAR_MIN: list length from which id sorting, scan-cache build and occurrence updates run on all cores
     uint64_t bce_maxwords;       // CP3_BCE_MAXWORDS: K9 mask words per variable in the batch (longer: rows on demand)
     bool no_devcommit, no_overlap, no_precompact, no_lazy, no_plan, no_bve_eval, no_bve_prefetch;   // CP3_NO_<...>=1: switch one form off
     bool debug_par, debug_bve, debug_fine, debug_ondemand, debug_pre;                                // CP3_DEBUG_<...>: phase timers on stderr
@@ -253,6 +254,7 @@ private:
     // grow a work array to n elements, new elements = val (existing ones are kept)
     template <class V, class T> void pgrow(V& v, size_t n, T val) { const size_t o = v.size(); if (n <= o) { return; } v.resize(n); parallelFor(n - o, [&](size_t b, size_t e, int) { std::fill(v.begin() + (std::ptrdiff_t)(o + b), v.begin() + (std::ptrdiff_t)(o + e), val); }); }
     template <class P> void parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred);
+    void sortUniqueIds(std::vector<uint32_t>& ids);      // sort + unique of a clause id list; long lists through a bitmap on all cores
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;

@@ -10,9 +10,44 @@ void Engine::updateOccurrences(bool useHeap, int ignore)
     // from here on nothing is pending any more (setDeleted() consults pend_rm)
     std::vector<OccUpd> ups; ups.swap(occ_upd);
     ++pend_epoch;
-    for (const OccUpd& u : ups) {
-        if (removeClauseFrom(u.cr, u.l)) { removedLiteral(u.l, 1, useHeap, ignore != 0, VAR_UNDEF); }
+    if (useHeap || in_bve_worker || ups.size() < std::max<size_t>(tune.par_min, 1) || nthreads < 2) {
+        for (const OccUpd& u : ups) {
+            if (removeClauseFrom(u.cr, u.l)) { removedLiteral(u.l, 1, useHeap, ignore != 0, VAR_UNDEF); }
+        }
+        return;
     }
+    // Long update lists (the first strengthening pass of a large formula): an update touches nothing but the list, the counter and
+    // the stale count of its own literal, and the order matters only among updates of the same list.  Literal buckets (64-aligned:
+    // no two share a word of the stale bitmap) in update order, one core each.
+    const size_t nlit = (size_t)2 * nvars; const int NB = nthreads;
+    auto bucketLo = [&](int bk) -> size_t { return std::min(nlit, ((nlit * (size_t)bk / (size_t)NB) + 63) / 64 * 64); };
+    const size_t bwidth = std::max<size_t>(64, (nlit / (size_t)NB) / 64 * 64);
+    auto bucketOf = [&](int x) -> int { int bk = (int)std::min<size_t>((size_t)NB - 1, (size_t)x / bwidth); while (bk > 0 && (size_t)x < bucketLo(bk)) { --bk; } while (bk + 1 < NB && (size_t)x >= bucketLo(bk + 1)) { ++bk; } return bk; };
+    std::vector<std::vector<OccUpd>> parts(((size_t)nthreads + 1) * (size_t)NB);
+    parallelFor(ups.size(), [&](size_t b, size_t e, int t) {
+        std::vector<OccUpd>* out = &parts[(size_t)t * (size_t)NB];
+        for (size_t i = b; i < e; ++i) { out[bucketOf(ups[i].l)].push_back(ups[i]); }
+    }, 4096);
+    std::vector<int64_t> removed((size_t)NB, 0);
+    parallelFor((size_t)NB, [&](size_t bb, size_t be, int) {
+        for (size_t bk = bb; bk < be; ++bk) {
+            int64_t r = 0;
+            for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) {                     // producer chunks are contiguous ranges of `ups`, in order
+                for (const OccUpd& u : parts[t2 * (size_t)NB + bk]) {
+                    const int x = u.l; uint32_t* lp = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n;
+                    for (uint32_t i = 0; i < n; ++i) {
+                        if (lp[i] != u.cr) { continue; }
+                        if (isDel(lp[i])) { staleDec(x); }
+                        lp[i] = lp[n - 1]; hot[x].n = n - 1;
+                        deletedVar(x >> 1); hot[x].cnt -= 1; ++r;                  // removedLiteral(l, 1) without a heap
+                        break;
+                    }
+                }
+            }
+            removed[bk] = r;
+        }
+    }, 1);
+    for (int64_t r : removed) { ca_wasted += (double)r; }
 }
 
 // the hit branch of both passes, Subsumption.cc:1385-1413 / 1474-1508
@@ -157,7 +192,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
             if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
             ids.push_back(c);
         }
-        sortUnique(ids);
+        sortUniqueIds(ids);
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
     DbgLap lap("str"); lap("prepare");
@@ -612,7 +647,7 @@ int Engine::naiveStrengthening(bool useHeap, int ignore)
     else if (opt.strength) {
         std::vector<uint32_t> ids;
         for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { ids.push_back(c); } }
-        sortUnique(ids);
+        sortUniqueIds(ids);
         c_str.clear();
         scanClauses(CP3G_STRENGTHEN, ids, c_str);
     } else { c_str.clear(); }

@@ -315,7 +315,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
     {
         std::vector<uint32_t> ids;
         parallelFilter(subq, ids, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
-        sortUnique(ids);
+        sortUniqueIds(ids);
         lap0("ids");
         scanClauses(CP3G_SUBSUME, ids, c_sub);
     }
@@ -334,7 +334,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
             const bool ov = overlap_str && !no_overlap && nthreads > 1 && opt.strength && strq.size() >= parsub_min && !hasToPropagate();
             if (ov) {
                 for (uint32_t c : strq) { if (!(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2) { sids.push_back(c); } }
-                sortUnique(sids);
+                sortUniqueIds(sids);
                 const uint32_t bulk_min2 = tune.bulk_min;
                 sbulk = sids.size() == n_live && n_live > bulk_min2;
                 flushDevice();

@@ -35,10 +35,16 @@ def _clauses(stream):
     return out
 
 
-@pytest.mark.parametrize("bulk_min", ["0", "4096"])
+@pytest.mark.parametrize("bulk_min", ["0", "4096", "forced"])
 def test_engine_fuzz_against_oracle(mock, gen, bulk_min, monkeypatch):
-    # CP3_BULK_MIN=0 forces the full-queue (bulk) scan path on tiny formulas as well
-    monkeypatch.setenv("CP3_BULK_MIN", bulk_min)
+    # CP3_BULK_MIN=0 forces the full-queue (bulk) scan path on tiny formulas as well; "forced" switches every large-queue form on
+    # (time-indexed subsumption commit, static plan + walk plans, parallel id sort / cache build / occurrence updates, 4 threads)
+    if bulk_min == "forced":
+        for k in ("CP3_BULK_MIN", "CP3_PARSUB_MIN", "CP3_STATIC_MIN", "CP3_PAR_MIN", "CP3_TOUCHED_MIN"):
+            monkeypatch.setenv(k, "0")
+        monkeypatch.setenv("CP3_THREADS", "4"); bulk_min = "7"
+    else:
+        monkeypatch.setenv("CP3_BULK_MIN", bulk_min)
     rng = np.random.default_rng(31337 + int(bulk_min))
     for r in range(150):
         lits, sizes = random_instance(rng)

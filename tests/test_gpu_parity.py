@@ -493,7 +493,7 @@ def test_forced_parallel_paths_on_gpu(gen):
         "    d = compare(run_gpu(stream, opts), run_oracle(stream, opts))\n"
         "    if d: bad += 1; print(r, opts, d[:3])\n"
         "print('BAD', bad)\n") % (ROOT, ROOT)
-    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3", CP3_INGEST_MIN="0", CP3_TOUCHED_MIN="0")
+    env = dict(os.environ, CP3_PARSUB_MIN="0", CP3_STATIC_MIN="0", CP3_BULK_MIN="0", CP3_THREADS="3", CP3_INGEST_MIN="0", CP3_TOUCHED_MIN="0", CP3_PAR_MIN="0")
     p = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "BAD 0" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
