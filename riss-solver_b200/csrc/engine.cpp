@@ -1214,6 +1214,7 @@ int64_t Engine::stat(const char* s) const
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
     ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("device_sub_passes", n_devsub) ST("overlapped_str_scans", n_overlap)
+    ST("component_passes", n_compar) ST("component_fallbacks", n_compar_fallback) ST("component_rounds", n_compar_rounds)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

@@ -1,6 +1,9 @@
 // engine_str.cpp - strengthening commit of the host engine (static plan, walk plans, ordered walk, naive variant) and
 // Subsumption::process.
 #include "engine_util.h"
+#include <atomic>
+#include <unordered_map>
+#include <unordered_set>
 
 namespace cp3 {
 
@@ -335,6 +338,13 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     }
     size_t ri = reals.size();                                       // reals[0..ri) are still ahead (the walk goes down)
     lap("reals");
+    // the real entries by dependency component on all cores; false = nothing was touched, the ordered walk below takes the pass
+    bool par_done = false;
+    if (static_lazy && !tune.no_components && nthreads > 1 && reals.size() >= std::max<size_t>(tune.par_min, 1) && !hasToPropagate()) {
+        par_done = strengthenComponents(reals);
+        if (!par_done) { ++n_compar_fallback; }
+        lap("components");
+    }
     // Walk plan of the real entries.  While the plan is valid (no unit, frozen counters, clean lists) the two list walks of an
     // entry are a pure function of its content: the step count is the length of the two lists and the candidates that can
     // hit are the cached hits in list order.  Both are evaluated here on all cores for the content the entry has NOW; the
@@ -343,7 +353,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     struct PlanEnt { uint32_t ver, scan; int32_t min; uint32_t steps1, steps2, cb, c1, c2; uint32_t t; uint32_t lit_off, lit_n; int32_t alt; };
     RawVec<PlanEnt> plan; std::vector<std::vector<Hit>> plan_c((size_t)nthreads + 1); std::vector<std::vector<PlanEnt>> plan_alt((size_t)nthreads + 1);
     const bool no_plan = tune.no_plan;
-    const bool planned = static_lazy && !no_plan && !reals.empty();
+    const bool planned = static_lazy && !no_plan && !reals.empty() && !par_done;
     if (planned) {
         const size_t nq = strq.size();
         plan.resize(reals.size());
@@ -401,7 +411,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     long cur_plan = -1;                                             // plan record of the entry being processed, if any
     lap("plan");
     std::vector<uint32_t> localQueue;
-    size_t end = strq.size();
+    size_t end = par_done ? 0 : strq.size();
     int ret = L_UNDEF; bool early = false;
     for (; end > 0 && (unlimited || str_steps < str_lim);) {
         uint32_t cr;
@@ -738,6 +748,340 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
     t_sub.modified = t_sub.modified || t_up.modified;   // propagation.appliedSomething(): its last call
     if (!t_sub.modified) { unsuccessful(t_sub); }
     return t_sub.modified;
+}
+
+} // namespace cp3
+
+namespace cp3 {
+
+// ------------------------------------------------------------------------------------------------ component commit
+// The real entries of a strengthening pass, committed on all cores.
+//
+// While no unit shows up, a strengthening pass changes nothing but clause contents and flags: the occurrence lists and counters
+// are frozen (updates are deferred, Subsumption.cc:1400,1523), lazily cleaned lists end in the same state whoever walks them
+// first, and the step counter is a sum.  Two queue entries can therefore only influence each other through a clause both of them
+// touch - as strengthener or as target of a cached hit.  The transitive closure of "touches the same clause" (union-find over all
+// cached hits of all content versions) cuts the real entries into dependency components; inside a component the reference's
+// order is replayed exactly - queue position descending, re-queued clauses right behind the entry that hit them (the LIFO
+// localQueue) - on PRIVATE copies of the clauses it edits, components side by side on the cores.  Nothing of the engine's state
+// is written before every component has finished: a component that meets a content version without a scan record reports it,
+// the missing versions are scanned in one batch and the simulation is repeated; a unit clause, a hit on a statically inert
+// entry or the step limit in reach hands the pass - still untouched - to the ordered walk.  The commit then applies the final
+// clause contents, and the queue pushes / occurrence updates in the order of their (queue time, sequence) keys.
+bool Engine::strengthenComponents(const std::vector<uint32_t>& reals)
+{
+    const size_t nq = strq.size(), ncl = C.size(), nlit = (size_t)2 * nvars;
+    const bool unlimited = !opt.limited;
+    const bool dbg = tune.debug_par; int64_t tt = now_ns();
+    auto lap = [&](const char* w) { if (dbg) { const int64_t n2 = now_ns(); fprintf(stderr, "  compar %s %.1f ms\n", w, (n2 - tt) / 1e6); tt = n2; } };
+    const int T = std::max(1, nthreads);
+    struct Ent { uint32_t root, pos; };
+    struct Ev { uint64_t key; uint32_t clause; int32_t lit; uint32_t push_sub; };
+    struct Final { uint32_t clause, nrem; bool sub, str; std::vector<int32_t> lits; };
+    struct Missing { uint32_t clause; std::vector<int32_t> lits; };
+    // result of one simulated component: slices of its producer's event / final-state / cleaned-list arrays
+    struct Comp { uint32_t root; uint32_t ev0, ev1, fin0, fin1, st0, st1; int64_t steps; uint32_t nfast, nslow; bool valid; };
+    struct Out { std::vector<Ev> evs; std::vector<Final> fin; std::vector<int32_t> stale_lists; std::vector<Comp> comps; std::vector<Missing> miss; };
+    std::vector<Out> outs;                                       // one per (round, bucket); kept until the commit
+    // ---- components: a strengthener and every target of every cached content version of it (lock-free union-find, smaller root wins)
+    RawVec<uint32_t> uf; uf.resize(ncl);
+    parallelFor(ncl, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { uf[i] = (uint32_t)i; } });
+    auto find = [&](uint32_t x) -> uint32_t {
+        for (;;) {
+            const uint32_t p = __atomic_load_n(&uf[x], __ATOMIC_RELAXED);
+            if (p == x) { return x; }
+            const uint32_t g = __atomic_load_n(&uf[p], __ATOMIC_RELAXED);
+            if (g != p) { __atomic_store_n(&uf[x], g, __ATOMIC_RELAXED); }           // path halving
+            x = p;
+        }
+    };
+    auto unite = [&](uint32_t a, uint32_t b2) {
+        for (;;) {
+            a = find(a); b2 = find(b2);
+            if (a == b2) { return; }
+            if (a < b2) { std::swap(a, b2); }                                         // a > b2: a's tree goes under b2
+            uint32_t expect = a;
+            if (__atomic_compare_exchange_n(&uf[a], &expect, b2, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) { return; }
+        }
+    };
+    auto uniteEntries = [&](size_t first_ent) {
+        const size_t ne = c_str.ent.size();
+        // owner clause of a cache entry: walk the slot chains of the clauses that own one
+        parallelFor(c_str.used.size(), [&](size_t b, size_t e, int) {
+            for (size_t u = b; u < e; ++u) {
+                const uint32_t sc = c_str.used[u];
+                if (sc >= c_str.slot.size()) { continue; }
+                for (int32_t k = c_str.slot[sc]; k >= 0; k = c_str.ent[(size_t)k].next) {
+                    if ((size_t)k < first_ent) { continue; }
+                    const CacheEnt& ce = c_str.ent[(size_t)k];
+                    for (uint32_t h = ce.hb; h < ce.he; ++h) { unite(sc, c_str.hits[h].clause); }
+                }
+            }
+        }, 2048);
+        (void)ne;
+    };
+    uniteEntries(0);
+    lap("union-find");
+    // ---- the entries that will be processed
+    std::vector<std::vector<uint32_t>> tpos((size_t)T + 1); std::atomic<bool> unfit{false};
+    parallelFor(reals.size(), [&](size_t b, size_t e, int t) {
+        std::vector<uint32_t>& out = tpos[(size_t)t];
+        for (size_t i = b; i < e; ++i) {
+            const uint32_t p = reals[i]; const uint32_t c = strq[p]; const ClauseInfo ci = C[c];
+            if ((ci.flag & F_DEL) || !(ci.flag & F_STR)) { continue; }
+            if (ci.size < 2 || qtime[c] != (int32_t)(nq - 1 - p)) { unfit = true; continue; }       // a unit in the queue, a clause queued twice
+            out.push_back(p);
+        }
+    }, 4096);
+    if (unfit) { return false; }
+    std::unordered_set<uint32_t> dirty;                          // roots to simulate again (empty in the first round: everything)
+    for (int round = 0; round < 6; ++round) {
+        ++n_compar_rounds;
+        // bucket the entries by root range so that a component lands in exactly one bucket; sort by (root, position descending)
+        std::vector<std::vector<Ent>> bucket((size_t)T);
+        {
+            std::vector<std::vector<Ent>> parts(((size_t)T + 1) * (size_t)T);
+            const uint64_t width = ((uint64_t)ncl + (uint64_t)T - 1) / (uint64_t)T;
+            parallelFor((size_t)T + 1, [&](size_t b, size_t e, int) {
+                for (size_t t = b; t < e; ++t) {
+                    for (const uint32_t p : tpos[t]) {
+                        const uint32_t r = find(strq[p]);
+                        if (round > 0 && !dirty.count(r)) { continue; }
+                        parts[t * (size_t)T + (size_t)(r / width)].push_back(Ent{r, p});
+                    }
+                }
+            }, 1);
+            parallelFor((size_t)T, [&](size_t b, size_t e, int) {
+                for (size_t bk = b; bk < e; ++bk) {
+                    std::vector<Ent>& v = bucket[bk];
+                    for (size_t t = 0; t <= (size_t)T; ++t) { const std::vector<Ent>& src = parts[t * (size_t)T + bk]; v.insert(v.end(), src.begin(), src.end()); }
+                    std::sort(v.begin(), v.end(), [](const Ent& a, const Ent& b2) { return a.root != b2.root ? a.root < b2.root : a.pos > b2.pos; });
+                }
+            }, 1);
+        }
+        lap("entries");
+        // ---- simulate the components of this round
+        const size_t out0 = outs.size(); outs.resize(out0 + (size_t)T);
+        std::atomic<bool> abort_units{false};
+        parallelFor((size_t)T, [&](size_t bb, size_t be, int) {
+            for (size_t bk = bb; bk < be; ++bk) {
+                Out& out = outs[out0 + bk];
+                const std::vector<Ent>& ents = bucket[bk];
+                struct Rec { uint32_t c; uint8_t flag; bool changed; std::vector<int32_t> lits, removed; };
+                std::vector<Rec> recs; std::unordered_map<uint32_t, uint32_t> index;
+                std::vector<uint32_t> lq, clean1, clean2;
+                auto recOf = [&](uint32_t c) -> uint32_t {
+                    if (recs.size() <= 8) { for (uint32_t i = 0; i < recs.size(); ++i) { if (recs[i].c == c) { return i; } } }
+                    else { auto it = index.find(c); if (it != index.end()) { return it->second; } }
+                    recs.push_back(Rec{c, (uint8_t)C[c].flag, false, {}, {}});
+                    if (recs.size() == 9) { for (uint32_t i = 0; i < 8; ++i) { index[recs[i].c] = i; } }
+                    if (recs.size() > 8) { index[c] = (uint32_t)recs.size() - 1; }
+                    return (uint32_t)recs.size() - 1;
+                };
+                // occurrence list of x as a walk sees it: the list itself, or - deleted entries still listed - its lazily cleaned form
+                auto view = [&](int x, std::vector<uint32_t>& buf, const uint32_t*& p, uint32_t& n) {
+                    p = occ_pool.data() + occ[x].off; n = hot[x].n;
+                    if (!hasStale(x)) { return; }
+                    buf.assign(p, p + n);
+                    for (uint32_t j = 0; j < n;) { if (isDel(buf[j])) { buf[j] = buf[n - 1]; --n; } else { ++j; } }
+                    p = buf.data(); out.stale_lists.push_back(x);
+                };
+                size_t i = 0;
+                while (i < ents.size() && !abort_units) {
+                    size_t j = i; while (j < ents.size() && ents[j].root == ents[i].root) { ++j; }
+                    // one component: entries [i, j)
+                    recs.clear(); index.clear(); lq.clear();
+                    Comp cp{ents[i].root, (uint32_t)out.evs.size(), 0, (uint32_t)out.fin.size(), 0, (uint32_t)out.stale_lists.size(), 0, 0, 0, 0, true};
+                    bool deferred = false;
+                    uint64_t key = 0;
+                    auto process = [&](uint32_t cr) {
+                        const uint32_t ri = recOf(cr);
+                        if ((recs[ri].flag & F_DEL) || !(recs[ri].flag & F_STR)) { return; }
+                        const int32_t* s = recs[ri].changed ? recs[ri].lits.data() : CL(cr);
+                        const uint32_t sn = recs[ri].changed ? (uint32_t)recs[ri].lits.size() : (uint32_t)C[cr].size;
+                        if (sn < 2) { abort_units = true; return; }
+                        int minT = s[0];
+                        for (uint32_t k = 1; k < sn; ++k) { if (dcount(minT >> 1) > dcount(s[k] >> 1)) { minT = s[k]; } }
+                        const int mn = minT, nm = minT ^ 1;
+                        // scan record of this very content
+                        const CacheEnt* e = nullptr;
+                        if (!recs[ri].changed) { e = cached(c_str, cr); }
+                        else if (cr < c_str.slot.size()) {
+                            for (int32_t k = c_str.slot[cr]; k >= 0; k = c_str.ent[(size_t)k].next) {
+                                const CacheEnt& ce = c_str.ent[(size_t)k];
+                                if (ce.ver == UINT32_MAX && ce.lit_n == sn && !memcmp(c_str.lits.data() + ce.lit_off, s, sizeof(int32_t) * sn)) { e = &ce; break; }
+                            }
+                        }
+                        if (!e) { out.miss.push_back(Missing{cr, std::vector<int32_t>(s, s + sn)}); deferred = true; return; }
+                        const uint32_t* l1; uint32_t n1; const uint32_t* l2; uint32_t n2;
+                        view(mn, clean1, l1, n1); view(nm, clean2, l2, n2);
+                        cp.steps += (n1 ? (int64_t)n1 - 1 : 0) + (int64_t)n2;
+                        if (e->hb == e->he) { ++cp.nfast; }
+                        else {
+                            ++cp.nslow;
+                            for (int pass = 0; pass < 2 && !abort_units; ++pass) {
+                                const uint32_t* l = pass == 0 ? l1 : l2; const uint32_t n = pass == 0 ? n1 : n2;
+                                for (uint32_t q = 0; q < n; ++q) {
+                                    const uint32_t other = l[q];
+                                    if (pass == 0 && other == cr) { continue; }
+                                    const Hit* h = findHit(c_str.hits, e->hb, e->he, other);
+                                    if (!h || (pass == 0 ? h->lit == nm : h->lit != nm)) { continue; }
+                                    const uint32_t di = recOf(other);
+                                    // (recOf may have moved the records: the strengthener's literals are re-read from its record)
+                                    const int32_t* s2 = recs[ri].changed ? recs[ri].lits.data() : CL(cr);
+                                    bool valid = true;                       // the target lost the literal itself or a literal of the strengthener
+                                    for (int32_t x : recs[di].removed) { if (x == h->lit || containsLit(s2, sn, x)) { valid = false; break; } }
+                                    if (!valid) { continue; }
+                                    Rec& d = recs[di];
+                                    if (!d.changed) { d.lits.assign(CL(other), CL(other) + C[other].size); d.changed = true; }
+                                    int pos = -1;
+                                    for (size_t k2 = 0; k2 < d.lits.size(); ++k2) { if (d.lits[k2] == h->lit) { pos = (int)k2; break; } }
+                                    if (pos < 0) { continue; }
+                                    d.lits.erase(d.lits.begin() + pos); d.removed.push_back(h->lit);
+                                    out.evs.push_back(Ev{key++, other, h->lit, (d.flag & F_SUB) ? 0u : 1u});
+                                    d.flag |= F_SUB;
+                                    if (!(d.flag & F_STR)) { lq.push_back(other); d.flag |= F_STR; }
+                                    if (d.lits.size() == 1) { abort_units = true; break; }
+                                }
+                            }
+                        }
+                        recs[ri].flag &= (uint8_t)~F_STR;
+                    };
+                    for (size_t k = i; k < j && !deferred && !abort_units; ++k) {
+                        key = ((uint64_t)(nq - 1 - ents[k].pos) << 24);
+                        process(strq[ents[k].pos]);
+                        // QUIRK: the worker's loop ends with the entry at queue position 0 (`end > start`, Subsumption.cc:1276): clauses
+                        // that this very last entry re-queues are never processed and keep their flag
+                        if (ents[k].pos == 0) { lq.clear(); }
+                        while (!lq.empty() && !deferred && !abort_units) { const uint32_t c2 = lq.back(); lq.pop_back(); process(c2); }
+                    }
+                    if (deferred) { out.evs.resize(cp.ev0); out.stale_lists.resize(cp.st0); }
+                    else if (!abort_units) {
+                        for (Rec& r : recs) { if (r.changed) { out.fin.push_back(Final{r.c, (uint32_t)r.removed.size(), (r.flag & F_SUB) != 0, (r.flag & F_STR) != 0, std::move(r.lits)}); } }
+                        cp.ev1 = (uint32_t)out.evs.size(); cp.fin1 = (uint32_t)out.fin.size(); cp.st1 = (uint32_t)out.stale_lists.size();
+                        out.comps.push_back(cp);
+                    }
+                    i = j;
+                }
+            }
+        }, 1);
+        lap("simulate");
+        if (abort_units) { return false; }
+        size_t nmiss = 0; for (size_t o = out0; o < outs.size(); ++o) { nmiss += outs[o].miss.size(); }
+        if (nmiss == 0) { break; }
+        if (round == 5) { return false; }
+        // ---- scan the content versions nobody predicted (what the ordered walk would fetch one batch at a time), merge the components
+        //      their hits connect, and simulate those - and only those - again
+        std::vector<SpecReq> reqs; spec_lits.clear();
+        std::unordered_set<uint64_t> seen; dirty.clear();
+        for (size_t o = out0; o < outs.size(); ++o) {
+            for (const Missing& m : outs[o].miss) {
+                dirty.insert(find(m.clause));
+                uint64_t hsh = 1469598103934665603ull ^ m.clause; for (int32_t x : m.lits) { hsh = (hsh ^ (uint32_t)x) * 1099511628211ull; }
+                if (!seen.insert(hsh).second) { continue; }
+                reqs.push_back({m.clause, (uint32_t)spec_lits.size(), (uint32_t)m.lits.size(), 0.0});
+                spec_lits.insert(spec_lits.end(), m.lits.begin(), m.lits.end());
+            }
+        }
+        const size_t h0 = c_str.hits.size(), e0 = c_str.ent.size();
+        ++n_ondemand;
+        scanSpeculative(CP3G_STRENGTHEN, reqs, c_str);
+        // a new hit on a statically inert entry would make it a real one: leave that to the ordered walk
+        for (size_t h = h0; h < c_str.hits.size(); ++h) {
+            const uint32_t x = c_str.hits[h].clause;
+            if (x < qtime.size() && qtime[x] >= 0) { const size_t pos = nq - 1 - (size_t)qtime[x]; if (pos < contrib.size() && contrib[pos] >= 0) { return false; } }
+        }
+        // components that the new hits connect: both sides are simulated again under their common root
+        for (size_t k = e0; k < c_str.ent.size(); ++k) {
+            const CacheEnt& ce = c_str.ent[k];
+            const uint32_t sc = reqs[k - e0].clause;                                  // scanSpeculative appends one record per request, in order
+            for (uint32_t h = ce.hb; h < ce.he; ++h) { dirty.insert(find(sc)); dirty.insert(find(c_str.hits[h].clause)); unite(sc, c_str.hits[h].clause); }
+        }
+        { std::unordered_set<uint32_t> nd; for (uint32_t r : dirty) { nd.insert(find(r)); } dirty.swap(nd); }
+        for (Out& o : outs) { for (Comp& cp : o.comps) { if (cp.valid && dirty.count(find(cp.root))) { cp.valid = false; } } }
+        lap("missing versions");
+    }
+    // ---- commit: nothing of the engine's state was written so far
+    int64_t steps = 0, nfast = 0, nslow = 0; size_t nev = 0, nfin = 0;
+    std::vector<uint8_t> walked_stale(nlit, 0);
+    for (const Out& o : outs) {
+        for (const Comp& cp : o.comps) {
+            if (!cp.valid) { continue; }
+            steps += cp.steps; nfast += cp.nfast; nslow += cp.nslow; nev += cp.ev1 - cp.ev0; nfin += cp.fin1 - cp.fin0;
+            for (uint32_t k = cp.st0; k < cp.st1; ++k) { walked_stale[(size_t)o.stale_lists[k]] = 1; }
+        }
+    }
+    std::vector<int64_t> part((size_t)T + 1, 0), ninert((size_t)T + 1, 0), pstale((size_t)T + 1, 0);
+    parallelFor(nq, [&](size_t b, size_t e, int t) { int64_t a = 0, c2 = 0; for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { a += contrib[p]; ++c2; } } part[(size_t)t] = a; ninert[(size_t)t] = c2; });
+    // the first walk of a list pays one step per deleted entry it removes
+    parallelFor(nlit, [&](size_t b, size_t e, int t) {
+        int64_t a = 0;
+        for (size_t x = b; x < e; ++x) { if (walked_stale[x]) { const uint32_t* p = occ_pool.data() + occ[x].off; const uint32_t n = hot[x].n; for (uint32_t j = 0; j < n; ++j) { a += isDel(p[j]) ? 1 : 0; } } }
+        pstale[(size_t)t] = a;
+    });
+    int64_t inert_steps = 0, inert_n = 0, stale_steps = 0;
+    for (int t = 0; t <= T; ++t) { inert_steps += part[(size_t)t]; inert_n += ninert[(size_t)t]; stale_steps += pstale[(size_t)t]; }
+    const int64_t total = steps + inert_steps + stale_steps;
+    if (!unlimited && !(str_steps + total + 1 < str_lim)) { return false; }
+    // clause contents and flags; the real entries are done (the inert ones lost their flag up front), re-queued clauses are
+    // processed too - or left over by the last entry of the queue
+    parallelFor(reals.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { C[strq[reals[i]]].flag &= ~F_STR; } }, 4096);
+    std::vector<const Final*> fins; fins.reserve(nfin);
+    std::vector<Ev> evs; evs.reserve(nev);
+    for (const Out& o : outs) {
+        for (const Comp& cp : o.comps) {
+            if (!cp.valid) { continue; }
+            for (uint32_t k = cp.fin0; k < cp.fin1; ++k) { fins.push_back(&o.fin[k]); }
+            evs.insert(evs.end(), o.evs.begin() + cp.ev0, o.evs.begin() + cp.ev1);
+        }
+    }
+    parallelFor(fins.size(), [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; ++i) {
+            const Final& f = *fins[i]; ClauseInfo& ci = C[f.clause];
+            memcpy(pool.data() + ci.start, f.lits.data(), sizeof(int32_t) * f.lits.size());
+            ci.size = (uint32_t)f.lits.size(); ci.ver += f.nrem; ci.stamp = scan_id;
+            if (f.sub) { ci.flag |= F_SUB; }
+            if (f.str) { ci.flag |= F_STR; } else { ci.flag &= ~F_STR; }
+        }
+    }, 4096);
+    for (const Final* f : fins) {
+        const uint32_t c = f->clause;
+        if (dev_uploaded && c < shrunk_mark.size() && !shrunk_mark[c]) { shrunk_mark[c] = 1; pend_shrunk.push_back(c); }
+    }
+    // queue pushes and occurrence updates in reference order: sorted by (queue time, sequence) - ranges of the key per core
+    {
+        const uint64_t kmax = ((uint64_t)nq << 24) + 1, kw = kmax / (uint64_t)T + 1;
+        std::vector<std::vector<Ev>> kb((size_t)T);
+        parallelFor((size_t)T, [&](size_t b, size_t e, int) {
+            for (size_t bk = b; bk < e; ++bk) {
+                std::vector<Ev>& v = kb[bk];
+                for (const Ev& ev : evs) { if (ev.key / kw == bk) { v.push_back(ev); } }
+                std::sort(v.begin(), v.end(), [](const Ev& a, const Ev& b2) { return a.key < b2.key; });
+            }
+        }, 1);
+        for (const std::vector<Ev>& v : kb) {
+            for (const Ev& ev : v) {
+                if (ev.push_sub) { subq.push_back(ev.clause); }
+                occ_upd.push_back({ev.clause, ev.lit});
+                if (opt.bve) { touchClauseVars(ev.clause); bveTouch(ev.lit >> 1); }
+            }
+        }
+    }
+    removedLiterals += (int)evs.size();
+    if (!evs.empty()) { successful(t_sub); }
+    // lists that a walk cleaned
+    parallelForG((nlit + 63) / 64, 512, [&](size_t wb, size_t we, int) {
+        for (size_t x = wb * 64; x < std::min(nlit, we * 64); ++x) {
+            if (!walked_stale[x]) { continue; }
+            uint32_t* p = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n;
+            for (uint32_t j = 0; j < n;) { if (isDel(p[j])) { p[j] = p[n - 1]; --n; } else { ++j; } }
+            hot[x].n = n; staleClear((int)x);
+        }
+    });
+    str_steps += total; n_fast += nfast; n_slow += nslow; n_lazy = inert_n;
+    ++n_compar;
+    lap("commit");
+    return true;
 }
 
 } // namespace cp3
