@@ -843,6 +843,12 @@ void Engine::extLit(int x) { undo.push_back(0); undo.push_back(toDimacs(x)); }
 
 void Engine::filterDeleted(std::vector<uint32_t>& a)
 {
+    if (a.size() >= 262144 && nthreads > 1) {
+        std::vector<uint32_t> out;
+        parallelFilter(a, out, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
+        a.swap(out);
+        return;
+    }
     size_t j = 0;
     for (size_t i = 0; i < a.size(); ++i) { if (!(C[a[i]].flag & F_DEL)) { a[j++] = a[i]; } }
     a.resize(j);
@@ -1058,9 +1064,12 @@ void Engine::preprocess()
     PhaseTimer ptot(ph_total);
     ensureGpu();                                  // fail before touching anything when there is no device
     sub_lim = opt.sub_limit; str_lim = opt.str_limit;
+    DbgLap plap("preprocess");
     { PhaseTimer ps(ph_simplify); if (!solverSimplify()) { return; } }
     sortPermuted();
+    plap("simplify + sort");
     initData();
+    plap("initData");
     int status = L_UNDEF;
     for (int it = 0; it < opt.iters; ++it) {
         if (opt.up) { if (status == L_UNDEF) { status = propagationProcess(true, false, VAR_UNDEF); } }
@@ -1083,9 +1092,11 @@ void Engine::preprocess()
         }
         if (!ok) { break; }
     }
+    plap("techniques");
     if (ok && hasToPropagate()) { propagationProcess(false, false, VAR_UNDEF); }
     if (opt.dense) { denseCompress(); }           // very last step, Coprocessor.cc:492-496
     if (ok) { filterDeleted(clauses); }           // reSetupSolver, CoprocessorTypes.h:937-1008
+    plap("tail");
     if (opt.stats) {
         fprintf(stderr, "c [STAT] SuSi(1) %d cls,  with %d lits, %d strengthed\n", subsumedClauses, subsumedLiterals, removedLiterals);
         fprintf(stderr, "c [STAT] SuSi(2) %lld subs-steps, %lld strenght-steps, %d increases\n", (long long)sub_steps, (long long)str_steps, limitIncreases);

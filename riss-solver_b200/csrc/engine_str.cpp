@@ -634,7 +634,7 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         ret = ok ? L_UNDEF : L_FALSE;
     }
     lap("updateOcc");
-    for (uint32_t c : strq) { if (c < qtime.size()) { qtime[c] = -1; } }
+    parallelFor(strq.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { const uint32_t c = strq[i]; if (c < qtime.size()) { qtime[c] = -1; } } });
     if (lap.on) { fprintf(stderr, "  str lazy entries %lld, lazy still on %d\n", (long long)n_lazy, (int)static_lazy); }
     static_pass = false; static_lazy = false; n_fast += n_lazy; n_static += n_lazy; n_lazy = 0;
     if (tune.debug_pre) { fprintf(stderr, "strpass q=%zu steps=%lld removed=%d pre=%zu active=%d static=%lld\n", strq.size(), (long long)str_steps, removedLiterals, pre_lists.size(), (int)pre_active, (long long)n_static); }

@@ -6,7 +6,9 @@ namespace cp3 {
 // ------------------------------------------------------------------------------------------------ Subsumption
 void Engine::clearQueue(std::vector<uint32_t>& q, uint8_t flag)
 {
-    for (uint32_t c : q) { C[c].flag &= ~flag; }
+    // (a clause is queued once per pass, so the chunks of a long queue write disjoint records)
+    if (q.size() >= 65536 && nthreads > 1) { parallelFor(q.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { __atomic_fetch_and((uint32_t*)&C[q[i]] + 1, ~((uint32_t)flag << 24), __ATOMIC_RELAXED); } }); }
+    else { for (uint32_t c : q) { C[c].flag &= ~flag; } }
     q.clear();
 }
 
