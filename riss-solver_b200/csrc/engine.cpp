@@ -329,11 +329,33 @@ void Engine::flushDevice()
     }
     if (!pend_shrunk.empty()) {
         std::vector<uint32_t> ids, st, sz; std::vector<int32_t> li;
+        if (pend_shrunk.size() >= std::max<size_t>(tune.par_min, 1) && nthreads > 1) {
+            // long edit lists (a strengthening pass over a large formula): sizes per chunk, prefix, fill - on all cores
+            const size_t np = pend_shrunk.size();
+            std::vector<size_t> cn((size_t)nthreads + 2, 0), cl((size_t)nthreads + 2, 0);
+            parallelFor(np, [&](size_t b, size_t e, int t) {
+                size_t a = 0, l = 0;
+                for (size_t i = b; i < e; ++i) { const uint32_t c = pend_shrunk[i]; shrunk_mark[c] = 0; if (c < old_ncl) { ++a; l += C[c].size; } }
+                cn[(size_t)t + 1] = a; cl[(size_t)t + 1] = l;
+            }, 4096);
+            for (size_t t = 1; t < cn.size(); ++t) { cn[t] += cn[t - 1]; cl[t] += cl[t - 1]; }
+            ids.resize(cn.back()); st.resize(cn.back()); sz.resize(cn.back()); li.resize(cl.back());
+            parallelFor(np, [&](size_t b, size_t e, int t) {
+                size_t a = cn[(size_t)t], l = cl[(size_t)t];
+                for (size_t i = b; i < e; ++i) {
+                    const uint32_t c = pend_shrunk[i];
+                    if (c >= old_ncl) { continue; }
+                    ids[a] = c; st[a] = (uint32_t)l; sz[a] = C[c].size; ++a;
+                    memcpy(li.data() + l, CL(c), sizeof(int32_t) * C[c].size); l += C[c].size;
+                }
+            }, 4096);
+        } else {
         for (uint32_t c : pend_shrunk) {
             shrunk_mark[c] = 0;
             if (c >= old_ncl) { continue; }          // appended above with its current content
             ids.push_back(c); st.push_back((uint32_t)li.size()); sz.push_back(C[c].size);
             li.insert(li.end(), CL(c), CL(c) + C[c].size);
+        }
         }
         pend_shrunk.clear();
         if (!ids.empty() && cp3g_shrink(gpu, (uint32_t)ids.size(), ids.data(), st.data(), sz.data(), li.data(), li.size()) != CP3G_OK) { die("shrink failed"); }
@@ -967,10 +989,12 @@ void Engine::initData()
     if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
     occ_pool.resize((size_t)off[n2] + 16);                 // filled by ensureHostLists() / the device-side commit of the first pass
     lists_on_device = true;
-    for (int x = 0; x < n2; ++x) {
-        occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];
-        hot[x].cnt = (int32_t)hot[x].n;
-    }
+    parallelFor((size_t)n2, [&](size_t b, size_t e, int) {
+        for (size_t x = b; x < e; ++x) {
+            occ[x].off = off[x]; hot[x].n = occ[x].cap = off[x + 1] - off[x];
+            hot[x].cnt = (int32_t)hot[x].n;
+        }
+    });
     ph_download += now_ns() - ti0;
     DbgLap lap("init"); 
     {   // every live clause: count it, queue it per its flags (Subsumption::initClause), drop the deleted ones.
@@ -984,7 +1008,9 @@ void Engine::initData()
         size_t full = 0; for (size_t a : part) { full += a; }
         if (full == clauses.size()) {
             numberOfCls += (int)clauses.size();
-            subq.insert(subq.end(), clauses.begin(), clauses.end()); strq.insert(strq.end(), clauses.begin(), clauses.end());
+            const size_t nc = clauses.size(), s0 = subq.size(), t0q = strq.size();
+            subq.resize(s0 + nc); strq.resize(t0q + nc);
+            parallelFor(nc, [&](size_t b, size_t e, int) { memcpy(subq.data() + s0 + b, clauses.data() + b, sizeof(uint32_t) * (e - b)); memcpy(strq.data() + t0q + b, clauses.data() + b, sizeof(uint32_t) * (e - b)); });
         } else {
             size_t kept = 0;
             for (size_t i = 0; i < clauses.size(); ++i) {

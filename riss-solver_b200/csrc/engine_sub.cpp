@@ -57,12 +57,36 @@ bool Engine::subsumptionCommitParallel()
     // step 1: death times.  Entries with hits, in processing order (time = nq-1-position).
     std::vector<std::pair<int32_t, uint32_t>> hitters;           // (time, cache entry)
     // the cache is keyed by clause: walk the clauses that own an entry
+    if (c_sub.used.size() >= std::max<size_t>(tune.par_min, 1) && nthreads > 1) {
+        // long lists: collected per time range on all cores, each range sorted by its owner, ranges concatenated
+        const size_t NBk = (size_t)nthreads;
+        std::vector<std::vector<std::pair<int32_t, uint32_t>>> parts(((size_t)nthreads + 1) * NBk);
+        parallelFor(c_sub.used.size(), [&](size_t b, size_t e, int t) {
+            std::vector<std::pair<int32_t, uint32_t>>* out = &parts[(size_t)t * NBk];
+            for (size_t u = b; u < e; ++u) {
+                const uint32_t c = c_sub.used[u]; const int32_t slot = c_sub.slot[c];
+                if (slot < 0 || c_sub.ent[slot].hb == c_sub.ent[slot].he || sub_pos[c] < 0 || (C[c].flag & F_DEL)) { continue; }
+                const int32_t tm = (int32_t)(nq - 1 - (size_t)sub_pos[c]);
+                out[(size_t)tm * NBk / nq].push_back({tm, (uint32_t)slot});
+            }
+        }, 4096);
+        std::vector<std::vector<std::pair<int32_t, uint32_t>>> sorted(NBk);
+        parallelFor(NBk, [&](size_t b, size_t e, int) {
+            for (size_t bk = b; bk < e; ++bk) {
+                std::vector<std::pair<int32_t, uint32_t>>& v = sorted[bk];
+                for (size_t t2 = 0; t2 <= (size_t)nthreads; ++t2) { const auto& src = parts[t2 * NBk + bk]; v.insert(v.end(), src.begin(), src.end()); }
+                std::sort(v.begin(), v.end());
+            }
+        }, 1);
+        for (const auto& v : sorted) { hitters.insert(hitters.end(), v.begin(), v.end()); }
+    } else {
     for (uint32_t c : c_sub.used) {
         const int32_t slot = c_sub.slot[c];
         if (slot < 0 || c_sub.ent[slot].hb == c_sub.ent[slot].he || sub_pos[c] < 0 || (C[c].flag & F_DEL)) { continue; }
         hitters.push_back({(int32_t)(nq - 1 - (size_t)sub_pos[c]), (uint32_t)slot});
     }
     std::sort(hitters.begin(), hitters.end());
+    }
     std::vector<uint32_t> dead;
     for (const auto& h : hitters) {
         const CacheEnt& e = c_sub.ent[h.second];
