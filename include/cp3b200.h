@@ -136,6 +136,17 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead, uint
  * post-pass order (first list_n[x] entries of list x).  NULL skips an output. */
 int cp3g_sub_pass_fetch(cp3g* g, uint32_t* dead, uint32_t* list_n, uint32_t* list_stale, uint32_t* refs);
 
+/* K10: the static part of the strengthening pass that follows a committed cp3g_sub_pass (strengthening_worker,
+ * Subsumption.cc:1276-1310 + the list walks of the entries that no hit touches), on the tables the device holds after that pass.
+ * real_bits: one bit per clause, set = the host commits this queue entry itself (it has hits or is the target of one).  Every
+ * other live clause of size >= 2 chooses the literal whose variable has the smallest occurrence count (counts after the pass, the
+ * first such literal in clause order), adds live_len(min) - 1 + live_len(~min) steps and marks both lists as walked.
+ * Out: number of such entries, their step total, live clauses of size < 2 outside real_bits (units in the queue: the caller must
+ * take the ordered walk then), walked_bits (one bit per literal, 2*nvars bits).  *status 1: not applicable (no committed pass,
+ * or the data base changed since) - nothing is returned. */
+int cp3g_str_static(cp3g* g, const uint32_t* real_bits, int* status, uint64_t* inert_entries, uint64_t* inert_steps, uint64_t* small_clauses,
+                    uint32_t* walked_bits);
+
 /* K5: resolvent anticipation for candidate variables.  Variable i owns pos refs p_off[i]..p_off[i+1] and
  * neg refs n_off[i]..n_off[i+1] (host list order).  sizes[pair_off[i] + a*nneg + b] = number of literals
  * of the resolvent of pos a and neg b on vars[i], -1 for a tautology (BVE.h:248-299), -2 when a parent is

@@ -27,7 +27,7 @@ CP_SYMBOLS = [
 CP3G_SYMBOLS = [
     "cp3g_device_count", "cp3g_create", "cp3g_destroy", "cp3g_last_error", "cp3g_upload", "cp3g_upload_packed", "cp3g_build",
     "cp3g_download_occ", "cp3g_set_deleted", "cp3g_shrink", "cp3g_append", "cp3g_scan", "cp3g_scan_all", "cp3g_bve_pairs", "cp3g_bce_masks",
-    "cp3g_bve_resolve", "cp3g_sub_pass", "cp3g_sub_pass_fetch", "cp3g_bve_eval", "cp3g_bve_stream", "cp3g_dense", "cp3g_compact", "cp3g_ingest", "cp3g_download_arena", "cp3g_nccl_unique_id", "cp3g_nccl_init", "cp3g_counter",
+    "cp3g_bve_resolve", "cp3g_sub_pass", "cp3g_sub_pass_fetch", "cp3g_str_static", "cp3g_bve_eval", "cp3g_bve_stream", "cp3g_dense", "cp3g_compact", "cp3g_ingest", "cp3g_download_arena", "cp3g_nccl_unique_id", "cp3g_nccl_init", "cp3g_counter",
 ]
 
 
@@ -83,6 +83,8 @@ def load(path: str | None = None) -> C.CDLL:
         L.cp3g_bce_masks.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, vp, u32p]; L.cp3g_bce_masks.restype = C.c_int
     L.cp3g_bve_resolve.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, vp, i32p, C.c_size_t]; L.cp3g_bve_resolve.restype = C.c_int
     L.cp3g_sub_pass.argtypes = [vp, C.c_uint32, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]; L.cp3g_sub_pass.restype = C.c_int
+    if hasattr(L, "cp3g_str_static"):
+        L.cp3g_str_static.argtypes = [vp, u32p, C.POINTER(C.c_int), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), u32p]; L.cp3g_str_static.restype = C.c_int
     L.cp3g_sub_pass_fetch.argtypes = [vp, u32p, u32p, u32p, u32p]; L.cp3g_sub_pass_fetch.restype = C.c_int
     L.cp3g_bve_eval.argtypes = [vp, C.c_uint32, u32p, u32p, u32p, u32p, u32p, C.c_int, vp, vp, vp]; L.cp3g_bve_eval.restype = C.c_int
     L.cp3g_bve_stream.argtypes = [vp, C.c_uint32, u32p, vp, vp, vp, i32p]; L.cp3g_bve_stream.restype = C.c_int

@@ -165,7 +165,80 @@ __global__ void k_sp_replay(const ClauseHdr* __restrict__ hdr, const int32_t* __
     if (threadIdx.x == 0) { unsigned long long s = 0; for (unsigned w2 = 0; w2 < (blockDim.x >> 5); ++w2) { s += wsum[w2]; } if (s) { atomicAdd(steps, s); } }
 }
 
+// K10: static part of the strengthening pass behind a committed subsumption pass.  One thread per clause; the per-literal tables
+// (CSR offsets, deaths, post-pass list lengths, deleted entries still listed) are 4 x 8 MB at C2 and stay L2 resident, the clause
+// arena is streamed once: 16 + 4*#C bytes per clause, one 4-byte atomic OR per walker.
+__global__ void __launch_bounds__(256) k_str_static(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, uint32_t ncl,
+                                                    const uint32_t* __restrict__ real_bits, const uint32_t* __restrict__ off, const uint32_t* __restrict__ dl_cnt,
+                                                    const uint32_t* __restrict__ ln, const uint32_t* __restrict__ ls, uint32_t* __restrict__ walked,
+                                                    unsigned long long* __restrict__ out3)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long st = 0; uint32_t ent = 0, small = 0;
+    if (c < ncl && !((real_bits[c >> 5] >> (c & 31)) & 1u)) {
+        const ClauseHdr h = hdr[c];
+        const uint32_t sz = h.szfl & SIZE_MASK;
+        if (!(h.szfl & FLAG_DEL)) {
+            if (sz < 2) { small = 1; }
+            else {
+                int32_t mn = 0, best = 0;
+                for (uint32_t k = 0; k < sz; ++k) {
+                    const int32_t x = lits[h.start + k]; const uint32_t p = (uint32_t)x & ~1u;
+                    // lit_occurrence_count after the pass: list length at build time minus twice the deaths (Subsumption.cc:284,305)
+                    const int32_t d = (int32_t)(off[p + 2] - off[p]) - 2 * (int32_t)(dl_cnt[p] + dl_cnt[p + 1]);
+                    if (k == 0 || best > d) { best = d; mn = x; }
+                }
+                const uint32_t l1 = ln[mn] - ls[mn], l2 = ln[mn ^ 1] - ls[mn ^ 1];
+                st = (l1 ? l1 - 1 : 0) + l2; ent = 1;
+                atomicOr(&walked[(uint32_t)mn >> 5], 3u << ((uint32_t)mn & 30u));          // both literals of the variable share a word
+            }
+        }
+    }
+    // block totals: steps, entries, small clauses
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { st += __shfl_xor_sync(0xffffffffu, st, d); ent += __shfl_xor_sync(0xffffffffu, ent, d); small += __shfl_xor_sync(0xffffffffu, small, d); }
+    __shared__ unsigned long long ws[8]; __shared__ uint32_t we[8], wm[8];
+    if ((threadIdx.x & 31) == 0) { ws[threadIdx.x >> 5] = st; we[threadIdx.x >> 5] = ent; wm[threadIdx.x >> 5] = small; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long s = 0, e = 0, m = 0;
+        for (unsigned w = 0; w < (blockDim.x >> 5); ++w) { s += ws[w]; e += we[w]; m += wm[w]; }
+        if (s) { atomicAdd(out3, s); } if (e) { atomicAdd(out3 + 1, e); } if (m) { atomicAdd(out3 + 2, m); }
+    }
+}
+
 extern "C" {
+
+int cp3g_str_static(cp3g* g, const uint32_t* real_bits, int* status, uint64_t* inert_entries, uint64_t* inert_steps, uint64_t* small_clauses,
+                    uint32_t* walked_bits)
+{
+    if (!g) { return CP3G_ERR_NODEVICE; }
+    cudaSetDevice(g->device);
+    if (status) { *status = 1; }
+    if (!g->sp_valid || g->sp_build != g->build_count || g->sp_ncl != g->ncl || g->ncl != g->ncl_csr || !g->ovf_host.empty()) { return CP3G_OK; }
+    const uint32_t ncl = g->ncl, nlit = 2 * g->nvars;
+    const size_t rwords = ((size_t)ncl + 31) / 32, wwords = ((size_t)nlit + 31) / 32;
+    RESERVE(g->scratch_u32, rwords + wwords + 8, false);
+    uint32_t* d_real = g->scratch_u32.p; uint32_t* d_walked = g->scratch_u32.p + rwords;
+    unsigned long long* d_out = (unsigned long long*)(g->counters.p + 8);
+    CK(cudaMemcpyAsync(d_real, real_bits, rwords * 4, cudaMemcpyHostToDevice, g->stream));
+    CK(cudaMemsetAsync(d_walked, 0, wwords * 4, g->stream));
+    CK(cudaMemsetAsync(g->counters.p + 8, 0, 8 * sizeof(uint32_t), g->stream));
+    KTimer t(g);
+    k_str_static<<<grid_for(ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->lits.p, ncl, d_real, g->occ_off.p, g->sp_dlcnt.p, g->sp_n.p, g->sp_stale.p, d_walked, d_out);
+    t.stop();
+    unsigned long long out3[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(out3, d_out, sizeof(out3), cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaMemcpyAsync(walked_bits, d_walked, wwords * 4, cudaMemcpyDeviceToHost, g->stream));
+    CK(cudaStreamSynchronize(g->stream));
+    CK(cudaGetLastError());
+    g->commit_ns += t.collect(); g->launches++;
+    g->commit_bytes += 16ll * (int64_t)ncl + 4ll * (int64_t)g->nlits;
+    g->h2d += (int64_t)rwords * 4; g->d2h += (int64_t)wwords * 4 + 24;
+    if (inert_steps) { *inert_steps = out3[0]; } if (inert_entries) { *inert_entries = out3[1]; } if (small_clauses) { *small_clauses = out3[2]; }
+    if (status) { *status = 0; }
+    return CP3G_OK;
+}
 
 int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead_out, uint64_t* nlits_out, uint64_t* steps_out, uint64_t* checks_out)
 {
@@ -264,7 +337,7 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead_out, 
     // algorithmic bytes: the hits once per fixpoint round (12 B), per clause header + literals + death time + choice, per
     // occurrence the pristine and the working list (read + written)
     g->commit_bytes += 12ll * (int64_t)nh * 3 + (16ll + 8ll) * (int64_t)ncl + 4ll * (int64_t)g->nlits + 12ll * (int64_t)g->total_occ;
-    g->sp_valid = true; g->sp_ndead = ndead;
+    g->sp_valid = true; g->sp_ndead = ndead; g->sp_build = g->build_count; g->sp_ncl = g->ncl;
     if (status) { *status = 0; }
     if (ndead_out) { *ndead_out = ndead; }
     if (nlits_out) { *nlits_out = nl; }

@@ -305,7 +305,7 @@ void Engine::uploadAll()
     if (!resident && cp3g_upload_packed(gpu, (uint32_t)nvars, ncl, pool.data(), pool.size(), C.data()) != CP3G_OK) { die("upload failed"); }
     if (cp3g_build(gpu) != CP3G_OK) { die("occurrence build failed"); }
     host_ns_gpuwait += now_ns() - t0;
-    dev_ncl = ncl; dev_uploaded = true;
+    dev_ncl = ncl; dev_uploaded = true; dev_static_ok = false;
     pend_del.clear(); pend_shrunk.clear();
     shrunk_mark.assign(ncl, 0);
 }
@@ -316,6 +316,7 @@ void Engine::flushDevice()
     const uint32_t ncl = (uint32_t)C.size();
     int64_t t0 = now_ns();
     const uint32_t old_ncl = dev_ncl;
+    if (ncl > dev_ncl || !pend_shrunk.empty() || !pend_del.empty()) { dev_static_ok = false; }      // the device tables of the last pass commit are history
     if (ncl > dev_ncl) {
         std::vector<uint32_t> sz; std::vector<int32_t> li;
         for (uint32_t c = dev_ncl; c < ncl; ++c) {
@@ -1251,7 +1252,7 @@ int64_t Engine::stat(const char* s) const
     ST("ph_upload_ns", ph_upload) ST("ph_download_ns", ph_download) ST("ph_simplify_ns", ph_simplify)
     ST("ph_init_ns", ph_init) ST("ph_sub_ns", ph_sub) ST("ph_str_ns", ph_str) ST("ph_prefetch_ns", ph_prefetch) ST("ph_total_ns", ph_total)
     ST("queue_static", n_static) ST("parallel_sub_passes", n_parsub) ST("device_sub_passes", n_devsub) ST("overlapped_str_scans", n_overlap)
-    ST("component_passes", n_compar) ST("component_fallbacks", n_compar_fallback) ST("component_rounds", n_compar_rounds)
+    ST("device_static_passes", n_devstatic) ST("component_passes", n_compar) ST("component_fallbacks", n_compar_fallback) ST("component_rounds", n_compar_rounds)
     ST("spec_requests", n_spec_requests) ST("spec_rounds", n_spec_rounds) ST("spec_used", n_spec_used)
     ST("host_commit_ns", host_ns_commit) ST("host_gpuwait_ns", host_ns_gpuwait)
     if (!strncmp(s, "gpu_", 4)) { return gpu ? cp3g_counter(gpu, s + 4) : 0; }

@@ -67,7 +67,7 @@ struct Tuning {
     uint32_t devcommit_maxlist;  // CP3_DEVCOMMIT_MAXLIST: longest list with deaths that one device thread may replay
     size_t par_min;              // CP3_PAR_MIN: list length from which id sorting, scan-cache build and occurrence updates run on all cores
     uint64_t bce_maxwords;       // CP3_BCE_MAXWORDS: K9 mask words per variable in the batch (longer: rows on demand)
-    bool no_devcommit, no_overlap, no_precompact, no_lazy, no_plan, no_components, no_bve_eval, no_bve_prefetch;   // CP3_NO_<...>=1: switch one form off
+    bool no_devcommit, no_overlap, no_precompact, no_lazy, no_plan, no_components, no_devstatic, no_bve_eval, no_bve_prefetch;   // CP3_NO_<...>=1: switch one form off
     bool debug_par, debug_bve, debug_fine, debug_ondemand, debug_pre;                                // CP3_DEBUG_<...>: phase timers on stderr
     Tuning();
 };
@@ -384,7 +384,12 @@ private:
     int strengtheningWorker(bool useHeap, int ignore);
     int naiveStrengthening(bool useHeap, int ignore);
     // the real entries of a strengthening pass, committed by dependency component on all cores (engine_str.cpp)
-    bool strengthenComponents(const std::vector<uint32_t>& reals);
+    // static part of the pass as the device computed it (K10, cp3g_str_static): the inert entries' number and steps, the lists they walk
+    struct DevStatic { uint64_t inert_n = 0, inert_steps = 0; std::vector<uint32_t> walked_bits, real_bits; };
+    bool strengthenComponents(const std::vector<uint32_t>& reals, const DevStatic* ds = nullptr);
+    // first strengthening pass behind a device-committed subsumption pass: K10 replaces the static plan of the host
+    bool dev_static_ok = false; int64_t n_devstatic = 0;
+    bool strengthenFirstPassDevice();
     int64_t n_compar = 0, n_compar_fallback = 0, n_compar_rounds = 0;
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
     void updateOccurrences(bool useHeap, int ignore);

@@ -102,7 +102,7 @@ Tuning::Tuning()
       touched_min((uint64_t)envNum("CP3_TOUCHED_MIN", 262144)), devcommit_maxlist((uint32_t)envNum("CP3_DEVCOMMIT_MAXLIST", 4096)),
       par_min((size_t)envNum("CP3_PAR_MIN", 16384)), bce_maxwords((uint64_t)envNum("CP3_BCE_MAXWORDS", 1ll << 22)),
       no_devcommit(envSet("CP3_NO_DEVCOMMIT")), no_overlap(envSet("CP3_NO_OVERLAP")), no_precompact(envSet("CP3_NO_PRECOMPACT")),
-      no_lazy(envSet("CP3_NO_LAZY")), no_plan(envSet("CP3_NO_PLAN")), no_components(envSet("CP3_NO_COMPONENTS")), no_bve_eval(envSet("CP3_NO_BVE_EVAL")), no_bve_prefetch(envSet("CP3_NO_BVE_PREFETCH")),
+      no_lazy(envSet("CP3_NO_LAZY")), no_plan(envSet("CP3_NO_PLAN")), no_components(envSet("CP3_NO_COMPONENTS")), no_devstatic(envSet("CP3_NO_DEVSTATIC")), no_bve_eval(envSet("CP3_NO_BVE_EVAL")), no_bve_prefetch(envSet("CP3_NO_BVE_PREFETCH")),
       debug_par(envSet("CP3_DEBUG_PAR")), debug_bve(envSet("CP3_DEBUG_BVE")), debug_fine(envSet("CP3_DEBUG_FINE")),
       debug_ondemand(envSet("CP3_DEBUG_ONDEMAND")), debug_pre(envSet("CP3_DEBUG_PRE"))
 {

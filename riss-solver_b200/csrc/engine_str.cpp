@@ -199,6 +199,15 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
     DbgLap lap("str"); lap("prepare");
+    // first pass behind a device-committed subsumption pass: the static plan comes from the device (K10), the real entries are
+    // committed by component; false = nothing was touched, the host plan below takes the pass
+    bool fast_done = false;
+    if (dev_static_ok && opt.strength && !tune.no_devstatic && !tune.no_components && nthreads > 1 && !hasToPropagate() &&
+        strq.size() >= std::max<size_t>(tune.par_min, 1)) {
+        fast_done = strengthenFirstPassDevice();
+        lap("device static + components");
+    }
+    dev_static_ok = false;
     const bool fine = lap.on && tune.debug_fine;          // per-entry timers (they cost as much as the entries)
     int64_t t0 = now_ns();
     // Statically inert queue entries.  While no unit is propagated, lit_occurrence_count and the occurrence lists
@@ -206,9 +215,9 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     // (a) has no candidate hit, (b) is no candidate target of anybody and (c) walks two lists without deleted
     // entries only adds |occ(min)| - 1 + |occ(~min)| steps - independent of everything else.  Those are
     // evaluated on all host cores; the ordered walk below just adds the number up when it passes them.
-    pfill(contrib, strq.size(), -1); pfill(contrib_t, strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size());
+    if (!fast_done) { pfill(contrib, strq.size(), -1); pfill(contrib_t, strq.size(), -1); tmin.resize(strq.size()); plan_ver.resize(strq.size()); }
     const size_t static_min = tune.static_min;
-    bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate();
+    bool static_valid = opt.strength && strq.size() > static_min && !hasToPropagate() && !fast_done;
     if (static_valid) {
         is_target.assign((C.size() >> 6) + 1, 0ull);
         for (const Hit& h : c_str.hits) { is_target[h.clause >> 6] |= 1ull << (h.clause & 63); }
@@ -339,8 +348,8 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
     size_t ri = reals.size();                                       // reals[0..ri) are still ahead (the walk goes down)
     lap("reals");
     // the real entries by dependency component on all cores; false = nothing was touched, the ordered walk below takes the pass
-    bool par_done = false;
-    if (static_lazy && !tune.no_components && nthreads > 1 && reals.size() >= std::max<size_t>(tune.par_min, 1) && !hasToPropagate()) {
+    bool par_done = fast_done;
+    if (!fast_done && static_lazy && !tune.no_components && nthreads > 1 && reals.size() >= std::max<size_t>(tune.par_min, 1) && !hasToPropagate()) {
         par_done = strengthenComponents(reals);
         if (!par_done) { ++n_compar_fallback; }
         lap("components");
@@ -768,7 +777,7 @@ namespace cp3 {
 // the missing versions are scanned in one batch and the simulation is repeated; a unit clause, a hit on a statically inert
 // entry or the step limit in reach hands the pass - still untouched - to the ordered walk.  The commit then applies the final
 // clause contents, and the queue pushes / occurrence updates in the order of their (queue time, sequence) keys.
-bool Engine::strengthenComponents(const std::vector<uint32_t>& reals)
+bool Engine::strengthenComponents(const std::vector<uint32_t>& reals, const DevStatic* ds)
 {
     const size_t nq = strq.size(), ncl = C.size(), nlit = (size_t)2 * nvars;
     const bool unlimited = !opt.limited;
@@ -989,7 +998,8 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals)
         // a new hit on a statically inert entry would make it a real one: leave that to the ordered walk
         for (size_t h = h0; h < c_str.hits.size(); ++h) {
             const uint32_t x = c_str.hits[h].clause;
-            if (x < qtime.size() && qtime[x] >= 0) { const size_t pos = nq - 1 - (size_t)qtime[x]; if (pos < contrib.size() && contrib[pos] >= 0) { return false; } }
+            if (ds) { if (x < ncl && !((ds->real_bits[x >> 5] >> (x & 31)) & 1u) && !(C[x].flag & F_DEL)) { return false; } }
+            else if (x < qtime.size() && qtime[x] >= 0) { const size_t pos = nq - 1 - (size_t)qtime[x]; if (pos < contrib.size() && contrib[pos] >= 0) { return false; } }
         }
         // components that the new hits connect: both sides are simulated again under their common root
         for (size_t k = e0; k < c_str.ent.size(); ++k) {
@@ -1012,7 +1022,13 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals)
         }
     }
     std::vector<int64_t> part((size_t)T + 1, 0), ninert((size_t)T + 1, 0), pstale((size_t)T + 1, 0);
-    parallelFor(nq, [&](size_t b, size_t e, int t) { int64_t a = 0, c2 = 0; for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { a += contrib[p]; ++c2; } } part[(size_t)t] = a; ninert[(size_t)t] = c2; });
+    if (ds) {
+        // the inert entries were evaluated by K10; the lists they walk are cleaned (and paid for) together with the simulated walks'
+        part[0] = (int64_t)ds->inert_steps; ninert[0] = (int64_t)ds->inert_n;
+        parallelFor(nlit, [&](size_t b, size_t e, int) { for (size_t x = b; x < e; ++x) { if (((ds->walked_bits[x >> 5] >> (x & 31)) & 1u) && hasStale((int)x)) { walked_stale[x] = 1; } } });
+    } else {
+        parallelFor(nq, [&](size_t b, size_t e, int t) { int64_t a = 0, c2 = 0; for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { a += contrib[p]; ++c2; } } part[(size_t)t] = a; ninert[(size_t)t] = c2; });
+    }
     // the first walk of a list pays one step per deleted entry it removes
     parallelFor(nlit, [&](size_t b, size_t e, int t) {
         int64_t a = 0;
@@ -1081,6 +1097,50 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals)
     str_steps += total; n_fast += nfast; n_slow += nslow; n_lazy = inert_n;
     ++n_compar;
     lap("commit");
+    return true;
+}
+
+// The first strengthening pass of a run, planned by the device.  The queue holds every clause in clause order and the device still
+// holds the tables of the subsumption pass it has just committed (list lengths, deleted entries still listed, deaths per literal):
+// K10 evaluates every queue entry that no cached hit touches - literal choice, the two list lengths, the lists it walks - in one
+// launch; the host only needs the entries hits do touch (O(#hits)) and commits them by component.
+bool Engine::strengthenFirstPassDevice()
+{
+    const size_t ncl = C.size(), nq = strq.size();
+    if (nq != ncl || ncl == 0 || c_str.slot.size() < ncl) { return false; }
+    std::atomic<bool> fit{true};
+    parallelFor(nq, [&](size_t b, size_t e, int) {
+        bool good = true;
+        for (size_t p = b; p < e && good; ++p) { const ClauseInfo& ci = C[p]; good = strq[p] == (uint32_t)p && ((ci.flag & F_DEL) || (ci.flag & F_STR)); }
+        if (!good) { fit = false; }
+    });
+    if (!fit) { return false; }
+    DevStatic ds;
+    ds.real_bits.assign((ncl + 31) / 32, 0u);
+    // real entries: clauses with a scan record (own hits, predicted contents) and the targets of all cached hits
+    parallelFor(c_str.used.size(), [&](size_t b, size_t e, int) { for (size_t u = b; u < e; ++u) { const uint32_t c = c_str.used[u]; __atomic_fetch_or(&ds.real_bits[c >> 5], 1u << (c & 31), __ATOMIC_RELAXED); } }, 8192);
+    parallelFor(c_str.hits.size(), [&](size_t b, size_t e, int) { for (size_t h = b; h < e; ++h) { const uint32_t c = c_str.hits[h].clause; __atomic_fetch_or(&ds.real_bits[c >> 5], 1u << (c & 31), __ATOMIC_RELAXED); } }, 8192);
+    ds.walked_bits.assign(((size_t)2 * nvars + 31) / 32 + 1, 0u);
+    int status = 1; uint64_t small = 0;
+    const int64_t t0 = now_ns();
+    if (cp3g_str_static(gpu, ds.real_bits.data(), &status, &ds.inert_n, &ds.inert_steps, &small, ds.walked_bits.data()) != CP3G_OK) { die("device static plan failed"); }
+    host_ns_gpuwait += now_ns() - t0;
+    if (status != 0 || small != 0) { return false; }
+    // queue positions of the real entries = their clause indices, ascending
+    std::vector<uint32_t> reals;
+    {
+        const size_t words = ds.real_bits.size();
+        std::vector<size_t> cnt((size_t)nthreads + 2, 0);
+        parallelFor(words, [&](size_t b, size_t e, int t) { size_t c = 0; for (size_t w = b; w < e; ++w) { c += (size_t)__builtin_popcount(ds.real_bits[w]); } cnt[(size_t)t + 1] = c; }, 4096);
+        for (size_t t = 1; t < cnt.size(); ++t) { cnt[t] += cnt[t - 1]; }
+        reals.resize(cnt.back());
+        parallelFor(words, [&](size_t b, size_t e, int t) {
+            size_t o = cnt[(size_t)t];
+            for (size_t w = b; w < e; ++w) { uint32_t x = ds.real_bits[w]; while (x) { reals[o++] = (uint32_t)(w * 32 + (size_t)__builtin_ctz(x)); x &= x - 1; } }
+        }, 4096);
+    }
+    if (!strengthenComponents(reals, &ds)) { return false; }
+    ++n_devstatic;
     return true;
 }
 

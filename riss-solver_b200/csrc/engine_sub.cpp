@@ -305,6 +305,7 @@ bool Engine::subsumptionCommitDevice()
     touchDeadClauses(dead);
     if (ndead) { successful(t_sub); }
     sub_steps += (int64_t)steps;
+    dev_static_ok = true;                              // the device holds the post-pass tables: K10 can plan the strengthening pass
     parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { C[subq[p]].flag &= ~F_SUB; } });
     lap("bookkeeping");
     return true;

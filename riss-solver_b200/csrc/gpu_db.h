@@ -54,7 +54,7 @@ struct cp3g {
     DevBuf<uint32_t> bu0, bu1, bu2, bu3, bu4; DevBuf<unsigned long long> bq0; DevBuf<int16_t> bs0; DevBuf<int32_t> bl0;
     // device-side pass commit (commit.cu)
     DevBuf<int32_t> sp_da, sp_db, sp_chosen, sp_dltime; DevBuf<uint32_t> sp_dlcnt, sp_dloff, sp_dlfill, sp_n, sp_stale, sp_dead, sp_refs;
-    const int32_t* sp_dtime = nullptr; bool sp_valid = false; uint32_t sp_ndead = 0; int64_t commit_ns = 0;
+    const int32_t* sp_dtime = nullptr; bool sp_valid = false; uint32_t sp_ndead = 0; int64_t commit_ns = 0; int64_t sp_build = -1; uint32_t sp_ncl = 0;
     // device-side BVE evaluation (bve_eval.cu): the batch stays resident between cp3g_bve_eval and cp3g_bve_stream
     DevBuf<unsigned char> ev_recs; DevBuf<uint16_t> ev_pst, ev_nst, ev_rsz; DevBuf<unsigned long long> ev_loff; uint32_t ev_nv = 0; int64_t bve_ns = 0;
     int64_t bce_ns = 0, bce_bytes = 0;                                 // K9 (bce.cu)

@@ -18,7 +18,7 @@ struct cp3g {
     // result of the last cp3g_sub_pass
     // last cp3g_bve_eval batch (cp3g_bve_stream reads it)
     std::vector<uint32_t> ev_vars, ev_poff, ev_prefs, ev_noff, ev_nrefs; std::vector<cp3g_bve_rec> ev_recs;
-    bool sp_valid = false; std::vector<uint32_t> sp_dead, sp_n, sp_stale; std::vector<std::vector<uint32_t>> sp_lists;
+    bool sp_valid = false; std::vector<uint32_t> sp_dead, sp_n, sp_stale, sp_dlc, sp_len0; std::vector<std::vector<uint32_t>> sp_lists; size_t sp_ncl = 0;
     std::string err;
 };
 
@@ -121,9 +121,35 @@ int cp3g_sub_pass(cp3g* g, uint32_t max_list, int* status, uint32_t* ndead, uint
     for (uint32_t d : dead) { for (int32_t x : g->cl[d]) { if (g->occ[x].size() > max_list) { return CP3G_OK; } } }
     g->sp_dead = dead; g->sp_lists = L; g->sp_n.assign(L.size(), 0); g->sp_stale.assign(L.size(), 0);
     for (size_t x = 0; x < L.size(); ++x) { g->sp_n[x] = (uint32_t)L[x].size(); for (uint32_t d : L[x]) { g->sp_stale[x] += del[d] && !g->del[d]; } }
-    for (uint32_t d : dead) { g->del[d] = 1; }
+    g->sp_dlc.assign(L.size(), 0); g->sp_len0.assign(L.size(), 0);
+    for (size_t x = 0; x < L.size(); ++x) { g->sp_len0[x] = (uint32_t)g->occ[x].size(); }
+    for (uint32_t d : dead) { g->del[d] = 1; for (int32_t x : g->cl[d]) { ++g->sp_dlc[x]; } }
+    g->sp_ncl = g->cl.size();
     g->sp_valid = true; g->launches += 12;
     *status = 0; *ndead = (uint32_t)dead.size(); *nlits = nl; *steps = st; if (checks) { *checks = st; }
+    return CP3G_OK;
+}
+int cp3g_str_static(cp3g* g, const uint32_t* real_bits, int* status, uint64_t* inert_entries, uint64_t* inert_steps, uint64_t* small_clauses,
+                    uint32_t* walked_bits)
+{
+    *status = 1;
+    if (!g->sp_valid || g->sp_ncl != g->cl.size()) { return CP3G_OK; }
+    const size_t nlit = g->occ.size();
+    for (size_t w = 0; w < (nlit + 31) / 32; ++w) { walked_bits[w] = 0; }
+    uint64_t ent = 0, st = 0, small = 0;
+    auto cnt = [&](int32_t y) { return (int)g->sp_len0[y] - 2 * (int)g->sp_dlc[y]; };
+    for (uint32_t c = 0; c < g->cl.size(); ++c) {
+        if (g->del[c] || ((real_bits[c >> 5] >> (c & 31)) & 1u)) { continue; }
+        const std::vector<int32_t>& C = g->cl[c];
+        if (C.size() < 2) { ++small; continue; }
+        int32_t mn = C[0]; int best = cnt(mn & ~1) + cnt(mn | 1);
+        for (size_t k = 1; k < C.size(); ++k) { const int d = cnt(C[k] & ~1) + cnt(C[k] | 1); if (best > d) { best = d; mn = C[k]; } }
+        const uint32_t l1 = g->sp_n[mn] - g->sp_stale[mn], l2 = g->sp_n[mn ^ 1] - g->sp_stale[mn ^ 1];
+        st += (l1 ? l1 - 1 : 0) + l2; ++ent;
+        walked_bits[(uint32_t)mn >> 5] |= 3u << ((uint32_t)mn & 30u);
+    }
+    g->launches++;
+    *inert_entries = ent; *inert_steps = st; *small_clauses = small; *status = 0;
     return CP3G_OK;
 }
 int cp3g_sub_pass_fetch(cp3g* g, uint32_t* dead, uint32_t* list_n, uint32_t* list_stale, uint32_t* refs)
