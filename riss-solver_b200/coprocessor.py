@@ -206,6 +206,17 @@ class ScanService:
         return {"dead": np.sort(dead[:nd.value]), "lits": int(nl.value), "steps": int(steps.value), "checks": int(chk.value),
                 "off": off, "n": n, "stale": stale, "refs": refs[:int(off[-1])]}
 
+    def str_static(self, real_bits):
+        """K10 (cp3g_str_static) behind a committed sub_pass: real_bits = uint32 words, one bit per clause.  Returns None when not
+        applicable, else (inert entries, inert steps, small clauses, walked bits as uint32 words over the literals)"""
+        real_bits = np.ascontiguousarray(real_bits, dtype=np.uint32)
+        st = C.c_int(1); ne = C.c_uint64(0); ns = C.c_uint64(0); sm = C.c_uint64(0)
+        walked = np.zeros((2 * self.nvars + 31) // 32 + 1, dtype=np.uint32)
+        self._ck(self.L.cp3g_str_static(self.g, real_bits.ctypes.data, C.byref(st), C.byref(ne), C.byref(ns), C.byref(sm), walked.ctypes.data), "str_static")
+        if st.value != 0:
+            return None
+        return int(ne.value), int(ns.value), int(sm.value), walked
+
     def bve_pairs(self, vars_, pos_lists, neg_lists):
         vars_ = np.ascontiguousarray(vars_, dtype=np.uint32)
         p_off = np.zeros(vars_.size + 1, dtype=np.uint32); n_off = np.zeros(vars_.size + 1, dtype=np.uint32)

@@ -170,12 +170,16 @@ void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
     // processing time of the queue entries: the queue is drained from the back
     if (qtime.size() < C.size()) { pgrow(qtime, C.size() + 1024, -1); }
     // (a clause queued twice keeps the time of its last entry, like the sequential fill)
-    { bool inc = true; for (size_t i = 1; i < strq.size(); ++i) { if (strq[i - 1] >= strq[i]) { inc = false; break; } }
+    { std::atomic<bool> inc{true};
       const size_t nq = strq.size();
+      parallelFor(nq, [&](size_t b, size_t e, int) { bool g = true; for (size_t i = std::max<size_t>(b, 1); i < e && g; ++i) { g = strq[i - 1] < strq[i]; } if (!g) { inc = false; } });
       if (inc) { parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } }); }
       else { for (size_t i = 0; i < nq; ++i) { qtime[strq[i]] = (int32_t)(nq - 1 - i); } } }
-    for (size_t k = 0; k < c_str.ent.size(); ++k) { c_str.ent[k].time = 0; }
-    for (uint32_t c : ids) { if (c_str.slot[c] >= 0) { c_str.ent[c_str.slot[c]].time = (double)qtime[c]; } }
+    // the records of this scan belong to the clauses in c_str.used: their queue time is the time of the record
+    parallelFor(c_str.ent.size(), [&](size_t b, size_t e, int) { for (size_t k = b; k < e; ++k) { c_str.ent[k].time = 0; } }, 16384);
+    parallelFor(c_str.used.size(), [&](size_t b, size_t e, int) {
+        for (size_t u = b; u < e; ++u) { const uint32_t c = c_str.used[u]; if (c_str.slot[c] >= 0 && qtime[c] >= 0) { c_str.ent[(size_t)c_str.slot[c]].time = (double)qtime[c]; } }
+    }, 8192);
     lap("qtime");
     prefetchStrengthenClosure();
     lap("closure");

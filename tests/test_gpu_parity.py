@@ -383,6 +383,46 @@ def test_device_subsumption_commit_matches_the_ordered_walk(gen):
             assert np.array_equal(a["refs"][o:o + k], b["refs"][o:o + k]), x
 
 
+def test_k10_static_strengthening_plan_matches_the_host_rule(gen):
+    """cp3g_str_static (K10) behind cp3g_sub_pass: entries, step total and walked lists against the rule restated in numpy from the
+    fetched post-pass tables (literal choice by variable occurrence count after the double decrement, Subsumption.cc:1292-1299;
+    steps = live length of occ(min) - 1 + live length of occ(~min)), and against the CPU mock of the scan service."""
+    from fuzz_engine import build_mock
+    mock = build_mock()
+    for lits, sizes in (gen.random_ksat(20000, 85200, 3, seed=31, dup=0.04, sup=0.06, flip=0.04), gen.community_ksat(15000, 75000, seed=32)):
+        n = int(np.abs(lits).max()); codes = _sorted_clauses(lits, sizes); cstart = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        ncl = sizes.size
+        rng = np.random.default_rng(7)
+        real = np.zeros((ncl + 31) // 32, dtype=np.uint32)
+        pick = rng.choice(ncl, size=ncl // 10, replace=False)
+        np.bitwise_or.at(real, pick >> 5, (np.uint32(1) << (pick & 31).astype(np.uint32)))
+        res = []
+        for lib in (None, mock):
+            svc = rs.ScanService(lib_path=lib); svc.upload(n, codes, sizes); svc.build()
+            sp = svc.sub_pass(max_list=1 << 20); assert sp is not None
+            res.append((sp, svc.str_static(real))); svc.close()
+        (sp, a), (_, b) = res
+        assert a is not None and b is not None
+        assert a[:3] == b[:3] and np.array_equal(a[3], b[3])
+        # numpy restatement from the fetched tables
+        dead = np.zeros(ncl, dtype=bool); dead[sp["dead"]] = True
+        len0 = (sp["off"][1:] - sp["off"][:-1]).astype(np.int64)
+        deaths = np.bincount(np.concatenate([codes[cstart[d]:cstart[d + 1]] for d in sp["dead"]]), minlength=2 * n).astype(np.int64)
+        cnt = len0 - 2 * deaths; live = sp["n"].astype(np.int64) - sp["stale"].astype(np.int64)
+        ent = 0; steps = 0; walked = np.zeros_like(a[3])
+        isreal = ((real[np.arange(ncl) >> 5] >> (np.arange(ncl) & 31).astype(np.uint32)) & 1).astype(bool)
+        for c in np.flatnonzero(~dead & ~isreal):
+            L = codes[cstart[c]:cstart[c + 1]]
+            if L.size < 2:
+                continue
+            d = cnt[L & ~1] + cnt[L | 1]
+            mn = int(L[int(np.argmin(d))])                      # the first literal with the smallest count
+            steps += (int(live[mn]) - 1 if live[mn] else 0) + int(live[mn ^ 1]); ent += 1
+            walked[mn >> 5] |= np.uint32(3) << np.uint32(mn & 30)
+        assert (ent, steps) == a[:2] and a[2] == 0
+        assert np.array_equal(walked, a[3])
+
+
 def test_bve_evaluation_kernels_match_the_per_variable_sequence(gen):
     """K5'/K6' (bve_eval.cu: gate detection with list reordering, lazy cleaning, anticipation, resolvent streams) against the plain
     per-variable sequence of bve_worker run on the CPU (tests/mock): records, rewritten list ORDER, per-clause statistics, and
