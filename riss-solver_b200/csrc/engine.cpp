@@ -3,9 +3,73 @@
 // (subsumption), engine_str.cpp (strengthening), engine_bve.cpp (BVE), engine_bce.cpp (BCE).  Reference lines are cited per function.
 #include "engine_util.h"
 #include <sys/mman.h>
+#include <condition_variable>
+#include <mutex>
 #include <new>
 
 namespace cp3 {
+
+// ------------------------------------------------------------------------------------------------ worker pool
+struct Engine::WorkerPool {
+    std::vector<std::thread> th;
+    std::mutex m, user;                                  // m guards the job state, user serialises callers
+    std::condition_variable cv, done;
+    const std::function<void(int)>* job = nullptr;
+    int ntasks = 0, next = 0, pending = 0; uint64_t gen = 0; bool stop = false;
+    explicit WorkerPool(int workers)
+    {
+        for (int w = 0; w < workers; ++w) {
+            th.emplace_back([this]() {
+                uint64_t seen = 0;
+                std::unique_lock<std::mutex> lk(m);
+                for (;;) {
+                    cv.wait(lk, [&]() { return stop || gen != seen; });
+                    if (stop) { return; }
+                    seen = gen;
+                    while (next < ntasks) {
+                        const int t = next++;
+                        const std::function<void(int)>* j = job;
+                        lk.unlock(); (*j)(t); lk.lock();
+                        if (--pending == 0) { done.notify_all(); }
+                    }
+                }
+            });
+        }
+    }
+    ~WorkerPool()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        for (auto& x : th) { x.join(); }
+    }
+};
+
+void Engine::poolRun(int tasks, const std::function<void(int)>& job)
+{
+    if (tasks <= 0) { return; }
+    if (tasks == 1) { job(0); return; }
+    if (!pool_) { pool_ = new WorkerPool(std::max(1, nthreads - 1)); }
+    WorkerPool& P = *pool_;
+    if (!P.user.try_lock()) {                            // the pool is busy with another caller's loop: plain threads for this one
+        std::vector<std::thread> th;
+        for (int t = 0; t < tasks; ++t) { th.emplace_back([&job, t]() { job(t); }); }
+        for (auto& x : th) { x.join(); }
+        return;
+    }
+    {
+        std::unique_lock<std::mutex> lk(P.m);
+        P.job = &job; P.ntasks = tasks; P.next = 0; P.pending = tasks; ++P.gen;
+        P.cv.notify_all();
+        while (P.next < P.ntasks) {                      // the caller works too
+            const int t = P.next++;
+            lk.unlock(); job(t); lk.lock();
+            if (--P.pending == 0) { P.done.notify_all(); }
+        }
+        P.done.wait(lk, [&]() { return P.pending == 0; });
+        P.job = nullptr;
+    }
+    P.user.unlock();
+}
 
 void* hugeAlloc(size_t bytes)
 {
@@ -51,7 +115,7 @@ Engine::Engine()
     nthreads = tune.threads;
     if (nthreads < 1) { nthreads = 1; }
 }
-Engine::~Engine() { if (gpu) { cp3g_destroy(gpu); } }
+Engine::~Engine() { delete pool_; if (gpu) { cp3g_destroy(gpu); } }
 
 void Engine::die(const char* msg) const
 {
@@ -491,24 +555,25 @@ const Engine::CacheEnt* Engine::cached(const ScanCache& cache, uint32_t c) const
 }
 
 // Scan explicit literal contents (predicted future versions of clauses) against the current device state.
-void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache)
+void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache, bool grouped)
 {
     if (reqs.empty()) { return; }
     ++scan_id; ++n_scan_batches; ++n_spec_rounds; n_spec_requests += (int64_t)reqs.size();
     pgrow(cache.slot, C.size(), -1);
-    std::vector<uint32_t> self(reqs.size()), roff(reqs.size() + 1); std::vector<int32_t> rl;
+    const size_t nr = reqs.size();
+    std::vector<uint32_t> self(nr), roff(nr + 1);
     roff[0] = 0;
-    for (size_t i = 0; i < reqs.size(); ++i) {
-        self[i] = reqs[i].clause;
-        rl.insert(rl.end(), spec_lits.begin() + reqs[i].off, spec_lits.begin() + reqs[i].off + reqs[i].n);
-        roff[i + 1] = (uint32_t)rl.size();
-    }
+    for (size_t i = 0; i < nr; ++i) { roff[i + 1] = roff[i] + reqs[i].n; }
+    RawVec<int32_t> rl; rl.resize((size_t)roff[nr] + 1);
+    parallelFor(nr, [&](size_t b2, size_t e2, int) {
+        for (size_t i = b2; i < e2; ++i) { self[i] = reqs[i].clause; memcpy(rl.data() + roff[i], spec_lits.data() + reqs[i].off, sizeof(int32_t) * reqs[i].n); }
+    }, 8192);
     int64_t t0 = now_ns();
-    uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, reqs.size() / 4));
+    uint32_t cap = (uint32_t)std::max<size_t>(hitbuf.size(), std::max<size_t>(4096, nr / 4));
     uint32_t n = 0; uint64_t chk = 0;
     for (;;) {
         hitbuf.resize(cap);
-        int r = cp3g_scan(gpu, kind, (uint32_t)reqs.size(), self.data(), roff.data(), rl.data(), hitbuf.data(), cap, &n, &chk);
+        int r = cp3g_scan(gpu, kind, (uint32_t)nr, self.data(), roff.data(), rl.data(), hitbuf.data(), cap, &n, &chk);
         if (r == CP3G_OK) { break; }
         if (r == CP3G_ERR_OVERFLOW) { cap = n + n / 8 + 1024; continue; }
         die("speculative scan failed");
@@ -516,16 +581,40 @@ void Engine::scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCac
     host_ns_gpuwait += now_ns() - t0;
     if (tune.debug_par) { fprintf(stderr, "  scanSpeculative gpu call %.1f ms, %zu reqs, %u hits\n", (now_ns() - t0) / 1e6, reqs.size(), n); }
     sortHits(hitbuf, n);
-    uint32_t h = 0;
-    for (uint32_t i = 0; i < reqs.size(); ++i) {
-        CacheEnt e; e.ver = UINT32_MAX; e.scan = scan_id; e.hb = (uint32_t)cache.hits.size();
-        while (h < n && hitbuf[h].req == i) { cache.hits.push_back({hitbuf[h].clause, hitbuf[h].lit}); ++h; }
-        e.he = (uint32_t)cache.hits.size();
-        e.lit_off = (uint32_t)cache.lits.size(); e.lit_n = reqs[i].n; e.time = reqs[i].time;
-        cache.lits.insert(cache.lits.end(), spec_lits.begin() + reqs[i].off, spec_lits.begin() + reqs[i].off + reqs[i].n);
-        e.next = cache.slot[reqs[i].clause];
-        cache.setSlot(reqs[i].clause, (int32_t)cache.ent.size());
-        cache.ent.push_back(e);
+    // one record per request, in request order: hit ranges by counting, literals as one block, fields on all cores
+    const size_t e0 = cache.ent.size(), l0 = cache.lits.size(), h0 = cache.hits.size();
+    std::vector<uint32_t> hstart(nr + 1, 0u);
+    for (uint32_t k = 0; k < n; ++k) { ++hstart[(size_t)hitbuf[k].req + 1]; }
+    for (size_t i = 0; i < nr; ++i) { hstart[i + 1] += hstart[i]; }
+    cache.hits.resize(h0 + n);
+    for (uint32_t k = 0; k < n; ++k) { cache.hits[h0 + k] = Hit{hitbuf[k].clause, hitbuf[k].lit}; }
+    cache.lits.resize(l0 + roff[nr]);
+    cache.ent.resize(e0 + nr);
+    parallelFor(nr, [&](size_t b2, size_t e2, int) {
+        memcpy(cache.lits.data() + l0 + roff[b2], rl.data() + roff[b2], sizeof(int32_t) * (size_t)(roff[e2] - roff[b2]));
+        for (size_t i = b2; i < e2; ++i) {
+            CacheEnt& en = cache.ent[e0 + i];
+            en.ver = UINT32_MAX; en.scan = scan_id; en.hb = (uint32_t)(h0 + hstart[i]); en.he = (uint32_t)(h0 + hstart[i + 1]);
+            en.lit_off = (uint32_t)(l0 + roff[i]); en.lit_n = reqs[i].n; en.time = reqs[i].time; en.next = -1;
+        }
+    }, 8192);
+    // chains: the newest record of a clause first
+    if (grouped && nr >= std::max<size_t>(tune.par_min, 1) && nthreads > 1) {
+        std::vector<std::vector<uint32_t>> fresh((size_t)nthreads + 1);
+        parallelFor(nr, [&](size_t b2, size_t e2, int t) {
+            for (size_t i = b2; i < e2; ++i) {
+                if (i > 0 && reqs[i - 1].clause == reqs[i].clause) { continue; }          // a run belongs to the chunk it starts in
+                const uint32_t c = reqs[i].clause;
+                int32_t prev = cache.slot[c];
+                if (prev < 0) { fresh[(size_t)t].push_back(c); }
+                size_t j = i;
+                for (; j < nr && reqs[j].clause == c; ++j) { cache.ent[e0 + j].next = prev; prev = (int32_t)(e0 + j); }
+                cache.slot[c] = prev;
+            }
+        }, 8192);
+        for (const auto& v : fresh) { cache.used.insert(cache.used.end(), v.begin(), v.end()); }
+    } else {
+        for (size_t i = 0; i < nr; ++i) { cache.ent[e0 + i].next = cache.slot[reqs[i].clause]; cache.setSlot(reqs[i].clause, (int32_t)(e0 + i)); }
     }
 }
 
@@ -647,7 +736,7 @@ void Engine::prefetchStrengthenClosure()
         }
         lap("merge");
         if (reqs.empty()) { break; }
-        scanSpeculative(CP3G_STRENGTHEN, reqs, c_str);
+        scanSpeculative(CP3G_STRENGTHEN, reqs, c_str, true);
         lap("scanSpeculative");
     }
 }

@@ -18,6 +18,7 @@
 #include <queue>
 #include <thread>
 #include <memory>
+#include <functional>
 #include "../../include/cp3b200.h"
 
 namespace cp3 {
@@ -223,7 +224,8 @@ private:
     inline bool isDel(uint32_t c) const { return (delbits[c >> 6] >> (c & 63)) & 1; }
     struct SpecReq { uint32_t clause; uint32_t off, n; double time; };   // literals in spec_lits[off..off+n)
     std::vector<int32_t> spec_lits;
-    void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache);
+    // grouped: the requests of one clause are consecutive (the closure builds them clause by clause): records are linked on all cores
+    void scanSpeculative(int kind, const std::vector<SpecReq>& reqs, ScanCache& cache, bool grouped = false);
     void prefetchStrengthenClosure();
     RawVec<int32_t> qtime;                           // strengthening queue: processing time of a pending clause
     int64_t n_spec_requests = 0, n_spec_rounds = 0, n_spec_used = 0, n_static = 0;
@@ -247,6 +249,11 @@ private:
     void restoreOneList(int x);
     void unpredictedEdit(uint32_t c);               // a clause the static plan relied on was modified
     template <class F> void parallelFor(size_t n, F f, size_t grain = 65536);
+    // persistent workers behind parallelFor (a fixpoint makes ~60 such calls; starting 16 threads for each costs more than many of
+    // the loops themselves).  One job at a time: a second caller - the scan helper thread - starts its own threads instead.
+    struct WorkerPool;
+    WorkerPool* pool_ = nullptr;
+    void poolRun(int tasks, const std::function<void(int)>& job);
     template <class F> void parallelForG(size_t n, size_t grain, F f) { parallelFor(n, f, grain); }
     // stable parallel filter: out = [x in src | pred(x)] (count per chunk, prefix, write)
     // size a work array and fill it on all cores

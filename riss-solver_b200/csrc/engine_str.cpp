@@ -853,16 +853,30 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals, const DevS
         // bucket the entries by root range so that a component lands in exactly one bucket; sort by (root, position descending)
         std::vector<std::vector<Ent>> bucket((size_t)T);
         {
+            // root ranges with about the same number of entries each (roots are the smallest clause index of their component:
+            // low indices are over-represented): 4096 coarse bins, cut where the running count passes k/T of the total
             std::vector<std::vector<Ent>> parts(((size_t)T + 1) * (size_t)T);
-            const uint64_t width = ((uint64_t)ncl + (uint64_t)T - 1) / (uint64_t)T;
+            std::vector<std::vector<Ent>> rooted((size_t)T + 1);
+            const uint64_t NBIN = 4096, bw = ((uint64_t)ncl + NBIN - 1) / NBIN;
+            std::vector<std::vector<uint32_t>> hist((size_t)T + 1, std::vector<uint32_t>(NBIN, 0u));
             parallelFor((size_t)T + 1, [&](size_t b, size_t e, int) {
                 for (size_t t = b; t < e; ++t) {
                     for (const uint32_t p : tpos[t]) {
                         const uint32_t r = find(strq[p]);
                         if (round > 0 && !dirty.count(r)) { continue; }
-                        parts[t * (size_t)T + (size_t)(r / width)].push_back(Ent{r, p});
+                        rooted[t].push_back(Ent{r, p}); ++hist[t][(size_t)(r / bw)];
                     }
                 }
+            }, 1);
+            std::vector<uint32_t> bin_bucket(NBIN, 0u);
+            { uint64_t tot = 0; for (size_t t = 0; t <= (size_t)T; ++t) { for (uint64_t k = 0; k < NBIN; ++k) { tot += hist[t][k]; } }
+              uint64_t run = 0;
+              for (uint64_t k = 0; k < NBIN; ++k) {
+                  bin_bucket[k] = (uint32_t)std::min<uint64_t>((uint64_t)T - 1, tot ? run * (uint64_t)T / tot : 0);
+                  for (size_t t = 0; t <= (size_t)T; ++t) { run += hist[t][k]; }
+              } }
+            parallelFor((size_t)T + 1, [&](size_t b, size_t e, int) {
+                for (size_t t = b; t < e; ++t) { for (const Ent& x : rooted[t]) { parts[t * (size_t)T + bin_bucket[(size_t)(x.root / bw)]].push_back(x); } }
             }, 1);
             parallelFor((size_t)T, [&](size_t b, size_t e, int) {
                 for (size_t bk = b; bk < e; ++bk) {

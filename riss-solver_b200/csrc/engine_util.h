@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <functional>
 
 namespace cp3 {
 
@@ -66,14 +67,10 @@ template <class F> void Engine::parallelFor(size_t n, F f, size_t grain)
 {
     const int T = (int)std::min<size_t>((size_t)nthreads, (n + grain - 1) / grain);
     if (T <= 1) { f((size_t)0, n, 0); return; }
-    std::vector<std::thread> th;
     const size_t per = (n + T - 1) / T;
-    for (int t = 0; t < T; ++t) {
-        const size_t b = per * t, e = std::min(n, per * (t + 1));
-        if (b >= e) { break; }
-        th.emplace_back([=]() { f(b, e, t); });
-    }
-    for (auto& x : th) { x.join(); }
+    int tasks = 0;
+    for (int t = 0; t < T; ++t) { if (per * t < n) { ++tasks; } }
+    poolRun(tasks, [&](int t) { const size_t b = per * (size_t)t, e = std::min(n, per * ((size_t)t + 1)); f(b, e, t); });
 }
 
 template <class P> void Engine::parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred)
