@@ -955,10 +955,21 @@ void Engine::extLit(int x) { undo.push_back(0); undo.push_back(toDimacs(x)); }
 
 void Engine::filterDeleted(std::vector<uint32_t>& a)
 {
-    if (a.size() >= 262144 && nthreads > 1) {
-        std::vector<uint32_t> out;
-        parallelFilter(a, out, [&](uint32_t c) { return !(C[c].flag & F_DEL); });
-        a.swap(out);
+    if (a.size() >= std::max<size_t>(4 * tune.par_min, 2) && nthreads > 1) {
+        // in place: every chunk compacts itself on its own core, then the chunks are moved down in order (no second array to fault in)
+        const size_t n = a.size();
+        const int T = nthreads; const size_t per = (n + (size_t)T - 1) / (size_t)T;
+        std::vector<size_t> kept((size_t)T, 0);
+        parallelFor((size_t)T, [&](size_t tb, size_t te, int) {
+            for (size_t t = tb; t < te; ++t) {
+                const size_t b = per * t, e = std::min(n, per * (t + 1)); size_t j = b;
+                for (size_t i = b; i < e; ++i) { if (!(C[a[i]].flag & F_DEL)) { a[j++] = a[i]; } }
+                kept[t] = j > b ? j - b : 0;
+            }
+        }, 1);
+        size_t o = 0;
+        for (int t = 0; t < T; ++t) { const size_t b = per * (size_t)t; if (b >= n) { break; } if (o != b && kept[(size_t)t]) { memmove(a.data() + o, a.data() + b, sizeof(uint32_t) * kept[(size_t)t]); } o += kept[(size_t)t]; }
+        a.resize(o);
         return;
     }
     size_t j = 0;
