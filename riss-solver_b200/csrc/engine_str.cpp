@@ -1093,13 +1093,27 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals, const DevS
                 std::sort(v.begin(), v.end(), [](const Ev& a, const Ev& b2) { return a.key < b2.key; });
             }
         }, 1);
-        for (const std::vector<Ev>& v : kb) {
-            for (const Ev& ev : v) {
-                if (ev.push_sub) { subq.push_back(ev.clause); }
-                occ_upd.push_back({ev.clause, ev.lit});
-                if (opt.bve) { touchClauseVars(ev.clause); bveTouch(ev.lit >> 1); }
+        // (with an empty BVE heap touching a variable is a counter increment: on all cores, like the deaths of a subsumption pass)
+        const bool touch_seq = opt.bve && !heap.empty();
+        size_t nsub = 0; std::vector<size_t> base((size_t)T + 1, 0), sbase((size_t)T + 1, 0);
+        for (size_t bk = 0; bk < (size_t)T; ++bk) { size_t c2 = 0; for (const Ev& ev : kb[bk]) { c2 += ev.push_sub ? 1 : 0; } base[bk + 1] = base[bk] + kb[bk].size(); sbase[bk + 1] = sbase[bk] + c2; nsub += c2; }
+        const size_t s0 = subq.size(), u0 = occ_upd.size();
+        subq.resize(s0 + nsub); occ_upd.resize(u0 + base[(size_t)T]);
+        parallelFor((size_t)T, [&](size_t b, size_t e, int) {
+            for (size_t bk = b; bk < e; ++bk) {
+                size_t si = s0 + sbase[bk], ui = u0 + base[bk];
+                for (const Ev& ev : kb[bk]) {
+                    if (ev.push_sub) { subq[si++] = ev.clause; }
+                    occ_upd[ui++] = OccUpd{ev.clause, ev.lit};
+                    if (opt.bve && !touch_seq) {
+                        const int32_t* l = CL(ev.clause);
+                        for (uint32_t k = 0; k < C[ev.clause].size; ++k) { __atomic_fetch_add(&var_touch[(size_t)(l[k] >> 1)], 1u, __ATOMIC_RELAXED); }
+                        __atomic_fetch_add(&var_touch[(size_t)(ev.lit >> 1)], 1u, __ATOMIC_RELAXED);
+                    }
+                }
             }
-        }
+        }, 1);
+        if (touch_seq) { for (const std::vector<Ev>& v : kb) { for (const Ev& ev : v) { touchClauseVars(ev.clause); bveTouch(ev.lit >> 1); } } }
     }
     removedLiterals += (int)evs.size();
     if (!evs.empty()) { successful(t_sub); }
