@@ -22,6 +22,8 @@ A "step" is one whole simplification fixpoint over one formula:
                        (community k-SAT 10M vars / 54M clauses, -up -subsimp -bve): the target configuration takes ~20 s per
                        step, so it is measured once per run, not K times (DESIGN.md "Measurement").
 --config c3            configs[2] as the K-step workload.
+--config c4            configs[3]: the Riss427-style pipeline (-up -subsimp -bve -bce -dense) on one 25M-clause shard per rank of the
+                       200M-clause community k-SAT formula (--gpus 8: weak, one shard each); --vars scales the shard.
 --config zipf          configs[4]: literal-frequency skew sweep, one JSON line per exponent s.
 --impl reference       the reference's own CPU Coprocessor (oracle/_ref, unmodified sources, all host threads) on the same
                        workload and metric.
@@ -49,17 +51,18 @@ UNIT = "checks/s"
 REFSHIM = os.path.join(ROOT, "oracle", "_ref", "refshim")
 SUSI = ["-enabled_cp3", "-subsimp", "-no-cp3_limited"]
 FULL = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-no-cp3_limited"]
-CHECK_STATS = ("sub_subsSteps", "sub_strengthSteps", "bve_steps")
+R427 = ["-enabled_cp3", "-up", "-subsimp", "-bve", "-bce", "-dense", "-no-cp3_limited"]
+CHECK_STATS = ("sub_subsSteps", "sub_strengthSteps", "bve_steps", "bce_steps")
 
 
 class Config:
     def __init__(self, name, n_vars):
         self.name, self.n = name, n_vars
-        self.opts = SUSI if name in ("c2", "zipf") else FULL
+        self.opts = SUSI if name in ("c2", "zipf") else (R427 if name == "c4" else FULL)
 
     def generate(self, seed_offset=0, zipf_s=0.0):
         import riss_solver_b200 as rs
-        if self.name == "c3":
+        if self.name in ("c3", "c4"):
             lits, sizes = rs.gen.community_ksat(self.n, 5 * self.n, seed=20260001 + seed_offset)
         else:
             lits, sizes = rs.gen.random_ksat(self.n, int(4.26 * self.n), 3, seed=(12345 if zipf_s == 0 else 777) + seed_offset, zipf_s=zipf_s)
@@ -67,6 +70,10 @@ class Config:
 
     def workload(self):
         """the string both arms print: what is simplified, with which options"""
+        if self.name == "c4":
+            return (f"BASELINE configs[3]: Riss427-style pipeline (unit propagation, subsumption + strengthening, BVE, blocked clause elimination, Dense) on one "
+                    f"shard of the 200M-clause community-attachment k-SAT formula: {self.n} vars / {5 * self.n} base clauses per rank (8 ranks x 25M = 200M), "
+                    f"seed 20260001 + rank ({' '.join(R427)})")
         if self.name == "c3":
             return (f"BASELINE configs[2]: community-attachment k-SAT {self.n} vars / {5 * self.n} base clauses, k in 3/4/5 (50/30/20 %), 5 % rare variables, "
                     f"+2 % duplicates, 3 % supersets, 3 % flipped copies, seed 20260001; unit propagation + subsumption + strengthening + BVE to the fixpoint ({' '.join(FULL)})")
@@ -154,7 +161,7 @@ def reference_arm(args, cfg: Config):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/refshim missing (reference not built)"}))
         return
     # c2 runs the full workload (2.5 s per step with the thread pool); c3 a tenth of it (the full one takes minutes per step)
-    sample = cfg if cfg.name != "c3" else Config("c3", max(1, cfg.n // 10))
+    sample = cfg if cfg.name not in ("c3", "c4") else Config(cfg.name, max(1, cfg.n // 10))
     _, sizes, stream = sample.generate()
     cores = os.cpu_count() or 1
     seq = run_refshim(stream, sample.opts, "seq")                 # untimed: the step counters of this sample (thread-independent unit)
@@ -203,8 +210,9 @@ KERNEL_FAMILIES = [   # (label, ns counter, algorithmic-bytes counter)
     ("K4 k_full<strengthen>", "gpu_full1_ns", "gpu_full1_bytes"),
     ("commit k_sp_* (device pass commit)", "gpu_commit_ns", "gpu_commit_bytes"),
     ("K5'+K6' k_bve_eval/k_bve_stream", "gpu_bve_ns", "gpu_bve_bytes"),
+    ("K9 k_bce_masks", "gpu_bce_ns", "gpu_bce_bytes"),
 ]
-STEP_STATS = ["sub_subsSteps", "sub_strengthSteps", "bve_steps", "gpu_launches", "gpu_h2d_bytes", "gpu_d2h_bytes", "sub_subsumedClauses", "sub_removedLiterals",
+STEP_STATS = ["sub_subsSteps", "sub_strengthSteps", "bve_steps", "bce_steps", "bce_remBCE", "gpu_launches", "gpu_h2d_bytes", "gpu_d2h_bytes", "sub_subsumedClauses", "sub_removedLiterals",
               "bve_eliminatedVars", "scan_batches", "scan_ondemand", "device_sub_passes", "eval_batches", "gpu_kernel_ns", "gpu_scan_ns",
               "gpu_full0_checks", "gpu_full1_checks", "gpu_full0_launches", "gpu_full1_launches", "gpu_build_count"] + [k for f in KERNEL_FAMILIES for k in f[1:]]
 
@@ -251,7 +259,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c3", "zipf"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "zipf"])
     ap.add_argument("--vars", type=int, default=0, help="variables of the workload (default: 1M for c2/zipf, 10M for c3)")
     ap.add_argument("--mode", default="weak", choices=["weak", "sharded"],
                     help="N>1: weak = one independent formula per rank (each rank its own GPU and share of the host cores); sharded = one formula, "
@@ -260,7 +268,7 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the configs[2]-scale fixpoint that the default c2 run appends at N=1")
     ap.add_argument("--c3-vars", type=int, default=10000000)
     args = ap.parse_args()
-    cfg = Config(args.config, args.vars or (10000000 if args.config == "c3" else 1000000))
+    cfg = Config(args.config, args.vars or (10000000 if args.config == "c3" else (5000000 if args.config == "c4" else 1000000)))
     if args.impl == "reference":
         return reference_arm(args, cfg)
 
@@ -383,7 +391,7 @@ def main():
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(cfg, cfg if cfg.name != "c3" else Config("c3", max(1, cfg.n // 10)))
+            line["cpu_baseline"] = cpu_baseline(cfg, cfg if cfg.name not in ("c3", "c4") else Config(cfg.name, max(1, cfg.n // 10)))
         if world == 1 and cfg.name == "c2" and not args.no_c3:
             # the target configuration, once per run (one untimed + one timed fixpoint)
             c3 = Config("c3", args.c3_vars)
