@@ -69,6 +69,9 @@ static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 #ifndef CP3_WH
 #define CP3_WH 32
 #endif
+#ifndef CP3_FQWARPS
+#define CP3_FQWARPS 4
+#endif
 static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = CP3_GROUPMAX, TCAP = TILE + GROUP_MAX, OFFCAP = CP3_OFFCAP, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
 
@@ -604,7 +607,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
 //   phase 2  the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
 //            which would otherwise stall 31 lanes behind one)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
-static constexpr int WQ_CAP = CP3_WQ, WH_CAP = CP3_WH, FQ_WARPS = 4;
+static constexpr int WQ_CAP = CP3_WQ, WH_CAP = CP3_WH, FQ_WARPS = CP3_FQWARPS;
 static constexpr uint32_t WORK_CAP = CP3_WORKCAP, DCHUNK = CP3_DCHUNK;     // flat work list per tile: (subsumer, <= 8 consecutive candidates)
 struct TileDesc { uint32_t s, n, x0, xe, xa, noff; bool pure; };
 __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
@@ -621,7 +624,7 @@ __device__ __forceinline__ TileDesc make_desc(const uint2 a, const uint2 b)
 template <int KIND>
 __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits,
         const uint32_t* __restrict__ occ_off, const OccEnt* __restrict__ occ_ent, const uint2* __restrict__ tiles,
-        const uint32_t* __restrict__ delbits, uint32_t tile_first, uint32_t tile_last,
+        uint32_t tile_first, uint32_t tile_last,
         cp3g_hit* __restrict__ out, uint32_t cap, uint32_t* __restrict__ nout, unsigned long long* __restrict__ checks)
 {
     __shared__ __align__(16) OccEnt e_s[FQ_WARPS][2][TCAP + DCHUNK];      // + DCHUNK: a unit may read (and ignore) past its chunk
@@ -631,9 +634,9 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
     __shared__ unsigned long long sh_chk[FQ_WARPS], sh_byt[FQ_WARPS];
     __shared__ uint32_t q_s[FQ_WARPS][WQ_CAP], q_d[FQ_WARPS][WQ_CAP]; __shared__ int32_t q_l[FQ_WARPS][WQ_CAP];
     __shared__ cp3g_hit h_buf[FQ_WARPS][WH_CAP];
-    __shared__ uint32_t q_n[FQ_WARPS], h_n[FQ_WARPS];
+    __shared__ uint32_t q_n[FQ_WARPS], h_n[FQ_WARPS], u_n[FQ_WARPS];
     const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    if (lane == 0) { q_n[w] = 0; h_n[w] = 0; mbar_init(&bar[w][0], 1); mbar_init(&bar[w][1], 1); }
+    if (lane == 0) { q_n[w] = 0; h_n[w] = 0; u_n[w] = 0; mbar_init(&bar[w][0], 1); mbar_init(&bar[w][1], 1); }
     __syncwarp();
     unsigned long long nchk = 0, nbytes = 0;
     const uint32_t gwarp = blockIdx.x * FQ_WARPS + w, nwarps = gridDim.x * FQ_WARPS;
@@ -667,6 +670,18 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
         if (lane == 0) { h_n[w] = 0; }
         __syncwarp();
     };
+    // Warp-wide verification of the queued pairs, one pair per lane: the dependent random loads of a pair (two headers,
+    // two literal arrays) overlap with those of 31 others.  Every lane calls it; nothing happens below `at_least` pairs.
+    auto drain = [&](uint32_t at_least) {
+        __syncwarp();
+        const uint32_t qn = min(q_n[w], (uint32_t)WQ_CAP);
+        if (qn < at_least) { return; }
+        for (uint32_t k = lane; k < qn; k += 32) { verify(q_s[w][k], q_d[w][k], q_l[w][k] >> 1, q_l[w][k] & 1); }
+        __syncwarp();
+        if (lane == 0) { q_n[w] = 0; }
+        __syncwarp();
+        if (h_n[w] >= (uint32_t)(WH_CAP / 2)) { flush_hits(); }
+    };
     auto issue = [&](const TileDesc& d, int b) {          // lane 0 only
         const uint32_t bytes_e = d.n * (uint32_t)sizeof(OccEnt), bytes_o = d.noff * 4u;
         mbar_expect_tx(&bar[w][b], bytes_e + bytes_o);
@@ -674,18 +689,18 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
         if (bytes_o) { bulk_g2s(&o_s[w][b][0], occ_off + d.xa, bytes_o, &bar[w][b]); }
     };
 
-    uint32_t t = tile_first + gwarp;
+    uint32_t t = tile_first + gwarp, t1 = t + nwarps, t2 = t1 + nwarps;
     if (t < tile_last) {
         TileDesc cur = make_desc(tiles[t], tiles[t + 1]), nxt = cur;
-        if (t + nwarps < tile_last) { nxt = make_desc(tiles[t + nwarps], tiles[t + nwarps + 1]); }
+        if (t1 < tile_last) { nxt = make_desc(tiles[t1], tiles[t1 + 1]); }
         if (lane == 0 && cur.n) { issue(cur, 0); }
         uint32_t phase = 0;                                  // bit b = parity the next fill of buffer b completes
-        for (uint32_t it = 0; t < tile_last; t += nwarps, ++it) {
+        for (uint32_t it = 0; t < tile_last; ++it) {
             const int b = it & 1;
-            const bool more = t + nwarps < tile_last;
+            const bool more = t1 < tile_last;
             if (lane == 0 && more && nxt.n) { issue(nxt, b ^ 1); }
             TileDesc nn = nxt;
-            if (t + 2 * nwarps < tile_last) { nn = make_desc(tiles[t + 2 * nwarps], tiles[t + 2 * nwarps + 1]); }
+            if (t2 < tile_last) { nn = make_desc(tiles[t2], tiles[t2 + 1]); }
             if (cur.n) {
                 mbar_wait(&bar[w][b], (phase >> b) & 1u); phase ^= 1u << b;
                 const OccEnt* es = e_s[w][b]; const uint32_t* os = o_s[w][b];
@@ -708,43 +723,54 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                 uint32_t* vf = vf_s[w]; uint32_t* work = work_s[w];
                 auto OFF = [&](uint32_t y) -> uint32_t { return (y - xa < noff) ? os[y - xa] : occ_off[y]; };
                 auto enqueue = [&](uint32_t sref, uint32_t dref, uint32_t x, uint32_t pass) {
-                    if (((delbits[dref >> 5] >> (dref & 31)) | (delbits[sref >> 5] >> (sref & 31))) & 1u) { return; }
                     const uint32_t q = atomicAdd(&q_n[w], 1u);
                     if (q < (uint32_t)WQ_CAP) { q_s[w][q] = sref; q_d[w][q] = dref; q_l[w][q] = (int32_t)((x << 1) | pass); }
                     else { verify(sref, dref, (int32_t)x, (int)pass); }
                 };
                 auto entry_form = [&]() {
-                    for (uint32_t p = lane; p < n; p += 32) {
-                        const OccEnt en = es[p];
-                        const uint32_t dx = en.szfl >> 24;
-                        uint32_t x = cur.x0 + dx;
-                        if (dx == 255u) {                            // far from the tile's first literal (runs of empty lists)
-                            uint32_t lo = x, hi = cur.xe;           // last x with off[x] <= s + p
-                            while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= s + p) { lo = mid; } else { hi = mid; } }
-                            x = lo;
+                    const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
+                    for (uint32_t base = 0; base < n; base += 32) {          // warp-uniform: the queue is drained in between
+                        const uint32_t p = base + lane;
+                        const bool act = p < n;
+                        OccEnt en; en.ref = 0; en.szfl = 0; en.sig = 0;
+                        uint32_t x = cur.x0;
+                        if (act) {
+                            en = es[p];
+                            const uint32_t dx = en.szfl >> 24;
+                            x = cur.x0 + dx;
+                            if (dx == 255u) {                            // far from the tile's first literal (runs of empty lists)
+                                uint32_t lo = x, hi = cur.xe;           // last x with off[x] <= s + p
+                                while (hi - lo > 1) { const uint32_t mid = lo + ((hi - lo) >> 1); if (occ_off[mid] <= s + p) { lo = mid; } else { hi = mid; } }
+                                x = lo;
+                            }
                         }
                         const uint32_t dref = en.ref & REF_MASK, esz = en.szfl & SIZE_MASK;
                         const unsigned long long dboth = var_fold(en.sig) * 3ull;     // both polarity bits of every variable of D
                         uint32_t cnt = 0;
-                        const int npass = KIND == CP3G_STRENGTHEN ? 2 : 1;
                         for (int pass = 0; pass < npass; ++pass) {
                             const uint32_t xx = pass == 0 ? x : (x ^ 1u);
-                            const uint32_t kb = OFF(xx), ke = OFF(xx + 1);
-                            for (uint32_t k = kb; k < ke; ++k) {
-                                const bool in = k - s < n;
-                                const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
-                                const uint32_t cls = a.x >> 30;
-                                if (KIND == CP3G_SUBSUME) { if (cls == CLS_NONE) { break; } if (cls & CLS_NOSUB) { continue; } }
-                                else { if (cls & CLS_NOSTR) { break; } }
-                                const uint32_t sref = a.x & REF_MASK;
-                                if (sref == dref) { continue; }
-                                cnt += 1;
-                                if (esz < (a.y & SIZE_MASK)) { continue; }
-                                const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
-                                const unsigned long long miss = ssig & ~en.sig;
-                                if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
-                                else { if ((ssig & ~dboth) || (miss & (miss - 1))) { continue; } }
-                                enqueue(sref, dref, x, (uint32_t)pass);
+                            uint32_t k = 0, ke = 0;
+                            if (act) { k = OFF(xx); ke = OFF(xx + 1); }
+                            while (__any_sync(0xffffffffu, k < ke)) {
+                                const uint32_t stop = min(ke, k + 16u);
+                                for (; k < stop; ++k) {
+                                    const bool in = k - s < n;
+                                    const uint2 a = in ? *reinterpret_cast<const uint2*>(&es[k - s]) : *reinterpret_cast<const uint2*>(&occ_ent[k]);
+                                    const uint32_t cls = a.x >> 30;
+                                    // the tagged classes are a prefix of the list
+                                    if (KIND == CP3G_SUBSUME) { if (cls == CLS_NONE) { k = ke; break; } if (cls & CLS_NOSUB) { continue; } }
+                                    else { if (cls & CLS_NOSTR) { k = ke; break; } }
+                                    const uint32_t sref = a.x & REF_MASK;
+                                    if (sref == dref) { continue; }
+                                    cnt += 1;
+                                    if (esz < (a.y & SIZE_MASK)) { continue; }
+                                    const unsigned long long ssig = in ? es[k - s].sig : occ_ent[k].sig;
+                                    const unsigned long long miss = ssig & ~en.sig;
+                                    if (KIND == CP3G_SUBSUME) { if (miss) { continue; } }
+                                    else { if ((ssig & ~dboth) || (miss & (miss - 1))) { continue; } }
+                                    enqueue(sref, dref, x, (uint32_t)pass);
+                                }
+                                drain(32u);
                             }
                         }
                         nchk += cnt; nbytes += (unsigned long long)cnt * (12 + 4 * esz);
@@ -754,6 +780,7 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                     const uint32_t xb = cur.x0 - xa;
                     uint32_t U = 0; bool fits = true;
                     // one lane per entry: a tagged entry S emits its units, every entry gets its 32-bit variable signature
+#pragma unroll 2
                     for (uint32_t base = 0; base < n; base += 32) {
                         const uint32_t p = base + lane;
                         uint32_t cnt = 0, kb = 0, len = 0, kb1 = 0, len1 = 0;
@@ -772,19 +799,21 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                                 }
                             }
                         }
-                        uint32_t inc = cnt;
-#pragma unroll
-                        for (int d = 1; d < 32; d <<= 1) { const uint32_t t2 = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= (uint32_t)d) { inc += t2; } }
-                        const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
-                        if (U + tot > WORK_CAP) { fits = false; break; }
-                        uint32_t o = U + inc - cnt;
-                        for (uint32_t c = 0; c < len; c += DCHUNK) { work[o++] = p | ((kb + c) << 8) | (min(DCHUNK, len - c) << 16); }
-                        if (KIND == CP3G_STRENGTHEN) {
-                            for (uint32_t c = 0; c < len1; c += DCHUNK) { work[o++] = p | ((kb1 + c) << 8) | (min(DCHUNK, len1 - c) << 16) | (1u << 20); }
+                        // the order of the units is irrelevant: every tagged lane reserves its slots with one shared-memory atomic
+                        if (cnt) {
+                            uint32_t o = atomicAdd(&u_n[w], cnt);
+                            if (o + cnt <= WORK_CAP) {
+                                for (uint32_t c = 0; c < len; c += DCHUNK) { work[o++] = p | ((kb + c) << 8) | (min(DCHUNK, len - c) << 16); }
+                                if (KIND == CP3G_STRENGTHEN) {
+                                    for (uint32_t c = 0; c < len1; c += DCHUNK) { work[o++] = p | ((kb1 + c) << 8) | (min(DCHUNK, len1 - c) << 16) | (1u << 20); }
+                                }
+                            }
                         }
-                        U += tot;
                     }
                     __syncwarp();
+                    U = u_n[w]; fits = U <= WORK_CAP;
+                    __syncwarp();
+                    if (lane == 0) { u_n[w] = 0; }
                     if (fits) {
                         for (uint32_t u = lane; u < U; u += 32) {
                             const uint32_t wk = work[u];
@@ -812,7 +841,9 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                                 enqueue(sref, dd.x & REF_MASK, cur.x0 + (dd.y >> 24), pass);     // pure tile: dx is exact
                             }
                         }
-                    } else { entry_form(); }
+                    } else {
+                        entry_form();
+                    }
                 } else {
                     // the list of the first entry (uniform over the warp); does it cover the whole tile?
                     const uint32_t dx0 = es[0].szfl >> 24;
@@ -840,24 +871,28 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                                 if (k < se) { if (k - s < n) { S = es[k - s]; } else { S = occ_ent[k]; } }
                                 const uint32_t cls = S.ref >> 30;
                                 const bool tagged = !(cls & (KIND == CP3G_SUBSUME ? CLS_NOSUB : CLS_NOSTR));
-                                if (tagged) {
-                                    const uint32_t sref = S.ref & REF_MASK, sn = S.szfl & SIZE_MASK;
-                                    const unsigned long long sf = var_fold(S.sig);
-                                    const uint32_t svf = (uint32_t)sf | ((uint32_t)(sf >> 32) << 1);
-                                    uint32_t c = 0; unsigned long long szsum = 0;
-                                    for (uint32_t d = 0; d < n; ++d) {
-                                        const uint2 dd = *reinterpret_cast<const uint2*>(&es[d]);
-                                        const uint32_t dref = dd.x & REF_MASK, esz = dd.y & SIZE_MASK;
-                                        const bool live = dref != sref;
-                                        c += live; szsum += live ? esz : 0u;
-                                        if (live && esz >= sn && (svf & ~vf[d]) == 0u) {
-                                            const unsigned long long miss = S.sig & ~es[d].sig;
-                                            if (KIND == CP3G_SUBSUME ? miss != 0 : (miss & (miss - 1)) != 0) { continue; }
-                                            enqueue(sref, dref, y, (uint32_t)pass);
+                                const uint32_t sref = S.ref & REF_MASK, sn = S.szfl & SIZE_MASK;
+                                const unsigned long long sf = var_fold(S.sig);
+                                const uint32_t svf = (uint32_t)sf | ((uint32_t)(sf >> 32) << 1);
+                                uint32_t c = 0; unsigned long long szsum = 0;
+                                for (uint32_t db = 0; db < n; db += 16) {             // 16 candidates, then the queue is looked at
+                                    if (tagged) {
+                                        const uint32_t de = min(db + 16u, n);
+                                        for (uint32_t d = db; d < de; ++d) {
+                                            const uint2 dd = *reinterpret_cast<const uint2*>(&es[d]);
+                                            const uint32_t dref = dd.x & REF_MASK, esz = dd.y & SIZE_MASK;
+                                            const bool live = dref != sref;
+                                            c += live; szsum += live ? esz : 0u;
+                                            if (live && esz >= sn && (svf & ~vf[d]) == 0u) {
+                                                const unsigned long long miss = S.sig & ~es[d].sig;
+                                                if (KIND == CP3G_SUBSUME ? miss != 0 : (miss & (miss - 1)) != 0) { continue; }
+                                                enqueue(sref, dref, y, (uint32_t)pass);
+                                            }
                                         }
                                     }
-                                    nchk += c; nbytes += 12ull * c + 4ull * szsum;
+                                    drain(32u);
                                 }
+                                nchk += c; nbytes += 12ull * c + 4ull * szsum;
                                 // the tagged classes are a prefix (strengtheners) resp. everything below class 3 (subsumers)
                                 const bool more_s = KIND == CP3G_STRENGTHEN ? tagged : (cls != CLS_NONE);
                                 if (!__any_sync(0xffffffffu, more_s)) { break; }
@@ -867,15 +902,8 @@ __global__ void __launch_bounds__(FQ_WARPS * 32, CP3_MINBLOCKS) k_full(const Cla
                 }
             }
             __syncwarp();                                  // all reads of buffer b are done before it is refilled
-            const uint32_t qn = min(q_n[w], (uint32_t)WQ_CAP);
-            if (qn >= 16u || !more) {                      // verify when the queue is worth a full warp pass
-                for (uint32_t k = lane; k < qn; k += 32) { verify(q_s[w][k], q_d[w][k], q_l[w][k] >> 1, q_l[w][k] & 1); }
-                __syncwarp();
-                if (lane == 0) { q_n[w] = 0; }
-                __syncwarp();
-                if (h_n[w] >= (uint32_t)(WH_CAP / 2)) { flush_hits(); }
-            }
-            cur = nxt; nxt = nn;
+            drain(more ? 16u : 1u);                        // verify when the queue is worth a warp pass
+            cur = nxt; nxt = nn; t = t1; t1 = t2; t2 += nwarps;
         }
     }
     flush_hits();
@@ -962,19 +990,10 @@ __global__ void k_bve_resolve(const ClauseHdr* __restrict__ hdr, const int32_t* 
 }
 
 // ------------------------------------------------------------------------------------------ edits
-__global__ void k_set_deleted(ClauseHdr* __restrict__ hdr, uint32_t* __restrict__ delbits, const uint32_t* __restrict__ ids, uint32_t n)
+__global__ void k_set_deleted(ClauseHdr* __restrict__ hdr, const uint32_t* __restrict__ ids, uint32_t n)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { const uint32_t c = ids[i]; hdr[c].szfl |= FLAG_DEL; atomicOr(&delbits[c >> 5], 1u << (c & 31)); }
-}
-// deleted flags as a bitmap (ncl/8 bytes: L2 resident) so the bulk kernels need no header gather for them
-__global__ void k_init_delbits(const ClauseHdr* __restrict__ hdr, uint32_t* __restrict__ delbits, uint32_t first_word, uint32_t ncl)
-{
-    const uint32_t w = first_word + blockIdx.x * blockDim.x + threadIdx.x;
-    if (w * 32 >= ncl) { return; }
-    uint32_t bits = 0;
-    for (uint32_t k = 0; k < 32 && w * 32 + k < ncl; ++k) { if (hdr[w * 32 + k].szfl & FLAG_DEL) { bits |= 1u << k; } }
-    delbits[w] = bits;
+    if (i < n) { hdr[ids[i]].szfl |= FLAG_DEL; }
 }
 // host clause records are {start:u32, size:24|flags:8, x, y}; flag bit 0 = deleted
 __global__ void k_make_hdr(const uint4* __restrict__ rec, ClauseHdr* __restrict__ hdr, uint32_t n)
@@ -1180,7 +1199,7 @@ int dev_host_order_lists(cp3g* g)
 int dev_set_deleted(cp3g* g, const uint32_t* dev_ids, uint32_t n)
 {
     if (!n) { return CP3G_OK; }
-    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, dev_ids, n);
+    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, dev_ids, n);
     g->launches++;
     return CP3G_OK;
 }
@@ -1222,7 +1241,7 @@ void cp3g_destroy(cp3g* g)
     cudaSetDevice(g->device);
     cudaStreamSynchronize(g->stream);
     g->lits.release(g->stream); g->lits2.release(g->stream); g->hdr.release(g->stream); g->occ_off.release(g->stream); g->occ_tmp.release(g->stream); g->occ_rank.release(g->stream); g->srt_v.release(g->stream); g->srt_k2.release(g->stream); g->srt_v2.release(g->stream); g->tile_sum.release(g->stream);
-    g->long_lits.release(g->stream); g->ovf.release(g->stream); g->scratch_u32.release(g->stream); g->occ_ent.release(g->stream); g->tiles.release(g->stream); g->delbits.release(g->stream); g->refs_tmp.release(g->stream);
+    g->long_lits.release(g->stream); g->ovf.release(g->stream); g->scratch_u32.release(g->stream); g->occ_ent.release(g->stream); g->tiles.release(g->stream); g->refs_tmp.release(g->stream);
     g->sort_tmp.release(g->stream); g->req_self.release(g->stream); g->req_off.release(g->stream); g->req_lits.release(g->stream); g->hits.release(g->stream); g->counters.release(g->stream);
     g->bu0.release(g->stream); g->bu1.release(g->stream); g->bu2.release(g->stream); g->bu3.release(g->stream); g->bu4.release(g->stream); g->bq0.release(g->stream);
     g->bs0.release(g->stream); g->bl0.release(g->stream);
@@ -1255,22 +1274,16 @@ int cp3g_upload(cp3g* g, uint32_t nvars, uint32_t ncl, const int32_t* lits, size
         h[i].sig = 0;
     }
     CK(cudaMemcpyAsync(g->hdr.p, h.data(), (size_t)ncl * sizeof(ClauseHdr), cudaMemcpyHostToDevice, g->stream));
-    RESERVE(g->delbits, ((size_t)ncl + ncl / 4 + 1024) / 32 + 2, false);
-    CK(cudaMemsetAsync(g->delbits.p, 0, g->delbits.cap * sizeof(uint32_t), g->stream));
-    if (ncl) { k_init_delbits<<<grid_for((ncl + 31) / 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, 0, ncl); g->launches++; }
     CK(cudaStreamSynchronize(g->stream));
-    g->lits.used = nlits; g->hdr.used = ncl; g->delbits.used = g->delbits.cap;
+    g->lits.used = nlits; g->hdr.used = ncl;
     g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * sizeof(ClauseHdr));
     return CP3G_OK;
 }
 
 static int finish_upload(cp3g* g, uint32_t ncl, size_t nlits)
 {
-    RESERVE(g->delbits, ((size_t)ncl + ncl / 4 + 1024) / 32 + 2, false);
-    CK(cudaMemsetAsync(g->delbits.p, 0, g->delbits.cap * sizeof(uint32_t), g->stream));
-    if (ncl) { k_init_delbits<<<grid_for((ncl + 31) / 32, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, 0, ncl); g->launches++; }
     CK(cudaStreamSynchronize(g->stream));
-    g->lits.used = nlits; g->hdr.used = ncl; g->delbits.used = g->delbits.cap;
+    g->lits.used = nlits; g->hdr.used = ncl;
     return CP3G_OK;
 }
 
@@ -1413,7 +1426,7 @@ int cp3g_set_deleted(cp3g* g, uint32_t n, const uint32_t* ids)
     cudaSetDevice(g->device);
     RESERVE(g->scratch_u32, n, false);
     CK(cudaMemcpyAsync(g->scratch_u32.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, g->stream));
-    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->delbits.p, g->scratch_u32.p, n);
+    k_set_deleted<<<grid_for(n, 256), 256, 0, g->stream>>>(g->hdr.p, g->scratch_u32.p, n);
     g->launches++; g->h2d += (int64_t)n * 4;        // stream ordered: the next scan on this stream sees it
     return CP3G_OK;
 }
@@ -1442,12 +1455,6 @@ int cp3g_append(cp3g* g, uint32_t n, const uint32_t* size, const int32_t* lits, 
     cudaSetDevice(g->device);
     RESERVE(g->lits, g->nlits + nlits, true);
     RESERVE(g->hdr, (size_t)g->ncl + n, true);
-    if (((size_t)g->ncl + n) / 32 + 2 > g->delbits.cap) {
-        const size_t oldcap = g->delbits.cap;
-        RESERVE(g->delbits, ((size_t)g->ncl + n) / 32 + 2, true);
-        CK(cudaMemsetAsync(g->delbits.p + oldcap, 0, (g->delbits.cap - oldcap) * sizeof(uint32_t), g->stream));
-        g->delbits.used = g->delbits.cap;
-    }
     std::vector<ClauseHdr> h(n);
     size_t pos = g->nlits, src = 0;
     for (uint32_t i = 0; i < n; ++i) {
@@ -1596,10 +1603,10 @@ int cp3g_scan_all(cp3g* g, int kind, cp3g_hit* out, uint32_t cap, uint32_t* nout
         const unsigned blocks = std::min<unsigned>(grid_for(te - tb, FQ_WARPS), (unsigned)g->num_sms * per_sm);
         if (kind == CP3G_SUBSUME) {
             k_full<CP3G_SUBSUME><<<blocks, FQ_WARPS * 32, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->tiles.p,
-                g->delbits.p, tb, te, g->hits.p, cap, g->counters.p, dchecks);
+                tb, te, g->hits.p, cap, g->counters.p, dchecks);
         } else {
             k_full<CP3G_STRENGTHEN><<<blocks, FQ_WARPS * 32, 0, g->stream>>>(g->hdr.p, g->lits.p, g->occ_off.p, g->occ_ent.p, g->tiles.p,
-                g->delbits.p, tb, te, g->hits.p, cap, g->counters.p, dchecks);
+                tb, te, g->hits.p, cap, g->counters.p, dchecks);
         }
         g->launches++;
     }

@@ -47,7 +47,7 @@ struct cp3g {
     size_t nlits = 0;
     DevBuf<int32_t> lits, lits2; DevBuf<ClauseHdr> hdr;
     DevBuf<uint32_t> occ_off, occ_tmp, occ_rank, srt_v, srt_k2, srt_v2, tile_sum, long_lits, ovf, scratch_u32;
-    DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> delbits, refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
+    DevBuf<OccEnt> occ_ent; DevBuf<uint2> tiles; DevBuf<uint32_t> refs_tmp; uint32_t ntiles = 0; bool dirty_since_build = true;
     DevBuf<uint32_t> req_self, req_off; DevBuf<int32_t> req_lits;
     DevBuf<unsigned char> sort_tmp;
     DevBuf<cp3g_hit> hits; DevBuf<uint32_t> counters; // [0]=nout [1]=nlong [2]=total ; checks at +4 (u64)

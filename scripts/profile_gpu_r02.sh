@@ -11,6 +11,7 @@ echo "launch list rc=$?"
 ARGS2="--steps 1 --warmup 0 --no-cpu-baseline --no-c3"
 python bench.py $ARGS2 > gpurun_out/r02_plain_bench2.log 2>&1 && {
 ncu --set full --clock-control none --import-source on -k regex:k_full -c 2 -f -o gpurun_out/r02_prof_full python bench.py $ARGS2 > gpurun_out/r02_ncu_full.log 2>&1; echo "k_full rc=$?"
+[ -n "${PROF_ONLY_FULL:-}" ] && exit 0      # re-capture of the headline kernel only
 ncu --set full --clock-control none --import-source on -k regex:"k_occ_|k_tiles" -c 6 -f -o gpurun_out/r02_prof_k2 python bench.py $ARGS2 > gpurun_out/r02_ncu_k2.log 2>&1; echo "k2 rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"k_sp_|k_str_static" -c 16 -f -o gpurun_out/r02_prof_commit python bench.py $ARGS2 > gpurun_out/r02_ncu_commit.log 2>&1; echo "commit rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"k_ing_" -c 6 -f -o gpurun_out/r02_prof_ingest python bench.py $ARGS2 > gpurun_out/r02_ncu_ingest.log 2>&1; echo "ingest rc=$?"

@@ -1,0 +1,12 @@
+"""A/B of k_full build variants (riss-solver_b200/csrc/_obj/var/lib_<name>.so): K3/K4 launch times at C2 and a C3-shaped point."""
+import os, subprocess, sys
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+names = sys.argv[1:]
+for nm in names:
+    lib, _, blocks = nm.partition("@")
+    env = dict(os.environ, CP3B200_LIB=os.path.join(root, "riss-solver_b200", "csrc", "_obj", "var", f"lib_{lib}.so"))
+    if blocks:
+        env["CP3_FQ_BLOCKS"] = blocks
+    for cmd in (["scripts/bench_kernels.py", "1000000", "4"], ["scripts/c3_kernels.py", "3000000"], ["scripts/bench_kernels.py", "1000000", "2", "1.0"], ["scripts/bench_kernels.py", "1000000", "2", "1.2"]):
+        r = subprocess.run([sys.executable] + cmd, cwd=root, env=env, capture_output=True, text=True, timeout=900)
+        print(f"== {nm} {' '.join(cmd)}\n" + "\n".join(r.stdout.strip().splitlines()[-2:]) + ("\n" + r.stderr[-400:] if r.returncode else ""), flush=True)
