@@ -7,8 +7,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from bench import Config, to_codes_sorted
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
-zipf_s = float(sys.argv[3]) if len(sys.argv) > 3 else 0.0
-lits, sizes, stream = (Config("zipf", n).generate(zipf_s=zipf_s) if zipf_s else Config("c2", n).generate())
+# a third argument selects the Zipf sweep formula (BASELINE configs[4]) with that skew exponent, 0 included
+lits, sizes, stream = (Config("zipf", n).generate(zipf_s=float(sys.argv[3])) if len(sys.argv) > 3 else Config("c2", n).generate())
 codes = to_codes_sorted(lits, sizes)
 svc = rs.ScanService(0)
 svc.upload(int(np.abs(lits).max()), codes, sizes)
