@@ -55,24 +55,28 @@ __global__ void k_sp_diff(const cp3g_hit* __restrict__ h, uint32_t n, const int3
 __global__ void k_sp_dead(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, const int32_t* __restrict__ dtime, uint32_t ncl,
                           uint32_t* __restrict__ dead, uint32_t* __restrict__ ndead, unsigned long long* __restrict__ nlits, uint32_t* __restrict__ dl_cnt)
 {
-    // the two global counters are same-address atomics (~1.4 ns each: 0.39 ms for the 2.8*10^5 subsumed clauses of C2): one per
-    // warp instead - ballot for the slots, shuffle reduction for the literal total
+    // the two global counters are same-address atomics (~1.2 ns each): one pair per block - ballot + shared-memory atomics for the
+    // slots inside the block, shuffle reduction for the literal total (one pair per warp still cost 0.3 ms at C2)
+    __shared__ uint32_t s_cnt, s_base; __shared__ unsigned long long s_tot;
+    if (threadIdx.x == 0) { s_cnt = 0; s_tot = 0; }
+    __syncthreads();
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     const bool is_dead = c < ncl && dtime[c] != T_INF;
     const unsigned m = __ballot_sync(0xffffffffu, is_dead);
-    if (m == 0) { return; }
     const unsigned lane = threadIdx.x & 31;
     uint32_t sz = 0; ClauseHdr h{};
     if (is_dead) { h = hdr[c]; sz = h.szfl & SIZE_MASK; }
     uint32_t tot = sz;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) { tot += __shfl_xor_sync(0xffffffffu, tot, d); }
-    uint32_t base = 0;
-    const int leader = __ffs(m) - 1;
-    if ((int)lane == leader) { base = atomicAdd(ndead, (uint32_t)__popc(m)); atomicAdd(nlits, (unsigned long long)tot); }
-    base = __shfl_sync(0xffffffffu, base, leader);
+    uint32_t wbase = 0;
+    if (lane == 0 && m) { wbase = atomicAdd(&s_cnt, (uint32_t)__popc(m)); atomicAdd(&s_tot, (unsigned long long)tot); }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) { s_base = atomicAdd(ndead, s_cnt); atomicAdd(nlits, s_tot); }
+    __syncthreads();
     if (!is_dead) { return; }
-    dead[base + __popc(m & ((1u << lane) - 1u))] = c;
+    dead[s_base + wbase + __popc(m & ((1u << lane) - 1u))] = c;
     for (uint32_t k = 0; k < sz; ++k) { atomicAdd(&dl_cnt[lits[h.start + k]], 1u); }
 }
 __global__ void k_sp_dlfill(const ClauseHdr* __restrict__ hdr, const int32_t* __restrict__ lits, const int32_t* __restrict__ dtime,
@@ -355,8 +359,8 @@ int cp3g_sub_pass_fetch(cp3g* g, uint32_t* dead, uint32_t* list_n, uint32_t* lis
     if (dead && g->sp_ndead) { CK(cudaMemcpyAsync(dead, g->sp_dead.p, (size_t)g->sp_ndead * 4, cudaMemcpyDeviceToHost, g->stream)); g->d2h += (int64_t)g->sp_ndead * 4; }
     if (list_n) { CK(cudaMemcpyAsync(list_n, g->sp_n.p, (size_t)nlit * 4, cudaMemcpyDeviceToHost, g->stream)); g->d2h += (int64_t)nlit * 4; }
     if (list_stale) { CK(cudaMemcpyAsync(list_stale, g->sp_stale.p, (size_t)nlit * 4, cudaMemcpyDeviceToHost, g->stream)); g->d2h += (int64_t)nlit * 4; }
-    if (refs && g->total_occ) { CK(cudaMemcpyAsync(refs, g->sp_refs.p, (size_t)g->total_occ * 4, cudaMemcpyDeviceToHost, g->stream)); g->d2h += (int64_t)g->total_occ * 4; }
     CK(cudaStreamSynchronize(g->stream));
+    if (refs && g->total_occ) { int r = d2h_staged(g, refs, g->sp_refs.p, (size_t)g->total_occ * 4); if (r != CP3G_OK) { return r; } g->d2h += (int64_t)g->total_occ * 4; }
     return CP3G_OK;
 }
 

@@ -1412,8 +1412,8 @@ int cp3g_download_occ(cp3g* g, uint32_t* off, uint32_t* refs)
     if (refs && g->total_occ) {
         int r = dev_host_order_lists(g);
         if (r != CP3G_OK) { return r; }
-        CK(cudaMemcpyAsync(refs, g->refs_tmp.p, (size_t)g->total_occ * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->stream));
-        CK(cudaStreamSynchronize(g->stream));
+        r = d2h_staged(g, refs, g->refs_tmp.p, (size_t)g->total_occ * sizeof(uint32_t));
+        if (r != CP3G_OK) { return r; }
         g->d2h += (int64_t)g->total_occ * 4;
     }
     return CP3G_OK;
@@ -1847,10 +1847,9 @@ int cp3g_download_arena(cp3g* g, int32_t* lits, void* records16)
         RESERVE(g->refs_tmp, (size_t)g->ncl * 4 + 4, false);     // staging for the 16-byte records (a build-time temporary)
         k_arena_records<<<grid_for(g->ncl, 256), 256, 0, g->stream>>>(g->hdr.p, g->ncl, reinterpret_cast<uint4*>(g->refs_tmp.p));
         g->launches++;
-        CK(cudaMemcpyAsync(records16, g->refs_tmp.p, (size_t)g->ncl * 16, cudaMemcpyDeviceToHost, g->stream));
+        { int r = d2h_staged(g, records16, g->refs_tmp.p, (size_t)g->ncl * 16); if (r != CP3G_OK) { return r; } }
     }
-    if (g->nlits) { CK(cudaMemcpyAsync(lits, g->lits.p, g->nlits * sizeof(int32_t), cudaMemcpyDeviceToHost, g->stream)); }
-    CK(cudaStreamSynchronize(g->stream));
+    if (g->nlits) { int r = d2h_staged(g, lits, g->lits.p, g->nlits * sizeof(int32_t)); if (r != CP3G_OK) { return r; } }
     g->d2h += (int64_t)g->nlits * 4 + (int64_t)g->ncl * 16;
     return CP3G_OK;
 }
