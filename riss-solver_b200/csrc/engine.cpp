@@ -2,6 +2,7 @@
 // CoprocessorData bookkeeping, unit propagation, Dense and the preprocess() driver.  The techniques live in engine_sub.cpp
 // (subsumption), engine_str.cpp (strengthening), engine_bve.cpp (BVE), engine_bce.cpp (BCE).  Reference lines are cited per function.
 #include "engine_util.h"
+#include <atomic>
 #include <sys/mman.h>
 #include <condition_variable>
 #include <mutex>
@@ -83,12 +84,26 @@ void* hugeAlloc(size_t bytes)
     return p;
 }
 
+// strictly increasing (sorted, no duplicates): the identity queue of a first pass, checked on all cores
+bool Engine::isIncreasing(const uint32_t* v, size_t n)
+{
+    if (n < std::max<size_t>(tune.par_min, 2) || nthreads < 2) {
+        for (size_t i = 1; i < n; ++i) { if (!(v[i - 1] < v[i])) { return false; } }
+        return true;
+    }
+    std::atomic<bool> inc{true};
+    parallelFor(n, [&](size_t b, size_t e, int) {
+        bool g = true;
+        for (size_t i = std::max<size_t>(b, 1); i < e && g; ++i) { g = v[i - 1] < v[i]; }
+        if (!g) { inc.store(false, std::memory_order_relaxed); }
+    }, 65536);
+    return inc.load();
+}
+
 void Engine::sortUniqueIds(std::vector<uint32_t>& ids)
 {
     if (ids.size() < std::max<size_t>(tune.par_min, 2) || nthreads < 2) { sortUnique(ids); return; }
-    bool inc = true;
-    for (size_t i = 1; i < ids.size() && inc; ++i) { inc = ids[i - 1] < ids[i]; }
-    if (inc) { return; }
+    if (isIncreasing(ids)) { return; }
     // mark, count per chunk of words, extract in order
     const size_t words = (C.size() + 63) / 64;
     std::vector<uint64_t> bm(words, 0ull);
@@ -436,7 +451,7 @@ void Engine::flushDevice()
 void Engine::scanClauses(int kind, const std::vector<uint32_t>& ids, ScanCache& cache, int forceBulk)
 {
     if (ids.empty()) { return; }
-    DbgLap lap(kind == CP3G_SUBSUME ? "scanClauses<sub>" : "scanClauses<str>");
+    DbgLap lap(kind == CP3G_SUBSUME ? "scanClauses<sub>" : "scanClauses<str>", tune.debug_par);
     if (!scan_no_flush) { flushDevice(); }
     lap("flush");
     ++scan_id; ++n_scan_batches;
@@ -651,7 +666,7 @@ void Engine::prefetchStrengthenClosure()
     std::vector<HashSet> requested((size_t)W);
     std::vector<std::vector<Ev>> evs((size_t)W);                 // per worker: predicted removals of its clauses, sorted by (clause, time)
     size_t first_ent = 0;
-    DbgLap lap("closure");
+    DbgLap lap("closure", tune.debug_par);
     // Speculation is only worth its scans while they are cheap next to the full-queue pass: a request costs the
     // length of its shortest list pair (long on skewed inputs), and after a unit shows up most predictions are void.
     // Budget: four times the occurrence count of the data base; what is not prefetched is scanned on demand.
@@ -953,11 +968,10 @@ void Engine::extClause(uint32_t c, int x)
 }
 void Engine::extLit(int x) { undo.push_back(0); undo.push_back(toDimacs(x)); }
 
-void Engine::filterDeleted(std::vector<uint32_t>& a)
+size_t Engine::filterDeletedRange(uint32_t* a, size_t n)
 {
-    if (a.size() >= std::max<size_t>(4 * tune.par_min, 2) && nthreads > 1) {
+    if (n >= std::max<size_t>(4 * tune.par_min, 2) && nthreads > 1) {
         // in place: every chunk compacts itself on its own core, then the chunks are moved down in order (no second array to fault in)
-        const size_t n = a.size();
         const int T = nthreads; const size_t per = (n + (size_t)T - 1) / (size_t)T;
         std::vector<size_t> kept((size_t)T, 0);
         parallelFor((size_t)T, [&](size_t tb, size_t te, int) {
@@ -968,13 +982,12 @@ void Engine::filterDeleted(std::vector<uint32_t>& a)
             }
         }, 1);
         size_t o = 0;
-        for (int t = 0; t < T; ++t) { const size_t b = per * (size_t)t; if (b >= n) { break; } if (o != b && kept[(size_t)t]) { memmove(a.data() + o, a.data() + b, sizeof(uint32_t) * kept[(size_t)t]); } o += kept[(size_t)t]; }
-        a.resize(o);
-        return;
+        for (int t = 0; t < T; ++t) { const size_t b = per * (size_t)t; if (b >= n) { break; } if (o != b && kept[(size_t)t]) { memmove(a + o, a + b, sizeof(uint32_t) * kept[(size_t)t]); } o += kept[(size_t)t]; }
+        return o;
     }
     size_t j = 0;
-    for (size_t i = 0; i < a.size(); ++i) { if (!(C[a[i]].flag & F_DEL)) { a[j++] = a[i]; } }
-    a.resize(j);
+    for (size_t i = 0; i < n; ++i) { if (!(C[a[i]].flag & F_DEL)) { a[j++] = a[i]; } }
+    return j;
 }
 // garbageCollect / relocAll, CoprocessorTypes.h:1396-1550 (stable removal of deleted clauses everywhere)
 void Engine::checkGarbage()

@@ -172,7 +172,7 @@ private:
     inline void staleDec(int x) { if (stale[x] > 0 && --stale[x] == 0) { stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); } }
     inline void staleClear(int x) { stale[x] = 0; stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); }
     int numberOfCls = 0;
-    std::vector<uint32_t> subq, strq; std::vector<int32_t> undo;
+    RawVec<uint32_t> subq, strq; std::vector<int32_t> undo;      // (no zero fill when initData sizes the queues)
     HVec<uint32_t> modTimer; uint32_t modStep = 0;
     std::vector<uint32_t> ma; uint32_t ma_step = 0;
 
@@ -260,8 +260,10 @@ private:
     template <class V, class T> void pfill(V& v, size_t n, T val) { v.resize(n); parallelFor(n, [&](size_t b, size_t e, int) { std::fill(v.begin() + (std::ptrdiff_t)b, v.begin() + (std::ptrdiff_t)e, val); }); }
     // grow a work array to n elements, new elements = val (existing ones are kept)
     template <class V, class T> void pgrow(V& v, size_t n, T val) { const size_t o = v.size(); if (n <= o) { return; } v.resize(n); parallelFor(n - o, [&](size_t b, size_t e, int) { std::fill(v.begin() + (std::ptrdiff_t)(o + b), v.begin() + (std::ptrdiff_t)(o + e), val); }); }
-    template <class P> void parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred);
+    template <class V, class P> void parallelFilter(const V& src, std::vector<uint32_t>& out, P pred);
     void sortUniqueIds(std::vector<uint32_t>& ids);      // sort + unique of a clause id list; long lists through a bitmap on all cores
+    bool isIncreasing(const uint32_t* v, size_t n);
+    template <class V> bool isIncreasing(const V& v) { return isIncreasing(v.data(), v.size()); }
     ScanCache c_sub, c_str;
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
@@ -330,7 +332,8 @@ private:
     void addSubStrength(uint32_t c);
     void extClause(uint32_t c, int x);
     void extLit(int x);
-    void filterDeleted(std::vector<uint32_t>& a);
+    size_t filterDeletedRange(uint32_t* a, size_t n);
+    template <class V> void filterDeleted(V& a) { a.resize(filterDeletedRange(a.data(), a.size())); }
     void checkGarbage();
     void removePosSorted(uint32_t c, int pos);
     void removePosUnsorted(uint32_t c, int pos);
@@ -401,7 +404,7 @@ private:
     void strengthenHit(std::vector<uint32_t>& localQueue, uint32_t other, int pos);
     void updateOccurrences(bool useHeap, int ignore);
     bool subsumptionProcess(bool doStrengthen, bool useHeap, int ignore);
-    void clearQueue(std::vector<uint32_t>& q, uint8_t flag);
+    void clearQueue(RawVec<uint32_t>& q, uint8_t flag);
     bool findGates(int v, int& p_limit, int& n_limit);
     int anticipate(int v, int p_limit, int n_limit, int& lit_clauses, int& resolvents);
     void bveRemoveClauses(int x, int extLitOrNeg);

@@ -162,7 +162,7 @@ void Engine::unpredictedEdit(uint32_t c)
 // K4 over the strengthening queue + speculative closure (first half of a strengthening pass)
 void Engine::prepareStrengthening(const std::vector<uint32_t>& ids, bool bulk)
 {
-    DbgLap lap("prepStr");
+    DbgLap lap("prepStr", tune.debug_par);
     c_str.clear();
     lap("clear");
     scanClauses(CP3G_STRENGTHEN, ids, c_str, scan_no_flush ? (bulk ? 1 : 0) : -1);
@@ -190,19 +190,19 @@ int Engine::strengtheningWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_str);
     const bool unlimited = !opt.limited;
+    DbgLap lap("str", tune.debug_par);
     ensureHostLists();
     logClear(); dirty_str.clear();
+    lap("host lists");
     if (str_prepared) { str_prepared = false; }            // scan + closure were done while the subsumption commit ran
     else if (opt.strength) {
         std::vector<uint32_t> ids;
-        for (uint32_t c : strq) {
-            if ((C[c].flag & F_DEL) || !(C[c].flag & F_STR) || C[c].size < 2) { continue; }
-            ids.push_back(c);
-        }
+        parallelFilter(strq, ids, [&](uint32_t c) { return !(C[c].flag & F_DEL) && (C[c].flag & F_STR) && C[c].size >= 2; });
         sortUniqueIds(ids);
+        lap("ids");
         prepareStrengthening(ids, false);
     } else { c_str.clear(); }
-    DbgLap lap("str"); lap("prepare");
+    lap("prepare");
     // first pass behind a device-committed subsumption pass: the static plan comes from the device (K10), the real entries are
     // committed by component; false = nothing was touched, the host plan below takes the pass
     bool fast_done = false;
@@ -744,17 +744,22 @@ bool Engine::subsumptionProcess(bool doStrengthen, bool useHeap, int ignore)
     //  verified against the compiled reference with all limits set to 10.  The options are accepted and have no effect.)
     if (!(sub_steps + opt.call_inc < sub_lim)) { sub_lim += opt.call_inc; limitIncreases++; }
     if (!(str_steps + opt.call_inc < str_lim)) { str_lim += opt.call_inc; limitIncreases++; }
+    DbgLap lap("susi", tune.debug_par);
     while (ok && (!subq.empty() || !strq.empty())) {
         if (!subq.empty()) {
             overlap_str = doStrengthen && !strq.empty();
             subsumptionWorker(useHeap, ignore);
             overlap_str = false;
+            lap("subsumption worker");
             clearQueue(subq, F_SUB);
+            lap("clear queue");
         }
         if (!strq.empty()) {
             if (!doStrengthen) { clearQueue(strq, F_STR); continue; }
             if (opt.naive_strength) { naiveStrengthening(useHeap, ignore); } else { strengtheningWorker(useHeap, ignore); }
+            lap("strengthening worker");
             clearQueue(strq, F_STR);
+            lap("clear queue");
         }
         str_prepared = false;
     }

@@ -4,10 +4,14 @@
 namespace cp3 {
 
 // ------------------------------------------------------------------------------------------------ Subsumption
-void Engine::clearQueue(std::vector<uint32_t>& q, uint8_t flag)
+void Engine::clearQueue(RawVec<uint32_t>& q, uint8_t flag)
 {
-    // (a clause is queued once per pass, so the chunks of a long queue write disjoint records)
-    if (q.size() >= 65536 && nthreads > 1) { parallelFor(q.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { __atomic_fetch_and((uint32_t*)&C[q[i]] + 1, ~((uint32_t)flag << 24), __ATOMIC_RELAXED); } }); }
+    // a queue in clause order (first pass) names every record once: plain stores, chunk by chunk; otherwise a clause may be queued
+    // twice and two chunks may meet in one record
+    if (q.size() >= 65536 && nthreads > 1) {
+        if (isIncreasing(q)) { parallelFor(q.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { C[q[i]].flag &= ~flag; } }); }
+        else { parallelFor(q.size(), [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { __atomic_fetch_and((uint32_t*)&C[q[i]] + 1, ~((uint32_t)flag << 24), __ATOMIC_RELAXED); } }); }
+    }
     else { for (uint32_t c : q) { C[c].flag &= ~flag; } }
     q.clear();
 }
@@ -125,7 +129,7 @@ bool Engine::subsumptionCommitParallel()
         }
     }, 1);
     // 2-byte copy of the counters as of the pass start (cache resident); out-of-range values read the original
-    std::vector<int16_t> cnt16(nlit);
+    RawVec<int16_t> cnt16; cnt16.resize(nlit);                  // filled right below, on all cores
     parallelFor(nlit, [&](size_t b, size_t e, int) {
         for (size_t x = b; x < e; ++x) { const int32_t c = hot[x].cnt; cnt16[x] = (c > 32000 || c < -32000) ? INT16_MIN : (int16_t)c; }
     });
@@ -268,7 +272,7 @@ bool Engine::subsumptionCommitDevice()
         if (!good) { ok_q = false; }
     });
     if (!ok_q) { return false; }
-    DbgLap lap("devsub");
+    DbgLap lap("devsub", tune.debug_par);
     int status = 1; uint32_t ndead = 0; uint64_t nlits = 0, steps = 0, checks = 0;
     int64_t t0 = now_ns();
     if (cp3g_sub_pass(gpu, max_list, &status, &ndead, &nlits, &steps, &checks) != CP3G_OK) { die("device subsumption pass failed"); }
@@ -306,8 +310,7 @@ bool Engine::subsumptionCommitDevice()
     if (ndead) { successful(t_sub); }
     sub_steps += (int64_t)steps;
     dev_static_ok = true;                              // the device holds the post-pass tables: K10 can plan the strengthening pass
-    parallelFor(nq, [&](size_t b, size_t e, int) { for (size_t p = b; p < e; ++p) { C[subq[p]].flag &= ~F_SUB; } });
-    lap("bookkeeping");
+    lap("bookkeeping");                                // (the queue flags are cleared by the caller's clearQueue)
     return true;
 }
 
@@ -317,7 +320,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
 {
     PhaseTimer pt(ph_sub);
     const bool unlimited = !opt.limited;
-    DbgLap lap0("sub"); 
+    DbgLap lap0("sub", tune.debug_par);
     c_sub.clear(); logClear();
     lap0("clear");
     if (lists_on_device) {
@@ -346,7 +349,7 @@ void Engine::subsumptionWorker(bool useHeap, int ignore)
         lap0("ids");
         scanClauses(CP3G_SUBSUME, ids, c_sub);
     }
-    DbgLap lap("sub"); lap("start(after scan)");
+    DbgLap lap("sub", tune.debug_par); lap("start(after scan)");
     int64_t t0 = now_ns();
     const size_t parsub_min = tune.parsub_min;
     if (!useHeap && subq.size() >= parsub_min) {

@@ -41,6 +41,7 @@ static inline void sortHits(std::vector<cp3g_hit>& h, uint32_t n)
 struct DbgLap {
     bool on; int64_t t; const char* who;
     explicit DbgLap(const char* w) : on(getenv("CP3_DEBUG_PAR") != nullptr), t(on ? now_ns() : 0), who(w) {}
+    DbgLap(const char* w, bool enabled) : on(enabled), t(on ? now_ns() : 0), who(w) {}      // per-variable callers: no getenv
     void operator()(const char* what) { if (on) { int64_t n2 = now_ns(); fprintf(stderr, "  %s %s %.1f ms\n", who, what, (n2 - t) / 1e6); t = n2; } }
 };
 
@@ -73,7 +74,7 @@ template <class F> void Engine::parallelFor(size_t n, F f, size_t grain)
     poolRun(tasks, [&](int t) { const size_t b = per * (size_t)t, e = std::min(n, per * ((size_t)t + 1)); f(b, e, t); });
 }
 
-template <class P> void Engine::parallelFilter(const std::vector<uint32_t>& src, std::vector<uint32_t>& out, P pred)
+template <class V, class P> void Engine::parallelFilter(const V& src, std::vector<uint32_t>& out, P pred)
 {
     const size_t n = src.size();
     std::vector<size_t> cnt((size_t)nthreads + 2, 0);

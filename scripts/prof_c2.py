@@ -5,8 +5,9 @@ import riss_solver_b200 as rs
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
 opts = sys.argv[2:] or ["-enabled_cp3", "-subsimp", "-no-cp3_limited"]
 t = time.time(); lits, sizes = rs.gen.random_ksat(n, int(4.26 * n), 3, seed=12345); stream = rs.gen.csr_to_stream(lits, sizes); print(f"gen {time.time()-t:.2f}s clauses {sizes.size}")
-for rep in range(2):
+for rep in range(3):
     cp = rs.Coprocessor(opts)
+    print(f"=== rep {rep}", file=sys.stderr, flush=True)
     t = time.time(); cp.add_stream(stream); t_add = time.time() - t
     t = time.time(); cp.preprocess(); t_pp = time.time() - t
     names = ["sub_subsSteps", "sub_strengthSteps", "sub_subsumedClauses", "sub_removedLiterals", "bve_eliminatedVars", "bve_steps", "scan_batches", "scan_ondemand",
