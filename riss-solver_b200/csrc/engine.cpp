@@ -293,17 +293,23 @@ void Engine::addStream(const int32_t* s, size_t n)
             for (size_t f : first) { m = std::min(m, f); }
             if (m < bulk_min) { m = 0; }
         }
+        DbgLap lap("ingest", tune.debug_par);
+        lap("first unit");
         if (m) {
             ensureGpu();
+            lap("device handle");
             uint32_t nv = 0, nc = 0; size_t nl = 0; int st = 1;
             int64_t t0 = now_ns();
             if (cp3g_ingest(gpu, s, m, &nv, &nc, &nl, &st) != CP3G_OK) { die("bulk ingest failed"); }
+            lap("cp3g_ingest");
             if (st == 0) {
                 if ((int)nv > nvars) { assigns.resize((size_t)nv, (uint8_t)L_UNDEF); frozen.resize((size_t)nv, 0); nvars = (int)nv; }
                 pool.resize(nl); C.resize(nc);
                 if (cp3g_download_arena(gpu, pool.data(), C.data()) != CP3G_OK) { die("arena download failed"); }
+                lap("arena download");
                 clauses.resize(nc);
                 parallelFor(nc, [&](size_t b, size_t e, int) { for (size_t i = b; i < e; ++i) { clauses[i] = (uint32_t)i; C[i].stamp = scan_id; } });
+                lap("clause list");
                 n_live = nc; ca_size += 2.0 * (double)nc + (double)nl;
                 if (((size_t)nc >> 6) >= delbits.size()) { delbits.resize(((size_t)nc >> 6) + 1024, 0); }
                 dev_arena_ncl = nc; dev_arena_valid = true; ++n_bulk_ingests;
@@ -386,7 +392,7 @@ void Engine::uploadAll()
     host_ns_gpuwait += now_ns() - t0;
     dev_ncl = ncl; dev_uploaded = true; dev_static_ok = false;
     pend_del.clear(); pend_shrunk.clear();
-    shrunk_mark.assign(ncl, 0);
+    pfill(shrunk_mark, (size_t)ncl, (uint8_t)0);
 }
 
 // push the edits committed since the last scan (new resolvents, shrunk clauses, deletions)
@@ -1090,16 +1096,17 @@ void Engine::initData()
 {
     PhaseTimer pt(ph_init);
     const int n2 = 2 * nvars;
-    pfill(occ, (size_t)n2, OccList()); pfill(hot, (size_t)n2, LitHot()); stale.assign((size_t)n2, 0u);
+    // (per-literal / per-variable tables: unzeroed storage, filled on all cores)
+    pfill(occ, (size_t)n2, OccList()); pfill(hot, (size_t)n2, LitHot()); pfill(stale, (size_t)n2, 0u);
     stalebits.assign(((size_t)n2 >> 6) + 1, 0ull);
-    modTimer.assign((size_t)std::max(nvars, 1), 0); ma.assign((size_t)std::max(n2, 1), 0);
-    var_touch.assign((size_t)std::max(nvars, 1), 0); bve_inpend.assign((size_t)std::max(nvars, 1), 0); bve_pending.clear();
+    pfill(modTimer, (size_t)std::max(nvars, 1), 0u); pfill(ma, (size_t)std::max(n2, 1), 0u);
+    pfill(var_touch, (size_t)std::max(nvars, 1), 0u); pfill(bve_inpend, (size_t)std::max(nvars, 1), (uint8_t)0); bve_pending.clear();
     modStep = 0; numberOfCls = 0; qhead = 0;
     subq.clear(); strq.clear();
     int64_t ti0 = now_ns();
     uploadAll();
     ph_upload += now_ns() - ti0; ti0 = now_ns();
-    std::vector<uint32_t> off((size_t)n2 + 1, 0);
+    RawVec<uint32_t> off; off.resize((size_t)n2 + 1);
     if (cp3g_download_occ(gpu, off.data(), nullptr) != CP3G_OK) { die("download_occ failed"); }
     occ_pool.resize((size_t)off[n2] + 16);                 // filled by ensureHostLists() / the device-side commit of the first pass
     lists_on_device = true;

@@ -165,7 +165,7 @@ private:
     // ---------------- CoprocessorData mirror
     bool data_ready = false; int data_nvars = 0;      // CoprocessorData::numberOfVars: 0 until the first data.init()
     RawVec<OccList> occ; RawVec<LitHot> hot; RawVec<uint32_t> occ_pool;
-    HVec<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
+    RawVec<uint32_t> stale; std::vector<uint64_t> stalebits;   // deleted clauses still listed in occ[l] (+ bitmap of >0)
     inline ListRef L(int x) { return ListRef{occ[x].off, occ[x].cap, hot[x].n}; }
     inline bool hasStale(int x) const { return (stalebits[(uint32_t)x >> 6] >> (x & 63)) & 1; }
     inline void staleInc(int x) { if (stale[x]++ == 0) { stalebits[(uint32_t)x >> 6] |= 1ull << (x & 63); } }
@@ -173,8 +173,8 @@ private:
     inline void staleClear(int x) { stale[x] = 0; stalebits[(uint32_t)x >> 6] &= ~(1ull << (x & 63)); }
     int numberOfCls = 0;
     RawVec<uint32_t> subq, strq; std::vector<int32_t> undo;      // (no zero fill when initData sizes the queues)
-    HVec<uint32_t> modTimer; uint32_t modStep = 0;
-    std::vector<uint32_t> ma; uint32_t ma_step = 0;
+    RawVec<uint32_t> modTimer; uint32_t modStep = 0;
+    RawVec<uint32_t> ma; uint32_t ma_step = 0;
 
     // ---------------- technique state
     Tech t_sub, t_up, t_bve, t_bce;
@@ -199,7 +199,7 @@ private:
     struct BvePr { uint32_t cp, cn; int size; uint64_t off; };
     std::vector<BvePr> bve_prs; std::vector<int32_t> bve_rl; std::vector<uint32_t> bve_vv, bve_pr, bve_nr; std::vector<uint64_t> bve_off; std::vector<int> bve_col;
     std::vector<uint32_t> pend_del, pend_shrunk; uint32_t dev_ncl = 0;    // edits not yet on the device
-    HVec<uint8_t> shrunk_mark;
+    RawVec<uint8_t> shrunk_mark;
     uint32_t scan_id = 0;                            // number of scans issued so far
     // literals removed per clause during the current pass: per-clause chains in one flat node array
     struct LogNode { uint32_t stamp; int32_t lit; int32_t next; uint32_t pending; };
@@ -268,7 +268,7 @@ private:
     std::vector<uint32_t> dirty_str;                 // pending strengtheners edited after their scan
     std::vector<cp3g_hit> hitbuf;
     // BVE pair cache
-    HVec<uint32_t> var_touch; HVec<uint8_t> bve_inpend; std::vector<int> bve_pending;
+    RawVec<uint32_t> var_touch; RawVec<uint8_t> bve_inpend; std::vector<int> bve_pending;
     inline void bveTouch(int v) { ++var_touch[v]; if (!bve_inpend[v] && inHeap(v)) { bve_inpend[v] = 1; bve_pending.push_back(v); } }
     // K5/K6 results per variable: views into per-batch blocks (one allocation per batch, not per variable)
     template <class T> struct Span { const T* p = nullptr; size_t n = 0; size_t size() const { return n; } const T& operator[](size_t i) const { return p[i]; } };

@@ -1052,15 +1052,18 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals, const DevS
     } else {
         parallelFor(nq, [&](size_t b, size_t e, int t) { int64_t a = 0, c2 = 0; for (size_t p = b; p < e; ++p) { if (contrib[p] >= 0) { a += contrib[p]; ++c2; } } part[(size_t)t] = a; ninert[(size_t)t] = c2; });
     }
-    // the first walk of a list pays one step per deleted entry it removes
-    parallelFor(nlit, [&](size_t b, size_t e, int t) {
-        int64_t a = 0;
-        for (size_t x = b; x < e; ++x) { if (walked_stale[x]) { const uint32_t* p = occ_pool.data() + occ[x].off; const uint32_t n = hot[x].n; for (uint32_t j = 0; j < n; ++j) { a += isDel(p[j]) ? 1 : 0; } } }
-        pstale[(size_t)t] = a;
-    });
+    // the first walk of a list pays one step per deleted entry it removes: counted ahead of the commit when the step limit
+    // can stop the pass, otherwise while the lists are cleaned below
+    if (!unlimited) {
+        parallelFor(nlit, [&](size_t b, size_t e, int t) {
+            int64_t a = 0;
+            for (size_t x = b; x < e; ++x) { if (walked_stale[x]) { const uint32_t* p = occ_pool.data() + occ[x].off; const uint32_t n = hot[x].n; for (uint32_t j = 0; j < n; ++j) { a += isDel(p[j]) ? 1 : 0; } } }
+            pstale[(size_t)t] = a;
+        });
+    }
     int64_t inert_steps = 0, inert_n = 0, stale_steps = 0;
     for (int t = 0; t <= T; ++t) { inert_steps += part[(size_t)t]; inert_n += ninert[(size_t)t]; stale_steps += pstale[(size_t)t]; }
-    const int64_t total = steps + inert_steps + stale_steps;
+    int64_t total = steps + inert_steps + stale_steps;
     if (!unlimited && !(str_steps + total + 1 < str_lim)) { return false; }
     // clause contents and flags; the real entries are done (the inert ones lost their flag up front), re-queued clauses are
     // processed too - or left over by the last entry of the queue
@@ -1123,14 +1126,18 @@ bool Engine::strengthenComponents(const std::vector<uint32_t>& reals, const DevS
     removedLiterals += (int)evs.size();
     if (!evs.empty()) { successful(t_sub); }
     // lists that a walk cleaned
-    parallelForG((nlit + 63) / 64, 512, [&](size_t wb, size_t we, int) {
+    std::vector<int64_t> premoved((size_t)T + 1, 0);
+    parallelForG((nlit + 63) / 64, 512, [&](size_t wb, size_t we, int t) {
+        int64_t removed = 0;
         for (size_t x = wb * 64; x < std::min(nlit, we * 64); ++x) {
             if (!walked_stale[x]) { continue; }
             uint32_t* p = occ_pool.data() + occ[x].off; uint32_t n = hot[x].n;
-            for (uint32_t j = 0; j < n;) { if (isDel(p[j])) { p[j] = p[n - 1]; --n; } else { ++j; } }
+            for (uint32_t j = 0; j < n;) { if (isDel(p[j])) { p[j] = p[n - 1]; --n; ++removed; } else { ++j; } }
             hot[x].n = n; staleClear((int)x);
         }
+        premoved[(size_t)t] += removed;
     });
+    if (unlimited) { for (int64_t r : premoved) { total += r; } }
     str_steps += total; n_fast += nfast; n_slow += nslow; n_lazy = inert_n;
     ++n_compar;
     lap("commit");
