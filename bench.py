@@ -277,6 +277,14 @@ def main():
     # one engine per rank: split the host cores between the ranks of this node (the ordered commit uses a thread pool)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     os.environ.setdefault("CP3_THREADS", str(max(1, min(24, (os.cpu_count() or 1) // max(1, local_world)))))
+    # ... and give every rank its own contiguous set of them, like numactl would: the ranks' thread pools then do not migrate over
+    # each other's cores and caches (CP3_BENCH_PIN=0 leaves the affinity alone)
+    affinity = "inherited"
+    if local_world > 1 and os.environ.get("CP3_BENCH_PIN", "1") != "0" and hasattr(os, "sched_setaffinity"):
+        cpus = sorted(os.sched_getaffinity(0)); per = len(cpus) // local_world
+        if per >= 1:
+            os.sched_setaffinity(0, cpus[local * per:(local + 1) * per])
+            affinity = f"rank-contiguous, {per} cpus"
     # a process that calls CPpreprocess repeatedly keeps the engine's work arrays in its heap (opt-in, capi.cpp)
     os.environ.setdefault("CP3_KEEP_HEAP", "1")
     import torch
@@ -378,7 +386,7 @@ def main():
                        "clauses": ncl, "value_leg": "CPpreprocess: the whole fixpoint, clause arena resident in HBM at the start (wall clock, barrier + device sync on both sides)",
                        "e2e_leg": "CPaddLits (DIMACS stream in pinned host memory) + CPpreprocess + read-back of the simplified CNF",
                        "l2": "working set (occurrence entries + headers + literals) larger than the 126 MB L2; a 256 MB buffer is also written between steps",
-                       "host_threads_per_rank": int(os.environ["CP3_THREADS"]),
+                       "host_threads_per_rank": int(os.environ["CP3_THREADS"]), "cpu_affinity": affinity,
                        "parallelism": ("1 gpu" if world == 1 else (f"{world} ranks, one independent formula per rank (no data-path collective)" if args.mode == "weak"
                                        else f"{world} ranks, one formula: scan requests partitioned, hits all-gathered over NCCL"))},
             "roofline": roofline_of([r[3] for r in res], peak, peak_src, traffic.get("k_full_bytes_per_launch")),

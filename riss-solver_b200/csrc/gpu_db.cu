@@ -37,6 +37,8 @@
 #include <algorithm>
 #include <type_traits>
 #include <chrono>
+#include <mutex>
+#include <utility>
 
 #include "../../include/cp3b200.h"
 #include "gpu_db.h"
@@ -74,6 +76,8 @@ static constexpr uint32_t CLS_NOSUB = 1u, CLS_NOSTR = 2u, CLS_NONE = 3u;
 #endif
 static constexpr uint32_t TILE = CP3_TILE, GROUP_MAX = CP3_GROUPMAX, TCAP = TILE + GROUP_MAX, OFFCAP = CP3_OFFCAP, TILE_ALIGNED = 0x80000000u;
 static constexpr uint32_t PIN_HITS = 8192;
+static std::mutex g_pin_mu;
+static std::vector<std::pair<uint32_t*, cp3g_hit*>> g_pin_free;      // pinned pairs of destroyed handles, reused by the next one
 
 
 __host__ __device__ __forceinline__ unsigned long long lit_bit(int32_t x)
@@ -1231,7 +1235,13 @@ cp3g* cp3g_create(int device)
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep); }
     }
     if (g->counters.reserve(16, false, g->stream)) { delete g; return nullptr; }
-    if (cudaHostAlloc((void**)&g->pin_cnt, 64, cudaHostAllocDefault) != cudaSuccess || cudaHostAlloc((void**)&g->pin_hits, PIN_HITS * sizeof(cp3g_hit), cudaHostAllocDefault) != cudaSuccess) { delete g; return nullptr; }
+    // pinned counters + hit window: page-locking costs milliseconds, so handles hand their pair on (a client creates one
+    // handle per CPinit)
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (!g_pin_free.empty()) { g->pin_cnt = g_pin_free.back().first; g->pin_hits = g_pin_free.back().second; g_pin_free.pop_back(); }
+    }
+    if (!g->pin_cnt && (cudaHostAlloc((void**)&g->pin_cnt, 64, cudaHostAllocPortable) != cudaSuccess || cudaHostAlloc((void**)&g->pin_hits, PIN_HITS * sizeof(cp3g_hit), cudaHostAllocPortable) != cudaSuccess)) { delete g; return nullptr; }
     return g;
 }
 
@@ -1250,6 +1260,10 @@ void cp3g_destroy(cp3g* g)
     g->sp_dlfill.release(g->stream); g->sp_n.release(g->stream); g->sp_stale.release(g->stream); g->sp_dead.release(g->stream); g->sp_refs.release(g->stream);
     cudaStreamSynchronize(g->stream);
     cp3g_nccl_free(g->nccl);
+    if (g->pin_cnt && g->pin_hits) {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (g_pin_free.size() < 16) { g_pin_free.push_back({g->pin_cnt, g->pin_hits}); g->pin_cnt = nullptr; g->pin_hits = nullptr; }
+    }
     if (g->pin_cnt) { cudaFreeHost(g->pin_cnt); } if (g->pin_hits) { cudaFreeHost(g->pin_hits); }
     cudaEventDestroy(g->ev0); cudaEventDestroy(g->ev1);
     cudaStreamDestroy(g->stream);
