@@ -172,11 +172,12 @@ def _hits_key(h):
     return np.stack([h["req"][o], h["clause"][o], h["lit"][o].astype(np.int64)], 1)
 
 
-@pytest.mark.parametrize("shape", ["uniform", "zipf", "community", "sparse_vars", "very_sparse_vars", "one_long_pair"])
+@pytest.mark.parametrize("shape", ["uniform", "zipf", "community", "sparse_vars", "very_sparse_vars", "one_long_pair", "dense_hits"])
 def test_k3_k4_full_queue_kernel_equals_request_kernel(gen, shape):
     """k_full (tile-staged, class-prefixed lists) against k_scan (one warp per request) on the same snapshot: same
     hit set and the same number of checks.  The shapes hit every tile flavour: pure tiles, lists longer than a tile,
-    more lists per tile than the staged offset window holds, and list distances that saturate the dx byte."""
+    more lists per tile than the staged offset window holds, list distances that saturate the dx byte, and long lists
+    of many-fold duplicates whose tiles produce far more survivors than the per-warp queue holds (the in-tile drains)."""
     if shape == "uniform":
         lits, sizes = gen.random_ksat(6000, 25000, 3, seed=31, dup=0.03, sup=0.05, flip=0.05)
     elif shape == "zipf":
@@ -187,6 +188,12 @@ def test_k3_k4_full_queue_kernel_equals_request_kernel(gen, shape):
         lits, sizes = gen.random_ksat(3000, 12000, 3, seed=34, dup=0.03, sup=0.05, flip=0.05)
         gap = 7 if shape == "sparse_vars" else 401          # runs of empty occurrence lists between used variables
         lits = (np.sign(lits) * ((np.abs(lits) - 1) * gap + 1)).astype(np.int32)
+    elif shape == "dense_hits":
+        rng = np.random.default_rng(36)                      # 20000 clauses over 12 variables: ~11 copies of everything
+        m = 20000
+        vars_ = np.stack([rng.permutation(12)[:3] + 1 for _ in range(m)])
+        rows = vars_ * rng.choice([-1, 1], size=(m, 3))
+        lits = rows.reshape(-1).astype(np.int32); sizes = np.full(m, 3, np.int64)
     else:
         rng = np.random.default_rng(35)                      # every clause holds variable 1: two lists of ~6000 entries
         m = 12000
