@@ -598,18 +598,22 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, uint32_t parity
     } while (!ok);
 }
 
-// Full-queue pass (every live clause is a subsumer / strengthener), candidate-major: one lane per occurrence entry
-// *as the candidate* D.  The clauses whose full-queue scan walks list x are exactly the entries of x with the
-// matching class bit clear (k_occ_fill), and they sit at the front of the list - so the subsumer set of a candidate
-// is a prefix of its own list and, for a short list, lies in the same tile.
+// Full-queue pass (every live clause is a subsumer / strengthener).  The clauses whose full-queue scan walks list x are
+// exactly the entries of x with the matching class bit clear (k_occ_fill), and they sit at the front of the list - so
+// the subsumer set of a candidate is a prefix of its own list and, for a short list, lies in the same tile.
 //
-// Warps are persistent and fully independent (no block barrier in the loop).  Each warp owns a double-buffered
-// staging area: the tile (<= 159 entries x 16 B, whole list pairs, k_tiles) and the CSR offsets of its lists are
-// moved global -> shared by the bulk-copy engine (cp.async.bulk + mbarrier) one tile ahead of the processing.
-//   phase 1  every lane takes entries p = lane, lane+32, ..: finds its list (binary search in the staged offsets),
-//            tests the tagged prefix (from shared memory) with size + signature filters; survivors are queued
-//   phase 2  the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
-//            which would otherwise stall 31 lanes behind one)
+// Warps are persistent and fully independent (no block barrier in the loop; tiles are dealt out by static striding -
+// a global tile counter was measured and lost).  Each warp owns a double-buffered staging area:
+// the tile (<= 159 entries x 16 B, whole list pairs, k_tiles) and the CSR offsets of its lists are moved global ->
+// shared by the bulk-copy engine (cp.async.bulk + mbarrier) one tile ahead of the processing.
+//   filter   pure tiles: one lane per entry emits (subsumer, <= 8 candidates) units into the warp's work list (slots by
+//            one shared-memory atomic per tagged lane), then one lane per unit tests its chunk in straight-line code;
+//            tiles inside one long list / cut by one: segment and entry forms.  Size + signature filters only;
+//            survivors are queued
+//   verify   the lanes verify one queued pair each (merge of the two literal arrays: 4 dependent random loads,
+//            which would otherwise stall 31 lanes behind one); the deleted flag is read from the headers loaded
+//            here.  The queue is drained at the end of a tile and, in the segment / entry forms, whenever it holds
+//            32 pairs (skewed inputs produce thousands of survivors per tile)
 //   hits are buffered per warp and reserved in the global list with one atomic per ~16 hits
 static constexpr int WQ_CAP = CP3_WQ, WH_CAP = CP3_WH, FQ_WARPS = CP3_FQWARPS;
 static constexpr uint32_t WORK_CAP = CP3_WORKCAP, DCHUNK = CP3_DCHUNK;     // flat work list per tile: (subsumer, <= 8 consecutive candidates)
