@@ -1817,7 +1817,7 @@ int cp3g_ingest(cp3g* g, const int32_t* stream, size_t n, uint32_t* nvars, uint3
     const uint32_t N = (uint32_t)n;
     DevBuf<int32_t>& S = g->bl0;                     // the stream; bu0 = flags / sizes, bu1 = scans, bu2 = clause ends
     RESERVE(S, n + 1, false); RESERVE(g->bu0, n + 2, false); RESERVE(g->bu1, n + 2, false);
-    CK(cudaMemcpyAsync(S.p, stream, n * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
+    { int r = h2d_staged(g, S.p, stream, n * sizeof(int32_t)); if (r != CP3G_OK) { return r; } }
     g->h2d += (int64_t)n * 4;
     CK(cudaMemsetAsync(g->counters.p, 0, 16 * sizeof(uint32_t), g->stream));
     KTimer t(g);

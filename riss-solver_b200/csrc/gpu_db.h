@@ -101,8 +101,9 @@ struct KTimer {
 
 
 // helpers defined in gpu_db.cu and used by commit.cu
-int d2h_staged(cp3g* g, void* dst, const void* src, size_t bytes);   // staging.cu: large copy into pageable host memory, returns when it is there
+int d2h_staged(cp3g* g, void* dst, const void* src, size_t bytes);      // staging.cu: large copy into pageable host memory, returns when it is there
+int h2d_staged(cp3g* g, void* ddst, const void* src, size_t bytes);     // staging.cu: large copy out of pageable host memory (plain async copy for pinned sources)
 extern "C" int scan_u32(cp3g* g, const uint32_t* in, uint32_t* out, size_t n);     // exclusive scan on the handle stream, total in counters[2]
-int dev_set_deleted(cp3g* g, const uint32_t* dev_ids, uint32_t n);       // mark clauses deleted (header flag + bitmap), ids on the device
+int dev_set_deleted(cp3g* g, const uint32_t* dev_ids, uint32_t n);       // mark clauses deleted (header flag), ids on the device
 int dev_host_order_lists(cp3g* g);                                        // refs_tmp := occurrence lists in ascending clause order
 #endif
