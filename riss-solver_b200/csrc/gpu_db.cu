@@ -1313,8 +1313,8 @@ extern "C" int cp3g_upload_packed(cp3g* g, uint32_t nvars, uint32_t ncl, const i
     RESERVE(g->lits, nlits + nlits / 4 + 1024, false);
     RESERVE(g->hdr, (size_t)ncl + ncl / 4 + 1024, false);
     RESERVE(g->occ_ent, (size_t)ncl + 1, false);                 // staging for the raw records (rebuilt by cp3g_build anyway)
-    CK(cudaMemcpyAsync(g->lits.p, lits, nlits * sizeof(int32_t), cudaMemcpyHostToDevice, g->stream));
-    CK(cudaMemcpyAsync(g->occ_ent.p, records16, (size_t)ncl * 16, cudaMemcpyHostToDevice, g->stream));
+    { int r = h2d_staged(g, g->lits.p, lits, nlits * sizeof(int32_t)); if (r != CP3G_OK) { return r; } }
+    { int r = h2d_staged(g, g->occ_ent.p, records16, (size_t)ncl * 16); if (r != CP3G_OK) { return r; } }
     if (ncl) { k_make_hdr<<<grid_for(ncl, 256), 256, 0, g->stream>>>(reinterpret_cast<const uint4*>(g->occ_ent.p), g->hdr.p, ncl); g->launches++; }
     g->h2d += (int64_t)(nlits * sizeof(int32_t) + (size_t)ncl * 16);
     return finish_upload(g, ncl, nlits);
